@@ -1,0 +1,144 @@
+"""Named workloads (BASELINE.json `configs`, restated as concrete inputs in SURVEY.md §8d).
+
+Each builder returns a :class:`Workload` holding the keyword arguments for ``make_input_dict`` (identical for
+the reference's and this package's ``make_input_dict``), the line-of-sight grid of the default
+``EsymmtricCauchyPlasma`` profile, and a reference theta given *by tag* so that each side assembles the vector
+through its own ``plasma.slices``.
+
+Measured spectra for the two demo configs come from the reference's demo directory
+(`/root/reference/demo/zero_fit_config.json`, `/root/reference/demo/AUG_ROV012_32244.txt`, parsed as in
+`demo/baysar_asdex_demo.py:317-324`) and are stored, together with the self-consistent synthetic spectra, in
+``data/workload_inputs.npz`` (written by ``oracle/make_golden.py``).
+"""
+import pathlib
+
+import numpy as np
+
+_DATA = pathlib.Path(__file__).resolve().parent / "data" / "workload_inputs.npz"
+
+X_TRIPLET = [[[4024.78, 4025.33, 4026.33]], [[0.541, 0.373, 0.086]]]
+
+
+class Workload:
+    def __init__(self, name, input_kwargs, los, reference_theta, description):
+        self.name = name
+        self.input_kwargs = input_kwargs
+        self.los = los  # None -> profile default linspace(-10, 25, 50)
+        self.reference_theta = reference_theta  # {tag: list of values}
+        self.description = description
+
+    def theta_from_tags(self, slices, start):
+        """Overwrite ``start`` (a vector inside the bounds) with the tagged reference values."""
+        theta = np.array(start, dtype=float)
+        for tag, vals in self.reference_theta.items():
+            if tag in slices:
+                theta[slices[tag]] = vals
+        return theta
+
+
+def _stored(key, default=None):
+    if _DATA.exists():
+        with np.load(_DATA) as z:
+            if key in z.files:
+                return z[key]
+    if default is None:
+        raise FileNotFoundError(f"{key} not in {_DATA}; run oracle/make_golden.py in the build container")
+    return default
+
+
+def gaussian_if(npix=31, sigma_px=1.2):
+    x = np.arange(float(npix))
+    return np.exp(-0.5 * ((x - (npix - 1) / 2.0) / sigma_px) ** 2)
+
+
+def balmer_series(data="selfconsistent"):
+    """configs[1]: `demo/balmer_series.py` — H Balmer n=5..9->2, 1024 px, refine 0.1, L=50, n=10."""
+    wave = _stored("balmer_wave")
+    if data == "zero_fit":
+        ems = _stored("balmer_zero_fit_ems")
+    else:
+        ems = _stored("balmer_selfconsistent_ems", default=_stored("balmer_zero_fit_ems"))
+    kw = dict(wavelength_axis=[wave], experimental_emission=[ems], instrument_function=[_stored("balmer_if")],
+              emission_constant=[1e11], noise_region=[[4150.0, 4250.0]], species=["H"], ions=[["0"]],
+              mystery_lines=None, refine=0.1, no_sample_neutrals=False, ion_resolved_temperatures=False,
+              ion_resolved_tau=False)
+    ref = {"electron_density": [np.log10(8e13), 0.0, 3.0], "electron_temperature": [np.log10(5.0), 3.0, 1.0],
+           "H_0_dens": [np.log10(8e13)], "H_0_tau": [-8.0], "H_0_velocity": [0.0], "background_0": [12.05]}
+    return Workload("balmer_series", kw, None, ref, "H Balmer series with Stark broadening (demo/balmer_series.py)")
+
+
+def multi_species(n_chords=1, data="selfconsistent", flags=None):
+    """configs[2]/[3]: D Balmer + N II/N III + C III + X triplet, 1024 px, refine 0.05, L=100."""
+    npix = 1024
+    wave = np.linspace(3960.0, 4110.0, npix)
+    rng = np.random.default_rng(20261019 + 3)
+    waves, emss, ifs = [], [], []
+    for c in range(n_chords):
+        key = f"multi_selfconsistent_ems_{c}"
+        if data == "selfconsistent" and _DATA.exists() and key in np.load(_DATA).files:
+            ems = _stored(key)
+        else:
+            ems = 1e12 + rng.normal(0.0, 2e10, npix)
+        waves.append(wave.copy())
+        emss.append(ems)
+        ifs.append(gaussian_if(31, 1.2))
+    kw = dict(wavelength_axis=waves, experimental_emission=emss, instrument_function=ifs,
+              emission_constant=[1e11] * n_chords, noise_region=[[4008.0, 4020.0]] * n_chords,
+              species=["D", "N", "C"], ions=[["0"], ["1", "2"], ["2"]], mystery_lines=X_TRIPLET,
+              refine=[0.05] * n_chords, ion_resolved_temperatures=False, ion_resolved_tau=True)
+    if flags:
+        kw.update(flags)
+    ref = {"electron_density": [14.6, 0.5, 3.0], "electron_temperature": [0.9, 3.0, 0.8],
+           "N_1_dens": [12.6], "C_2_dens": [12.2], "D_0_dens": [12.9], "D_0_tau": [-4.0], "N_1_tau": [-1.0],
+           "N_2_tau": [-3.0], "C_2_tau": [-2.0], "D_0_velocity": [2.0], "N_1_velocity": [-3.0],
+           "C_2_velocity": [1.0], "X_4024.78_4025.33_4026.33": [12.3]}
+    for c in range(n_chords):
+        ref[f"background_{c}"] = [12.0 + 0.01 * c]
+    name = "multi_species" if n_chords == 1 else f"multi_species_{n_chords}chords"
+    return Workload(name, kw, np.linspace(-10.0, 25.0, 100), ref,
+                    f"D Balmer + N II/N III + C III + X triplet, {n_chords} chord(s)")
+
+
+def aug_demo():
+    """configs[0]: AUG divertor chord ROV012 #32244 (`demo/baysar_asdex_demo.py`), 512 px, refine 0.05."""
+    wave = _stored("aug_wave")
+    ems = _stored("aug_ems")
+    x = np.arange(31.0)
+    fwhm_px = 0.4 / np.mean(np.diff(wave))
+    sigma = fwhm_px / np.sqrt(8.0 * np.log(2.0))
+    inst = np.exp(-0.5 * ((x - 15.0) / sigma) ** 2) / (np.sqrt(2.0 * np.pi) * sigma)
+    kw = dict(wavelength_axis=[wave], experimental_emission=[ems], instrument_function=[inst],
+              emission_constant=[1e11], noise_region=[[3975.0, 3990.0]], species=["D", "N"],
+              ions=[["0"], ["1", "2", "3"]], mystery_lines=X_TRIPLET, refine=[0.05],
+              ion_resolved_temperatures=False, ion_resolved_tau=True)
+    ref = {"background_0": [12.0], "electron_density": [14.8, 0.0, 3.0], "electron_temperature": [1.0, 3.0, 1.0],
+           "N_1_dens": [12.7], "D_0_tau": [-4.0], "N_1_tau": [-1.0], "N_2_tau": [-4.0], "N_3_tau": [-4.0],
+           "D_0_velocity": [0.0], "N_1_velocity": [0.0], "X_4024.78_4025.33_4026.33": [12.3]}
+    return Workload("aug_demo", kw, None, ref, "AUG_ROV012_32244 divertor chord, D + N II/III/IV + X triplet")
+
+
+def synthetic_sweep(n_los=100, n_lines=20, n_pix=1024, balmer=True):
+    """configs[4]: shape sweep — single-component impurity lines at evenly spaced cwls (custom line_data)."""
+    wave = 3960.0 + 0.15 * np.arange(n_pix)
+    rng = np.random.default_rng(20261019 + 5)
+    ems = 1e12 + rng.normal(0.0, 2e10, n_pix)
+    line_data = {"N": {"atomic_mass": 14, "atomic_charge": 7, "ionisation_balance_year": 96, "ions": ["1"], "1": {}}}
+    lo, hi = wave.min() + 2.0, wave.max() - 2.0
+    for k, cwl in enumerate(np.linspace(lo, hi, n_lines)):
+        cwl = float(np.round(cwl, 3))
+        line_data["N"]["1"][cwl] = {"wavelenght": cwl, "jj_frac": [1], "pec": "sweep_n1.dat", "exc_block": 1 + (k % 28),
+                                    "rec_block": 31 + (k % 28)}
+    species, ions = ["N"], [["1"]]
+    if balmer:
+        from .line_data import fresh_line_data
+
+        line_data["D"] = fresh_line_data()["D"]
+        species, ions = ["D", "N"], [["0"], ["1"]]
+    kw = dict(wavelength_axis=[wave], experimental_emission=[ems], instrument_function=[gaussian_if(31, 1.2)],
+              emission_constant=[1e11], noise_region=[[wave[5], wave[60]]], species=species, ions=ions,
+              line_data=line_data, mystery_lines=None, refine=[0.05], ion_resolved_temperatures=False,
+              ion_resolved_tau=True)
+    ref = {"electron_density": [14.5, 0.0, 3.0], "electron_temperature": [1.0, 3.0, 1.0], "N_1_dens": [12.5],
+           "N_1_tau": [-2.0], "D_0_tau": [-4.0], "background_0": [12.0]}
+    return Workload(f"sweep_L{n_los}_G{n_lines}_P{n_pix}", kw, np.linspace(-10.0, 25.0, n_los), ref,
+                    "synthetic shape sweep")
