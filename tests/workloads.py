@@ -1,0 +1,15 @@
+"""Fixture name -> workload builder, shared by the oracle and the GPU parity tests."""
+from baysar_b200 import configs
+
+WORKLOADS = {
+    "balmer_series": lambda: configs.balmer_series(),
+    "balmer_zero_fit": lambda: configs.balmer_series("zero_fit"),
+    "multi_species": lambda: configs.multi_species(1),
+    "multi_species_3chords": lambda: configs.multi_species(3),
+    "aug_demo": lambda: configs.aug_demo(),
+    "multi_hot": lambda: configs.multi_species(1, flags=dict(cold_neutrals=False, cold_ions=False)),
+    "multi_sampled_neutrals": lambda: configs.multi_species(1, flags=dict(no_sample_neutrals=False)),
+    "multi_calibrated": lambda: configs.multi_species(
+        1, flags=dict(calibrate_wavelength=True, calibrate_intensity=True, calibrate_instrument_function=True)),
+    "multi_no_doppler": lambda: configs.multi_species(1, flags=dict(doppler_shifts=False)),
+}
