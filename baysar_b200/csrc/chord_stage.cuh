@@ -1,0 +1,443 @@
+// K2 — spectral stage: one CTA per (theta, chord).  float32 element-wise work on the fine wavelength grid held in
+// shared memory, float64 for wavelength differences, tap tables, reductions and the pixel / likelihood epilogue.
+//
+// Replaces, per (theta, chord) (reference file:line):
+//   BalmerHydrogenLine.__call__ (shape part)   baysar/linemodels.py:838-865
+//   HydrogenLineShape.__call__, stehle_param   baysar/linemodels.py:688-723, :554-566
+//   DopplerLine / Gaussian.make_peak           baysar/linemodels.py:283-300, baysar/lineshapes.py:126-131,206-217
+//   ADAS406Lines.__call__ (shape part), XLine  baysar/linemodels.py:401-403,428 ; :213-233
+//   SpectrometerChord.forward_model            baysar/spectrometers.py:197-335
+//   SpectrometerChord.likelihood               baysar/spectrometers.py:154-195
+//
+// Algorithmic departures from the reference's arithmetic (validated on CPU in tests/test_kernel_model.py):
+//   * direct "same" convolutions, out[j] = sum_k w[k] s[j + (K-1)/2 - k], instead of FFT convolutions;
+//   * taps / Gaussian samples with exp(-z^2/2) < 1e-17 (|tap| < 1e-17 max) are dropped;
+//   * the two trapz normalisations of the Stark (x) Doppler profile collapse into A = sum_i u[i] G[i], with G the
+//     trapz weights pulled back through the convolution (constant inside, tap prefix sums at the two ends);
+//   * uniform trapz weights on the arange grid; the four end outputs of the instrument convolution in float64.
+#pragma once
+#include "device_common.cuh"
+
+struct ChordArgs {
+  const double* theta;      // [N][n_params]
+  int64_t n;
+  int chord_begin;          // blockIdx.y + chord_begin = chord
+  const double* lines;      // [N][n_ulines][BAYSAR_LINE_STRIDE]  (K1 output)
+  double* components;       // [N][n_chords + n_priors]; this kernel fills column `chord`
+  double* spectra;          // optional [N][P] (single chord launches only)
+  float* fine_pre;          // optional [N][F]
+  float* fine_post;         // optional [N][F]
+  uint32_t* status;         // [N] OR-ed
+};
+
+struct ChordSmem {
+  // sizes in bytes for the dynamic shared-memory carve-up; all multiples of 16
+  size_t buf_floats;   // floats per padded fine-grid buffer
+  size_t taps_floats;  // floats in the q-indexed tap buffer
+  size_t tapd_doubles; // doubles for Doppler taps + prefix sums
+  size_t total;
+};
+
+static inline ChordSmem chord_smem_layout(int F, int halo, int taps_max, int kd_max) {
+  ChordSmem s;
+  int f4 = (F + 3) / 4 * 4;
+  s.buf_floats = (size_t)f4 + 2 * (size_t)halo + 8;
+  s.taps_floats = (size_t)(taps_max + 8 + 3) / 4 * 4;
+  s.tapd_doubles = 2 * (size_t)kd_max + 4;
+  s.total = 2 * s.buf_floats * sizeof(float) + s.taps_floats * sizeof(float) + s.tapd_doubles * sizeof(double) +
+            64 * sizeof(double) + 16 * sizeof(int);
+  s.total = (s.total + 15) / 16 * 16;
+  return s;
+}
+
+// fine-grid coordinate, bit-identical to numpy.arange's fill: start + j * delta (two roundings, no FMA)
+BAYSAR_DEV double grid_x(double x0, double delta, int j) { return __dadd_rn(x0, __dmul_rn((double)j, delta)); }
+
+// 4 consecutive outputs of a zero-padded "same" convolution.
+// src points at padded_buffer + halo + j0 + q_start (16-byte aligned); tq[qi] = w[o - (q_start + qi)].
+BAYSAR_DEV float4 conv4(const float* src, const float* tq, int nq) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 cur = *reinterpret_cast<const float4*>(src);
+  for (int qi = 0; qi < nq; qi += 4) {
+    const float4 nxt = *reinterpret_cast<const float4*>(src + qi + 4);
+    const float4 w = *reinterpret_cast<const float4*>(tq + qi);
+    acc.x = fmaf(w.x, cur.x, acc.x); acc.y = fmaf(w.x, cur.y, acc.y);
+    acc.z = fmaf(w.x, cur.z, acc.z); acc.w = fmaf(w.x, cur.w, acc.w);
+    acc.x = fmaf(w.y, cur.y, acc.x); acc.y = fmaf(w.y, cur.z, acc.y);
+    acc.z = fmaf(w.y, cur.w, acc.z); acc.w = fmaf(w.y, nxt.x, acc.w);
+    acc.x = fmaf(w.z, cur.z, acc.x); acc.y = fmaf(w.z, cur.w, acc.y);
+    acc.z = fmaf(w.z, nxt.x, acc.z); acc.w = fmaf(w.z, nxt.y, acc.w);
+    acc.x = fmaf(w.w, cur.w, acc.x); acc.y = fmaf(w.w, nxt.x, acc.y);
+    acc.z = fmaf(w.w, nxt.y, acc.z); acc.w = fmaf(w.w, nxt.z, acc.w);
+    cur = nxt;
+  }
+  return acc;
+}
+
+// exp(arg) for arg <= 0 computed as 2^n * ex2(f): the argument reduction is done in float64 so that the result
+// keeps float32 relative accuracy even for arg ~ -40 (a narrow Gaussian sampled far from its centre).
+BAYSAR_DEV float exp_neg_f32(double arg) {
+  double t = arg * 1.4426950408889634;
+  double nn = rint(t);
+  float f = (float)(t - nn);
+  int e = (int)nn;
+  if (e < -126) return 0.f;
+  return exp2f(f) * __int_as_float((e + 127) << 23);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) chord_stage_kernel(ModelDev m, ChordArgs a) {
+#ifdef BAYSAR_CPU_EMU
+  unsigned char* chord_smem_raw = emu_dynamic_smem();
+#else
+  extern __shared__ __align__(16) unsigned char chord_smem_raw[];
+#endif
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n = blockIdx.x;
+  const int c = a.chord_begin + blockIdx.y;
+  const int64_t* I = m.I;
+  const int n_params = (int)I[I_N_PARAMS], n_ul = (int)I[I_N_ULINES];
+  const int ncomp_cols = (int)I[I_N_CHORDS] + (int)I[I_N_PRIORS];
+  const int* ch = m.ch_i + c * CH_I_COUNT;
+  const double* chd = m.ch_d + c * CH_D_COUNT;
+  const int F = ch[CH_F], P = ch[CH_P], HALO = ch[CH_HALO], TAPS_MAX = ch[CH_TAPS_MAX];
+  const double x0 = chd[CH_X0], delta = chd[CH_DELTA], dl = chd[CH_DL];
+  const double* th = a.theta + n * n_params;
+  const double* lines_n = a.lines + n * (int64_t)n_ul * BAYSAR_LINE_STRIDE;
+
+  // ---- shared memory carve-up (must match chord_smem_layout)
+  int kd_max = 0;
+  for (int k = 0; k < ch[CH_N_LINES]; ++k) {
+    int kd = m.cl_i[(ch[CH_LINE_OFF] + k) * CL_I_COUNT + CL_KD];
+    kd_max = kd > kd_max ? kd : kd_max;
+  }
+  const int f4 = (F + 3) / 4 * 4;
+  const size_t buf_floats = (size_t)f4 + 2 * (size_t)HALO + 8;
+  const size_t taps_floats = (size_t)(TAPS_MAX + 8 + 3) / 4 * 4;
+  float* bufA = reinterpret_cast<float*>(chord_smem_raw);
+  float* bufB = bufA + buf_floats;
+  float* tapq = bufB + buf_floats;
+  double* tapd = reinterpret_cast<double*>(tapq + taps_floats);  // [kd_max] taps, then [kd_max + 1] prefix sums
+  double* tappre = tapd + kd_max;
+  double* scratch = tappre + kd_max + 4;  // 64 doubles
+  int* iscr = reinterpret_cast<int*>(scratch + 64);  // 16 ints
+  double* edge64 = scratch + 48;  // 4 doubles inside the scratch area that block_sum never touches (needs <= 48)
+
+  uint32_t st = 0;
+  for (size_t i = tid; i < 2 * buf_floats; i += NT) bufA[i] = 0.f;
+  __syncthreads();
+  float* A = bufA + HALO;  // A[j], j in [-HALO, f4 + HALO + 8)
+  float* B = bufB + HALO;
+
+  const double cal = ch[CH_CAL_IDX] >= 0 ? pow(10.0, th[ch[CH_CAL_IDX]]) : 1.0;
+  const double fwhm_to_sigma = 0.42466090014400953;  // 1 / sqrt(8 ln 2)
+  const double c_light = 299792458.0;
+
+  // ================= line objects ==============================================================================
+  for (int k = 0; k < ch[CH_N_LINES]; ++k) {
+    const int* cl = m.cl_i + (ch[CH_LINE_OFF] + k) * CL_I_COUNT;
+    const double* cld = m.cl_d + (ch[CH_LINE_OFF] + k) * CL_D_COUNT;
+    const double* rec = lines_n + cl[CL_ULINE] * BAYSAR_LINE_STRIDE;
+    const int kind = cl[CL_KIND];
+    double vel = 0.0; int has_vel = 0;
+    if (cl[CL_SPECIES] >= 0) {
+      int vi = m.sp_i[cl[CL_SPECIES] * SP_I_COUNT + SP_VEL_IDX];
+      if (vi >= 0) { vel = 1e3 * th[vi]; has_vel = 1; }
+    }
+    if (kind == 0) {
+      // ---------------- Balmer line: Stark (x) Doppler ----------------
+      const double cwl0 = cld[CL_CWL0];
+      const double cwl = has_vel ? cwl0 * (vel / c_light + 1.0) : cwl0;
+      const double ti = rec[6];
+      const double sigma = cwl * 7.715e-5 * sqrt(ti / cld[CL_MASS]) * fwhm_to_sigma;
+      if (!(sigma > 0.0)) st |= 1u << 5;
+      const int KD = cl[CL_KD], o = (KD - 1) / 2;
+      const double dshift = cwl - cwl0;
+      // tap window |z| <= Z_CUT
+      if (tid == 0) { iscr[0] = KD; iscr[1] = -1; }
+      __syncthreads();
+      for (int q = tid; q < KD; q += NT) {
+        double xk = __dadd_rn(cld[CL_DOP_START], __dmul_rn((double)q, cld[CL_DOP_DELTA]));
+        double z = ((xk + dshift) - cwl) / sigma;
+        if (fabs(z) <= BAYSAR_Z_CUT) { atomicMin(&iscr[0], q); atomicMax(&iscr[1], q); }
+      }
+      __syncthreads();
+      const int k_lo = iscr[0], k_hi = iscr[1] + 1;
+      const int T = k_hi - k_lo;
+      __syncthreads();
+      if (T <= 0) { st |= 1u << 6; continue; }  // uniform across the block
+      for (int q = tid; q < T; q += NT) {
+        double xk = __dadd_rn(cld[CL_DOP_START], __dmul_rn((double)(k_lo + q), cld[CL_DOP_DELTA]));
+        double z = ((xk + dshift) - cwl) / sigma;
+        tapd[q] = exp(-0.5 * z * z);
+      }
+      // q-indexed float taps for conv4: q = o - k in [o - k_hi + 1, o - k_lo]
+      const int q_min = o - k_hi + 1, q_max = o - k_lo;
+      const int q_start = q_min & ~3;
+      const int nq = (q_max - q_start + 1 + 3) & ~3;
+      __syncthreads();
+      for (int qi = tid; qi < nq; qi += NT) {
+        int kk = o - (q_start + qi);
+        tapq[qi] = (kk >= k_lo && kk < k_hi) ? (float)tapd[kk - k_lo] : 0.f;
+      }
+      if (warp == 0) {  // exclusive prefix sums of the taps (float64), one contiguous chunk per lane
+        int chunk = (T + 31) / 32, b = lane * chunk, e = b + chunk;
+        e = e > T ? T : e;
+        double s = 0.0;
+        for (int q = b; q < e; ++q) s += tapd[q];
+        double incl = s;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          double v = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += v;
+        }
+        double run = incl - s;
+        for (int q = b; q < e; ++q) { tappre[q] = run; run += tapd[q]; }
+        if (lane == 31) tappre[T] = incl;
+      }
+      __syncthreads();
+      const double g_full = tappre[T];
+      // interior points: every tap of the window lands on a valid output with full trapz weight
+      const int i_lo = o - k_lo + 1;          // first interior i
+      const int i_hi = F - 1 + o - k_hi;      // last interior i
+      // Stark widths (stehle_param, linemodels.py:554-566): gamma^2.5 for the rec- and exc-weighted plasmas
+      const double la = cld[CL_LOMAN_A], lb = cld[CL_LOMAN_B], lc = cld[CL_LOMAN_C];
+      const double g_rec = (10.0 * lc * (pow(1e6 * rec[2], la) / pow(rec[3], lb))) / 2.0;
+      const double g_exc = (10.0 * lc * (pow(1e6 * rec[4], la) / pow(rec[5], lb))) / 2.0;
+      const float g25_rec = (float)pow(g_rec, 2.5), g25_exc = (float)pow(g_exc, 2.5);
+      const double c0 = x0 - cwl;
+      // pass 1: A_e = sum_i u_e[i] G[i]
+      float sr = 0.f, se = 0.f;
+      double er = 0.0, ee = 0.0;
+      for (int j = tid; j < F; j += NT) {
+        float d = fabsf((float)fma((double)j, delta, c0));
+        float a25 = d * d * sqrtf(d);
+        float ur = __fdividef(1.f, a25 + g25_rec), ue = __fdividef(1.f, a25 + g25_exc);
+        if (j >= i_lo && j <= i_hi) { sr += ur; se += ue; }
+        else {
+          int kmin = o - j, kmax = F - 1 + o - j;  // taps that reach outputs 0 and F-1
+          int lo = kmin > k_lo ? kmin : k_lo, hi = kmax + 1 < k_hi ? kmax + 1 : k_hi;
+          double G = 0.0;
+          if (hi > lo) {
+            G = tappre[hi - k_lo] - tappre[lo - k_lo];
+            if (kmin >= lo && kmin < hi) G -= 0.5 * tapd[kmin - k_lo];
+            if (kmax >= lo && kmax < hi) G -= 0.5 * tapd[kmax - k_lo];
+          }
+          er += (double)ur * G; ee += (double)ue * G;
+        }
+      }
+      double red[2] = {(double)sr * g_full + er, (double)se * g_full + ee};
+      block_sum<NT, 2>(red, scratch);
+      const double s_rec = rec[0] / (dl * red[0]) / cal, s_exc = rec[1] / (dl * red[1]) / cal;
+      if (!(s_rec - s_rec == 0.0) || !(s_exc - s_exc == 0.0)) st |= 1u << 6;
+      const float fr = (float)s_rec, fe = (float)s_exc;
+      // pass 2: m = s_rec u_rec + s_exc u_exc -> B, then A += m (*) g
+      for (int j = tid; j < F; j += NT) {
+        float d = fabsf((float)fma((double)j, delta, c0));
+        float a25 = d * d * sqrtf(d);
+        B[j] = fr * __fdividef(1.f, a25 + g25_rec) + fe * __fdividef(1.f, a25 + g25_exc);
+      }
+      __syncthreads();
+      for (int j0 = 4 * tid; j0 < F; j0 += 4 * NT) {
+        float4 r = conv4(B + j0 + q_start, tapq, nq);
+        float4* dst = reinterpret_cast<float4*>(A + j0);
+        float4 v = *dst;
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        *dst = v;
+      }
+      __syncthreads();
+      for (int j = F + tid; j < f4; j += NT) A[j] = 0.f;  // keep the alignment tail clean
+      __syncthreads();
+    } else {
+      // ---------------- Gaussian multiplet (ADAS406Lines / XLine) ----------------
+      const double ems = rec[0];
+      const int ncmp = cl[CL_NCOMP];
+      for (int q = 0; q < ncmp; ++q) {
+        const double* cp = m.comp_d + (cl[CL_COMP_OFF] + q) * 2;
+        double cw = cp[0];
+        double fwhm;
+        if (kind == 1) {
+          if (has_vel) cw = cw * (vel / c_light + 1.0);
+          fwhm = cw * 7.715e-5 * sqrt(rec[4] / cld[CL_MASS]);
+        } else {
+          fwhm = cld[CL_FWHM];
+        }
+        if (!(fwhm > 0.0) || !(cp[1] > 0.0)) st |= 1u << 5;
+        const double sigma = fwhm * fwhm_to_sigma;
+        const double amp = (ems * (cp[1] / (2.5066282746310002 * sigma))) / cal;
+        if (!(amp - amp == 0.0)) st |= 1u << 6;
+        const double half = BAYSAR_Z_CUT * sigma;
+        double jl = ceil((cw - half - x0) / delta - 1e-9), jh = floor((cw + half - x0) / delta + 1e-9);
+        if (!(jl == jl) || !(jh == jh)) continue;
+        int j_lo = jl < 0.0 ? 0 : (jl > (double)F ? F : (int)jl);
+        int j_hi = jh < -1.0 ? -1 : (jh > (double)(F - 1) ? F - 1 : (int)jh);
+        int j = j_lo + ((tid - (j_lo % NT)) + NT) % NT;  // this thread's first owned point in the window
+        const float ampf = (float)amp;
+        for (; j <= j_hi; j += NT) {
+          double z = (grid_x(x0, delta, j) - cw) / sigma;
+          if (fabs(z) <= BAYSAR_Z_CUT) A[j] += ampf * exp_neg_f32(-0.5 * z * z);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ================= pre-convolution area and minimum (spectrometers.py:256, :271) ===============================
+  double pre_s = 0.0;
+  float mn = 3.402823466e38f;
+  int bad = 0;
+  for (int j = tid; j < F; j += NT) {
+    float v = A[j];
+    double w = (j == 0 || j == F - 1) ? 0.5 : 1.0;
+    pre_s += w * (double)v;
+    mn = v < mn ? v : mn;
+    if (!(v - v == 0.f)) bad = 1;
+  }
+  if (a.fine_pre) {
+    float* o_ = a.fine_pre + n * (int64_t)F;
+    for (int j = tid; j < F; j += NT) o_[j] = A[j];
+  }
+  mn = warp_min_f(mn);
+  if (lane == 0) reinterpret_cast<float*>(iscr)[4 + warp] = mn;  // iscr[4 .. 4 + NT/32)
+  double red1[1] = {pre_s};
+  block_sum<NT, 1>(red1, scratch);
+  for (int w = 0; w < NT / 32; ++w) { float o_ = reinterpret_cast<float*>(iscr)[4 + w]; mn = o_ < mn ? o_ : mn; }
+  const double pre = dl * red1[0];
+  if (__syncthreads_or(bad)) st |= 1u << 6;
+
+  // ================= instrument function taps (spectrometers.py:229-253) ========================================
+  int KI, k_lo, k_hi;
+  if (ch[CH_CALINT_IDX] >= 0) {
+    // sampled Gaussian instrument function over the whole fine grid (plasmas.py:96-98), pixel normalised
+    KI = F;
+    const double fw = pow(10.0, th[ch[CH_CALINT_IDX]]);
+    const double sigma = fw * fwhm_to_sigma, xm = chd[CH_X_MEAN];
+    if (!(fw > 0.0)) st |= 1u << 5;
+    if (tid == 0) { iscr[0] = F; iscr[1] = -1; }
+    __syncthreads();
+    double gs = 0.0;
+    for (int q = tid; q < F; q += NT) {
+      double z = (grid_x(x0, delta, q) - xm) / sigma;
+      if (fabs(z) <= BAYSAR_Z_CUT) { atomicMin(&iscr[0], q); atomicMax(&iscr[1], q); gs += exp(-0.5 * z * z); }
+    }
+    __syncthreads();
+    k_lo = iscr[0]; k_hi = iscr[1] + 1;
+    double red2[1] = {gs};
+    block_sum<NT, 1>(red2, scratch);
+    if (!(red2[0] > 0.0)) st |= 1u << 7;
+    int o = (KI - 1) / 2;
+    // clamp the window to the shared-memory capacity sized from the parameter bounds
+    int lim = HALO - 4 < TAPS_MAX / 2 - 4 ? HALO - 4 : TAPS_MAX / 2 - 4;
+    if (k_hi - 1 - o > lim) { k_hi = o + lim + 1; st |= 1u << 16; }
+    if (o - k_lo > lim) { k_lo = o - lim; st |= 1u << 16; }
+    if (k_hi <= k_lo) { k_lo = o; k_hi = o + 1; }
+    const int q_min = o - k_hi + 1, q_max = o - k_lo;
+    const int q_start = q_min & ~3;
+    const int nq = (q_max - q_start + 1 + 3) & ~3;
+    for (int qi = tid; qi < nq; qi += NT) {
+      int kk = o - (q_start + qi);
+      float w = 0.f;
+      if (kk >= k_lo && kk < k_hi) {
+        double z = (grid_x(x0, delta, kk) - xm) / sigma;
+        w = (float)(exp(-0.5 * z * z) / red2[0]);
+      }
+      tapq[qi] = w;
+    }
+  } else {
+    KI = ch[CH_KI]; k_lo = ch[CH_IF_KLO]; k_hi = ch[CH_IF_KHI];
+    const int o = (KI - 1) / 2;
+    const int q_min = o - k_hi + 1, q_max = o - k_lo;
+    const int q_start = q_min & ~3;
+    const int nq = (q_max - q_start + 1 + 3) & ~3;
+    const double* w = m.ifn + ch[CH_IF_OFF];
+    for (int qi = tid; qi < nq; qi += NT) {
+      int kk = o - (q_start + qi);
+      tapq[qi] = (kk >= k_lo && kk < k_hi) ? (float)w[kk] : 0.f;
+    }
+  }
+  const int o_if = (KI - 1) / 2;
+  const int q_min_if = o_if - k_hi + 1, q_max_if = o_if - k_lo;
+  const int q_start_if = q_min_if & ~3;
+  const int nq_if = (q_max_if - q_start_if + 1 + 3) & ~3;
+  __syncthreads();
+
+  // ================= instrument convolution, clip at the pre-convolution minimum (spectrometers.py:269-271) =====
+  double post_s = 0.0;
+  bad = 0;
+  for (int j0 = 4 * tid; j0 < F; j0 += 4 * NT) {
+    float4 r = conv4(A + j0 + q_start_if, tapq, nq_if);
+    r.x = r.x < mn ? mn : r.x; r.y = r.y < mn ? mn : r.y; r.z = r.z < mn ? mn : r.z; r.w = r.w < mn ? mn : r.w;
+    *reinterpret_cast<float4*>(B + j0) = r;
+    float vv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int j = j0 + q;
+      if (j < F) {
+        double w = (j == 0 || j == F - 1) ? 0.5 : 1.0;
+        post_s += w * (double)vv[q];
+        if (!(vv[q] - vv[q] == 0.f)) bad = 1;
+      }
+    }
+  }
+  // the four end outputs in float64: they set the slope interp1d extrapolates with (sampled wavelength maps)
+  if (warp < 4) {
+    int j = warp < 2 ? warp : F - 4 + warp;
+    double s = 0.0;
+    for (int qi = lane; qi < nq_if; qi += 32) s += (double)tapq[qi] * (double)A[j + q_start_if + qi];
+    s = warp_sum(s);
+    if (lane == 0) edge64[warp] = s < (double)mn ? (double)mn : s;
+  }
+  double red3[1] = {post_s};
+  block_sum<NT, 1>(red3, scratch);
+  if (__syncthreads_or(bad)) st |= 1u << 8;
+  const double post = dl * red3[0];
+  const double ratio = post / pre;
+  const double ratio2 = (post / ratio) / pre;
+  if (!(fabs(ratio2 - 1.0) <= 1e-8 + 1e-2)) st |= 1u << 9;  // np.isclose(ratio2, 1, rtol=1e-2)
+  const double bg = pow(10.0, th[ch[CH_BG_IDX]]);
+  if (a.fine_post) {
+    float* o_ = a.fine_post + n * (int64_t)F;
+    for (int j = tid; j < F; j += NT) o_[j] = (float)((double)B[j] / ratio + bg);
+  }
+
+  // ================= wavelength map, clip at the background, Cauchy likelihood (spectrometers.py:299-310, :154-195)
+  const int poff = ch[CH_PIX_OFF];
+  const int cw_idx = ch[CH_CALWAVE_IDX];
+  const double cwl_map = cw_idx >= 0 ? th[cw_idx] : chd[CH_CALWAVE_CWL];
+  const double disp_map = cw_idx >= 0 ? th[cw_idx + 1] : chd[CH_CALWAVE_DISP];
+  double acc = 0.0;
+  for (int p = tid; p < P; p += NT) {
+    int i; double w;
+    if (cw_idx >= 0) {
+      double px = ((double)p - chd[CH_PIX_MEAN]) * disp_map + cwl_map;
+      double g = floor((px - x0) / delta);
+      int jj = g < 0.0 ? 0 : (g > (double)(F - 1) ? F - 1 : (int)g);
+      while (jj > 0 && grid_x(x0, delta, jj - 1) >= px) --jj;
+      while (jj < F && grid_x(x0, delta, jj) < px) ++jj;
+      i = jj - 1;
+      i = i < 0 ? 0 : (i > F - 2 ? F - 2 : i);
+      double xi = grid_x(x0, delta, i);
+      w = (px - xi) / (grid_x(x0, delta, i + 1) - xi);
+    } else {
+      i = m.pix_idx[poff + p];
+      w = m.pix_frac[poff + p];
+    }
+    double v0 = (i < 2) ? edge64[i] : (i >= F - 2 ? edge64[i - (F - 4)] : (double)B[i]);
+    int i1 = i + 1;
+    double v1 = (i1 < 2) ? edge64[i1] : (i1 >= F - 2 ? edge64[i1 - (F - 4)] : (double)B[i1]);
+    double fm = (v0 + w * (v1 - v0)) / ratio + bg;
+    fm = fm < bg ? bg : fm;
+    if (!(fm - fm == 0.0)) st |= 1u << 10;
+    if (a.spectra) a.spectra[n * (int64_t)P + p] = fm;
+    double r = (m.y[poff + p] - fm) / m.err[poff + p];
+    double r2 = r * r;
+    if (r2 == 0.0) st |= 1u << 11;
+    if (!(r2 - r2 == 0.0)) st |= 1u << 12;
+    acc += log(1.0 + r2);
+  }
+  double red4[1] = {acc};
+  block_sum<NT, 1>(red4, scratch);
+  if (tid == 0) a.components[n * (int64_t)ncomp_cols + c] = -red4[0];
+  st = __syncthreads_or((int)st);
+  if (tid == 0 && st) atomicOr(&a.status[n], st);
+}

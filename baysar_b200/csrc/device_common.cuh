@@ -1,0 +1,178 @@
+// Shared device helpers: model view, searches, table interpolation, reductions.
+#pragma once
+#include <stdint.h>
+
+#include "layout.h"
+
+#ifndef BAYSAR_CPU_EMU
+#include <cuda_runtime.h>
+#define BAYSAR_DEV __device__ __forceinline__
+#else
+#include "cpu_emu.h"  // tests/emu: std::thread-based execution of the same kernel source (test-only)
+#endif
+
+#define BAYSAR_LINE_STRIDE 12
+#define BAYSAR_HDR_STRIDE 4  // per-theta header written by the LOS stage: ne_max, reserved...
+#define BAYSAR_Z_CUT 8.85    // exp(-z*z/2) < 1e-17 beyond this
+
+// Device-side view of one compiled model: pointers into the single HBM copy of the descriptor blob.
+struct ModelDev {
+  const int64_t* I;
+  const double* D;
+  const double* los_x;
+  const double* los_w;
+  const double* prof_d;
+  const int* sp_i;
+  const double* sp_d;
+  const int* elem_dens_idx;
+  const double* a11_ne;
+  const double* a11_te;
+  const double* a11_scd;
+  const double* h_ne;
+  const double* h_te;
+  const double* h_tab;
+  const double* tau_grid;
+  const double* spl_tx;
+  const double* spl_ty;
+  const double* spl_c;
+  const int* ul_i;
+  const int* pr_i;
+  const double* pr_d;
+  const int* cso_off;
+  const int* cso_ul;
+  const int* ch_i;
+  const double* ch_d;
+  const int* cl_i;
+  const double* cl_d;
+  const double* comp_d;
+  const double* y;
+  const double* err;
+  const double* ifn;
+  const int* pix_idx;
+  const double* pix_frac;
+};
+
+// np.clip(v, lo, None): NaN propagates (fmax would swallow it)
+BAYSAR_DEV double clip_lo(double v, double lo) { return v < lo ? lo : v; }
+
+// np.nan_to_num: NaN -> 0, +-inf -> +-DBL_MAX
+BAYSAR_DEV double nan_to_num(double v) {
+  if (v != v) return 0.0;
+  if (v > 1.7976931348623157e308) return 1.7976931348623157e308;
+  if (v < -1.7976931348623157e308) return -1.7976931348623157e308;
+  return v;
+}
+
+// max([0, x]) of the reference's gaussian_{high,low}_pass_cost (priors.py:4-11): NaN -> 0
+BAYSAR_DEV double pos_part(double x) { return x > 0.0 ? x : 0.0; }
+BAYSAR_DEV double high_pass(double v, double thr, double err) {
+  double t = pos_part(thr - v) / err;
+  return -0.5 * (t * t);
+}
+BAYSAR_DEV double low_pass(double v, double thr, double err) {
+  double t = pos_part(v - thr) / err;
+  return -0.5 * (t * t);
+}
+
+// numpy.searchsorted(g, x, side="left")
+BAYSAR_DEV int lower_bound(const double* g, int n, double x) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (g[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// cell + unclamped weight of scipy's linear RegularGridInterpolator (bounds_error=False, fill_value=None)
+BAYSAR_DEV void linear_cell(const double* g, int n, double x, int& i, double& a) {
+  int k = lower_bound(g, n, x) - 1;
+  k = k < 0 ? 0 : (k > n - 2 ? n - 2 : k);
+  i = k;
+  a = (x - g[k]) / (g[k + 1] - g[k]);
+}
+
+BAYSAR_DEV double bilinear(const double* t, int n1, int i, int j, double a, double b) {
+  const double* r0 = t + (int64_t)i * n1 + j;
+  const double* r1 = r0 + n1;
+  return r0[0] * (1 - a) * (1 - b) + r0[1] * (1 - a) * b + r1[0] * a * (1 - b) + r1[1] * a * b;
+}
+
+// FITPACK fpbisp/fpbspl for one coordinate, degree 3: clamp to the knot span, locate the interval
+// t[l] <= x < t[l+1] and return the 4 non-zero B-spline basis values (scipy RectBivariateSpline.ev -> bispeu).
+BAYSAR_DEV void bspline_basis3(const double* t, int n, double x, int& l, double* h) {
+  const int k = 3;
+  double tb = t[k], te = t[n - k - 1];
+  if (x < tb) x = tb;
+  if (x > te) x = te;
+  int lo = k;
+  while (lo < n - k - 2 && x >= t[lo + 1]) ++lo;
+  l = lo;
+  double hh[3];
+  h[0] = 1.0;
+  for (int j = 1; j <= k; ++j) {
+    for (int i = 0; i < j; ++i) hh[i] = h[i];
+    h[0] = 0.0;
+    for (int i = 0; i < j; ++i) {
+      int li = l + i + 1;
+      int lj = li - j;
+      double f = hh[i] / (t[li] - t[lj]);
+      h[i] = h[i] + f * (t[li] - x);
+      h[i + 1] = f * (x - t[lj]);
+    }
+  }
+}
+
+BAYSAR_DEV double bspline_eval(const double* c, int ncy, int lx, int ly, const double* hx, const double* hy) {
+  double sp = 0.0;
+  const double* base = c + (int64_t)(lx - 3) * ncy + (ly - 3);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sp += base[i * ncy + j] * hx[i] * hy[j];
+  }
+  return sp;
+}
+
+// ---- warp / block reductions ------------------------------------------------------------------------------
+BAYSAR_DEV double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+BAYSAR_DEV double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w > v ? w : v;
+  }
+  return v;
+}
+BAYSAR_DEV float warp_min_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w < v ? w : v;
+  }
+  return v;
+}
+
+// Sum NV doubles over the block.  scratch: NV * (NT/32) doubles.  Result valid in every thread.
+template <int NT, int NV>
+BAYSAR_DEV void block_sum(double* v, double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = warp_sum(v[k]);
+    if (lane == 0) scratch[k * (NT / 32) + warp] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) s += scratch[k * (NT / 32) + w];
+    v[k] = s;
+  }
+  __syncthreads();
+}

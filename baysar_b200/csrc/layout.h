@@ -1,0 +1,166 @@
+/*
+ * Descriptor-blob layout shared by the host-side model compiler (baysar_b200/model.py parses the enums below with a
+ * regex — keep one enumerator per line, no explicit values) and the CUDA side.
+ *
+ * blob = [ int64 magic, int64 version, int64 n_sections, { int64 offset_bytes, int64 count } x n_sections ] payload...
+ * Every section is 16-byte aligned.  Element types are fixed per section (see comments).
+ */
+#ifndef BAYSAR_LAYOUT_H
+#define BAYSAR_LAYOUT_H
+
+#define BAYSAR_BLOB_MAGIC 0x4252415359534142LL /* "BAYSYSAB" */
+#define BAYSAR_BLOB_VERSION 3
+
+enum BaysarSection {
+  SEC_I,              /* int64  [I_COUNT]           model-wide integer scalars                         */
+  SEC_D,              /* double [D_COUNT]           model-wide double scalars                          */
+  SEC_LOS_X,          /* double [L]                 line-of-sight coordinate                           */
+  SEC_LOS_W,          /* double [L]                 trapz weights of the LOS grid                      */
+  SEC_PROF_D,         /* double [PROF_D_COUNT]      profile-family constants                           */
+  SEC_SP_I,           /* int32  [n_species][SP_I_COUNT]                                                 */
+  SEC_SP_D,           /* double [n_species][SP_D_COUNT]                                                 */
+  SEC_ELEM_DENS_IDX,  /* int32  [n_elem]            theta index of the density of each impurity element */
+  SEC_A11_NE,         /* double [a11_nne]           adf11 (scd) density grid                           */
+  SEC_A11_TE,         /* double [a11_nte]                                                              */
+  SEC_A11_SCD,        /* double [a11_nne][a11_nte]  ionisation rate, raw values                        */
+  SEC_H_NE,           /* double [h_nne]             adf15 density grid                                 */
+  SEC_H_TE,           /* double [h_nte]                                                                */
+  SEC_H_TAB,          /* double [n_htab][h_nne][h_nte]  log(PEC)                                       */
+  SEC_TAU_GRID,       /* double [n_tau]             log10 tau grid ("magical_tau")                     */
+  SEC_SPL_TX,         /* double [spl_nx]            bicubic spline knots in ne                         */
+  SEC_SPL_TY,         /* double [spl_ny]            bicubic spline knots in Te                         */
+  SEC_SPL_C,          /* double [n_tec][n_tau][(spl_nx-4)*(spl_ny-4)]  B-spline coefficients of log(ne*TEC) */
+  SEC_UL_I,           /* int32  [n_ulines][UL_I_COUNT]  unique (line-of-sight) lines                    */
+  SEC_PR_I,           /* int32  [n_priors][PR_I_COUNT]                                                  */
+  SEC_PR_D,           /* double [n_priors][PR_D_COUNT]                                                  */
+  SEC_CSO_OFF,        /* int32  [n_elem + 1]        ChargeStateOrderPrior: per element, offsets into CSO_UL */
+  SEC_CSO_UL,         /* int32  [..]                unique-line ids ordered by charge state             */
+  SEC_CH_I,           /* int32  [n_chords][CH_I_COUNT]                                                  */
+  SEC_CH_D,           /* double [n_chords][CH_D_COUNT]                                                  */
+  SEC_CL_I,           /* int32  [n_clines][CL_I_COUNT]  per-chord line objects                          */
+  SEC_CL_D,           /* double [n_clines][CL_D_COUNT]                                                  */
+  SEC_COMP_D,         /* double [n_comps][2]        multiplet members: centre wavelength, fraction      */
+  SEC_Y,              /* double [sum P]             measured spectra                                    */
+  SEC_ERR,            /* double [sum P]             error model                                         */
+  SEC_IF,             /* double [sum KI]            fine-grid instrument function                       */
+  SEC_PIX_IDX,        /* int32  [sum P]             default wavelength map: lower fine-grid index       */
+  SEC_PIX_FRAC,       /* double [sum P]             default wavelength map: interpolation weight        */
+  SEC_COUNT
+};
+
+enum BaysarI {
+  I_N_PARAMS,
+  I_L,
+  I_N_CHORDS,
+  I_N_SPECIES,
+  I_N_ELEM,
+  I_N_ULINES,
+  I_N_PRIORS,
+  I_N_CLINES,
+  I_PROFILE_KIND,       /* 0 = EsymmtricCauchyPlasma */
+  I_NE_IDX,             /* first theta index of the electron_density slice */
+  I_TE_IDX,
+  I_HAS_HYDROGEN,
+  I_H_SPECIES,          /* index into the species table */
+  I_COLD_NEUTRALS,
+  I_COLD_IONS,
+  I_THERMALISED,
+  I_CAL_WAVE,
+  I_CAL_INT,
+  I_CAL_IF,
+  I_A11_NNE,
+  I_A11_NTE,
+  I_H_NNE,
+  I_H_NTE,
+  I_N_HTAB,
+  I_N_TAU,
+  I_SPL_NX,
+  I_SPL_NY,
+  I_N_TEC,
+  I_P_MAX,
+  I_F_MAX,
+  I_COUNT
+};
+
+enum BaysarD {
+  D_RESERVED,
+  D_COUNT
+};
+
+enum BaysarProfD {
+  PROF_NE_CENTRE_FIXED, /* 1.0 if the density profile has a fixed centre (dr given), else the centre is sampled */
+  PROF_NE_CENTRE,
+  PROF_TE_CENTRE,
+  PROF_NE_FLOOR,        /* 1e-3 */
+  PROF_D_COUNT
+};
+
+enum BaysarSpI { SP_DENS_IDX, SP_TAU_IDX, SP_VEL_IDX, SP_TI_IDX, SP_IS_H, SP_IS_IMPURITY, SP_I_COUNT };
+enum BaysarSpD { SP_MASS, SP_D_COUNT };
+
+enum BaysarUlI {
+  UL_KIND,     /* 0 Balmer, 1 ADAS406, 2 XLine */
+  UL_SPECIES,
+  UL_TAB_A,    /* Balmer: excitation log-PEC table; ADAS406: TEC table; XLine: theta index */
+  UL_TAB_B,    /* Balmer: recombination log-PEC table */
+  UL_I_COUNT
+};
+
+enum BaysarPriorKind {
+  PRIOR_STATIC_PRESSURE,
+  PRIOR_NEUTRAL_FRACTION,
+  PRIOR_STARK_TO_PEAK,
+  PRIOR_ANTIPROTON,
+  PRIOR_MAIN_ION_FRACTION,
+  PRIOR_CHARGE_STATE_ORDER,
+  PRIOR_WAVELENGTH_CAL,
+  PRIOR_INTENSITY_CAL,
+  PRIOR_GAUSSIAN_IF,
+  PRIOR_KIND_COUNT
+};
+enum BaysarPrI { PR_KIND, PR_I0, PR_I1, PR_I_COUNT };
+enum BaysarPrD { PR_D0, PR_D1, PR_D2, PR_D3, PR_D_COUNT };
+
+enum BaysarChI {
+  CH_P,
+  CH_F,
+  CH_KI,         /* instrument-function taps */
+  CH_IF_KLO,     /* first / one-past-last significant tap */
+  CH_IF_KHI,
+  CH_N_LINES,
+  CH_LINE_OFF,
+  CH_BG_IDX,
+  CH_CAL_IDX,
+  CH_CALWAVE_IDX,
+  CH_CALINT_IDX,
+  CH_PIX_OFF,    /* offset into SEC_Y / SEC_ERR / SEC_PIX_* */
+  CH_IF_OFF,
+  CH_HALO,       /* zero padding (multiple of 4) on each side of the fine-grid shared-memory buffers */
+  CH_TAPS_MAX,   /* capacity of the shared-memory tap buffer */
+  CH_I_COUNT
+};
+enum BaysarChD {
+  CH_X0,            /* fine grid = X0 + j * DELTA (numpy arange), bit-exact */
+  CH_DELTA,
+  CH_DL,            /* mean spacing, the trapz weight */
+  CH_CALWAVE_CWL,   /* default wavelength map constants */
+  CH_CALWAVE_DISP,
+  CH_PIX_MEAN,      /* mean(arange(P)) */
+  CH_X_MEAN,        /* mean of the fine grid: centre of the sampled Gaussian instrument function */
+  CH_D_COUNT
+};
+
+enum BaysarClI { CL_KIND, CL_ULINE, CL_SPECIES, CL_NCOMP, CL_COMP_OFF, CL_KD, CL_I_COUNT };
+enum BaysarClD {
+  CL_CWL0,
+  CL_LOMAN_A,
+  CL_LOMAN_B,
+  CL_LOMAN_C,
+  CL_MASS,
+  CL_DOP_START,   /* Doppler tap grid = DOP_START + k * DOP_DELTA (numpy arange) */
+  CL_DOP_DELTA,
+  CL_FWHM,        /* XLine: fixed FWHM */
+  CL_D_COUNT
+};
+
+#endif /* BAYSAR_LAYOUT_H */

@@ -1,0 +1,339 @@
+// K1 — line-of-sight stage (float64).  One warp per theta; LOS points across lanes; warp-shuffle reductions.
+//
+// Replaces, per theta (reference file:line):
+//   PlasmaLine.update_plasma_state            baysar/plasmas.py:642-694   theta -> ne, Te, main-ion density
+//   EsymmtricProfile.__call__                 baysar/lineshapes.py:779-817
+//   PlasmaLine.calc_total_impurity_electrons  baysar/plasmas.py:876-889   (concstar)
+//   PlasmaLine.update_neutral_profile         baysar/plasmas.py:696-741   (scd only; acd/plt/prb feed side outputs)
+//   BalmerHydrogenLine.__call__ (LOS part)    baysar/linemodels.py:758-836
+//   ADAS406Lines.__call__ / get_tec (LOS part) baysar/linemodels.py:386-426, :445-494
+//   XLine.__call__ (amplitude)                baysar/linemodels.py:228-230
+//   default priors                            baysar/priors.py:14-101, :509-556, :646-667, :1046-1089
+#pragma once
+#include "device_common.cuh"
+
+struct LosArgs {
+  const double* theta;  // [N][n_params]
+  int64_t n;
+  double* lines;       // [N][n_ulines][BAYSAR_LINE_STRIDE]
+  double* components;  // [N][n_chords + n_priors]; this kernel fills the prior columns
+  double* hdr;         // [N][BAYSAR_HDR_STRIDE]
+  double* profiles;    // optional [N][4][L]
+  uint32_t* status;    // [N] (overwritten)
+};
+
+// bytes of dynamic shared memory one warp needs for L line-of-sight points
+__host__ __device__ static inline size_t los_smem_per_warp(int L) { return (size_t)L * (14 * sizeof(double) + 4 * sizeof(int)); }
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) los_stage_kernel(ModelDev m, LosArgs a) {
+#ifdef BAYSAR_CPU_EMU
+  unsigned char* los_smem_raw = emu_dynamic_smem();
+#else
+  extern __shared__ __align__(16) unsigned char los_smem_raw[];
+#endif
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n = (int64_t)blockIdx.x * WARPS + warp;
+  if (n >= a.n) return;  // whole warp exits together; no block-level barrier is used in this kernel
+
+  const int64_t* I = m.I;
+  const int L = (int)I[I_L], n_params = (int)I[I_N_PARAMS], n_elem = (int)I[I_N_ELEM];
+  const int n_species = (int)I[I_N_SPECIES], n_ul = (int)I[I_N_ULINES], n_pr = (int)I[I_N_PRIORS];
+  const int n_chords = (int)I[I_N_CHORDS];
+  const double* th = a.theta + n * n_params;
+
+  unsigned char* base = los_smem_raw + (size_t)warp * los_smem_per_warp(L);
+  double* ne_s = (double*)base;
+  double* te_s = ne_s + L;
+  double* nm_s = te_s + L;   // main ion density
+  double* n0_s = nm_s + L;   // neutral density profile
+  double* ha_s = n0_s + L;   // adf15-grid cell weights
+  double* hb_s = ha_s + L;
+  double* bx_s = hb_s + L;   // [L][4] spline basis in ne
+  double* by_s = bx_s + 4 * L;
+  int* hi_s = (int*)(by_s + 4 * L);
+  int* hj_s = hi_s + L;
+  int* lx_s = hj_s + L;
+  int* ly_s = lx_s + L;
+
+  uint32_t st = 0;
+  for (int k = lane; k < n_params; k += 32) {
+    double v = th[k];
+    if (v != v) st |= 1u << 0;
+    if (v - v != 0.0 && v == v) st |= 1u << 1;  // +-inf
+  }
+
+  // ---- electron density / temperature profiles (lineshapes.py:779-817)
+  const int ne_idx = (int)I[I_NE_IDX], te_idx = (int)I[I_TE_IDX];
+  double ne_A, ne_c, ne_f, ne_floor;
+  if (m.prof_d[PROF_NE_CENTRE_FIXED] != 0.0) {
+    ne_A = th[ne_idx]; ne_f = th[ne_idx + 1]; ne_floor = th[ne_idx + 2]; ne_c = m.prof_d[PROF_NE_CENTRE];
+  } else {
+    ne_A = th[ne_idx]; ne_c = th[ne_idx + 1]; ne_f = th[ne_idx + 2]; ne_floor = m.prof_d[PROF_NE_FLOOR];
+  }
+  const double te_A = th[te_idx], te_f = th[te_idx + 1], te_floor = th[te_idx + 2], te_c = m.prof_d[PROF_TE_CENTRE];
+  const double ne_pk = pow(10.0, ne_A), te_pk = pow(10.0, te_A);
+  double nemax = -1.7976931348623157e308;
+  for (int l = lane; l < L; l += 32) {
+    double x = m.los_x[l];
+    double dx = x - ne_c;
+    double sg = 0.2 * ne_f + ne_f / (1.0 + exp(-dx));
+    double r = dx / sg;
+    double v = clip_lo(ne_pk / (1.0 + r * r), ne_floor);
+    ne_s[l] = v;
+    nemax = v > nemax ? v : nemax;
+    dx = x - te_c;
+    sg = 0.2 * te_f + te_f / (1.0 + exp(-dx));
+    r = dx / sg;
+    te_s[l] = clip_lo(te_pk / (1.0 + r * r), te_floor);
+  }
+  nemax = warp_max(nemax);
+
+  // ---- impurity electrons, main ion density (plasmas.py:876-889, :673)
+  for (int l = lane; l < L; l += 32) {
+    double ne = ne_s[l], tot = 0.0;
+    for (int e = 0; e < n_elem; ++e) {
+      double dens = pow(10.0, th[m.elem_dens_idx[e]]);
+      double conc = (dens / nemax) * ne;
+      tot += (conc / nemax) * ne;
+    }
+    nm_s[l] = ne - nan_to_num(tot);
+  }
+
+  // ---- impurity tau must index the ADAS tau grid (plasmas.py:1410-1429 raise; linemodels.py:454-467)
+  const int n_tau = (int)I[I_N_TAU];
+  for (int s = lane; s < n_species; s += 32) {
+    const int* sp = m.sp_i + s * SP_I_COUNT;
+    if (sp[SP_IS_IMPURITY]) {
+      double lt = log10(pow(10.0, th[sp[SP_TAU_IDX]]));
+      if (!(lt > m.tau_grid[0] && lt <= m.tau_grid[n_tau - 1])) st |= 1u << 2;
+    }
+  }
+
+  // ---- neutral hydrogen profile (plasmas.py:696-741)
+  const int has_h = (int)I[I_HAS_HYDROGEN];
+  if (has_h) {
+    const int* sp = m.sp_i + (int)I[I_H_SPECIES] * SP_I_COUNT;
+    const int dens_idx = sp[SP_DENS_IDX];
+    const double tau_h = pow(10.0, th[sp[SP_TAU_IDX]]);
+    const double n0_sampled = dens_idx >= 0 ? pow(10.0, th[dens_idx]) : 0.0;
+    const int nne = (int)I[I_A11_NNE], nte = (int)I[I_A11_NTE];
+    for (int l = lane; l < L; l += 32) {
+      double ne = ne_s[l], te = te_s[l];
+      int ci, cj; double ca, cb;
+      linear_cell(m.a11_ne, nne, ne, ci, ca);
+      linear_cell(m.a11_te, nte, te, cj, cb);
+      double scd = bilinear(m.a11_scd, nte, ci, cj, ca, cb);
+      double n0 = dens_idx >= 0 ? n0_sampled : nm_s[l];
+      n0 = n0 - n0 * ne * scd * tau_h;
+      n0 = clip_lo(n0, 1.0);
+      if (n0 != n0) st |= 1u << 3;
+      n0_s[l] = n0;
+    }
+    // adf15 grid cells, shared by every Balmer line
+    const int hne = (int)I[I_H_NNE], hte = (int)I[I_H_NTE];
+    for (int l = lane; l < L; l += 32) {
+      int ci, cj; double ca, cb;
+      linear_cell(m.h_ne, hne, ne_s[l], ci, ca);
+      linear_cell(m.h_te, hte, te_s[l], cj, cb);
+      hi_s[l] = ci; hj_s[l] = cj; ha_s[l] = ca; hb_s[l] = cb;
+    }
+  } else {
+    for (int l = lane; l < L; l += 32) n0_s[l] = 0.0;
+  }
+
+  // ---- bicubic B-spline basis per LOS point, shared by every impurity line and tau slice
+  const int n_tec = (int)I[I_N_TEC];
+  const int snx = (int)I[I_SPL_NX], sny = (int)I[I_SPL_NY];
+  if (n_tec > 0) {
+    for (int l = lane; l < L; l += 32) {
+      int lx, ly; double hx[4], hy[4];
+      bspline_basis3(m.spl_tx, snx, ne_s[l], lx, hx);
+      bspline_basis3(m.spl_ty, sny, te_s[l], ly, hy);
+      lx_s[l] = lx; ly_s[l] = ly;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { bx_s[4 * l + q] = hx[q]; by_s[4 * l + q] = hy[q]; }
+    }
+  }
+  __syncwarp();
+
+  if (a.profiles) {
+    double* p = a.profiles + n * 4 * (int64_t)L;
+    for (int l = lane; l < L; l += 32) {
+      p[l] = ne_s[l]; p[L + l] = te_s[l]; p[2 * L + l] = nm_s[l]; p[3 * L + l] = n0_s[l];
+    }
+  }
+
+  // ---- unique lines
+  const double four_pi = 4.0 * 3.141592653589793;
+  double* lines_n = a.lines + n * (int64_t)n_ul * BAYSAR_LINE_STRIDE;
+  const int cold_neutrals = (int)I[I_COLD_NEUTRALS], cold_ions = (int)I[I_COLD_IONS];
+  const int thermalised = (int)I[I_THERMALISED];
+  for (int u = 0; u < n_ul; ++u) {
+    const int* ul = m.ul_i + u * UL_I_COUNT;
+    const int kind = ul[UL_KIND];
+    double* rec = lines_n + u * BAYSAR_LINE_STRIDE;
+    if (kind == 0) {  // Balmer (linemodels.py:782-836)
+      const int hne = (int)I[I_H_NNE], hte = (int)I[I_H_NTE];
+      const double* texc = m.h_tab + (int64_t)ul[UL_TAB_A] * hne * hte;
+      const double* trec = m.h_tab + (int64_t)ul[UL_TAB_B] * hne * hte;
+      double s[12];
+#pragma unroll
+      for (int q = 0; q < 12; ++q) s[q] = 0.0;
+      for (int l = lane; l < L; l += 32) {
+        double ne = ne_s[l], te = te_s[l], w = m.los_w[l];
+        double pe = exp(bilinear(texc, hte, hi_s[l], hj_s[l], ha_s[l], hb_s[l]));
+        double pr = exp(bilinear(trec, hte, hi_s[l], hj_s[l], ha_s[l], hb_s[l]));
+        if (pe != pe || pr != pr) st |= 1u << 4;
+        double rp = clip_lo(nm_s[l], 1.0) * ne * pr;
+        double ep = n0_s[l] * ne * pe;
+        double tp = rp + ep;
+        s[0] += rp; s[1] += ep; s[2] += w * rp; s[3] += w * ep;
+        s[4] += rp * ne; s[5] += rp * te; s[6] += ep * ne; s[7] += ep * te;
+        s[8] += tp; s[9] += w * tp; s[10] += tp * ne; s[11] += tp * te;
+      }
+#pragma unroll
+      for (int q = 0; q < 12; ++q) s[q] = warp_sum(s[q]);
+      double rec_sum = s[2] / four_pi, exc_sum = s[3] / four_pi, ems = s[9] / four_pi;
+      double rec_ne = s[4] / s[0], rec_te = s[5] / s[0], exc_ne = s[6] / s[1], exc_te = s[7] / s[1];
+      double f_rec = rec_sum / ems;
+      double ti;
+      const int* sp = m.sp_i + ul[UL_SPECIES] * SP_I_COUNT;
+      if (cold_neutrals) ti = 0.01;
+      else if (thermalised) ti = (1 - f_rec) * exc_te + f_rec * rec_te;
+      else ti = pow(10.0, th[sp[SP_TI_IDX]]);
+      if (lane == 0) {
+        rec[0] = rec_sum; rec[1] = exc_sum; rec[2] = rec_ne; rec[3] = rec_te; rec[4] = exc_ne; rec[5] = exc_te;
+        rec[6] = ti; rec[7] = f_rec; rec[8] = s[10] / s[8]; rec[9] = s[11] / s[8]; rec[10] = ems; rec[11] = 0.0;
+      }
+    } else if (kind == 1) {  // ADAS406 (linemodels.py:386-426, :445-494)
+      const int* sp = m.sp_i + ul[UL_SPECIES] * SP_I_COUNT;
+      const double dens = pow(10.0, th[sp[SP_DENS_IDX]]);
+      const double lt = log10(pow(10.0, th[sp[SP_TAU_IDX]]));
+      int j = lower_bound(m.tau_grid, n_tau, lt);
+      if (j >= n_tau) { st |= 1u << 2; j = n_tau - 1; }
+      int i = j - 1;
+      if (i < 0) i = n_tau - 1;  // python's negative index (already flagged above)
+      const double ti_ = m.tau_grid[i], tj_ = m.tau_grid[j];
+      const double i_w = 1.0 + (lt - ti_) / (ti_ - tj_), j_w = 1.0 + (tj_ - lt) / (ti_ - tj_);
+      const int ncx = snx - 4, ncy = sny - 4;
+      const double* ci_ = m.spl_c + ((int64_t)ul[UL_TAB_A] * n_tau + i) * ncx * ncy;
+      const double* cj_ = m.spl_c + ((int64_t)ul[UL_TAB_A] * n_tau + j) * ncx * ncy;
+      double s[5] = {0, 0, 0, 0, 0};
+      for (int l = lane; l < L; l += 32) {
+        double ne = ne_s[l], te = te_s[l];
+        double n0 = dens * (ne / nemax);
+        double vi = bspline_eval(ci_, ncy, lx_s[l], ly_s[l], bx_s + 4 * l, by_s + 4 * l);
+        double vj = bspline_eval(cj_, ncy, lx_s[l], ly_s[l], bx_s + 4 * l, by_s + 4 * l);
+        double tec = nan_to_num(exp(vi) * i_w + exp(vj) * j_w);
+        double p = clip_lo(n0 * tec, 1.0);
+        s[0] += p; s[1] += m.los_w[l] * p; s[2] += p * ne; s[3] += p * (n0 / ne); s[4] += p * te;
+      }
+#pragma unroll
+      for (int q = 0; q < 5; ++q) s[q] = warp_sum(s[q]);
+      double ems_te = s[4] / s[0];
+      double ti;
+      if (cold_ions) ti = 0.01;
+      else if (thermalised) ti = ems_te;
+      else ti = pow(10.0, th[sp[SP_TI_IDX]]);
+      if (lane == 0) {
+        rec[0] = s[1] / four_pi; rec[1] = s[2] / s[0]; rec[2] = s[3] / s[0]; rec[3] = ems_te; rec[4] = ti;
+        for (int q = 5; q < BAYSAR_LINE_STRIDE; ++q) rec[q] = 0.0;
+      }
+    } else {  // XLine (linemodels.py:228-230)
+      if (lane == 0) {
+        rec[0] = pow(10.0, th[ul[UL_TAB_A]]);
+        for (int q = 1; q < BAYSAR_LINE_STRIDE; ++q) rec[q] = 0.0;
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- priors, in posterior_components order (posterior.py:108-161)
+  double* comp = a.components + n * (int64_t)(n_chords + n_pr) + n_chords;
+  for (int k = 0; k < n_pr; ++k) {
+    const int* pi = m.pr_i + k * PR_I_COUNT;
+    const double* pd = m.pr_d + k * PR_D_COUNT;
+    const int kind = pi[PR_KIND];
+    double val = 0.0;
+    if (kind == PRIOR_STATIC_PRESSURE) {  // priors.py:51-64
+      double s = 0.0;
+      for (int l = lane; l < L; l += 32) {
+        double pe = clip_lo(te_s[l], 0.01) * clip_lo(ne_s[l], 1.0);
+        s += low_pass(pe / 5e15, 1.0, 0.1);
+      }
+      val = warp_sum(s);
+    } else if (kind == PRIOR_NEUTRAL_FRACTION) {  // priors.py:83-101
+      double s = 0.0;
+      for (int l = lane; l < L; l += 32) {
+        double f0 = clip_lo(n0_s[l], 1.0) / ne_s[l];
+        s += high_pass(f0 / 5e-3, 1.0, 0.1);
+      }
+      val = warp_sum(s);
+    } else if (kind == PRIOR_STARK_TO_PEAK) {  // priors.py:646-667
+      const double* r = lines_n + pi[PR_I0] * BAYSAR_LINE_STRIDE;
+      double exc = high_pass(r[4] / nemax, 0.65, 0.075) * (1 - r[7]);
+      double rc = high_pass(r[2] / nemax, 0.65, 0.075) * r[7];
+      val = exc + rc;
+    } else if (kind == PRIOR_ANTIPROTON) {  // priors.py:14-24
+      double s = 0.0; int any_neg = 0;
+      for (int l = lane; l < L; l += 32) {
+        double ni = nm_s[l];
+        if (ni < 0) { any_neg = 1; double t = ni / 1e11; s += t * t; }
+      }
+      s = warp_sum(s);
+      any_neg = __any_sync(0xffffffffu, any_neg);
+      val = any_neg ? -0.5 * s : 0.0;
+    } else if (kind == PRIOR_MAIN_ION_FRACTION) {  // priors.py:27-48
+      double best = -1.7976931348623157e308; int bi = 0x7fffffff;
+      for (int l = lane; l < L; l += 32) {
+        double v = nm_s[l];
+        if (v > best) { best = v; bi = l; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (bi >= L) bi = 0;
+      const double ref = clip_lo(ne_s[bi], 1.0);
+      double s = 0.0;
+      for (int l = lane; l < L; l += 32) {
+        double nec = clip_lo(ne_s[l], 1.0);
+        double factor = clip_lo(nec / ref, 0.3);
+        s += high_pass(nm_s[l] / nec, factor * 0.8, 0.1);
+      }
+      val = warp_sum(s);
+    } else if (kind == PRIOR_CHARGE_STATE_ORDER) {  // priors.py:509-556
+      double cost = 0.0;
+      for (int e = 0; e < n_elem; ++e) {
+        for (int q = m.cso_off[e]; q + 1 < m.cso_off[e + 1]; ++q) {
+          double t0 = lines_n[m.cso_ul[q] * BAYSAR_LINE_STRIDE + 3];
+          double t1 = lines_n[m.cso_ul[q + 1] * BAYSAR_LINE_STRIDE + 3];
+          cost += high_pass(t1 - t0, 2.0, 0.2);
+        }
+      }
+      val = cost;
+    } else if (kind == PRIOR_WAVELENGTH_CAL) {  // priors.py:1046-1060 (always calwave_0)
+      double t0 = (pd[PR_D0] - th[pi[PR_I0]]) / pd[PR_D2];
+      double t1 = (pd[PR_D1] - th[pi[PR_I0] + 1]) / pd[PR_D3];
+      val = -0.5 * (t0 * t0) + -0.5 * (t1 * t1);
+    } else if (kind == PRIOR_INTENSITY_CAL) {  // priors.py:1063-1076
+      double t0 = (1.0 - pow(10.0, th[pi[PR_I0]])) / 0.2;
+      val = -0.5 * (t0 * t0);
+    } else if (kind == PRIOR_GAUSSIAN_IF) {  // priors.py:1079-1089
+      double t0 = (pow(10.0, th[pi[PR_I0]]) - 0.8) / 0.1;
+      val = -0.5 * (t0 * t0);
+    }
+    if (lane == 0) comp[k] = val;
+  }
+
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) st |= __shfl_xor_sync(0xffffffffu, st, o);
+  if (lane == 0) {
+    a.status[n] = st;
+    double* h = a.hdr + n * BAYSAR_HDR_STRIDE;
+    h[0] = nemax; h[1] = 0.0; h[2] = 0.0; h[3] = 0.0;
+  }
+}

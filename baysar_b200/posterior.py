@@ -1,0 +1,280 @@
+"""``BaysarPosterior`` — the drop-in boundary of the posterior-evaluation path.
+
+Same constructor and call protocol as the reference (`/root/reference/baysar/posterior.py:57-258`):
+
+    posterior = BaysarPosterior(input_dict, profile_function=None, priors=[], check_bounds=False, temper=1.0,
+                                curvature=None, print_errors=False, skip_test=False)
+    logp = posterior(theta)          # 1-D theta -> float, raising TypeError / ValueError like the reference
+    cost = posterior.cost(theta)
+
+plus the batched form the reference lacks: ``posterior(theta)`` with a 2-D ``(N, n_params)`` array (numpy, host) or
+CUDA tensor returns N log-posteriors evaluated by three CUDA kernel launches; per-sample failures come back as status
+flags (``posterior.last_status``) instead of exceptions.  Extra keyword arguments: ``atomic_data`` (provider, see
+``baysar_b200.atomic_data``) and ``device``.
+
+There is no CPU path: construction needs a CUDA device and the in-tree ``libbaysar_b200.so``.
+"""
+import numpy as np
+
+from . import runtime
+from .model import compile_model
+from .plasmas import PlasmaLine
+from .priors import (AntiprotonCost, CalibrationPrior, ChargeStateOrderPrior, GaussianInstrumentFunctionPrior,
+                     MainIonFractionCost, NeutralFractionCost, StarkToPeakPrior, StaticElectronPressureCost,
+                     WavelengthCalibrationPrior, _DevicePrior)
+from .spectrometers import BalmerHydrogenLine, SpectrometerChord, XLine
+
+# status bit -> (exception type, message) in the order the reference would hit them (include/baysar_b200.h)
+_STATUS = [
+    (0, TypeError, "Theta contains NaNs"), (1, TypeError, "Theta contains infinities"),
+    (2, ValueError, "impurity tau outside the ADAS tau grid"),
+    (3, ValueError, "Negative numbers in neutral density profile!"), (4, ValueError, "NaNs in the PECs!"),
+    (5, ValueError, "fwhm must be a positive scalar"), (6, TypeError, "NaNs/infs in line peaks"),
+    (7, ValueError, "Instrument function is not pixel normalised!"), (8, TypeError, "spectra contains NaNs/infs"),
+    (9, ValueError, "Area not conserved in convolution!"), (10, TypeError, "spectra contains NaNs/infs"),
+    (11, ValueError, "Some points of square_normalised_residuals are zero"),
+    (12, ValueError, "Some points of square_normalised_residuals are inf/nan"),
+    (13, ValueError, "logP is NaNs"), (14, ValueError, "logP is inf"), (15, ValueError, "lopP is positive"),
+]
+
+
+def build_components(plasma, input_dict, curvature=None, passed_priors=()):
+    """Chords, then the default priors in the reference's order (posterior.py:263-269, :108-165)."""
+    chords = [SpectrometerChord(plasma=plasma, refine=refine, chord_number=c)
+              for c, refine in enumerate(input_dict["refine"])]
+    priors = []
+    if curvature is not None:
+        raise NotImplementedError("CurvatureCost needs the MeshLine profile family (SURVEY.md §8f-4)")
+    if plasma.calibrate_wavelength:
+        for num in range(plasma.num_chords):
+            inmean = chords[num].x_data.mean()
+            indisp = np.diff(chords[0].x_data).mean()
+            priors.append(WavelengthCalibrationPrior([inmean, indisp], [2 * indisp, indisp * 0.05]))
+    if plasma.calibrate_intensity:
+        priors.append(CalibrationPrior())
+    if plasma.calibrate_instrument_function:
+        priors.append(GaussianInstrumentFunctionPrior())
+    priors.append(StaticElectronPressureCost())
+    if plasma.contains_hydrogen:
+        priors.append(NeutralFractionCost(species=plasma.hydrogen_species[0]))
+        balmer = [l for ch in chords for l in ch.lines if type(l) == BalmerHydrogenLine]
+        if balmer:
+            priors.append(StarkToPeakPrior(line=balmer[0]))
+    if len(plasma.impurities) > 0:
+        priors.append(AntiprotonCost())
+        priors.append(MainIonFractionCost())
+        priors.append(ChargeStateOrderPrior(chords, plasma))
+    for p in passed_priors:
+        if not isinstance(p, _DevicePrior):
+            raise NotImplementedError(f"user prior {type(p).__name__} has no device implementation; only the default "
+                                      "components of posterior.py:108-161 run on the CUDA path")
+        if not any(type(q) is type(p) for q in priors):
+            priors.append(p)
+    return chords, priors
+
+
+def set_sensible_bounds(plasma, chords, dcwl=2, ddisp=0.005):
+    """Data-driven theta bounds (reference posterior.py:271-356)."""
+    tb, sl = plasma.theta_bounds, plasma.slices
+    for c, chord in enumerate(chords):
+        if f"cal_{c}" in sl:
+            tb[sl[f"cal_{c}"]] = [-0.3, 0.3] if chord.y_data.max() > 1e6 else [8, 15]
+        if f"calwave_{c}" in sl:
+            cwl, disp = chord.x_data.mean(), np.diff(chord.x_data).mean()
+            tb[sl[f"calwave_{c}"]][0] = [cwl - dcwl, cwl + dcwl]
+            tb[sl[f"calwave_{c}"]][1] = [disp - ddisp, disp + ddisp]
+        level, spread = chord.y_data_continuum.mean(), chord.y_data_continuum.std()
+        lo, hi = max(level - spread, level / 10), min(level + spread, level * 10)
+        tb[sl[f"background_{c}"]] = [np.log10(lo), np.log10(hi)]
+    for tag in sl:
+        if tag.endswith("_dens"):
+            charge = float(tag.split("_")[-2])
+            top = tb[sl["electron_density"]][0, 1]
+            if charge != 0:
+                top, decades = top - np.log10(charge), 2
+            else:
+                decades = 3
+            tb[sl[tag]][0] = [top - decades, top]
+        if not plasma.thermalised and tag.endswith("_Ti"):
+            tb[sl[tag]][0] = [0, 1.7]
+    for chord in chords:
+        for line in chord.lines:
+            if type(line) == XLine:
+                line.estimate_ems_and_bounds(chord.x_data, chord.y_data)
+                tb[sl[line.line_tag]] = line.bounds
+    if np.isnan(tb).any():
+        raise ValueError("NaNs in theta bounds!")
+
+
+class BaysarPosterior:
+    def __init__(self, input_dict, profile_function=None, priors=[], check_bounds=False, temper=1.0, curvature=None,
+                 print_errors=False, skip_test=False, atomic_data=None, device=None):
+        self.check_init_inputs(priors, check_bounds, temper, curvature, print_errors)
+        self.input_dict = input_dict
+        self.plasma = PlasmaLine(input_dict=input_dict, profile_function=profile_function, atomic_data=atomic_data)
+        self.check_bounds, self.print_errors, self.temper = check_bounds, print_errors, temper
+        self.passed_priors, self.curvature = priors, curvature
+        self.nan_thetas, self.inf_thetas, self.positive_thetas, self.runtimes = [], [], [], []
+        self.last_proposal = None
+        self.last_status = None
+
+        self.chords, self.priors = build_components(self.plasma, input_dict, curvature, priors)
+        self.posterior_components = list(self.chords) + list(self.priors)
+        set_sensible_bounds(self.plasma, self.chords)
+
+        self.blob, self.model_info = compile_model(self.plasma, self.chords, self.priors)
+        if device is None:
+            import torch
+
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self.device = int(device)
+        self.model = runtime.DeviceModel(self.blob, self.device)  # raises without a GPU / library: no CPU fallback
+        for c in self.chords:
+            c._posterior = self
+        for k, p in enumerate(self.priors):
+            p._posterior, p._column = self, len(self.chords) + k
+        self.plasma._evaluator = self._evaluate_los
+        self.init_test(skip_test)
+
+    # ------------------------------------------------------------------------------------------ reference protocol
+    def check_init_inputs(self, priors, check_bounds, temper, curvature, print_errors):
+        """posterior.py:167-195."""
+        if len(priors) > 0 and type(priors) is not list:
+            raise TypeError("If priors are being passed then it must be a list of functions")
+        if type(check_bounds) is not bool:
+            raise TypeError("check_bounds must be True or False and is False by default")
+        if not np.isreal(temper):
+            raise TypeError("temper must be a real number")
+        if temper < 0:
+            raise ValueError("temper must be positive (should, but doesn't have to, be greater than 1)")
+        if curvature is not None:
+            if type(curvature) not in (int, float, np.int64, np.float64):
+                raise TypeError("curvature must be an int or float")
+            if curvature < 1:
+                raise ValueError("curvature must be greater than 1")
+        if type(print_errors) is not bool:
+            raise TypeError("print_errors must be True or False and is False by default")
+
+    def got_p(self, comp):
+        return any(type(p) is comp for p in self.posterior_components)
+
+    def init_test(self, skip_test):
+        """One evaluation at a random start must give a finite negative logP (posterior.py:197-217)."""
+        start = self.random_start()
+        run_check = self(start, skip_test)
+        if not (np.isreal(run_check) and -1e50 < run_check and run_check < 0):
+            err = ValueError("Posterior is not evalauating correctly. logP =", run_check, "from input=", start)
+            if skip_test:
+                print(err)
+            else:
+                raise err
+
+    def __call__(self, theta, skip_error=False):
+        import torch
+
+        if isinstance(theta, torch.Tensor):
+            if theta.dim() == 2:
+                return self.logp_batch(theta)
+            theta = theta.detach().cpu().numpy()
+        arr = np.asarray(theta, dtype=float)
+        if arr.ndim == 2:
+            logp, status = self.model.eval_logp_host(arr)
+            self.last_status = status
+            return logp
+        theta = list(arr)
+        self.last_proposal = theta
+        if not skip_error:
+            self.check_call_input(theta, skip_error)
+        logp, status = self.model.eval_logp_host(arr[None, :])
+        self.last_status = status
+        prob = float(logp[0])
+        self._publish_line_attributes(arr)
+        if not skip_error:
+            self._raise_from_status(int(status[0]), theta=theta)
+        self.last_proposal_logp = prob
+        return prob
+
+    def check_call_input(self, theta, skip_error):
+        if any(np.isnan(theta)):
+            raise TypeError("Theta contains NaNs")
+        if any(np.isinf(theta)):
+            raise TypeError("Theta contains infinities")
+        if skip_error not in (True, False):
+            raise TypeError("skip_error not in (True, False)")
+
+    def _raise_from_status(self, status, theta=None, mask=0xFFFF):
+        status &= mask
+        if not status:
+            return
+        for bit, exc, msg in _STATUS:
+            if status & (1 << bit):
+                if theta is not None and bit in (13, 14, 15):
+                    {13: self.nan_thetas, 14: self.inf_thetas, 15: self.positive_thetas}[bit].append(theta)
+                raise exc(msg)
+
+    def cost(self, theta):
+        return -self.__call__(theta)
+
+    def random_start(self, order=1, flat=False):
+        """Uniform draw inside theta_bounds, background re-drawn near the measured continuum (posterior.py:358-395).
+        Consumes the global numpy RNG in the same order as the reference."""
+        start = [np.mean(np.random.uniform(b[0], b[1], size=order)) for b in self.plasma.theta_bounds]
+        if flat:
+            for param in ("electron_density", "electron_temperature"):
+                s = self.plasma.slices[param]
+                for index in np.arange(s.start, s.stop):
+                    start[index] = start[s.start]
+        for chord in self.chords:
+            mean = np.log10(np.mean(chord.y_data_continuum))
+            start[self.plasma.slices["background_" + str(chord.chord_number)].start] = \
+                np.random.uniform(mean - 0.1, mean + 0.1)
+        return np.array(start)
+
+    def random_sample(self, number=1, order=1, flat=False):
+        """N independent evaluations sorted by logP (posterior.py:463-472) — one batched launch here."""
+        thetas = np.array([self.random_start(order, flat) for _ in range(number)])
+        logp = self(thetas)
+        keep = np.isfinite(logp) & (self.last_status == 0)
+        order_ = np.argsort(-logp[keep])
+        return thetas[keep][order_], logp[keep][order_]
+
+    # ------------------------------------------------------------------------------------------ batched device API
+    def _as_device(self, theta):
+        import torch
+
+        if isinstance(theta, torch.Tensor):
+            return theta.to(device=f"cuda:{self.device}", dtype=torch.float64)
+        return torch.as_tensor(np.asarray(theta, dtype=float), device=f"cuda:{self.device}")
+
+    def logp_batch(self, theta, return_status=False):
+        """theta: CUDA float64 tensor (N, n_params) -> CUDA tensor of N log-posteriors (no host round trip)."""
+        logp, status, _ = self.model.eval_logp(self._as_device(theta))
+        self.last_status_device = status
+        return (logp, status) if return_status else logp
+
+    def components_batch(self, theta):
+        """-> (components [N, n_chords + n_priors], status) as numpy arrays, reference posterior_components order."""
+        _, status, comps = self.model.eval_logp(self._as_device(theta), want_components=True)
+        return comps.cpu().numpy(), status.cpu().numpy().astype(np.uint32)
+
+    def spectra_batch(self, theta, chord=0, want_fine=False):
+        spectra, status, pre, post = self.model.eval_spectra(self._as_device(theta), chord, want_fine)
+        if want_fine:
+            return spectra.cpu().numpy(), status.cpu().numpy().astype(np.uint32), pre.cpu().numpy(), post.cpu().numpy()
+        return spectra.cpu().numpy(), status.cpu().numpy().astype(np.uint32)
+
+    def lines_batch(self, theta, want_profiles=False):
+        lines, status, prof = self.model.eval_lines(self._as_device(theta), want_profiles)
+        out = lines.cpu().numpy(), status.cpu().numpy().astype(np.uint32)
+        return out + (prof.cpu().numpy(),) if want_profiles else out
+
+    def _evaluate_los(self, theta):
+        lines, _, prof = self.lines_batch(np.asarray(theta, dtype=float)[None], want_profiles=True)
+        return dict(ne=prof[0, 0], te=prof[0, 1], main_ion_density=prof[0, 2], n0=prof[0, 3], lines=lines[0])
+
+    def _publish_line_attributes(self, theta):
+        """After a scalar call, expose the reference's line attributes and plasma_state (priors/demos read them)."""
+        out = self.plasma.update_plasma_state(theta)
+        for c, chord in enumerate(self.chords):
+            for k, line in enumerate(chord.lines):
+                line._publish(out["lines"][self.model_info["chord_line_uline"][c][k]])

@@ -1,0 +1,102 @@
+"""Default prior / cost components as descriptors.
+
+The reference evaluates each prior as a zero-argument Python callable reading the shared ``plasma_state``
+(`/root/reference/baysar/priors.py`).  Here every default component (`posterior.py:108-161`) is a small descriptor
+that the model compiler turns into one row of the device prior table; the arithmetic runs in the CUDA line-of-sight
+kernel (csrc/los_stage.cuh, citing priors.py per branch).  ``prior()`` returns the value at the posterior's last
+scalar theta so that reference-style introspection (``for p in posterior.posterior_components: p()``) still works.
+"""
+import numpy as np
+
+
+def gaussian_high_pass_cost(tmp, threshold, error):
+    """Everything above the threshold is good (priors.py:4-6)."""
+    return -0.5 * (max([0, threshold - tmp]) / error) ** 2
+
+
+def gaussian_low_pass_cost(tmp, threshold, error):
+    """Everything below the threshold is good (priors.py:9-11)."""
+    return -0.5 * (max([0, tmp - threshold]) / error) ** 2
+
+
+class _DevicePrior:
+    kind = None  # name of the BaysarPriorKind enumerator in csrc/layout.h
+
+    def __init__(self):
+        self._posterior = None
+        self._column = None
+
+    def __call__(self):
+        post = self._posterior
+        if post is None or post.last_proposal is None:
+            raise RuntimeError("call the posterior with a theta first")
+        comps, _ = post.components_batch(np.asarray(post.last_proposal, dtype=float)[None])
+        return float(comps[0, self._column])
+
+
+class StaticElectronPressureCost(_DevicePrior):
+    kind = "PRIOR_STATIC_PRESSURE"  # priors.py:51-64 (threshold 5e15, sigma 0.1)
+
+
+class NeutralFractionCost(_DevicePrior):
+    kind = "PRIOR_NEUTRAL_FRACTION"  # priors.py:83-101 (threshold 5e-3, sigma 0.1)
+
+    def __init__(self, species):
+        super().__init__()
+        self.species = species
+
+
+class StarkToPeakPrior(_DevicePrior):
+    kind = "PRIOR_STARK_TO_PEAK"  # priors.py:646-667 (mean 0.65, sigma 0.075)
+
+    def __init__(self, line):
+        super().__init__()
+        self.line = line
+
+
+class AntiprotonCost(_DevicePrior):
+    kind = "PRIOR_ANTIPROTON"  # priors.py:14-24 (sigma 1e11)
+
+
+class MainIonFractionCost(_DevicePrior):
+    kind = "PRIOR_MAIN_ION_FRACTION"  # priors.py:27-48 (threshold 0.8, sigma 0.1)
+
+
+class ChargeStateOrderPrior(_DevicePrior):
+    kind = "PRIOR_CHARGE_STATE_ORDER"  # priors.py:509-556 (mean 2.0, sigma 0.2)
+
+    def __init__(self, chords, plasma):
+        super().__init__()
+        # first line of every impurity ion, in chord then line order (priors.py:515-524)
+        self.impurity_indicies_dict = {}
+        for c, chord in enumerate(chords):
+            for i, l in enumerate(chord.lines):
+                sp = getattr(l, "species", None)
+                if sp in plasma.impurity_species and sp not in self.impurity_indicies_dict:
+                    self.impurity_indicies_dict[sp] = (c, i)
+
+    def ordered_lines(self, plasma):
+        """Per element: (chord, line) pairs ordered by charge state — prefix match on the element name (Q10)."""
+        idx = self.impurity_indicies_dict
+        out = []
+        for elem in plasma.impurities:
+            ions = sorted([ion for ion in idx if ion.startswith(elem)], key=lambda x: idx[x])
+            ions = sorted(ions, key=lambda x: float(x.split("_")[1]))
+            out.append([idx[ion] for ion in ions])
+        return out
+
+
+class WavelengthCalibrationPrior(_DevicePrior):
+    kind = "PRIOR_WAVELENGTH_CAL"  # priors.py:1046-1060 — always reads calwave_0 (Q11)
+
+    def __init__(self, mean, std):
+        super().__init__()
+        self.mean, self.std = mean, std
+
+
+class CalibrationPrior(_DevicePrior):
+    kind = "PRIOR_INTENSITY_CAL"  # priors.py:1063-1076 (mean 1, std 0.2)
+
+
+class GaussianInstrumentFunctionPrior(_DevicePrior):
+    kind = "PRIOR_GAUSSIAN_IF"  # priors.py:1079-1089 (mean 0.8, std 0.1)

@@ -1,0 +1,168 @@
+"""ctypes binding of the C ABI (include/baysar_b200.h) and the in-tree build of the CUDA library.
+
+PyTorch supplies device memory and streams (plumbing); every computation on the posterior path happens inside
+``libbaysar_b200.so``.  There is NO CPU fallback: if the library is missing or no CUDA device is present the
+functions here raise.
+"""
+import ctypes
+import os
+import pathlib
+import subprocess
+
+PKG = pathlib.Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB_PATH = PKG / "libbaysar_b200.so"
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "--compiler-options", "-fPIC", "-shared"]
+
+
+def build_library(force=False, verbose=False):
+    """Compile csrc/baysar_abi.cu for sm_100a into the package directory (nvcc cross-compiles without a GPU)."""
+    sources = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h"))
+    if LIB_PATH.exists() and not force:
+        newest = max(s.stat().st_mtime for s in sources)
+        if LIB_PATH.stat().st_mtime >= newest:
+            return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, "-Xptxas", "-v", "-o", str(LIB_PATH), str(CSRC / "baysar_abi.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def library():
+    """Load the CUDA library; fail loudly when it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the posterior path has no CPU fallback)")
+    lib = ctypes.CDLL(str(LIB_PATH))
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    lib.baysar_model_create.argtypes = [vp, ctypes.c_size_t, i32, ctypes.POINTER(vp)]
+    lib.baysar_model_create.restype = i32
+    lib.baysar_model_destroy.argtypes = [vp]
+    lib.baysar_model_destroy.restype = None
+    lib.baysar_model_query.argtypes = [vp, i32, i32]
+    lib.baysar_model_query.restype = i64
+    lib.baysar_eval_logp.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.baysar_eval_logp.restype = i32
+    lib.baysar_eval_spectra.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp]
+    lib.baysar_eval_spectra.restype = i32
+    lib.baysar_eval_lines.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.baysar_eval_lines.restype = i32
+    lib.baysar_eval_logp_host.argtypes = [vp, vp, i64, vp, vp]
+    lib.baysar_eval_logp_host.restype = i32
+    lib.baysar_last_error.restype = ctypes.c_char_p
+    lib.baysar_version.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = ["baysar_model_create", "baysar_model_destroy", "baysar_model_query", "baysar_eval_logp",
+                    "baysar_eval_spectra", "baysar_eval_lines", "baysar_eval_logp_host", "baysar_last_error",
+                    "baysar_version"]
+
+
+class DeviceModel:
+    """One compiled model resident in one GPU's HBM."""
+
+    def __init__(self, blob, device=0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("baysar_b200 needs a CUDA device: the posterior path has no CPU fallback")
+        self.lib = library()
+        self.torch = torch
+        self.device = int(device)
+        self.handle = ctypes.c_void_p()
+        buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        rc = self.lib.baysar_model_create(ctypes.cast(buf, ctypes.c_void_p), len(blob), self.device,
+                                          ctypes.byref(self.handle))
+        self._check(rc)
+        q = lambda what, arg=0: int(self.lib.baysar_model_query(self.handle, what, arg))  # noqa: E731
+        self.n_params, self.n_chords, self.n_ulines, self.n_priors = q(0), q(1), q(2), q(3)
+        self.n_los = q(8)
+        self.pixels = [q(6, c) for c in range(self.n_chords)]
+        self.fine = [q(7, c) for c in range(self.n_chords)]
+        self.launches_per_eval = q(9)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("baysar_b200: " + self.lib.baysar_last_error().decode())
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.baysar_model_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _theta(self, theta):
+        t = self.torch
+        if theta.dtype != t.float64 or not theta.is_cuda or theta.dim() != 2 or theta.shape[1] != self.n_params:
+            raise ValueError(f"theta must be a CUDA float64 tensor of shape (N, {self.n_params})")
+        return theta.contiguous()
+
+    def eval_logp(self, theta, want_components=False):
+        t = self.torch
+        theta = self._theta(theta)
+        n = theta.shape[0]
+        logp = t.empty(n, dtype=t.float64, device=theta.device)
+        status = t.empty(n, dtype=t.int32, device=theta.device)
+        comps = t.empty((n, self.n_chords + self.n_priors), dtype=t.float64, device=theta.device) if want_components else None
+        self._check(self.lib.baysar_eval_logp(self.handle, theta.data_ptr(), n, logp.data_ptr(), status.data_ptr(),
+                                              comps.data_ptr() if comps is not None else None, self._stream()))
+        return logp, status, comps
+
+    def eval_spectra(self, theta, chord, want_fine=False):
+        t = self.torch
+        theta = self._theta(theta)
+        n = theta.shape[0]
+        spectra = t.empty((n, self.pixels[chord]), dtype=t.float64, device=theta.device)
+        status = t.empty(n, dtype=t.int32, device=theta.device)
+        pre = t.empty((n, self.fine[chord]), dtype=t.float32, device=theta.device) if want_fine else None
+        post = t.empty((n, self.fine[chord]), dtype=t.float32, device=theta.device) if want_fine else None
+        self._check(self.lib.baysar_eval_spectra(self.handle, theta.data_ptr(), n, chord, spectra.data_ptr(),
+                                                 pre.data_ptr() if want_fine else None,
+                                                 post.data_ptr() if want_fine else None, status.data_ptr(),
+                                                 self._stream()))
+        return spectra, status, pre, post
+
+    def eval_lines(self, theta, want_profiles=False):
+        t = self.torch
+        theta = self._theta(theta)
+        n = theta.shape[0]
+        lines = t.empty((n, max(self.n_ulines, 1), 12), dtype=t.float64, device=theta.device)
+        status = t.empty(n, dtype=t.int32, device=theta.device)
+        prof = t.empty((n, 4, self.n_los), dtype=t.float64, device=theta.device) if want_profiles else None
+        self._check(self.lib.baysar_eval_lines(self.handle, theta.data_ptr(), n, lines.data_ptr(),
+                                               prof.data_ptr() if want_profiles else None, status.data_ptr(),
+                                               self._stream()))
+        return lines, status, prof
+
+    def eval_logp_host(self, theta_np):
+        """HOST buffers in, HOST buffers out: the copies happen inside the C call (the `e2e` path of bench.py)."""
+        import numpy as np
+
+        theta_np = np.ascontiguousarray(theta_np, dtype=np.float64)
+        n = theta_np.shape[0]
+        logp = np.empty(n, dtype=np.float64)
+        status = np.empty(n, dtype=np.uint32)
+        self._check(self.lib.baysar_eval_logp_host(self.handle, theta_np.ctypes.data, n, logp.ctypes.data,
+                                                   status.ctypes.data))
+        return logp, status

@@ -1,0 +1,99 @@
+/*
+ * baysar_b200 — C ABI of the B200-native BaySAR posterior-evaluation path.
+ *
+ * The reference (dgahle/baysar) is pure Python and has no FFI: its boundary for this path is the duck-typed call
+ * `BaysarPosterior.__call__(theta) -> float` (reference baysar/posterior.py:219-235) plus the per-chord
+ * `SpectrometerChord.forward_model()` (baysar/spectrometers.py:197-335) and the per-line diagnostic attributes
+ * read by priors and demos (baysar/linemodels.py:800-836, :407-426).  Each entry point below replaces one of those
+ * calls for a whole batch of thetas; the Python host side (`baysar_b200/posterior.py`) binds them with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `theta`, output and status pointer is a DEVICE pointer unless the
+ *     function name ends in `_host`;
+ *   - the caller owns all buffers; the model owns its device constants and a workspace that grows on demand;
+ *   - return value 0 = ok, non-zero = error (message via baysar_last_error(), thread-local); nothing throws;
+ *   - per-sample numerical failures (the reference's `raise` sites) are reported as bit flags in `status[N]`
+ *     (BAYSAR_ST_*), never as a return code; logp of a failed sample is whatever arithmetic produced (NaN/inf);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous w.r.t.
+ *     the host except the `_host` variants;
+ *   - a model is immutable after creation: evaluation is re-entrant across models; one model (and its
+ *     workspace) must not be used from two streams at the same time.
+ */
+#ifndef BAYSAR_B200_H
+#define BAYSAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct baysar_model baysar_model_t;
+
+/* status bits: one per reference raise site (file:line of the reference in the comment) */
+#define BAYSAR_ST_THETA_NAN        (1u << 0)  /* posterior.py:239-240  TypeError  */
+#define BAYSAR_ST_THETA_INF        (1u << 1)  /* posterior.py:242-243  TypeError  */
+#define BAYSAR_ST_TAU_RANGE        (1u << 2)  /* plasmas.py:1410-1429, linemodels.py:454-467  ValueError/IndexError */
+#define BAYSAR_ST_N0_NAN           (1u << 3)  /* linemodels.py:768-769  ValueError */
+#define BAYSAR_ST_PEC_NAN          (1u << 4)  /* linemodels.py:790-796  ValueError */
+#define BAYSAR_ST_FWHM_NONPOS      (1u << 5)  /* lineshapes.py:97-103   ValueError */
+#define BAYSAR_ST_LINE_NAN         (1u << 6)  /* linemodels.py:430-441, :860-863  TypeError/ValueError */
+#define BAYSAR_ST_IF_NORM          (1u << 7)  /* spectrometers.py:246-250  ValueError */
+#define BAYSAR_ST_CONV_NANINF      (1u << 8)  /* spectrometers.py:279-282  TypeError  */
+#define BAYSAR_ST_AREA             (1u << 9)  /* spectrometers.py:292-297  ValueError */
+#define BAYSAR_ST_SPECTRA_NANINF   (1u << 10) /* spectrometers.py:330-333  TypeError  */
+#define BAYSAR_ST_RES_ZERO         (1u << 11) /* spectrometers.py:169-170  ValueError */
+#define BAYSAR_ST_RES_NANINF       (1u << 12) /* spectrometers.py:172-183  ValueError */
+#define BAYSAR_ST_LOGP_NAN         (1u << 13) /* posterior.py:250-252  ValueError */
+#define BAYSAR_ST_LOGP_INF         (1u << 14) /* posterior.py:253-255  ValueError */
+#define BAYSAR_ST_LOGP_POSITIVE    (1u << 15) /* posterior.py:256-258  ValueError */
+#define BAYSAR_ST_WINDOW_CLAMPED   (1u << 16) /* not a reference error: a theta-dependent kernel was wider than
+                                                 the shared-memory halo sized from the parameter bounds */
+
+/* number of doubles per (theta, line) record returned by baysar_eval_lines */
+#define BAYSAR_LINE_STRIDE 12
+/* record layout, by line kind:
+ *   Balmer (kind 0): rec_sum, exc_sum, rec_ne, rec_te, exc_ne, exc_te, ti, f_rec, ems_ne, ems_te, emission_fitted, 0
+ *   ADAS406 (kind 1): emission_fitted, ems_ne, ems_conc, ems_te, ti, 0...
+ *   XLine (kind 2):   emission_fitted, 0...                                                                       */
+
+/* Build a model from the descriptor blob produced by baysar_b200.model.compile_model (format: csrc/layout.h);
+ * copies every constant table to HBM on `device` once.   Replaces BaysarPosterior.__init__'s object graph. */
+int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar_model_t** out);
+void baysar_model_destroy(baysar_model_t* model);
+
+/* Sizes a caller needs to allocate outputs. what: 0 n_params, 1 n_chords, 2 n_unique_lines, 3 n_priors,
+ * 4 max pixels per chord, 5 max fine-grid points per chord, 6 pixels of chord `arg`, 7 fine points of chord `arg`,
+ * 8 LOS points, 9 kernels launched per baysar_eval_logp call. */
+int64_t baysar_model_query(const baysar_model_t* model, int what, int arg);
+
+/* logp[n] = BaysarPosterior.__call__(theta[n])  (posterior.py:219-235): theta [N][n_params] row-major doubles.
+ * Optional outputs (may be NULL): status[N]; components [N][n_chords + n_priors] in the reference's
+ * posterior_components order (chord log-likelihoods, then priors). */
+int baysar_eval_logp(baysar_model_t* model, const double* theta, int64_t n, double* logp, uint32_t* status,
+                     double* components, void* stream);
+
+/* spectra[n][p] = SpectrometerChord.forward_model() of chord `chord` (spectrometers.py:197-335), P doubles per
+ * theta.  fine_pre / fine_post (may be NULL): the fine-grid spectrum before the instrument convolution (after the
+ * intensity calibration) and after convolution + renormalisation + background, F floats per theta. */
+int baysar_eval_spectra(baysar_model_t* model, const double* theta, int64_t n, int chord, double* spectra,
+                        float* fine_pre, float* fine_post, uint32_t* status, void* stream);
+
+/* lines [N][n_unique_lines][BAYSAR_LINE_STRIDE]: the line-of-sight stage scalars the reference exposes as line
+ * attributes (linemodels.py:800-836, :407-426); profiles (may be NULL) [N][4][L]: ne, Te, main-ion density, n0. */
+int baysar_eval_lines(baysar_model_t* model, const double* theta, int64_t n, double* lines, double* profiles,
+                      uint32_t* status, void* stream);
+
+/* Convenience for callers with HOST buffers (what a scalar `posterior(theta)` call or an emcee vectorised
+ * call hands over): copies theta H2D, evaluates, copies logp/status D2H, synchronises. */
+int baysar_eval_logp_host(baysar_model_t* model, const double* theta_host, int64_t n, double* logp_host,
+                          uint32_t* status_host);
+
+const char* baysar_last_error(void);
+const char* baysar_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAYSAR_B200_H */
