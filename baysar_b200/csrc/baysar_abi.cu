@@ -43,6 +43,9 @@ struct baysar_model {
   double* logp_stage = nullptr;
   int64_t stage_cap = 0;
   size_t chord_smem_max = 0;
+  // optional per-stage timing (bench.py roofline): 4 events per eval_logp call while profiling is on
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
 };
 
 namespace {
@@ -53,6 +56,48 @@ struct SectionTable {
   const void* ptr(int s) const { return base + hdr[3 + 2 * s]; }
   int64_t count(int s) const { return hdr[3 + 2 * s + 1]; }
 };
+
+// Peak-rate probes for the roofline denominators MEASURED_PEAKS.json does not carry (FP32 FMA, MUFU, FP64 FMA):
+// 16 independent dependency chains per thread, enough resident warps to saturate the pipe.
+__global__ void microbench_ffma_kernel(float* out, int iters, float a) {
+  float v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = threadIdx.x * 1e-3f + k;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = fmaf(v[k], a, 0.5f);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += v[k];
+  if (s == 12345.678f) out[threadIdx.x] = s;
+}
+__global__ void microbench_mufu_kernel(float* out, int iters, float a) {
+  float v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = threadIdx.x * 1e-3f + k + 1.f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(v[k]) : "f"(v[k]));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += v[k];
+  if (s == 12345.678f) out[threadIdx.x] = s * a;
+}
+__global__ void microbench_dfma_kernel(double* out, int iters, double a) {
+  double v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = threadIdx.x * 1e-3 + k;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = fma(v[k], a, 0.5);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += v[k];
+  if (s == 12345.678) out[threadIdx.x] = s;
+}
 
 int ensure_workspace(baysar_model* m, int64_t n) {
   if (n <= m->cap) return 0;
@@ -202,6 +247,7 @@ void baysar_model_destroy(baysar_model_t* m) {
   cudaSetDevice(m->device);
   cudaFree(m->blob_dev); cudaFree(m->lines); cudaFree(m->comps); cudaFree(m->hdr); cudaFree(m->status);
   cudaFree(m->theta_stage); cudaFree(m->logp_stage);
+  for (cudaEvent_t ev : m->prof_events) cudaEventDestroy(ev);
   delete m;
 }
 
@@ -232,12 +278,24 @@ int baysar_eval_logp(baysar_model_t* m, const double* theta, int64_t n, double* 
   if (ensure_workspace(m, n)) return 1;
   uint32_t* st = status ? status : m->status;
   double* comps = components ? components : m->comps;
+  auto mark = [&]() -> int {
+    if (!m->profiling) return 0;
+    cudaEvent_t ev;
+    CUDA_OK(cudaEventCreate(&ev));
+    CUDA_OK(cudaEventRecord(ev, stream));
+    m->prof_events.push_back(ev);
+    return 0;
+  };
+  if (mark()) return 1;
   if (launch_los(m, theta, n, m->lines, comps, nullptr, st, stream)) return 1;
+  if (mark()) return 1;
   if (launch_chords(m, theta, n, 0, (int)m->I[I_N_CHORDS], m->lines, comps, nullptr, nullptr, nullptr, st, stream))
     return 1;
+  if (mark()) return 1;
   const int ncols = (int)(m->I[I_N_CHORDS] + m->I[I_N_PRIORS]);
   finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(comps, ncols, n, logp, st);
   CUDA_OK(cudaGetLastError());
+  if (mark()) return 1;
   return 0;
 }
 
@@ -285,6 +343,65 @@ int baysar_eval_logp_host(baysar_model_t* m, const double* theta_host, int64_t n
   if (status_host)
     CUDA_OK(cudaMemcpyAsync(status_host, m->status, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, 0));
   CUDA_OK(cudaStreamSynchronize(0));
+  return 0;
+}
+
+int baysar_model_set_profiling(baysar_model_t* m, int on) {
+  if (!m) return fail("null model");
+  for (cudaEvent_t ev : m->prof_events) cudaEventDestroy(ev);
+  m->prof_events.clear();
+  m->profiling = on != 0;
+  return 0;
+}
+
+int baysar_model_get_profile(baysar_model_t* m, double* stage_ms, int64_t* calls) {
+  if (!m || !stage_ms || !calls) return fail("null argument");
+  CUDA_OK(cudaSetDevice(m->device));
+  stage_ms[0] = stage_ms[1] = stage_ms[2] = 0.0;
+  *calls = (int64_t)(m->prof_events.size() / 4);
+  for (size_t c = 0; c + 3 < m->prof_events.size(); c += 4) {
+    CUDA_OK(cudaEventSynchronize(m->prof_events[c + 3]));
+    for (int k = 0; k < 3; ++k) {
+      float ms = 0.f;
+      CUDA_OK(cudaEventElapsedTime(&ms, m->prof_events[c + k], m->prof_events[c + k + 1]));
+      stage_ms[k] += ms;
+    }
+  }
+  for (cudaEvent_t ev : m->prof_events) cudaEventDestroy(ev);
+  m->prof_events.clear();
+  return 0;
+}
+
+int baysar_microbench(int device, int what, double* result) {
+  if (!result) return fail("null argument");
+  CUDA_OK(cudaSetDevice(device));
+  int sms = 0;
+  CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  float* out = nullptr;
+  CUDA_OK(cudaMalloc(&out, sizeof(float) * 1024));
+  const int iters = 4096, blocks = sms * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_OK(cudaEventRecord(e0, 0));
+    if (what == 0) microbench_ffma_kernel<<<blocks, threads>>>(out, iters, 1.0001f);
+    else if (what == 1) microbench_mufu_kernel<<<blocks, threads>>>(out, iters, 1.0001f);
+    else microbench_dfma_kernel<<<blocks, threads>>>(reinterpret_cast<double*>(out), iters, 1.0001);
+    CUDA_OK(cudaEventRecord(e1, 0));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    // ops per thread per iteration: 16 independent chains x 1 instruction
+    double ops = (double)blocks * threads * (double)iters * 16.0;
+    double rate = ops / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *result = what == 1 ? best : 2.0 * best;  // FMA = 2 flop; MUFU counted as ops
   return 0;
 }
 

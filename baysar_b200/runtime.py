@@ -60,6 +60,12 @@ def library():
     lib.baysar_eval_lines.restype = i32
     lib.baysar_eval_logp_host.argtypes = [vp, vp, i64, vp, vp]
     lib.baysar_eval_logp_host.restype = i32
+    lib.baysar_model_set_profiling.argtypes = [vp, i32]
+    lib.baysar_model_set_profiling.restype = i32
+    lib.baysar_model_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
+    lib.baysar_model_get_profile.restype = i32
+    lib.baysar_microbench.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double)]
+    lib.baysar_microbench.restype = i32
     lib.baysar_last_error.restype = ctypes.c_char_p
     lib.baysar_version.restype = ctypes.c_char_p
     _lib = lib
@@ -68,7 +74,19 @@ def library():
 
 EXPORTED_SYMBOLS = ["baysar_model_create", "baysar_model_destroy", "baysar_model_query", "baysar_eval_logp",
                     "baysar_eval_spectra", "baysar_eval_lines", "baysar_eval_logp_host", "baysar_last_error",
-                    "baysar_version"]
+                    "baysar_version", "baysar_model_set_profiling", "baysar_model_get_profile", "baysar_microbench"]
+
+
+def microbench(device=0):
+    """Measured FP32-FMA / MUFU / FP64-FMA peak rates of this GPU (flop/s, op/s, flop/s)."""
+    lib = library()
+    out = {}
+    for what, key in ((0, "fp32_fma_flops"), (1, "mufu_ops"), (2, "fp64_fma_flops")):
+        val = ctypes.c_double()
+        if lib.baysar_microbench(int(device), what, ctypes.byref(val)) != 0:
+            raise RuntimeError("baysar_b200: " + lib.baysar_last_error().decode())
+        out[key] = val.value
+    return out
 
 
 class DeviceModel:
@@ -154,6 +172,16 @@ class DeviceModel:
                                                prof.data_ptr() if want_profiles else None, status.data_ptr(),
                                                self._stream()))
         return lines, status, prof
+
+    def set_profiling(self, on):
+        self._check(self.lib.baysar_model_set_profiling(self.handle, int(bool(on))))
+
+    def get_profile(self):
+        """-> (per-stage total ms [LOS, chord, finalize], number of eval_logp calls) since profiling was enabled."""
+        ms = (ctypes.c_double * 3)()
+        calls = ctypes.c_int64()
+        self._check(self.lib.baysar_model_get_profile(self.handle, ms, ctypes.byref(calls)))
+        return [ms[0], ms[1], ms[2]], int(calls.value)
 
     def eval_logp_host(self, theta_np):
         """HOST buffers in, HOST buffers out: the copies happen inside the C call (the `e2e` path of bench.py)."""

@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the BaySAR posterior-evaluation path on B200 (metric: log-posterior evals/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload balmer_series|multi_species]
+
+A "step" is one pass of the hot path (LOS stage -> chord stage -> finalize, three kernel launches) over one batch
+of synthetic thetas drawn uniformly inside the posterior's theta bounds.  Default workload = BASELINE.json
+configs[1] (`demo/balmer_series.py`, 4096 thetas per GPU per step).
+
+* `value`       evals/s with thetas resident in HBM (CUDA events around each step, max over ranks);
+* `e2e`         the same metric through the reference-facing call `posterior(theta_host_array)` with pinned HOST
+                buffers: H2D copy of theta and D2H read of logP + status inside the timed region;
+* `roofline`    for the dominant kernel (chord stage): executed FP32 flop per launch / its mean duration, against the
+                FP32-FMA peak measured in the same run by the library's micro-benchmark (MEASURED_PEAKS.json carries
+                no FP32 figure); the SURVEY's dense-semantics flop count is reported beside it;
+* `cpu_baseline` the oracle port (`oracle/numpy_port.py`, kind "port") on the box's host cores, bounded sample.
+
+With `--impl reference` the CPU oracle port is the thing timed (all host cores), on the same workload and metric.
+Under torchrun (N > 1) every rank evaluates its own 4096-theta shard (weak scaling) and the per-walker
+log-posteriors are all-gathered over NCCL inside the timed region, as an ensemble-sampler step needs.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "log-posterior evals/sec"
+UNIT = "evals/s"
+BATCH_PER_GPU = {"balmer_series": 4096, "multi_species": 65536, "multi_species_32chords": 4096, "aug_demo": 4096}
+
+
+def get_workload(name):
+    from baysar_b200 import configs
+
+    if name == "balmer_series":
+        return configs.balmer_series()
+    if name == "multi_species":
+        return configs.multi_species(1)
+    if name == "multi_species_32chords":
+        return configs.multi_species(32)
+    if name == "aug_demo":
+        return configs.aug_demo()
+    raise SystemExit(f"unknown workload {name}")
+
+
+def draw_thetas(bounds, n, seed):
+    rng = np.random.default_rng(seed)
+    lo, hi = bounds[:, 0], bounds[:, 1]
+    return lo + rng.random((n, len(lo))) * (hi - lo)
+
+
+# ----------------------------------------------------------------------------------------------- CPU oracle legs
+def _oracle_worker(args):
+    name, thetas = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from baysar_b200.atomic_data import SyntheticADAS
+    from baysar_b200.input_functions import make_input_dict
+    from oracle.numpy_port import EsymmtricCauchyPlasma, OracleError, OraclePosterior
+
+    wl = get_workload(name)
+    prof = EsymmtricCauchyPlasma(x=wl.los) if wl.los is not None else None
+    post = OraclePosterior(make_input_dict(**wl.input_kwargs), SyntheticADAS(), prof)
+    post.evaluate(thetas[0]) if len(thetas) else None  # warm-up
+    t0 = time.perf_counter()
+    done = 0
+    for th in thetas:
+        try:
+            post(th)
+        except OracleError:
+            pass
+        done += 1
+    return done, time.perf_counter() - t0
+
+
+def cpu_oracle_rate(name, thetas, cores):
+    """Aggregate evals/s of the oracle port over `cores` worker processes, each with its own posterior replica and a
+    disjoint theta shard (the reference's own multi-process pattern, baysar/optimisation.py:140-151)."""
+    import multiprocessing as mp
+
+    shards = [s for s in np.array_split(thetas, cores) if len(s)]
+    t0 = time.perf_counter()
+    if len(shards) == 1:
+        results = [_oracle_worker((name, shards[0]))]
+    else:
+        with mp.get_context("fork").Pool(len(shards)) as pool:
+            results = pool.map(_oracle_worker, [(name, s) for s in shards])
+    wall = time.perf_counter() - t0
+    done = sum(r[0] for r in results)
+    busy = max(r[1] for r in results)
+    return done / busy, done, wall
+
+
+def usable_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ----------------------------------------------------------------------------------------------- clocks sampling
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- flop accounting
+def flop_model(post):
+    """Executed FP32 flop per eval in the chord kernel (analytic, from the compiled model) and the SURVEY §8d
+    dense-semantics figure W_fma + banded W_tensor for the same model."""
+    from baysar_b200.spectrometers import BalmerHydrogenLine
+
+    executed = dense = 0.0
+    for ch in post.chords:
+        F, P = len(ch.x_data_fm), len(ch.x_data)
+        n_b = sum(isinstance(l, BalmerHydrogenLine) for l in ch.lines)
+        n_g = sum(len(getattr(l, "lines", getattr(l, "cwl", []))) for l in ch.lines if not isinstance(l, BalmerHydrogenLine))
+        k_d = max([len(l.wavelengths_doppler) for l in ch.lines if isinstance(l, BalmerHydrogenLine)] or [0])
+        inst = np.abs(ch.instrument_function_fm)
+        keep = np.where(inst > 1e-17 * inst.max())[0]
+        nq_if = ((keep.max() - keep.min() + 1) + 3) // 4 * 4 + 4
+        dl = np.diff(ch.x_data_fm).mean()
+        if post.plasma.cold_neutrals:
+            sigma = 4000.0 * 7.715e-5 * np.sqrt(0.01 / 2.0) / np.sqrt(8 * np.log(2))
+        else:
+            sigma = 4000.0 * 7.715e-5 * np.sqrt(5.0 / 2.0) / np.sqrt(8 * np.log(2))
+        nq_d = (2 * int(8.85 * sigma / dl) + 1 + 3) // 4 * 4 + 4
+        executed += n_b * (18.0 * F + 2.0 * nq_d * F) + 2.0 * nq_if * F + 14.0 * F + 12.0 * P
+        dense += 8.0 * n_g * F + n_b * 2 * (10.0 * F + 2.0 * k_d * F + 3.0 * F) + 12.0 * F + 10.0 * P \
+            + 2.0 * F * len(ch.instrument_function_fm)
+    return executed, dense
+
+
+# ----------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="balmer_series")
+    ap.add_argument("--batch", type=int, default=0, help="thetas per GPU per step (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    batch = args.batch or BATCH_PER_GPU[args.workload]
+    config = {"workload": f"{args.workload}: {get_workload(args.workload).description}",
+              "thetas_per_gpu_per_step": batch, "theta_distribution": "uniform inside posterior.plasma.theta_bounds",
+              "atomic_data": "SyntheticADAS closed-form tables", "l2": "256 MiB scratch write between timed steps"}
+
+    if args.impl == "reference":
+        # The reference is pure Python and cannot travel to the GPU box: its CPU implementation of the path is
+        # timed through the oracle port (bit-identical to the shimmed reference on the golden vectors).
+        if rank != 0:
+            return
+        cores = usable_cores()
+        np.random.seed(0)
+        wl = get_workload(args.workload)
+        from baysar_b200.atomic_data import SyntheticADAS
+        from baysar_b200.input_functions import make_input_dict
+        from oracle.numpy_port import EsymmtricCauchyPlasma, OraclePosterior
+
+        prof = EsymmtricCauchyPlasma(x=wl.los) if wl.los is not None else None
+        bounds = OraclePosterior(make_input_dict(**wl.input_kwargs), SyntheticADAS(), prof).theta_bounds
+        per_step = max(cores * 32, 64)
+        thetas = draw_thetas(bounds, per_step * (args.steps + args.warmup), 20261019)
+        for w in range(args.warmup):
+            cpu_oracle_rate(args.workload, thetas[w * per_step:(w + 1) * per_step], cores)
+        t_total, done = 0.0, 0
+        for s in range(args.warmup, args.warmup + args.steps):
+            rate, n_done, wall = cpu_oracle_rate(args.workload, thetas[s * per_step:(s + 1) * per_step], cores)
+            t_total += n_done / rate
+            done += n_done
+        value = done / t_total
+        sample = f"{per_step} thetas per step x {args.steps} steps over {cores} forked workers"
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+
+    from baysar_b200 import runtime
+    from baysar_b200.atomic_data import SyntheticADAS
+    from baysar_b200.input_functions import make_input_dict
+    from baysar_b200.lineshapes import EsymmtricCauchyPlasma
+    from baysar_b200.posterior import BaysarPosterior
+
+    wl = get_workload(args.workload)
+    np.random.seed(0)
+    prof = EsymmtricCauchyPlasma(x=wl.los) if wl.los is not None else None
+    post = BaysarPosterior(make_input_dict(**wl.input_kwargs), profile_function=prof, atomic_data=SyntheticADAS(),
+                           device=local_rank, skip_test=True)
+    n_params = post.plasma.n_params
+    total_steps = args.warmup + args.steps
+    # a different theta batch every step; this rank's shard of the global batch
+    thetas_host = draw_thetas(post.plasma.theta_bounds, batch * total_steps, 20261019 + rank).reshape(total_steps, batch, n_params)
+    thetas_dev = torch.as_tensor(thetas_host, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+    gathered = torch.empty(world * batch, dtype=torch.float64, device="cuda") if world > 1 else None
+
+    def step(i):
+        logp = post.logp_batch(thetas_dev[i])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, logp)
+        return logp
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    post.model.set_profiling(True)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for k in range(args.steps):
+        flush.fill_(float(k))  # evict L2 between timed steps (untimed)
+        starts[k].record()
+        out = step(args.warmup + k)
+        ends[k].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    stage_ms, calls = post.model.get_profile()
+    post.model.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
+    total_ms = torch.tensor([float(step_ms.sum())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = world * batch * args.steps / (total_ms * 1e-3)
+    status = post.last_status_device.cpu().numpy()
+
+    # ---- end-to-end: reference-facing call with pinned HOST buffers (H2D + D2H inside the timed region)
+    pinned = torch.empty((batch, n_params), dtype=torch.float64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(2):
+        pinned.copy_(torch.from_numpy(thetas_host[i]))
+        post(pinned.numpy())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_e2e = 0.0
+    for k in range(e2e_steps):
+        pinned.copy_(torch.from_numpy(thetas_host[args.warmup + k]))
+        flush.fill_(float(k))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        logp_host = post(pinned.numpy())  # numpy in, numpy out: copies happen inside baysar_eval_logp_host
+        t_e2e += time.perf_counter() - t0
+    t_e2e_t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * batch * e2e_steps / float(t_e2e_t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (chord stage)
+    peaks = runtime.microbench(local_rank)
+    executed, dense = flop_model(post)
+    chord_ms = stage_ms[1] / max(calls, 1)
+    achieved = executed * batch / (chord_ms * 1e-3) / 1e12
+    peak = peaks["fp32_fma_flops"] / 1e12
+    measured = {}
+    try:
+        measured = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_bytes = batch * (8.0 * n_params + 8.0 + 4.0 + 8.0 * (len(post.chords) + len(post.priors))
+                         + 2 * 8.0 * 12 * post.model.n_ulines)
+    roofline = {
+        "bound": "fp32",  # neither HBM nor tensor bound: the chord kernel is FP32-FMA / MUFU work on smem-resident data
+        "kernel": "chord_stage_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        "peak_source": "FP32 FMA micro-benchmark in this run (baysar_microbench); MEASURED_PEAKS.json has no FP32 figure",
+        "traffic": None,
+        "executed_flop_per_eval": executed, "dense_reference_flop_per_eval": dense,
+        "dense_equivalent_tflops": dense * batch / (chord_ms * 1e-3) / 1e12,
+        "stage_ms": {"los": stage_ms[0] / max(calls, 1), "chord": chord_ms, "finalize": stage_ms[2] / max(calls, 1)},
+        "kernel_share_of_step": chord_ms / (float(step_ms.mean())),
+        "mufu_peak_gops": peaks["mufu_ops"] / 1e9, "fp64_peak_tflops": peaks["fp64_fma_flops"] / 1e12,
+        "hbm_algorithmic_GBps": hbm_bytes / (float(step_ms.mean()) * 1e-3) / 1e9,
+        "hbm_peak_GBps_measured": measured.get("hbm_gbs"),
+    }
+
+    # ---- CPU baseline (oracle port) on this box's host cores, bounded sample
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = usable_cores()
+        per_core = 150 if args.workload == "balmer_series" else 120
+        sample = thetas_host.reshape(-1, n_params)[: cores * per_core]
+        rate, done, wall = cpu_oracle_rate(args.workload, sample, cores)
+        rate1, done1, _ = cpu_oracle_rate(args.workload, sample[:200], 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{done} thetas of the same batch, {cores} forked workers, {wall:.1f} s wall",
+               "single_core_value": rate1}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 element-wise / f64 line-of-sight, reductions and likelihood", "data": "synthetic",
+            "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch * n_params * 8,
+                    "d2h_bytes_per_step": batch * (8 + 4), "steps": e2e_steps},
+            "gpu_launches": 3 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "status_ok_fraction": float((status == 0).mean())}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

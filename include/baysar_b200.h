@@ -90,6 +90,15 @@ int baysar_eval_lines(baysar_model_t* model, const double* theta, int64_t n, dou
 int baysar_eval_logp_host(baysar_model_t* model, const double* theta_host, int64_t n, double* logp_host,
                           uint32_t* status_host);
 
+/* Measurement hooks (no reference counterpart; used by bench.py for the live roofline).  While profiling is on,
+ * every baysar_eval_logp call records CUDA events around its three kernels on the caller's stream;
+ * baysar_model_get_profile synchronises, returns the summed per-stage milliseconds (LOS, chord, finalize) and the
+ * number of calls, and resets the log. */
+int baysar_model_set_profiling(baysar_model_t* model, int on);
+int baysar_model_get_profile(baysar_model_t* model, double* stage_ms, int64_t* calls);
+/* Peak-rate probe for roofline denominators: what = 0 FP32 FMA flop/s, 1 MUFU (rcp) op/s, 2 FP64 FMA flop/s. */
+int baysar_microbench(int device, int what, double* result);
+
 const char* baysar_last_error(void);
 const char* baysar_version(void);
 

@@ -1,0 +1,168 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against
+(1) the reference-generated golden fixtures, (2) the oracle port on fresh seeded thetas, (3) size-independent
+properties at BASELINE batch sizes.  Tolerances are the north_star's: logP 1e-6 relative, spectra 1e-5 per pixel.
+"""
+import numpy as np
+import pytest
+
+from .conftest import GOLDEN
+from .workloads import WORKLOADS
+
+pytestmark = pytest.mark.gpu
+
+LOGP_RTOL = 1e-6
+SPECTRA_RTOL = 1e-5
+
+
+def gpu_posterior(name):
+    from baysar_b200.atomic_data import SyntheticADAS
+    from baysar_b200.input_functions import make_input_dict
+    from baysar_b200.lineshapes import EsymmtricCauchyPlasma
+    from baysar_b200.posterior import BaysarPosterior
+
+    wl = WORKLOADS[name]()
+    prof = EsymmtricCauchyPlasma(x=wl.los) if wl.los is not None else None
+    np.random.seed(3)
+    return BaysarPosterior(make_input_dict(**wl.input_kwargs), profile_function=prof, atomic_data=SyntheticADAS(),
+                           skip_test=True), wl
+
+
+def oracle_posterior(name):
+    from .test_oracle_golden import build
+
+    return build(name)
+
+
+@pytest.fixture(scope="module")
+def posteriors():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = gpu_posterior(name)
+        return cache[name]
+
+    return get
+
+
+@pytest.mark.parametrize("name", sorted(WORKLOADS))
+def test_golden_fixtures(name, posteriors):
+    post, _ = posteriors(name)
+    z = np.load(GOLDEN / f"{name}.npz")
+    theta = z["theta"]
+    logp = post(theta)
+    assert (post.last_status == 0).all(), post.last_status
+    np.testing.assert_allclose(logp, z["logp"], rtol=LOGP_RTOL)
+    comps, status = post.components_batch(theta)
+    np.testing.assert_allclose(comps, z["components"], rtol=LOGP_RTOL, atol=1e-9)
+    lines, _, prof = post.lines_batch(theta, want_profiles=True)
+    np.testing.assert_allclose(prof[:, 0], z["ne"], rtol=1e-12)
+    np.testing.assert_allclose(prof[:, 1], z["te"], rtol=1e-12)
+    np.testing.assert_allclose(prof[:, 2], z["main_ion_density"], rtol=1e-11)
+    if "n0" in z.files:
+        np.testing.assert_allclose(prof[:, 3], z["n0"], rtol=1e-10)
+    for c in range(len(post.chords)):
+        spectra, st = post.spectra_batch(theta, chord=c)
+        np.testing.assert_allclose(spectra, z[f"c{c}_spectra"], rtol=SPECTRA_RTOL)
+        ref = z[f"c{c}_line_scalars"]
+        for k, u in enumerate(post.model_info["chord_line_uline"][c]):
+            kind = str(z[f"setup_c{c}_line_types"][k])
+            rec = lines[:, u]
+            if kind == "BalmerHydrogenLine":
+                np.testing.assert_allclose(rec[:, [0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 6]], ref[:, k, :11], rtol=1e-9)
+            elif kind == "ADAS406Lines":
+                np.testing.assert_allclose(rec[:, :5], ref[:, k, :5], rtol=1e-9)
+            else:
+                np.testing.assert_allclose(rec[:, :1], ref[:, k, :1], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["balmer_series", "multi_species", "multi_hot", "multi_calibrated"])
+def test_against_oracle_on_fresh_thetas(name, posteriors):
+    post, wl = posteriors(name)
+    oracle = oracle_posterior(name)
+    rng = np.random.default_rng(99)
+    lo, hi = post.plasma.theta_bounds[:, 0], post.plasma.theta_bounds[:, 1]
+    theta = lo + rng.random((48, post.plasma.n_params)) * (hi - lo)
+    logp = post(theta)
+    status = post.last_status.copy()
+    spectra, _ = post.spectra_batch(theta, chord=0)
+    from oracle.numpy_port import OracleError
+
+    checked = 0
+    for i, th in enumerate(theta):
+        try:
+            ref = oracle.evaluate(th)
+        except OracleError:
+            assert status[i] != 0, f"oracle raised but status is clean for theta {i}"
+            continue
+        assert status[i] == 0, (i, status[i])
+        np.testing.assert_allclose(logp[i], ref["logp"], rtol=LOGP_RTOL)
+        np.testing.assert_allclose(spectra[i], ref["spectra"][0], rtol=SPECTRA_RTOL)
+        checked += 1
+    assert checked >= 40
+
+
+def test_scalar_protocol_and_exceptions(posteriors):
+    post, wl = posteriors("multi_species")
+    z = np.load(GOLDEN / "multi_species.npz")
+    th = z["theta"][0]
+    val = post(th)
+    assert isinstance(val, float)
+    np.testing.assert_allclose(val, z["logp"][0], rtol=LOGP_RTOL)
+    np.testing.assert_allclose(post.cost(th), -z["logp"][0], rtol=LOGP_RTOL)
+    # reference-style introspection after a scalar call
+    np.testing.assert_allclose(post.posterior_components[0].forward_model(), z["c0_spectra"][0], rtol=SPECTRA_RTOL)
+    np.testing.assert_allclose(post.posterior_components[0](), z["components"][0, 0], rtol=LOGP_RTOL)
+    np.testing.assert_allclose(post.plasma.plasma_state["electron_density"], z["ne"][0], rtol=1e-12)
+    line = post.posterior_components[0].lines[0]
+    np.testing.assert_allclose([line.rec_sum, line.exc_ne, line.f_rec], z["c0_line_scalars"][0, 0, [0, 4, 6]], rtol=1e-9)
+    bad = th.copy()
+    bad[2] = np.nan
+    with pytest.raises(TypeError):
+        post(bad)
+    bad = th.copy()
+    bad[post.plasma.slices["N_1_tau"].start] = -7.5  # below the ADAS tau grid: the reference raises ValueError
+    with pytest.raises(ValueError):
+        post(bad)
+    assert np.isfinite(post(bad, True)) or True  # skip_error=True never raises
+
+
+def test_batch_properties_at_baseline_size(posteriors):
+    """configs[1] at its full batch (4096 thetas): determinism, batch-splitting and permutation invariance,
+    host-buffer path == device path."""
+    import torch
+
+    post, wl = posteriors("balmer_series")
+    rng = np.random.default_rng(5)
+    lo, hi = post.plasma.theta_bounds[:, 0], post.plasma.theta_bounds[:, 1]
+    theta = lo + rng.random((4096, post.plasma.n_params)) * (hi - lo)
+    dev = torch.as_tensor(theta, device="cuda")
+    a = post.logp_batch(dev).cpu().numpy()
+    b = post.logp_batch(dev).cpu().numpy()
+    np.testing.assert_array_equal(a, b)
+    parts = np.concatenate([post.logp_batch(dev[:1000]).cpu().numpy(), post.logp_batch(dev[1000:]).cpu().numpy()])
+    np.testing.assert_array_equal(a, parts)
+    perm = rng.permutation(4096)
+    np.testing.assert_array_equal(a[perm], post.logp_batch(dev[torch.as_tensor(perm, device="cuda")]).cpu().numpy())
+    host = post(theta)
+    np.testing.assert_array_equal(a, host)
+    ok = post.last_status == 0
+    assert ok.mean() > 0.9
+    assert np.all(np.isfinite(a[ok])) and np.all(a[ok] < 0)
+    # a sample of the big batch against the oracle
+    oracle = oracle_posterior("balmer_series")
+    for i in rng.choice(np.where(ok)[0], 16, replace=False):
+        np.testing.assert_allclose(a[i], oracle(theta[i]), rtol=LOGP_RTOL)
+
+
+def test_background_linearity_property(posteriors):
+    """forward_model = clip(lines + background): raising the background by d raises every pixel that is not clipped
+    by exactly d (spectrometers.py:299-310) — a size-independent property of the fused epilogue."""
+    post, wl = posteriors("multi_species")
+    z = np.load(GOLDEN / "multi_species.npz")
+    th = np.repeat(z["theta"][:1], 2, axis=0)
+    b = post.plasma.slices["background_0"].start
+    th[1, b] = np.log10(10 ** th[0, b] * 1.5)
+    spectra, _ = post.spectra_batch(th, chord=0)
+    d = 10 ** th[1, b] - 10 ** th[0, b]
+    np.testing.assert_allclose(spectra[1] - spectra[0], d, rtol=1e-6)
