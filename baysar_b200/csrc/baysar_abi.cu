@@ -203,6 +203,7 @@ int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar
   d.spl_ty = static_cast<const double*>(dev.ptr(SEC_SPL_TY));
   d.spl_c = static_cast<const double*>(dev.ptr(SEC_SPL_C));
   d.ul_i = static_cast<const int*>(dev.ptr(SEC_UL_I));
+  d.ul_d = static_cast<const double*>(dev.ptr(SEC_UL_D));
   d.pr_i = static_cast<const int*>(dev.ptr(SEC_PR_I));
   d.pr_d = static_cast<const double*>(dev.ptr(SEC_PR_D));
   d.cso_off = static_cast<const int*>(dev.ptr(SEC_CSO_OFF));

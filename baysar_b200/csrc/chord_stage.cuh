@@ -1,5 +1,5 @@
 // K2 — spectral stage: one CTA per (theta, chord).  float32 element-wise work on the fine wavelength grid held in
-// shared memory, float64 for wavelength differences, tap tables, reductions and the pixel / likelihood epilogue.
+// shared memory, float64 for tap tables, reductions and the pixel / likelihood epilogue.
 //
 // Replaces, per (theta, chord) (reference file:line):
 //   BalmerHydrogenLine.__call__ (shape part)   baysar/linemodels.py:838-865
@@ -15,6 +15,11 @@
 //   * the two trapz normalisations of the Stark (x) Doppler profile collapse into A = sum_i u[i] G[i], with G the
 //     trapz weights pulled back through the convolution (constant inside, tap prefix sums at the two ends);
 //   * uniform trapz weights on the arange grid; the four end outputs of the instrument convolution in float64.
+//
+// Shared-memory layout: two zero-haloed fine-grid buffers A (accumulated spectrum) and B (scratch / convolved
+// spectrum), XOR-swizzled at float4 granularity: element i lives at i ^ ((i >> 3) & 4), i.e. odd 32-element blocks
+// swap their float4 pairs.  Threads that own 8 consecutive convolution outputs read float4s at a 32-byte stride; the
+// swizzle spreads a quarter-warp's eight reads over all eight 16-byte bank groups for every alignment (no padding).
 #pragma once
 #include "device_common.cuh"
 
@@ -30,18 +35,20 @@ struct ChordArgs {
   uint32_t* status;         // [N] OR-ed
 };
 
+__host__ __device__ static inline int pad_index(int i) { return i ^ ((i >> 3) & 4); }
+
 struct ChordSmem {
-  // sizes in bytes for the dynamic shared-memory carve-up; all multiples of 16
-  size_t buf_floats;   // floats per padded fine-grid buffer
+  size_t buf_floats;   // physical floats per padded fine-grid buffer
   size_t taps_floats;  // floats in the q-indexed tap buffer
   size_t tapd_doubles; // doubles for Doppler taps + prefix sums
-  size_t total;
+  size_t total;        // bytes
 };
 
-static inline ChordSmem chord_smem_layout(int F, int halo, int taps_max, int kd_max) {
+__host__ __device__ static inline ChordSmem chord_smem_layout(int F, int halo, int taps_max, int kd_max) {
   ChordSmem s;
-  int f4 = (F + 3) / 4 * 4;
-  s.buf_floats = (size_t)f4 + 2 * (size_t)halo + 8;
+  int f8 = (F + 7) / 8 * 8;
+  int logical = f8 + 2 * halo + 16;
+  s.buf_floats = (size_t)(logical + 8 + 3) / 4 * 4;
   s.taps_floats = (size_t)(taps_max + 8 + 3) / 4 * 4;
   s.tapd_doubles = 2 * (size_t)kd_max + 4;
   s.total = 2 * s.buf_floats * sizeof(float) + s.taps_floats * sizeof(float) + s.tapd_doubles * sizeof(double) +
@@ -53,25 +60,28 @@ static inline ChordSmem chord_smem_layout(int F, int halo, int taps_max, int kd_
 // fine-grid coordinate, bit-identical to numpy.arange's fill: start + j * delta (two roundings, no FMA)
 BAYSAR_DEV double grid_x(double x0, double delta, int j) { return __dadd_rn(x0, __dmul_rn((double)j, delta)); }
 
-// 4 consecutive outputs of a zero-padded "same" convolution.
-// src points at padded_buffer + halo + j0 + q_start (16-byte aligned); tq[qi] = w[o - (q_start + qi)].
-BAYSAR_DEV float4 conv4(const float* src, const float* tq, int nq) {
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 cur = *reinterpret_cast<const float4*>(src);
+BAYSAR_DEV float4 ld4(const float* buf, int e) { return *reinterpret_cast<const float4*>(buf + pad_index(e)); }
+
+// 8 consecutive outputs of a zero-padded "same" convolution.  `e0` = logical element index of (first output + q_start)
+// in the padded buffer (a multiple of 4); tq[qi] = w[o - (q_start + qi)], nq a multiple of 4.
+BAYSAR_DEV void conv8(const float* buf, int e0, const float* tq, int nq, float* acc) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+  float4 c0 = ld4(buf, e0), c1 = ld4(buf, e0 + 4);
   for (int qi = 0; qi < nq; qi += 4) {
-    const float4 nxt = *reinterpret_cast<const float4*>(src + qi + 4);
+    const float4 c2 = ld4(buf, e0 + qi + 8);
     const float4 w = *reinterpret_cast<const float4*>(tq + qi);
-    acc.x = fmaf(w.x, cur.x, acc.x); acc.y = fmaf(w.x, cur.y, acc.y);
-    acc.z = fmaf(w.x, cur.z, acc.z); acc.w = fmaf(w.x, cur.w, acc.w);
-    acc.x = fmaf(w.y, cur.y, acc.x); acc.y = fmaf(w.y, cur.z, acc.y);
-    acc.z = fmaf(w.y, cur.w, acc.z); acc.w = fmaf(w.y, nxt.x, acc.w);
-    acc.x = fmaf(w.z, cur.z, acc.x); acc.y = fmaf(w.z, cur.w, acc.y);
-    acc.z = fmaf(w.z, nxt.x, acc.z); acc.w = fmaf(w.z, nxt.y, acc.w);
-    acc.x = fmaf(w.w, cur.w, acc.x); acc.y = fmaf(w.w, nxt.x, acc.y);
-    acc.z = fmaf(w.w, nxt.y, acc.z); acc.w = fmaf(w.w, nxt.z, acc.w);
-    cur = nxt;
+    const float s[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      acc[r] = fmaf(w.x, s[r], acc[r]);
+      acc[r] = fmaf(w.y, s[r + 1], acc[r]);
+      acc[r] = fmaf(w.z, s[r + 2], acc[r]);
+      acc[r] = fmaf(w.w, s[r + 3], acc[r]);
+    }
+    c0 = c1;
+    c1 = c2;
   }
-  return acc;
 }
 
 // exp(arg) for arg <= 0 computed as 2^n * ex2(f): the argument reduction is done in float64 so that the result
@@ -85,8 +95,11 @@ BAYSAR_DEV float exp_neg_f32(double arg) {
   return exp2f(f) * __int_as_float((e + 127) << 23);
 }
 
+#ifndef BAYSAR_CHORD_MIN_BLOCKS
+#define BAYSAR_CHORD_MIN_BLOCKS 3  // 3 CTAs (24 warps) per SM: caps the kernel at 80 registers, no spills
+#endif
 template <int NT>
-__global__ void __launch_bounds__(NT) chord_stage_kernel(ModelDev m, ChordArgs a) {
+__global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kernel(ModelDev m, ChordArgs a) {
 #ifdef BAYSAR_CPU_EMU
   unsigned char* chord_smem_raw = emu_dynamic_smem();
 #else
@@ -111,27 +124,27 @@ __global__ void __launch_bounds__(NT) chord_stage_kernel(ModelDev m, ChordArgs a
     int kd = m.cl_i[(ch[CH_LINE_OFF] + k) * CL_I_COUNT + CL_KD];
     kd_max = kd > kd_max ? kd : kd_max;
   }
-  const int f4 = (F + 3) / 4 * 4;
-  const size_t buf_floats = (size_t)f4 + 2 * (size_t)HALO + 8;
-  const size_t taps_floats = (size_t)(TAPS_MAX + 8 + 3) / 4 * 4;
+  const ChordSmem lay = chord_smem_layout(F, HALO, TAPS_MAX, kd_max);
+  const int f8 = (F + 7) / 8 * 8;
   float* bufA = reinterpret_cast<float*>(chord_smem_raw);
-  float* bufB = bufA + buf_floats;
-  float* tapq = bufB + buf_floats;
-  double* tapd = reinterpret_cast<double*>(tapq + taps_floats);  // [kd_max] taps, then [kd_max + 1] prefix sums
+  float* bufB = bufA + lay.buf_floats;
+  float* tapq = bufB + lay.buf_floats;
+  double* tapd = reinterpret_cast<double*>(tapq + lay.taps_floats);  // [kd_max] taps, then [kd_max + 1] prefix sums
   double* tappre = tapd + kd_max;
   double* scratch = tappre + kd_max + 4;  // 64 doubles
   int* iscr = reinterpret_cast<int*>(scratch + 64);  // 16 ints
   double* edge64 = scratch + 48;  // 4 doubles inside the scratch area that block_sum never touches (needs <= 48)
+#define A_AT(j) bufA[pad_index(HALO + (j))]
+#define B_AT(j) bufB[pad_index(HALO + (j))]
 
   uint32_t st = 0;
-  for (size_t i = tid; i < 2 * buf_floats; i += NT) bufA[i] = 0.f;
+  for (size_t i = tid; i < 2 * lay.buf_floats; i += NT) bufA[i] = 0.f;
   __syncthreads();
-  float* A = bufA + HALO;  // A[j], j in [-HALO, f4 + HALO + 8)
-  float* B = bufB + HALO;
 
   const double cal = ch[CH_CAL_IDX] >= 0 ? pow(10.0, th[ch[CH_CAL_IDX]]) : 1.0;
   const double fwhm_to_sigma = 0.42466090014400953;  // 1 / sqrt(8 ln 2)
   const double c_light = 299792458.0;
+  const float NTf = (float)NT;
 
   // ================= line objects ==============================================================================
   for (int k = 0; k < ch[CH_N_LINES]; ++k) {
@@ -139,17 +152,10 @@ __global__ void __launch_bounds__(NT) chord_stage_kernel(ModelDev m, ChordArgs a
     const double* cld = m.cl_d + (ch[CH_LINE_OFF] + k) * CL_D_COUNT;
     const double* rec = lines_n + cl[CL_ULINE] * BAYSAR_LINE_STRIDE;
     const int kind = cl[CL_KIND];
-    double vel = 0.0; int has_vel = 0;
-    if (cl[CL_SPECIES] >= 0) {
-      int vi = m.sp_i[cl[CL_SPECIES] * SP_I_COUNT + SP_VEL_IDX];
-      if (vi >= 0) { vel = 1e3 * th[vi]; has_vel = 1; }
-    }
     if (kind == 0) {
       // ---------------- Balmer line: Stark (x) Doppler ----------------
       const double cwl0 = cld[CL_CWL0];
-      const double cwl = has_vel ? cwl0 * (vel / c_light + 1.0) : cwl0;
-      const double ti = rec[6];
-      const double sigma = cwl * 7.715e-5 * sqrt(ti / cld[CL_MASS]) * fwhm_to_sigma;
+      const double cwl = rec[13], sigma = rec[14];  // shifted centre and Doppler sigma from the LOS stage
       if (!(sigma > 0.0)) st |= 1u << 5;
       const int KD = cl[CL_KD], o = (KD - 1) / 2;
       const double dshift = cwl - cwl0;
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(NT) chord_stage_kernel(ModelDev m, ChordArgs a
         double z = ((xk + dshift) - cwl) / sigma;
         tapd[q] = exp(-0.5 * z * z);
       }
-      // q-indexed float taps for conv4: q = o - k in [o - k_hi + 1, o - k_lo]
+      // q-indexed float taps for conv8: q = o - k in [o - k_hi + 1, o - k_lo]
       const int q_min = o - k_hi + 1, q_max = o - k_lo;
       const int q_start = q_min & ~3;
       const int nq = (q_max - q_start + 1 + 3) & ~3;
@@ -200,19 +206,26 @@ __global__ void __launch_bounds__(NT) chord_stage_kernel(ModelDev m, ChordArgs a
       // interior points: every tap of the window lands on a valid output with full trapz weight
       const int i_lo = o - k_lo + 1;          // first interior i
       const int i_hi = F - 1 + o - k_hi;      // last interior i
-      // Stark widths (stehle_param, linemodels.py:554-566): gamma^2.5 for the rec- and exc-weighted plasmas
-      const double la = cld[CL_LOMAN_A], lb = cld[CL_LOMAN_B], lc = cld[CL_LOMAN_C];
-      const double g_rec = (10.0 * lc * (pow(1e6 * rec[2], la) / pow(rec[3], lb))) / 2.0;
-      const double g_exc = (10.0 * lc * (pow(1e6 * rec[4], la) / pow(rec[5], lb))) / 2.0;
-      const float g25_rec = (float)pow(g_rec, 2.5), g25_exc = (float)pow(g_exc, 2.5);
+      const float g25_rec = (float)rec[11], g25_exc = (float)rec[12];
+      // lambda_j - cwl = (j - jc) * delta + r, with jc the grid point nearest the line centre and |r| <= delta / 2:
+      // the large, cancelling parts are removed in float64 once, the per-point work is two float32 FMAs with a
+      // float-float split of delta (error ~1 ulp of the difference itself, even next to the line centre).
       const double c0 = x0 - cwl;
-      // pass 1: A_e = sum_i u_e[i] G[i]
+      const int jc = (int)rint(-c0 / delta);
+      const float r_f = (float)fma((double)jc, delta, c0);
+      const float d_hi = (float)delta, d_lo = (float)(delta - (double)(float)delta);
+      // pass 1: a25 = |d|^2.5 stashed in B;  A_e = sum_i u_e[i] G[i] with u_rec = den_exc * inv, u_exc = den_rec * inv,
+      // inv = 1 / (den_rec * den_exc): one reciprocal serves both profiles
       float sr = 0.f, se = 0.f;
       double er = 0.0, ee = 0.0;
-      for (int j = tid; j < F; j += NT) {
-        float d = fabsf((float)fma((double)j, delta, c0));
-        float a25 = d * d * sqrtf(d);
-        float ur = __fdividef(1.f, a25 + g25_rec), ue = __fdividef(1.f, a25 + g25_exc);
+      float kf = (float)(tid - jc);
+      for (int j = tid; j < F; j += NT, kf += NTf) {
+        float d = fabsf(fmaf(kf, d_hi, fmaf(kf, d_lo, r_f)));
+        float a25 = d * d * sqrt_approx(d);
+        B_AT(j) = a25;
+        float dr = a25 + g25_rec, de = a25 + g25_exc;
+        float inv = rcp_approx(dr * de);
+        float ur = de * inv, ue = dr * inv;
         if (j >= i_lo && j <= i_hi) { sr += ur; se += ue; }
         else {
           int kmin = o - j, kmax = F - 1 + o - j;  // taps that reach outputs 0 and F-1
@@ -231,25 +244,36 @@ __global__ void __launch_bounds__(NT) chord_stage_kernel(ModelDev m, ChordArgs a
       const double s_rec = rec[0] / (dl * red[0]) / cal, s_exc = rec[1] / (dl * red[1]) / cal;
       if (!(s_rec - s_rec == 0.0) || !(s_exc - s_exc == 0.0)) st |= 1u << 6;
       const float fr = (float)s_rec, fe = (float)s_exc;
-      // pass 2: m = s_rec u_rec + s_exc u_exc -> B, then A += m (*) g
+      // pass 2: m = s_rec u_rec + s_exc u_exc = (s_rec den_exc + s_exc den_rec) * inv  (in place over the stash)
       for (int j = tid; j < F; j += NT) {
-        float d = fabsf((float)fma((double)j, delta, c0));
-        float a25 = d * d * sqrtf(d);
-        B[j] = fr * __fdividef(1.f, a25 + g25_rec) + fe * __fdividef(1.f, a25 + g25_exc);
+        float a25 = B_AT(j);
+        float dr = a25 + g25_rec, de = a25 + g25_exc;
+        B_AT(j) = fmaf(fr, de, fe * dr) * rcp_approx(dr * de);
       }
       __syncthreads();
-      for (int j0 = 4 * tid; j0 < F; j0 += 4 * NT) {
-        float4 r = conv4(B + j0 + q_start, tapq, nq);
-        float4* dst = reinterpret_cast<float4*>(A + j0);
-        float4 v = *dst;
-        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-        *dst = v;
+      // A += m (*) g
+      for (int j0 = 8 * tid; j0 < F; j0 += 8 * NT) {
+        float acc[8];
+        conv8(bufB, HALO + j0 + q_start, tapq, nq, acc);
+        float4* dst = reinterpret_cast<float4*>(bufA + pad_index(HALO + j0));
+        float4 v = dst[0];
+        v.x += acc[0]; v.y += acc[1]; v.z += acc[2]; v.w += acc[3];
+        dst[0] = v;
+        dst = reinterpret_cast<float4*>(bufA + pad_index(HALO + j0 + 4));
+        v = dst[0];
+        v.x += acc[4]; v.y += acc[5]; v.z += acc[6]; v.w += acc[7];
+        dst[0] = v;
       }
       __syncthreads();
-      for (int j = F + tid; j < f4; j += NT) A[j] = 0.f;  // keep the alignment tail clean
+      for (int j = F + tid; j < f8; j += NT) A_AT(j) = 0.f;  // keep the alignment tail clean
       __syncthreads();
     } else {
       // ---------------- Gaussian multiplet (ADAS406Lines / XLine) ----------------
+      double vel = 0.0; int has_vel = 0;
+      if (cl[CL_SPECIES] >= 0) {
+        int vi = m.sp_i[cl[CL_SPECIES] * SP_I_COUNT + SP_VEL_IDX];
+        if (vi >= 0) { vel = 1e3 * th[vi]; has_vel = 1; }
+      }
       const double ems = rec[0];
       const int ncmp = cl[CL_NCOMP];
       for (int q = 0; q < ncmp; ++q) {
@@ -275,7 +299,7 @@ __global__ void __launch_bounds__(NT) chord_stage_kernel(ModelDev m, ChordArgs a
         const float ampf = (float)amp;
         for (; j <= j_hi; j += NT) {
           double z = (grid_x(x0, delta, j) - cw) / sigma;
-          if (fabs(z) <= BAYSAR_Z_CUT) A[j] += ampf * exp_neg_f32(-0.5 * z * z);
+          if (fabs(z) <= BAYSAR_Z_CUT) A_AT(j) += ampf * exp_neg_f32(-0.5 * z * z);
         }
       }
     }
@@ -287,7 +311,7 @@ __global__ void __launch_bounds__(NT) chord_stage_kernel(ModelDev m, ChordArgs a
   float mn = 3.402823466e38f;
   int bad = 0;
   for (int j = tid; j < F; j += NT) {
-    float v = A[j];
+    float v = A_AT(j);
     double w = (j == 0 || j == F - 1) ? 0.5 : 1.0;
     pre_s += w * (double)v;
     mn = v < mn ? v : mn;
@@ -295,7 +319,7 @@ __global__ void __launch_bounds__(NT) chord_stage_kernel(ModelDev m, ChordArgs a
   }
   if (a.fine_pre) {
     float* o_ = a.fine_pre + n * (int64_t)F;
-    for (int j = tid; j < F; j += NT) o_[j] = A[j];
+    for (int j = tid; j < F; j += NT) o_[j] = A_AT(j);
   }
   mn = warp_min_f(mn);
   if (lane == 0) reinterpret_cast<float*>(iscr)[4 + warp] = mn;  // iscr[4 .. 4 + NT/32)
@@ -327,7 +351,7 @@ __global__ void __launch_bounds__(NT) chord_stage_kernel(ModelDev m, ChordArgs a
     if (!(red2[0] > 0.0)) st |= 1u << 7;
     int o = (KI - 1) / 2;
     // clamp the window to the shared-memory capacity sized from the parameter bounds
-    int lim = HALO - 4 < TAPS_MAX / 2 - 4 ? HALO - 4 : TAPS_MAX / 2 - 4;
+    int lim = HALO - 8 < TAPS_MAX / 2 - 8 ? HALO - 8 : TAPS_MAX / 2 - 8;
     if (k_hi - 1 - o > lim) { k_hi = o + lim + 1; st |= 1u << 16; }
     if (o - k_lo > lim) { k_lo = o - lim; st |= 1u << 16; }
     if (k_hi <= k_lo) { k_lo = o; k_hi = o + 1; }
@@ -364,26 +388,27 @@ __global__ void __launch_bounds__(NT) chord_stage_kernel(ModelDev m, ChordArgs a
   // ================= instrument convolution, clip at the pre-convolution minimum (spectrometers.py:269-271) =====
   double post_s = 0.0;
   bad = 0;
-  for (int j0 = 4 * tid; j0 < F; j0 += 4 * NT) {
-    float4 r = conv4(A + j0 + q_start_if, tapq, nq_if);
-    r.x = r.x < mn ? mn : r.x; r.y = r.y < mn ? mn : r.y; r.z = r.z < mn ? mn : r.z; r.w = r.w < mn ? mn : r.w;
-    *reinterpret_cast<float4*>(B + j0) = r;
-    float vv[4] = {r.x, r.y, r.z, r.w};
+  for (int j0 = 8 * tid; j0 < F; j0 += 8 * NT) {
+    float acc[8];
+    conv8(bufA, HALO + j0 + q_start_if, tapq, nq_if, acc);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 8; ++q) {
+      acc[q] = acc[q] < mn ? mn : acc[q];
       int j = j0 + q;
       if (j < F) {
         double w = (j == 0 || j == F - 1) ? 0.5 : 1.0;
-        post_s += w * (double)vv[q];
-        if (!(vv[q] - vv[q] == 0.f)) bad = 1;
+        post_s += w * (double)acc[q];
+        if (!(acc[q] - acc[q] == 0.f)) bad = 1;
       }
     }
+    *reinterpret_cast<float4*>(bufB + pad_index(HALO + j0)) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(bufB + pad_index(HALO + j0 + 4)) = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
   // the four end outputs in float64: they set the slope interp1d extrapolates with (sampled wavelength maps)
   if (warp < 4) {
     int j = warp < 2 ? warp : F - 4 + warp;
     double s = 0.0;
-    for (int qi = lane; qi < nq_if; qi += 32) s += (double)tapq[qi] * (double)A[j + q_start_if + qi];
+    for (int qi = lane; qi < nq_if; qi += 32) s += (double)tapq[qi] * (double)A_AT(j + q_start_if + qi);
     s = warp_sum(s);
     if (lane == 0) edge64[warp] = s < (double)mn ? (double)mn : s;
   }
@@ -397,7 +422,7 @@ __global__ void __launch_bounds__(NT) chord_stage_kernel(ModelDev m, ChordArgs a
   const double bg = pow(10.0, th[ch[CH_BG_IDX]]);
   if (a.fine_post) {
     float* o_ = a.fine_post + n * (int64_t)F;
-    for (int j = tid; j < F; j += NT) o_[j] = (float)((double)B[j] / ratio + bg);
+    for (int j = tid; j < F; j += NT) o_[j] = (float)((double)B_AT(j) / ratio + bg);
   }
 
   // ================= wavelength map, clip at the background, Cauchy likelihood (spectrometers.py:299-310, :154-195)
@@ -422,9 +447,9 @@ __global__ void __launch_bounds__(NT) chord_stage_kernel(ModelDev m, ChordArgs a
       i = m.pix_idx[poff + p];
       w = m.pix_frac[poff + p];
     }
-    double v0 = (i < 2) ? edge64[i] : (i >= F - 2 ? edge64[i - (F - 4)] : (double)B[i]);
+    double v0 = (i < 2) ? edge64[i] : (i >= F - 2 ? edge64[i - (F - 4)] : (double)B_AT(i));
     int i1 = i + 1;
-    double v1 = (i1 < 2) ? edge64[i1] : (i1 >= F - 2 ? edge64[i1 - (F - 4)] : (double)B[i1]);
+    double v1 = (i1 < 2) ? edge64[i1] : (i1 >= F - 2 ? edge64[i1 - (F - 4)] : (double)B_AT(i1));
     double fm = (v0 + w * (v1 - v0)) / ratio + bg;
     fm = fm < bg ? bg : fm;
     if (!(fm - fm == 0.0)) st |= 1u << 10;
@@ -440,4 +465,6 @@ __global__ void __launch_bounds__(NT) chord_stage_kernel(ModelDev m, ChordArgs a
   if (tid == 0) a.components[n * (int64_t)ncomp_cols + c] = -red4[0];
   st = __syncthreads_or((int)st);
   if (tid == 0 && st) atomicOr(&a.status[n], st);
+#undef A_AT
+#undef B_AT
 }

@@ -11,7 +11,7 @@
 #include "cpu_emu.h"  // tests/emu: std::thread-based execution of the same kernel source (test-only)
 #endif
 
-#define BAYSAR_LINE_STRIDE 12
+#define BAYSAR_LINE_STRIDE 16
 #define BAYSAR_HDR_STRIDE 4  // per-theta header written by the LOS stage: ne_max, reserved...
 #define BAYSAR_Z_CUT 8.85    // exp(-z*z/2) < 1e-17 beyond this
 
@@ -36,6 +36,7 @@ struct ModelDev {
   const double* spl_ty;
   const double* spl_c;
   const int* ul_i;
+  const double* ul_d;
   const int* pr_i;
   const double* pr_d;
   const int* cso_off;
@@ -51,6 +52,15 @@ struct ModelDev {
   const int* pix_idx;
   const double* pix_frac;
 };
+
+// approximate reciprocal / square root (one MUFU op each, ~1 ulp): the float32 spectral sweeps do not need IEEE rounding
+#ifndef BAYSAR_CPU_EMU
+BAYSAR_DEV float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+BAYSAR_DEV float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#else
+BAYSAR_DEV float rcp_approx(float x) { return 1.0f / x; }
+BAYSAR_DEV float sqrt_approx(float x) { return sqrtf(x); }
+#endif
 
 // np.clip(v, lo, None): NaN propagates (fmax would swallow it)
 BAYSAR_DEV double clip_lo(double v, double lo) { return v < lo ? lo : v; }

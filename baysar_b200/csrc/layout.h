@@ -9,7 +9,7 @@
 #define BAYSAR_LAYOUT_H
 
 #define BAYSAR_BLOB_MAGIC 0x4252415359534142LL /* "BAYSYSAB" */
-#define BAYSAR_BLOB_VERSION 3
+#define BAYSAR_BLOB_VERSION 4
 
 enum BaysarSection {
   SEC_I,              /* int64  [I_COUNT]           model-wide integer scalars                         */
@@ -31,6 +31,7 @@ enum BaysarSection {
   SEC_SPL_TY,         /* double [spl_ny]            bicubic spline knots in Te                         */
   SEC_SPL_C,          /* double [n_tec][n_tau][(spl_nx-4)*(spl_ny-4)]  B-spline coefficients of log(ne*TEC) */
   SEC_UL_I,           /* int32  [n_ulines][UL_I_COUNT]  unique (line-of-sight) lines                    */
+  SEC_UL_D,           /* double [n_ulines][UL_D_COUNT]                                                  */
   SEC_PR_I,           /* int32  [n_priors][PR_I_COUNT]                                                  */
   SEC_PR_D,           /* double [n_priors][PR_D_COUNT]                                                  */
   SEC_CSO_OFF,        /* int32  [n_elem + 1]        ChargeStateOrderPrior: per element, offsets into CSO_UL */
@@ -104,6 +105,15 @@ enum BaysarUlI {
   UL_TAB_A,    /* Balmer: excitation log-PEC table; ADAS406: TEC table; XLine: theta index */
   UL_TAB_B,    /* Balmer: recombination log-PEC table */
   UL_I_COUNT
+};
+
+enum BaysarUlD {
+  UL_CWL0,     /* Balmer: rest wavelength */
+  UL_LOMAN_A,  /* Balmer: Stark-width parameterisation a_ij, b_ij, c_ij */
+  UL_LOMAN_B,
+  UL_LOMAN_C,
+  UL_MASS,
+  UL_D_COUNT
 };
 
 enum BaysarPriorKind {

@@ -202,9 +202,24 @@ __global__ void __launch_bounds__(WARPS * 32) los_stage_kernel(ModelDev m, LosAr
       if (cold_neutrals) ti = 0.01;
       else if (thermalised) ti = (1 - f_rec) * exc_te + f_rec * rec_te;
       else ti = pow(10.0, th[sp[SP_TI_IDX]]);
-      if (lane == 0) {
+      // shape constants shared by every chord that sees this line: Stark half-widths gamma^2.5 (stehle_param,
+      // linemodels.py:554-566), Doppler-shifted centre (:239-241) and Doppler sigma (:298, lineshapes.py:128).
+      // Lanes 0 / 1 take the two pow-heavy widths so that they run side by side.
+      const double* ud = m.ul_d + u * UL_D_COUNT;
+      if (lane < 2) {
+        const double la = ud[UL_LOMAN_A], lb = ud[UL_LOMAN_B], lc = ud[UL_LOMAN_C];
+        const double wne = lane == 0 ? rec_ne : exc_ne, wte = lane == 0 ? rec_te : exc_te;
+        const double g = (10.0 * lc * (pow(1e6 * wne, la) / pow(wte, lb))) / 2.0;
+        rec[11 + lane] = pow(g, 2.5);
+      }
+      if (lane == 2) {
         rec[0] = rec_sum; rec[1] = exc_sum; rec[2] = rec_ne; rec[3] = rec_te; rec[4] = exc_ne; rec[5] = exc_te;
-        rec[6] = ti; rec[7] = f_rec; rec[8] = s[10] / s[8]; rec[9] = s[11] / s[8]; rec[10] = ems; rec[11] = 0.0;
+        rec[6] = ti; rec[7] = f_rec; rec[8] = s[10] / s[8]; rec[9] = s[11] / s[8]; rec[10] = ems;
+        const int vi = sp[SP_VEL_IDX];
+        const double cwl = vi >= 0 ? ud[UL_CWL0] * ((1e3 * th[vi]) / 299792458.0 + 1.0) : ud[UL_CWL0];
+        rec[13] = cwl;
+        rec[14] = cwl * 7.715e-5 * sqrt(ti / ud[UL_MASS]) * 0.42466090014400953;
+        rec[15] = 0.0;
       }
     } else if (kind == 1) {  // ADAS406 (linemodels.py:386-426, :445-494)
       const int* sp = m.sp_i + ul[UL_SPECIES] * SP_I_COUNT;

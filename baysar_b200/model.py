@@ -140,10 +140,13 @@ def compile_model(plasma, chords, priors):
     E_CL_I, E_CL_D, E_CH_I, E_CH_D = e["BaysarClI"], e["BaysarClD"], e["BaysarChI"], e["BaysarChD"]
     info = {"uline_names": [], "chord_line_uline": []}
 
-    def unique_line(key, kind, sp, tab_a, tab_b):
+    ul_d_rows = []
+
+    def unique_line(key, kind, sp, tab_a, tab_b, shape=None):
         if key not in ul_index:
             ul_index[key] = len(ul_rows)
             ul_rows.append([kind, sp, tab_a, tab_b])
+            ul_d_rows.append(list(shape) if shape is not None else [0.0] * e["BaysarUlD"]["UL_D_COUNT"])
             info["uline_names"].append(key)
         return ul_index[key]
 
@@ -209,7 +212,8 @@ def compile_model(plasma, chords, priors):
             ci[E_CL_I["CL_COMP_OFF"]] = len(comps)
             if isinstance(line, BalmerHydrogenLine):
                 sp = species.index(line.species)
-                u = unique_line(line.line, 0, sp, htab_index[line.line + "_exc"], htab_index[line.line + "_rec"])
+                u = unique_line(line.line, 0, sp, htab_index[line.line + "_exc"], htab_index[line.line + "_rec"],
+                                shape=[line.cwl, *line.loman_ij_abc, line.atomic_mass])
                 dop = _is_arange(line.wavelengths_doppler)
                 if dop is None:
                     raise ValueError("Doppler tap grid is not an arange")
@@ -253,6 +257,7 @@ def compile_model(plasma, chords, priors):
     sec["SEC_CL_D"] = np.array(cl_d_rows) if cl_d_rows else np.zeros((1, E_CL_D["CL_D_COUNT"]))
     sec["SEC_COMP_D"] = np.array(comps, dtype=float) if comps else np.zeros((1, 2))
     sec["SEC_UL_I"] = np.array(ul_rows, dtype=np.int32) if ul_rows else np.zeros((1, 4), np.int32)
+    sec["SEC_UL_D"] = np.array(ul_d_rows, dtype=float) if ul_d_rows else np.zeros((1, e["BaysarUlD"]["UL_D_COUNT"]))
     cat = lambda arrs, dt: np.concatenate(arrs).astype(dt) if arrs else np.zeros(2, dtype=dt)  # noqa: E731
     sec["SEC_Y"], sec["SEC_ERR"], sec["SEC_IF"] = cat(ys, float), cat(errs, float), cat(ifs, float)
     sec["SEC_PIX_IDX"], sec["SEC_PIX_FRAC"] = cat(pix_idx, np.int32), cat(pix_frac, float)

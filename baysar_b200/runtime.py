@@ -12,6 +12,7 @@ import subprocess
 PKG = pathlib.Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB_PATH = PKG / "libbaysar_b200.so"
+LINE_STRIDE = 16  # BAYSAR_LINE_STRIDE (include/baysar_b200.h)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--compiler-options", "-fPIC", "-shared"]
 
@@ -165,7 +166,7 @@ class DeviceModel:
         t = self.torch
         theta = self._theta(theta)
         n = theta.shape[0]
-        lines = t.empty((n, max(self.n_ulines, 1), 12), dtype=t.float64, device=theta.device)
+        lines = t.empty((n, max(self.n_ulines, 1), LINE_STRIDE), dtype=t.float64, device=theta.device)
         status = t.empty(n, dtype=t.int32, device=theta.device)
         prof = t.empty((n, 4, self.n_los), dtype=t.float64, device=theta.device) if want_profiles else None
         self._check(self.lib.baysar_eval_lines(self.handle, theta.data_ptr(), n, lines.data_ptr(),

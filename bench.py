@@ -267,13 +267,12 @@ def main():
     thetas_host = draw_thetas(post.plasma.theta_bounds, batch * total_steps, 20261019 + rank).reshape(total_steps, batch, n_params)
     thetas_dev = torch.as_tensor(thetas_host, device="cuda")
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
-    gathered = torch.empty(world * batch, dtype=torch.float64, device="cuda") if world > 1 else None
+    from baysar_b200.parallel import ShardedEvaluator
+
+    sharded = ShardedEvaluator(post.logp_batch)  # world 1: plain call; world > 1: + NCCL all-gather of logP
 
     def step(i):
-        logp = post.logp_batch(thetas_dev[i])
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, logp)
-        return logp
+        return sharded.evaluate_local(thetas_dev[i])
 
     for i in range(args.warmup):
         step(i)
@@ -345,7 +344,7 @@ def main():
     except OSError:
         pass
     hbm_bytes = batch * (8.0 * n_params + 8.0 + 4.0 + 8.0 * (len(post.chords) + len(post.priors))
-                         + 2 * 8.0 * 12 * post.model.n_ulines)
+                         + 2 * 8.0 * 16 * post.model.n_ulines)
     roofline = {
         "bound": "fp32",  # neither HBM nor tensor bound: the chord kernel is FP32-FMA / MUFU work on smem-resident data
         "kernel": "chord_stage_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,

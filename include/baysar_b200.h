@@ -52,9 +52,10 @@ typedef struct baysar_model baysar_model_t;
                                                  the shared-memory halo sized from the parameter bounds */
 
 /* number of doubles per (theta, line) record returned by baysar_eval_lines */
-#define BAYSAR_LINE_STRIDE 12
+#define BAYSAR_LINE_STRIDE 16
 /* record layout, by line kind:
- *   Balmer (kind 0): rec_sum, exc_sum, rec_ne, rec_te, exc_ne, exc_te, ti, f_rec, ems_ne, ems_te, emission_fitted, 0
+ *   Balmer (kind 0): rec_sum, exc_sum, rec_ne, rec_te, exc_ne, exc_te, ti, f_rec, ems_ne, ems_te, emission_fitted,
+ *                    gamma_rec^2.5, gamma_exc^2.5 (Stark half-widths), Doppler-shifted centre, Doppler sigma, 0
  *   ADAS406 (kind 1): emission_fitted, ems_ne, ems_conc, ems_te, ti, 0...
  *   XLine (kind 2):   emission_fitted, 0...                                                                       */
 

@@ -15,7 +15,7 @@ static ModelDev view(const unsigned char* blob) {
   d.a11_scd = (const double*)P(SEC_A11_SCD); d.h_ne = (const double*)P(SEC_H_NE); d.h_te = (const double*)P(SEC_H_TE);
   d.h_tab = (const double*)P(SEC_H_TAB); d.tau_grid = (const double*)P(SEC_TAU_GRID);
   d.spl_tx = (const double*)P(SEC_SPL_TX); d.spl_ty = (const double*)P(SEC_SPL_TY); d.spl_c = (const double*)P(SEC_SPL_C);
-  d.ul_i = (const int*)P(SEC_UL_I); d.pr_i = (const int*)P(SEC_PR_I); d.pr_d = (const double*)P(SEC_PR_D);
+  d.ul_i = (const int*)P(SEC_UL_I); d.ul_d = (const double*)P(SEC_UL_D); d.pr_i = (const int*)P(SEC_PR_I); d.pr_d = (const double*)P(SEC_PR_D);
   d.cso_off = (const int*)P(SEC_CSO_OFF); d.cso_ul = (const int*)P(SEC_CSO_UL); d.ch_i = (const int*)P(SEC_CH_I);
   d.ch_d = (const double*)P(SEC_CH_D); d.cl_i = (const int*)P(SEC_CL_I); d.cl_d = (const double*)P(SEC_CL_D);
   d.comp_d = (const double*)P(SEC_COMP_D); d.y = (const double*)P(SEC_Y); d.err = (const double*)P(SEC_ERR);

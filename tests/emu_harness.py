@@ -49,7 +49,7 @@ def emu_eval(blob, theta, chord=0, n_chords=1, n_priors=0, n_ul=1, L=50, P=1, F=
     theta = np.ascontiguousarray(theta, dtype=np.float64)
     n = theta.shape[0]
     out = dict(logp=np.zeros(n), status=np.zeros(n, dtype=np.uint32), comps=np.zeros((n, n_chords + n_priors)),
-               lines=np.zeros((n, max(n_ul, 1), 12)), profiles=np.zeros((n, 4, L)), spectra=np.zeros((n, P)),
+               lines=np.zeros((n, max(n_ul, 1), 16)), profiles=np.zeros((n, 4, L)), spectra=np.zeros((n, P)),
                fine_pre=np.zeros((n, F), dtype=np.float32), fine_post=np.zeros((n, F), dtype=np.float32))
     buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
