@@ -77,5 +77,5 @@ def test_stretch_move_is_affine_combination():
     # proposal - partner is parallel to walker - partner with ratio z: recover the partner and check membership
     keep = (1 - z).abs() > 0.05  # the back-solve is ill-conditioned for z ~ 1
     partner = (prop[keep] - z[keep, None] * w[keep]) / (1 - z[keep, None])
-    d = torch.cdist(partner, c).min(dim=1).values
+    d = (partner[:, None, :] - c[None, :, :]).norm(dim=2).min(dim=1).values
     assert keep.sum() > 32 and np.all(d.numpy() < 1e-9)
