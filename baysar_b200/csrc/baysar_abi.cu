@@ -1,6 +1,7 @@
 // C ABI of the B200-native BaySAR posterior path (include/baysar_b200.h): model upload, workspace, launches.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -10,6 +11,7 @@
 #include "../../include/baysar_b200.h"
 #include "chord_stage.cuh"
 #include "finalize.cuh"
+#include "if_contract.cuh"
 #include "los_stage.cuh"
 
 static thread_local std::string g_last_error;
@@ -23,6 +25,27 @@ static int fail(const std::string& msg) {
     cudaError_t e_ = (expr);                                                                   \
     if (e_ != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));    \
   } while (0)
+
+namespace {
+// Host-side packing of one chord's instrument function for the tensor-core contraction (if_contract.cuh).
+struct IfcPlan {
+  int m_lo = 0, m_hi = 0, pad_left = 0, n_tiles = 0, taps_len = 0;
+  int64_t pitch = 0, out_pitch = 0;
+  std::vector<float> taps_rev;  // [2][4][taps_len]
+};
+
+static float tf32_round(float v) {  // round to nearest, ties away from zero, 10-bit mantissa (cvt.rna.tf32.f32)
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
+static inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+}  // namespace
 
 struct baysar_model {
   int device = 0;
@@ -43,9 +66,20 @@ struct baysar_model {
   double* logp_stage = nullptr;
   int64_t stage_cap = 0;
   size_t chord_smem_max = 0;
-  // optional per-stage timing (bench.py roofline): 4 events per eval_logp call while profiling is on
+  // tensor-core path (if_contract.cuh): per chord plan (empty taps_rev = chord stays on the fused kernel)
+  std::vector<IfcPlan> ifc;
+  std::vector<float*> ifc_taps_dev;
+  bool any_ifc = false;
+  int64_t ifc_rows = 0;              // rows of the split / conv workspaces (multiple of 128)
+  float *split_hi = nullptr, *split_lo = nullptr, *conv = nullptr;
+  double *trapz_part = nullptr, *aux = nullptr;
+  int64_t split_pitch_max = 0, conv_pitch_max = 0;
+  int tiles_max = 0;
+  int last_launches = 3;
+  // optional per-stage timing (bench.py roofline): events tagged with the stage that ends at them
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
+  std::vector<int> prof_slots;
 };
 
 namespace {
@@ -99,6 +133,33 @@ __global__ void microbench_dfma_kernel(double* out, int iters, double a) {
   if (s == 12345.678) out[threadIdx.x] = s;
 }
 
+IfcPlan make_ifc_plan(const double* w, int KI, int k_lo, int k_hi, int F) {
+  IfcPlan pl;
+  const int o = (KI - 1) / 2;
+  pl.m_lo = floor_div(o - k_hi + 1, ifc::TILE_K);
+  pl.m_hi = floor_div(ifc::TILE_N - 1 + o - k_lo, ifc::TILE_K);
+  pl.pad_left = -ifc::TILE_K * pl.m_lo;
+  if (pl.pad_left < 0) pl.pad_left = 0;
+  pl.n_tiles = (F + ifc::TILE_N - 1) / ifc::TILE_N;
+  int64_t last_col = (int64_t)pl.pad_left + (int64_t)(pl.n_tiles - 1) * ifc::TILE_N + ifc::TILE_K * pl.m_hi + ifc::TILE_K;
+  if (last_col < pl.pad_left + F) last_col = pl.pad_left + F;
+  pl.pitch = (last_col + 31) / 32 * 32;
+  pl.out_pitch = (int64_t)pl.n_tiles * ifc::TILE_N;
+  pl.taps_len = (164 + ifc::TILE_K * (pl.m_hi - pl.m_lo) + 3) / 4 * 4;
+  const int x_max = ifc::TILE_N - 1 + o - ifc::TILE_K * pl.m_lo;
+  pl.taps_rev.assign((size_t)8 * pl.taps_len, 0.f);
+  for (int s = 0; s < 4; ++s) {
+    for (int i = 0; i < pl.taps_len; ++i) {
+      const int x = x_max - (i + s);  // copy_s[i] = rev[i + s] = w[x_max - i - s]
+      float v = (x >= k_lo && x < k_hi) ? (float)w[x] : 0.f;
+      float hi = tf32_round(v), lo = tf32_round(v - hi);
+      pl.taps_rev[(size_t)s * pl.taps_len + i] = hi;
+      pl.taps_rev[(size_t)(4 + s) * pl.taps_len + i] = lo;
+    }
+  }
+  return pl;
+}
+
 int ensure_workspace(baysar_model* m, int64_t n) {
   if (n <= m->cap) return 0;
   int64_t cap = n < 1024 ? 1024 : n;
@@ -135,18 +196,120 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
   return 0;
 }
 
+int ensure_ifc_workspace(baysar_model* m, int64_t n) {
+  // rows handled per pass of the tensor-core path: bounded so that the split / convolved spectra stay within a
+  // fixed HBM budget (8 bytes of operands + 4 bytes of output per fine-grid point and row)
+  const int64_t budget = (int64_t)24 << 30;
+  const int64_t per_row = 4 * (2 * m->split_pitch_max + m->conv_pitch_max) + 8 * m->tiles_max;
+  int64_t rows = (n + ifc::TILE_M - 1) / ifc::TILE_M * ifc::TILE_M;
+  int64_t max_rows = budget / per_row / ifc::TILE_M * ifc::TILE_M;
+  if (max_rows < ifc::TILE_M) max_rows = ifc::TILE_M;
+  if (rows > max_rows) rows = max_rows;
+  if (rows <= m->ifc_rows) return 0;
+  cudaFree(m->split_hi); cudaFree(m->split_lo); cudaFree(m->conv); cudaFree(m->trapz_part); cudaFree(m->aux);
+  m->split_hi = m->split_lo = m->conv = nullptr; m->trapz_part = m->aux = nullptr; m->ifc_rows = 0;
+  CUDA_OK(cudaMalloc(&m->split_hi, sizeof(float) * rows * m->split_pitch_max));
+  CUDA_OK(cudaMalloc(&m->split_lo, sizeof(float) * rows * m->split_pitch_max));
+  CUDA_OK(cudaMalloc(&m->conv, sizeof(float) * rows * m->conv_pitch_max));
+  CUDA_OK(cudaMalloc(&m->trapz_part, sizeof(double) * rows * m->tiles_max));
+  CUDA_OK(cudaMalloc(&m->aux, sizeof(double) * rows * BAYSAR_AUX_STRIDE));
+  // rows past the end of a batch are multiplied too (M = 128 granularity): keep them finite
+  CUDA_OK(cudaMemset(m->split_hi, 0, sizeof(float) * rows * m->split_pitch_max));
+  CUDA_OK(cudaMemset(m->split_lo, 0, sizeof(float) * rows * m->split_pitch_max));
+  m->ifc_rows = rows;
+  return 0;
+}
+
+// stage tags for the optional event log
+enum { ST_BEGIN = -1, ST_LOS = 0, ST_CHORD = 1, ST_CONTRACT = 2, ST_PIXEL = 3, ST_FINAL = 4, ST_COUNT = 5 };
+
+int mark(baysar_model* m, int slot, cudaStream_t stream) {
+  if (!m->profiling) return 0;
+  cudaEvent_t ev;
+  CUDA_OK(cudaEventCreate(&ev));
+  CUDA_OK(cudaEventRecord(ev, stream));
+  m->prof_events.push_back(ev);
+  m->prof_slots.push_back(slot);
+  return 0;
+}
+
 int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_begin, int n_chords,
                   const double* lines, double* comps, double* spectra, float* fine_pre, float* fine_post,
                   uint32_t* status, cudaStream_t stream) {
-  ChordArgs a;
-  a.theta = theta; a.n = n; a.chord_begin = chord_begin; a.lines = lines; a.components = comps;
-  a.spectra = spectra; a.fine_pre = fine_pre; a.fine_post = fine_post; a.status = status;
   constexpr int NT = 256;
-  CUDA_OK(cudaFuncSetAttribute(chord_stage_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)m->chord_smem_max));
-  dim3 grid((unsigned)n, (unsigned)n_chords);
-  chord_stage_kernel<NT><<<grid, NT, m->chord_smem_max, stream>>>(m->dev, a);
-  CUDA_OK(cudaGetLastError());
+  const int n_params = (int)m->I[I_N_PARAMS];
+  const int ncols = (int)(m->I[I_N_CHORDS] + m->I[I_N_PRIORS]);
+  bool any = false;
+  for (int c = chord_begin; c < chord_begin + n_chords; ++c) any = any || !m->ifc[c].taps_rev.empty();
+  if (!any) {
+    ChordArgs a{};
+    a.theta = theta; a.n = n; a.chord_begin = chord_begin; a.lines = lines; a.components = comps;
+    a.spectra = spectra; a.fine_pre = fine_pre; a.fine_post = fine_post; a.status = status;
+    CUDA_OK(cudaFuncSetAttribute(chord_stage_kernel<NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)m->chord_smem_max));
+    dim3 grid((unsigned)n, (unsigned)n_chords);
+    chord_stage_kernel<NT, 0><<<grid, NT, m->chord_smem_max, stream>>>(m->dev, a);
+    CUDA_OK(cudaGetLastError());
+    m->last_launches += 1;
+    if (mark(m, ST_CHORD, stream)) return 1;
+    return 0;
+  }
+  if (ensure_ifc_workspace(m, n)) return 1;
+  for (int c = chord_begin; c < chord_begin + n_chords; ++c) {
+    const IfcPlan& pl = m->ifc[c];
+    const int P = m->ch_i[c * CH_I_COUNT + CH_P], F = m->ch_i[c * CH_I_COUNT + CH_F];
+    if (pl.taps_rev.empty()) {
+      ChordArgs a{};
+      a.theta = theta; a.n = n; a.chord_begin = c; a.lines = lines; a.components = comps;
+      a.spectra = spectra; a.fine_pre = fine_pre; a.fine_post = fine_post; a.status = status;
+      CUDA_OK(cudaFuncSetAttribute(chord_stage_kernel<NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)m->chord_smem_max));
+      chord_stage_kernel<NT, 0><<<dim3((unsigned)n, 1), NT, m->chord_smem_max, stream>>>(m->dev, a);
+      CUDA_OK(cudaGetLastError());
+      m->last_launches += 1;
+      if (mark(m, ST_CHORD, stream)) return 1;
+      continue;
+    }
+    for (int64_t r0 = 0; r0 < n; r0 += m->ifc_rows) {
+      const int64_t rows = (n - r0) < m->ifc_rows ? (n - r0) : m->ifc_rows;
+      const int64_t rows128 = (rows + ifc::TILE_M - 1) / ifc::TILE_M * ifc::TILE_M;
+      // K2a: spectrum -> TF32-split rows + per-theta scalars
+      ChordArgs a{};
+      a.theta = theta + r0 * n_params; a.n = rows; a.chord_begin = c;
+      a.lines = lines + r0 * m->I[I_N_ULINES] * BAYSAR_LINE_STRIDE;
+      a.components = comps + r0 * ncols; a.spectra = nullptr;
+      a.fine_pre = fine_pre ? fine_pre + r0 * F : nullptr; a.fine_post = nullptr; a.status = status + r0;
+      a.split_hi = m->split_hi; a.split_lo = m->split_lo; a.split_pitch = pl.pitch; a.split_pad = pl.pad_left;
+      a.aux = m->aux;
+      CUDA_OK(cudaFuncSetAttribute(chord_stage_kernel<NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)m->chord_smem_max));
+      chord_stage_kernel<NT, 1><<<dim3((unsigned)rows, 1), NT, m->chord_smem_max, stream>>>(m->dev, a);
+      CUDA_OK(cudaGetLastError());
+      if (mark(m, ST_CHORD, stream)) return 1;
+      // K2b: tcgen05 contraction with the banded-Toeplitz instrument matrix
+      ifc::Params p{};
+      p.s_hi = m->split_hi; p.s_lo = m->split_lo; p.pitch = pl.pitch; p.pad_left = pl.pad_left; p.F = F;
+      p.n_rows = (int)rows128; p.m_lo = pl.m_lo; p.m_hi = pl.m_hi; p.taps_rev = m->ifc_taps_dev[c];
+      p.taps_len = pl.taps_len; p.row_min = nullptr; p.aux = m->aux; p.aux_rows = (int)rows;
+      p.out = m->conv; p.out_pitch = pl.out_pitch; p.trapz_part = m->trapz_part; p.n_tiles = pl.n_tiles;
+      const size_t smem = ifc::smem_bytes(pl.taps_len);
+      CUDA_OK(cudaFuncSetAttribute(ifc::if_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ifc::if_contract_kernel<<<dim3((unsigned)pl.n_tiles, (unsigned)(rows128 / ifc::TILE_M)), ifc::THREADS, smem,
+                                stream>>>(p);
+      CUDA_OK(cudaGetLastError());
+      if (mark(m, ST_CONTRACT, stream)) return 1;
+      // K2c: area renormalisation, wavelength map, likelihood
+      PixelArgs pa{};
+      pa.theta = theta + r0 * n_params; pa.n = rows; pa.chord = c; pa.conv = m->conv; pa.conv_pitch = pl.out_pitch;
+      pa.trapz_part = m->trapz_part; pa.n_tiles = pl.n_tiles; pa.aux = m->aux; pa.components = comps + r0 * ncols;
+      pa.spectra = spectra ? spectra + r0 * P : nullptr; pa.fine_post = fine_post ? fine_post + r0 * F : nullptr;
+      pa.status = status + r0;
+      pixel_stage_kernel<128><<<(unsigned)rows, 128, 0, stream>>>(m->dev, pa);
+      CUDA_OK(cudaGetLastError());
+      if (mark(m, ST_PIXEL, stream)) return 1;
+      m->last_launches += 3;
+    }
+  }
   return 0;
 }
 
@@ -239,6 +402,30 @@ int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar
     return fail("fine grid too long for the shared-memory chord stage (needs " + std::to_string(smem_max) + " B)");
   }
   m->chord_smem_max = smem_max;
+  // tensor-core contraction for chords with a long, theta-independent instrument function
+  const char* env = getenv("BAYSAR_IFC");
+  const bool ifc_enabled = !(env && env[0] == '0');
+  const char* env_taps = getenv("BAYSAR_IFC_MIN_TAPS");
+  const int min_taps = env_taps ? atoi(env_taps) : 160;
+  m->ifc.resize(n_chords);
+  m->ifc_taps_dev.assign(n_chords, nullptr);
+  const double* ifn_host = static_cast<const double*>(host.ptr(SEC_IF));
+  for (int c = 0; c < n_chords; ++c) {
+    const int* ch = m->ch_i + c * CH_I_COUNT;
+    const int window = ch[CH_IF_KHI] - ch[CH_IF_KLO];
+    if (!ifc_enabled || ch[CH_CALINT_IDX] >= 0 || window < min_taps || ch[CH_F] < 256) continue;
+    m->ifc[c] = make_ifc_plan(ifn_host + ch[CH_IF_OFF], ch[CH_KI], ch[CH_IF_KLO], ch[CH_IF_KHI], ch[CH_F]);
+    const IfcPlan& pl = m->ifc[c];
+    if (ifc::smem_bytes(pl.taps_len) > 227 * 1024) { m->ifc[c] = IfcPlan(); continue; }
+    cudaError_t e2 = cudaMalloc(&m->ifc_taps_dev[c], sizeof(float) * pl.taps_rev.size());
+    if (e2 == cudaSuccess)
+      e2 = cudaMemcpy(m->ifc_taps_dev[c], pl.taps_rev.data(), sizeof(float) * pl.taps_rev.size(), cudaMemcpyHostToDevice);
+    if (e2 != cudaSuccess) { baysar_model_destroy(m); return fail(std::string("ifc taps upload: ") + cudaGetErrorString(e2)); }
+    m->any_ifc = true;
+    m->split_pitch_max = pl.pitch > m->split_pitch_max ? pl.pitch : m->split_pitch_max;
+    m->conv_pitch_max = pl.out_pitch > m->conv_pitch_max ? pl.out_pitch : m->conv_pitch_max;
+    m->tiles_max = pl.n_tiles > m->tiles_max ? pl.n_tiles : m->tiles_max;
+  }
   *out = m;
   return 0;
 }
@@ -248,6 +435,8 @@ void baysar_model_destroy(baysar_model_t* m) {
   cudaSetDevice(m->device);
   cudaFree(m->blob_dev); cudaFree(m->lines); cudaFree(m->comps); cudaFree(m->hdr); cudaFree(m->status);
   cudaFree(m->theta_stage); cudaFree(m->logp_stage);
+  cudaFree(m->split_hi); cudaFree(m->split_lo); cudaFree(m->conv); cudaFree(m->trapz_part); cudaFree(m->aux);
+  for (float* t : m->ifc_taps_dev) cudaFree(t);
   for (cudaEvent_t ev : m->prof_events) cudaEventDestroy(ev);
   delete m;
 }
@@ -264,7 +453,8 @@ int64_t baysar_model_query(const baysar_model_t* m, int what, int arg) {
     case 6: return (arg >= 0 && arg < m->I[I_N_CHORDS]) ? m->ch_i[arg * CH_I_COUNT + CH_P] : -1;
     case 7: return (arg >= 0 && arg < m->I[I_N_CHORDS]) ? m->ch_i[arg * CH_I_COUNT + CH_F] : -1;
     case 8: return m->I[I_L];
-    case 9: return 3;
+    case 9: return m->last_launches;
+    case 11: return m->any_ifc ? 1 : 0;
     case 10: return (int64_t)m->chord_smem_max;
     default: return -1;
   }
@@ -279,24 +469,18 @@ int baysar_eval_logp(baysar_model_t* m, const double* theta, int64_t n, double* 
   if (ensure_workspace(m, n)) return 1;
   uint32_t* st = status ? status : m->status;
   double* comps = components ? components : m->comps;
-  auto mark = [&]() -> int {
-    if (!m->profiling) return 0;
-    cudaEvent_t ev;
-    CUDA_OK(cudaEventCreate(&ev));
-    CUDA_OK(cudaEventRecord(ev, stream));
-    m->prof_events.push_back(ev);
-    return 0;
-  };
-  if (mark()) return 1;
+  m->last_launches = 0;
+  if (mark(m, ST_BEGIN, stream)) return 1;
   if (launch_los(m, theta, n, m->lines, comps, nullptr, st, stream)) return 1;
-  if (mark()) return 1;
+  m->last_launches += 1;
+  if (mark(m, ST_LOS, stream)) return 1;
   if (launch_chords(m, theta, n, 0, (int)m->I[I_N_CHORDS], m->lines, comps, nullptr, nullptr, nullptr, st, stream))
     return 1;
-  if (mark()) return 1;
   const int ncols = (int)(m->I[I_N_CHORDS] + m->I[I_N_PRIORS]);
   finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(comps, ncols, n, logp, st);
   CUDA_OK(cudaGetLastError());
-  if (mark()) return 1;
+  m->last_launches += 1;
+  if (mark(m, ST_FINAL, stream)) return 1;
   return 0;
 }
 
@@ -351,6 +535,7 @@ int baysar_model_set_profiling(baysar_model_t* m, int on) {
   if (!m) return fail("null model");
   for (cudaEvent_t ev : m->prof_events) cudaEventDestroy(ev);
   m->prof_events.clear();
+  m->prof_slots.clear();
   m->profiling = on != 0;
   return 0;
 }
@@ -358,18 +543,66 @@ int baysar_model_set_profiling(baysar_model_t* m, int on) {
 int baysar_model_get_profile(baysar_model_t* m, double* stage_ms, int64_t* calls) {
   if (!m || !stage_ms || !calls) return fail("null argument");
   CUDA_OK(cudaSetDevice(m->device));
-  stage_ms[0] = stage_ms[1] = stage_ms[2] = 0.0;
-  *calls = (int64_t)(m->prof_events.size() / 4);
-  for (size_t c = 0; c + 3 < m->prof_events.size(); c += 4) {
-    CUDA_OK(cudaEventSynchronize(m->prof_events[c + 3]));
-    for (int k = 0; k < 3; ++k) {
-      float ms = 0.f;
-      CUDA_OK(cudaEventElapsedTime(&ms, m->prof_events[c + k], m->prof_events[c + k + 1]));
-      stage_ms[k] += ms;
-    }
+  for (int k = 0; k < ST_COUNT; ++k) stage_ms[k] = 0.0;
+  *calls = 0;
+  for (size_t e = 0; e < m->prof_events.size(); ++e) {
+    if (m->prof_slots[e] == ST_BEGIN) { *calls += 1; continue; }
+    CUDA_OK(cudaEventSynchronize(m->prof_events[e]));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, m->prof_events[e - 1], m->prof_events[e]));
+    stage_ms[m->prof_slots[e]] += ms;
   }
   for (cudaEvent_t ev : m->prof_events) cudaEventDestroy(ev);
   m->prof_events.clear();
+  m->prof_slots.clear();
+  return 0;
+}
+
+int baysar_debug_if_contract(const float* spectra_dev, int64_t n_rows, int F, const double* taps_host, int KI,
+                             const float* row_min_dev, float* out_dev, double* trapz_dev, int64_t* out_pitch,
+                             int* n_tiles, float* elapsed_ms) {
+  // Unit-test hook for the tcgen05 contraction: out[r][j] = max(sum_k w[k] S[r][j + (KI-1)/2 - k], row_min[r]).
+  if (!spectra_dev || !taps_host || !out_dev) return fail("null argument");
+  if (n_rows % ifc::TILE_M != 0) return fail("n_rows must be a multiple of 128");
+  double wmax = 0.0;
+  for (int k = 0; k < KI; ++k) wmax = fabs(taps_host[k]) > wmax ? fabs(taps_host[k]) : wmax;
+  int k_lo = KI, k_hi = 0;
+  for (int k = 0; k < KI; ++k)
+    if (fabs(taps_host[k]) > 1e-17 * wmax) { k_lo = k < k_lo ? k : k_lo; k_hi = k + 1; }
+  IfcPlan pl = make_ifc_plan(taps_host, KI, k_lo, k_hi, F);
+  if (out_pitch) *out_pitch = pl.out_pitch;
+  if (n_tiles) *n_tiles = pl.n_tiles;
+  float *hi = nullptr, *lo = nullptr, *taps = nullptr;
+  CUDA_OK(cudaMalloc(&hi, sizeof(float) * n_rows * pl.pitch));
+  CUDA_OK(cudaMalloc(&lo, sizeof(float) * n_rows * pl.pitch));
+  CUDA_OK(cudaMalloc(&taps, sizeof(float) * pl.taps_rev.size()));
+  CUDA_OK(cudaMemset(hi, 0, sizeof(float) * n_rows * pl.pitch));
+  CUDA_OK(cudaMemset(lo, 0, sizeof(float) * n_rows * pl.pitch));
+  CUDA_OK(cudaMemcpy(taps, pl.taps_rev.data(), sizeof(float) * pl.taps_rev.size(), cudaMemcpyHostToDevice));
+  ifc::split_rows_kernel<<<dim3(8, (unsigned)n_rows), 256>>>(spectra_dev, n_rows, F, hi, lo, pl.pitch, pl.pad_left);
+  CUDA_OK(cudaGetLastError());
+  ifc::Params p;
+  p.s_hi = hi; p.s_lo = lo; p.pitch = pl.pitch; p.pad_left = pl.pad_left; p.F = F; p.n_rows = (int)n_rows;
+  p.m_lo = pl.m_lo; p.m_hi = pl.m_hi; p.taps_rev = taps; p.taps_len = pl.taps_len; p.row_min = row_min_dev; p.aux = nullptr; p.aux_rows = 0;
+  p.out = out_dev; p.out_pitch = pl.out_pitch; p.trapz_part = trapz_dev; p.n_tiles = pl.n_tiles;
+  const size_t smem = ifc::smem_bytes(pl.taps_len);
+  CUDA_OK(cudaFuncSetAttribute(ifc::if_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  dim3 grid((unsigned)pl.n_tiles, (unsigned)(n_rows / ifc::TILE_M));
+  for (int rep = 0; rep < 2; ++rep) {
+    CUDA_OK(cudaEventRecord(e0, 0));
+    ifc::if_contract_kernel<<<grid, ifc::THREADS, smem>>>(p);
+    CUDA_OK(cudaEventRecord(e1, 0));
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventSynchronize(e1));
+  }
+  float ms = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+  if (elapsed_ms) *elapsed_ms = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(hi); cudaFree(lo); cudaFree(taps);
   return 0;
 }
 

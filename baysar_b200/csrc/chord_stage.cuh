@@ -33,7 +33,15 @@ struct ChordArgs {
   float* fine_pre;          // optional [N][F]
   float* fine_post;         // optional [N][F]
   uint32_t* status;         // [N] OR-ed
+  // MODE 1 (spectral stage of the tensor-core path): TF32-split pre-convolution spectra and per-theta scalars
+  float* split_hi;          // [rows][split_pitch], written at column split_pad + j
+  float* split_lo;
+  int64_t split_pitch;
+  int split_pad;
+  double* aux;              // [N][BAYSAR_AUX_STRIDE]: pre-area, minimum, 4 float64 end outputs
 };
+
+#define BAYSAR_AUX_STRIDE 8
 
 __host__ __device__ static inline int pad_index(int i) { return i ^ ((i >> 3) & 4); }
 
@@ -84,6 +92,25 @@ BAYSAR_DEV void conv8(const float* buf, int e0, const float* tq, int nq, float* 
   }
 }
 
+// v ~ hi + lo with both terms representable in TF32 (10-bit mantissa): the operands of the 3xTF32 contraction
+#ifndef BAYSAR_CPU_EMU
+BAYSAR_DEV void split_tf32_pair(float v, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+  hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+  lo = __uint_as_float(l);
+}
+#else
+BAYSAR_DEV float emu_tf32(float v) {
+  uint32_t u; std::memcpy(&u, &v, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  float r; std::memcpy(&r, &u, 4);
+  return r;
+}
+BAYSAR_DEV void split_tf32_pair(float v, float& hi, float& lo) { hi = emu_tf32(v); lo = emu_tf32(v - hi); }
+#endif
+
 // exp(arg) for arg <= 0 computed as 2^n * ex2(f): the argument reduction is done in float64 so that the result
 // keeps float32 relative accuracy even for arg ~ -40 (a narrow Gaussian sampled far from its centre).
 BAYSAR_DEV float exp_neg_f32(double arg) {
@@ -95,10 +122,79 @@ BAYSAR_DEV float exp_neg_f32(double arg) {
   return exp2f(f) * __int_as_float((e + 127) << 23);
 }
 
+// Fetchers for the convolved fine-grid spectrum: shared memory (fused kernel) or global memory (tensor-core path)
+struct FetchSmem {
+  const float* buf; int halo;
+  BAYSAR_DEV double operator()(int i) const { return (double)buf[pad_index(halo + i)]; }
+};
+struct FetchGlobal {
+  const float* row;
+  BAYSAR_DEV double operator()(int i) const { return (double)row[i]; }
+};
+
+// Area renormalisation, + background, wavelength map, clip, Cauchy likelihood (spectrometers.py:286-310, :154-195).
+// `post` and `pre` are the trapz integrals after / before the instrument convolution; edge64 the four end outputs.
+template <int NT, class Fetch>
+BAYSAR_DEV void pixel_likelihood(const ModelDev& m, const int* ch, const double* chd, const double* th, int64_t n, int c,
+                                 int ncomp_cols, double pre, double post, const double* edge64, Fetch fetch,
+                                 double* scratch, double* components, double* spectra, float* fine_post, uint32_t& st) {
+  const int tid = threadIdx.x;
+  const int F = ch[CH_F], P = ch[CH_P];
+  const double x0 = chd[CH_X0], delta = chd[CH_DELTA];
+  const double ratio = post / pre;
+  const double ratio2 = (post / ratio) / pre;
+  if (!(fabs(ratio2 - 1.0) <= 1e-8 + 1e-2)) st |= 1u << 9;  // np.isclose(ratio2, 1, rtol=1e-2)
+  const double bg = pow(10.0, th[ch[CH_BG_IDX]]);
+  if (fine_post) {
+    float* o_ = fine_post + n * (int64_t)F;
+    for (int j = tid; j < F; j += NT) o_[j] = (float)(fetch(j) / ratio + bg);
+  }
+  const int poff = ch[CH_PIX_OFF];
+  const int cw_idx = ch[CH_CALWAVE_IDX];
+  const double cwl_map = cw_idx >= 0 ? th[cw_idx] : chd[CH_CALWAVE_CWL];
+  const double disp_map = cw_idx >= 0 ? th[cw_idx + 1] : chd[CH_CALWAVE_DISP];
+  double acc = 0.0;
+  for (int p = tid; p < P; p += NT) {
+    int i; double w;
+    if (cw_idx >= 0) {
+      double px = ((double)p - chd[CH_PIX_MEAN]) * disp_map + cwl_map;
+      double g = floor((px - x0) / delta);
+      int jj = g < 0.0 ? 0 : (g > (double)(F - 1) ? F - 1 : (int)g);
+      while (jj > 0 && grid_x(x0, delta, jj - 1) >= px) --jj;
+      while (jj < F && grid_x(x0, delta, jj) < px) ++jj;
+      i = jj - 1;
+      i = i < 0 ? 0 : (i > F - 2 ? F - 2 : i);
+      double xi = grid_x(x0, delta, i);
+      w = (px - xi) / (grid_x(x0, delta, i + 1) - xi);
+    } else {
+      i = m.pix_idx[poff + p];
+      w = m.pix_frac[poff + p];
+    }
+    double v0 = (i < 2) ? edge64[i] : (i >= F - 2 ? edge64[i - (F - 4)] : fetch(i));
+    int i1 = i + 1;
+    double v1 = (i1 < 2) ? edge64[i1] : (i1 >= F - 2 ? edge64[i1 - (F - 4)] : fetch(i1));
+    double fm = (v0 + w * (v1 - v0)) / ratio + bg;
+    fm = fm < bg ? bg : fm;
+    if (!(fm - fm == 0.0)) st |= 1u << 10;
+    if (spectra) spectra[n * (int64_t)P + p] = fm;
+    double r = (m.y[poff + p] - fm) / m.err[poff + p];
+    double r2 = r * r;
+    if (r2 == 0.0) st |= 1u << 11;
+    if (!(r2 - r2 == 0.0)) st |= 1u << 12;
+    acc += log(1.0 + r2);
+  }
+  double red4[1] = {acc};
+  block_sum<NT, 1>(red4, scratch);
+  if (tid == 0) components[n * (int64_t)ncomp_cols + c] = -red4[0];
+}
+
 #ifndef BAYSAR_CHORD_MIN_BLOCKS
 #define BAYSAR_CHORD_MIN_BLOCKS 3  // 3 CTAs (24 warps) per SM: caps the kernel at 80 registers, no spills
 #endif
-template <int NT>
+// MODE 0: fused (spectrum -> instrument convolution on the FP32 pipe -> likelihood, everything in shared memory).
+// MODE 1: spectral stage only: writes the TF32-split pre-convolution spectrum and the per-theta scalars for the
+//         tensor-core contraction (if_contract.cuh) and the pixel stage (pixel_stage_kernel below).
+template <int NT, int MODE>
 __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kernel(ModelDev m, ChordArgs a) {
 #ifdef BAYSAR_CPU_EMU
   unsigned char* chord_smem_raw = emu_dynamic_smem();
@@ -113,7 +209,7 @@ __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kerne
   const int ncomp_cols = (int)I[I_N_CHORDS] + (int)I[I_N_PRIORS];
   const int* ch = m.ch_i + c * CH_I_COUNT;
   const double* chd = m.ch_d + c * CH_D_COUNT;
-  const int F = ch[CH_F], P = ch[CH_P], HALO = ch[CH_HALO], TAPS_MAX = ch[CH_TAPS_MAX];
+  const int F = ch[CH_F], HALO = ch[CH_HALO], TAPS_MAX = ch[CH_TAPS_MAX];
   const double x0 = chd[CH_X0], delta = chd[CH_DELTA], dl = chd[CH_DL];
   const double* th = a.theta + n * n_params;
   const double* lines_n = a.lines + n * (int64_t)n_ul * BAYSAR_LINE_STRIDE;
@@ -385,6 +481,40 @@ __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kerne
   const int nq_if = (q_max_if - q_start_if + 1 + 3) & ~3;
   __syncthreads();
 
+  // the four end outputs in float64: they set the slope interp1d extrapolates with (sampled wavelength maps)
+  if (warp < 4) {
+    int j = warp < 2 ? warp : F - 4 + warp;
+    double s = 0.0;
+    for (int qi = lane; qi < nq_if; qi += 32) s += (double)tapq[qi] * (double)A_AT(j + q_start_if + qi);
+    s = warp_sum(s);
+    if (lane == 0) edge64[warp] = s < (double)mn ? (double)mn : s;
+  }
+
+  if (MODE == 1) {
+    // ================= hand the spectrum to the tensor-core contraction =========================================
+    __syncthreads();
+    float* hi = a.split_hi + n * a.split_pitch + a.split_pad;
+    float* lo = a.split_lo + n * a.split_pitch + a.split_pad;
+    // the workspace is shared by chords with different paddings: (re)write this row's zero padding as well
+    for (int j = tid - a.split_pad; j < 0; j += NT) { hi[j] = 0.f; lo[j] = 0.f; }
+    for (int64_t j = F + tid; j < a.split_pitch - a.split_pad; j += NT) { hi[j] = 0.f; lo[j] = 0.f; }
+    for (int j = tid; j < F; j += NT) {
+      const float v = A_AT(j);
+      float h, l;
+      split_tf32_pair(v, h, l);
+      hi[j] = h;
+      lo[j] = l;
+    }
+    if (tid == 0) {
+      double* ax = a.aux + n * BAYSAR_AUX_STRIDE;
+      ax[0] = pre; ax[1] = (double)mn; ax[2] = edge64[0]; ax[3] = edge64[1]; ax[4] = edge64[2]; ax[5] = edge64[3];
+      ax[6] = 0.0; ax[7] = 0.0;
+    }
+    st = __syncthreads_or((int)st);
+    if (tid == 0 && st) atomicOr(&a.status[n], st);
+    return;
+  }
+
   // ================= instrument convolution, clip at the pre-convolution minimum (spectrometers.py:269-271) =====
   double post_s = 0.0;
   bad = 0;
@@ -404,67 +534,63 @@ __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kerne
     *reinterpret_cast<float4*>(bufB + pad_index(HALO + j0)) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     *reinterpret_cast<float4*>(bufB + pad_index(HALO + j0 + 4)) = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
-  // the four end outputs in float64: they set the slope interp1d extrapolates with (sampled wavelength maps)
-  if (warp < 4) {
-    int j = warp < 2 ? warp : F - 4 + warp;
-    double s = 0.0;
-    for (int qi = lane; qi < nq_if; qi += 32) s += (double)tapq[qi] * (double)A_AT(j + q_start_if + qi);
-    s = warp_sum(s);
-    if (lane == 0) edge64[warp] = s < (double)mn ? (double)mn : s;
-  }
   double red3[1] = {post_s};
   block_sum<NT, 1>(red3, scratch);
   if (__syncthreads_or(bad)) st |= 1u << 8;
   const double post = dl * red3[0];
-  const double ratio = post / pre;
-  const double ratio2 = (post / ratio) / pre;
-  if (!(fabs(ratio2 - 1.0) <= 1e-8 + 1e-2)) st |= 1u << 9;  // np.isclose(ratio2, 1, rtol=1e-2)
-  const double bg = pow(10.0, th[ch[CH_BG_IDX]]);
-  if (a.fine_post) {
-    float* o_ = a.fine_post + n * (int64_t)F;
-    for (int j = tid; j < F; j += NT) o_[j] = (float)((double)B_AT(j) / ratio + bg);
-  }
-
-  // ================= wavelength map, clip at the background, Cauchy likelihood (spectrometers.py:299-310, :154-195)
-  const int poff = ch[CH_PIX_OFF];
-  const int cw_idx = ch[CH_CALWAVE_IDX];
-  const double cwl_map = cw_idx >= 0 ? th[cw_idx] : chd[CH_CALWAVE_CWL];
-  const double disp_map = cw_idx >= 0 ? th[cw_idx + 1] : chd[CH_CALWAVE_DISP];
-  double acc = 0.0;
-  for (int p = tid; p < P; p += NT) {
-    int i; double w;
-    if (cw_idx >= 0) {
-      double px = ((double)p - chd[CH_PIX_MEAN]) * disp_map + cwl_map;
-      double g = floor((px - x0) / delta);
-      int jj = g < 0.0 ? 0 : (g > (double)(F - 1) ? F - 1 : (int)g);
-      while (jj > 0 && grid_x(x0, delta, jj - 1) >= px) --jj;
-      while (jj < F && grid_x(x0, delta, jj) < px) ++jj;
-      i = jj - 1;
-      i = i < 0 ? 0 : (i > F - 2 ? F - 2 : i);
-      double xi = grid_x(x0, delta, i);
-      w = (px - xi) / (grid_x(x0, delta, i + 1) - xi);
-    } else {
-      i = m.pix_idx[poff + p];
-      w = m.pix_frac[poff + p];
-    }
-    double v0 = (i < 2) ? edge64[i] : (i >= F - 2 ? edge64[i - (F - 4)] : (double)B_AT(i));
-    int i1 = i + 1;
-    double v1 = (i1 < 2) ? edge64[i1] : (i1 >= F - 2 ? edge64[i1 - (F - 4)] : (double)B_AT(i1));
-    double fm = (v0 + w * (v1 - v0)) / ratio + bg;
-    fm = fm < bg ? bg : fm;
-    if (!(fm - fm == 0.0)) st |= 1u << 10;
-    if (a.spectra) a.spectra[n * (int64_t)P + p] = fm;
-    double r = (m.y[poff + p] - fm) / m.err[poff + p];
-    double r2 = r * r;
-    if (r2 == 0.0) st |= 1u << 11;
-    if (!(r2 - r2 == 0.0)) st |= 1u << 12;
-    acc += log(1.0 + r2);
-  }
-  double red4[1] = {acc};
-  block_sum<NT, 1>(red4, scratch);
-  if (tid == 0) a.components[n * (int64_t)ncomp_cols + c] = -red4[0];
+  FetchSmem fetch{bufB, HALO};
+  pixel_likelihood<NT>(m, ch, chd, th, n, c, ncomp_cols, pre, post, edge64, fetch, scratch, a.components, a.spectra,
+                       a.fine_post, st);
   st = __syncthreads_or((int)st);
   if (tid == 0 && st) atomicOr(&a.status[n], st);
 #undef A_AT
 #undef B_AT
+}
+
+// K2c — pixel / likelihood stage of the tensor-core path: one CTA per (theta, chord).  Reads the convolved spectrum
+// the contraction kernel left in global memory (L2-resident), its per-tile trapz partials (summed in tile order:
+// deterministic) and the scalars of the spectral stage.
+struct PixelArgs {
+  const double* theta;
+  int64_t n;
+  int chord;
+  const float* conv;        // [rows][conv_pitch]
+  int64_t conv_pitch;
+  const double* trapz_part; // [rows][n_tiles]
+  int n_tiles;
+  const double* aux;        // [N][BAYSAR_AUX_STRIDE]
+  double* components;
+  double* spectra;          // optional [N][P]
+  float* fine_post;         // optional [N][F]
+  uint32_t* status;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) pixel_stage_kernel(ModelDev m, PixelArgs a) {
+#ifdef BAYSAR_CPU_EMU
+  double* scratch = reinterpret_cast<double*>(emu_dynamic_smem());
+#else
+  __shared__ double scratch[64];
+#endif
+  const int tid = threadIdx.x;
+  const int64_t n = blockIdx.x;
+  const int c = a.chord;
+  const int64_t* I = m.I;
+  const int n_params = (int)I[I_N_PARAMS];
+  const int ncomp_cols = (int)I[I_N_CHORDS] + (int)I[I_N_PRIORS];
+  const int* ch = m.ch_i + c * CH_I_COUNT;
+  const double* chd = m.ch_d + c * CH_D_COUNT;
+  const double* th = a.theta + n * n_params;
+  const double* ax = a.aux + n * BAYSAR_AUX_STRIDE;
+  uint32_t st = 0;
+  double post_s = 0.0;
+  const double* part = a.trapz_part + n * (int64_t)a.n_tiles;
+  for (int t = 0; t < a.n_tiles; ++t) post_s += part[t];
+  if (!(post_s - post_s == 0.0)) st |= 1u << 8;
+  const double post = chd[CH_DL] * post_s;
+  FetchGlobal fetch{a.conv + n * a.conv_pitch};
+  pixel_likelihood<NT>(m, ch, chd, th, n, c, ncomp_cols, ax[0], post, ax + 2, fetch, scratch, a.components, a.spectra,
+                       a.fine_post, st);
+  st = __syncthreads_or((int)st);
+  if (tid == 0 && st) atomicOr(&a.status[n], st);
 }

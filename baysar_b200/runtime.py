@@ -67,6 +67,9 @@ def library():
     lib.baysar_model_get_profile.restype = i32
     lib.baysar_microbench.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double)]
     lib.baysar_microbench.restype = i32
+    lib.baysar_debug_if_contract.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp, ctypes.POINTER(i64),
+                                             ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_float)]
+    lib.baysar_debug_if_contract.restype = i32
     lib.baysar_last_error.restype = ctypes.c_char_p
     lib.baysar_version.restype = ctypes.c_char_p
     _lib = lib
@@ -75,7 +78,7 @@ def library():
 
 EXPORTED_SYMBOLS = ["baysar_model_create", "baysar_model_destroy", "baysar_model_query", "baysar_eval_logp",
                     "baysar_eval_spectra", "baysar_eval_lines", "baysar_eval_logp_host", "baysar_last_error",
-                    "baysar_version", "baysar_model_set_profiling", "baysar_model_get_profile", "baysar_microbench"]
+                    "baysar_version", "baysar_model_set_profiling", "baysar_model_get_profile", "baysar_microbench", "baysar_debug_if_contract"]
 
 
 def microbench(device=0):
@@ -88,6 +91,29 @@ def microbench(device=0):
             raise RuntimeError("baysar_b200: " + lib.baysar_last_error().decode())
         out[key] = val.value
     return out
+
+
+def debug_if_contract(spectra, taps, row_min=None):
+    """Run the tcgen05 instrument-function contraction on a CUDA float32 tensor [n_rows (multiple of 128), F].
+    -> (out [n_rows, F] float32, trapz partial sums [n_rows] float64, kernel milliseconds)."""
+    import numpy as np
+    import torch
+
+    lib = library()
+    spectra = spectra.contiguous()
+    n, F = spectra.shape
+    taps = np.ascontiguousarray(taps, dtype=np.float64)
+    n_tiles = -(-F // 128)
+    out = torch.empty((n, n_tiles * 128), dtype=torch.float32, device=spectra.device)
+    part = torch.empty((n, n_tiles), dtype=torch.float64, device=spectra.device)
+    pitch, tiles, ms = ctypes.c_int64(), ctypes.c_int(), ctypes.c_float()
+    rc = lib.baysar_debug_if_contract(spectra.data_ptr(), n, F, taps.ctypes.data, len(taps),
+                                      row_min.data_ptr() if row_min is not None else None, out.data_ptr(),
+                                      part.data_ptr(), ctypes.byref(pitch), ctypes.byref(tiles), ctypes.byref(ms))
+    if rc != 0:
+        raise RuntimeError("baysar_b200: " + lib.baysar_last_error().decode())
+    torch.cuda.synchronize()
+    return out[:, :F], part.sum(dim=1), ms.value
 
 
 class DeviceModel:
@@ -111,7 +137,11 @@ class DeviceModel:
         self.n_los = q(8)
         self.pixels = [q(6, c) for c in range(self.n_chords)]
         self.fine = [q(7, c) for c in range(self.n_chords)]
-        self.launches_per_eval = q(9)
+        self.uses_tensor_cores = bool(q(11))
+
+    @property
+    def launches_last_eval(self):
+        return int(self.lib.baysar_model_query(self.handle, 9, 0))
 
     def _check(self, rc):
         if rc != 0:
@@ -178,11 +208,12 @@ class DeviceModel:
         self._check(self.lib.baysar_model_set_profiling(self.handle, int(bool(on))))
 
     def get_profile(self):
-        """-> (per-stage total ms [LOS, chord, finalize], number of eval_logp calls) since profiling was enabled."""
-        ms = (ctypes.c_double * 3)()
+        """-> (per-stage total ms {los, chord, contract, pixel, finalize}, number of eval_logp calls) since profiling
+        was enabled.  `chord` is the fused chord kernel or, on the tensor-core path, its spectral stage."""
+        ms = (ctypes.c_double * 5)()
         calls = ctypes.c_int64()
         self._check(self.lib.baysar_model_get_profile(self.handle, ms, ctypes.byref(calls)))
-        return [ms[0], ms[1], ms[2]], int(calls.value)
+        return dict(zip(("los", "chord", "contract", "pixel", "finalize"), list(ms))), int(calls.value)
 
     def eval_logp_host(self, theta_np):
         """HOST buffers in, HOST buffers out: the copies happen inside the C call (the `e2e` path of bench.py)."""

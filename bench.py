@@ -164,11 +164,15 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------- flop accounting
 def flop_model(post):
-    """Executed FP32 flop per eval in the chord kernel (analytic, from the compiled model) and the SURVEY §8d
-    dense-semantics figure W_fma + banded W_tensor for the same model."""
+    """Executed flop per eval, per kernel, from the compiled model, and the SURVEY section 8d dense-semantics figure.
+
+    chord (FP32 pipe): Stark sweeps 18 F per Balmer line, Doppler and (fused path only) instrument convolutions at
+    2 flop per tap and output, 14 F + 12 P of bookkeeping.  contract (tensor pipe, 3xTF32): per 128x128 output tile and
+    32-wide k-block one N=256 and one N=128 MMA per 8-deep k-step, including the zero part of the Toeplitz tiles."""
     from baysar_b200.spectrometers import BalmerHydrogenLine
 
-    executed = dense = 0.0
+    tensor_path = post.model.uses_tensor_cores
+    chord = contract = dense = 0.0
     for ch in post.chords:
         F, P = len(ch.x_data_fm), len(ch.x_data)
         n_b = sum(isinstance(l, BalmerHydrogenLine) for l in ch.lines)
@@ -176,17 +180,23 @@ def flop_model(post):
         k_d = max([len(l.wavelengths_doppler) for l in ch.lines if isinstance(l, BalmerHydrogenLine)] or [0])
         inst = np.abs(ch.instrument_function_fm)
         keep = np.where(inst > 1e-17 * inst.max())[0]
-        nq_if = ((keep.max() - keep.min() + 1) + 3) // 4 * 4 + 4
+        k_lo, k_hi = int(keep.min()), int(keep.max()) + 1
+        nq_if = ((k_hi - k_lo) + 3) // 4 * 4 + 4
         dl = np.diff(ch.x_data_fm).mean()
-        if post.plasma.cold_neutrals:
-            sigma = 4000.0 * 7.715e-5 * np.sqrt(0.01 / 2.0) / np.sqrt(8 * np.log(2))
-        else:
-            sigma = 4000.0 * 7.715e-5 * np.sqrt(5.0 / 2.0) / np.sqrt(8 * np.log(2))
+        ti = 0.01 if post.plasma.cold_neutrals else 5.0
+        sigma = 4000.0 * 7.715e-5 * np.sqrt(ti / 2.0) / np.sqrt(8 * np.log(2))
         nq_d = (2 * int(8.85 * sigma / dl) + 1 + 3) // 4 * 4 + 4
-        executed += n_b * (18.0 * F + 2.0 * nq_d * F) + 2.0 * nq_if * F + 14.0 * F + 12.0 * P
+        chord += n_b * (18.0 * F + 2.0 * nq_d * F) + 14.0 * F + 12.0 * P
+        if tensor_path:
+            o = (len(inst) - 1) // 2
+            n_kb = (127 + o - k_lo) // 32 - (o - k_hi + 1) // 32 + 1
+            n_tiles = -(-F // 128)
+            contract += n_tiles * n_kb * 4 * 2.0 * (128 * 256 * 8 + 128 * 128 * 8) / 128.0
+        else:
+            chord += 2.0 * nq_if * F
         dense += 8.0 * n_g * F + n_b * 2 * (10.0 * F + 2.0 * k_d * F + 3.0 * F) + 12.0 * F + 10.0 * P \
             + 2.0 * F * len(ch.instrument_function_fm)
-    return executed, dense
+    return {"chord": chord, "contract": contract, "dense": dense}
 
 
 # ----------------------------------------------------------------------------------------------- main
@@ -332,32 +342,46 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (chord stage)
+    # ---- roofline of the dominant kernel, measured live (CUDA events around every kernel of the timed steps)
     peaks = runtime.microbench(local_rank)
-    executed, dense = flop_model(post)
-    chord_ms = stage_ms[1] / max(calls, 1)
-    achieved = executed * batch / (chord_ms * 1e-3) / 1e12
-    peak = peaks["fp32_fma_flops"] / 1e12
+    flops = flop_model(post)
+    per_call = {k: v / max(calls, 1) for k, v in stage_ms.items()}
     measured = {}
     try:
         measured = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
+    fp32_peak = peaks["fp32_fma_flops"] / 1e12
+    tf32_peak = measured.get("bf16_tflops", 1590.0) / 2.0
+    kernels = {
+        "chord_stage_kernel": {"bound": "fp32", "ms": per_call["chord"], "flop_per_eval": flops["chord"],
+                               "peak": fp32_peak,
+                               "peak_source": "FP32 FMA micro-benchmark in this run (baysar_microbench); "
+                                              "MEASURED_PEAKS.json has no FP32 figure"},
+        "if_contract_kernel": {"bound": "tensor", "ms": per_call["contract"], "flop_per_eval": flops["contract"],
+                               "peak": tf32_peak,
+                               "peak_source": "TF32 dense = half of MEASURED_PEAKS.json bf16_tflops (burst)"
+                               if measured else "TF32 dense = half of the fallback 1.59 PFLOP/s bf16"},
+    }
+    for k in kernels.values():
+        k["achieved"] = k["flop_per_eval"] * batch / (k["ms"] * 1e-3) / 1e12 if k["ms"] > 0 else 0.0
+        k["frac"] = k["achieved"] / k["peak"]
+        k["unit"] = "TFLOP/s"
+    dom = max(kernels, key=lambda name: kernels[name]["ms"])
     hbm_bytes = batch * (8.0 * n_params + 8.0 + 4.0 + 8.0 * (len(post.chords) + len(post.priors))
                          + 2 * 8.0 * 16 * post.model.n_ulines)
-    roofline = {
-        "bound": "fp32",  # neither HBM nor tensor bound: the chord kernel is FP32-FMA / MUFU work on smem-resident data
-        "kernel": "chord_stage_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        "peak_source": "FP32 FMA micro-benchmark in this run (baysar_microbench); MEASURED_PEAKS.json has no FP32 figure",
-        "traffic": None,
-        "executed_flop_per_eval": executed, "dense_reference_flop_per_eval": dense,
-        "dense_equivalent_tflops": dense * batch / (chord_ms * 1e-3) / 1e12,
-        "stage_ms": {"los": stage_ms[0] / max(calls, 1), "chord": chord_ms, "finalize": stage_ms[2] / max(calls, 1)},
-        "kernel_share_of_step": chord_ms / (float(step_ms.mean())),
+    if post.model.uses_tensor_cores:  # split spectra (write + read once per k-band) and convolved spectra
+        hbm_bytes += batch * sum(len(c.x_data_fm) for c in post.chords) * (8.0 + 8.0 + 4.0 + 4.0 * 0.3)
+    roofline = dict(kernels[dom])
+    roofline.update({
+        "kernel": dom, "traffic": None, "kernels": kernels,
+        "dense_reference_flop_per_eval": flops["dense"],
+        "dense_equivalent_tflops": flops["dense"] * batch / (float(step_ms.mean()) * 1e-3) / 1e12,
+        "stage_ms": per_call, "kernel_share_of_step": kernels[dom]["ms"] / float(step_ms.mean()),
         "mufu_peak_gops": peaks["mufu_ops"] / 1e9, "fp64_peak_tflops": peaks["fp64_fma_flops"] / 1e12,
         "hbm_algorithmic_GBps": hbm_bytes / (float(step_ms.mean()) * 1e-3) / 1e9,
         "hbm_peak_GBps_measured": measured.get("hbm_gbs"),
-    }
+    })
 
     # ---- CPU baseline (oracle port) on this box's host cores, bounded sample
     cpu = None
@@ -374,10 +398,10 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 element-wise / f64 line-of-sight, reductions and likelihood", "data": "synthetic",
-            "config": config, "clocks": clocks,
+            "config": dict(config, tensor_core_contraction=post.model.uses_tensor_cores), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch * n_params * 8,
                     "d2h_bytes_per_step": batch * (8 + 4), "steps": e2e_steps},
-            "gpu_launches": 3 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": post.model.launches_last_eval * args.steps, "roofline": roofline, "cpu_baseline": cpu,
             "status_ok_fraction": float((status == 0).mean())}
     print(json.dumps(line))
     if world > 1:

@@ -100,6 +100,14 @@ int baysar_model_get_profile(baysar_model_t* model, double* stage_ms, int64_t* c
 /* Peak-rate probe for roofline denominators: what = 0 FP32 FMA flop/s, 1 MUFU (rcp) op/s, 2 FP64 FMA flop/s. */
 int baysar_microbench(int device, int what, double* result);
 
+/* Unit-test hook for the tcgen05 instrument-function contraction (csrc/if_contract.cuh): for n_rows (multiple of 128)
+ * rows of F floats, out[r][j] = max(sum_k taps[k] * spectra[r][j + (KI-1)/2 - k], row_min[r]) (zero padded "same"
+ * convolution, scipy.signal.fftconvolve semantics of spectrometers.py:269-271).  out_dev must hold
+ * n_rows * ceil(F/128)*128 floats; trapz_dev (optional) n_rows * ceil(F/128) doubles. */
+int baysar_debug_if_contract(const float* spectra_dev, int64_t n_rows, int F, const double* taps_host, int KI,
+                             const float* row_min_dev, float* out_dev, double* trapz_dev, int64_t* out_pitch,
+                             int* n_tiles, float* elapsed_ms);
+
 const char* baysar_last_error(void);
 const char* baysar_version(void);
 

@@ -23,6 +23,70 @@ static ModelDev view(const unsigned char* blob) {
   return d;
 }
 
+// Tensor-core path in emulation: the spectral stage (MODE 1) and the pixel stage run through the thread emulator; the
+// tcgen05 contraction itself cannot, so a plain loop multiplies the TF32-split operands the way 3xTF32 does
+// (hi*hi + hi*lo + lo*hi, float accumulation).  Checks the hand-over logic (padding, aux, partial sums, fetch).
+extern "C" int emu_eval_split(const unsigned char* blob, const double* theta, long n, int chord, double* logp,
+                              unsigned* status, double* comps, double* lines, double* spectra) {
+  ModelDev m = view(blob);
+  const int64_t* I = m.I;
+  const int L = (int)I[I_L], n_chords = (int)I[I_N_CHORDS];
+  std::vector<double> hdr(n * BAYSAR_HDR_STRIDE);
+  LosArgs la{theta, n, lines, comps, hdr.data(), nullptr, status};
+  EmuDim3 g;
+  g.x = (unsigned)((n + 3) / 4);
+  emu_launch(los_stage_kernel<4>, g, 128u, 4 * los_smem_per_warp(L), m, la);
+  for (int c = 0; c < n_chords; ++c) {
+    const int* ch = m.ch_i + c * CH_I_COUNT;
+    const int F = ch[CH_F], KI = ch[CH_KI], k_lo = ch[CH_IF_KLO], k_hi = ch[CH_IF_KHI], o = (KI - 1) / 2;
+    int kd_max = 0;
+    for (int k = 0; k < ch[CH_N_LINES]; ++k) {
+      int kd = m.cl_i[(ch[CH_LINE_OFF] + k) * CL_I_COUNT + CL_KD];
+      kd_max = kd > kd_max ? kd : kd_max;
+    }
+    ChordSmem s = chord_smem_layout(F, ch[CH_HALO], ch[CH_TAPS_MAX], kd_max);
+    const int pad = 64, n_tiles = (F + 127) / 128;
+    const int64_t pitch = pad + F + 96, cpitch = (int64_t)n_tiles * 128;
+    std::vector<float> hi(n * pitch, 7.f), lo(n * pitch, 7.f), conv(n * cpitch, 0.f);
+    std::vector<double> aux(n * BAYSAR_AUX_STRIDE), part(n * n_tiles, 0.0);
+    ChordArgs ca{};
+    ca.theta = theta; ca.n = n; ca.chord_begin = c; ca.lines = lines; ca.components = comps; ca.status = status;
+    ca.split_hi = hi.data(); ca.split_lo = lo.data(); ca.split_pitch = pitch; ca.split_pad = pad; ca.aux = aux.data();
+    EmuDim3 gc;
+    gc.x = (unsigned)n; gc.y = 1;
+    emu_launch(chord_stage_kernel<256, 1>, gc, 256u, s.total, m, ca);
+    const double* w = m.ifn + ch[CH_IF_OFF];
+    for (long r = 0; r < n; ++r) {
+      const float* h = hi.data() + r * pitch + pad;
+      const float* l = lo.data() + r * pitch + pad;
+      const float clip = (float)aux[r * BAYSAR_AUX_STRIDE + 1];
+      for (int j = 0; j < F; ++j) {
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int k = k_lo; k < k_hi; ++k) {
+          int kp = j + o - k;
+          if (kp < -pad || kp >= F + 96) continue;
+          float wh = emu_tf32((float)w[k]), wl = emu_tf32((float)w[k] - wh);
+          acc0 += h[kp] * wh;
+          acc1 += h[kp] * wl + l[kp] * wh;
+        }
+        float v = acc0 + acc1;
+        v = v < clip ? clip : v;
+        conv[r * cpitch + j] = v;
+        part[r * n_tiles + j / 128] += ((j == 0 || j == F - 1) ? 0.5 : 1.0) * (double)v;
+      }
+    }
+    PixelArgs pa{};
+    pa.theta = theta; pa.n = n; pa.chord = c; pa.conv = conv.data(); pa.conv_pitch = cpitch; pa.trapz_part = part.data();
+    pa.n_tiles = n_tiles; pa.aux = aux.data(); pa.components = comps; pa.spectra = (c == chord) ? spectra : nullptr;
+    pa.status = status;
+    emu_launch(pixel_stage_kernel<128>, gc, 128u, 64 * sizeof(double), m, pa);
+  }
+  EmuDim3 gf;
+  gf.x = (unsigned)((n + 255) / 256);
+  emu_launch(finalize_kernel, gf, 256u, 0, (const double*)comps, (int)(n_chords + I[I_N_PRIORS]), (int64_t)n, logp, status);
+  return 0;
+}
+
 extern "C" int emu_eval(const unsigned char* blob, const double* theta, long n, int chord_for_spectra, double* logp,
                         unsigned* status, double* comps, double* lines, double* profiles, double* spectra,
                         float* fine_pre, float* fine_post) {
@@ -43,11 +107,13 @@ extern "C" int emu_eval(const unsigned char* blob, const double* theta, long n, 
     }
     ChordSmem s = chord_smem_layout(ch[CH_F], ch[CH_HALO], ch[CH_TAPS_MAX], kd_max);
     bool want = c == chord_for_spectra;
-    ChordArgs ca{theta, n, c, lines, comps, want ? spectra : nullptr, want ? fine_pre : nullptr,
-                 want ? fine_post : nullptr, status};
+    ChordArgs ca{};
+    ca.theta = theta; ca.n = n; ca.chord_begin = c; ca.lines = lines; ca.components = comps;
+    ca.spectra = want ? spectra : nullptr; ca.fine_pre = want ? fine_pre : nullptr;
+    ca.fine_post = want ? fine_post : nullptr; ca.status = status;
     EmuDim3 gc;
     gc.x = (unsigned)n; gc.y = 1;
-    emu_launch(chord_stage_kernel<256>, gc, 256u, s.total, m, ca);
+    emu_launch(chord_stage_kernel<256, 0>, gc, 256u, s.total, m, ca);
   }
   EmuDim3 gf;
   gf.x = (unsigned)((n + 255) / 256);

@@ -58,3 +58,19 @@ def emu_eval(blob, theta, chord=0, n_chords=1, n_priors=0, n_ul=1, L=50, P=1, F=
                       p(out["fine_post"]))
     assert rc == 0
     return out
+
+
+def emu_eval_split(blob, theta, chord=0, n_chords=1, n_priors=0, n_ul=1, P=1):
+    """Same evaluation through the tensor-core path's spectral + pixel stages (contraction emulated by a loop)."""
+    lib = emu_library()
+    lib.emu_eval_split.restype = ctypes.c_int
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    n = theta.shape[0]
+    out = dict(logp=np.zeros(n), status=np.zeros(n, dtype=np.uint32), comps=np.zeros((n, n_chords + n_priors)),
+               lines=np.zeros((n, max(n_ul, 1), 16)), spectra=np.zeros((n, P)))
+    buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    rc = lib.emu_eval_split(buf, p(theta), ctypes.c_long(n), ctypes.c_int(chord), p(out["logp"]), p(out["status"]),
+                            p(out["comps"]), p(out["lines"]), p(out["spectra"]))
+    assert rc == 0
+    return out

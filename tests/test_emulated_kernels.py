@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from .conftest import GOLDEN
-from .emu_harness import emu_eval, host_model
+from .emu_harness import emu_eval, emu_eval_split, host_model
 from .workloads import WORKLOADS
 
 N_THETA = 3
@@ -74,3 +74,16 @@ def test_status_flags_in_emulation():
     assert o["status"][0] & 1
     assert o["status"][1] & 2
     assert o["status"][2] & 4
+
+
+@pytest.mark.parametrize("name", ["balmer_series", "multi_species", "aug_demo"])
+def test_split_path_stages_in_emulation(name):
+    """Spectral stage (MODE 1) -> emulated 3xTF32 contraction -> pixel stage reproduces the fixtures."""
+    z = np.load(GOLDEN / f"{name}.npz")
+    plasma, chords, priors, blob, info = host_model(WORKLOADS[name]())
+    th = z["theta"][:2]
+    o = emu_eval_split(blob, th, chord=0, n_chords=len(chords), n_priors=len(priors), n_ul=info["n_ulines"],
+                       P=len(chords[0].x_data))
+    assert (o["status"] == 0).all()
+    np.testing.assert_allclose(o["logp"], z["logp"][:2], rtol=1e-6)
+    np.testing.assert_allclose(o["spectra"], z["c0_spectra"][:2], rtol=1e-5)
