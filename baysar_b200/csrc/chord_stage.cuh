@@ -23,6 +23,11 @@
 #pragma once
 #include "device_common.cuh"
 
+// Doppler taps are kept while exp(-z^2/2) >= 4.6e-11 of the central tap: next to a Stark profile the neglected taps
+// change a fine-grid sample by < 1.5e-8 relative (adjacent samples differ by at most ~10^2.5), below float32 resolution.
+#define BAYSAR_Z_CUT_DOPPLER 6.9
+#define BAYSAR_MAX_FUSED_LINES 8
+
 struct ChordArgs {
   const double* theta;      // [N][n_params]
   int64_t n;
@@ -60,7 +65,7 @@ __host__ __device__ static inline ChordSmem chord_smem_layout(int F, int halo, i
   s.taps_floats = (size_t)(taps_max + 8 + 3) / 4 * 4;
   s.tapd_doubles = 2 * (size_t)kd_max + 4;
   s.total = 2 * s.buf_floats * sizeof(float) + s.taps_floats * sizeof(float) + s.tapd_doubles * sizeof(double) +
-            64 * sizeof(double) + 16 * sizeof(int);
+            192 * sizeof(double) + 16 * sizeof(int) + 8 * BAYSAR_MAX_FUSED_LINES * sizeof(double);
   s.total = (s.total + 15) / 16 * 16;
   return s;
 }
@@ -227,20 +232,84 @@ __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kerne
   float* tapq = bufB + lay.buf_floats;
   double* tapd = reinterpret_cast<double*>(tapq + lay.taps_floats);  // [kd_max] taps, then [kd_max + 1] prefix sums
   double* tappre = tapd + kd_max;
-  double* scratch = tappre + kd_max + 4;  // 64 doubles
-  int* iscr = reinterpret_cast<int*>(scratch + 64);  // 16 ints
-  double* edge64 = scratch + 48;  // 4 doubles inside the scratch area that block_sum never touches (needs <= 48)
+  double* scratch = tappre + kd_max + 4;  // 192 doubles: [0,128) block_sum (up to 16 values x 8 warps), [128,132) edge64
+  int* iscr = reinterpret_cast<int*>(scratch + 192);  // 16 ints
+  // constants of the Balmer lines handled by the fused narrow-Doppler passes: [8][MAXF] doubles
+  double* fz = reinterpret_cast<double*>(iscr + 16);
+  float4* fz4 = reinterpret_cast<float4*>(fz);                     // per line: jc, lambda[jc] - centre, gamma_rec^2.5, gamma_exc^2.5
+  float2* fz2 = reinterpret_cast<float2*>(fz + 2 * BAYSAR_MAX_FUSED_LINES);  // per line: rec / exc amplitude over its integral
+  double* fz_sum = fz + 3 * BAYSAR_MAX_FUSED_LINES;                // [2][MAXF] rec_sum, exc_sum
+  double* edge64 = scratch + 128;
 #define A_AT(j) bufA[pad_index(HALO + (j))]
 #define B_AT(j) bufB[pad_index(HALO + (j))]
 
   uint32_t st = 0;
-  for (size_t i = tid; i < 2 * lay.buf_floats; i += NT) bufA[i] = 0.f;
+  for (size_t i = tid; i < lay.buf_floats; i += NT) bufA[i] = 0.f;
+  for (int i = tid; i < HALO; i += NT) bufB[pad_index(i)] = 0.f;                       // left halo of B
+  for (int i = HALO + F + tid; i < (int)lay.buf_floats; i += NT) bufB[pad_index(i)] = 0.f;  // tail + right halo of B
   __syncthreads();
 
   const double cal = ch[CH_CAL_IDX] >= 0 ? pow(10.0, th[ch[CH_CAL_IDX]]) : 1.0;
   const double fwhm_to_sigma = 0.42466090014400953;  // 1 / sqrt(8 ln 2)
   const double c_light = 299792458.0;
   const float NTf = (float)NT;
+
+  const float d_hi = (float)delta, d_lo = (float)(delta - (double)(float)delta);
+
+  // ================= Balmer lines whose Doppler kernel is a single tap (sigma << grid step) ====================
+  // Stark (x) delta = Stark: no convolution, no stash; ALL such lines share two sweeps over the grid and one block
+  // reduction: sweep 1 integrates u_rec / u_exc of every line (trapz, half weights at the ends), sweep 2 adds
+  // sum_b (rec_sum_b u_rec_b / I_rec_b + exc_sum_b u_exc_b / I_exc_b) to the spectrum.
+  int nf = 0;
+  auto flush_fused = [&]() {
+    __syncthreads();  // constants written by thread 0
+    // sweep 1, one line at a time with its constants in registers: I_rec, I_exc = trapz of the two Stark profiles.
+    // Per-warp partial sums go to shared memory; a single barrier then serves all lines.
+    for (int b = 0; b < nf; ++b) {
+      const float4 cst = fz4[b];  // jc, r, gamma_rec^2.5, gamma_exc^2.5
+      float sr = 0.f, se = 0.f;
+      float kf = (float)tid - cst.x;
+      for (int j = tid; j < F; j += NT, kf += NTf) {
+        const float d = fabsf(fmaf(kf, d_hi, fmaf(kf, d_lo, cst.y)));
+        const float a25 = d * d * sqrt_approx(d);
+        const float dr = a25 + cst.z, de = a25 + cst.w;
+        const float inv = rcp_approx(dr * de);
+        sr = fmaf(de, inv, sr);
+        se = fmaf(dr, inv, se);
+        if (j == 0 || j == F - 1) { sr = fmaf(-0.5f * de, inv, sr); se = fmaf(-0.5f * dr, inv, se); }  // trapz ends
+      }
+      const double wr = warp_sum((double)sr), we = warp_sum((double)se);
+      if (lane == 0) { scratch[(2 * b) * (NT / 32) + warp] = wr; scratch[(2 * b + 1) * (NT / 32) + warp] = we; }
+    }
+    __syncthreads();
+    if (tid < nf) {
+      double ir = 0.0, ie = 0.0;
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) { ir += scratch[(2 * tid) * (NT / 32) + w]; ie += scratch[(2 * tid + 1) * (NT / 32) + w]; }
+      const double s_rec = fz_sum[tid] / (dl * ir) / cal;
+      const double s_exc = fz_sum[BAYSAR_MAX_FUSED_LINES + tid] / (dl * ie) / cal;
+      if (!(s_rec - s_rec == 0.0) || !(s_exc - s_exc == 0.0)) atomicOr(&a.status[n], 1u << 6);
+      fz2[tid] = make_float2((float)s_rec, (float)s_exc);
+    }
+    __syncthreads();
+    // sweep 2, all lines per point: spectrum += sum_b (s_rec_b den_exc + s_exc_b den_rec) / (den_rec den_exc)
+    float jf = (float)tid;
+    for (int j = tid; j < F; j += NT, jf += NTf) {
+      float v = 0.f;
+      for (int b = 0; b < nf; ++b) {
+        const float4 cst = fz4[b];
+        const float2 amp = fz2[b];
+        const float kf = jf - cst.x;
+        const float d = fabsf(fmaf(kf, d_hi, fmaf(kf, d_lo, cst.y)));
+        const float a25 = d * d * sqrt_approx(d);
+        const float dr = a25 + cst.z, de = a25 + cst.w;
+        v = fmaf(fmaf(amp.x, de, amp.y * dr), rcp_approx(dr * de), v);
+      }
+      A_AT(j) += v;
+    }
+    __syncthreads();  // the constants may be overwritten by the next group
+    nf = 0;
+  };
 
   // ================= line objects ==============================================================================
   for (int k = 0; k < ch[CH_N_LINES]; ++k) {
@@ -255,13 +324,35 @@ __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kerne
       if (!(sigma > 0.0)) st |= 1u << 5;
       const int KD = cl[CL_KD], o = (KD - 1) / 2;
       const double dshift = cwl - cwl0;
+      {
+        // single-tap test (block-uniform): the tap at the "same"-alignment centre is inside the cut, its neighbours not
+        double zc[3];
+        const double zlim = BAYSAR_Z_CUT_DOPPLER * sigma;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          double xk = __dadd_rn(cld[CL_DOP_START], __dmul_rn((double)(o - 1 + t), cld[CL_DOP_DELTA]));
+          zc[t] = fabs((xk + dshift) - cwl);
+        }
+        if (KD >= 3 && zc[1] <= zlim && zc[0] > zlim && zc[2] > zlim) {
+          if (tid == 0) {
+            const double c0 = x0 - cwl;
+            const int jc = (int)rint(-c0 / delta);
+            fz4[nf] = make_float4((float)jc, (float)fma((double)jc, delta, c0), (float)rec[11], (float)rec[12]);
+            fz_sum[nf] = rec[0];
+            fz_sum[BAYSAR_MAX_FUSED_LINES + nf] = rec[1];
+          }
+          if (++nf == BAYSAR_MAX_FUSED_LINES) flush_fused();
+          continue;
+        }
+      }
+      if (nf > 0) flush_fused();  // keep the (float) summation order of the lines deterministic
       // tap window |z| <= Z_CUT
       if (tid == 0) { iscr[0] = KD; iscr[1] = -1; }
       __syncthreads();
       for (int q = tid; q < KD; q += NT) {
         double xk = __dadd_rn(cld[CL_DOP_START], __dmul_rn((double)q, cld[CL_DOP_DELTA]));
         double z = ((xk + dshift) - cwl) / sigma;
-        if (fabs(z) <= BAYSAR_Z_CUT) { atomicMin(&iscr[0], q); atomicMax(&iscr[1], q); }
+        if (fabs(z) <= BAYSAR_Z_CUT_DOPPLER) { atomicMin(&iscr[0], q); atomicMax(&iscr[1], q); }
       }
       __syncthreads();
       const int k_lo = iscr[0], k_hi = iscr[1] + 1;
@@ -309,7 +400,6 @@ __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kerne
       const double c0 = x0 - cwl;
       const int jc = (int)rint(-c0 / delta);
       const float r_f = (float)fma((double)jc, delta, c0);
-      const float d_hi = (float)delta, d_lo = (float)(delta - (double)(float)delta);
       // pass 1: a25 = |d|^2.5 stashed in B;  A_e = sum_i u_e[i] G[i] with u_rec = den_exc * inv, u_exc = den_rec * inv,
       // inv = 1 / (den_rec * den_exc): one reciprocal serves both profiles
       float sr = 0.f, se = 0.f;
@@ -400,19 +490,20 @@ __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kerne
       }
     }
   }
+  if (nf > 0) flush_fused();
   __syncthreads();
 
   // ================= pre-convolution area and minimum (spectrometers.py:256, :271) ===============================
-  double pre_s = 0.0;
+  float pre_f = 0.f;
   float mn = 3.402823466e38f;
   int bad = 0;
   for (int j = tid; j < F; j += NT) {
     float v = A_AT(j);
-    double w = (j == 0 || j == F - 1) ? 0.5 : 1.0;
-    pre_s += w * (double)v;
+    pre_f += (j == 0 || j == F - 1) ? 0.5f * v : v;   // <= 40 terms per thread in float32, float64 across threads
     mn = v < mn ? v : mn;
     if (!(v - v == 0.f)) bad = 1;
   }
+  double pre_s = (double)pre_f;
   if (a.fine_pre) {
     float* o_ = a.fine_pre + n * (int64_t)F;
     for (int j = tid; j < F; j += NT) o_[j] = A_AT(j);

@@ -19,6 +19,7 @@ import numpy as np
 from scipy.constants import pi, speed_of_light
 
 Z_CUT = 8.85
+Z_CUT_DOPPLER = 6.9  # Doppler taps: exp(-z^2/2) >= 4.6e-11 of the central tap
 FWHM_TO_SIGMA = 1 / np.sqrt(8 * np.log(2))
 f32 = np.float32
 
@@ -28,7 +29,7 @@ def _taps_doppler(line, cwl_new, cwl0, ti):
     xk = line["doppler_x"] + (cwl_new - cwl0)
     z = (xk - cwl_new) / sigma
     g = np.exp(-0.5 * z * z)
-    keep = np.abs(z) <= Z_CUT
+    keep = np.abs(z) <= Z_CUT_DOPPLER
     k = np.where(keep)[0]
     return g, int(k.min()), int(k.max()) + 1
 
