@@ -67,6 +67,20 @@ def balmer_series(data="selfconsistent"):
     return Workload("balmer_series", kw, None, ref, "H Balmer series with Stark broadening (demo/balmer_series.py)")
 
 
+def balmer_two_chords():
+    """Two copies of the Balmer-series chord (second one with a shifted background level): exercises the per-chord
+    loop of the tensor-core path and its shared workspace."""
+    wl = balmer_series()
+    kw = dict(wl.input_kwargs)
+    wave, ems, inst = kw["wavelength_axis"][0], kw["experimental_emission"][0], kw["instrument_function"][0]
+    kw.update(wavelength_axis=[wave, wave.copy()], experimental_emission=[ems, ems * 1.02 + 3e10],
+              instrument_function=[inst, inst.copy()], emission_constant=[1e11, 1e11],
+              noise_region=[[4150.0, 4250.0], [4150.0, 4250.0]], refine=[0.1, 0.1])
+    ref = dict(wl.reference_theta)
+    ref["background_1"] = [12.06]
+    return Workload("balmer_two_chords", kw, None, ref, "two H Balmer-series chords sharing one plasma")
+
+
 def multi_species(n_chords=1, data="selfconsistent", flags=None):
     """configs[2]/[3]: D Balmer + N II/N III + C III + X triplet, 1024 px, refine 0.05, L=100."""
     npix = 1024

@@ -199,7 +199,8 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
 int ensure_ifc_workspace(baysar_model* m, int64_t n) {
   // rows handled per pass of the tensor-core path: bounded so that the split / convolved spectra stay within a
   // fixed HBM budget (8 bytes of operands + 4 bytes of output per fine-grid point and row)
-  const int64_t budget = (int64_t)24 << 30;
+  const char* env_budget = getenv("BAYSAR_IFC_BUDGET_MB");
+  const int64_t budget = env_budget ? ((int64_t)atoll(env_budget) << 20) : ((int64_t)24 << 30);
   const int64_t per_row = 4 * (2 * m->split_pitch_max + m->conv_pitch_max) + 8 * m->tiles_max;
   int64_t rows = (n + ifc::TILE_M - 1) / ifc::TILE_M * ifc::TILE_M;
   int64_t max_rows = budget / per_row / ifc::TILE_M * ifc::TILE_M;

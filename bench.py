@@ -108,58 +108,55 @@ def usable_cores():
 
 # ----------------------------------------------------------------------------------------------- clocks sampling
 class ClockSampler:
-    """Polls NVML (SM clock, max SM clock, power, clock-event reasons) every few ms from a thread while the timed
-    region runs; the timed region is far too short for `nvidia-smi -lms`."""
+    """SM clock / power / clock-event reasons DURING the timed region, from a separate `nvidia-smi -lms 20` process
+    (started well before the timed region so that it is already streaming; a polling thread inside this process
+    perturbs multi-rank steps through the GIL).  Rows are time-stamped; only those inside [t0, t1] are used."""
 
-    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+    FIELDS = ["timestamp", "clocks.sm", "clocks.max.sm", "power.draw", "clocks_event_reasons.hw_slowdown",
+              "clocks_event_reasons.hw_thermal_slowdown", "clocks_event_reasons.sw_thermal_slowdown",
+              "clocks_event_reasons.sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self.thread, self.stop_flag = index, [], None, False
-        self.max_mhz = None
+        self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = visible.split(",")[self.index] if visible else str(self.index)
         try:
-            import pynvml
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={idx}", "--query-gpu=" + ",".join(self.FIELDS),
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
 
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
-        except Exception:
-            self.nv = None
-            return
-        self.thread = threading.Thread(target=self._poll, daemon=True)
-        self.thread.start()
+    def _pump(self):
+        import datetime
 
-    def _poll(self):
-        nv = self.nv
-        while not self.stop_flag:
+        for line in self.proc.stdout:
+            cells = [c.strip() for c in line.split(",")]
+            if len(cells) != len(self.FIELDS):
+                continue
             try:
-                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
-                try:
-                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
-                except Exception:
-                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                power = nv.nvmlDeviceGetPowerUsage(self.handle) / 1e3
-                self.rows.append((float(sm), int(reasons), power))
-            except Exception:
-                pass
-            time.sleep(0.002)
+                ts = datetime.datetime.strptime(cells[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                self.rows.append((ts, float(cells[1]), float(cells[2]), float(cells[3]), cells[4:]))
+            except ValueError:
+                continue
 
-    def stop(self):
-        self.stop_flag = True
-        if self.thread is not None:
-            self.thread.join(timeout=1.0)
-        sm = [r[0] for r in self.rows]
+    def stop(self, t0, t1):
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+        inside = [r for r in self.rows if t0 - 0.02 <= r[0] <= t1 + 0.02] or self.rows[-3:]
         reasons = set()
-        for r in self.rows:
-            for bit, name in self.REASONS.items():
-                if r[1] & bit:
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
+                if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max([r[2] for r in self.rows]) if self.rows else None}
+        sm = [r[1] for r in inside]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max([r[2] for r in inside]) if inside else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_total": len(self.rows),
+                "power_w_max": max([r[3] for r in inside]) if inside else None}
 
 
 # ----------------------------------------------------------------------------------------------- flop accounting
@@ -266,6 +263,9 @@ def main():
     from baysar_b200.lineshapes import EsymmtricCauchyPlasma
     from baysar_b200.posterior import BaysarPosterior
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     wl = get_workload(args.workload)
     np.random.seed(0)
     prof = EsymmtricCauchyPlasma(x=wl.los) if wl.los is not None else None
@@ -289,24 +289,23 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    post.model.set_profiling(True)
+    post.model.set_profiling(os.environ.get("BAYSAR_BENCH_NOPROF") != "1")
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    t_wall0 = time.time()
     for k in range(args.steps):
         flush.fill_(float(k))  # evict L2 between timed steps (untimed)
         starts[k].record()
         out = step(args.warmup + k)
         ends[k].record()
     torch.cuda.synchronize()
+    t_wall1 = time.time()
     if world > 1:
         dist.barrier()
     stage_ms, calls = post.model.get_profile()
     post.model.set_profiling(False)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
     total_ms = torch.tensor([float(step_ms.sum())], dtype=torch.float64, device="cuda")
     if world > 1:

@@ -166,3 +166,79 @@ def test_background_linearity_property(posteriors):
     spectra, _ = post.spectra_batch(th, chord=0)
     d = 10 ** th[1, b] - 10 ** th[0, b]
     np.testing.assert_allclose(spectra[1] - spectra[0], d, rtol=1e-6)
+
+
+def _fresh_posterior(workload, env):
+    """A posterior created under temporary environment switches (read by baysar_model_create)."""
+    import os
+
+    from baysar_b200.atomic_data import SyntheticADAS
+    from baysar_b200.input_functions import make_input_dict
+    from baysar_b200.posterior import BaysarPosterior
+
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        np.random.seed(3)
+        return BaysarPosterior(make_input_dict(**workload.input_kwargs), atomic_data=SyntheticADAS(), skip_test=True)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_tensor_core_path_agrees_with_fused_path():
+    """The tcgen05 contraction (spectral -> contraction -> pixel stages) and the fused FP32 kernel are two
+    implementations of the same chord evaluation: compare them on 640 thetas, and both against the oracle."""
+    from baysar_b200 import configs
+
+    wl = configs.balmer_series()
+    tensor = _fresh_posterior(wl, {"BAYSAR_IFC": "1"})
+    fused = _fresh_posterior(wl, {"BAYSAR_IFC": "0"})
+    assert tensor.model.uses_tensor_cores and not fused.model.uses_tensor_cores
+    rng = np.random.default_rng(11)
+    lo, hi = tensor.plasma.theta_bounds[:, 0], tensor.plasma.theta_bounds[:, 1]
+    theta = lo + rng.random((640, tensor.plasma.n_params)) * (hi - lo)
+    a, b = tensor(theta), fused(theta)
+    ok = (tensor.last_status == 0) & (fused.last_status == 0)
+    assert ok.mean() > 0.9
+    np.testing.assert_allclose(a[ok], b[ok], rtol=LOGP_RTOL)
+    sa, _ = tensor.spectra_batch(theta[:64], 0)
+    sb, _ = fused.spectra_batch(theta[:64], 0)
+    np.testing.assert_allclose(sa, sb, rtol=SPECTRA_RTOL)
+    oracle = oracle_posterior("balmer_series")
+    for i in np.where(ok)[0][:24]:
+        ref = oracle.evaluate(theta[i])
+        np.testing.assert_allclose(a[i], ref["logp"], rtol=LOGP_RTOL)
+        if i < 64:
+            np.testing.assert_allclose(sa[i], ref["spectra"][0], rtol=SPECTRA_RTOL)
+
+
+def test_tensor_core_path_multi_chord_and_row_chunks():
+    """Two chords through the tensor path with a workspace budget that forces several row chunks per chord."""
+    from baysar_b200 import configs
+    from baysar_b200.atomic_data import SyntheticADAS
+    from baysar_b200.input_functions import make_input_dict
+    from oracle.numpy_port import OraclePosterior
+
+    wl = configs.balmer_two_chords()
+    small = _fresh_posterior(wl, {"BAYSAR_IFC": "1", "BAYSAR_IFC_BUDGET_MB": "40"})   # 384 rows per pass
+    fused = _fresh_posterior(wl, {"BAYSAR_IFC": "0"})
+    assert small.model.uses_tensor_cores and len(small.chords) == 2
+    rng = np.random.default_rng(12)
+    lo, hi = small.plasma.theta_bounds[:, 0], small.plasma.theta_bounds[:, 1]
+    theta = lo + rng.random((1000, small.plasma.n_params)) * (hi - lo)
+    a, b = small(theta), fused(theta)
+    ok = (small.last_status == 0) & (fused.last_status == 0)
+    assert ok.mean() > 0.9
+    np.testing.assert_allclose(a[ok], b[ok], rtol=LOGP_RTOL)
+    assert small.model.launches_last_eval > 3 + 3 * 2  # more than one chunk per chord
+    oracle = OraclePosterior(make_input_dict(**wl.input_kwargs), SyntheticADAS())
+    for i in np.where(ok)[0][:12]:
+        ref = oracle.evaluate(theta[i])
+        np.testing.assert_allclose(a[i], ref["logp"], rtol=LOGP_RTOL)
+        for c in range(2):
+            spec, _ = small.spectra_batch(theta[i:i + 1], c)
+            np.testing.assert_allclose(spec[0], ref["spectra"][c], rtol=SPECTRA_RTOL)
