@@ -71,6 +71,7 @@ struct baysar_model {
   std::vector<float*> ifc_taps_dev;
   bool any_ifc = false;
   int64_t ifc_rows = 0;              // rows of the split / conv workspaces (multiple of 128)
+  int64_t ifc_budget_bytes = (int64_t)24 << 30;  // HBM budget of those workspaces (BAYSAR_IFC_BUDGET_MB at create)
   float *split_hi = nullptr, *split_lo = nullptr, *conv = nullptr;
   double *trapz_part = nullptr, *aux = nullptr;
   int64_t split_pitch_max = 0, conv_pitch_max = 0;
@@ -199,8 +200,7 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
 int ensure_ifc_workspace(baysar_model* m, int64_t n) {
   // rows handled per pass of the tensor-core path: bounded so that the split / convolved spectra stay within a
   // fixed HBM budget (8 bytes of operands + 4 bytes of output per fine-grid point and row)
-  const char* env_budget = getenv("BAYSAR_IFC_BUDGET_MB");
-  const int64_t budget = env_budget ? ((int64_t)atoll(env_budget) << 20) : ((int64_t)24 << 30);
+  const int64_t budget = m->ifc_budget_bytes;
   const int64_t per_row = 4 * (2 * m->split_pitch_max + m->conv_pitch_max) + 8 * m->tiles_max;
   int64_t rows = (n + ifc::TILE_M - 1) / ifc::TILE_M * ifc::TILE_M;
   int64_t max_rows = budget / per_row / ifc::TILE_M * ifc::TILE_M;
@@ -408,6 +408,8 @@ int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar
   const bool ifc_enabled = !(env && env[0] == '0');
   const char* env_taps = getenv("BAYSAR_IFC_MIN_TAPS");
   const int min_taps = env_taps ? atoi(env_taps) : 160;
+  const char* env_budget = getenv("BAYSAR_IFC_BUDGET_MB");
+  if (env_budget) m->ifc_budget_bytes = (int64_t)atoll(env_budget) << 20;
   m->ifc.resize(n_chords);
   m->ifc_taps_dev.assign(n_chords, nullptr);
   const double* ifn_host = static_cast<const double*>(host.ptr(SEC_IF));
