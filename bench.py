@@ -325,7 +325,7 @@ def main():
         dist.barrier()
     t_e2e = 0.0
     for k in range(e2e_steps):
-        pinned.copy_(torch.from_numpy(thetas_host[args.warmup + k]))
+        pinned.copy_(torch.from_numpy(thetas_host[(args.warmup + k) % total_steps]))
         flush.fill_(float(k))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -386,10 +386,12 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         cores = usable_cores()
-        per_core = 150 if args.workload == "balmer_series" else 120
-        sample = thetas_host.reshape(-1, n_params)[: cores * per_core]
+        pool = thetas_host.reshape(-1, n_params)
+        rate1, done1, _ = cpu_oracle_rate(args.workload, pool[:200], 1)
+        # bounded sample: about 12 s of CPU work per worker at the single-core rate just measured
+        want = int(cores * max(200, 12.0 * rate1))
+        sample = pool[np.arange(want) % len(pool)]
         rate, done, wall = cpu_oracle_rate(args.workload, sample, cores)
-        rate1, done1, _ = cpu_oracle_rate(args.workload, sample[:200], 1)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{done} thetas of the same batch, {cores} forked workers, {wall:.1f} s wall",
                "single_core_value": rate1}
