@@ -113,12 +113,51 @@ __global__ void microbench_mufu_kernel(float* out, int iters, float a) {
   for (int k = 0; k < 16; ++k) v[k] = threadIdx.x * 1e-3f + k + 1.f;
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k) asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(v[k]) : "f"(v[k]));
+    for (int k = 0; k < 16; ++k) asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(v[k]) : "f"(v[k]));
   }
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < 16; ++k) s += v[k];
   if (s == 12345.678f) out[threadIdx.x] = s * a;
+}
+// FFMA with all three operands in registers (the form real kernels issue; the immediate form above is the pipe's
+// best case) and the packed FFMA2 (fma.rn.f32x2, two FMAs per lane and instruction, sm_100+)
+__global__ void microbench_ffma_reg_kernel(float* out, int iters, float a, float b) {
+  float v[16];
+  const float ar = a + (float)(threadIdx.x & 1) * 1e-9f, br = b + (float)(threadIdx.x & 2) * 1e-9f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = threadIdx.x * 1e-3f + k;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = fmaf(v[k], ar, br);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += v[k];
+  if (s == 12345.678f) out[threadIdx.x] = s;
+}
+__global__ void microbench_ffma2_kernel(float* out, int iters, float a, float b) {
+  unsigned long long v[16], ar, br;
+  const float a0 = a + (float)(threadIdx.x & 1) * 1e-9f, b0 = b + (float)(threadIdx.x & 2) * 1e-9f;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ar) : "f"(a0), "f"(a0));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(br) : "f"(b0), "f"(b0));
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float x = threadIdx.x * 1e-3f + k;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v[k]) : "f"(x), "f"(x + 0.5f));
+  }
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v[k]) : "l"(ar), "l"(br));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v[k]));
+    s += lo + hi;
+  }
+  if (s == 12345.678f) out[threadIdx.x] = s;
 }
 __global__ void microbench_dfma_kernel(double* out, int iters, double a) {
   double v[16];
@@ -182,7 +221,7 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
   a.theta = theta; a.n = n; a.lines = lines; a.components = comps; a.hdr = m->hdr; a.profiles = profiles;
   a.status = status;
   const int L = (int)m->I[I_L];
-  const size_t per_warp = los_smem_per_warp(L);
+  const size_t per_warp = los_smem_per_warp(L, (int)m->I[I_N_PARAMS]);
   if (per_warp > 200 * 1024) return fail("line-of-sight grid too long for the shared-memory LOS stage");
   if (4 * per_warp <= 200 * 1024) {
     size_t smem = 4 * per_warp;
@@ -625,13 +664,15 @@ int baysar_microbench(int device, int what, double* result) {
     CUDA_OK(cudaEventRecord(e0, 0));
     if (what == 0) microbench_ffma_kernel<<<blocks, threads>>>(out, iters, 1.0001f);
     else if (what == 1) microbench_mufu_kernel<<<blocks, threads>>>(out, iters, 1.0001f);
+    else if (what == 3) microbench_ffma_reg_kernel<<<blocks, threads>>>(out, iters, 1.0001f, 0.5f);
+    else if (what == 4) microbench_ffma2_kernel<<<blocks, threads>>>(out, iters, 1.0001f, 0.5f);
     else microbench_dfma_kernel<<<blocks, threads>>>(reinterpret_cast<double*>(out), iters, 1.0001);
     CUDA_OK(cudaEventRecord(e1, 0));
     CUDA_OK(cudaEventSynchronize(e1));
     float ms = 0.f;
     CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
     // ops per thread per iteration: 16 independent chains x 1 instruction
-    double ops = (double)blocks * threads * (double)iters * 16.0;
+    double ops = (double)blocks * threads * (double)iters * 16.0 * (what == 4 ? 2.0 : 1.0);
     double rate = ops / (ms * 1e-3);
     if (rep > 0 && rate > best) best = rate;
   }

@@ -48,6 +48,24 @@ struct ChordArgs {
 
 #define BAYSAR_AUX_STRIDE 8
 
+// Per-line constants of the fused narrow-Doppler Balmer passes (one 64-byte record per line, shared memory)
+struct FusedLine {
+  float jc_f, r, g_r, g_e;   // grid point nearest the centre, lambda[jc] - centre, gamma_rec^2.5, gamma_exc^2.5
+  float s_r, s_e, c0, c1;    // amplitudes over the profile integrals; far-field series coefficients
+  float c2, d_far;           // far field: |d| >= d_far  <=>  |d|^2.5 >= BAYSAR_FAR_RATIO * max(g_r, g_e)
+  int jL, jR;                // densely integrated window of sweep 1
+  double sum_r, sum_e;       // line-of-sight integrals (recombination, excitation)
+};
+// Parameters of one Gaussian component, computed once per (theta, chord) (32 bytes)
+struct GaussComp {
+  double cw, inv_sigma;  // (Doppler-shifted) centre, 1 / sigma
+  float amp;             // area-normalised amplitude over the intensity calibration
+  int j_lo, j_hi, pad;   // fine-grid window |z| <= BAYSAR_Z_CUT
+};
+#define BAYSAR_EM_STRIDE 16     // sweep 1 samples the tails at this stride (Euler-Maclaurin corrected)
+#define BAYSAR_EM_WINDOW 256    // ... outside +-this many grid points of the line centre
+#define BAYSAR_FAR_RATIO 500.f  // sweep 2: series in g / |d|^2.5 beyond this ratio (third-order term < 1e-8)
+
 __host__ __device__ static inline int pad_index(int i) { return i ^ ((i >> 3) & 4); }
 
 struct ChordSmem {
@@ -234,11 +252,8 @@ __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kerne
   double* tappre = tapd + kd_max;
   double* scratch = tappre + kd_max + 4;  // 192 doubles: [0,128) block_sum (up to 16 values x 8 warps), [128,132) edge64
   int* iscr = reinterpret_cast<int*>(scratch + 192);  // 16 ints
-  // constants of the Balmer lines handled by the fused narrow-Doppler passes: [8][MAXF] doubles
-  double* fz = reinterpret_cast<double*>(iscr + 16);
-  float4* fz4 = reinterpret_cast<float4*>(fz);                     // per line: jc, lambda[jc] - centre, gamma_rec^2.5, gamma_exc^2.5
-  float2* fz2 = reinterpret_cast<float2*>(fz + 2 * BAYSAR_MAX_FUSED_LINES);  // per line: rec / exc amplitude over its integral
-  double* fz_sum = fz + 3 * BAYSAR_MAX_FUSED_LINES;                // [2][MAXF] rec_sum, exc_sum
+  // constants of the Balmer lines handled by the fused narrow-Doppler passes (BAYSAR_MAX_FUSED_LINES x 64 bytes)
+  FusedLine* fl = reinterpret_cast<FusedLine*>(iscr + 16);
   double* edge64 = scratch + 128;
 #define A_AT(j) bufA[pad_index(HALO + (j))]
 #define B_AT(j) bufB[pad_index(HALO + (j))]
@@ -263,53 +278,178 @@ __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kerne
   int nf = 0;
   auto flush_fused = [&]() {
     __syncthreads();  // constants written by thread 0
-    // sweep 1, one line at a time with its constants in registers: I_rec, I_exc = trapz of the two Stark profiles.
-    // Per-warp partial sums go to shared memory; a single barrier then serves all lines.
+    // ---- sweep 1: I_rec, I_exc = trapz of the two Stark profiles of every line over the whole grid.
+    // Only a window of +-BAYSAR_EM_WINDOW points around the line centre is summed point by point; on the two tails,
+    // where 1 / (|d|^2.5 + g) is smooth on the scale of the grid, every BAYSAR_EM_STRIDE-th point is sampled and the
+    // difference between the coarse and the fine trapezoid is restored from the Euler-Maclaurin expansion
+    //   T_1[a,b] = T_s[a,b] - (s^2 - 1)/12 (f1(b) - f1(a)) + (s^4 - 1)/720 (f3(b) - f3(a)) - ...
+    // (f1, f3: first and third derivative per grid index; relative error of the integral < 1e-8 for every width
+    // and centre, checked in tests/test_kernel_model.py).  Per-warp partial sums go to shared memory; one barrier
+    // serves all lines.
+    constexpr int S = BAYSAR_EM_STRIDE;
     for (int b = 0; b < nf; ++b) {
-      const float4 cst = fz4[b];  // jc, r, gamma_rec^2.5, gamma_exc^2.5
+      const float4 cst = *reinterpret_cast<const float4*>(&fl[b].jc_f);  // jc, r, gamma_rec^2.5, gamma_exc^2.5
+      const int jL = fl[b].jL, jR = fl[b].jR;
+      const int n_c = jR - jL + 1;
+      const int n_lt = jL > 0 ? jL / S + 1 : 0;
+      const int n_rt = jR < F - 1 ? (F - 1 - jR) / S + 1 : 0;
       float sr = 0.f, se = 0.f;
-      float kf = (float)tid - cst.x;
-      for (int j = tid; j < F; j += NT, kf += NTf) {
+      for (int t = tid; t < n_c + n_lt + n_rt; t += NT) {
+        int j; float w;
+        if (t < n_c) { j = jL + t; w = (t == 0 || t == n_c - 1) ? (n_c == 1 ? 0.f : 0.5f) : 1.f; }
+        else if (t < n_c + n_lt) { const int q = t - n_c; j = q * S; w = (q == 0 || q == n_lt - 1) ? 0.5f * S : (float)S; }
+        else { const int q = t - n_c - n_lt; j = jR + q * S; w = (q == 0 || q == n_rt - 1) ? 0.5f * S : (float)S; }
+        const float kf = (float)j - cst.x;
         const float d = fabsf(fmaf(kf, d_hi, fmaf(kf, d_lo, cst.y)));
         const float a25 = d * d * sqrt_approx(d);
         const float dr = a25 + cst.z, de = a25 + cst.w;
-        const float inv = rcp_approx(dr * de);
+        const float inv = w * rcp_approx(dr * de);
         sr = fmaf(de, inv, sr);
         se = fmaf(dr, inv, se);
-        if (j == 0 || j == F - 1) { sr = fmaf(-0.5f * de, inv, sr); se = fmaf(-0.5f * dr, inv, se); }  // trapz ends
       }
       const double wr = warp_sum((double)sr), we = warp_sum((double)se);
       if (lane == 0) { scratch[(2 * b) * (NT / 32) + warp] = wr; scratch[(2 * b + 1) * (NT / 32) + warp] = we; }
     }
     __syncthreads();
     if (tid < nf) {
+      FusedLine& L = fl[tid];
       double ir = 0.0, ie = 0.0;
 #pragma unroll
       for (int w = 0; w < NT / 32; ++w) { ir += scratch[(2 * tid) * (NT / 32) + w]; ie += scratch[(2 * tid + 1) * (NT / 32) + w]; }
-      const double s_rec = fz_sum[tid] / (dl * ir) / cal;
-      const double s_exc = fz_sum[BAYSAR_MAX_FUSED_LINES + tid] / (dl * ie) / cal;
+      // Euler-Maclaurin end corrections of the strided tails (float64, once per line)
+      const double gr = (double)L.g_r, ge = (double)L.g_e;
+      const double c1 = (double)(S * S - 1) / 12.0, c3 = ((double)S * S * S * S - 1.0) / 720.0;
+      for (int side = 0; side < 2; ++side) {
+        const int ja = side == 0 ? 0 : L.jR, jb = side == 0 ? L.jL : F - 1;
+        if (jb <= ja) continue;
+        double f1[2][2], f3[2][2];  // [end][rec, exc]
+        double sgn = 1.0;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double xs = ((double)(e == 0 ? ja : jb) - (double)L.jc_f) * delta + (double)L.r;
+          if (e == 0) sgn = xs > 0.0 ? 1.0 : -1.0;
+          const double x = fabs(xs), sq = sqrt(x);
+          const double D1 = 2.5 * x * sq, D2 = 3.75 * sq, D3 = 1.875 / sq, x25 = x * x * sq;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const double iD = 1.0 / (x25 + (q == 0 ? gr : ge)), iD2 = iD * iD;
+            f1[e][q] = -D1 * iD2;
+            f3[e][q] = -D3 * iD2 + 6.0 * D1 * D2 * iD2 * iD - 6.0 * D1 * D1 * D1 * iD2 * iD2;
+          }
+        }
+        const double h1 = sgn * delta, h3 = sgn * delta * delta * delta;
+        ir += -c1 * h1 * (f1[1][0] - f1[0][0]) + c3 * h3 * (f3[1][0] - f3[0][0]);
+        ie += -c1 * h1 * (f1[1][1] - f1[0][1]) + c3 * h3 * (f3[1][1] - f3[0][1]);
+      }
+      const double s_rec = L.sum_r / (dl * ir) / cal;
+      const double s_exc = L.sum_e / (dl * ie) / cal;
       if (!(s_rec - s_rec == 0.0) || !(s_exc - s_exc == 0.0)) atomicOr(&a.status[n], 1u << 6);
-      fz2[tid] = make_float2((float)s_rec, (float)s_exc);
+      // sweep-2 constants: exact form next to the centre, far-field series
+      //   s_r / (a + g_r) + s_e / (a + g_e) = (1/a) (c0 - (1/a) (c1 - (1/a) c2)) + O((g/a)^3),  a = |d|^2.5
+      L.s_r = (float)s_rec; L.s_e = (float)s_exc;
+      L.c0 = (float)(s_rec + s_exc);
+      L.c1 = (float)(s_rec * gr + s_exc * ge);
+      L.c2 = (float)(s_rec * gr * gr + s_exc * ge * ge);
+      const double gmax = gr > ge ? gr : ge;
+      L.d_far = (float)pow((double)BAYSAR_FAR_RATIO * gmax, 0.4);
     }
     __syncthreads();
-    // sweep 2, all lines per point: spectrum += sum_b (s_rec_b den_exc + s_exc_b den_rec) / (den_rec den_exc)
-    float jf = (float)tid;
-    for (int j = tid; j < F; j += NT, jf += NTf) {
-      float v = 0.f;
+    // ---- sweep 2, four points per thread and line: spectrum += sum_b (s_rec_b / den_rec + s_exc_b / den_exc)
+    for (int jb = tid; jb < F; jb += 4 * NT) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      const float jf = (float)jb;
       for (int b = 0; b < nf; ++b) {
-        const float4 cst = fz4[b];
-        const float2 amp = fz2[b];
-        const float kf = jf - cst.x;
-        const float d = fabsf(fmaf(kf, d_hi, fmaf(kf, d_lo, cst.y)));
-        const float a25 = d * d * sqrt_approx(d);
-        const float dr = a25 + cst.z, de = a25 + cst.w;
-        v = fmaf(fmaf(amp.x, de, amp.y * dr), rcp_approx(dr * de), v);
+        const float4 cst = *reinterpret_cast<const float4*>(&fl[b].jc_f);
+        const float4 ser = *reinterpret_cast<const float4*>(&fl[b].s_r);   // s_r, s_e, c0, c1
+        const float2 far = *reinterpret_cast<const float2*>(&fl[b].c2);    // c2, d_far
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float kf = (jf + (float)(u * NT)) - cst.x;
+          const float d = fabsf(fmaf(kf, d_hi, fmaf(kf, d_lo, cst.y)));
+          if (d >= far.y) {
+            const float rs = rsqrt_approx(d);
+            const float rs2 = rs * rs;
+            const float ia = rs2 * rs2 * rs;
+            v[u] = fmaf(ia, fmaf(-ia, fmaf(-ia, far.x, ser.w), ser.z), v[u]);
+          } else {
+            const float a25 = d * d * sqrt_approx(d);
+            const float dr = a25 + cst.z, de = a25 + cst.w;
+            v[u] = fmaf(fmaf(ser.x, de, ser.y * dr), rcp_approx(dr * de), v[u]);
+          }
+        }
       }
-      A_AT(j) += v;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (jb + u * NT < F) A_AT(jb + u * NT) += v[u];
     }
     __syncthreads();  // the constants may be overwritten by the next group
     nf = 0;
   };
+
+  // ================= Gaussian multiplets (ADAS406Lines / XLine): linemodels.py:401-403,428 ; :213-233 ============
+  // The float64 parameters of every component (Doppler-shifted centre, 1 / sigma, amplitude, sample window) are
+  // computed ONCE by one thread per component into a scratch table (the interior of buffer B, dead until the first
+  // Balmer line or the instrument convolution); the block then adds the components point by point with
+  // thread-consistent ownership j = tid (mod NT), so there is no barrier between components.
+  {
+    GaussComp* gc = reinterpret_cast<GaussComp*>(bufB + ((HALO + 7) & ~7));
+    const int gcap = (((HALO + F) & ~7) - ((HALO + 7) & ~7)) * (int)sizeof(float) / (int)sizeof(GaussComp);
+    int total = 0;
+    for (int k = 0; k < ch[CH_N_LINES]; ++k) {
+      const int* cl = m.cl_i + (ch[CH_LINE_OFF] + k) * CL_I_COUNT;
+      if (cl[CL_KIND] != 0) total += cl[CL_NCOMP];
+    }
+    for (int base = 0; base < total; base += gcap) {
+      const int nb = total - base < gcap ? total - base : gcap;
+      for (int g = tid; g < nb; g += NT) {
+        // locate the line object of component base + g
+        int k = 0, first = 0;
+        const int* cl = nullptr;
+        for (; k < ch[CH_N_LINES]; ++k) {
+          cl = m.cl_i + (ch[CH_LINE_OFF] + k) * CL_I_COUNT;
+          if (cl[CL_KIND] == 0) continue;
+          if (base + g < first + cl[CL_NCOMP]) break;
+          first += cl[CL_NCOMP];
+        }
+        const double* cld = m.cl_d + (ch[CH_LINE_OFF] + k) * CL_D_COUNT;
+        const double* rec = lines_n + cl[CL_ULINE] * BAYSAR_LINE_STRIDE;
+        const double* cp = m.comp_d + (cl[CL_COMP_OFF] + (base + g - first)) * 2;
+        double cw = cp[0], fwhm;
+        if (cl[CL_KIND] == 1) {
+          if (cl[CL_SPECIES] >= 0) {
+            const int vi = m.sp_i[cl[CL_SPECIES] * SP_I_COUNT + SP_VEL_IDX];
+            if (vi >= 0) cw = cw * ((1e3 * th[vi]) / c_light + 1.0);
+          }
+          fwhm = cw * 7.715e-5 * sqrt(rec[4] / cld[CL_MASS]);
+        } else {
+          fwhm = cld[CL_FWHM];
+        }
+        if (!(fwhm > 0.0) || !(cp[1] > 0.0)) st |= 1u << 5;
+        const double sigma = fwhm * fwhm_to_sigma;
+        const double amp = (rec[0] * (cp[1] / (2.5066282746310002 * sigma))) / cal;
+        if (!(amp - amp == 0.0)) st |= 1u << 6;
+        const double half = BAYSAR_Z_CUT * sigma;
+        const double jl = ceil((cw - half - x0) / delta - 1e-9), jh = floor((cw + half - x0) / delta + 1e-9);
+        GaussComp c;
+        c.cw = cw; c.inv_sigma = 1.0 / sigma; c.amp = (float)amp;
+        c.j_lo = jl < 0.0 ? 0 : (jl > (double)F ? F : (int)jl);
+        c.j_hi = jh < -1.0 ? -1 : (jh > (double)(F - 1) ? F - 1 : (int)jh);
+        if (!(jl == jl) || !(jh == jh)) { c.j_lo = 0; c.j_hi = -1; }
+        c.pad = 0;
+        gc[g] = c;
+      }
+      __syncthreads();
+      for (int q = 0; q < nb; ++q) {
+        const GaussComp c = gc[q];
+        int j = c.j_lo + ((tid - (c.j_lo % NT)) + NT) % NT;  // this thread's first owned point in the window
+        for (; j <= c.j_hi; j += NT) {
+          const double z = (grid_x(x0, delta, j) - c.cw) * c.inv_sigma;
+          if (fabs(z) <= BAYSAR_Z_CUT) A_AT(j) += c.amp * exp_neg_f32(-0.5 * z * z);
+        }
+      }
+      __syncthreads();
+    }
+  }
 
   // ================= line objects ==============================================================================
   for (int k = 0; k < ch[CH_N_LINES]; ++k) {
@@ -337,9 +477,15 @@ __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kerne
           if (tid == 0) {
             const double c0 = x0 - cwl;
             const int jc = (int)rint(-c0 / delta);
-            fz4[nf] = make_float4((float)jc, (float)fma((double)jc, delta, c0), (float)rec[11], (float)rec[12]);
-            fz_sum[nf] = rec[0];
-            fz_sum[BAYSAR_MAX_FUSED_LINES + nf] = rec[1];
+            FusedLine& L = fl[nf];
+            L.jc_f = (float)jc; L.r = (float)fma((double)jc, delta, c0); L.g_r = (float)rec[11]; L.g_e = (float)rec[12];
+            L.sum_r = rec[0]; L.sum_e = rec[1];
+            int jL = jc - BAYSAR_EM_WINDOW, jR = jc + BAYSAR_EM_WINDOW;
+            jL = jL < 0 ? 0 : (jL > F - 1 ? F - 1 : jL);
+            jR = jR < 0 ? 0 : (jR > F - 1 ? F - 1 : jR);
+            if (jL > 0) jL -= jL % BAYSAR_EM_STRIDE;                    // both tails: a whole number of strides
+            if (jR < F - 1) jR += (F - 1 - jR) % BAYSAR_EM_STRIDE;
+            L.jL = jL; L.jR = jR;
           }
           if (++nf == BAYSAR_MAX_FUSED_LINES) flush_fused();
           continue;
@@ -453,41 +599,6 @@ __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kerne
       __syncthreads();
       for (int j = F + tid; j < f8; j += NT) A_AT(j) = 0.f;  // keep the alignment tail clean
       __syncthreads();
-    } else {
-      // ---------------- Gaussian multiplet (ADAS406Lines / XLine) ----------------
-      double vel = 0.0; int has_vel = 0;
-      if (cl[CL_SPECIES] >= 0) {
-        int vi = m.sp_i[cl[CL_SPECIES] * SP_I_COUNT + SP_VEL_IDX];
-        if (vi >= 0) { vel = 1e3 * th[vi]; has_vel = 1; }
-      }
-      const double ems = rec[0];
-      const int ncmp = cl[CL_NCOMP];
-      for (int q = 0; q < ncmp; ++q) {
-        const double* cp = m.comp_d + (cl[CL_COMP_OFF] + q) * 2;
-        double cw = cp[0];
-        double fwhm;
-        if (kind == 1) {
-          if (has_vel) cw = cw * (vel / c_light + 1.0);
-          fwhm = cw * 7.715e-5 * sqrt(rec[4] / cld[CL_MASS]);
-        } else {
-          fwhm = cld[CL_FWHM];
-        }
-        if (!(fwhm > 0.0) || !(cp[1] > 0.0)) st |= 1u << 5;
-        const double sigma = fwhm * fwhm_to_sigma;
-        const double amp = (ems * (cp[1] / (2.5066282746310002 * sigma))) / cal;
-        if (!(amp - amp == 0.0)) st |= 1u << 6;
-        const double half = BAYSAR_Z_CUT * sigma;
-        double jl = ceil((cw - half - x0) / delta - 1e-9), jh = floor((cw + half - x0) / delta + 1e-9);
-        if (!(jl == jl) || !(jh == jh)) continue;
-        int j_lo = jl < 0.0 ? 0 : (jl > (double)F ? F : (int)jl);
-        int j_hi = jh < -1.0 ? -1 : (jh > (double)(F - 1) ? F - 1 : (int)jh);
-        int j = j_lo + ((tid - (j_lo % NT)) + NT) % NT;  // this thread's first owned point in the window
-        const float ampf = (float)amp;
-        for (; j <= j_hi; j += NT) {
-          double z = (grid_x(x0, delta, j) - cw) / sigma;
-          if (fabs(z) <= BAYSAR_Z_CUT) A_AT(j) += ampf * exp_neg_f32(-0.5 * z * z);
-        }
-      }
     }
   }
   if (nf > 0) flush_fused();

@@ -57,9 +57,11 @@ struct ModelDev {
 #ifndef BAYSAR_CPU_EMU
 BAYSAR_DEV float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 BAYSAR_DEV float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+BAYSAR_DEV float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #else
 BAYSAR_DEV float rcp_approx(float x) { return 1.0f / x; }
 BAYSAR_DEV float sqrt_approx(float x) { return sqrtf(x); }
+BAYSAR_DEV float rsqrt_approx(float x) { return 1.0f / sqrtf(x); }
 #endif
 
 // np.clip(v, lo, None): NaN propagates (fmax would swallow it)
@@ -134,12 +136,15 @@ BAYSAR_DEV void bspline_basis3(const double* t, int n, double x, int& l, double*
 }
 
 BAYSAR_DEV double bspline_eval(const double* c, int ncy, int lx, int ly, const double* hx, const double* hy) {
+  // sum_i hx[i] (sum_j c[i][j] hy[j]): 20 fused multiply-adds (FITPACK's fpbisp forms the same sum term by term)
   double sp = 0.0;
   const double* base = c + (int64_t)(lx - 3) * ncy + (ly - 3);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
+    double row = base[i * ncy] * hy[0];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) sp += base[i * ncy + j] * hx[i] * hy[j];
+    for (int j = 1; j < 4; ++j) row = fma(base[i * ncy + j], hy[j], row);
+    sp = fma(row, hx[i], sp);
   }
   return sp;
 }

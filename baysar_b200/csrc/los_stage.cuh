@@ -23,7 +23,9 @@ struct LosArgs {
 };
 
 // bytes of dynamic shared memory one warp needs for L line-of-sight points
-__host__ __device__ static inline size_t los_smem_per_warp(int L) { return (size_t)L * (14 * sizeof(double) + 4 * sizeof(int)); }
+__host__ __device__ static inline size_t los_smem_per_warp(int L, int n_params) {
+  return (size_t)L * (14 * sizeof(double) + 4 * sizeof(int)) + (size_t)(2 * n_params + (L & 1)) * sizeof(double);
+}
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) los_stage_kernel(ModelDev m, LosArgs a) {
@@ -42,8 +44,10 @@ __global__ void __launch_bounds__(WARPS * 32) los_stage_kernel(ModelDev m, LosAr
   const int n_chords = (int)I[I_N_CHORDS];
   const double* th = a.theta + n * n_params;
 
-  unsigned char* base = los_smem_raw + (size_t)warp * los_smem_per_warp(L);
-  double* ne_s = (double*)base;
+  unsigned char* base = los_smem_raw + (size_t)warp * los_smem_per_warp(L, n_params);
+  double* p10 = (double*)base;        // 10^theta[k]: every pow(10, theta) of the reference, one lane per parameter
+  double* l10 = p10 + n_params;       // log10(10^theta[k]) (the reference takes log10 of the transformed tau)
+  double* ne_s = l10 + n_params;
   double* te_s = ne_s + L;
   double* nm_s = te_s + L;   // main ion density
   double* n0_s = nm_s + L;   // neutral density profile
@@ -61,7 +65,11 @@ __global__ void __launch_bounds__(WARPS * 32) los_stage_kernel(ModelDev m, LosAr
     double v = th[k];
     if (v != v) st |= 1u << 0;
     if (v - v != 0.0 && v == v) st |= 1u << 1;  // +-inf
+    const double p = pow(10.0, v);
+    p10[k] = p;
+    l10[k] = log10(p);
   }
+  __syncwarp();
 
   // ---- electron density / temperature profiles (lineshapes.py:779-817)
   const int ne_idx = (int)I[I_NE_IDX], te_idx = (int)I[I_TE_IDX];
@@ -72,7 +80,7 @@ __global__ void __launch_bounds__(WARPS * 32) los_stage_kernel(ModelDev m, LosAr
     ne_A = th[ne_idx]; ne_c = th[ne_idx + 1]; ne_f = th[ne_idx + 2]; ne_floor = m.prof_d[PROF_NE_FLOOR];
   }
   const double te_A = th[te_idx], te_f = th[te_idx + 1], te_floor = th[te_idx + 2], te_c = m.prof_d[PROF_TE_CENTRE];
-  const double ne_pk = pow(10.0, ne_A), te_pk = pow(10.0, te_A);
+  const double ne_pk = p10[ne_idx], te_pk = p10[te_idx];
   double nemax = -1.7976931348623157e308;
   for (int l = lane; l < L; l += 32) {
     double x = m.los_x[l];
@@ -93,7 +101,7 @@ __global__ void __launch_bounds__(WARPS * 32) los_stage_kernel(ModelDev m, LosAr
   for (int l = lane; l < L; l += 32) {
     double ne = ne_s[l], tot = 0.0;
     for (int e = 0; e < n_elem; ++e) {
-      double dens = pow(10.0, th[m.elem_dens_idx[e]]);
+      double dens = p10[m.elem_dens_idx[e]];
       double conc = (dens / nemax) * ne;
       tot += (conc / nemax) * ne;
     }
@@ -105,7 +113,7 @@ __global__ void __launch_bounds__(WARPS * 32) los_stage_kernel(ModelDev m, LosAr
   for (int s = lane; s < n_species; s += 32) {
     const int* sp = m.sp_i + s * SP_I_COUNT;
     if (sp[SP_IS_IMPURITY]) {
-      double lt = log10(pow(10.0, th[sp[SP_TAU_IDX]]));
+      double lt = l10[sp[SP_TAU_IDX]];
       if (!(lt > m.tau_grid[0] && lt <= m.tau_grid[n_tau - 1])) st |= 1u << 2;
     }
   }
@@ -115,8 +123,8 @@ __global__ void __launch_bounds__(WARPS * 32) los_stage_kernel(ModelDev m, LosAr
   if (has_h) {
     const int* sp = m.sp_i + (int)I[I_H_SPECIES] * SP_I_COUNT;
     const int dens_idx = sp[SP_DENS_IDX];
-    const double tau_h = pow(10.0, th[sp[SP_TAU_IDX]]);
-    const double n0_sampled = dens_idx >= 0 ? pow(10.0, th[dens_idx]) : 0.0;
+    const double tau_h = p10[sp[SP_TAU_IDX]];
+    const double n0_sampled = dens_idx >= 0 ? p10[dens_idx] : 0.0;
     const int nne = (int)I[I_A11_NNE], nte = (int)I[I_A11_NTE];
     for (int l = lane; l < L; l += 32) {
       double ne = ne_s[l], te = te_s[l];
@@ -201,17 +209,11 @@ __global__ void __launch_bounds__(WARPS * 32) los_stage_kernel(ModelDev m, LosAr
       const int* sp = m.sp_i + ul[UL_SPECIES] * SP_I_COUNT;
       if (cold_neutrals) ti = 0.01;
       else if (thermalised) ti = (1 - f_rec) * exc_te + f_rec * rec_te;
-      else ti = pow(10.0, th[sp[SP_TI_IDX]]);
-      // shape constants shared by every chord that sees this line: Stark half-widths gamma^2.5 (stehle_param,
-      // linemodels.py:554-566), Doppler-shifted centre (:239-241) and Doppler sigma (:298, lineshapes.py:128).
-      // Lanes 0 / 1 take the two pow-heavy widths so that they run side by side.
+      else ti = p10[sp[SP_TI_IDX]];
+      // shape constants shared by every chord that sees this line: Doppler-shifted centre (linemodels.py:239-241) and
+      // Doppler sigma (:298, lineshapes.py:128); the pow-heavy Stark half-widths follow after the line loop, one
+      // lane per (line, recombination / excitation)
       const double* ud = m.ul_d + u * UL_D_COUNT;
-      if (lane < 2) {
-        const double la = ud[UL_LOMAN_A], lb = ud[UL_LOMAN_B], lc = ud[UL_LOMAN_C];
-        const double wne = lane == 0 ? rec_ne : exc_ne, wte = lane == 0 ? rec_te : exc_te;
-        const double g = (10.0 * lc * (pow(1e6 * wne, la) / pow(wte, lb))) / 2.0;
-        rec[11 + lane] = pow(g, 2.5);
-      }
       if (lane == 2) {
         rec[0] = rec_sum; rec[1] = exc_sum; rec[2] = rec_ne; rec[3] = rec_te; rec[4] = exc_ne; rec[5] = exc_te;
         rec[6] = ti; rec[7] = f_rec; rec[8] = s[10] / s[8]; rec[9] = s[11] / s[8]; rec[10] = ems;
@@ -223,8 +225,8 @@ __global__ void __launch_bounds__(WARPS * 32) los_stage_kernel(ModelDev m, LosAr
       }
     } else if (kind == 1) {  // ADAS406 (linemodels.py:386-426, :445-494)
       const int* sp = m.sp_i + ul[UL_SPECIES] * SP_I_COUNT;
-      const double dens = pow(10.0, th[sp[SP_DENS_IDX]]);
-      const double lt = log10(pow(10.0, th[sp[SP_TAU_IDX]]));
+      const double dens = p10[sp[SP_DENS_IDX]];
+      const double lt = l10[sp[SP_TAU_IDX]];
       int j = lower_bound(m.tau_grid, n_tau, lt);
       if (j >= n_tau) { st |= 1u << 2; j = n_tau - 1; }
       int i = j - 1;
@@ -250,17 +252,30 @@ __global__ void __launch_bounds__(WARPS * 32) los_stage_kernel(ModelDev m, LosAr
       double ti;
       if (cold_ions) ti = 0.01;
       else if (thermalised) ti = ems_te;
-      else ti = pow(10.0, th[sp[SP_TI_IDX]]);
+      else ti = p10[sp[SP_TI_IDX]];
       if (lane == 0) {
         rec[0] = s[1] / four_pi; rec[1] = s[2] / s[0]; rec[2] = s[3] / s[0]; rec[3] = ems_te; rec[4] = ti;
         for (int q = 5; q < BAYSAR_LINE_STRIDE; ++q) rec[q] = 0.0;
       }
     } else {  // XLine (linemodels.py:228-230)
       if (lane == 0) {
-        rec[0] = pow(10.0, th[ul[UL_TAB_A]]);
+        rec[0] = p10[ul[UL_TAB_A]];
         for (int q = 1; q < BAYSAR_LINE_STRIDE; ++q) rec[q] = 0.0;
       }
     }
+  }
+  __syncwarp();
+  // Stark half-widths gamma^2.5 of every Balmer line (stehle_param, linemodels.py:554-566): lane 2q / 2q+1 take the
+  // recombination / excitation width of the q-th Balmer line, so that all the pow() calls run side by side
+  for (int idx = lane; idx < 2 * n_ul; idx += 32) {
+    const int u = idx >> 1, which = idx & 1;
+    if (m.ul_i[u * UL_I_COUNT + UL_KIND] != 0) continue;
+    const double* ud = m.ul_d + u * UL_D_COUNT;
+    double* rec = lines_n + u * BAYSAR_LINE_STRIDE;
+    const double la = ud[UL_LOMAN_A], lb = ud[UL_LOMAN_B], lc = ud[UL_LOMAN_C];
+    const double wne = rec[2 + 2 * which], wte = rec[3 + 2 * which];
+    const double g = (10.0 * lc * (pow(1e6 * wne, la) / pow(wte, lb))) / 2.0;
+    rec[11 + which] = pow(g, 2.5);
   }
   __syncwarp();
 
@@ -335,10 +350,10 @@ __global__ void __launch_bounds__(WARPS * 32) los_stage_kernel(ModelDev m, LosAr
       double t1 = (pd[PR_D1] - th[pi[PR_I0] + 1]) / pd[PR_D3];
       val = -0.5 * (t0 * t0) + -0.5 * (t1 * t1);
     } else if (kind == PRIOR_INTENSITY_CAL) {  // priors.py:1063-1076
-      double t0 = (1.0 - pow(10.0, th[pi[PR_I0]])) / 0.2;
+      double t0 = (1.0 - p10[pi[PR_I0]]) / 0.2;
       val = -0.5 * (t0 * t0);
     } else if (kind == PRIOR_GAUSSIAN_IF) {  // priors.py:1079-1089
-      double t0 = (pow(10.0, th[pi[PR_I0]]) - 0.8) / 0.1;
+      double t0 = (p10[pi[PR_I0]] - 0.8) / 0.1;
       val = -0.5 * (t0 * t0);
     }
     if (lane == 0) comp[k] = val;

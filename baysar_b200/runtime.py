@@ -85,7 +85,8 @@ def microbench(device=0):
     """Measured FP32-FMA / MUFU / FP64-FMA peak rates of this GPU (flop/s, op/s, flop/s)."""
     lib = library()
     out = {}
-    for what, key in ((0, "fp32_fma_flops"), (1, "mufu_ops"), (2, "fp64_fma_flops")):
+    for what, key in ((0, "fp32_fma_flops"), (1, "mufu_ops"), (2, "fp64_fma_flops"), (3, "fp32_fma_reg_flops"),
+                      (4, "fp32_fma2_flops")):
         val = ctypes.c_double()
         if lib.baysar_microbench(int(device), what, ctypes.byref(val)) != 0:
             raise RuntimeError("baysar_b200: " + lib.baysar_last_error().decode())

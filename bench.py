@@ -161,19 +161,24 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------- flop accounting
 def flop_model(post):
-    """Executed flop per eval, per kernel, from the compiled model, and the SURVEY section 8d dense-semantics figure.
+    """Executed FP32 flop and MUFU (SFU) ops per eval, per kernel, from the compiled model, and the SURVEY section 8d
+    dense-semantics figure.
 
-    chord (FP32 pipe): Stark sweeps 18 F per Balmer line, Doppler and (fused path only) instrument convolutions at
-    2 flop per tap and output, 14 F + 12 P of bookkeeping.  contract (tensor pipe, 3xTF32): per 128x128 output tile and
-    32-wide k-block one N=256 and one N=128 MMA per 8-deep k-step, including the zero part of the Toeplitz tiles."""
+    chord (FP32 + MUFU pipes): narrow-Doppler Balmer lines (cold neutrals) cost 15 flop + 2 MUFU per sweep-1 sample
+    (dense +-256-point window, every 16th point on the tails) and 14 flop + 1 MUFU per fine-grid point in sweep 2;
+    Balmer lines with a multi-tap Doppler kernel 18 F + 2 taps F flop and 3 F MUFU; Gaussian components 8 flop + 1
+    MUFU per point of their +-8.85 sigma window; 14 F + 12 P of bookkeeping and (fused path only) the instrument
+    convolution at 2 flop per tap and output.  contract (tensor pipe, 3xTF32): per 128x128 output tile and 32-wide
+    k-block one N=256 and one N=128 MMA per 8-deep k-step, including the zero part of the Toeplitz tiles."""
     from baysar_b200.spectrometers import BalmerHydrogenLine
 
     tensor_path = post.model.uses_tensor_cores
-    chord = contract = dense = 0.0
+    chord = contract = dense = mufu = 0.0
     for ch in post.chords:
         F, P = len(ch.x_data_fm), len(ch.x_data)
         n_b = sum(isinstance(l, BalmerHydrogenLine) for l in ch.lines)
-        n_g = sum(len(getattr(l, "lines", getattr(l, "cwl", []))) for l in ch.lines if not isinstance(l, BalmerHydrogenLine))
+        gauss = [l for l in ch.lines if not isinstance(l, BalmerHydrogenLine)]
+        n_g = sum(len(getattr(l, "lines", getattr(l, "cwl", []))) for l in gauss)
         k_d = max([len(l.wavelengths_doppler) for l in ch.lines if isinstance(l, BalmerHydrogenLine)] or [0])
         inst = np.abs(ch.instrument_function_fm)
         keep = np.where(inst > 1e-17 * inst.max())[0]
@@ -182,8 +187,20 @@ def flop_model(post):
         dl = np.diff(ch.x_data_fm).mean()
         ti = 0.01 if post.plasma.cold_neutrals else 5.0
         sigma = 4000.0 * 7.715e-5 * np.sqrt(ti / 2.0) / np.sqrt(8 * np.log(2))
-        nq_d = (2 * int(8.85 * sigma / dl) + 1 + 3) // 4 * 4 + 4
-        chord += n_b * (18.0 * F + 2.0 * nq_d * F) + 14.0 * F + 12.0 * P
+        n_taps = 2 * int(6.9 * sigma / dl) + 1
+        if n_taps == 1:
+            n_s1 = min(F, 545) + max(F - 545, 0) / 16.0
+            chord += n_b * (15.0 * n_s1 + 14.0 * F)
+            mufu += n_b * (2.0 * n_s1 + F)
+        else:
+            nq_d = (n_taps + 3) // 4 * 4 + 4
+            chord += n_b * (18.0 * F + 2.0 * nq_d * F)
+            mufu += n_b * 3.0 * F
+        # Gaussian components: typical window for an impurity ion at Ti = 0.01 eV / a pixel-wide X line
+        sig_g = max(4000.0 * 7.715e-5 * np.sqrt(0.01 / 14.0) / np.sqrt(8 * np.log(2)), 0.0)
+        pts_g = n_g * (2 * 8.85 * max(sig_g, dl / 4) / dl + 1)
+        chord += 8.0 * pts_g + 14.0 * F + 12.0 * P
+        mufu += pts_g + P
         if tensor_path:
             o = (len(inst) - 1) // 2
             n_kb = (127 + o - k_lo) // 32 - (o - k_hi + 1) // 32 + 1
@@ -193,7 +210,7 @@ def flop_model(post):
             chord += 2.0 * nq_if * F
         dense += 8.0 * n_g * F + n_b * 2 * (10.0 * F + 2.0 * k_d * F + 3.0 * F) + 12.0 * F + 10.0 * P \
             + 2.0 * F * len(ch.instrument_function_fm)
-    return {"chord": chord, "contract": contract, "dense": dense}
+    return {"chord": chord, "contract": contract, "dense": dense, "chord_mufu": mufu}
 
 
 # ----------------------------------------------------------------------------------------------- main
@@ -366,6 +383,17 @@ def main():
         k["achieved"] = k["flop_per_eval"] * batch / (k["ms"] * 1e-3) / 1e12 if k["ms"] > 0 else 0.0
         k["frac"] = k["achieved"] / k["peak"]
         k["unit"] = "TFLOP/s"
+    # the spectral kernel issues FP32 and MUFU work side by side: report both pipes, the larger fraction governs
+    ck = kernels["chord_stage_kernel"]
+    ck["mufu_per_eval"] = flops["chord_mufu"]
+    ck["mufu_achieved_Gops"] = flops["chord_mufu"] * batch / (ck["ms"] * 1e-3) / 1e9 if ck["ms"] > 0 else 0.0
+    ck["mufu_peak_Gops"] = peaks["mufu_ops"] / 1e9
+    ck["frac_mufu"] = ck["mufu_achieved_Gops"] / ck["mufu_peak_Gops"]
+    ck["frac_fp32"] = ck["frac"]
+    if ck["frac_mufu"] > ck["frac"]:
+        ck["bound"], ck["frac"] = "mufu", ck["frac_mufu"]
+    ck["fp32_peak_3reg_tflops"] = peaks["fp32_fma_reg_flops"] / 1e12
+    ck["fp32_peak_ffma2_tflops"] = peaks["fp32_fma2_flops"] / 1e12
     dom = max(kernels, key=lambda name: kernels[name]["ms"])
     hbm_bytes = batch * (8.0 * n_params + 8.0 + 4.0 + 8.0 * (len(post.chords) + len(post.priors))
                          + 2 * 8.0 * 16 * post.model.n_ulines)

@@ -35,7 +35,7 @@ extern "C" int emu_eval_split(const unsigned char* blob, const double* theta, lo
   LosArgs la{theta, n, lines, comps, hdr.data(), nullptr, status};
   EmuDim3 g;
   g.x = (unsigned)((n + 3) / 4);
-  emu_launch(los_stage_kernel<4>, g, 128u, 4 * los_smem_per_warp(L), m, la);
+  emu_launch(los_stage_kernel<4>, g, 128u, 4 * los_smem_per_warp(L, (int)I[I_N_PARAMS]), m, la);
   for (int c = 0; c < n_chords; ++c) {
     const int* ch = m.ch_i + c * CH_I_COUNT;
     const int F = ch[CH_F], KI = ch[CH_KI], k_lo = ch[CH_IF_KLO], k_hi = ch[CH_IF_KHI], o = (KI - 1) / 2;
@@ -97,7 +97,7 @@ extern "C" int emu_eval(const unsigned char* blob, const double* theta, long n, 
   LosArgs la{theta, n, lines, comps, hdr.data(), profiles, status};
   EmuDim3 g;
   g.x = (unsigned)((n + 3) / 4);
-  emu_launch(los_stage_kernel<4>, g, 128u, 4 * los_smem_per_warp(L), m, la);
+  emu_launch(los_stage_kernel<4>, g, 128u, 4 * los_smem_per_warp(L, (int)I[I_N_PARAMS]), m, la);
   for (int c = 0; c < n_chords; ++c) {
     const int* ch = m.ch_i + c * CH_I_COUNT;
     int kd_max = 0;

@@ -145,3 +145,51 @@ def chord_forward_model(oracle, ch, st, scalars):
     fm = np.maximum(bg + (Sc64[i] + a * (Sc64[i + 1] - Sc64[i])) / ratio, bg)
     r2 = ((ch.y_data - fm) / ch.error) ** 2
     return fm, -np.log(1 + r2).sum()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Narrow-Doppler Balmer lines: strided-tail integral (Euler-Maclaurin) and far-field series of the fused sweeps
+EM_STRIDE, EM_WINDOW, FAR_RATIO = 16, 256, 500.0  # keep in sync with csrc/chord_stage.cuh
+
+
+def stark_integral_strided(F, delta, jc, r, g, stride=EM_STRIDE, window=EM_WINDOW):
+    """trapz (unit spacing, half weights at the two ends of the grid) of 1 / (|x_j|^2.5 + g), x_j = (j - jc) delta + r,
+    the way sweep 1 of the chord kernel forms it: dense inside the window, every `stride`-th point on the tails plus
+    the first two Euler-Maclaurin end corrections.  float64 throughout (the kernel's float32 partial sums are covered
+    by the fixture comparisons)."""
+    f = lambda x: 1.0 / (np.abs(x) ** 2.5 + g)  # noqa: E731
+    x = (np.arange(F) - jc) * delta + r
+    jL, jR = np.clip(jc - window, 0, F - 1), np.clip(jc + window, 0, F - 1)
+    if jL > 0:
+        jL -= jL % stride
+    if jR < F - 1:
+        jR += (F - 1 - jR) % stride
+    tot = 0.0
+    if jR > jL:
+        w = np.ones(jR - jL + 1)
+        w[0] = w[-1] = 0.5
+        tot += np.sum(w * f(x[jL:jR + 1]))
+    for a, b in ((0, jL), (jR, F - 1)):
+        if b <= a:
+            continue
+        idx = np.arange(a, b + 1, stride)
+        w = np.full(len(idx), float(stride))
+        w[0] = w[-1] = 0.5 * stride
+        tot += np.sum(w * f(x[idx]))
+        sgn = 1.0 if x[a] > 0 else -1.0
+        d1, d3 = [], []
+        for xe in (abs(x[a]), abs(x[b])):
+            sq = np.sqrt(xe)
+            D, D1, D2, D3 = xe * xe * sq + g, 2.5 * xe * sq, 3.75 * sq, 1.875 / sq
+            d1.append(-D1 / D ** 2)
+            d3.append(-D3 / D ** 2 + 6 * D1 * D2 / D ** 3 - 6 * D1 ** 3 / D ** 4)
+        tot += -(stride ** 2 - 1) / 12 * sgn * delta * (d1[1] - d1[0])
+        tot += (stride ** 4 - 1) / 720 * sgn * delta ** 3 * (d3[1] - d3[0])
+    return tot
+
+
+def stark_pair_far_field(d, s_r, s_e, g_r, g_e):
+    """s_r / (d^2.5 + g_r) + s_e / (d^2.5 + g_e) by the three-term series in 1 / d^2.5 that sweep 2 uses where
+    d^2.5 >= FAR_RATIO max(g_r, g_e)."""
+    ia = d ** -2.5
+    return ia * ((s_r + s_e) - ia * ((s_r * g_r + s_e * g_e) - ia * (s_r * g_r ** 2 + s_e * g_e ** 2)))

@@ -26,3 +26,40 @@ def test_fp32_algorithm_holds_tolerance(name):
     print(f"{name}: spectra rel {worst_s:.2e}  logL rel {worst_l:.2e}")
     assert worst_s < 1e-5
     assert worst_l < 1e-6
+
+
+def test_strided_tail_integral_matches_dense_trapz():
+    """Sweep 1 of the narrow-Doppler Balmer passes: dense window + strided tails + Euler-Maclaurin end terms equals
+    the dense trapz over the whole fine grid to < 1e-8 relative, for every Stark width and line position."""
+    from .kernel_model import stark_integral_strided
+
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for trial in range(600):
+        F = int(rng.integers(700, 9000))
+        delta = float(rng.choice([0.01, 0.05, 0.1]))
+        gamma = 10 ** rng.uniform(-2.5, 1.2)  # Angstrom
+        jc = int(rng.integers(-400, F + 400)) if trial % 4 == 0 else int(rng.integers(0, F))
+        r = float(rng.uniform(-0.5, 0.5)) * delta
+        x = (np.arange(F) - jc) * delta + r
+        w = np.ones(F)
+        w[0] = w[-1] = 0.5
+        dense = np.sum(w / (np.abs(x) ** 2.5 + gamma ** 2.5))
+        worst = max(worst, abs(stark_integral_strided(F, delta, jc, r, gamma ** 2.5) - dense) / dense)
+    print(f"strided-tail integral: worst relative error {worst:.2e}")
+    assert worst < 1e-8
+
+
+def test_far_field_series_of_stark_pair():
+    from .kernel_model import FAR_RATIO, stark_pair_far_field
+
+    rng = np.random.default_rng(6)
+    worst = 0.0
+    for _ in range(2000):
+        g_r, g_e = 10 ** rng.uniform(-6, 3, size=2)
+        s_r, s_e = 10 ** rng.uniform(8, 14, size=2)
+        d = (FAR_RATIO * max(g_r, g_e)) ** 0.4 * 10 ** rng.uniform(0, 2)
+        exact = s_r / (d ** 2.5 + g_r) + s_e / (d ** 2.5 + g_e)
+        worst = max(worst, abs(stark_pair_far_field(d, s_r, s_e, g_r, g_e) - exact) / exact)
+    print(f"far-field series: worst relative error {worst:.2e}")
+    assert worst < 2e-8
