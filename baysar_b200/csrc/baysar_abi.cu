@@ -72,7 +72,8 @@ struct baysar_model {
   bool any_ifc = false;
   int64_t ifc_rows = 0;              // rows of the split / conv workspaces (multiple of 128)
   int64_t ifc_budget_bytes = (int64_t)24 << 30;  // HBM budget of those workspaces (BAYSAR_IFC_BUDGET_MB at create)
-  float *split_hi = nullptr, *split_lo = nullptr, *conv = nullptr;
+  float *spec = nullptr, *conv = nullptr;  // zero-padded FP32 spectra (A operand), convolved spectra
+  int sm_count = 0;
   double *trapz_part = nullptr, *aux = nullptr;
   int64_t split_pitch_max = 0, conv_pitch_max = 0;
   int tiles_max = 0;
@@ -240,22 +241,20 @@ int ensure_ifc_workspace(baysar_model* m, int64_t n) {
   // rows handled per pass of the tensor-core path: bounded so that the split / convolved spectra stay within a
   // fixed HBM budget (8 bytes of operands + 4 bytes of output per fine-grid point and row)
   const int64_t budget = m->ifc_budget_bytes;
-  const int64_t per_row = 4 * (2 * m->split_pitch_max + m->conv_pitch_max) + 8 * m->tiles_max;
+  const int64_t per_row = 4 * (m->split_pitch_max + m->conv_pitch_max) + 8 * m->tiles_max;
   int64_t rows = (n + ifc::TILE_M - 1) / ifc::TILE_M * ifc::TILE_M;
   int64_t max_rows = budget / per_row / ifc::TILE_M * ifc::TILE_M;
   if (max_rows < ifc::TILE_M) max_rows = ifc::TILE_M;
   if (rows > max_rows) rows = max_rows;
   if (rows <= m->ifc_rows) return 0;
-  cudaFree(m->split_hi); cudaFree(m->split_lo); cudaFree(m->conv); cudaFree(m->trapz_part); cudaFree(m->aux);
-  m->split_hi = m->split_lo = m->conv = nullptr; m->trapz_part = m->aux = nullptr; m->ifc_rows = 0;
-  CUDA_OK(cudaMalloc(&m->split_hi, sizeof(float) * rows * m->split_pitch_max));
-  CUDA_OK(cudaMalloc(&m->split_lo, sizeof(float) * rows * m->split_pitch_max));
+  cudaFree(m->spec); cudaFree(m->conv); cudaFree(m->trapz_part); cudaFree(m->aux);
+  m->spec = m->conv = nullptr; m->trapz_part = m->aux = nullptr; m->ifc_rows = 0;
+  CUDA_OK(cudaMalloc(&m->spec, sizeof(float) * rows * m->split_pitch_max));
   CUDA_OK(cudaMalloc(&m->conv, sizeof(float) * rows * m->conv_pitch_max));
   CUDA_OK(cudaMalloc(&m->trapz_part, sizeof(double) * rows * m->tiles_max));
   CUDA_OK(cudaMalloc(&m->aux, sizeof(double) * rows * BAYSAR_AUX_STRIDE));
   // rows past the end of a batch are multiplied too (M = 128 granularity): keep them finite
-  CUDA_OK(cudaMemset(m->split_hi, 0, sizeof(float) * rows * m->split_pitch_max));
-  CUDA_OK(cudaMemset(m->split_lo, 0, sizeof(float) * rows * m->split_pitch_max));
+  CUDA_OK(cudaMemset(m->spec, 0, sizeof(float) * rows * m->split_pitch_max));
   m->ifc_rows = rows;
   return 0;
 }
@@ -319,7 +318,7 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
       a.lines = lines + r0 * m->I[I_N_ULINES] * BAYSAR_LINE_STRIDE;
       a.components = comps + r0 * ncols; a.spectra = nullptr;
       a.fine_pre = fine_pre ? fine_pre + r0 * F : nullptr; a.fine_post = nullptr; a.status = status + r0;
-      a.split_hi = m->split_hi; a.split_lo = m->split_lo; a.split_pitch = pl.pitch; a.split_pad = pl.pad_left;
+      a.spec = m->spec; a.split_pitch = pl.pitch; a.split_pad = pl.pad_left;
       a.aux = m->aux;
       CUDA_OK(cudaFuncSetAttribute(chord_stage_kernel<NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)m->chord_smem_max));
@@ -328,14 +327,15 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
       if (mark(m, ST_CHORD, stream)) return 1;
       // K2b: tcgen05 contraction with the banded-Toeplitz instrument matrix
       ifc::Params p{};
-      p.s_hi = m->split_hi; p.s_lo = m->split_lo; p.pitch = pl.pitch; p.pad_left = pl.pad_left; p.F = F;
-      p.n_rows = (int)rows128; p.m_lo = pl.m_lo; p.m_hi = pl.m_hi; p.taps_rev = m->ifc_taps_dev[c];
+      p.s = m->spec; p.pitch = pl.pitch; p.pad_left = pl.pad_left; p.F = F;
+      p.n_row_blocks = (int)(rows128 / ifc::TILE_M); p.m_lo = pl.m_lo; p.m_hi = pl.m_hi; p.taps_rev = m->ifc_taps_dev[c];
       p.taps_len = pl.taps_len; p.row_min = nullptr; p.aux = m->aux; p.aux_rows = (int)rows;
       p.out = m->conv; p.out_pitch = pl.out_pitch; p.trapz_part = m->trapz_part; p.n_tiles = pl.n_tiles;
-      const size_t smem = ifc::smem_bytes(pl.taps_len);
+      const size_t smem = ifc::smem_bytes(pl.m_hi - pl.m_lo + 1);
       CUDA_OK(cudaFuncSetAttribute(ifc::if_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      ifc::if_contract_kernel<<<dim3((unsigned)pl.n_tiles, (unsigned)(rows128 / ifc::TILE_M)), ifc::THREADS, smem,
-                                stream>>>(p);
+      const int64_t tiles = (int64_t)p.n_row_blocks * pl.n_tiles;
+      const unsigned ctas = (unsigned)(tiles < m->sm_count ? tiles : m->sm_count);  // persistent: one CTA per SM
+      ifc::if_contract_kernel<<<ctas, ifc::THREADS, smem, stream>>>(p);
       CUDA_OK(cudaGetLastError());
       if (mark(m, ST_CONTRACT, stream)) return 1;
       // K2c: area renormalisation, wavelength map, likelihood
@@ -442,6 +442,8 @@ int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar
     return fail("fine grid too long for the shared-memory chord stage (needs " + std::to_string(smem_max) + " B)");
   }
   m->chord_smem_max = smem_max;
+  cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (m->sm_count <= 0) m->sm_count = 148;
   // tensor-core contraction for chords with a long, theta-independent instrument function
   const char* env = getenv("BAYSAR_IFC");
   const bool ifc_enabled = !(env && env[0] == '0');
@@ -458,7 +460,7 @@ int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar
     if (!ifc_enabled || ch[CH_CALINT_IDX] >= 0 || window < min_taps || ch[CH_F] < 256) continue;
     m->ifc[c] = make_ifc_plan(ifn_host + ch[CH_IF_OFF], ch[CH_KI], ch[CH_IF_KLO], ch[CH_IF_KHI], ch[CH_F]);
     const IfcPlan& pl = m->ifc[c];
-    if (ifc::smem_bytes(pl.taps_len) > 227 * 1024) { m->ifc[c] = IfcPlan(); continue; }
+    if (pl.m_hi - pl.m_lo + 1 > ifc::MAX_KB) { m->ifc[c] = IfcPlan(); continue; }  // band too wide for the master tile
     cudaError_t e2 = cudaMalloc(&m->ifc_taps_dev[c], sizeof(float) * pl.taps_rev.size());
     if (e2 == cudaSuccess)
       e2 = cudaMemcpy(m->ifc_taps_dev[c], pl.taps_rev.data(), sizeof(float) * pl.taps_rev.size(), cudaMemcpyHostToDevice);
@@ -477,7 +479,7 @@ void baysar_model_destroy(baysar_model_t* m) {
   cudaSetDevice(m->device);
   cudaFree(m->blob_dev); cudaFree(m->lines); cudaFree(m->comps); cudaFree(m->hdr); cudaFree(m->status);
   cudaFree(m->theta_stage); cudaFree(m->logp_stage);
-  cudaFree(m->split_hi); cudaFree(m->split_lo); cudaFree(m->conv); cudaFree(m->trapz_part); cudaFree(m->aux);
+  cudaFree(m->spec); cudaFree(m->conv); cudaFree(m->trapz_part); cudaFree(m->aux);
   for (float* t : m->ifc_taps_dev) cudaFree(t);
   for (cudaEvent_t ev : m->prof_events) cudaEventDestroy(ev);
   delete m;
@@ -614,28 +616,30 @@ int baysar_debug_if_contract(const float* spectra_dev, int64_t n_rows, int F, co
   IfcPlan pl = make_ifc_plan(taps_host, KI, k_lo, k_hi, F);
   if (out_pitch) *out_pitch = pl.out_pitch;
   if (n_tiles) *n_tiles = pl.n_tiles;
-  float *hi = nullptr, *lo = nullptr, *taps = nullptr;
-  CUDA_OK(cudaMalloc(&hi, sizeof(float) * n_rows * pl.pitch));
-  CUDA_OK(cudaMalloc(&lo, sizeof(float) * n_rows * pl.pitch));
+  if (pl.m_hi - pl.m_lo + 1 > ifc::MAX_KB) return fail("instrument function too wide for the tensor-core contraction");
+  float *spec = nullptr, *taps = nullptr;
+  CUDA_OK(cudaMalloc(&spec, sizeof(float) * n_rows * pl.pitch));
   CUDA_OK(cudaMalloc(&taps, sizeof(float) * pl.taps_rev.size()));
-  CUDA_OK(cudaMemset(hi, 0, sizeof(float) * n_rows * pl.pitch));
-  CUDA_OK(cudaMemset(lo, 0, sizeof(float) * n_rows * pl.pitch));
+  CUDA_OK(cudaMemset(spec, 0, sizeof(float) * n_rows * pl.pitch));
   CUDA_OK(cudaMemcpy(taps, pl.taps_rev.data(), sizeof(float) * pl.taps_rev.size(), cudaMemcpyHostToDevice));
-  ifc::split_rows_kernel<<<dim3(8, (unsigned)n_rows), 256>>>(spectra_dev, n_rows, F, hi, lo, pl.pitch, pl.pad_left);
+  ifc::pad_rows_kernel<<<dim3(8, (unsigned)n_rows), 256>>>(spectra_dev, n_rows, F, spec, pl.pitch, pl.pad_left);
   CUDA_OK(cudaGetLastError());
-  ifc::Params p;
-  p.s_hi = hi; p.s_lo = lo; p.pitch = pl.pitch; p.pad_left = pl.pad_left; p.F = F; p.n_rows = (int)n_rows;
+  ifc::Params p{};
+  p.s = spec; p.pitch = pl.pitch; p.pad_left = pl.pad_left; p.F = F; p.n_row_blocks = (int)(n_rows / ifc::TILE_M);
   p.m_lo = pl.m_lo; p.m_hi = pl.m_hi; p.taps_rev = taps; p.taps_len = pl.taps_len; p.row_min = row_min_dev; p.aux = nullptr; p.aux_rows = 0;
   p.out = out_dev; p.out_pitch = pl.out_pitch; p.trapz_part = trapz_dev; p.n_tiles = pl.n_tiles;
-  const size_t smem = ifc::smem_bytes(pl.taps_len);
+  const size_t smem = ifc::smem_bytes(pl.m_hi - pl.m_lo + 1);
   CUDA_OK(cudaFuncSetAttribute(ifc::if_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t e0, e1;
   CUDA_OK(cudaEventCreate(&e0));
   CUDA_OK(cudaEventCreate(&e1));
-  dim3 grid((unsigned)pl.n_tiles, (unsigned)(n_rows / ifc::TILE_M));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int64_t tiles = (int64_t)p.n_row_blocks * pl.n_tiles;
+  const unsigned ctas = (unsigned)(tiles < sms ? tiles : sms);
   for (int rep = 0; rep < 2; ++rep) {
     CUDA_OK(cudaEventRecord(e0, 0));
-    ifc::if_contract_kernel<<<grid, ifc::THREADS, smem>>>(p);
+    ifc::if_contract_kernel<<<ctas, ifc::THREADS, smem>>>(p);
     CUDA_OK(cudaEventRecord(e1, 0));
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventSynchronize(e1));
@@ -644,7 +648,7 @@ int baysar_debug_if_contract(const float* spectra_dev, int64_t n_rows, int F, co
   CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
   if (elapsed_ms) *elapsed_ms = ms;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(hi); cudaFree(lo); cudaFree(taps);
+  cudaFree(spec); cudaFree(taps);
   return 0;
 }
 

@@ -38,9 +38,8 @@ struct ChordArgs {
   float* fine_pre;          // optional [N][F]
   float* fine_post;         // optional [N][F]
   uint32_t* status;         // [N] OR-ed
-  // MODE 1 (spectral stage of the tensor-core path): TF32-split pre-convolution spectra and per-theta scalars
-  float* split_hi;          // [rows][split_pitch], written at column split_pad + j
-  float* split_lo;
+  // MODE 1 (spectral stage of the tensor-core path): zero-padded pre-convolution spectra and per-theta scalars
+  float* spec;              // [rows][split_pitch], written at column split_pad + j
   int64_t split_pitch;
   int split_pad;
   double* aux;              // [N][BAYSAR_AUX_STRIDE]: pre-area, minimum, 4 float64 end outputs
@@ -276,7 +275,13 @@ __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kerne
   // reduction: sweep 1 integrates u_rec / u_exc of every line (trapz, half weights at the ends), sweep 2 adds
   // sum_b (rec_sum_b u_rec_b / I_rec_b + exc_sum_b u_exc_b / I_exc_b) to the spectrum.
   int nf = 0;
-  auto flush_fused = [&]() {
+  // accumulated by the LAST fused pass (which then also owns the pre-convolution area / minimum and, in MODE 1, the
+  // hand-over of the spectrum) or by the separate pass further down
+  float pre_f = 0.f;
+  float mn = 3.402823466e38f;
+  int bad = 0;
+  bool pre_done = false;
+  auto flush_fused = [&](const bool final_pass) {
     __syncthreads();  // constants written by thread 0
     // ---- sweep 1: I_rec, I_exc = trapz of the two Stark profiles of every line over the whole grid.
     // Only a window of +-BAYSAR_EM_WINDOW points around the line centre is summed point by point; on the two tails,
@@ -311,77 +316,116 @@ __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kerne
       if (lane == 0) { scratch[(2 * b) * (NT / 32) + warp] = wr; scratch[(2 * b + 1) * (NT / 32) + warp] = we; }
     }
     __syncthreads();
-    if (tid < nf) {
-      FusedLine& L = fl[tid];
-      double ir = 0.0, ie = 0.0;
+    // one thread per (line, recombination / excitation): integral, Euler-Maclaurin end terms, amplitude
+    if (tid < 2 * nf) {
+      FusedLine& L = fl[tid >> 1];
+      const int q = tid & 1;
+      double integ = 0.0;
 #pragma unroll
-      for (int w = 0; w < NT / 32; ++w) { ir += scratch[(2 * tid) * (NT / 32) + w]; ie += scratch[(2 * tid + 1) * (NT / 32) + w]; }
-      // Euler-Maclaurin end corrections of the strided tails (float64, once per line)
-      const double gr = (double)L.g_r, ge = (double)L.g_e;
-      const double c1 = (double)(S * S - 1) / 12.0, c3 = ((double)S * S * S * S - 1.0) / 720.0;
+      for (int w = 0; w < NT / 32; ++w) integ += scratch[tid * (NT / 32) + w];
+      // the end terms are ~1e-6 of the integral: float32 with approximate reciprocals is ample
+      const float g = q == 0 ? L.g_r : L.g_e;
+      const float c1 = (float)(S * S - 1) / 12.f, c3 = ((float)S * S * S * S - 1.f) / 720.f;
+      const float df = (float)delta;
+      float corr = 0.f;
+#pragma unroll
       for (int side = 0; side < 2; ++side) {
         const int ja = side == 0 ? 0 : L.jR, jb = side == 0 ? L.jL : F - 1;
-        if (jb <= ja) continue;
-        double f1[2][2], f3[2][2];  // [end][rec, exc]
-        double sgn = 1.0;
+        if (jb > ja) {
+          float f1[2], f3[2];
+          float sgn = 1.f;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const double xs = ((double)(e == 0 ? ja : jb) - (double)L.jc_f) * delta + (double)L.r;
-          if (e == 0) sgn = xs > 0.0 ? 1.0 : -1.0;
-          const double x = fabs(xs), sq = sqrt(x);
-          const double D1 = 2.5 * x * sq, D2 = 3.75 * sq, D3 = 1.875 / sq, x25 = x * x * sq;
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const double iD = 1.0 / (x25 + (q == 0 ? gr : ge)), iD2 = iD * iD;
-            f1[e][q] = -D1 * iD2;
-            f3[e][q] = -D3 * iD2 + 6.0 * D1 * D2 * iD2 * iD - 6.0 * D1 * D1 * D1 * iD2 * iD2;
+          for (int e = 0; e < 2; ++e) {
+            const float xs = ((float)(e == 0 ? ja : jb) - L.jc_f) * df + L.r;
+            if (e == 0) sgn = xs > 0.f ? 1.f : -1.f;
+            const float x = fabsf(xs), sq = sqrt_approx(x);
+            const float D1 = 2.5f * x * sq, D2 = 3.75f * sq, D3 = 1.875f * rcp_approx(sq);
+            const float iD = rcp_approx(x * x * sq + g), iD2 = iD * iD;
+            f1[e] = -D1 * iD2;
+            f3[e] = -D3 * iD2 + 6.f * D1 * D2 * iD2 * iD - 6.f * D1 * D1 * D1 * iD2 * iD2;
           }
+          corr += sgn * (-c1 * df * (f1[1] - f1[0]) + c3 * df * df * df * (f3[1] - f3[0]));
         }
-        const double h1 = sgn * delta, h3 = sgn * delta * delta * delta;
-        ir += -c1 * h1 * (f1[1][0] - f1[0][0]) + c3 * h3 * (f3[1][0] - f3[0][0]);
-        ie += -c1 * h1 * (f1[1][1] - f1[0][1]) + c3 * h3 * (f3[1][1] - f3[0][1]);
       }
-      const double s_rec = L.sum_r / (dl * ir) / cal;
-      const double s_exc = L.sum_e / (dl * ie) / cal;
-      if (!(s_rec - s_rec == 0.0) || !(s_exc - s_exc == 0.0)) atomicOr(&a.status[n], 1u << 6);
-      // sweep-2 constants: exact form next to the centre, far-field series
-      //   s_r / (a + g_r) + s_e / (a + g_e) = (1/a) (c0 - (1/a) (c1 - (1/a) c2)) + O((g/a)^3),  a = |d|^2.5
-      L.s_r = (float)s_rec; L.s_e = (float)s_exc;
-      L.c0 = (float)(s_rec + s_exc);
-      L.c1 = (float)(s_rec * gr + s_exc * ge);
-      L.c2 = (float)(s_rec * gr * gr + s_exc * ge * ge);
-      const double gmax = gr > ge ? gr : ge;
-      L.d_far = (float)pow((double)BAYSAR_FAR_RATIO * gmax, 0.4);
+      integ += (double)corr;
+      const double amp = (q == 0 ? L.sum_r : L.sum_e) / (dl * integ) / cal;
+      if (!(amp - amp == 0.0)) atomicOr(&a.status[n], 1u << 6);
+      (q == 0 ? L.s_r : L.s_e) = (float)amp;
     }
     __syncthreads();
-    // ---- sweep 2, four points per thread and line: spectrum += sum_b (s_rec_b / den_rec + s_exc_b / den_exc)
+    if (tid < nf) {
+      // sweep-2 constants: exact form next to the centre, far-field series
+      //   s_r / (a + g_r) + s_e / (a + g_e) = (1/a) (c0 - (1/a) (c1 - (1/a) c2)) + O((g/a)^3),  a = |d|^2.5
+      FusedLine& L = fl[tid];
+      L.c0 = L.s_r + L.s_e;
+      L.c1 = L.s_r * L.g_r + L.s_e * L.g_e;
+      L.c2 = L.s_r * L.g_r * L.g_r + L.s_e * L.g_e * L.g_e;
+      const float gmax = L.g_r > L.g_e ? L.g_r : L.g_e;
+      L.d_far = exp2f(0.4f * log2f(BAYSAR_FAR_RATIO * gmax)) * 1.0001f;
+    }
+    __syncthreads();
+    // ---- sweep 2, four points per thread and line: spectrum += sum_b (s_rec_b / den_rec + s_exc_b / den_exc).
+    // Far-field points go two at a time through the packed FP32 pipe (fma.rn.f32x2): one issue slot per two FMAs.
+    float* sp = (MODE == 1) ? a.spec + n * a.split_pitch + a.split_pad : nullptr;
+    const f32x2 dhi2 = pack2(d_hi, d_hi), dlo2 = pack2(d_lo, d_lo);
     for (int jb = tid; jb < F; jb += 4 * NT) {
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      const float jf = (float)jb;
+      f32x2 v01 = pack2(0.f, 0.f), v23 = pack2(0.f, 0.f);
+      const f32x2 jf01 = pack2((float)jb, (float)(jb + NT)), jf23 = pack2((float)(jb + 2 * NT), (float)(jb + 3 * NT));
       for (int b = 0; b < nf; ++b) {
         const float4 cst = *reinterpret_cast<const float4*>(&fl[b].jc_f);
         const float4 ser = *reinterpret_cast<const float4*>(&fl[b].s_r);   // s_r, s_e, c0, c1
         const float2 far = *reinterpret_cast<const float2*>(&fl[b].c2);    // c2, d_far
+        const f32x2 mjc2 = pack2(-cst.x, -cst.x), r2 = pack2(cst.y, cst.y);
+        const f32x2 c0p = pack2(ser.z, ser.z), mc1p = pack2(-ser.w, -ser.w), c2p = pack2(far.x, far.x);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float kf = (jf + (float)(u * NT)) - cst.x;
-          const float d = fabsf(fmaf(kf, d_hi, fmaf(kf, d_lo, cst.y)));
-          if (d >= far.y) {
-            const float rs = rsqrt_approx(d);
-            const float rs2 = rs * rs;
-            const float ia = rs2 * rs2 * rs;
-            v[u] = fmaf(ia, fmaf(-ia, fmaf(-ia, far.x, ser.w), ser.z), v[u]);
+        for (int h = 0; h < 2; ++h) {
+          f32x2& v2 = h == 0 ? v01 : v23;
+          const f32x2 kf2 = add2(h == 0 ? jf01 : jf23, mjc2);
+          const f32x2 d2 = fma2(kf2, dhi2, fma2(kf2, dlo2, r2));
+          float dx, dy;
+          unpack2(d2, dx, dy);
+          dx = fabsf(dx); dy = fabsf(dy);
+          if (dx >= far.y && dy >= far.y) {
+            const f32x2 rs = pack2(rsqrt_approx(dx), rsqrt_approx(dy));
+            const f32x2 rs2 = mul2(rs, rs);
+            const f32x2 ia = mul2(mul2(rs2, rs2), rs);
+            v2 = fma2(ia, fma2(ia, fma2(ia, c2p, mc1p), c0p), v2);   // ia (c0 - ia (c1 - ia c2))
           } else {
-            const float a25 = d * d * sqrt_approx(d);
-            const float dr = a25 + cst.z, de = a25 + cst.w;
-            v[u] = fmaf(fmaf(ser.x, de, ser.y * dr), rcp_approx(dr * de), v[u]);
+            float vx, vy;
+            unpack2(v2, vx, vy);
+            {
+              const float a25 = dx * dx * sqrt_approx(dx);
+              const float dr = a25 + cst.z, de = a25 + cst.w;
+              vx = fmaf(fmaf(ser.x, de, ser.y * dr), rcp_approx(dr * de), vx);
+            }
+            {
+              const float a25 = dy * dy * sqrt_approx(dy);
+              const float dr = a25 + cst.z, de = a25 + cst.w;
+              vy = fmaf(fmaf(ser.x, de, ser.y * dr), rcp_approx(dr * de), vy);
+            }
+            v2 = pack2(vx, vy);
           }
         }
       }
+      float v[4];
+      unpack2(v01, v[0], v[1]);
+      unpack2(v23, v[2], v[3]);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (jb + u * NT < F) A_AT(jb + u * NT) += v[u];
+      for (int u = 0; u < 4; ++u) {
+        const int j = jb + u * NT;
+        if (j < F) {
+          const float val = A_AT(j) + v[u];
+          A_AT(j) = val;
+          if (final_pass) {  // pre-convolution area / minimum (spectrometers.py:256, :271) and MODE 1 hand-over
+            pre_f += (j == 0 || j == F - 1) ? 0.5f * val : val;
+            mn = val < mn ? val : mn;
+            if (!(val - val == 0.f)) bad = 1;
+            if (MODE == 1) sp[j] = val;
+          }
+        }
+      }
     }
+    if (final_pass) pre_done = true;
     __syncthreads();  // the constants may be overwritten by the next group
     nf = 0;
   };
@@ -487,11 +531,11 @@ __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kerne
             if (jR < F - 1) jR += (F - 1 - jR) % BAYSAR_EM_STRIDE;
             L.jL = jL; L.jR = jR;
           }
-          if (++nf == BAYSAR_MAX_FUSED_LINES) flush_fused();
+          if (++nf == BAYSAR_MAX_FUSED_LINES) flush_fused(false);
           continue;
         }
       }
-      if (nf > 0) flush_fused();  // keep the (float) summation order of the lines deterministic
+      if (nf > 0) flush_fused(false);  // keep the (float) summation order of the lines deterministic
       // tap window |z| <= Z_CUT
       if (tid == 0) { iscr[0] = KD; iscr[1] = -1; }
       __syncthreads();
@@ -601,18 +645,17 @@ __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kerne
       __syncthreads();
     }
   }
-  if (nf > 0) flush_fused();
+  if (nf > 0) flush_fused(true);
   __syncthreads();
 
   // ================= pre-convolution area and minimum (spectrometers.py:256, :271) ===============================
-  float pre_f = 0.f;
-  float mn = 3.402823466e38f;
-  int bad = 0;
-  for (int j = tid; j < F; j += NT) {
-    float v = A_AT(j);
-    pre_f += (j == 0 || j == F - 1) ? 0.5f * v : v;   // <= 40 terms per thread in float32, float64 across threads
-    mn = v < mn ? v : mn;
-    if (!(v - v == 0.f)) bad = 1;
+  if (!pre_done) {
+    for (int j = tid; j < F; j += NT) {
+      float v = A_AT(j);
+      pre_f += (j == 0 || j == F - 1) ? 0.5f * v : v;   // <= 40 terms per thread in float32, float64 across threads
+      mn = v < mn ? v : mn;
+      if (!(v - v == 0.f)) bad = 1;
+    }
   }
   double pre_s = (double)pre_f;
   if (a.fine_pre) {
@@ -695,18 +738,11 @@ __global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kerne
   if (MODE == 1) {
     // ================= hand the spectrum to the tensor-core contraction =========================================
     __syncthreads();
-    float* hi = a.split_hi + n * a.split_pitch + a.split_pad;
-    float* lo = a.split_lo + n * a.split_pitch + a.split_pad;
+    float* sp = a.spec + n * a.split_pitch + a.split_pad;
     // the workspace is shared by chords with different paddings: (re)write this row's zero padding as well
-    for (int j = tid - a.split_pad; j < 0; j += NT) { hi[j] = 0.f; lo[j] = 0.f; }
-    for (int64_t j = F + tid; j < a.split_pitch - a.split_pad; j += NT) { hi[j] = 0.f; lo[j] = 0.f; }
-    for (int j = tid; j < F; j += NT) {
-      const float v = A_AT(j);
-      float h, l;
-      split_tf32_pair(v, h, l);
-      hi[j] = h;
-      lo[j] = l;
-    }
+    for (int j = tid - a.split_pad; j < 0; j += NT) sp[j] = 0.f;
+    for (int64_t j = F + tid; j < a.split_pitch - a.split_pad; j += NT) sp[j] = 0.f;
+    if (!pre_done) for (int j = tid; j < F; j += NT) sp[j] = A_AT(j);
     if (tid == 0) {
       double* ax = a.aux + n * BAYSAR_AUX_STRIDE;
       ax[0] = pre; ax[1] = (double)mn; ax[2] = edge64[0]; ax[3] = edge64[1]; ax[4] = edge64[2]; ax[5] = edge64[3];

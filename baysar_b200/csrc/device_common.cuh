@@ -64,6 +64,23 @@ BAYSAR_DEV float sqrt_approx(float x) { return sqrtf(x); }
 BAYSAR_DEV float rsqrt_approx(float x) { return 1.0f / sqrtf(x); }
 #endif
 
+// Packed FP32 pairs (fma.rn.f32x2 and friends, sm_100+): two FMAs per lane and issue slot
+#ifndef BAYSAR_CPU_EMU
+struct f32x2 { unsigned long long v; };
+BAYSAR_DEV f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+BAYSAR_DEV void unpack2(f32x2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+BAYSAR_DEV f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+BAYSAR_DEV f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+BAYSAR_DEV f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+#else
+struct f32x2 { float lo, hi; };
+BAYSAR_DEV f32x2 pack2(float lo, float hi) { return f32x2{lo, hi}; }
+BAYSAR_DEV void unpack2(f32x2 a, float& lo, float& hi) { lo = a.lo; hi = a.hi; }
+BAYSAR_DEV f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { return f32x2{fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)}; }
+BAYSAR_DEV f32x2 mul2(f32x2 a, f32x2 b) { return f32x2{a.lo * b.lo, a.hi * b.hi}; }
+BAYSAR_DEV f32x2 add2(f32x2 a, f32x2 b) { return f32x2{a.lo + b.lo, a.hi + b.hi}; }
+#endif
+
 // np.clip(v, lo, None): NaN propagates (fmax would swallow it)
 BAYSAR_DEV double clip_lo(double v, double lo) { return v < lo ? lo : v; }
 

@@ -5,46 +5,54 @@
 //
 //     C[theta, j] = sum_k' S[theta, k'] * T[k', j],     T[k', j] = w[j + o - k']   (banded Toeplitz, o = (K_I - 1) / 2)
 //
-// * M = 128 thetas (one TMEM lane each), N = 128 fine-grid outputs per CTA, K walks the band in blocks of 32.
-// * A operand: the pre-convolution spectra, split into two TF32 terms (hi, lo) by the spectral kernel and stored
-//   zero-padded in HBM/L2 as [N][pitch]; tiles are copied global -> shared with 16-byte cp.async into the canonical
-//   K-major SWIZZLE_128B layout (8 rows x 128 B atoms, 16-byte chunk index XOR row-in-atom).
-// * B operand: the Toeplitz tile depends only on (j0 - k0), so it is GENERATED in shared memory from the taps (kept
-//   reversed, TF32-split, in four element-shifted copies so that every 4-tap chunk is one aligned 16-byte load);
-//   streaming it from L2 as well would double the operand traffic and make the kernel L2-bound.
+// * M = 128 thetas (one TMEM lane each), N = 128 fine-grid outputs per tile, K walks the band in blocks of 32.
+// * Persistent: one CTA per SM loops over (theta block, output tile) pairs; neighbouring CTAs work on neighbouring
+//   output tiles of the same thetas, so the overlapping parts of their k-ranges are served by L2.
+// * B operand — the Toeplitz tile depends only on (j0 - k0): ALL k-blocks of the band are windows of ONE tall
+//   "master" tile (128 + 32 (n_kb - 1) rows of 32 taps, K-major SWIZZLE_128B, TF32 hi and lo parts), which every
+//   CTA builds once in shared memory (<= 221 KB).  The B descriptor of k-block kb is the master's base plus
+//   4096 (n_kb - 1 - kb) bytes; nothing is generated or copied per k-block.
+// * A operand — the pre-convolution spectra, plain FP32 rows [theta][pitch] in HBM/L2 (zero padded).  Producer
+//   threads own one theta row each: they load 64 bytes per k-block (four k-blocks in flight in registers), split the
+//   values into two TF32 terms (hi, lo) and write them to TENSOR MEMORY with tcgen05.st; the MMAs take A from TMEM
+//   (the .ts form).  Shared memory carries no per-k-block traffic at all: it holds the master tile only, and
+//   the tensor pipe's operand reads are the only shared-memory reads in the main loop.
 // * 3xTF32: hi*hi accumulates in one FP32 TMEM tile, hi*lo + lo*hi in a second one; the epilogue adds them.
 //   TMEM accumulation truncates (measured: signed error mean -2.5e-6, never positive, with one accumulator and
 //   k-blocks in natural order), so (a) the 2^-11-sized cross terms get their own accumulator and (b) k-blocks are
 //   visited from the edges of the band towards its centre: the big contributions arrive last and most roundings
 //   happen while the accumulator is still small.
-// * Warp-specialised pipeline, 3 shared-memory stages: warps 0-7 produce (cp.async A tiles, generate B tiles) and
-//   later run the epilogue; warp 8 issues the MMAs.  full[s] (producers -> issuer) and empty[s] (tcgen05.commit ->
-//   producers) mbarriers; no block-wide barrier inside the k loop.
+// * TMEM map (512 columns): [0,128) accumulator hi*hi, [128,256) accumulator cross terms, [256,512) four A stages of
+//   32 hi + 32 lo columns.
+// * Warp roles: warps 0-7 produce A (warp w: TMEM lanes 32 (w % 4).., k columns 16 (w / 4)..), warps 8-11 run the
+//   epilogue (so the producers already fill the A stages of the next tile while the accumulators drain), warp 12
+//   issues the MMAs.  full[s] (producers -> issuer), empty[s] (tcgen05.commit -> producers), acc_full (commit ->
+//   epilogue), acc_free (epilogue -> issuer) mbarriers; no block-wide barrier after the prologue.
 // * Epilogue: tcgen05.ld (32 lanes x 32 columns), clip at the per-theta pre-convolution minimum, trapz partial per
-//   (theta, tile) in float64 (deterministic: summed in order by the pixel kernel), FP32 store.
+//   (theta, tile) in float64 (deterministic: summed in tile order by the pixel kernel), FP32 store.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace ifc {
 
-constexpr int TILE_M = 128;   // thetas per CTA
-constexpr int TILE_N = 128;   // fine-grid outputs per CTA
+constexpr int TILE_M = 128;   // thetas per tile
+constexpr int TILE_N = 128;   // fine-grid outputs per tile
 constexpr int TILE_K = 32;    // TF32 elements per k-block = one 128-byte swizzle row
-constexpr int STAGES = 3;
-constexpr int PRODUCER_THREADS = 256;
-constexpr int THREADS = PRODUCER_THREADS + 32;              // + one MMA-issuing warp
-constexpr int OPERAND_BYTES = TILE_M * TILE_K * 4;          // 16 KB per operand per stage
-constexpr int STAGE_BYTES = 4 * OPERAND_BYTES;              // A_hi, A_lo, B_hi, B_lo
-constexpr int TMEM_COLS = 2 * TILE_N;                       // two FP32 accumulators
+constexpr int A_STAGES = 4;
+constexpr int PRODUCER_WARPS = 8, EPILOGUE_WARPS = 4;
+constexpr int THREADS = (PRODUCER_WARPS + EPILOGUE_WARPS + 1) * 32;
+constexpr int TMEM_COLS = 512;
+constexpr int TMEM_ACC1 = TILE_N;          // cross-term accumulator
+constexpr int TMEM_A = 2 * TILE_N;         // first A stage
+constexpr int MAX_KB = 24;                 // master tile <= 864 rows x 128 B x 2 = 221 184 bytes
 
 struct Params {
-  const float* s_hi;      // [n_rows][pitch]  TF32-rounded spectra, zero padded: column pad_left + k'
-  const float* s_lo;      // [n_rows][pitch]  TF32-rounded remainder
+  const float* s;         // [n_rows][pitch]  FP32 spectra, zero padded: column pad_left + k'
   int64_t pitch;          // floats per row (multiple of 32)
   int pad_left;           // multiple of 32
   int F;                  // valid outputs per row
-  int n_rows;             // multiple of 128 (workspace rows beyond the batch hold stale but finite data)
+  int n_row_blocks;       // blocks of 128 rows (workspace rows beyond the batch hold stale but finite data)
   int m_lo, m_hi;         // k-blocks k0 = j0 + 32 * m for m in [m_lo, m_hi]
   const float* taps_rev;  // [2][4][taps_len]: rev[i] = w[x_max - i], x_max = 127 + o - 32 m_lo (zero outside the tap
                           // window), TF32 hi then lo, each in 4 element-shifted copies copy_s[i] = rev[i + s]
@@ -97,13 +105,14 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem]: the A-from-tensor-memory form (cute::SM100_MMA_TF32_TS)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate));
 }
 
 // byte offset of (row, 16-byte chunk) inside a K-major SWIZZLE_128B operand tile whose base is 1024-byte aligned
@@ -126,176 +135,224 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
 }
 
+// 32 lanes x 16 columns, registers -> tensor memory
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
+// Split an FP32 value into two TF32 terms (round-to-nearest): v ~ hi + lo with |v - hi - lo| <= 2^-22 |v|.
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(v - __uint_as_float(hi)));
+}
+
+inline int master_rows(int n_kb) { return TILE_N + TILE_K * (n_kb - 1); }
+inline size_t smem_bytes(int n_kb) {
+  return (size_t)2 * master_rows(n_kb) * 128 + (2 * A_STAGES + 2) * sizeof(uint64_t) + 16 + 1024;  // + alignment slack
+}
+
 __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // carve: [STAGES][A_hi | A_lo | B_hi | B_lo] (1024-byte aligned), then taps, then barriers
-  unsigned char* stage_base = smem_raw;
-  float* taps = reinterpret_cast<float*>(smem_raw + STAGES * STAGE_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(taps + 8 * p.taps_len);
-  uint64_t* empty = full + STAGES;
-  uint64_t* all_done = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
+  extern __shared__ unsigned char smem_dyn[];
+  // carve (1024-byte aligned): master_hi | master_lo | barriers | TMEM slot
+  unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  const int n_kb = p.m_hi - p.m_lo + 1;
+  const int R = TILE_N + TILE_K * (n_kb - 1);
+  unsigned char* master_hi = smem_raw;
+  unsigned char* master_lo = smem_raw + (size_t)R * 128;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)2 * R * 128);
+  uint64_t* empty = full + A_STAGES;
+  uint64_t* acc_full = empty + A_STAGES;
+  uint64_t* acc_free = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int j0 = blockIdx.x * TILE_N;
-  const int row0 = blockIdx.y * TILE_M;
-  const int n_kb = p.m_hi - p.m_lo + 1;
+  const int64_t total_tiles = (int64_t)p.n_row_blocks * p.n_tiles;
+  const int64_t my_tiles = total_tiles > blockIdx.x ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  for (int i = tid; i < 8 * p.taps_len; i += THREADS) taps[i] = p.taps_rev[i];
+  // ---- prologue: master Toeplitz tile.  Row rho, chunk q holds the taps rev[base - rho + 4 q + (0..3)]
+  {
+    const int base = 127 + TILE_K * (n_kb - 1);
+    for (int c = tid; c < R * 8; c += THREADS) {
+      const int rho = c >> 3, q = c & 7;
+      const int idx = base - rho + 4 * q;
+      const int sh = idx & 3;
+      const float4 hi = *reinterpret_cast<const float4*>(p.taps_rev + (size_t)sh * p.taps_len + (idx - sh));
+      const float4 lo = *reinterpret_cast<const float4*>(p.taps_rev + (size_t)(4 + sh) * p.taps_len + (idx - sh));
+      const uint32_t off = swz(rho, q);
+      *reinterpret_cast<float4*>(master_hi + off) = hi;
+      *reinterpret_cast<float4*>(master_lo + off) = lo;
+    }
+  }
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 2 * PRODUCER_THREADS); mbar_init(&empty[s], 1); }
-    mbar_init(all_done, 1);
+    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&full[s], PRODUCER_WARPS); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_free, EPILOGUE_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
-  if (warp == 8) {
+  if (warp == PRODUCER_WARPS + EPILOGUE_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // master tile (generic proxy) -> tensor-core proxy
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_d = *tmem_slot;
 
-  if (warp < 8) {
-    // ===================== producers =====================
-    for (int i = 0; i < n_kb; ++i) {
-      const int s = i % STAGES;
-      if (i >= STAGES) mbar_wait(&empty[s], (uint32_t)(((i / STAGES) - 1) & 1));  // MMAs of the previous user are done
+  if (warp < PRODUCER_WARPS) {
+    // ===================== A producers =====================
+    const int quad = warp & 3, khalf = warp >> 2;
+    const int row_in_tile = quad * 32 + lane;
+    const int64_t iters = my_tiles * n_kb;
+    // source of this thread's 16 floats of global k-block iteration g (tiles of this CTA back to back)
+    auto src = [&](int64_t g) -> const float4* {
+      const int64_t q = g / n_kb;
+      const int i = (int)(g - q * n_kb);
+      const int64_t t = blockIdx.x + q * gridDim.x;
+      const int rb = (int)(t / p.n_tiles), nt = (int)(t - (int64_t)rb * p.n_tiles);
       const int kb = kb_order(i, n_kb);
-      unsigned char* st = stage_base + s * STAGE_BYTES;
-      const int64_t col0 = (int64_t)p.pad_left + j0 + 32 * (p.m_lo + kb);
-      // ---- A: 128 rows x 8 chunks for hi and lo, 16-byte cp.async, coalesced along the row
+      return reinterpret_cast<const float4*>(p.s + (int64_t)(rb * TILE_M + row_in_tile) * p.pitch + p.pad_left +
+                                             nt * TILE_N + TILE_K * (p.m_lo + kb) + 16 * khalf);
+    };
+    float4 buf[A_STAGES][4];
 #pragma unroll
-      for (int r = 0; r < (TILE_M * 8) / PRODUCER_THREADS; ++r) {
-        const int c = tid + r * PRODUCER_THREADS;
-        const int row = c >> 3, chunk = c & 7;
-        const int64_t g = (int64_t)(row0 + row) * p.pitch + col0 + chunk * 4;
-        const uint32_t off = swz(row, chunk);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(st + off)), "l"(p.s_hi + g) : "memory");
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(st + OPERAND_BYTES + off)), "l"(p.s_lo + g) : "memory");
-      }
-      // ---- B: Toeplitz tile, row n (output j0 + n), chunk q -> taps w[x], x = n - kk + o - 32 m, kk = 4q..4q+3.
-      // In the reversed array the four taps are ascending: rev index = x_max - x = 127 - n + 4q + 32 kb + e.
+    for (int d = 0; d < A_STAGES; ++d) {
+      if (d < iters) {
+        const float4* a = src(d);
 #pragma unroll
-      for (int r = 0; r < (TILE_N * 8) / PRODUCER_THREADS; ++r) {
-        const int c = tid + r * PRODUCER_THREADS;
-        const int n = c >> 3, q = c & 7;
-        const int idx = 127 - n + 4 * q + 32 * kb;
-        const int sh = idx & 3;
-        const float4 hi = *reinterpret_cast<const float4*>(taps + sh * p.taps_len + (idx - sh));
-        const float4 lo = *reinterpret_cast<const float4*>(taps + (4 + sh) * p.taps_len + (idx - sh));
-        const uint32_t off = swz(n, q);
-        *reinterpret_cast<float4*>(st + 2 * OPERAND_BYTES + off) = hi;
-        *reinterpret_cast<float4*>(st + 3 * OPERAND_BYTES + off) = lo;
+        for (int c = 0; c < 4; ++c) buf[d][c] = __ldg(a + c);
       }
-      // two arrivals per thread on full[s]: one fires when this thread's cp.async copies have landed, the other is a
-      // plain (release) arrive that publishes its st.shared writes of the B tile
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[s])) : "memory");
-      mbar_arrive(&full[s]);
+    }
+    const uint32_t lane_base = tmem_d + ((uint32_t)(quad * 32) << 16) + TMEM_A + 16 * khalf;
+    for (int64_t g0 = 0; g0 < iters; g0 += A_STAGES) {
+#pragma unroll
+      for (int d = 0; d < A_STAGES; ++d) {
+        const int64_t g = g0 + d;
+        if (g < iters) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            split_tf32(buf[d][c].x, hi[4 * c + 0], lo[4 * c + 0]);
+            split_tf32(buf[d][c].y, hi[4 * c + 1], lo[4 * c + 1]);
+            split_tf32(buf[d][c].z, hi[4 * c + 2], lo[4 * c + 2]);
+            split_tf32(buf[d][c].w, hi[4 * c + 3], lo[4 * c + 3]);
+          }
+          if (g + A_STAGES < iters) {  // refill this register stage: four k-blocks ahead
+            const float4* a = src(g + A_STAGES);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) buf[d][c] = __ldg(a + c);
+          }
+          if (g >= A_STAGES) {  // stage d: the MMAs of its previous user are done
+            mbar_wait(&empty[d], (uint32_t)(((g / A_STAGES) - 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;");
+          }
+          tmem_st16(lane_base + 64 * d, hi);
+          tmem_st16(lane_base + 64 * d + 32, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[d]);
+        }
+      }
+    }
+  } else if (warp < PRODUCER_WARPS + EPILOGUE_WARPS) {
+    // ===================== epilogue (warps 8-11): TMEM -> registers -> add accumulators, clip, trapz -> global ====
+    const int quad = warp & 3;
+    for (int64_t q = 0; q < my_tiles; ++q) {
+      const int64_t t = blockIdx.x + q * gridDim.x;
+      const int rb = (int)(t / p.n_tiles), nt = (int)(t - (int64_t)rb * p.n_tiles);
+      const int j0 = nt * TILE_N;
+      const int row = rb * TILE_M + quad * 32 + lane;
+      float clip = -3.402823466e38f;
+      if (p.row_min) clip = p.row_min[row];
+      else if (p.aux && row < p.aux_rows) clip = (float)p.aux[(int64_t)row * 8 + 1];
+      float* orow = p.out + (int64_t)row * p.out_pitch;
+      double part = 0.0;
+      mbar_wait(acc_full, (uint32_t)(q & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll 1
+      for (int c0 = 0; c0 < TILE_N; c0 += 32) {
+        uint32_t v[32], u[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
+        tmem_ld32(taddr, v);
+        tmem_ld32(taddr + TMEM_ACC1, u);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c0 + 32 == TILE_N) {  // accumulators are in registers: the next tile's MMAs may start
+          asm volatile("tcgen05.fence::before_thread_sync;");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_free);
+        }
+#pragma unroll
+        for (int e4 = 0; e4 < 32; e4 += 4) {
+          float f[4];
+          float psum = 0.f;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = __uint_as_float(v[e4 + e]) + __uint_as_float(u[e4 + e]);
+            x = x < clip ? clip : x;
+            f[e] = x;
+            const int j = j0 + c0 + e4 + e;
+            if (j < p.F) {
+              if (j == 0 || j == p.F - 1) part += 0.5 * (double)x; else psum += x;
+            }
+          }
+          part += (double)psum;
+          if (j0 + c0 + e4 < p.F) *reinterpret_cast<float4*>(orow + j0 + c0 + e4) = make_float4(f[0], f[1], f[2], f[3]);
+        }
+      }
+      if (p.trapz_part) p.trapz_part[(int64_t)row * p.n_tiles + nt] = part;
     }
   } else {
-    // ===================== MMA issuer (warp 8) =====================
-    // B_hi and B_lo sit back to back in a stage, i.e. they form ONE 256-row K-major operand: a single N = 256 MMA
-    // computes A_hi*B_hi into accumulator 0 (columns 0-127) and A_hi*B_lo into accumulator 1 (columns 128-255) while
-    // reading A_hi from shared memory once; A_lo*B_hi then adds into accumulator 1 with an N = 128 MMA.
-    const uint32_t idesc256 = make_idesc(2 * TILE_N), idesc128 = make_idesc(TILE_N);
-    for (int i = 0; i < n_kb; ++i) {
-      const int s = i % STAGES;
-      mbar_wait(&full[s], (uint32_t)((i / STAGES) & 1));
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // producers' generic-proxy writes -> tensor-core proxy
-      asm volatile("tcgen05.fence::after_thread_sync;");
-      if (lane == 0) {
-        const uint32_t a_hi = smem_u32(stage_base + s * STAGE_BYTES);
-        const uint64_t d_ahi = make_desc(a_hi), d_alo = make_desc(a_hi + OPERAND_BYTES);
-        const uint64_t d_bhi = make_desc(a_hi + 2 * OPERAND_BYTES);
-#pragma unroll
-        for (int ks = 0; ks < TILE_K / 8; ++ks) {
-          const uint64_t adv = (uint64_t)((ks * 8 * 4) >> 4);  // 32 bytes per k-step inside the 128-byte swizzle row
-          mma_tf32(tmem_d, d_ahi + adv, d_bhi + adv, idesc256, (i | ks) ? 1u : 0u);
-          mma_tf32(tmem_d + TILE_N, d_alo + adv, d_bhi + adv, idesc128, 1u);
-        }
-        // frees this stage when the MMAs above (and all earlier ones) have completed
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
-        if (i == n_kb - 1)
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(all_done)) : "memory");
+    // ===================== MMA issuer (warp 12) =====================
+    const uint32_t idesc = make_idesc(TILE_N);
+    const uint32_t mh = smem_u32(master_hi), ml = smem_u32(master_lo);
+    int64_t g = 0;
+    for (int64_t q = 0; q < my_tiles; ++q) {
+      if (q > 0) {  // the epilogue has read the accumulators of the previous tile
+        mbar_wait(acc_free, (uint32_t)((q - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;");
       }
-      __syncwarp();
-    }
-  }
-
-  // ---- epilogue (warps 0-7): TMEM -> registers -> add accumulators, clip, trapz partial -> global
-  if (warp < 8) {
-    mbar_wait(all_done, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int chalf = warp >> 2;               // columns [64 * chalf, 64 * chalf + 64)
-    const int row = row0 + quad * 32 + lane;
-    float clip = -3.402823466e38f;
-    if (p.row_min) clip = p.row_min[row];
-    else if (p.aux && row < p.aux_rows) clip = (float)p.aux[(int64_t)row * 8 + 1];
-    double part = 0.0;
-    float* orow = p.out + (int64_t)row * p.out_pitch;
-#pragma unroll 1
-    for (int c0 = 64 * chalf; c0 < 64 * chalf + 64; c0 += 32) {
-      uint32_t v[32], u[32];
-      const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
-      tmem_ld32(taddr, v);
-      tmem_ld32(taddr + TILE_N, u);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int i = 0; i < n_kb; ++i, ++g) {
+        const int s = (int)(g % A_STAGES);
+        mbar_wait(&full[s], (uint32_t)((g / A_STAGES) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        if (lane == 0) {
+          const int kb = kb_order(i, n_kb);
+          const uint32_t boff = (uint32_t)(4096 * (n_kb - 1 - kb));
+          const uint64_t d_bhi = make_desc(mh + boff), d_blo = make_desc(ml + boff);
+          const uint32_t a_hi = tmem_d + TMEM_A + 64 * s, a_lo = a_hi + 32;
 #pragma unroll
-      for (int q = 0; q < 32; q += 4) {
-        float f[4];
-        float psum = 0.f;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float x = __uint_as_float(v[q + e]) + __uint_as_float(u[q + e]);
-          x = x < clip ? clip : x;
-          f[e] = x;
-          const int j = j0 + c0 + q + e;
-          if (j < p.F) {
-            if (j == 0 || j == p.F - 1) part += 0.5 * (double)x; else psum += x;
+          for (int ks = 0; ks < TILE_K / 8; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * 8 * 4) >> 4);  // 32 bytes per k-step inside the 128-byte swizzle row
+            mma_tf32_ts(tmem_d, a_hi + 8 * ks, d_bhi + adv, idesc, (i | ks) ? 1u : 0u);
+            mma_tf32_ts(tmem_d + TMEM_ACC1, a_hi + 8 * ks, d_blo + adv, idesc, (i | ks) ? 1u : 0u);
+            mma_tf32_ts(tmem_d + TMEM_ACC1, a_lo + 8 * ks, d_bhi + adv, idesc, 1u);
           }
+          // frees this A stage when the MMAs above (and all earlier ones) have completed
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+          if (i == n_kb - 1)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(acc_full)) : "memory");
         }
-        part += (double)psum;
-        if (j0 + c0 + q < p.F) *reinterpret_cast<float4*>(orow + j0 + c0 + q) = make_float4(f[0], f[1], f[2], f[3]);
+        __syncwarp();
       }
-    }
-    if (p.trapz_part) {
-      // the two column halves of a row live in warps w and w + 4: combine through shared memory (taps are dead now)
-      double* xch = reinterpret_cast<double*>(taps);
-      if (chalf == 1) xch[quad * 32 + lane] = part;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (chalf == 0) p.trapz_part[(int64_t)row * p.n_tiles + blockIdx.x] = part + xch[quad * 32 + lane];
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS));
+  if (warp == PRODUCER_WARPS + EPILOGUE_WARPS)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS));
 }
 
-// Split FP32 values into two TF32 terms (round-to-nearest): v ~ hi + lo with |v - hi - lo| <= 2^-22 |v|.
-__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-  hi = __uint_as_float(h);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
-  lo = __uint_as_float(l);
-}
-
-// test / utility: rows of FP32 spectra [n][F] -> padded TF32-split rows
-__global__ void split_rows_kernel(const float* s, int64_t n, int F, float* hi, float* lo, int64_t pitch, int pad_left) {
+// test / utility: rows of FP32 spectra [n][F] -> zero-padded rows [n][pitch]
+__global__ void pad_rows_kernel(const float* s, int64_t n, int F, float* out, int64_t pitch, int pad_left) {
   const int64_t r = blockIdx.y;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < F; j += gridDim.x * blockDim.x) {
-    float h, l;
-    split_tf32(s[r * F + j], h, l);
-    hi[r * pitch + pad_left + j] = h;
-    lo[r * pitch + pad_left + j] = l;
-  }
-}
-
-inline size_t smem_bytes(int taps_len) {
-  return (size_t)STAGES * STAGE_BYTES + (size_t)8 * taps_len * sizeof(float) + (2 * STAGES + 1) * sizeof(uint64_t) + 16;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < F; j += gridDim.x * blockDim.x) out[r * pitch + pad_left + j] = s[r * F + j];
 }
 
 }  // namespace ifc

@@ -47,18 +47,17 @@ extern "C" int emu_eval_split(const unsigned char* blob, const double* theta, lo
     ChordSmem s = chord_smem_layout(F, ch[CH_HALO], ch[CH_TAPS_MAX], kd_max);
     const int pad = 64, n_tiles = (F + 127) / 128;
     const int64_t pitch = pad + F + 96, cpitch = (int64_t)n_tiles * 128;
-    std::vector<float> hi(n * pitch, 7.f), lo(n * pitch, 7.f), conv(n * cpitch, 0.f);
+    std::vector<float> spec(n * pitch, 7.f), conv(n * cpitch, 0.f);
     std::vector<double> aux(n * BAYSAR_AUX_STRIDE), part(n * n_tiles, 0.0);
     ChordArgs ca{};
     ca.theta = theta; ca.n = n; ca.chord_begin = c; ca.lines = lines; ca.components = comps; ca.status = status;
-    ca.split_hi = hi.data(); ca.split_lo = lo.data(); ca.split_pitch = pitch; ca.split_pad = pad; ca.aux = aux.data();
+    ca.spec = spec.data(); ca.split_pitch = pitch; ca.split_pad = pad; ca.aux = aux.data();
     EmuDim3 gc;
     gc.x = (unsigned)n; gc.y = 1;
     emu_launch(chord_stage_kernel<256, 1>, gc, 256u, s.total, m, ca);
     const double* w = m.ifn + ch[CH_IF_OFF];
     for (long r = 0; r < n; ++r) {
-      const float* h = hi.data() + r * pitch + pad;
-      const float* l = lo.data() + r * pitch + pad;
+      const float* sp = spec.data() + r * pitch + pad;
       const float clip = (float)aux[r * BAYSAR_AUX_STRIDE + 1];
       for (int j = 0; j < F; ++j) {
         float acc0 = 0.f, acc1 = 0.f;
@@ -66,8 +65,10 @@ extern "C" int emu_eval_split(const unsigned char* blob, const double* theta, lo
           int kp = j + o - k;
           if (kp < -pad || kp >= F + 96) continue;
           float wh = emu_tf32((float)w[k]), wl = emu_tf32((float)w[k] - wh);
-          acc0 += h[kp] * wh;
-          acc1 += h[kp] * wl + l[kp] * wh;
+          float h, l;
+          split_tf32_pair(sp[kp], h, l);  // what the contraction's producer threads do before tcgen05.st
+          acc0 += h * wh;
+          acc1 += h * wl + l * wh;
         }
         float v = acc0 + acc1;
         v = v < clip ? clip : v;
