@@ -32,6 +32,10 @@ struct IfcPlan {
   int m_lo = 0, m_hi = 0, pad_left = 0, n_tiles = 0, taps_len = 0;
   int64_t pitch = 0, out_pitch = 0;
   std::vector<float> taps_rev;  // [2][4][taps_len]
+  // compact output for a static wavelength map: needed-column bit mask / running count per 32 columns
+  std::vector<uint32_t> cmask;
+  std::vector<int> cbase;
+  int64_t c_pitch = 0;
 };
 
 static float tf32_round(float v) {  // round to nearest, ties away from zero, 10-bit mantissa (cvt.rna.tf32.f32)
@@ -69,6 +73,10 @@ struct baysar_model {
   // tensor-core path (if_contract.cuh): per chord plan (empty taps_rev = chord stays on the fused kernel)
   std::vector<IfcPlan> ifc;
   std::vector<float*> ifc_taps_dev;
+  std::vector<uint32_t*> ifc_cmask_dev;
+  std::vector<int*> ifc_cbase_dev;
+  float* conv_c = nullptr;
+  int64_t conv_c_pitch_max = 0;
   bool any_ifc = false;
   int64_t ifc_rows = 0;              // rows of the split / conv workspaces (multiple of 128)
   int64_t ifc_budget_bytes = (int64_t)24 << 30;  // HBM budget of those workspaces (BAYSAR_IFC_BUDGET_MB at create)
@@ -224,10 +232,12 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
   const int L = (int)m->I[I_L];
   const size_t per_warp = los_smem_per_warp(L, (int)m->I[I_N_PARAMS]);
   if (per_warp > 200 * 1024) return fail("line-of-sight grid too long for the shared-memory LOS stage");
+  static const int minb = getenv("BAYSAR_LOS_MINB") ? atoi(getenv("BAYSAR_LOS_MINB")) : 4;  // register cap experiment
   if (4 * per_warp <= 200 * 1024) {
     size_t smem = 4 * per_warp;
-    CUDA_OK(cudaFuncSetAttribute(los_stage_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    los_stage_kernel<4><<<(unsigned)((n + 3) / 4), 128, smem, stream>>>(m->dev, a);
+    auto kern = minb >= 6 ? los_stage_kernel<4, 6> : (minb == 5 ? los_stage_kernel<4, 5> : los_stage_kernel<4, 4>);
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)((n + 3) / 4), 128, smem, stream>>>(m->dev, a);
   } else {
     size_t smem = per_warp;
     CUDA_OK(cudaFuncSetAttribute(los_stage_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -241,16 +251,17 @@ int ensure_ifc_workspace(baysar_model* m, int64_t n) {
   // rows handled per pass of the tensor-core path: bounded so that the split / convolved spectra stay within a
   // fixed HBM budget (8 bytes of operands + 4 bytes of output per fine-grid point and row)
   const int64_t budget = m->ifc_budget_bytes;
-  const int64_t per_row = 4 * (m->split_pitch_max + m->conv_pitch_max) + 8 * m->tiles_max;
+  const int64_t per_row = 4 * (m->split_pitch_max + m->conv_pitch_max + m->conv_c_pitch_max) + 8 * m->tiles_max;
   int64_t rows = (n + ifc::TILE_M - 1) / ifc::TILE_M * ifc::TILE_M;
   int64_t max_rows = budget / per_row / ifc::TILE_M * ifc::TILE_M;
   if (max_rows < ifc::TILE_M) max_rows = ifc::TILE_M;
   if (rows > max_rows) rows = max_rows;
   if (rows <= m->ifc_rows) return 0;
-  cudaFree(m->spec); cudaFree(m->conv); cudaFree(m->trapz_part); cudaFree(m->aux);
-  m->spec = m->conv = nullptr; m->trapz_part = m->aux = nullptr; m->ifc_rows = 0;
+  cudaFree(m->spec); cudaFree(m->conv); cudaFree(m->conv_c); cudaFree(m->trapz_part); cudaFree(m->aux);
+  m->spec = m->conv = m->conv_c = nullptr; m->trapz_part = m->aux = nullptr; m->ifc_rows = 0;
   CUDA_OK(cudaMalloc(&m->spec, sizeof(float) * rows * m->split_pitch_max));
   CUDA_OK(cudaMalloc(&m->conv, sizeof(float) * rows * m->conv_pitch_max));
+  if (m->conv_c_pitch_max > 0) CUDA_OK(cudaMalloc(&m->conv_c, sizeof(float) * rows * m->conv_c_pitch_max));
   CUDA_OK(cudaMalloc(&m->trapz_part, sizeof(double) * rows * m->tiles_max));
   CUDA_OK(cudaMalloc(&m->aux, sizeof(double) * rows * BAYSAR_AUX_STRIDE));
   // rows past the end of a batch are multiplied too (M = 128 granularity): keep them finite
@@ -331,16 +342,23 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
       p.n_row_blocks = (int)(rows128 / ifc::TILE_M); p.m_lo = pl.m_lo; p.m_hi = pl.m_hi; p.taps_rev = m->ifc_taps_dev[c];
       p.taps_len = pl.taps_len; p.row_min = nullptr; p.aux = m->aux; p.aux_rows = (int)rows;
       p.out = m->conv; p.out_pitch = pl.out_pitch; p.trapz_part = m->trapz_part; p.n_tiles = pl.n_tiles;
+      p.ring = ifc::ring_stages(pl.m_hi - pl.m_lo + 1);
+      // static wavelength map and no fine-grid diagnostics requested: store only the columns the pixel stage reads
+      const bool compact = m->ifc_cmask_dev[c] != nullptr && !fine_post;
+      if (compact) {
+        p.cmask = m->ifc_cmask_dev[c]; p.cbase = m->ifc_cbase_dev[c]; p.out_c = m->conv_c; p.out_c_pitch = pl.c_pitch;
+      }
       const size_t smem = ifc::smem_bytes(pl.m_hi - pl.m_lo + 1);
-      CUDA_OK(cudaFuncSetAttribute(ifc::if_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_OK(cudaFuncSetAttribute(ifc::if_contract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const int64_t tiles = (int64_t)p.n_row_blocks * pl.n_tiles;
       const unsigned ctas = (unsigned)(tiles < m->sm_count ? tiles : m->sm_count);  // persistent: one CTA per SM
-      ifc::if_contract_kernel<<<ctas, ifc::THREADS, smem, stream>>>(p);
+      ifc::if_contract_kernel<false><<<ctas, ifc::THREADS, smem, stream>>>(p);
       CUDA_OK(cudaGetLastError());
       if (mark(m, ST_CONTRACT, stream)) return 1;
       // K2c: area renormalisation, wavelength map, likelihood
       PixelArgs pa{};
       pa.theta = theta + r0 * n_params; pa.n = rows; pa.chord = c; pa.conv = m->conv; pa.conv_pitch = pl.out_pitch;
+      if (compact) { pa.conv = m->conv_c; pa.conv_pitch = pl.c_pitch; pa.cmask = p.cmask; pa.cbase = p.cbase; }
       pa.trapz_part = m->trapz_part; pa.n_tiles = pl.n_tiles; pa.aux = m->aux; pa.components = comps + r0 * ncols;
       pa.spectra = spectra ? spectra + r0 * P : nullptr; pa.fine_post = fine_post ? fine_post + r0 * F : nullptr;
       pa.status = status + r0;
@@ -453,6 +471,9 @@ int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar
   if (env_budget) m->ifc_budget_bytes = (int64_t)atoll(env_budget) << 20;
   m->ifc.resize(n_chords);
   m->ifc_taps_dev.assign(n_chords, nullptr);
+  m->ifc_cmask_dev.assign(n_chords, nullptr);
+  m->ifc_cbase_dev.assign(n_chords, nullptr);
+  const int* pix_idx_host = static_cast<const int*>(host.ptr(SEC_PIX_IDX));
   const double* ifn_host = static_cast<const double*>(host.ptr(SEC_IF));
   for (int c = 0; c < n_chords; ++c) {
     const int* ch = m->ch_i + c * CH_I_COUNT;
@@ -466,6 +487,26 @@ int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar
       e2 = cudaMemcpy(m->ifc_taps_dev[c], pl.taps_rev.data(), sizeof(float) * pl.taps_rev.size(), cudaMemcpyHostToDevice);
     if (e2 != cudaSuccess) { baysar_model_destroy(m); return fail(std::string("ifc taps upload: ") + cudaGetErrorString(e2)); }
     m->any_ifc = true;
+    if (ch[CH_CALWAVE_IDX] < 0) {  // static wavelength map: the pixel stage reads columns i_p and i_p + 1 only
+      IfcPlan& plw = m->ifc[c];
+      const int words = plw.n_tiles * (ifc::TILE_N / 32);
+      plw.cmask.assign(words, 0u);
+      plw.cbase.assign(words, 0);
+      for (int px = 0; px < ch[CH_P]; ++px) {
+        const int i = pix_idx_host[ch[CH_PIX_OFF] + px];
+        for (int j = i; j <= i + 1; ++j)
+          if (j >= 0 && j < ch[CH_F]) plw.cmask[j >> 5] |= 1u << (j & 31);
+      }
+      int run = 0;
+      for (int w = 0; w < words; ++w) { plw.cbase[w] = run; run += __builtin_popcount(plw.cmask[w]); }
+      plw.c_pitch = (run + 31) / 32 * 32;
+      cudaError_t e3 = cudaMalloc(&m->ifc_cmask_dev[c], sizeof(uint32_t) * words);
+      if (e3 == cudaSuccess) e3 = cudaMalloc(&m->ifc_cbase_dev[c], sizeof(int) * words);
+      if (e3 == cudaSuccess) e3 = cudaMemcpy(m->ifc_cmask_dev[c], plw.cmask.data(), sizeof(uint32_t) * words, cudaMemcpyHostToDevice);
+      if (e3 == cudaSuccess) e3 = cudaMemcpy(m->ifc_cbase_dev[c], plw.cbase.data(), sizeof(int) * words, cudaMemcpyHostToDevice);
+      if (e3 != cudaSuccess) { baysar_model_destroy(m); return fail(std::string("compact map upload: ") + cudaGetErrorString(e3)); }
+      m->conv_c_pitch_max = plw.c_pitch > m->conv_c_pitch_max ? plw.c_pitch : m->conv_c_pitch_max;
+    }
     m->split_pitch_max = pl.pitch > m->split_pitch_max ? pl.pitch : m->split_pitch_max;
     m->conv_pitch_max = pl.out_pitch > m->conv_pitch_max ? pl.out_pitch : m->conv_pitch_max;
     m->tiles_max = pl.n_tiles > m->tiles_max ? pl.n_tiles : m->tiles_max;
@@ -479,8 +520,10 @@ void baysar_model_destroy(baysar_model_t* m) {
   cudaSetDevice(m->device);
   cudaFree(m->blob_dev); cudaFree(m->lines); cudaFree(m->comps); cudaFree(m->hdr); cudaFree(m->status);
   cudaFree(m->theta_stage); cudaFree(m->logp_stage);
-  cudaFree(m->spec); cudaFree(m->conv); cudaFree(m->trapz_part); cudaFree(m->aux);
+  cudaFree(m->spec); cudaFree(m->conv); cudaFree(m->conv_c); cudaFree(m->trapz_part); cudaFree(m->aux);
   for (float* t : m->ifc_taps_dev) cudaFree(t);
+  for (uint32_t* t : m->ifc_cmask_dev) cudaFree(t);
+  for (int* t : m->ifc_cbase_dev) cudaFree(t);
   for (cudaEvent_t ev : m->prof_events) cudaEventDestroy(ev);
   delete m;
 }
@@ -628,8 +671,18 @@ int baysar_debug_if_contract(const float* spectra_dev, int64_t n_rows, int F, co
   p.s = spec; p.pitch = pl.pitch; p.pad_left = pl.pad_left; p.F = F; p.n_row_blocks = (int)(n_rows / ifc::TILE_M);
   p.m_lo = pl.m_lo; p.m_hi = pl.m_hi; p.taps_rev = taps; p.taps_len = pl.taps_len; p.row_min = row_min_dev; p.aux = nullptr; p.aux_rows = 0;
   p.out = out_dev; p.out_pitch = pl.out_pitch; p.trapz_part = trapz_dev; p.n_tiles = pl.n_tiles;
+  p.ring = ifc::ring_stages(pl.m_hi - pl.m_lo + 1);
+  p.debug = getenv("BAYSAR_IFC_DEBUG") ? atoi(getenv("BAYSAR_IFC_DEBUG")) : 0;
+  long long* dbg = nullptr;
+  if (getenv("BAYSAR_IFC_TRACE")) {
+    CUDA_OK(cudaMalloc(&dbg, sizeof(long long) * 8 * 256));
+    CUDA_OK(cudaMemset(dbg, 0, sizeof(long long) * 8 * 256));
+    p.dbg_cycles = dbg;
+  }
   const size_t smem = ifc::smem_bytes(pl.m_hi - pl.m_lo + 1);
-  CUDA_OK(cudaFuncSetAttribute(ifc::if_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool dbg_kernel = p.debug != 0 || dbg != nullptr;
+  CUDA_OK(cudaFuncSetAttribute(ifc::if_contract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_OK(cudaFuncSetAttribute(ifc::if_contract_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t e0, e1;
   CUDA_OK(cudaEventCreate(&e0));
   CUDA_OK(cudaEventCreate(&e1));
@@ -639,7 +692,8 @@ int baysar_debug_if_contract(const float* spectra_dev, int64_t n_rows, int F, co
   const unsigned ctas = (unsigned)(tiles < sms ? tiles : sms);
   for (int rep = 0; rep < 2; ++rep) {
     CUDA_OK(cudaEventRecord(e0, 0));
-    ifc::if_contract_kernel<<<ctas, ifc::THREADS, smem>>>(p);
+    if (dbg_kernel) ifc::if_contract_kernel<true><<<ctas, ifc::THREADS, smem>>>(p);
+    else ifc::if_contract_kernel<false><<<ctas, ifc::THREADS, smem>>>(p);
     CUDA_OK(cudaEventRecord(e1, 0));
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventSynchronize(e1));
@@ -648,6 +702,18 @@ int baysar_debug_if_contract(const float* spectra_dev, int64_t n_rows, int F, co
   CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
   if (elapsed_ms) *elapsed_ms = ms;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (dbg) {
+    std::vector<long long> h(8 * 256);
+    cudaMemcpy(h.data(), dbg, sizeof(long long) * 8 * 256, cudaMemcpyDeviceToHost);
+    const char* names[8] = {"conv.wait_landed", "conv.wait_empty", "conv.wait_st", "conv.total", "load.wait_consumed",
+                            "epi.wait_acc_full", "mma.wait_full", "mma.wait_acc_free"};
+    for (int k = 0; k < 8; ++k) {
+      double mean = 0;
+      for (unsigned b = 0; b < ctas; ++b) mean += (double)h[b * 8 + k];
+      fprintf(stderr, "[ifc trace] %-20s mean %.0f cycles per CTA (CTA0 %lld)\n", names[k], mean / ctas, h[k]);
+    }
+    cudaFree(dbg);
+  }
   cudaFree(spec); cudaFree(taps);
   return 0;
 }

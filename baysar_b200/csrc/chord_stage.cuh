@@ -153,6 +153,16 @@ struct FetchGlobal {
   const float* row;
   BAYSAR_DEV double operator()(int i) const { return (double)row[i]; }
 };
+// compact rows of the tensor-core path: only the columns a static wavelength map reads, packed in column order
+struct FetchCompact {
+  const float* row;
+  const uint32_t* cmask;  // bit e of word w: column 32 w + e is stored
+  const int* cbase;       // stored columns before word w
+  BAYSAR_DEV double operator()(int i) const {
+    const int w = i >> 5;
+    return (double)row[cbase[w] + __popc(cmask[w] & ((1u << (i & 31)) - 1u))];
+  }
+};
 
 // Area renormalisation, + background, wavelength map, clip, Cauchy likelihood (spectrometers.py:286-310, :154-195).
 // `post` and `pre` are the trapz integrals after / before the instrument convolution; edge64 the four end outputs.
@@ -792,8 +802,10 @@ struct PixelArgs {
   const double* theta;
   int64_t n;
   int chord;
-  const float* conv;        // [rows][conv_pitch]
+  const float* conv;        // [rows][conv_pitch]: every column, or (cmask != nullptr) the compact columns
   int64_t conv_pitch;
+  const uint32_t* cmask;
+  const int* cbase;
   const double* trapz_part; // [rows][n_tiles]
   int n_tiles;
   const double* aux;        // [N][BAYSAR_AUX_STRIDE]
@@ -821,14 +833,24 @@ __global__ void __launch_bounds__(NT) pixel_stage_kernel(ModelDev m, PixelArgs a
   const double* th = a.theta + n * n_params;
   const double* ax = a.aux + n * BAYSAR_AUX_STRIDE;
   uint32_t st = 0;
-  double post_s = 0.0;
+  // trapz of the convolved spectrum: the contraction's per-tile partial sums, one per thread, reduced in a fixed
+  // order (deterministic)
   const double* part = a.trapz_part + n * (int64_t)a.n_tiles;
-  for (int t = 0; t < a.n_tiles; ++t) post_s += part[t];
+  double red_p[1] = {0.0};
+  for (int t = tid; t < a.n_tiles; t += NT) red_p[0] += part[t];
+  block_sum<NT, 1>(red_p, scratch);
+  const double post_s = red_p[0];
   if (!(post_s - post_s == 0.0)) st |= 1u << 8;
   const double post = chd[CH_DL] * post_s;
-  FetchGlobal fetch{a.conv + n * a.conv_pitch};
-  pixel_likelihood<NT>(m, ch, chd, th, n, c, ncomp_cols, ax[0], post, ax + 2, fetch, scratch, a.components, a.spectra,
-                       a.fine_post, st);
+  if (a.cmask) {
+    FetchCompact fetch{a.conv + n * a.conv_pitch, a.cmask, a.cbase};
+    pixel_likelihood<NT>(m, ch, chd, th, n, c, ncomp_cols, ax[0], post, ax + 2, fetch, scratch, a.components, a.spectra,
+                         nullptr, st);
+  } else {
+    FetchGlobal fetch{a.conv + n * a.conv_pitch};
+    pixel_likelihood<NT>(m, ch, chd, th, n, c, ncomp_cols, ax[0], post, ax + 2, fetch, scratch, a.components, a.spectra,
+                         a.fine_post, st);
+  }
   st = __syncthreads_or((int)st);
   if (tid == 0 && st) atomicOr(&a.status[n], st);
 }

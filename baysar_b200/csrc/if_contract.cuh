@@ -10,13 +10,15 @@
 //   output tiles of the same thetas, so the overlapping parts of their k-ranges are served by L2.
 // * B operand — the Toeplitz tile depends only on (j0 - k0): ALL k-blocks of the band are windows of ONE tall
 //   "master" tile (128 + 32 (n_kb - 1) rows of 32 taps, K-major SWIZZLE_128B, TF32 hi and lo parts), which every
-//   CTA builds once in shared memory (<= 221 KB).  The B descriptor of k-block kb is the master's base plus
+//   CTA builds once in shared memory (<= 176 KB).  The B descriptor of k-block kb is the master's base plus
 //   4096 (n_kb - 1 - kb) bytes; nothing is generated or copied per k-block.
-// * A operand — the pre-convolution spectra, plain FP32 rows [theta][pitch] in HBM/L2 (zero padded).  Producer
-//   threads own one theta row each: they load 64 bytes per k-block (four k-blocks in flight in registers), split the
-//   values into two TF32 terms (hi, lo) and write them to TENSOR MEMORY with tcgen05.st; the MMAs take A from TMEM
-//   (the .ts form).  Shared memory carries no per-k-block traffic at all: it holds the master tile only, and
-//   the tensor pipe's operand reads are the only shared-memory reads in the main loop.
+// * A operand — the pre-convolution spectra, plain FP32 rows [theta][pitch] in HBM/L2 (zero padded).  A k-block of a
+//   tile (128 rows x 128 bytes) is copied global -> shared with coalesced 16-byte cp.async (each 128-byte line is
+//   touched by exactly one warp instruction; a row-per-thread LDG pattern was measured L1-tag bound at 75 % l1tex
+//   utilisation) into a 2-4 stage ring, XOR-swizzled so that the row-per-thread reads that follow are conflict-free.
+//   Converter threads then own one theta row each: they read 64 bytes, split the values into two TF32 terms
+//   (hi, lo) and write them to TENSOR MEMORY with tcgen05.st; the MMAs take A from TMEM (the .ts form), so the
+//   tensor pipe's only shared-memory reads are the B windows of the master tile.
 // * 3xTF32: hi*hi accumulates in one FP32 TMEM tile, hi*lo + lo*hi in a second one; the epilogue adds them.
 //   TMEM accumulation truncates (measured: signed error mean -2.5e-6, never positive, with one accumulator and
 //   k-blocks in natural order), so (a) the 2^-11-sized cross terms get their own accumulator and (b) k-blocks are
@@ -24,10 +26,11 @@
 //   happen while the accumulator is still small.
 // * TMEM map (512 columns): [0,128) accumulator hi*hi, [128,256) accumulator cross terms, [256,512) four A stages of
 //   32 hi + 32 lo columns.
-// * Warp roles: warps 0-7 produce A (warp w: TMEM lanes 32 (w % 4).., k columns 16 (w / 4)..), warps 8-11 run the
-//   epilogue (so the producers already fill the A stages of the next tile while the accumulators drain), warp 12
-//   issues the MMAs.  full[s] (producers -> issuer), empty[s] (tcgen05.commit -> producers), acc_full (commit ->
-//   epilogue), acc_free (epilogue -> issuer) mbarriers; no block-wide barrier after the prologue.
+// * Warp roles: warps 0-7 convert A (warp w: TMEM lanes 32 (w % 4).., k columns 16 (w / 4)..), warps 8-11 run the
+//   epilogue (so the A stages of the next tile fill while the accumulators drain), warp 12 issues the MMAs, warp 13
+//   issues the cp.async copies.  landed[r] (cp.async -> converters), consumed[r] (converters -> loader), full[s]
+//   (converters -> issuer), empty[s] (tcgen05.commit -> converters), acc_full (commit -> epilogue), acc_free
+//   (epilogue -> issuer) mbarriers; no block-wide barrier after the prologue.
 // * Epilogue: tcgen05.ld (32 lanes x 32 columns), clip at the per-theta pre-convolution minimum, trapz partial per
 //   (theta, tile) in float64 (deterministic: summed in tile order by the pixel kernel), FP32 store.
 #pragma once
@@ -39,13 +42,16 @@ namespace ifc {
 constexpr int TILE_M = 128;   // thetas per tile
 constexpr int TILE_N = 128;   // fine-grid outputs per tile
 constexpr int TILE_K = 32;    // TF32 elements per k-block = one 128-byte swizzle row
-constexpr int A_STAGES = 4;
+constexpr int A_STAGES = 4;     // tensor-memory stages of the split A operand
+constexpr int RING_MAX = 4;     // shared-memory stages of the raw FP32 A tiles (16 KB each): 2..4, what fits
+constexpr int A_TILE_BYTES = TILE_M * TILE_K * 4;
 constexpr int PRODUCER_WARPS = 8, EPILOGUE_WARPS = 4;
-constexpr int THREADS = (PRODUCER_WARPS + EPILOGUE_WARPS + 1) * 32;
+constexpr int THREADS = (PRODUCER_WARPS + EPILOGUE_WARPS + 2) * 32;  // + MMA issuer + loader
 constexpr int TMEM_COLS = 512;
 constexpr int TMEM_ACC1 = TILE_N;          // cross-term accumulator
 constexpr int TMEM_A = 2 * TILE_N;         // first A stage
-constexpr int MAX_KB = 24;                 // master tile <= 864 rows x 128 B x 2 = 221 184 bytes
+constexpr int MAX_KB = 21;                 // master tile <= 768 rows x 128 B x 2 = 196 608 bytes (+ 32 KB ring)
+constexpr size_t SMEM_LIMIT = 232448;      // 227 KB of dynamic shared memory per CTA
 
 struct Params {
   const float* s;         // [n_rows][pitch]  FP32 spectra, zero padded: column pad_left + k'
@@ -64,6 +70,15 @@ struct Params {
   int64_t out_pitch;
   double* trapz_part;     // [n_rows][n_tiles]  sum over the tile of w_j * out[j] (w = 1/2 at j = 0, F-1), may be nullptr
   int n_tiles;
+  int ring;               // shared-memory A stages (ring_stages(n_kb))
+  // compact output (static wavelength map): only the columns the pixel stage reads are stored, packed in column order
+  const uint32_t* cmask;  // [n_tiles * 4] bit e of word w: column 32 w + e is needed; nullptr = store every column to `out`
+  const int* cbase;       // [n_tiles * 4] number of needed columns before word w
+  float* out_c;           // [n_rows][out_c_pitch]
+  int64_t out_c_pitch;
+  int debug;              // timing experiments only (wrong results): &3: MMA mix; 4: no A loads; 8: no output stores;
+                          // 16: no tcgen05.st
+  long long* dbg_cycles;  // optional [gridDim.x][8] cycles spent waiting per role (timing experiments)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,6 +99,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra.uni WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
       "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <bool DEBUG>
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, long long& acc) {
+  if (DEBUG) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity);
+  }
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits
@@ -152,23 +178,34 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 }
 
 inline int master_rows(int n_kb) { return TILE_N + TILE_K * (n_kb - 1); }
-inline size_t smem_bytes(int n_kb) {
-  return (size_t)2 * master_rows(n_kb) * 128 + (2 * A_STAGES + 2) * sizeof(uint64_t) + 16 + 1024;  // + alignment slack
+inline size_t smem_fixed(int n_kb) {
+  return (size_t)2 * master_rows(n_kb) * 128 + (2 * A_STAGES + 2 * RING_MAX + 2) * sizeof(uint64_t) + 16 + 1024;  // + alignment slack
 }
+inline int ring_stages(int n_kb) {
+  const long room = (long)SMEM_LIMIT - (long)smem_fixed(n_kb);
+  const int r = (int)(room / A_TILE_BYTES);
+  return r > RING_MAX ? RING_MAX : r;
+}
+inline size_t smem_bytes(int n_kb) { return smem_fixed(n_kb) + (size_t)ring_stages(n_kb) * A_TILE_BYTES; }
 
+template <bool DEBUG>
 __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
+  const int dbg_mode = DEBUG ? p.debug : 0;  // timing experiments compile away in the production instantiation
   extern __shared__ unsigned char smem_dyn[];
-  // carve (1024-byte aligned): master_hi | master_lo | barriers | TMEM slot
+  // carve (1024-byte aligned): master_hi | master_lo | A ring | barriers | TMEM slot
   unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   const int n_kb = p.m_hi - p.m_lo + 1;
   const int R = TILE_N + TILE_K * (n_kb - 1);
   unsigned char* master_hi = smem_raw;
   unsigned char* master_lo = smem_raw + (size_t)R * 128;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)2 * R * 128);
+  unsigned char* ring = smem_raw + (size_t)2 * R * 128;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)p.ring * A_TILE_BYTES);
+  uint64_t* landed = full + A_STAGES + A_STAGES + 2;
+  uint64_t* consumed = landed + RING_MAX;
   uint64_t* empty = full + A_STAGES;
   uint64_t* acc_full = empty + A_STAGES;
   uint64_t* acc_free = acc_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1 + 2 * RING_MAX);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t total_tiles = (int64_t)p.n_row_blocks * p.n_tiles;
@@ -192,6 +229,7 @@ __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
     for (int s = 0; s < A_STAGES; ++s) { mbar_init(&full[s], PRODUCER_WARPS); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1);
     mbar_init(acc_free, EPILOGUE_WARPS);
+    for (int r = 0; r < RING_MAX; ++r) { mbar_init(&landed[r], 32); mbar_init(&consumed[r], PRODUCER_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   if (warp == PRODUCER_WARPS + EPILOGUE_WARPS) {
@@ -205,64 +243,97 @@ __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
   const uint32_t tmem_d = *tmem_slot;
 
   if (warp < PRODUCER_WARPS) {
-    // ===================== A producers =====================
+    // ===================== A converters: ring (shared memory) -> TF32 split -> tensor memory =====================
+    // Software pipelined: the tcgen05.st of k-block g completes (wait::st) while k-block g + 1 is read and split, so
+    // full[] of k-block g is signalled one iteration late; the four TMEM stages absorb the delay.
     const int quad = warp & 3, khalf = warp >> 2;
     const int row_in_tile = quad * 32 + lane;
     const int64_t iters = my_tiles * n_kb;
-    // source of this thread's 16 floats of global k-block iteration g (tiles of this CTA back to back)
-    auto src = [&](int64_t g) -> const float4* {
-      const int64_t q = g / n_kb;
-      const int i = (int)(g - q * n_kb);
+    const uint32_t lane_base = tmem_d + ((uint32_t)(quad * 32) << 16) + TMEM_A + 16 * khalf;
+    int r = 0;
+    uint32_t r_phase = 0;
+    int d_pending = -1;
+    long long w_landed = 0, w_empty = 0, w_st = 0;
+    const long long t_begin = DEBUG ? clock64() : 0;
+    for (int64_t g = 0; g < iters; ++g) {
+      const int d = (int)(g % A_STAGES);
+      mbar_wait_timed<DEBUG>(&landed[r], r_phase, w_landed);
+      // this thread's 16 floats of its theta row: chunks 4 khalf .. 4 khalf + 3 of the swizzled 128-byte row
+      float4 raw[4];
+      const unsigned char* row_ptr = ring + (size_t)r * A_TILE_BYTES;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) raw[c] = *reinterpret_cast<const float4*>(row_ptr + swz(row_in_tile, 4 * khalf + c));
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        split_tf32(raw[c].x, hi[4 * c + 0], lo[4 * c + 0]);
+        split_tf32(raw[c].y, hi[4 * c + 1], lo[4 * c + 1]);
+        split_tf32(raw[c].z, hi[4 * c + 2], lo[4 * c + 2]);
+        split_tf32(raw[c].w, hi[4 * c + 3], lo[4 * c + 3]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&consumed[r]);  // this warp has read ring stage r (the loader may refill it)
+      if (d_pending >= 0) {                      // k-block g - 1 is in tensor memory: hand it to the MMA issuer
+        const long long t0 = DEBUG ? clock64() : 0;
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (DEBUG) w_st += clock64() - t0;
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[d_pending]);
+      }
+      if (g >= A_STAGES) {  // TMEM stage d: the MMAs of its previous user are done
+        mbar_wait_timed<DEBUG>(&empty[d], (uint32_t)(((g / A_STAGES) - 1) & 1), w_empty);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+      }
+      if (!(dbg_mode & 16)) {
+        tmem_st16(lane_base + 64 * d, hi);
+        tmem_st16(lane_base + 64 * d + 32, lo);
+      }
+      d_pending = d;
+      if (++r == p.ring) { r = 0; r_phase ^= 1u; }
+    }
+    if (d_pending >= 0) {
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[d_pending]);
+    }
+    if (DEBUG && p.dbg_cycles && tid == 0) {
+      long long* o = p.dbg_cycles + (int64_t)blockIdx.x * 8;
+      o[0] = w_landed; o[1] = w_empty; o[2] = w_st; o[3] = clock64() - t_begin;
+    }
+  } else if (warp == PRODUCER_WARPS + EPILOGUE_WARPS + 1) {
+    // ===================== A loader (warp 13): global -> ring with coalesced 16-byte cp.async =====================
+    // Lane l copies the 16-byte chunk (l & 7) of rows (l >> 3) + 4 q, q = 0..31: every warp instruction covers four
+    // whole 128-byte lines.  k-block iterations of this CTA's tiles run back to back.
+    int r = 0;
+    uint32_t r_phase = 0;
+    int64_t g = 0;
+    long long w_consumed = 0;
+    for (int64_t q = 0; q < my_tiles; ++q) {
       const int64_t t = blockIdx.x + q * gridDim.x;
       const int rb = (int)(t / p.n_tiles), nt = (int)(t - (int64_t)rb * p.n_tiles);
-      const int kb = kb_order(i, n_kb);
-      return reinterpret_cast<const float4*>(p.s + (int64_t)(rb * TILE_M + row_in_tile) * p.pitch + p.pad_left +
-                                             nt * TILE_N + TILE_K * (p.m_lo + kb) + 16 * khalf);
-    };
-    float4 buf[A_STAGES][4];
-#pragma unroll
-    for (int d = 0; d < A_STAGES; ++d) {
-      if (d < iters) {
-        const float4* a = src(d);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) buf[d][c] = __ldg(a + c);
-      }
-    }
-    const uint32_t lane_base = tmem_d + ((uint32_t)(quad * 32) << 16) + TMEM_A + 16 * khalf;
-    for (int64_t g0 = 0; g0 < iters; g0 += A_STAGES) {
-#pragma unroll
-      for (int d = 0; d < A_STAGES; ++d) {
-        const int64_t g = g0 + d;
-        if (g < iters) {
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            split_tf32(buf[d][c].x, hi[4 * c + 0], lo[4 * c + 0]);
-            split_tf32(buf[d][c].y, hi[4 * c + 1], lo[4 * c + 1]);
-            split_tf32(buf[d][c].z, hi[4 * c + 2], lo[4 * c + 2]);
-            split_tf32(buf[d][c].w, hi[4 * c + 3], lo[4 * c + 3]);
-          }
-          if (g + A_STAGES < iters) {  // refill this register stage: four k-blocks ahead
-            const float4* a = src(g + A_STAGES);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) buf[d][c] = __ldg(a + c);
-          }
-          if (g >= A_STAGES) {  // stage d: the MMAs of its previous user are done
-            mbar_wait(&empty[d], (uint32_t)(((g / A_STAGES) - 1) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;");
-          }
-          tmem_st16(lane_base + 64 * d, hi);
-          tmem_st16(lane_base + 64 * d + 32, lo);
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          asm volatile("tcgen05.fence::before_thread_sync;");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full[d]);
+      const float* base = p.s + (int64_t)(rb * TILE_M + (lane >> 3)) * p.pitch + p.pad_left + nt * TILE_N + TILE_K * p.m_lo + 4 * (lane & 7);
+      for (int i = 0; i < n_kb; ++i, ++g) {
+        if (g >= p.ring) mbar_wait_timed<DEBUG>(&consumed[r], r_phase ^ 1u, w_consumed);  // all converter warps have read the previous use
+        const float* src = base + TILE_K * kb_order(i, n_kb);
+        unsigned char* dst = ring + (size_t)r * A_TILE_BYTES;
+#pragma unroll 8
+        for (int qq = 0; qq < ((dbg_mode & 4) ? 0 : 32); ++qq) {
+          const int row = (lane >> 3) + 4 * qq;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + swz(row, lane & 7))),
+                       "l"(src + (int64_t)(4 * qq) * p.pitch) : "memory");
         }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&landed[r])) : "memory");
+        if (++r == p.ring) { r = 0; r_phase ^= 1u; }
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (DEBUG && p.dbg_cycles && lane == 0) p.dbg_cycles[(int64_t)blockIdx.x * 8 + 4] = w_consumed;
   } else if (warp < PRODUCER_WARPS + EPILOGUE_WARPS) {
     // ===================== epilogue (warps 8-11): TMEM -> registers -> add accumulators, clip, trapz -> global ====
     const int quad = warp & 3;
+    long long w_accfull = 0;
     for (int64_t q = 0; q < my_tiles; ++q) {
       const int64_t t = blockIdx.x + q * gridDim.x;
       const int rb = (int)(t / p.n_tiles), nt = (int)(t - (int64_t)rb * p.n_tiles);
@@ -273,7 +344,7 @@ __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
       else if (p.aux && row < p.aux_rows) clip = (float)p.aux[(int64_t)row * 8 + 1];
       float* orow = p.out + (int64_t)row * p.out_pitch;
       double part = 0.0;
-      mbar_wait(acc_full, (uint32_t)(q & 1));
+      mbar_wait_timed<DEBUG>(acc_full, (uint32_t)(q & 1), w_accfull);
       asm volatile("tcgen05.fence::after_thread_sync;");
 #pragma unroll 1
       for (int c0 = 0; c0 < TILE_N; c0 += 32) {
@@ -287,39 +358,65 @@ __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_free);
         }
+        const bool interior = j0 > 0 && j0 + TILE_N < p.F;  // unit trapz weights, no bounds
+        uint32_t need = 0xffffffffu;
+        float* crow = nullptr;
+        if (p.cmask) {
+          const int w = (j0 + c0) >> 5;
+          need = p.cmask[w];
+          crow = p.out_c + (int64_t)row * p.out_c_pitch + p.cbase[w];
+        }
 #pragma unroll
         for (int e4 = 0; e4 < 32; e4 += 4) {
           float f[4];
-          float psum = 0.f;
+          if (interior) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x = __uint_as_float(v[e4 + e]) + __uint_as_float(u[e4 + e]);
-            x = x < clip ? clip : x;
-            f[e] = x;
-            const int j = j0 + c0 + e4 + e;
-            if (j < p.F) {
-              if (j == 0 || j == p.F - 1) part += 0.5 * (double)x; else psum += x;
+            for (int e = 0; e < 4; ++e) {
+              const float x = __uint_as_float(v[e4 + e]) + __uint_as_float(u[e4 + e]);
+              f[e] = x < clip ? clip : x;
             }
+            part += (double)((f[0] + f[1]) + (f[2] + f[3]));
+          } else {
+            float psum = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = __uint_as_float(v[e4 + e]) + __uint_as_float(u[e4 + e]);
+              x = x < clip ? clip : x;
+              f[e] = x;
+              const int j = j0 + c0 + e4 + e;
+              if (j < p.F) {
+                if (j == 0 || j == p.F - 1) part += 0.5 * (double)x; else psum += x;
+              }
+            }
+            part += (double)psum;
           }
-          part += (double)psum;
-          if (j0 + c0 + e4 < p.F) *reinterpret_cast<float4*>(orow + j0 + c0 + e4) = make_float4(f[0], f[1], f[2], f[3]);
+          if (dbg_mode & 8) {
+          } else if (crow) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (need & (1u << (e4 + e))) crow[__popc(need & ((1u << (e4 + e)) - 1u))] = f[e];
+          } else if (interior || j0 + c0 + e4 < p.F) {
+            *reinterpret_cast<float4*>(orow + j0 + c0 + e4) = make_float4(f[0], f[1], f[2], f[3]);
+          }
         }
       }
       if (p.trapz_part) p.trapz_part[(int64_t)row * p.n_tiles + nt] = part;
     }
-  } else {
+    if (DEBUG && p.dbg_cycles && warp == PRODUCER_WARPS && lane == 0) p.dbg_cycles[(int64_t)blockIdx.x * 8 + 5] = w_accfull;
+  } else if (warp == PRODUCER_WARPS + EPILOGUE_WARPS) {
     // ===================== MMA issuer (warp 12) =====================
     const uint32_t idesc = make_idesc(TILE_N);
     const uint32_t mh = smem_u32(master_hi), ml = smem_u32(master_lo);
     int64_t g = 0;
+    long long w_full = 0, w_accfree = 0;
     for (int64_t q = 0; q < my_tiles; ++q) {
       if (q > 0) {  // the epilogue has read the accumulators of the previous tile
-        mbar_wait(acc_free, (uint32_t)((q - 1) & 1));
+        mbar_wait_timed<DEBUG>(acc_free, (uint32_t)((q - 1) & 1), w_accfree);
         asm volatile("tcgen05.fence::after_thread_sync;");
       }
       for (int i = 0; i < n_kb; ++i, ++g) {
         const int s = (int)(g % A_STAGES);
-        mbar_wait(&full[s], (uint32_t)((g / A_STAGES) & 1));
+        mbar_wait_timed<DEBUG>(&full[s], (uint32_t)((g / A_STAGES) & 1), w_full);
         asm volatile("tcgen05.fence::after_thread_sync;");
         if (lane == 0) {
           const int kb = kb_order(i, n_kb);
@@ -329,9 +426,18 @@ __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
 #pragma unroll
           for (int ks = 0; ks < TILE_K / 8; ++ks) {
             const uint64_t adv = (uint64_t)((ks * 8 * 4) >> 4);  // 32 bytes per k-step inside the 128-byte swizzle row
-            mma_tf32_ts(tmem_d, a_hi + 8 * ks, d_bhi + adv, idesc, (i | ks) ? 1u : 0u);
-            mma_tf32_ts(tmem_d + TMEM_ACC1, a_hi + 8 * ks, d_blo + adv, idesc, (i | ks) ? 1u : 0u);
-            mma_tf32_ts(tmem_d + TMEM_ACC1, a_lo + 8 * ks, d_bhi + adv, idesc, 1u);
+            if ((dbg_mode & 3) == 0) {
+              mma_tf32_ts(tmem_d, a_hi + 8 * ks, d_bhi + adv, idesc, (i | ks) ? 1u : 0u);
+              mma_tf32_ts(tmem_d + TMEM_ACC1, a_hi + 8 * ks, d_blo + adv, idesc, (i | ks) ? 1u : 0u);
+              mma_tf32_ts(tmem_d + TMEM_ACC1, a_lo + 8 * ks, d_bhi + adv, idesc, 1u);
+            } else if ((dbg_mode & 3) == 1) {
+              mma_tf32_ts(tmem_d, a_hi + 8 * ks, d_bhi + adv, idesc, (i | ks) ? 1u : 0u);
+            } else if ((dbg_mode & 3) == 2) {
+              mma_tf32_ts(tmem_d, a_hi + 8 * ks, d_bhi + adv, make_idesc(2 * TILE_N), (i | ks) ? 1u : 0u);
+              mma_tf32_ts(tmem_d + TMEM_ACC1, a_lo + 8 * ks, d_bhi + adv, idesc, 1u);
+            } else if ((dbg_mode & 3) == 3) {
+              mma_tf32_ts(tmem_d, a_hi + 8 * ks, d_bhi + adv, make_idesc(2 * TILE_N), (i | ks) ? 1u : 0u);
+            }
           }
           // frees this A stage when the MMAs above (and all earlier ones) have completed
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
@@ -340,6 +446,10 @@ __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
         }
         __syncwarp();
       }
+    }
+    if (DEBUG && p.dbg_cycles && lane == 0) {
+      p.dbg_cycles[(int64_t)blockIdx.x * 8 + 6] = w_full;
+      p.dbg_cycles[(int64_t)blockIdx.x * 8 + 7] = w_accfree;
     }
   }
 

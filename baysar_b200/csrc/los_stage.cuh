@@ -27,8 +27,8 @@ __host__ __device__ static inline size_t los_smem_per_warp(int L, int n_params) 
   return (size_t)L * (14 * sizeof(double) + 4 * sizeof(int)) + (size_t)(2 * n_params + (L & 1)) * sizeof(double);
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) los_stage_kernel(ModelDev m, LosArgs a) {
+template <int WARPS, int MINB = 1>
+__global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m, LosArgs a) {
 #ifdef BAYSAR_CPU_EMU
   unsigned char* los_smem_raw = emu_dynamic_smem();
 #else

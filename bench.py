@@ -169,7 +169,7 @@ def flop_model(post):
     Balmer lines with a multi-tap Doppler kernel 18 F + 2 taps F flop and 3 F MUFU; Gaussian components 8 flop + 1
     MUFU per point of their +-8.85 sigma window; 14 F + 12 P of bookkeeping and (fused path only) the instrument
     convolution at 2 flop per tap and output.  contract (tensor pipe, 3xTF32): per 128x128 output tile and 32-wide
-    k-block one N=256 and one N=128 MMA per 8-deep k-step, including the zero part of the Toeplitz tiles."""
+    k-block three 128x128x8 MMAs per 8-deep k-step, including the zero part of the Toeplitz tiles."""
     from baysar_b200.spectrometers import BalmerHydrogenLine
 
     tensor_path = post.model.uses_tensor_cores
@@ -205,7 +205,7 @@ def flop_model(post):
             o = (len(inst) - 1) // 2
             n_kb = (127 + o - k_lo) // 32 - (o - k_hi + 1) // 32 + 1
             n_tiles = -(-F // 128)
-            contract += n_tiles * n_kb * 4 * 2.0 * (128 * 256 * 8 + 128 * 128 * 8) / 128.0
+            contract += n_tiles * n_kb * 4 * 3 * 2.0 * (128 * 128 * 8) / 128.0
         else:
             chord += 2.0 * nq_if * F
         dense += 8.0 * n_g * F + n_b * 2 * (10.0 * F + 2.0 * k_d * F + 3.0 * F) + 12.0 * F + 10.0 * P \
@@ -397,8 +397,8 @@ def main():
     dom = max(kernels, key=lambda name: kernels[name]["ms"])
     hbm_bytes = batch * (8.0 * n_params + 8.0 + 4.0 + 8.0 * (len(post.chords) + len(post.priors))
                          + 2 * 8.0 * 16 * post.model.n_ulines)
-    if post.model.uses_tensor_cores:  # split spectra (write + read once per k-band) and convolved spectra
-        hbm_bytes += batch * sum(len(c.x_data_fm) for c in post.chords) * (8.0 + 8.0 + 4.0 + 4.0 * 0.3)
+    if post.model.uses_tensor_cores:  # FP32 spectra and convolved spectra, each written and read once
+        hbm_bytes += batch * sum(len(c.x_data_fm) for c in post.chords) * (4.0 + 4.0 + 4.0 + 4.0)
     roofline = dict(kernels[dom])
     roofline.update({
         "kernel": dom, "traffic": None, "kernels": kernels,
