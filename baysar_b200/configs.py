@@ -20,12 +20,27 @@ X_TRIPLET = [[[4024.78, 4025.33, 4026.33]], [[0.541, 0.373, 0.086]]]
 
 
 class Workload:
-    def __init__(self, name, input_kwargs, los, reference_theta, description):
+    def __init__(self, name, input_kwargs, los, reference_theta, description, profile=None, curvature=None):
         self.name = name
         self.input_kwargs = input_kwargs
         self.los = los  # None -> profile default linspace(-10, 25, 50)
         self.reference_theta = reference_theta  # {tag: list of values}
         self.description = description
+        self.profile = profile      # None -> EsymmtricCauchyPlasma; {"family": "bowman_tee" | "mesh", ...kwargs}
+        self.curvature = curvature  # BaysarPosterior(curvature=...) (CurvatureCost needs the mesh family)
+
+    def make_profile(self, ns):
+        """Profile-function object from the namespace ``ns`` — the reference's ``baysar.lineshapes`` module,
+        ``oracle.numpy_port`` or ``baysar_b200.lineshapes`` all expose the same class names and signatures."""
+        spec = dict(self.profile or {"family": "esymmetric"})
+        family = spec.pop("family")
+        if family == "esymmetric":
+            return ns.EsymmtricCauchyPlasma(x=np.array(self.los, dtype=float)) if self.los is not None else None
+        if family == "bowman_tee":
+            return ns.BowmanTeePlasma(x=np.array(self.los, dtype=float), **spec)
+        if family == "mesh":
+            return ns.MeshPlasma(x=np.array(spec.pop("knots"), dtype=float), **spec)
+        raise ValueError(f"unknown profile family {family}")
 
     def theta_from_tags(self, slices, start):
         """Overwrite ``start`` (a vector inside the bounds) with the tagged reference values."""
@@ -111,6 +126,33 @@ def multi_species(n_chords=1, data="selfconsistent", flags=None):
     name = "multi_species" if n_chords == 1 else f"multi_species_{n_chords}chords"
     return Workload(name, kw, np.linspace(-10.0, 25.0, 100), ref,
                     f"D Balmer + N II/N III + C III + X triplet, {n_chords} chord(s)")
+
+
+def multi_species_bowman(background=False):
+    """The multi-species chord on the BowmanTeePlasma profile family (reference lineshapes.py:332-440), L = 120."""
+    wl = multi_species(1)
+    ref = dict(wl.reference_theta)
+    ref["electron_density"] = [14.6, 0.5, 2.5, 2.0, 3.0, 5.0, 0.5] + ([12.0] if background else [])
+    ref["electron_temperature"] = [0.9, 3.0, 2.0, 3.0, 5.0, 0.5] + ([-0.5] if background else [])
+    return Workload("multi_bowman" + ("_bg" if background else ""), wl.input_kwargs, np.linspace(-15.0, 25.0, 120), ref,
+                    "multi-species chord, BowmanTee ne/Te profiles", profile=dict(family="bowman_tee", background=background))
+
+
+def multi_species_mesh(curvature=None):
+    """The multi-species chord on the MeshPlasma profile family (reference lineshapes.py:235-329): 10^theta at 7
+    knots, linear interpolation onto arange(-10, 25, 0.1) (L = 350); optional CurvatureCost (priors.py:104-127)."""
+    wl = multi_species(1)
+    # The reference's MeshLine counts the two fixed end points as variables when ``zero_bounds`` is given, which its
+    # own bounds check then rejects (lineshapes.py:262, plasmas.py:419-425): the usable form has no fixed ends, so the
+    # knots span the whole line of sight.
+    knots = [-10.0, -6.0, -3.0, -1.0, 0.5, 2.0, 6.0, 12.0, 25.0]
+    ref = dict(wl.reference_theta)
+    ref["electron_density"] = [12.4, 13.0, 13.6, 14.2, 14.6, 14.3, 13.5, 12.6, 12.0]
+    ref["electron_temperature"] = [-0.3, 0.0, 0.4, 0.8, 0.9, 0.7, 0.3, -0.2, -0.5]
+    return Workload("multi_mesh" + ("_curv" if curvature else ""), wl.input_kwargs, None, ref,
+                    "multi-species chord, MeshLine ne/Te profiles",
+                    profile=dict(family="mesh", knots=knots, bounds=[-10.0, 25.0], zero_bounds_ne=None,
+                                 zero_bounds_te=None), curvature=curvature)
 
 
 def aug_demo():

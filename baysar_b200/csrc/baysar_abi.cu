@@ -439,6 +439,8 @@ int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar
   d.ifn = static_cast<const double*>(dev.ptr(SEC_IF));
   d.pix_idx = static_cast<const int*>(dev.ptr(SEC_PIX_IDX));
   d.pix_frac = static_cast<const double*>(dev.ptr(SEC_PIX_FRAC));
+  d.mesh_x = static_cast<const double*>(dev.ptr(SEC_MESH_X));
+  d.mesh_lo = static_cast<const int*>(dev.ptr(SEC_MESH_LO));
 
   // shared memory the chord kernel needs: the largest chord decides (one launch covers all chords)
   const int n_chords = (int)m->I[I_N_CHORDS];

@@ -51,6 +51,8 @@ struct ModelDev {
   const double* ifn;
   const int* pix_idx;
   const double* pix_frac;
+  const double* mesh_x;
+  const int* mesh_lo;
 };
 
 // approximate reciprocal / square root (one MUFU op each, ~1 ulp): the float32 spectral sweeps do not need IEEE rounding

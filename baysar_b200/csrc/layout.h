@@ -9,7 +9,7 @@
 #define BAYSAR_LAYOUT_H
 
 #define BAYSAR_BLOB_MAGIC 0x4252415359534142LL /* "BAYSYSAB" */
-#define BAYSAR_BLOB_VERSION 4
+#define BAYSAR_BLOB_VERSION 5
 
 enum BaysarSection {
   SEC_I,              /* int64  [I_COUNT]           model-wide integer scalars                         */
@@ -46,6 +46,8 @@ enum BaysarSection {
   SEC_IF,             /* double [sum KI]            fine-grid instrument function                       */
   SEC_PIX_IDX,        /* int32  [sum P]             default wavelength map: lower fine-grid index       */
   SEC_PIX_FRAC,       /* double [sum P]             default wavelength map: interpolation weight        */
+  SEC_MESH_X,         /* double [mesh_ne_n + mesh_te_n]  MeshLine knot positions (density, then temperature)  */
+  SEC_MESH_LO,        /* int32  [2][L]              MeshLine: lower knot of every LOS point (density, temperature) */
   SEC_COUNT
 };
 
@@ -58,7 +60,7 @@ enum BaysarI {
   I_N_ULINES,
   I_N_PRIORS,
   I_N_CLINES,
-  I_PROFILE_KIND,       /* 0 = EsymmtricCauchyPlasma */
+  I_PROFILE_KIND,       /* 0 = EsymmtricCauchyPlasma, 1 = BowmanTeePlasma, 2 = MeshPlasma */
   I_NE_IDX,             /* first theta index of the electron_density slice */
   I_TE_IDX,
   I_HAS_HYDROGEN,
@@ -80,6 +82,8 @@ enum BaysarI {
   I_N_TEC,
   I_P_MAX,
   I_F_MAX,
+  I_MESH_NE_N,          /* MeshLine: number of density / temperature knots */
+  I_MESH_TE_N,
   I_COUNT
 };
 
@@ -93,6 +97,9 @@ enum BaysarProfD {
   PROF_NE_CENTRE,
   PROF_TE_CENTRE,
   PROF_NE_FLOOR,        /* 1e-3 */
+  PROF_BACKGROUND,      /* BowmanTee: 1.0 if the last parameter of each profile is log10 of a background level */
+  PROF_MESH_NE_LOG,     /* MeshLine: 1.0 if the knot parameters are log10 values */
+  PROF_MESH_TE_LOG,
   PROF_D_COUNT
 };
 
@@ -126,6 +133,7 @@ enum BaysarPriorKind {
   PRIOR_WAVELENGTH_CAL,
   PRIOR_INTENSITY_CAL,
   PRIOR_GAUSSIAN_IF,
+  PRIOR_CURVATURE,
   PRIOR_KIND_COUNT
 };
 enum BaysarPrI { PR_KIND, PR_I0, PR_I1, PR_I_COUNT };

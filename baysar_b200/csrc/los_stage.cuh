@@ -71,29 +71,73 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
   }
   __syncwarp();
 
-  // ---- electron density / temperature profiles (lineshapes.py:779-817)
+  // ---- electron density / temperature profiles
   const int ne_idx = (int)I[I_NE_IDX], te_idx = (int)I[I_TE_IDX];
-  double ne_A, ne_c, ne_f, ne_floor;
-  if (m.prof_d[PROF_NE_CENTRE_FIXED] != 0.0) {
-    ne_A = th[ne_idx]; ne_f = th[ne_idx + 1]; ne_floor = th[ne_idx + 2]; ne_c = m.prof_d[PROF_NE_CENTRE];
-  } else {
-    ne_A = th[ne_idx]; ne_c = th[ne_idx + 1]; ne_f = th[ne_idx + 2]; ne_floor = m.prof_d[PROF_NE_FLOOR];
-  }
-  const double te_A = th[te_idx], te_f = th[te_idx + 1], te_floor = th[te_idx + 2], te_c = m.prof_d[PROF_TE_CENTRE];
-  const double ne_pk = p10[ne_idx], te_pk = p10[te_idx];
+  const int profile_kind = (int)I[I_PROFILE_KIND];
   double nemax = -1.7976931348623157e308;
-  for (int l = lane; l < L; l += 32) {
-    double x = m.los_x[l];
-    double dx = x - ne_c;
-    double sg = 0.2 * ne_f + ne_f / (1.0 + exp(-dx));
-    double r = dx / sg;
-    double v = clip_lo(ne_pk / (1.0 + r * r), ne_floor);
-    ne_s[l] = v;
-    nemax = v > nemax ? v : nemax;
-    dx = x - te_c;
-    sg = 0.2 * te_f + te_f / (1.0 + exp(-dx));
-    r = dx / sg;
-    te_s[l] = clip_lo(te_pk / (1.0 + r * r), te_floor);
+  if (profile_kind == 0) {
+    // EsymmtricProfile (lineshapes.py:779-817)
+    double ne_A, ne_c, ne_f, ne_floor;
+    if (m.prof_d[PROF_NE_CENTRE_FIXED] != 0.0) {
+      ne_A = th[ne_idx]; ne_f = th[ne_idx + 1]; ne_floor = th[ne_idx + 2]; ne_c = m.prof_d[PROF_NE_CENTRE];
+    } else {
+      ne_A = th[ne_idx]; ne_c = th[ne_idx + 1]; ne_f = th[ne_idx + 2]; ne_floor = m.prof_d[PROF_NE_FLOOR];
+    }
+    (void)ne_A;
+    const double te_f = th[te_idx + 1], te_floor = th[te_idx + 2], te_c = m.prof_d[PROF_TE_CENTRE];
+    const double ne_pk = p10[ne_idx], te_pk = p10[te_idx];
+    for (int l = lane; l < L; l += 32) {
+      double x = m.los_x[l];
+      double dx = x - ne_c;
+      double sg = 0.2 * ne_f + ne_f / (1.0 + exp(-dx));
+      double r = dx / sg;
+      double v = clip_lo(ne_pk / (1.0 + r * r), ne_floor);
+      ne_s[l] = v;
+      nemax = v > nemax ? v : nemax;
+      dx = x - te_c;
+      sg = 0.2 * te_f + te_f / (1.0 + exp(-dx));
+      r = dx / sg;
+      te_s[l] = clip_lo(te_pk / (1.0 + r * r), te_floor);
+    }
+  } else if (profile_kind == 1) {
+    // BowmanTeeNe / BowmanTeeTe (lineshapes.py:332-376): A (1 + |((x - x0) / sigma)|^q / nu)^(-(nu + 1) / 2) + b,
+    // sigma = sigma0 exp(f tanh(k (x - x0))); the temperature profile is centred on 0
+    const int bgf = m.prof_d[PROF_BACKGROUND] != 0.0;
+    const double nA = p10[ne_idx], nx0 = th[ne_idx + 1], ns0 = th[ne_idx + 2], nq = th[ne_idx + 3], nnu = th[ne_idx + 4],
+                 nk = th[ne_idx + 5], nf = th[ne_idx + 6], nb = bgf ? p10[ne_idx + 7] : 0.0;
+    const double tA = p10[te_idx], ts0 = th[te_idx + 1], tq = th[te_idx + 2], tnu = th[te_idx + 3], tk = th[te_idx + 4],
+                 tf = th[te_idx + 5], tb = bgf ? p10[te_idx + 6] : 0.0;
+    for (int l = lane; l < L; l += 32) {
+      const double x = m.los_x[l];
+      double sg = ns0 * exp(nf * tanh(nk * (x - nx0)));
+      double z = pow(fabs((x - nx0) / sg), nq);
+      const double v = nA * pow(1.0 + z / nnu, -(nnu + 1.0) * 0.5) + nb;
+      ne_s[l] = v;
+      nemax = v > nemax ? v : nemax;
+      sg = ts0 * exp(tf * tanh(tk * (x - 0.0)));
+      z = pow(fabs((x - 0.0) / sg), tq);
+      te_s[l] = tA * pow(1.0 + z / tnu, -(tnu + 1.0) * 0.5) + tb;
+    }
+  } else {
+    // MeshLine (lineshapes.py:282-301): values at the knots (10^theta if log), scipy interp1d "linear" with
+    // extrapolation: slope (x - x_lo) + y_lo on the segment [lo, lo + 1] fixed per LOS point at model build
+    const int n_ne = (int)I[I_MESH_NE_N];
+    const int ne_log = m.prof_d[PROF_MESH_NE_LOG] != 0.0, te_log = m.prof_d[PROF_MESH_TE_LOG] != 0.0;
+    const double* xk_ne = m.mesh_x;
+    const double* xk_te = m.mesh_x + n_ne;
+    for (int l = lane; l < L; l += 32) {
+      const double x = m.los_x[l];
+      int lo = m.mesh_lo[l];
+      double y0 = ne_log ? p10[ne_idx + lo] : th[ne_idx + lo], y1 = ne_log ? p10[ne_idx + lo + 1] : th[ne_idx + lo + 1];
+      double slope = (y1 - y0) / (xk_ne[lo + 1] - xk_ne[lo]);
+      const double v = __dadd_rn(__dmul_rn(slope, x - xk_ne[lo]), y0);
+      ne_s[l] = v;
+      nemax = v > nemax ? v : nemax;
+      lo = m.mesh_lo[L + l];
+      y0 = te_log ? p10[te_idx + lo] : th[te_idx + lo]; y1 = te_log ? p10[te_idx + lo + 1] : th[te_idx + lo + 1];
+      slope = (y1 - y0) / (xk_te[lo + 1] - xk_te[lo]);
+      te_s[l] = __dadd_rn(__dmul_rn(slope, x - xk_te[lo]), y0);
+    }
   }
   nemax = warp_max(nemax);
 
@@ -286,7 +330,34 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     const double* pd = m.pr_d + k * PR_D_COUNT;
     const int kind = pi[PR_KIND];
     double val = 0.0;
-    if (kind == PRIOR_STATIC_PRESSURE) {  // priors.py:51-64
+    if (kind == PRIOR_CURVATURE) {  // priors.py:104-127: curvature of the raw density-knot parameters
+      // grad = numpy.gradient (unit spacing): central differences inside, one-sided at the two ends
+      const int nk = (int)I[I_MESH_NE_N];
+      double* g1 = bx_s;  // scratch (the spline bases are dead by now)
+      double vmax = -1.7976931348623157e308;
+      for (int q = 0; q < nk; ++q) vmax = th[ne_idx + q] > vmax ? th[ne_idx + q] : vmax;
+      __syncwarp();
+      for (int q = lane; q < nk; q += 32) {
+        const double c = th[ne_idx + q] / vmax;
+        if (nk == 1) g1[q] = 0.0;
+        else if (q == 0) g1[q] = th[ne_idx + 1] / vmax - c;
+        else if (q == nk - 1) g1[q] = c - th[ne_idx + nk - 2] / vmax;
+        else g1[q] = (th[ne_idx + q + 1] / vmax - th[ne_idx + q - 1] / vmax) / 2.0;
+      }
+      __syncwarp();
+      double cv = 0.0;
+      for (int q = 0; q < nk; ++q) {  // sequential sum like Python's sum()
+        double g2;
+        if (nk == 1) g2 = 0.0;
+        else if (q == 0) g2 = g1[1] - g1[0];
+        else if (q == nk - 1) g2 = g1[nk - 1] - g1[nk - 2];
+        else g2 = (g1[q + 1] - g1[q - 1]) / 2.0;
+        const double den = 1.0 + g1[q] * g1[q];
+        cv += (g2 * g2) / (den * den * den);
+      }
+      val = -cv * pd[PR_D0];
+      __syncwarp();
+    } else if (kind == PRIOR_STATIC_PRESSURE) {  // priors.py:51-64
       double s = 0.0;
       for (int l = lane; l < L; l += 32) {
         double pe = clip_lo(te_s[l], 0.01) * clip_lo(ne_s[l], 1.0);

@@ -111,3 +111,103 @@ class EsymmtricCauchyPlasma:
         self.dr = dr
         self.electron_density = EsymmtricProfile(self.x, bounds_ne, centre=dr)
         self.electron_temperature = EsymmtricProfile(self.x, bounds_te, centre=0)
+
+
+class MeshLine:
+    """Profile given by its values at knots, interpolated linearly onto ``arange(min(x_ends), max(x_ends),
+    resolution)`` with linear extrapolation (reference lineshapes.py:235-301, ``kind="linear"``).  ``log``: the
+    sampled parameters are log10 of the knot values.  With ``zero_bounds`` the reference adds two fixed end points
+    at ``x_ends`` and counts them as variables (lineshapes.py:262), which its own bounds check then rejects — the
+    same ValueError is raised here by the parameter handler."""
+
+    kind = "mesh"
+
+    def __init__(self, x, x_ends=(-10, 10), zero_bounds=None, resolution=0.1, log=False, kind="linear", **kwargs):
+        self.__dict__.update(kwargs)
+        if kind != "linear":
+            raise NotImplementedError("only linear mesh interpolation is compiled for the GPU")
+        x = np.asarray(x, dtype=float)
+        self.log, self.zero_bounds = log, zero_bounds
+        if zero_bounds is None:
+            self.empty_theta = np.zeros(len(x))
+            self.slice = slice(0, len(x))
+            self.x_points = x
+        else:
+            self.slice = slice(1, -1)
+            self.empty_theta = np.zeros(len(x) + 2)
+            self.empty_theta[0] = self.empty_theta[-1] = zero_bounds
+            self.x_points = np.concatenate([np.array([min(x_ends)]), x, np.array([max(x_ends)])])
+        self.x_points = self.x_points.astype(float)
+        if any(t == 0 for t in np.diff(self.x_points)):
+            raise ValueError(f"Some of self.x_points are the same. Zero bounds = {zero_bounds}")
+        self.x = np.arange(min(x_ends), max(x_ends), resolution)
+        self.number_of_variables = len(self.x_points)
+        self.dr = False
+
+    def __call__(self, theta):
+        values = self.empty_theta.copy()
+        values[self.slice] = theta
+        if self.log:
+            values = np.power(10, values)
+        idx = np.clip(np.searchsorted(self.x_points, self.x), 1, len(self.x_points) - 1)
+        lo, hi = idx - 1, idx
+        slope = (values[hi] - values[lo]) / (self.x_points[hi] - self.x_points[lo])
+        return slope * (self.x - self.x_points[lo]) + values[lo]
+
+
+class MeshPlasma:
+    """Reference lineshapes.py:304-329."""
+
+    def __init__(self, x=None, bounds=None, zero_bounds_ne=11, zero_bounds_te=-2, bounds_ne=(11, 16), bounds_te=(-1, 2)):
+        self.electron_density = MeshLine(x=x, zero_bounds=zero_bounds_ne, x_ends=bounds, log=True,
+                                         bounds=[list(bounds_ne) for _ in x])
+        self.electron_temperature = MeshLine(x=x, zero_bounds=zero_bounds_te, x_ends=bounds, log=True,
+                                             bounds=[list(bounds_te) for _ in x])
+
+
+def bowman_tee_distribution(x, theta):
+    """Reference lineshapes.py:332-343."""
+    A, x0, sigma0, q, nu, k, f, b = theta
+    sigma = sigma0 * np.exp(f * np.tanh(k * (x - x0)))
+    z = np.power(abs((x - x0) / sigma), q)
+    return A * np.power(1 + z / nu, -(nu + 1) * 0.5) + b
+
+
+class BowmanTeeProfile:
+    """BowmanTeeNe / BowmanTeeTe (reference lineshapes.py:354-376).  Density: theta = [log10 A, x0, sigma0, q, nu, k, f
+    (, log10 b)]; temperature: centred on 0, theta = [log10 A, sigma0, q, nu, k, f (, log10 b)]."""
+
+    kind = "bowman_tee"
+
+    def __init__(self, x, background, centred):
+        self.x, self.background, self.centred = np.asarray(x, dtype=float), background, centred
+
+    def __call__(self, theta):
+        theta = np.array(theta, dtype=float)
+        theta[0] = np.power(10, theta[0])
+        if self.background:
+            theta[-1] = np.power(10, theta[-1])
+        else:
+            theta = np.concatenate((theta, np.zeros(1)))
+        if self.centred:
+            theta = np.concatenate((theta[:1], np.zeros(1), theta[1:]))
+        return bowman_tee_distribution(self.x, theta)
+
+
+class BowmanTeePlasma:
+    """Reference lineshapes.py:381-440."""
+
+    def __init__(self, x=None, bounds=None, dr_bounds=(-2, 2), bounds_ne=(11, 16), bounds_te=(-1, 2), background=False):
+        self.x = np.linspace(-15, 25, 500) if x is None else np.asarray(x, dtype=float)
+        self.bounds = [[1e-1, 10], [1.2, 3], [1, 5], [1, 50], [0, 2]] if bounds is None else bounds
+        self.background = background
+        self.electron_density = BowmanTeeProfile(self.x, background, centred=False)
+        self.electron_temperature = BowmanTeeProfile(self.x, background, centred=True)
+        self.bounds_ne = [list(bounds_ne), list(dr_bounds)] + [list(b) for b in self.bounds]
+        self.bounds_te = [list(bounds_te)] + [list(b) for b in self.bounds]
+        if background:
+            self.bounds_ne.append([bounds_ne[0], 13.0])
+            self.bounds_te.append([bounds_te[0], 0])
+        self.electron_density.bounds, self.electron_temperature.bounds = self.bounds_ne, self.bounds_te
+        self.electron_density.number_of_variables = len(self.bounds_ne)
+        self.electron_temperature.number_of_variables = len(self.bounds_te)

@@ -31,7 +31,7 @@ def _parse_layout():
 
 ENUMS, BLOB_MAGIC, BLOB_VERSION = _parse_layout()
 SEC = ENUMS["BaysarSection"]
-_DTYPES = {"SEC_I": np.int64, "SEC_SP_I": np.int32, "SEC_ELEM_DENS_IDX": np.int32, "SEC_UL_I": np.int32,
+_DTYPES = {"SEC_MESH_LO": np.int32, "SEC_I": np.int64, "SEC_SP_I": np.int32, "SEC_ELEM_DENS_IDX": np.int32, "SEC_UL_I": np.int32,
            "SEC_PR_I": np.int32, "SEC_CSO_OFF": np.int32, "SEC_CSO_UL": np.int32, "SEC_CH_I": np.int32,
            "SEC_CL_I": np.int32, "SEC_PIX_IDX": np.int32}
 
@@ -66,15 +66,35 @@ def compile_model(plasma, chords, priors):
 
     # ---- profile family
     ne_fn, te_fn = plasma.profile_function.electron_density, plasma.profile_function.electron_temperature
-    if getattr(ne_fn, "kind", None) != "esymmetric_cauchy" or getattr(te_fn, "kind", None) != "esymmetric_cauchy":
-        raise NotImplementedError("only the EsymmtricCauchyPlasma profile family is compiled for the GPU so far")
-    if te_fn.centre is None:
-        raise NotImplementedError("the temperature profile needs a fixed centre (reference default: 0)")
+    kinds = (getattr(ne_fn, "kind", None), getattr(te_fn, "kind", None))
     prof = np.zeros(e["BaysarProfD"]["PROF_D_COUNT"])
-    prof[e["BaysarProfD"]["PROF_NE_CENTRE_FIXED"]] = 0.0 if ne_fn.centre is None else 1.0
-    prof[e["BaysarProfD"]["PROF_NE_CENTRE"]] = 0.0 if ne_fn.centre is None else ne_fn.centre
-    prof[e["BaysarProfD"]["PROF_TE_CENTRE"]] = te_fn.centre
     prof[e["BaysarProfD"]["PROF_NE_FLOOR"]] = 1e-3
+    sec["SEC_MESH_X"], sec["SEC_MESH_LO"] = np.zeros(2), np.zeros(2, dtype=np.int32)
+    if kinds == ("esymmetric_cauchy", "esymmetric_cauchy"):
+        if te_fn.centre is None:
+            raise NotImplementedError("the temperature profile needs a fixed centre (reference default: 0)")
+        profile_kind = 0
+        prof[e["BaysarProfD"]["PROF_NE_CENTRE_FIXED"]] = 0.0 if ne_fn.centre is None else 1.0
+        prof[e["BaysarProfD"]["PROF_NE_CENTRE"]] = 0.0 if ne_fn.centre is None else ne_fn.centre
+        prof[e["BaysarProfD"]["PROF_TE_CENTRE"]] = te_fn.centre
+    elif kinds == ("bowman_tee", "bowman_tee"):
+        profile_kind = 1
+        prof[e["BaysarProfD"]["PROF_BACKGROUND"]] = 1.0 if ne_fn.background else 0.0
+    elif kinds == ("mesh", "mesh"):
+        profile_kind = 2
+        if ne_fn.zero_bounds is not None or te_fn.zero_bounds is not None:
+            raise NotImplementedError("MeshLine with fixed end values is rejected by the reference's own bounds check")
+        prof[e["BaysarProfD"]["PROF_MESH_NE_LOG"]] = 1.0 if ne_fn.log else 0.0
+        prof[e["BaysarProfD"]["PROF_MESH_TE_LOG"]] = 1.0 if te_fn.log else 0.0
+        lows = []
+        for fn in (ne_fn, te_fn):  # scipy interp1d._call_linear: clip(searchsorted(x, x_new), 1, n - 1) - 1
+            lows.append(np.clip(np.searchsorted(fn.x_points, los), 1, len(fn.x_points) - 1) - 1)
+        sec["SEC_MESH_X"] = np.concatenate([ne_fn.x_points, te_fn.x_points])
+        sec["SEC_MESH_LO"] = np.concatenate(lows).astype(np.int32)
+        iset("I_MESH_NE_N", len(ne_fn.x_points)), iset("I_MESH_TE_N", len(te_fn.x_points))
+    else:
+        raise NotImplementedError(f"profile family {kinds} is not compiled for the GPU "
+                                  "(EsymmtricCauchyPlasma, BowmanTeePlasma and MeshPlasma are)")
     sec["SEC_PROF_D"] = prof
 
     # ---- species
@@ -283,6 +303,8 @@ def compile_model(plasma, chords, priors):
             pr_i[k, 1] = _theta_index(plasma, "cal_0")
         elif p.kind == "PRIOR_GAUSSIAN_IF":
             pr_i[k, 1] = _theta_index(plasma, "calint_func_0")
+        elif p.kind == "PRIOR_CURVATURE":
+            pr_d[k, 0] = p.scale
     sec["SEC_PR_I"], sec["SEC_PR_D"] = pr_i, pr_d
     sec["SEC_CSO_OFF"] = np.array(cso_off, dtype=np.int32)
     sec["SEC_CSO_UL"] = np.array(cso_ul or [0], dtype=np.int32)
@@ -290,7 +312,7 @@ def compile_model(plasma, chords, priors):
     # ---- scalars
     iset("I_N_PARAMS", plasma.n_params), iset("I_L", L), iset("I_N_CHORDS", len(chords))
     iset("I_N_SPECIES", len(species)), iset("I_N_ELEM", len(plasma.impurities)), iset("I_N_ULINES", len(ul_rows))
-    iset("I_N_PRIORS", len(priors)), iset("I_N_CLINES", len(cl_i_rows)), iset("I_PROFILE_KIND", 0)
+    iset("I_N_PRIORS", len(priors)), iset("I_N_CLINES", len(cl_i_rows)), iset("I_PROFILE_KIND", profile_kind)
     iset("I_NE_IDX", plasma.slices["electron_density"].start)
     iset("I_TE_IDX", plasma.slices["electron_temperature"].start)
     iset("I_HAS_HYDROGEN", plasma.contains_hydrogen)

@@ -19,7 +19,7 @@ import numpy as np
 from . import runtime
 from .model import compile_model
 from .plasmas import PlasmaLine
-from .priors import (AntiprotonCost, CalibrationPrior, ChargeStateOrderPrior, GaussianInstrumentFunctionPrior,
+from .priors import (AntiprotonCost, CalibrationPrior, ChargeStateOrderPrior, CurvatureCost, GaussianInstrumentFunctionPrior,
                      MainIonFractionCost, NeutralFractionCost, StarkToPeakPrior, StaticElectronPressureCost,
                      WavelengthCalibrationPrior, _DevicePrior)
 from .spectrometers import BalmerHydrogenLine, SpectrometerChord, XLine
@@ -43,8 +43,8 @@ def build_components(plasma, input_dict, curvature=None, passed_priors=()):
     chords = [SpectrometerChord(plasma=plasma, refine=refine, chord_number=c)
               for c, refine in enumerate(input_dict["refine"])]
     priors = []
-    if curvature is not None:
-        raise NotImplementedError("CurvatureCost needs the MeshLine profile family (SURVEY.md §8f-4)")
+    if curvature is not None:  # posterior.py:109-110
+        priors.append(CurvatureCost(plasma, curvature))
     if plasma.calibrate_wavelength:
         for num in range(plasma.num_chords):
             inmean = chords[num].x_data.mean()

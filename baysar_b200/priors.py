@@ -34,6 +34,17 @@ class _DevicePrior:
         return float(comps[0, self._column])
 
 
+class CurvatureCost(_DevicePrior):
+    kind = "PRIOR_CURVATURE"  # priors.py:104-127: curvature of the raw density-knot parameters, times `scale`
+
+    def __init__(self, plasma, scale):
+        super().__init__()
+        fn = plasma.profile_function.electron_density
+        if getattr(fn, "kind", None) != "mesh":
+            raise AttributeError("CurvatureCost needs a MeshLine density profile (x_points / empty_theta)")
+        self.scale = scale
+
+
 class StaticElectronPressureCost(_DevicePrior):
     kind = "PRIOR_STATIC_PRESSURE"  # priors.py:51-64 (threshold 5e15, sigma 0.1)
 

@@ -93,6 +93,9 @@ def main():
         ("multi_calibrated", configs.multi_species(1, flags=dict(calibrate_wavelength=True, calibrate_intensity=True,
                                                                  calibrate_instrument_function=True)), 8, 1, {}),
         ("multi_no_doppler", configs.multi_species(1, flags=dict(doppler_shifts=False)), 6, 0, {}),
+        ("multi_bowman", configs.multi_species_bowman(), 10, 1, {}),
+        ("multi_bowman_bg", configs.multi_species_bowman(background=True), 8, 0, {}),
+        ("multi_mesh_curv", configs.multi_species_mesh(curvature=50.0), 10, 1, {}),
     ]
     only = sys.argv[1:]
     for name, wl, n, nfine, attrs in jobs:

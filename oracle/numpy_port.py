@@ -147,12 +147,109 @@ class EsymmtricCauchyPlasma:
         self.electron_temperature = EsymmtricProfile(self.x, list(bounds_te), centre=0)
 
 
+class MeshLine:
+    """lineshapes.py:235-301 (``kind="linear"``): theta at the knots (plus fixed end values ``zero_bounds`` at
+    ``x_ends``), ``10**`` if ``log``, linear interpolation with linear extrapolation onto ``arange(x_ends)``."""
+
+    def __init__(self, x, x_ends=(-10, 10), zero_bounds=None, resolution=0.1, log=False, bounds=None):
+        x = np.asarray(x, dtype=float)
+        self.log, self.zero_bounds = log, zero_bounds
+        if zero_bounds is None:
+            self.empty_theta = np.zeros(len(x))
+            self.slice = slice(0, len(x))
+            self.x_points = x
+        else:
+            self.slice = slice(1, -1)
+            self.empty_theta = np.zeros(len(x) + 2)
+            self.empty_theta[0] = self.empty_theta[-1] = zero_bounds
+            self.x_points = np.concatenate([np.array([min(x_ends)]), x, np.array([max(x_ends)])])
+        self.x_points = self.x_points.astype(float)
+        self.x = np.arange(min(x_ends), max(x_ends), resolution)
+        self.number_of_variables = len(self.x_points)  # sic: counts the fixed end points too (lineshapes.py:262)
+        self.bounds = bounds
+
+    def __call__(self, theta):
+        from scipy.interpolate import interp1d
+
+        values = self.empty_theta.copy()
+        values[self.slice] = theta
+        if self.log:
+            values = np.power(10, values)
+        return interp1d(self.x_points, values, "linear", bounds_error=False, fill_value="extrapolate")(self.x)
+
+
+class MeshPlasma:
+    """lineshapes.py:304-329."""
+
+    def __init__(self, x=None, bounds=None, zero_bounds_ne=11, zero_bounds_te=-2, bounds_ne=(11, 16), bounds_te=(-1, 2)):
+        self.electron_density = MeshLine(x=x, zero_bounds=zero_bounds_ne, x_ends=bounds, log=True,
+                                         bounds=[list(bounds_ne) for _ in x])
+        self.electron_temperature = MeshLine(x=x, zero_bounds=zero_bounds_te, x_ends=bounds, log=True,
+                                             bounds=[list(bounds_te) for _ in x])
+
+
+def bowman_tee_distribution(x, theta):
+    """lineshapes.py:332-343."""
+    A, x0, sigma0, q, nu, k, f, b = theta
+    sigma = sigma0 * np.exp(f * np.tanh(k * (x - x0)))
+    z = np.power(abs((x - x0) / sigma), q)
+    return A * np.power(1 + z / nu, -(nu + 1) * 0.5) + b
+
+
+class BowmanTeeProfile:
+    """BowmanTeeNe / BowmanTeeTe, lineshapes.py:354-376: ``10**`` of the peak (and of the background level when
+    ``background``), the temperature profile is centred on 0."""
+
+    def __init__(self, x, background, centred):
+        self.x, self.background, self.centred = x, background, centred
+
+    def __call__(self, theta):
+        theta = np.array(theta, dtype=float)
+        if self.background:
+            theta[0] = np.power(10, theta[0])
+            theta[-1] = np.power(10, theta[-1])
+        else:
+            theta[0] = np.power(10, theta[0])
+            theta = np.concatenate((theta, np.zeros(1)))
+        if self.centred:
+            A, sigma0, q, nu, k, f, b = theta
+            theta = [A, 0, sigma0, q, nu, k, f, b]
+        return bowman_tee_distribution(self.x, theta)
+
+
+class BowmanTeePlasma:
+    """lineshapes.py:381-440."""
+
+    def __init__(self, x=None, bounds=None, dr_bounds=(-2, 2), bounds_ne=(11, 16), bounds_te=(-1, 2), background=False):
+        self.x = np.linspace(-15, 25, 500) if x is None else x
+        shape = [[1e-1, 10], [1.2, 3], [1, 5], [1, 50], [0, 2]] if bounds is None else bounds
+        self.background = background
+        self.electron_density = BowmanTeeProfile(self.x, background, centred=False)
+        self.electron_temperature = BowmanTeeProfile(self.x, background, centred=True)
+        b_ne = [list(bounds_ne), list(dr_bounds)] + [list(b) for b in shape]
+        b_te = [list(bounds_te)] + [list(b) for b in shape]
+        if background:
+            b_ne.append([bounds_ne[0], 13.0])
+            b_te.append([bounds_te[0], 0])
+        self.electron_density.bounds, self.electron_temperature.bounds = b_ne, b_te
+        self.electron_density.number_of_variables = len(b_ne)
+        self.electron_temperature.number_of_variables = len(b_te)
+
+
+def curvature(profile):
+    """priors.py:104-107."""
+    grad1 = np.gradient(profile / max(profile))
+    grad2 = np.gradient(grad1)
+    return -sum(np.square(grad2) / np.power((1 + np.square(grad1)), 3))
+
+
 # ---------------------------------------------------------------------------------------------- the oracle
 class OraclePosterior:
     """Stateless restatement of ``BaysarPosterior`` for the default component set."""
 
-    def __init__(self, input_dict, provider, profile_function=None):
+    def __init__(self, input_dict, provider, profile_function=None, curvature=None):
         self.input_dict = input_dict
+        self.curvature = curvature
         self.provider = provider
         d = input_dict
         # ---- PlasmaLine.__init__ (plasmas.py:295-406)
@@ -423,6 +520,8 @@ class OraclePosterior:
     def _build_prior_list(self):
         """posterior.py:108-165 — the default component order after the chords."""
         p = []
+        if self.curvature is not None:  # posterior.py:109-110
+            p.append(("CurvatureCost", dict(scale=self.curvature)))
         if self.calibrate_wavelength:
             for num in range(self.num_chords):
                 inmean = self.chords[num].x_data.mean()
@@ -508,6 +607,7 @@ class OraclePosterior:
         for p, slc in self.slices.items():
             v = theta[slc].flatten()
             if p == "electron_density":
+                st["_theta_electron_density"] = v.copy()
                 v = self.profile_function.electron_density(v)
             elif p == "electron_temperature":
                 v = self.profile_function.electron_temperature(v)
@@ -696,6 +796,11 @@ class OraclePosterior:
     def prior(self, name, args, st, line_scalars):
         """priors.py — the default components (`posterior.py:108-161`)."""
         ne, te = st["electron_density"], st["electron_temperature"]
+        if name == "CurvatureCost":  # priors.py:110-127 (raw theta at the density knots between the fixed end values)
+            fn = self.profile_function.electron_density
+            values = fn.empty_theta.copy()
+            values[fn.slice] = st["_theta_electron_density"]
+            return curvature(values) * args["scale"]
         if name == "StaticElectronPressureCost":  # priors.py:51-64
             pe = te.clip(0.01) * ne.clip(1)
             return sum([low_pass(f, 1, 0.1) for f in pe / 5e15])

@@ -18,10 +18,9 @@ def build_reference_posterior(workload, provider=None, seed=0, plasma_attrs=None
     np.random.seed(seed)  # PlasmaLine.__init__ and init_test draw from the global RNG
     with ref_shim.quiet():
         input_dict = mods["input_functions"].make_input_dict(**kw)
-        profile = None
-        if workload.los is not None:
-            profile = mods["lineshapes"].EsymmtricCauchyPlasma(x=np.array(workload.los, dtype=float))
-        post = mods["posterior"].BaysarPosterior(input_dict=input_dict, profile_function=profile, skip_test=True)
+        profile = workload.make_profile(mods["lineshapes"])
+        post = mods["posterior"].BaysarPosterior(input_dict=input_dict, profile_function=profile, skip_test=True,
+                                                 curvature=getattr(workload, "curvature", None))
     for k, v in (plasma_attrs or {}).items():
         setattr(post.plasma, k, v)
     return post

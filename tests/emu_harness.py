@@ -30,15 +30,14 @@ def host_model(workload, atomic_data=None):
     """Host objects + blob without touching a GPU (BaysarPosterior itself needs one)."""
     from baysar_b200.atomic_data import SyntheticADAS
     from baysar_b200.input_functions import make_input_dict
-    from baysar_b200.lineshapes import EsymmtricCauchyPlasma
+    import baysar_b200.lineshapes as host_ns
     from baysar_b200.model import compile_model
     from baysar_b200.plasmas import PlasmaLine
     from baysar_b200.posterior import build_components, set_sensible_bounds
 
     d = make_input_dict(**workload.input_kwargs)
-    prof = EsymmtricCauchyPlasma(x=workload.los) if workload.los is not None else None
-    plasma = PlasmaLine(d, profile_function=prof, atomic_data=atomic_data or SyntheticADAS())
-    chords, priors = build_components(plasma, d)
+    plasma = PlasmaLine(d, profile_function=workload.make_profile(host_ns), atomic_data=atomic_data or SyntheticADAS())
+    chords, priors = build_components(plasma, d, curvature=workload.curvature)
     set_sensible_bounds(plasma, chords)
     blob, info = compile_model(plasma, chords, priors)
     return plasma, chords, priors, blob, info

@@ -17,14 +17,13 @@ SPECTRA_RTOL = 1e-5
 def gpu_posterior(name):
     from baysar_b200.atomic_data import SyntheticADAS
     from baysar_b200.input_functions import make_input_dict
-    from baysar_b200.lineshapes import EsymmtricCauchyPlasma
+    import baysar_b200.lineshapes as host_ns
     from baysar_b200.posterior import BaysarPosterior
 
     wl = WORKLOADS[name]()
-    prof = EsymmtricCauchyPlasma(x=wl.los) if wl.los is not None else None
     np.random.seed(3)
-    return BaysarPosterior(make_input_dict(**wl.input_kwargs), profile_function=prof, atomic_data=SyntheticADAS(),
-                           skip_test=True), wl
+    return BaysarPosterior(make_input_dict(**wl.input_kwargs), profile_function=wl.make_profile(host_ns),
+                           atomic_data=SyntheticADAS(), skip_test=True, curvature=wl.curvature), wl
 
 
 def oracle_posterior(name):

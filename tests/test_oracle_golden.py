@@ -9,7 +9,8 @@ import pytest
 
 from baysar_b200.atomic_data import SyntheticADAS
 from baysar_b200.input_functions import make_input_dict
-from oracle.numpy_port import EsymmtricCauchyPlasma, OraclePosterior
+import oracle.numpy_port as oracle_ns
+from oracle.numpy_port import OraclePosterior
 
 from .conftest import GOLDEN
 from .workloads import WORKLOADS
@@ -19,8 +20,8 @@ RTOL = 1e-12
 
 def build(name):
     wl = WORKLOADS[name]()
-    prof = EsymmtricCauchyPlasma(x=wl.los) if wl.los is not None else None
-    return OraclePosterior(make_input_dict(**wl.input_kwargs), SyntheticADAS(), prof)
+    return OraclePosterior(make_input_dict(**wl.input_kwargs), SyntheticADAS(), wl.make_profile(oracle_ns),
+                           curvature=wl.curvature)
 
 
 @pytest.mark.parametrize("name", sorted(WORKLOADS))

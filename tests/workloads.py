@@ -12,4 +12,7 @@ WORKLOADS = {
     "multi_calibrated": lambda: configs.multi_species(
         1, flags=dict(calibrate_wavelength=True, calibrate_intensity=True, calibrate_instrument_function=True)),
     "multi_no_doppler": lambda: configs.multi_species(1, flags=dict(doppler_shifts=False)),
+    "multi_bowman": lambda: configs.multi_species_bowman(),
+    "multi_bowman_bg": lambda: configs.multi_species_bowman(background=True),
+    "multi_mesh_curv": lambda: configs.multi_species_mesh(curvature=50.0),
 }
