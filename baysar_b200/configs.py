@@ -191,7 +191,7 @@ def synthetic_sweep(n_los=100, n_lines=20, n_pix=1024, balmer=True):
         line_data["D"] = fresh_line_data()["D"]
         species, ions = ["D", "N"], [["0"], ["1"]]
     kw = dict(wavelength_axis=[wave], experimental_emission=[ems], instrument_function=[gaussian_if(31, 1.2)],
-              emission_constant=[1e11], noise_region=[[wave[5], wave[60]]], species=species, ions=ions,
+              emission_constant=[1e11], noise_region=[[float(wave[5]), float(wave[60])]], species=species, ions=ions,
               line_data=line_data, mystery_lines=None, refine=[0.05], ion_resolved_temperatures=False,
               ion_resolved_tau=True)
     ref = {"electron_density": [14.5, 0.0, 3.0], "electron_temperature": [1.0, 3.0, 1.0], "N_1_dens": [12.5],

@@ -5,34 +5,41 @@
 //
 //     C[theta, j] = sum_k' S[theta, k'] * T[k', j],     T[k', j] = w[j + o - k']   (banded Toeplitz, o = (K_I - 1) / 2)
 //
-// * M = 128 thetas (one TMEM lane each), N = 128 fine-grid outputs per tile, K walks the band in blocks of 32.
+// * M = 128 thetas (one TMEM lane each), N = 128 fine-grid outputs per tile, K walks the band in blocks of 16.
 // * Persistent: one CTA per SM loops over (theta block, output tile) pairs; neighbouring CTAs work on neighbouring
 //   output tiles of the same thetas, so the overlapping parts of their k-ranges are served by L2.
 // * B operand — the Toeplitz tile depends only on (j0 - k0): ALL k-blocks of the band are windows of ONE tall
-//   "master" tile (128 + 32 (n_kb - 1) rows of 32 taps, K-major SWIZZLE_128B, TF32 hi and lo parts), which every
-//   CTA builds once in shared memory (<= 176 KB).  The B descriptor of k-block kb is the master's base plus
-//   4096 (n_kb - 1 - kb) bytes; nothing is generated or copied per k-block.
+//   "master" tile (128 + 16 (n_kb - 1) rows, K-major SWIZZLE_128B; each 128-byte row holds 16 taps as TF32 "hi" parts
+//   and the same 16 taps' TF32 "lo" parts), which every CTA builds once in shared memory (90 KB for a 455-tap
+//   instrument function).  The B descriptor of k-block kb is the master's base plus 2048 (n_kb - 1 - kb) bytes
+//   (+ 64 bytes for the lo half); nothing is generated or copied per k-block.
 // * A operand — the pre-convolution spectra, plain FP32 rows [theta][pitch] in HBM/L2 (zero padded).  A k-block of a
-//   tile (128 rows x 128 bytes) is copied global -> shared with coalesced 16-byte cp.async (each 128-byte line is
-//   touched by exactly one warp instruction; a row-per-thread LDG pattern was measured L1-tag bound at 75 % l1tex
-//   utilisation) into a 2-4 stage ring, XOR-swizzled so that the row-per-thread reads that follow are conflict-free.
-//   Converter threads then own one theta row each: they read 64 bytes, split the values into two TF32 terms
-//   (hi, lo) and write them to TENSOR MEMORY with tcgen05.st; the MMAs take A from TMEM (the .ts form), so the
-//   tensor pipe's only shared-memory reads are the B windows of the master tile.
+//   tile (128 rows x 64 bytes) is copied global -> shared with coalesced 16-byte cp.async (a row-per-thread LDG
+//   pattern was measured L1-tag bound at 75 % l1tex utilisation) into a ring of up to 8 stages, XOR-swizzled so that
+//   the row-per-thread reads that follow are conflict-free.  Converter threads then own one theta row each: they
+//   read 64 bytes, split the values into two TF32 terms (hi, lo) and write them to TENSOR MEMORY with tcgen05.st;
+//   the MMAs take A from TMEM (the .ts form), so the tensor pipe's only shared-memory reads are the B windows.
 // * 3xTF32: hi*hi accumulates in one FP32 TMEM tile, hi*lo + lo*hi in a second one; the epilogue adds them.
 //   TMEM accumulation truncates (measured: signed error mean -2.5e-6, never positive, with one accumulator and
 //   k-blocks in natural order), so (a) the 2^-11-sized cross terms get their own accumulator and (b) k-blocks are
 //   visited from the edges of the band towards its centre: the big contributions arrive last and most roundings
 //   happen while the accumulator is still small.
-// * TMEM map (512 columns): [0,128) accumulator hi*hi, [128,256) accumulator cross terms, [256,512) four A stages of
-//   32 hi + 32 lo columns.
-// * Warp roles: warps 0-7 convert A (warp w: TMEM lanes 32 (w % 4).., k columns 16 (w / 4)..), warps 8-11 run the
-//   epilogue (so the A stages of the next tile fill while the accumulators drain), warp 12 issues the MMAs, warp 13
-//   issues the cp.async copies.  landed[r] (cp.async -> converters), consumed[r] (converters -> loader), full[s]
-//   (converters -> issuer), empty[s] (tcgen05.commit -> converters), acc_full (commit -> epilogue), acc_free
-//   (epilogue -> issuer) mbarriers; no block-wide barrier after the prologue.
-// * Epilogue: tcgen05.ld (32 lanes x 32 columns), clip at the per-theta pre-convolution minimum, trapz partial per
-//   (theta, tile) in float64 (deterministic: summed in tile order by the pixel kernel), FP32 store.
+// * The tensor pipe is the bound: a 128 x 128 x 8 TF32 MMA was measured at ~108 cycles on B200 (the issuing thread
+//   spends its whole time in tcgen05.mma with every other stage removed; N = 96 costs the same as N = 128).  What
+//   the kernel can still lose is the gap between two tiles, while the accumulators are read out: the epilogue
+//   therefore only DRAINS them (tcgen05.ld, add, clip, swizzled st.shared into a 64 KB staging tile) before it
+//   releases them to the MMAs of the next tile, and does the trapz partial sums and the global stores afterwards,
+//   from shared memory, coalesced along the rows.
+// * TMEM map (512 columns): accumulator hi*hi [0,128), accumulator cross terms [128,256), eight A stages of 16 hi +
+//   16 lo columns from 256.
+// * Warp roles: warps 0-7 convert A (two groups of four warps take alternate k-blocks; warp w: TMEM lanes
+//   32 (w % 4)..), warps 8-11 run the epilogue, warp 12 issues the MMAs, warp 13 issues the cp.async copies.
+//   landed[r] (cp.async -> converters), consumed[r] (converters -> loader), full[s] (converters -> issuer),
+//   empty[s] (tcgen05.commit -> converters), acc_full (commit -> epilogue), acc_free (epilogue -> issuer)
+//   mbarriers; no block-wide barrier after the prologue.
+// * Epilogue: clip at the per-theta pre-convolution minimum, trapz partial per (theta, tile) in float64
+//   (deterministic: fixed shuffle tree, summed in a fixed order by the pixel kernel), FP32 store — every column, or
+//   only the columns a static wavelength map reads (compact rows).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -41,28 +48,30 @@ namespace ifc {
 
 constexpr int TILE_M = 128;   // thetas per tile
 constexpr int TILE_N = 128;   // fine-grid outputs per tile
-constexpr int TILE_K = 32;    // TF32 elements per k-block = one 128-byte swizzle row
-constexpr int A_STAGES = 4;     // tensor-memory stages of the split A operand
-constexpr int RING_MAX = 4;     // shared-memory stages of the raw FP32 A tiles (16 KB each): 2..4, what fits
+constexpr int TILE_K = 16;    // TF32 elements per k-block (two 8-deep MMA steps)
+constexpr int A_STAGES = 8;     // tensor-memory stages of the split A operand
+constexpr int RING_MAX = 8;     // shared-memory stages of the raw FP32 A tiles (8 KB each): 2..8, what fits
 constexpr int A_TILE_BYTES = TILE_M * TILE_K * 4;
-constexpr int PRODUCER_WARPS = 8, EPILOGUE_WARPS = 4;
-constexpr int THREADS = (PRODUCER_WARPS + EPILOGUE_WARPS + 2) * 32;  // + MMA issuer + loader
+constexpr int CONVERTER_WARPS = 8, EPILOGUE_WARPS = 4;
+constexpr int THREADS = (CONVERTER_WARPS + EPILOGUE_WARPS + 2) * 32;  // + MMA issuer + loader
 constexpr int TMEM_COLS = 512;
 constexpr int TMEM_ACC1 = TILE_N;          // cross-term accumulator
 constexpr int TMEM_A = 2 * TILE_N;         // first A stage
-constexpr int MAX_KB = 21;                 // master tile <= 768 rows x 128 B x 2 = 196 608 bytes (+ 32 KB ring)
+constexpr int TMEM_A_STAGE = 2 * TILE_K;   // columns per A stage (hi, then lo)
+constexpr int MAX_KB = 64;                 // master tile <= 1136 rows x 128 B (+ 64 KB staging + ring >= 2 stages)
+constexpr int STAGING_BYTES = TILE_M * TILE_N * 4;  // epilogue staging tile (64 KB)
 constexpr size_t SMEM_LIMIT = 232448;      // 227 KB of dynamic shared memory per CTA
 
 struct Params {
   const float* s;         // [n_rows][pitch]  FP32 spectra, zero padded: column pad_left + k'
   int64_t pitch;          // floats per row (multiple of 32)
-  int pad_left;           // multiple of 32
+  int pad_left;           // multiple of 16
   int F;                  // valid outputs per row
   int n_row_blocks;       // blocks of 128 rows (workspace rows beyond the batch hold stale but finite data)
-  int m_lo, m_hi;         // k-blocks k0 = j0 + 32 * m for m in [m_lo, m_hi]
-  const float* taps_rev;  // [2][4][taps_len]: rev[i] = w[x_max - i], x_max = 127 + o - 32 m_lo (zero outside the tap
-                          // window), TF32 hi then lo, each in 4 element-shifted copies copy_s[i] = rev[i + s]
-  int taps_len;           // multiple of 4, >= 164 + 32 (m_hi - m_lo)
+  int m_lo, m_hi;         // k-blocks k0 = j0 + 16 * m for m in [m_lo, m_hi]
+  const float* taps_rev;  // [2][4][taps_len]: rev[i] = w[x_max - i], x_max = TILE_N - 1 + o - 16 m_lo (zero outside the
+                          // tap window), TF32 hi then lo, each in 4 element-shifted copies copy_s[i] = rev[i + s]
+  int taps_len;           // multiple of 4, >= TILE_N + 16 (m_hi - m_lo) + 20
   const float* row_min;   // [n_rows] clip level (pre-convolution minimum), may be nullptr
   const double* aux;      // alternative source of the clip level: aux[row][8], element 1 (rows < aux_rows), may be nullptr
   int aux_rows;
@@ -76,8 +85,8 @@ struct Params {
   const int* cbase;       // [n_tiles * 4] number of needed columns before word w
   float* out_c;           // [n_rows][out_c_pitch]
   int64_t out_c_pitch;
-  int debug;              // timing experiments only (wrong results): &3: MMA mix; 4: no A loads; 8: no output stores;
-                          // 16: no tcgen05.st
+  int debug;              // timing experiments only (wrong results): 1: one MMA per k-step; 4: no A loads; 8: no output
+                          // stores; 16: no tcgen05.st
   long long* dbg_cycles;  // optional [gridDim.x][8] cycles spent waiting per role (timing experiments)
 };
 
@@ -110,6 +119,18 @@ __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, 
   } else {
     mbar_wait(bar, parity);
   }
+}
+
+// one elected lane of a converged warp (the compiler then issues tcgen05 instructions without a per-lane loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits
@@ -179,7 +200,8 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 
 inline int master_rows(int n_kb) { return TILE_N + TILE_K * (n_kb - 1); }
 inline size_t smem_fixed(int n_kb) {
-  return (size_t)2 * master_rows(n_kb) * 128 + (2 * A_STAGES + 2 * RING_MAX + 2) * sizeof(uint64_t) + 16 + 1024;  // + alignment slack
+  return (size_t)master_rows(n_kb) * 128 + STAGING_BYTES + (2 * A_STAGES + 2 * RING_MAX + 2) * sizeof(uint64_t) + 16 +
+         1024;  // + alignment slack
 }
 inline int ring_stages(int n_kb) {
   const long room = (long)SMEM_LIMIT - (long)smem_fixed(n_kb);
@@ -188,51 +210,55 @@ inline int ring_stages(int n_kb) {
 }
 inline size_t smem_bytes(int n_kb) { return smem_fixed(n_kb) + (size_t)ring_stages(n_kb) * A_TILE_BYTES; }
 
+// byte offset of (row, 16-byte chunk 0..3) inside a ring stage (128 rows x 64 bytes): rows two apart share a bank
+// quad, the XOR spreads a quarter-warp's eight row-per-thread reads over all eight 16-byte bank groups
+__device__ __forceinline__ uint32_t ring_off(int row, int chunk) { return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
+
 template <bool DEBUG>
 __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
   const int dbg_mode = DEBUG ? p.debug : 0;  // timing experiments compile away in the production instantiation
   extern __shared__ unsigned char smem_dyn[];
-  // carve (1024-byte aligned): master_hi | master_lo | A ring | barriers | TMEM slot
+  // carve (1024-byte aligned): master | epilogue staging | A ring | barriers | TMEM slot
   unsigned char* smem_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   const int n_kb = p.m_hi - p.m_lo + 1;
   const int R = TILE_N + TILE_K * (n_kb - 1);
-  unsigned char* master_hi = smem_raw;
-  unsigned char* master_lo = smem_raw + (size_t)R * 128;
-  unsigned char* ring = smem_raw + (size_t)2 * R * 128;
+  unsigned char* master = smem_raw;
+  unsigned char* staging = smem_raw + (size_t)R * 128;
+  unsigned char* ring = staging + STAGING_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)p.ring * A_TILE_BYTES);
-  uint64_t* landed = full + A_STAGES + A_STAGES + 2;
-  uint64_t* consumed = landed + RING_MAX;
   uint64_t* empty = full + A_STAGES;
   uint64_t* acc_full = empty + A_STAGES;
   uint64_t* acc_free = acc_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1 + 2 * RING_MAX);
+  uint64_t* landed = acc_free + 1;         // [RING_MAX]
+  uint64_t* consumed = landed + RING_MAX;  // [RING_MAX]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(consumed + RING_MAX);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t total_tiles = (int64_t)p.n_row_blocks * p.n_tiles;
   const int64_t my_tiles = total_tiles > blockIdx.x ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  // ---- prologue: master Toeplitz tile.  Row rho, chunk q holds the taps rev[base - rho + 4 q + (0..3)]
+  // ---- prologue: master Toeplitz tile.  Row rho: chunks 0-3 hold the hi parts of the taps rev[base - rho + (0..15)],
+  // chunks 4-7 the lo parts of the same taps.
   {
-    const int base = 127 + TILE_K * (n_kb - 1);
-    for (int c = tid; c < R * 8; c += THREADS) {
-      const int rho = c >> 3, q = c & 7;
+    const int base = TILE_N - 1 + TILE_K * (n_kb - 1);
+    for (int c = tid; c < R * 4; c += THREADS) {
+      const int rho = c >> 2, q = c & 3;
       const int idx = base - rho + 4 * q;
       const int sh = idx & 3;
       const float4 hi = *reinterpret_cast<const float4*>(p.taps_rev + (size_t)sh * p.taps_len + (idx - sh));
       const float4 lo = *reinterpret_cast<const float4*>(p.taps_rev + (size_t)(4 + sh) * p.taps_len + (idx - sh));
-      const uint32_t off = swz(rho, q);
-      *reinterpret_cast<float4*>(master_hi + off) = hi;
-      *reinterpret_cast<float4*>(master_lo + off) = lo;
+      *reinterpret_cast<float4*>(master + swz(rho, q)) = hi;
+      *reinterpret_cast<float4*>(master + swz(rho, 4 + q)) = lo;
     }
   }
   if (tid == 0) {
-    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&full[s], PRODUCER_WARPS); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&full[s], CONVERTER_WARPS / 2); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1);
     mbar_init(acc_free, EPILOGUE_WARPS);
-    for (int r = 0; r < RING_MAX; ++r) { mbar_init(&landed[r], 32); mbar_init(&consumed[r], PRODUCER_WARPS); }
+    for (int r = 0; r < RING_MAX; ++r) { mbar_init(&landed[r], 32); mbar_init(&consumed[r], CONVERTER_WARPS / 2); }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
-  if (warp == PRODUCER_WARPS + EPILOGUE_WARPS) {
+  if (warp == CONVERTER_WARPS + EPILOGUE_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -242,27 +268,28 @@ __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_d = *tmem_slot;
 
-  if (warp < PRODUCER_WARPS) {
+  if (warp < CONVERTER_WARPS) {
     // ===================== A converters: ring (shared memory) -> TF32 split -> tensor memory =====================
-    // Software pipelined: the tcgen05.st of k-block g completes (wait::st) while k-block g + 1 is read and split, so
-    // full[] of k-block g is signalled one iteration late; the four TMEM stages absorb the delay.
-    const int quad = warp & 3, khalf = warp >> 2;
+    // Group `grp` (warps 4 grp .. 4 grp + 3) takes the k-block iterations g = grp, grp + 2, ...  Software pipelined:
+    // the tcgen05.st of an iteration completes (wait::st) while the group's next k-block is read and split, so full[]
+    // is signalled one group iteration late; the four TMEM stages absorb the delay.
+    const int quad = warp & 3, grp = warp >> 2;
     const int row_in_tile = quad * 32 + lane;
     const int64_t iters = my_tiles * n_kb;
-    const uint32_t lane_base = tmem_d + ((uint32_t)(quad * 32) << 16) + TMEM_A + 16 * khalf;
-    int r = 0;
-    uint32_t r_phase = 0;
+    const uint32_t lane_base = tmem_d + ((uint32_t)(quad * 32) << 16) + TMEM_A;
+    int r = grp % p.ring;
+    uint32_t r_phase = (uint32_t)((grp / p.ring) & 1);
     int d_pending = -1;
     long long w_landed = 0, w_empty = 0, w_st = 0;
     const long long t_begin = DEBUG ? clock64() : 0;
-    for (int64_t g = 0; g < iters; ++g) {
+    for (int64_t g = grp; g < iters; g += 2) {
       const int d = (int)(g % A_STAGES);
       mbar_wait_timed<DEBUG>(&landed[r], r_phase, w_landed);
-      // this thread's 16 floats of its theta row: chunks 4 khalf .. 4 khalf + 3 of the swizzled 128-byte row
+      // this thread's 16 floats of its theta row (the whole 64-byte row of the stage)
       float4 raw[4];
       const unsigned char* row_ptr = ring + (size_t)r * A_TILE_BYTES;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) raw[c] = *reinterpret_cast<const float4*>(row_ptr + swz(row_in_tile, 4 * khalf + c));
+      for (int c = 0; c < 4; ++c) raw[c] = *reinterpret_cast<const float4*>(row_ptr + ring_off(row_in_tile, c));
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -273,7 +300,7 @@ __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&consumed[r]);  // this warp has read ring stage r (the loader may refill it)
-      if (d_pending >= 0) {                      // k-block g - 1 is in tensor memory: hand it to the MMA issuer
+      if (d_pending >= 0) {                      // the group's previous k-block is in tensor memory: hand it over
         const long long t0 = DEBUG ? clock64() : 0;
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         if (DEBUG) w_st += clock64() - t0;
@@ -286,11 +313,12 @@ __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
         asm volatile("tcgen05.fence::after_thread_sync;");
       }
       if (!(dbg_mode & 16)) {
-        tmem_st16(lane_base + 64 * d, hi);
-        tmem_st16(lane_base + 64 * d + 32, lo);
+        tmem_st16(lane_base + TMEM_A_STAGE * d, hi);
+        tmem_st16(lane_base + TMEM_A_STAGE * d + TILE_K, lo);
       }
       d_pending = d;
-      if (++r == p.ring) { r = 0; r_phase ^= 1u; }
+      r += 2;
+      if (r >= p.ring) { r -= p.ring; r_phase ^= 1u; }
     }
     if (d_pending >= 0) {
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -302,10 +330,10 @@ __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
       long long* o = p.dbg_cycles + (int64_t)blockIdx.x * 8;
       o[0] = w_landed; o[1] = w_empty; o[2] = w_st; o[3] = clock64() - t_begin;
     }
-  } else if (warp == PRODUCER_WARPS + EPILOGUE_WARPS + 1) {
+  } else if (warp == CONVERTER_WARPS + EPILOGUE_WARPS + 1) {
     // ===================== A loader (warp 13): global -> ring with coalesced 16-byte cp.async =====================
-    // Lane l copies the 16-byte chunk (l & 7) of rows (l >> 3) + 4 q, q = 0..31: every warp instruction covers four
-    // whole 128-byte lines.  k-block iterations of this CTA's tiles run back to back.
+    // Lane l copies the 16-byte chunk (l & 3) of rows (l >> 2) + 8 q, q = 0..15: every warp instruction covers eight
+    // whole 64-byte row segments.  k-block iterations of this CTA's tiles run back to back.
     int r = 0;
     uint32_t r_phase = 0;
     int64_t g = 0;
@@ -313,16 +341,16 @@ __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
     for (int64_t q = 0; q < my_tiles; ++q) {
       const int64_t t = blockIdx.x + q * gridDim.x;
       const int rb = (int)(t / p.n_tiles), nt = (int)(t - (int64_t)rb * p.n_tiles);
-      const float* base = p.s + (int64_t)(rb * TILE_M + (lane >> 3)) * p.pitch + p.pad_left + nt * TILE_N + TILE_K * p.m_lo + 4 * (lane & 7);
+      const float* base = p.s + (int64_t)(rb * TILE_M + (lane >> 2)) * p.pitch + p.pad_left + nt * TILE_N + TILE_K * p.m_lo + 4 * (lane & 3);
       for (int i = 0; i < n_kb; ++i, ++g) {
-        if (g >= p.ring) mbar_wait_timed<DEBUG>(&consumed[r], r_phase ^ 1u, w_consumed);  // all converter warps have read the previous use
+        if (g >= p.ring) mbar_wait_timed<DEBUG>(&consumed[r], r_phase ^ 1u, w_consumed);  // previous use has been read
         const float* src = base + TILE_K * kb_order(i, n_kb);
         unsigned char* dst = ring + (size_t)r * A_TILE_BYTES;
 #pragma unroll 8
-        for (int qq = 0; qq < ((dbg_mode & 4) ? 0 : 32); ++qq) {
-          const int row = (lane >> 3) + 4 * qq;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + swz(row, lane & 7))),
-                       "l"(src + (int64_t)(4 * qq) * p.pitch) : "memory");
+        for (int qq = 0; qq < ((dbg_mode & 4) ? 0 : 16); ++qq) {
+          const int row = (lane >> 2) + 8 * qq;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + ring_off(row, lane & 3))),
+                       "l"(src + (int64_t)(8 * qq) * p.pitch) : "memory");
         }
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&landed[r])) : "memory");
         if (++r == p.ring) { r = 0; r_phase ^= 1u; }
@@ -330,87 +358,101 @@ __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     if (DEBUG && p.dbg_cycles && lane == 0) p.dbg_cycles[(int64_t)blockIdx.x * 8 + 4] = w_consumed;
-  } else if (warp < PRODUCER_WARPS + EPILOGUE_WARPS) {
-    // ===================== epilogue (warps 8-11): TMEM -> registers -> add accumulators, clip, trapz -> global ====
+  } else if (warp < CONVERTER_WARPS + EPILOGUE_WARPS) {
+    // ===================== epilogue (warps 8-11) =====================
+    // Phase 1 (accumulators busy): TMEM -> registers, add the two accumulators, clip, st.shared into the staging tile
+    // (row r, 16-byte chunk c at chunk position c ^ (r & 31): conflict-free for the row-per-thread writes and for the
+    // row-per-warp reads), then release the accumulators.  Phase 2: trapz partial and global stores from shared memory.
     const int quad = warp & 3;
     long long w_accfull = 0;
     for (int64_t q = 0; q < my_tiles; ++q) {
       const int64_t t = blockIdx.x + q * gridDim.x;
       const int rb = (int)(t / p.n_tiles), nt = (int)(t - (int64_t)rb * p.n_tiles);
       const int j0 = nt * TILE_N;
-      const int row = rb * TILE_M + quad * 32 + lane;
-      float clip = -3.402823466e38f;
-      if (p.row_min) clip = p.row_min[row];
-      else if (p.aux && row < p.aux_rows) clip = (float)p.aux[(int64_t)row * 8 + 1];
-      float* orow = p.out + (int64_t)row * p.out_pitch;
-      double part = 0.0;
-      mbar_wait_timed<DEBUG>(acc_full, (uint32_t)(q & 1), w_accfull);
-      asm volatile("tcgen05.fence::after_thread_sync;");
+      const int my_row = quad * 32 + lane;
+      {
+        const int row = rb * TILE_M + my_row;
+        float clip = -3.402823466e38f;
+        if (p.row_min) clip = p.row_min[row];
+        else if (p.aux && row < p.aux_rows) clip = (float)p.aux[(int64_t)row * 8 + 1];
+        mbar_wait_timed<DEBUG>(acc_full, (uint32_t)(q & 1), w_accfull);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        unsigned char* srow = staging + (size_t)my_row * (TILE_N * 4);
 #pragma unroll 1
-      for (int c0 = 0; c0 < TILE_N; c0 += 32) {
-        uint32_t v[32], u[32];
-        const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
-        tmem_ld32(taddr, v);
-        tmem_ld32(taddr + TMEM_ACC1, u);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + 32 == TILE_N) {  // accumulators are in registers: the next tile's MMAs may start
-          asm volatile("tcgen05.fence::before_thread_sync;");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_free);
-        }
-        const bool interior = j0 > 0 && j0 + TILE_N < p.F;  // unit trapz weights, no bounds
-        uint32_t need = 0xffffffffu;
-        float* crow = nullptr;
-        if (p.cmask) {
-          const int w = (j0 + c0) >> 5;
-          need = p.cmask[w];
-          crow = p.out_c + (int64_t)row * p.out_c_pitch + p.cbase[w];
-        }
+        for (int c0 = 0; c0 < TILE_N; c0 += 32) {
+          uint32_t v[32], u[32];
+          const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
+          tmem_ld32(taddr, v);
+          tmem_ld32(taddr + TMEM_ACC1, u);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int e4 = 0; e4 < 32; e4 += 4) {
-          float f[4];
-          if (interior) {
+          for (int e4 = 0; e4 < 32; e4 += 4) {
+            float f[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float x = __uint_as_float(v[e4 + e]) + __uint_as_float(u[e4 + e]);
               f[e] = x < clip ? clip : x;
             }
-            part += (double)((f[0] + f[1]) + (f[2] + f[3]));
-          } else {
-            float psum = 0.f;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float x = __uint_as_float(v[e4 + e]) + __uint_as_float(u[e4 + e]);
-              x = x < clip ? clip : x;
-              f[e] = x;
-              const int j = j0 + c0 + e4 + e;
-              if (j < p.F) {
-                if (j == 0 || j == p.F - 1) part += 0.5 * (double)x; else psum += x;
-              }
-            }
-            part += (double)psum;
-          }
-          if (dbg_mode & 8) {
-          } else if (crow) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (need & (1u << (e4 + e))) crow[__popc(need & ((1u << (e4 + e)) - 1u))] = f[e];
-          } else if (interior || j0 + c0 + e4 < p.F) {
-            *reinterpret_cast<float4*>(orow + j0 + c0 + e4) = make_float4(f[0], f[1], f[2], f[3]);
+            const int chunk = (c0 + e4) >> 2;
+            *reinterpret_cast<float4*>(srow + (((chunk ^ (my_row & 31))) << 4)) = make_float4(f[0], f[1], f[2], f[3]);
           }
         }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncwarp();  // also orders this warp's staging writes before its reads below
+        if (lane == 0) mbar_arrive(acc_free);  // the MMAs of the next tile may overwrite the accumulators
       }
-      if (p.trapz_part) p.trapz_part[(int64_t)row * p.n_tiles + nt] = part;
+      // ---- phase 2: this warp's 32 rows, one row per iteration, lane l holds columns 4 l .. 4 l + 3
+      const bool interior = j0 > 0 && j0 + TILE_N < p.F;  // unit trapz weights, no bounds
+      uint32_t need = 0xffffffffu;
+      int cb = 0;
+      if (p.cmask) {
+        const int w = (j0 + 4 * lane) >> 5;
+        need = p.cmask[w];
+        cb = p.cbase[w];
+      }
+      const int bit0 = (4 * lane) & 31;
+      for (int rr = 0; rr < 32; ++rr) {
+        const int trow = quad * 32 + rr;
+        const int row = rb * TILE_M + trow;
+        const float4 f4 = *reinterpret_cast<const float4*>(staging + (size_t)trow * (TILE_N * 4) + ((lane ^ (trow & 31)) << 4));
+        const float f[4] = {f4.x, f4.y, f4.z, f4.w};
+        const int jc = j0 + 4 * lane;
+        double ps;
+        if (interior) {
+          ps = (double)((f[0] + f[1]) + (f[2] + f[3]));
+        } else {
+          ps = 0.0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = jc + e;
+            if (j < p.F) ps += ((j == 0 || j == p.F - 1) ? 0.5 : 1.0) * (double)f[e];
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+        if (lane == 0 && p.trapz_part) p.trapz_part[(int64_t)row * p.n_tiles + nt] = ps;
+        if (dbg_mode & 8) {
+        } else if (p.cmask) {
+          float* crow = p.out_c + (int64_t)row * p.out_c_pitch + cb;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (need & (1u << (bit0 + e))) crow[__popc(need & ((1u << (bit0 + e)) - 1u))] = f[e];
+        } else if (interior || jc < p.F) {
+          *reinterpret_cast<float4*>(p.out + (int64_t)row * p.out_pitch + jc) = f4;
+        }
+      }
+      __syncwarp();  // staging rows are rewritten by the next tile's phase 1
     }
-    if (DEBUG && p.dbg_cycles && warp == PRODUCER_WARPS && lane == 0) p.dbg_cycles[(int64_t)blockIdx.x * 8 + 5] = w_accfull;
-  } else if (warp == PRODUCER_WARPS + EPILOGUE_WARPS) {
+    if (DEBUG && p.dbg_cycles && warp == CONVERTER_WARPS && lane == 0) p.dbg_cycles[(int64_t)blockIdx.x * 8 + 5] = w_accfull;
+  } else if (warp == CONVERTER_WARPS + EPILOGUE_WARPS) {
     // ===================== MMA issuer (warp 12) =====================
     const uint32_t idesc = make_idesc(TILE_N);
-    const uint32_t mh = smem_u32(master_hi), ml = smem_u32(master_lo);
+    const uint32_t mb = smem_u32(master);
     int64_t g = 0;
     long long w_full = 0, w_accfree = 0;
     for (int64_t q = 0; q < my_tiles; ++q) {
-      if (q > 0) {  // the epilogue has read the accumulators of the previous tile
+      const uint32_t acc0 = tmem_d, acc1 = tmem_d + TMEM_ACC1;
+      if (q >= 1) {  // the epilogue has drained the accumulators of the previous tile
         mbar_wait_timed<DEBUG>(acc_free, (uint32_t)((q - 1) & 1), w_accfree);
         asm volatile("tcgen05.fence::after_thread_sync;");
       }
@@ -418,25 +460,18 @@ __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
         const int s = (int)(g % A_STAGES);
         mbar_wait_timed<DEBUG>(&full[s], (uint32_t)((g / A_STAGES) & 1), w_full);
         asm volatile("tcgen05.fence::after_thread_sync;");
-        if (lane == 0) {
+        if (elect_one()) {
           const int kb = kb_order(i, n_kb);
-          const uint32_t boff = (uint32_t)(4096 * (n_kb - 1 - kb));
-          const uint64_t d_bhi = make_desc(mh + boff), d_blo = make_desc(ml + boff);
-          const uint32_t a_hi = tmem_d + TMEM_A + 64 * s, a_lo = a_hi + 32;
+          const uint64_t d_bhi = make_desc(mb + (uint32_t)(2048 * (n_kb - 1 - kb)));
+          const uint64_t d_blo = d_bhi + (uint64_t)(64 >> 4);  // lo parts: second half of each 128-byte row
+          const uint32_t a_hi = tmem_d + TMEM_A + TMEM_A_STAGE * s, a_lo = a_hi + TILE_K;
 #pragma unroll
           for (int ks = 0; ks < TILE_K / 8; ++ks) {
             const uint64_t adv = (uint64_t)((ks * 8 * 4) >> 4);  // 32 bytes per k-step inside the 128-byte swizzle row
-            if ((dbg_mode & 3) == 0) {
-              mma_tf32_ts(tmem_d, a_hi + 8 * ks, d_bhi + adv, idesc, (i | ks) ? 1u : 0u);
-              mma_tf32_ts(tmem_d + TMEM_ACC1, a_hi + 8 * ks, d_blo + adv, idesc, (i | ks) ? 1u : 0u);
-              mma_tf32_ts(tmem_d + TMEM_ACC1, a_lo + 8 * ks, d_bhi + adv, idesc, 1u);
-            } else if ((dbg_mode & 3) == 1) {
-              mma_tf32_ts(tmem_d, a_hi + 8 * ks, d_bhi + adv, idesc, (i | ks) ? 1u : 0u);
-            } else if ((dbg_mode & 3) == 2) {
-              mma_tf32_ts(tmem_d, a_hi + 8 * ks, d_bhi + adv, make_idesc(2 * TILE_N), (i | ks) ? 1u : 0u);
-              mma_tf32_ts(tmem_d + TMEM_ACC1, a_lo + 8 * ks, d_bhi + adv, idesc, 1u);
-            } else if ((dbg_mode & 3) == 3) {
-              mma_tf32_ts(tmem_d, a_hi + 8 * ks, d_bhi + adv, make_idesc(2 * TILE_N), (i | ks) ? 1u : 0u);
+            mma_tf32_ts(acc0, a_hi + 8 * ks, d_bhi + adv, idesc, (i | ks) ? 1u : 0u);
+            if ((dbg_mode & 3) != 1) {
+              mma_tf32_ts(acc1, a_hi + 8 * ks, d_blo + adv, idesc, (i | ks) ? 1u : 0u);
+              mma_tf32_ts(acc1, a_lo + 8 * ks, d_bhi + adv, idesc, 1u);
             }
           }
           // frees this A stage when the MMAs above (and all earlier ones) have completed
@@ -455,7 +490,7 @@ __global__ void __launch_bounds__(THREADS, 1) if_contract_kernel(Params p) {
 
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
-  if (warp == PRODUCER_WARPS + EPILOGUE_WARPS)
+  if (warp == CONVERTER_WARPS + EPILOGUE_WARPS)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS));
 }
 

@@ -13,6 +13,7 @@ PKG = pathlib.Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB_PATH = PKG / "libbaysar_b200.so"
 LINE_STRIDE = 16  # BAYSAR_LINE_STRIDE (include/baysar_b200.h)
+IFC_TILE_N = 128  # ifc::TILE_N (csrc/if_contract.cuh): fine-grid outputs per contraction tile
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--compiler-options", "-fPIC", "-shared"]
 
@@ -104,8 +105,8 @@ def debug_if_contract(spectra, taps, row_min=None):
     spectra = spectra.contiguous()
     n, F = spectra.shape
     taps = np.ascontiguousarray(taps, dtype=np.float64)
-    n_tiles = -(-F // 128)
-    out = torch.empty((n, n_tiles * 128), dtype=torch.float32, device=spectra.device)
+    n_tiles = -(-F // IFC_TILE_N)
+    out = torch.empty((n, n_tiles * IFC_TILE_N), dtype=torch.float32, device=spectra.device)
     part = torch.empty((n, n_tiles), dtype=torch.float64, device=spectra.device)
     pitch, tiles, ms = ctypes.c_int64(), ctypes.c_int(), ctypes.c_float()
     rc = lib.baysar_debug_if_contract(spectra.data_ptr(), n, F, taps.ctypes.data, len(taps),

@@ -168,7 +168,7 @@ def flop_model(post):
     (dense +-256-point window, every 16th point on the tails) and 14 flop + 1 MUFU per fine-grid point in sweep 2;
     Balmer lines with a multi-tap Doppler kernel 18 F + 2 taps F flop and 3 F MUFU; Gaussian components 8 flop + 1
     MUFU per point of their +-8.85 sigma window; 14 F + 12 P of bookkeeping and (fused path only) the instrument
-    convolution at 2 flop per tap and output.  contract (tensor pipe, 3xTF32): per 128x128 output tile and 32-wide
+    convolution at 2 flop per tap and output.  contract (tensor pipe, 3xTF32): per 128x128 output tile and 16-wide
     k-block three 128x128x8 MMAs per 8-deep k-step, including the zero part of the Toeplitz tiles."""
     from baysar_b200.spectrometers import BalmerHydrogenLine
 
@@ -203,9 +203,9 @@ def flop_model(post):
         mufu += pts_g + P
         if tensor_path:
             o = (len(inst) - 1) // 2
-            n_kb = (127 + o - k_lo) // 32 - (o - k_hi + 1) // 32 + 1
+            n_kb = (127 + o - k_lo) // 16 - (o - k_hi + 1) // 16 + 1   # 16-wide k-blocks per 128-output tile
             n_tiles = -(-F // 128)
-            contract += n_tiles * n_kb * 4 * 3 * 2.0 * (128 * 128 * 8) / 128.0
+            contract += n_tiles * n_kb * 2 * 3 * 2.0 * (128 * 128 * 8) / 128.0
         else:
             chord += 2.0 * nq_if * F
         dense += 8.0 * n_g * F + n_b * 2 * (10.0 * F + 2.0 * k_d * F + 3.0 * F) + 12.0 * F + 10.0 * P \
