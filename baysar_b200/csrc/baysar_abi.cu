@@ -270,6 +270,20 @@ int ensure_ifc_workspace(baysar_model* m, int64_t n) {
   return 0;
 }
 
+// Launch the chord kernel with the register budget that matches how many CTAs the shared-memory footprint lets an SM hold
+template <int MODE>
+int launch_chord_kernel(baysar_model* m, const ChordArgs& a, dim3 grid, cudaStream_t stream) {
+  constexpr int NT = 256;
+  static const int cap = getenv("BAYSAR_CHORD_MINB") ? atoi(getenv("BAYSAR_CHORD_MINB")) : 5;
+  const int by_smem = (int)((size_t)232448 / (m->chord_smem_max + 1024));
+  const int minb = by_smem < cap ? by_smem : cap;
+  auto kern = minb >= 5 ? chord_stage_kernel<NT, MODE, 5> : (minb == 4 ? chord_stage_kernel<NT, MODE, 4> : chord_stage_kernel<NT, MODE, 3>);
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->chord_smem_max));
+  kern<<<grid, NT, m->chord_smem_max, stream>>>(m->dev, a);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // stage tags for the optional event log
 enum { ST_BEGIN = -1, ST_LOS = 0, ST_CHORD = 1, ST_CONTRACT = 2, ST_PIXEL = 3, ST_FINAL = 4, ST_COUNT = 5 };
 
@@ -295,11 +309,8 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
     ChordArgs a{};
     a.theta = theta; a.n = n; a.chord_begin = chord_begin; a.lines = lines; a.components = comps;
     a.spectra = spectra; a.fine_pre = fine_pre; a.fine_post = fine_post; a.status = status;
-    CUDA_OK(cudaFuncSetAttribute(chord_stage_kernel<NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)m->chord_smem_max));
     dim3 grid((unsigned)n, (unsigned)n_chords);
-    chord_stage_kernel<NT, 0><<<grid, NT, m->chord_smem_max, stream>>>(m->dev, a);
-    CUDA_OK(cudaGetLastError());
+    if (launch_chord_kernel<0>(m, a, grid, stream)) return 1;
     m->last_launches += 1;
     if (mark(m, ST_CHORD, stream)) return 1;
     return 0;
@@ -312,10 +323,7 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
       ChordArgs a{};
       a.theta = theta; a.n = n; a.chord_begin = c; a.lines = lines; a.components = comps;
       a.spectra = spectra; a.fine_pre = fine_pre; a.fine_post = fine_post; a.status = status;
-      CUDA_OK(cudaFuncSetAttribute(chord_stage_kernel<NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)m->chord_smem_max));
-      chord_stage_kernel<NT, 0><<<dim3((unsigned)n, 1), NT, m->chord_smem_max, stream>>>(m->dev, a);
-      CUDA_OK(cudaGetLastError());
+      if (launch_chord_kernel<0>(m, a, dim3((unsigned)n, 1), stream)) return 1;
       m->last_launches += 1;
       if (mark(m, ST_CHORD, stream)) return 1;
       continue;
@@ -331,10 +339,7 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
       a.fine_pre = fine_pre ? fine_pre + r0 * F : nullptr; a.fine_post = nullptr; a.status = status + r0;
       a.spec = m->spec; a.split_pitch = pl.pitch; a.split_pad = pl.pad_left;
       a.aux = m->aux;
-      CUDA_OK(cudaFuncSetAttribute(chord_stage_kernel<NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)m->chord_smem_max));
-      chord_stage_kernel<NT, 1><<<dim3((unsigned)rows, 1), NT, m->chord_smem_max, stream>>>(m->dev, a);
-      CUDA_OK(cudaGetLastError());
+      if (launch_chord_kernel<1>(m, a, dim3((unsigned)rows, 1), stream)) return 1;
       if (mark(m, ST_CHORD, stream)) return 1;
       // K2b: tcgen05 contraction with the banded-Toeplitz instrument matrix
       ifc::Params p{};

@@ -220,14 +220,13 @@ BAYSAR_DEV void pixel_likelihood(const ModelDev& m, const int* ch, const double*
   if (tid == 0) components[n * (int64_t)ncomp_cols + c] = -red4[0];
 }
 
-#ifndef BAYSAR_CHORD_MIN_BLOCKS
-#define BAYSAR_CHORD_MIN_BLOCKS 3  // 3 CTAs (24 warps) per SM: caps the kernel at 80 registers, no spills
-#endif
+// MINB = resident CTAs per SM the register allocation aims at: 3 (80 registers) when the shared-memory footprint allows
+// no more (long fine grids), 4 (64 registers, no spills) or 5 (48 registers, 16 bytes of spills) for short grids.
 // MODE 0: fused (spectrum -> instrument convolution on the FP32 pipe -> likelihood, everything in shared memory).
-// MODE 1: spectral stage only: writes the TF32-split pre-convolution spectrum and the per-theta scalars for the
-//         tensor-core contraction (if_contract.cuh) and the pixel stage (pixel_stage_kernel below).
-template <int NT, int MODE>
-__global__ void __launch_bounds__(NT, BAYSAR_CHORD_MIN_BLOCKS) chord_stage_kernel(ModelDev m, ChordArgs a) {
+// MODE 1: spectral stage only: writes the pre-convolution spectrum and the per-theta scalars for the tensor-core
+//         contraction (if_contract.cuh) and the pixel stage (pixel_stage_kernel below).
+template <int NT, int MODE, int MINB = 3>
+__global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, ChordArgs a) {
 #ifdef BAYSAR_CPU_EMU
   unsigned char* chord_smem_raw = emu_dynamic_smem();
 #else

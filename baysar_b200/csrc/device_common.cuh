@@ -136,8 +136,12 @@ BAYSAR_DEV void bspline_basis3(const double* t, int n, double x, int& l, double*
   double tb = t[k], te = t[n - k - 1];
   if (x < tb) x = tb;
   if (x > te) x = te;
-  int lo = k;
-  while (lo < n - k - 2 && x >= t[lo + 1]) ++lo;
+  // largest l in [k, n - k - 2] with t[l] <= x (FITPACK's forward scan, as a bisection)
+  int lo = k, hi = n - k - 2;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (x >= t[mid]) lo = mid; else hi = mid - 1;
+  }
   l = lo;
   double hh[3];
   h[0] = 1.0;
@@ -154,18 +158,26 @@ BAYSAR_DEV void bspline_basis3(const double* t, int n, double x, int& l, double*
   }
 }
 
-BAYSAR_DEV double bspline_eval(const double* c, int ncy, int lx, int ly, const double* hx, const double* hy) {
-  // sum_i hx[i] (sum_j c[i][j] hy[j]): 20 fused multiply-adds (FITPACK's fpbisp forms the same sum term by term)
-  double sp = 0.0;
-  const double* base = c + (int64_t)(lx - 3) * ncy + (ly - 3);
+// Two tau slices at once: c holds (slice i, slice i + 1) coefficient pairs.  sum_i hx[i] (sum_j c[i][j] hy[j]) per slice:
+// 2 x 20 fused multiply-adds from 16 sixteen-byte loads (FITPACK's fpbisp forms the same sums term by term).
+// hx / hy are strided (structure-of-arrays basis cache: element q of LOS point l at q * stride + l).
+struct Double2 { double x, y; };
+BAYSAR_DEV void bspline_eval_pair(const double* c, int ncy, int lx, int ly, const double* hx, const double* hy, int stride,
+                                  double& vi, double& vj) {
+  const Double2* base = reinterpret_cast<const Double2*>(c) + (int64_t)(lx - 3) * ncy + (ly - 3);
+  double si = 0.0, sj = 0.0;
+  const double y0 = hy[0], y1 = hy[stride], y2 = hy[2 * stride], y3 = hy[3 * stride];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    double row = base[i * ncy] * hy[0];
-#pragma unroll
-    for (int j = 1; j < 4; ++j) row = fma(base[i * ncy + j], hy[j], row);
-    sp = fma(row, hx[i], sp);
+    const Double2 c0 = base[i * ncy], c1 = base[i * ncy + 1], c2 = base[i * ncy + 2], c3 = base[i * ncy + 3];
+    const double ri = fma(c3.x, y3, fma(c2.x, y2, fma(c1.x, y1, c0.x * y0)));
+    const double rj = fma(c3.y, y3, fma(c2.y, y2, fma(c1.y, y1, c0.y * y0)));
+    const double xw = hx[i * stride];
+    si = fma(ri, xw, si);
+    sj = fma(rj, xw, sj);
   }
-  return sp;
+  vi = si;
+  vj = sj;
 }
 
 // ---- warp / block reductions ------------------------------------------------------------------------------

@@ -9,7 +9,7 @@
 #define BAYSAR_LAYOUT_H
 
 #define BAYSAR_BLOB_MAGIC 0x4252415359534142LL /* "BAYSYSAB" */
-#define BAYSAR_BLOB_VERSION 5
+#define BAYSAR_BLOB_VERSION 6
 
 enum BaysarSection {
   SEC_I,              /* int64  [I_COUNT]           model-wide integer scalars                         */
@@ -29,7 +29,8 @@ enum BaysarSection {
   SEC_TAU_GRID,       /* double [n_tau]             log10 tau grid ("magical_tau")                     */
   SEC_SPL_TX,         /* double [spl_nx]            bicubic spline knots in ne                         */
   SEC_SPL_TY,         /* double [spl_ny]            bicubic spline knots in Te                         */
-  SEC_SPL_C,          /* double [n_tec][n_tau][(spl_nx-4)*(spl_ny-4)]  B-spline coefficients of log(ne*TEC) */
+  SEC_SPL_C,          /* double [n_tec][n_tau-1][(spl_nx-4)*(spl_ny-4)][2]  B-spline coefficients of log(ne*TEC),
+                         stored as (tau slice i, tau slice i+1) pairs: one 16-byte load serves both slices */
   SEC_UL_I,           /* int32  [n_ulines][UL_I_COUNT]  unique (line-of-sight) lines                    */
   SEC_UL_D,           /* double [n_ulines][UL_D_COUNT]                                                  */
   SEC_PR_I,           /* int32  [n_priors][PR_I_COUNT]                                                  */

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
   double* n0_s = nm_s + L;   // neutral density profile
   double* ha_s = n0_s + L;   // adf15-grid cell weights
   double* hb_s = ha_s + L;
-  double* bx_s = hb_s + L;   // [L][4] spline basis in ne
+  double* bx_s = hb_s + L;   // [4][L] spline basis in ne (structure of arrays: conflict-free across lanes)
   double* by_s = bx_s + 4 * L;
   int* hi_s = (int*)(by_s + 4 * L);
   int* hj_s = hi_s + L;
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       bspline_basis3(m.spl_ty, sny, te_s[l], ly, hy);
       lx_s[l] = lx; ly_s[l] = ly;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { bx_s[4 * l + q] = hx[q]; by_s[4 * l + q] = hy[q]; }
+      for (int q = 0; q < 4; ++q) { bx_s[q * L + l] = hx[q]; by_s[q * L + l] = hy[q]; }
     }
   }
   __syncwarp();
@@ -278,14 +278,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       const double ti_ = m.tau_grid[i], tj_ = m.tau_grid[j];
       const double i_w = 1.0 + (lt - ti_) / (ti_ - tj_), j_w = 1.0 + (tj_ - lt) / (ti_ - tj_);
       const int ncx = snx - 4, ncy = sny - 4;
-      const double* ci_ = m.spl_c + ((int64_t)ul[UL_TAB_A] * n_tau + i) * ncx * ncy;
-      const double* cj_ = m.spl_c + ((int64_t)ul[UL_TAB_A] * n_tau + j) * ncx * ncy;
+      // coefficient pairs of tau slices (j - 1, j); the out-of-grid case j = 0 (flagged) reads pair 0
+      const int pair = j > 0 ? j - 1 : 0;
+      const double* cpair = m.spl_c + ((int64_t)ul[UL_TAB_A] * (n_tau - 1) + pair) * ncx * ncy * 2;
       double s[5] = {0, 0, 0, 0, 0};
       for (int l = lane; l < L; l += 32) {
         double ne = ne_s[l], te = te_s[l];
         double n0 = dens * (ne / nemax);
-        double vi = bspline_eval(ci_, ncy, lx_s[l], ly_s[l], bx_s + 4 * l, by_s + 4 * l);
-        double vj = bspline_eval(cj_, ncy, lx_s[l], ly_s[l], bx_s + 4 * l, by_s + 4 * l);
+        double vi, vj;
+        bspline_eval_pair(cpair, ncy, lx_s[l], ly_s[l], bx_s + l, by_s + l, L, vi, vj);
         double tec = nan_to_num(exp(vi) * i_w + exp(vj) * j_w);
         double p = clip_lo(n0 * tec, 1.0);
         s[0] += p; s[1] += m.los_w[l] * p; s[2] += p * ne; s[3] += p * (n0 / ne); s[4] += p * te;

@@ -143,7 +143,9 @@ def compile_model(plasma, chords, priors):
         tecs.append(coeffs)
     if tecs:
         tx, ty = plasma.tec_knots
-        sec["SEC_SPL_TX"], sec["SEC_SPL_TY"], sec["SEC_SPL_C"] = tx, ty, np.array(tecs)
+        c = np.array(tecs)  # [n_tec][n_tau][cells]
+        pairs = np.stack([c[:, :-1, :], c[:, 1:, :]], axis=-1)  # [n_tec][n_tau - 1][cells][2]: slices (i, i + 1)
+        sec["SEC_SPL_TX"], sec["SEC_SPL_TY"], sec["SEC_SPL_C"] = tx, ty, np.ascontiguousarray(pairs)
         iset("I_SPL_NX", len(tx)), iset("I_SPL_NY", len(ty))
         if np.array(tecs).shape[-1] != (len(tx) - 4) * (len(ty) - 4):
             raise ValueError("unexpected spline coefficient count")
