@@ -10,6 +10,7 @@
 
 #include "../../include/baysar_b200.h"
 #include "chord_stage.cuh"
+#include "ensemble.cuh"
 #include "finalize.cuh"
 #include "if_contract.cuh"
 #include "los_stage.cuh"
@@ -69,7 +70,8 @@ struct baysar_model {
   double* theta_stage = nullptr;  // for the *_host entry point
   double* logp_stage = nullptr;
   int64_t stage_cap = 0;
-  size_t chord_smem_max = 0;
+  size_t chord_smem_max = 0;            // fused launches covering several chords
+  std::vector<size_t> chord_smem;       // per chord (the tensor path's spectral stage may drop buffer B)
   // tensor-core path (if_contract.cuh): per chord plan (empty taps_rev = chord stays on the fused kernel)
   std::vector<IfcPlan> ifc;
   std::vector<float*> ifc_taps_dev;
@@ -272,14 +274,14 @@ int ensure_ifc_workspace(baysar_model* m, int64_t n) {
 
 // Launch the chord kernel with the register budget that matches how many CTAs the shared-memory footprint lets an SM hold
 template <int MODE>
-int launch_chord_kernel(baysar_model* m, const ChordArgs& a, dim3 grid, cudaStream_t stream) {
+int launch_chord_kernel(baysar_model* m, const ChordArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
   constexpr int NT = 256;
   static const int cap = getenv("BAYSAR_CHORD_MINB") ? atoi(getenv("BAYSAR_CHORD_MINB")) : 5;
-  const int by_smem = (int)((size_t)232448 / (m->chord_smem_max + 1024));
+  const int by_smem = (int)((size_t)232448 / (smem + 1024));
   const int minb = by_smem < cap ? by_smem : cap;
   auto kern = minb >= 5 ? chord_stage_kernel<NT, MODE, 5> : (minb == 4 ? chord_stage_kernel<NT, MODE, 4> : chord_stage_kernel<NT, MODE, 3>);
-  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->chord_smem_max));
-  kern<<<grid, NT, m->chord_smem_max, stream>>>(m->dev, a);
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, NT, smem, stream>>>(m->dev, a);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -310,7 +312,7 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
     a.theta = theta; a.n = n; a.chord_begin = chord_begin; a.lines = lines; a.components = comps;
     a.spectra = spectra; a.fine_pre = fine_pre; a.fine_post = fine_post; a.status = status;
     dim3 grid((unsigned)n, (unsigned)n_chords);
-    if (launch_chord_kernel<0>(m, a, grid, stream)) return 1;
+    if (launch_chord_kernel<0>(m, a, grid, m->chord_smem_max, stream)) return 1;
     m->last_launches += 1;
     if (mark(m, ST_CHORD, stream)) return 1;
     return 0;
@@ -323,7 +325,7 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
       ChordArgs a{};
       a.theta = theta; a.n = n; a.chord_begin = c; a.lines = lines; a.components = comps;
       a.spectra = spectra; a.fine_pre = fine_pre; a.fine_post = fine_post; a.status = status;
-      if (launch_chord_kernel<0>(m, a, dim3((unsigned)n, 1), stream)) return 1;
+      if (launch_chord_kernel<0>(m, a, dim3((unsigned)n, 1), m->chord_smem[c], stream)) return 1;
       m->last_launches += 1;
       if (mark(m, ST_CHORD, stream)) return 1;
       continue;
@@ -339,7 +341,7 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
       a.fine_pre = fine_pre ? fine_pre + r0 * F : nullptr; a.fine_post = nullptr; a.status = status + r0;
       a.spec = m->spec; a.split_pitch = pl.pitch; a.split_pad = pl.pad_left;
       a.aux = m->aux;
-      if (launch_chord_kernel<1>(m, a, dim3((unsigned)rows, 1), stream)) return 1;
+      if (launch_chord_kernel<1>(m, a, dim3((unsigned)rows, 1), m->chord_smem[c], stream)) return 1;
       if (mark(m, ST_CHORD, stream)) return 1;
       // K2b: tcgen05 contraction with the banded-Toeplitz instrument matrix
       ifc::Params p{};
@@ -461,6 +463,7 @@ int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar
     if (ch[CH_HALO] % 4 != 0) { baysar_model_destroy(m); return fail("CH_HALO must be a multiple of 4"); }
     ChordSmem s = chord_smem_layout(ch[CH_F], ch[CH_HALO], ch[CH_TAPS_MAX], kd_max);
     smem_max = s.total > smem_max ? s.total : smem_max;
+    m->chord_smem.push_back(s.total);
   }
   if (smem_max > 227 * 1024) {
     baysar_model_destroy(m);
@@ -494,6 +497,14 @@ int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar
       e2 = cudaMemcpy(m->ifc_taps_dev[c], pl.taps_rev.data(), sizeof(float) * pl.taps_rev.size(), cudaMemcpyHostToDevice);
     if (e2 != cudaSuccess) { baysar_model_destroy(m); return fail(std::string("ifc taps upload: ") + cudaGetErrorString(e2)); }
     m->any_ifc = true;
+    if (ch[CH_B_OPTIONAL]) {  // MODE 1 never touches buffer B on this chord
+      int kd_max = 0;
+      for (int k = 0; k < ch[CH_N_LINES]; ++k) {
+        int kd = m->cl_i[(ch[CH_LINE_OFF] + k) * CL_I_COUNT + CL_KD];
+        kd_max = kd > kd_max ? kd : kd_max;
+      }
+      m->chord_smem[c] = chord_smem_layout(ch[CH_F], ch[CH_HALO], ch[CH_TAPS_MAX], kd_max, 0).total;
+    }
     if (ch[CH_CALWAVE_IDX] < 0) {  // static wavelength map: the pixel stage reads columns i_p and i_p + 1 only
       IfcPlan& plw = m->ifc[c];
       const int words = plw.n_tiles * (ifc::TILE_N / 32);
@@ -722,6 +733,31 @@ int baysar_debug_if_contract(const float* spectra_dev, int64_t n_rows, int F, co
     cudaFree(dbg);
   }
   cudaFree(spec); cudaFree(taps);
+  return 0;
+}
+
+int baysar_stretch_propose(const double* walkers, const double* complement, int n_params, int64_t n_walkers,
+                           int64_t n_complement, double a, uint64_t seed, uint64_t step, double* proposal,
+                           double* log_factor, void* stream_) {
+  if (!walkers || !complement || !proposal || !log_factor) return fail("null argument");
+  if (n_params < 1 || n_complement < 1 || !(a > 1.0)) return fail("bad stretch-move arguments");
+  if (n_walkers <= 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ens::stretch_propose_kernel<<<(unsigned)((n_walkers + 127) / 128), 128, 0, stream>>>(
+      walkers, complement, n_params, n_walkers, n_complement, a, seed, step, proposal, log_factor);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int baysar_stretch_accept(double* walkers, double* logp, const double* proposal, const double* logp_new,
+                          const double* log_factor, const uint32_t* status_new, int n_params, int64_t n_walkers,
+                          uint64_t seed, uint64_t step, unsigned long long* n_accepted, void* stream_) {
+  if (!walkers || !logp || !proposal || !logp_new || !log_factor) return fail("null argument");
+  if (n_walkers <= 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ens::stretch_accept_kernel<<<(unsigned)((n_walkers + 127) / 128), 128, 0, stream>>>(
+      walkers, logp, proposal, logp_new, log_factor, status_new, n_params, n_walkers, seed, step, n_accepted);
+  CUDA_OK(cudaGetLastError());
   return 0;
 }
 

@@ -74,14 +74,14 @@ struct ChordSmem {
   size_t total;        // bytes
 };
 
-__host__ __device__ static inline ChordSmem chord_smem_layout(int F, int halo, int taps_max, int kd_max) {
+__host__ __device__ static inline ChordSmem chord_smem_layout(int F, int halo, int taps_max, int kd_max, int need_b = 1) {
   ChordSmem s;
   int f8 = (F + 7) / 8 * 8;
   int logical = f8 + 2 * halo + 16;
   s.buf_floats = (size_t)(logical + 8 + 3) / 4 * 4;
   s.taps_floats = (size_t)(taps_max + 8 + 3) / 4 * 4;
   s.tapd_doubles = 2 * (size_t)kd_max + 4;
-  s.total = 2 * s.buf_floats * sizeof(float) + s.taps_floats * sizeof(float) + s.tapd_doubles * sizeof(double) +
+  s.total = (need_b ? 2 : 1) * s.buf_floats * sizeof(float) + s.taps_floats * sizeof(float) + s.tapd_doubles * sizeof(double) +
             192 * sizeof(double) + 16 * sizeof(int) + 8 * BAYSAR_MAX_FUSED_LINES * sizeof(double);
   s.total = (s.total + 15) / 16 * 16;
   return s;
@@ -251,11 +251,13 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
     int kd = m.cl_i[(ch[CH_LINE_OFF] + k) * CL_I_COUNT + CL_KD];
     kd_max = kd > kd_max ? kd : kd_max;
   }
-  const ChordSmem lay = chord_smem_layout(F, HALO, TAPS_MAX, kd_max);
+  // buffer B (scratch / convolved spectrum) is left out when the tensor-core path's spectral stage cannot need it
+  const bool need_b = MODE == 0 || ch[CH_B_OPTIONAL] == 0;
+  const ChordSmem lay = chord_smem_layout(F, HALO, TAPS_MAX, kd_max, need_b ? 1 : 0);
   const int f8 = (F + 7) / 8 * 8;
   float* bufA = reinterpret_cast<float*>(chord_smem_raw);
   float* bufB = bufA + lay.buf_floats;
-  float* tapq = bufB + lay.buf_floats;
+  float* tapq = bufA + (need_b ? 2 : 1) * lay.buf_floats;
   double* tapd = reinterpret_cast<double*>(tapq + lay.taps_floats);  // [kd_max] taps, then [kd_max + 1] prefix sums
   double* tappre = tapd + kd_max;
   double* scratch = tappre + kd_max + 4;  // 192 doubles: [0,128) block_sum (up to 16 values x 8 warps), [128,132) edge64
@@ -268,8 +270,10 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
 
   uint32_t st = 0;
   for (size_t i = tid; i < lay.buf_floats; i += NT) bufA[i] = 0.f;
-  for (int i = tid; i < HALO; i += NT) bufB[pad_index(i)] = 0.f;                       // left halo of B
-  for (int i = HALO + F + tid; i < (int)lay.buf_floats; i += NT) bufB[pad_index(i)] = 0.f;  // tail + right halo of B
+  if (need_b) {
+    for (int i = tid; i < HALO; i += NT) bufB[pad_index(i)] = 0.f;                       // left halo of B
+    for (int i = HALO + F + tid; i < (int)lay.buf_floats; i += NT) bufB[pad_index(i)] = 0.f;  // tail + right halo of B
+  }
   __syncthreads();
 
   const double cal = ch[CH_CAL_IDX] >= 0 ? pow(10.0, th[ch[CH_CAL_IDX]]) : 1.0;
@@ -545,6 +549,7 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
         }
       }
       if (nf > 0) flush_fused(false);  // keep the (float) summation order of the lines deterministic
+      if (!need_b) { st |= 1u << 16; continue; }  // cannot happen: the host guarantees single-tap lines (CH_B_OPTIONAL)
       // tap window |z| <= Z_CUT
       if (tid == 0) { iscr[0] = KD; iscr[1] = -1; }
       __syncthreads();

@@ -9,7 +9,7 @@
 #define BAYSAR_LAYOUT_H
 
 #define BAYSAR_BLOB_MAGIC 0x4252415359534142LL /* "BAYSYSAB" */
-#define BAYSAR_BLOB_VERSION 6
+#define BAYSAR_BLOB_VERSION 7
 
 enum BaysarSection {
   SEC_I,              /* int64  [I_COUNT]           model-wide integer scalars                         */
@@ -156,6 +156,8 @@ enum BaysarChI {
   CH_IF_OFF,
   CH_HALO,       /* zero padding (multiple of 4) on each side of the fine-grid shared-memory buffers */
   CH_TAPS_MAX,   /* capacity of the shared-memory tap buffer */
+  CH_B_OPTIONAL, /* 1: no Gaussian components and every Balmer line is a guaranteed single Doppler tap, so the
+                    spectral stage of the tensor-core path needs no second fine-grid buffer */
   CH_I_COUNT
 };
 enum BaysarChD {

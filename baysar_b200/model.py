@@ -50,6 +50,31 @@ def _theta_index(plasma, tag):
     return plasma.slices[tag].start if tag in plasma.slices else -1
 
 
+def _single_tap_guaranteed(plasma, chord):
+    """True if the chord has only Balmer lines whose Doppler kernel is one tap for EVERY theta inside the bounds (cold
+    neutrals: sigma depends on theta only through the Doppler shift of the centre).  Mirrors the kernel's block-uniform
+    test (csrc/chord_stage.cuh): centre tap inside 6.9 sigma, both neighbours outside, with a 1e-3 margin on sigma."""
+    if not chord.lines or not plasma.cold_neutrals:
+        return False
+    for line in chord.lines:
+        if not isinstance(line, BalmerHydrogenLine):
+            return False
+        taps = np.asarray(line.wavelengths_doppler, dtype=float)
+        KD = len(taps)
+        if KD < 3:
+            return False
+        o = (KD - 1) // 2
+        zc = np.abs(taps[o - 1:o + 2] - line.cwl)
+        tag = line.species + "_velocity"
+        vmax = 1e3 * np.abs(plasma.theta_bounds[plasma.slices[tag].start]).max() if tag in plasma.slices else 0.0
+        cw = line.cwl * np.array([1 - vmax / 299792458.0, 1 + vmax / 299792458.0])
+        sigma = cw * 7.715e-5 * np.sqrt(0.01 / line.atomic_mass) * FWHM_TO_SIGMA
+        lo, hi = 6.9 * sigma.min() * (1 - 1e-3), 6.9 * sigma.max() * (1 + 1e-3)
+        if not (zc[1] <= lo and zc[0] > hi and zc[2] > hi):
+            return False
+    return True
+
+
 def compile_model(plasma, chords, priors):
     """-> (blob bytes, info dict).  ``priors``: the prior descriptors in posterior_components order."""
     e = ENUMS
@@ -271,6 +296,7 @@ def compile_model(plasma, chords, priors):
             cl_d_rows.append(cd)
             line_ulines.append(u)
         info["chord_line_uline"].append(line_ulines)
+        row[E_CH_I["CH_B_OPTIONAL"]] = int(_single_tap_guaranteed(plasma, chord))
         row[E_CH_I["CH_HALO"]] = (half + 4 + 3) // 4 * 4
         row[E_CH_I["CH_TAPS_MAX"]] = taps_needed + 8
 

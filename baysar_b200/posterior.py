@@ -252,6 +252,34 @@ class BaysarPosterior:
         self.last_status_device = status
         return (logp, status) if return_status else logp
 
+    def gradient(self, theta, step=None):
+        """Finite-difference gradient of logP at one theta from ONE batched launch of 2 n_params evaluations.
+
+        The reference's optimisers obtain gradients from scipy's ``approx_grad=True`` (`posterior.py:492-498`,
+        `optimisation.py:84-101`): n + 1 sequential posterior calls per gradient.  Here the shifted thetas form one
+        batch.  Central differences; ``step`` is per parameter (scalar or vector), default 1e-3 of each parameter's
+        bound range — the spectral stage computes in float32, so scipy's forward step of 1e-8 would only measure
+        rounding noise.  Samples whose evaluation raises in the reference (status != 0) give NaN components.
+        """
+        theta = np.asarray(theta, dtype=float)
+        n = self.plasma.n_params
+        if theta.shape != (n,):
+            raise ValueError("len(theta)!=self.n_params")
+        tb = np.asarray(self.plasma.theta_bounds, dtype=float)
+        h = 1e-3 * (tb[:, 1] - tb[:, 0]) if step is None else np.broadcast_to(np.asarray(step, dtype=float), (n,)).copy()
+        batch = np.repeat(theta[None], 2 * n, axis=0)
+        batch[np.arange(n), np.arange(n)] += h
+        batch[n + np.arange(n), np.arange(n)] -= h
+        logp, status = self.logp_batch(batch, return_status=True)
+        logp = logp.cpu().numpy()
+        bad = status.cpu().numpy() != 0
+        logp[bad] = np.nan
+        return (logp[:n] - logp[n:]) / (2 * h)
+
+    def cost_gradient(self, theta, step=None):
+        """``-gradient``: what `baysar/optimisation.py:84-92` passes to L-BFGS-B as ``fprime`` when it exists."""
+        return -self.gradient(theta, step)
+
     def components_batch(self, theta):
         """-> (components [N, n_chords + n_priors], status) as numpy arrays, reference posterior_components order."""
         _, status, comps = self.model.eval_logp(self._as_device(theta), want_components=True)

@@ -111,6 +111,23 @@ int baysar_debug_if_contract(const float* spectra_dev, int64_t n_rows, int F, co
 const char* baysar_last_error(void);
 const char* baysar_version(void);
 
+/*
+ * Affine-invariant ensemble step on the device (stretch move, red/blue split) — the caller of the batched posterior
+ * for large walker counts; replaces what emcee's EnsembleSampler does on the host between two posterior calls
+ * (reference caller: tulasa/fitting.py:1275-1304).  Philox4x32-10, counter (walker, step, draw), key = seed.
+ *   propose: proposal[s] = c + z (x_s - c), z = ((a - 1) u + 1)^2 / a, c uniform in `complement`;
+ *            log_factor[s] = (n_params - 1) ln z
+ *   accept:  x_s, logp[s] <- proposal, logp_new[s] if ln u' < log_factor + logp_new - logp and the proposal evaluated
+ *            cleanly (status_new[s] == 0, finite logp_new); n_accepted (device counter, may be NULL) += acceptances
+ * All pointers are device pointers.
+ */
+int baysar_stretch_propose(const double* walkers, const double* complement, int n_params, int64_t n_walkers,
+                           int64_t n_complement, double a, uint64_t seed, uint64_t step, double* proposal,
+                           double* log_factor, void* stream);
+int baysar_stretch_accept(double* walkers, double* logp, const double* proposal, const double* logp_new,
+                          const double* log_factor, const uint32_t* status_new, int n_params, int64_t n_walkers,
+                          uint64_t seed, uint64_t step, unsigned long long* n_accepted, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

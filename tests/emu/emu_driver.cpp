@@ -45,7 +45,7 @@ extern "C" int emu_eval_split(const unsigned char* blob, const double* theta, lo
       int kd = m.cl_i[(ch[CH_LINE_OFF] + k) * CL_I_COUNT + CL_KD];
       kd_max = kd > kd_max ? kd : kd_max;
     }
-    ChordSmem s = chord_smem_layout(F, ch[CH_HALO], ch[CH_TAPS_MAX], kd_max);
+    ChordSmem s = chord_smem_layout(F, ch[CH_HALO], ch[CH_TAPS_MAX], kd_max, ch[CH_B_OPTIONAL] ? 0 : 1);
     const int pad = 64, n_tiles = (F + 127) / 128;
     const int64_t pitch = pad + F + 96, cpitch = (int64_t)n_tiles * 128;
     std::vector<float> spec(n * pitch, 7.f), conv(n * cpitch, 0.f);

@@ -244,3 +244,23 @@ def test_tensor_core_path_multi_chord_and_row_chunks():
         for c in range(2):
             spec, _ = small.spectra_batch(theta[i:i + 1], c)
             np.testing.assert_allclose(spec[0], ref["spectra"][c], rtol=SPECTRA_RTOL)
+
+
+def test_batched_finite_difference_gradient(posteriors):
+    """posterior.gradient: one batched launch of 2 n evaluations reproduces the oracle's central differences."""
+    post, wl = posteriors("multi_species")
+    oracle = oracle_posterior("multi_species")
+    z = np.load(GOLDEN / "multi_species.npz")
+    theta = z["theta"][0]
+    grad = post.gradient(theta)
+    tb = np.asarray(oracle.theta_bounds, dtype=float)
+    h = 1e-3 * (tb[:, 1] - tb[:, 0])
+    ref = np.zeros(len(theta))
+    for k in range(len(theta)):
+        up, dn = theta.copy(), theta.copy()
+        up[k] += h[k]
+        dn[k] -= h[k]
+        ref[k] = (oracle.evaluate(up)["logp"] - oracle.evaluate(dn)["logp"]) / (2 * h[k])
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(grad, ref, rtol=2e-3, atol=2e-4 * scale)
+    np.testing.assert_allclose(post.cost_gradient(theta), -grad)
