@@ -14,6 +14,7 @@
 #include "finalize.cuh"
 #include "if_contract.cuh"
 #include "los_stage.cuh"
+#include "mma_probe.cuh"
 
 static thread_local std::string g_last_error;
 
@@ -758,6 +759,37 @@ int baysar_stretch_accept(double* walkers, double* logp, const double* proposal,
   ens::stretch_accept_kernel<<<(unsigned)((n_walkers + 127) / 128), 128, 0, stream>>>(
       walkers, logp, proposal, logp_new, log_factor, status_new, n_params, n_walkers, seed, step, n_accepted);
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int baysar_debug_mma_probe(int device, int tile_n, int form, int n_acc_hi, int b_stages, int pattern, int iters,
+                           double* cycles_per_mma) {
+  if (!cycles_per_mma) return fail("null argument");
+  if (tile_n < 8 || tile_n > 256 || tile_n % 8 || n_acc_hi < 1 || (n_acc_hi + 1) * tile_n > 512 || b_stages < 1 ||
+      b_stages > 4 || iters < 1)
+    return fail("bad probe arguments");
+  CUDA_OK(cudaSetDevice(device));
+  int sms = 0;
+  CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  long long* out = nullptr;
+  CUDA_OK(cudaMalloc(&out, sizeof(long long) * sms));
+  CUDA_OK(cudaMemset(out, 0, sizeof(long long) * sms));
+  const size_t smem = (size_t)4 * 256 * 128 + 128 * 128 + 1024;
+  CUDA_OK(cudaFuncSetAttribute(mmaprobe::mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int rep = 0; rep < 2; ++rep) {
+    mmaprobe::mma_probe_kernel<<<sms, 128, smem>>>(tile_n, form, n_acc_hi, b_stages, pattern, iters, out);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaDeviceSynchronize());
+  }
+  std::vector<long long> h(sms);
+  CUDA_OK(cudaMemcpy(h.data(), out, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+  cudaFree(out);
+  double worst = 0.0;
+  for (long long c : h) {
+    if (c < 0) return fail("probe timed out");
+    worst = (double)c > worst ? (double)c : worst;
+  }
+  *cycles_per_mma = worst / ((double)iters * (pattern == 2 ? 2.0 : 6.0));
   return 0;
 }
 

@@ -71,6 +71,8 @@ def library():
     lib.baysar_debug_if_contract.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp, ctypes.POINTER(i64),
                                              ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_float)]
     lib.baysar_debug_if_contract.restype = i32
+    lib.baysar_debug_mma_probe.argtypes = [i32, i32, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_double)]
+    lib.baysar_debug_mma_probe.restype = i32
     u64 = ctypes.c_uint64
     lib.baysar_stretch_propose.argtypes = [vp, vp, i32, i64, i64, ctypes.c_double, u64, u64, vp, vp, vp]
     lib.baysar_stretch_propose.restype = i32
@@ -84,7 +86,8 @@ def library():
 
 EXPORTED_SYMBOLS = ["baysar_model_create", "baysar_model_destroy", "baysar_model_query", "baysar_eval_logp",
                     "baysar_eval_spectra", "baysar_eval_lines", "baysar_eval_logp_host", "baysar_last_error",
-                    "baysar_version", "baysar_stretch_propose", "baysar_stretch_accept", "baysar_model_set_profiling", "baysar_model_get_profile", "baysar_microbench", "baysar_debug_if_contract"]
+                    "baysar_version", "baysar_stretch_propose", "baysar_stretch_accept", "baysar_model_set_profiling", "baysar_model_get_profile", "baysar_microbench", "baysar_debug_if_contract",
+                    "baysar_debug_mma_probe"]
 
 
 def microbench(device=0):

@@ -108,6 +108,12 @@ int baysar_debug_if_contract(const float* spectra_dev, int64_t n_rows, int F, co
                              const float* row_min_dev, float* out_dev, double* trapz_dev, int64_t* out_pitch,
                              int* n_tiles, float* elapsed_ms);
 
+/* Issue-rate probe of kind::tf32 tcgen05.mma (csrc/mma_probe.cuh): cycles per 128 x tile_n x 8 MMA, slowest SM, for the
+ * contraction kernels' issue pattern on constant operands.  form 0 = A from tensor memory, 1 = A from shared memory;
+ * pattern 0 = kernels' pattern, 1 = one accumulator, 2 = hi*hi only. */
+int baysar_debug_mma_probe(int device, int tile_n, int form, int n_acc_hi, int b_stages, int pattern, int iters,
+                           double* cycles_per_mma);
+
 const char* baysar_last_error(void);
 const char* baysar_version(void);
 
