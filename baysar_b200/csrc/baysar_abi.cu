@@ -4,6 +4,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <map>
 #include <new>
 #include <string>
 #include <vector>
@@ -15,6 +17,7 @@
 #include "if_contract.cuh"
 #include "los_stage.cuh"
 #include "mma_probe.cuh"
+#include "pix_contract.cuh"
 
 static thread_local std::string g_last_error;
 
@@ -38,6 +41,28 @@ struct IfcPlan {
   std::vector<uint32_t> cmask;
   std::vector<int> cbase;
   int64_t c_pitch = 0;
+};
+
+// Host-side plan of the folded pixel contraction (pix_contract.cuh) of one chord: column tiles with their bands, the
+// zero-padded tap table, the end-zone weights of the area identity, and per-batch-size schedules.
+struct PxcSchedule {
+  int ctas = 0, slots = 0;
+  int *d_sched = nullptr, *d_cnt = nullptr;
+};
+struct PxcPlan {
+  bool on = false;
+  int tn = 128, pad_left = 0, n_col_tiles = 0, wlen = 0, ring = 0;
+  int e_l = 0, e_r = 0, x_l = 0, x_r = 0, col_left0 = 0, col_right0 = 0, n_dl = 0, n_dr = 0;
+  int64_t pitch = 0, out_pitch = 0;
+  double wsum = 0.0;
+  std::vector<int> tile_kcol0, tile_nkb, tile_boff, col_idx, pix_col;
+  int n_fold_tiles = 0;
+  std::vector<float> col_frac, wtab, bbar;  // bbar: per folded tile, sum over its columns of B[s, c] (bias correction)
+  std::vector<double> dtab;
+  int *d_tile_kcol0 = nullptr, *d_tile_nkb = nullptr, *d_tile_boff = nullptr, *d_col_idx = nullptr, *d_pix_col = nullptr;
+  float *d_col_frac = nullptr, *d_wtab = nullptr, *d_bbar = nullptr;
+  double* d_dtab = nullptr;
+  std::map<int, PxcSchedule> schedules;  // by number of theta blocks
 };
 
 static float tf32_round(float v) {  // round to nearest, ties away from zero, 10-bit mantissa (cvt.rna.tf32.f32)
@@ -80,6 +105,7 @@ struct baysar_model {
   std::vector<int*> ifc_cbase_dev;
   float* conv_c = nullptr;
   int64_t conv_c_pitch_max = 0;
+  std::vector<PxcPlan> pxc;  // folded pixel contraction (static wavelength map, non-negative instrument function)
   bool any_ifc = false;
   int64_t ifc_rows = 0;              // rows of the split / conv workspaces (multiple of 128)
   int64_t ifc_budget_bytes = (int64_t)24 << 30;  // HBM budget of those workspaces (BAYSAR_IFC_BUDGET_MB at create)
@@ -212,6 +238,210 @@ IfcPlan make_ifc_plan(const double* w, int KI, int k_lo, int k_hi, int F) {
   return pl;
 }
 
+// Columns of the folded contraction: one per pixel (i_p, a_p), then the explicit fine-grid columns of the two edge
+// zones; every group padded to whole tiles by repeating its last column.
+PxcPlan make_pxc_plan(const double* w, int KI, int k_lo, int k_hi, int F, int P, const int* pix_idx, const double* pix_frac,
+                      int tn) {
+  PxcPlan pl;
+  pl.tn = tn;
+  const int o = (KI - 1) / 2;
+  for (int k = k_lo; k < k_hi; ++k)
+    if (!(w[k] >= 0.0)) return pl;  // the clip argument needs non-negative taps
+  pl.e_l = std::max(0, k_hi - 1 - o);
+  pl.e_r = std::max(0, o - k_lo);
+  pl.x_l = pl.e_l + 1;
+  pl.x_r = pl.e_r + 1;
+  if (F < 4 * (pl.e_l + pl.e_r + 2) + 2 * tn || P < 1) return pl;
+  std::vector<int> ci;
+  std::vector<double> ca;
+  auto pad_group = [&]() { while (ci.size() % tn) { ci.push_back(ci.back()); ca.push_back(ca.back()); } };
+  pl.pix_col.assign(P, -1);
+  for (int p = 0; p < P; ++p) {
+    const int i = std::min(std::max(pix_idx[p], 0), F - 2);
+    const bool edge = pix_idx[p] != i || i < pl.e_l || i + 1 >= F - pl.e_r;
+    if (!edge) pl.pix_col[p] = (int)ci.size();
+    ci.push_back(i);
+    ca.push_back(edge ? 0.0 : pix_frac[p]);
+  }
+  pad_group();
+  pl.col_left0 = (int)ci.size();
+  for (int j = 0; j < pl.x_l; ++j) { ci.push_back(j); ca.push_back(0.0); }
+  pad_group();
+  pl.col_right0 = (int)ci.size();
+  for (int j = F - pl.x_r; j < F; ++j) { ci.push_back(j); ca.push_back(0.0); }
+  pad_group();
+  pl.n_col_tiles = (int)ci.size() / tn;
+  pl.out_pitch = (int64_t)ci.size();
+  std::vector<int> k0(pl.n_col_tiles);
+  pl.tile_nkb.assign(pl.n_col_tiles, 0);
+  int min_k0 = 0, max_end = F;
+  for (int t = 0; t < pl.n_col_tiles; ++t) {
+    int i_min = F, i_max = 0;
+    for (int c = t * tn; c < (t + 1) * tn; ++c) {
+      i_min = std::min(i_min, ci[c]);
+      i_max = std::max(i_max, ci[c] + (ca[c] != 0.0 ? 1 : 0));
+    }
+    const int s_min = i_min + o - (k_hi - 1), s_max = i_max + o - k_lo;
+    k0[t] = floor_div(s_min, ifc::TILE_K) * ifc::TILE_K;
+    pl.tile_nkb[t] = std::max((s_max - k0[t]) / ifc::TILE_K + 1, pxc::MIN_KB);
+    min_k0 = std::min(min_k0, k0[t]);
+    max_end = std::max(max_end, k0[t] + ifc::TILE_K * pl.tile_nkb[t]);
+  }
+  pl.pad_left = -min_k0;  // multiple of 16
+  pl.pitch = ((int64_t)pl.pad_left + max_end + 31) / 32 * 32;
+  pl.tile_kcol0.resize(pl.n_col_tiles);
+  // tap index of (column c, source s): u = i_c + o - s; the table holds u in [u_base, u_base + wlen)
+  int u_base = 1 << 30, u_top = -(1 << 30);
+  for (int t = 0; t < pl.n_col_tiles; ++t) {
+    pl.tile_kcol0[t] = pl.pad_left + k0[t];
+    for (int c = t * tn; c < (t + 1) * tn; ++c) {
+      u_base = std::min(u_base, ci[c] + o - (k0[t] + ifc::TILE_K * pl.tile_nkb[t] - 1));
+      u_top = std::max(u_top, ci[c] + 1 + o - k0[t]);
+    }
+  }
+  u_base -= 4;  // the builders read five consecutive taps from x - 3
+  pl.wlen = (u_top - u_base + 1 + 4 + 3) / 4 * 4;
+  pl.wtab.assign(pl.wlen, 0.f);
+  for (int x = 0; x < pl.wlen; ++x) {
+    const int u = x + u_base;
+    if (u >= k_lo && u < k_hi) pl.wtab[x] = (float)w[u];
+  }
+  pl.col_idx.resize(ci.size());
+  pl.col_frac.resize(ci.size());
+  for (int t = 0; t < pl.n_col_tiles; ++t)
+    for (int c = t * tn; c < (t + 1) * tn; ++c) {
+      pl.col_idx[c] = ci[c] + o - k0[t] - u_base;
+      pl.col_frac[c] = (float)ca[c];
+    }
+  // area identity: G_s - W c_s at the two ends (exactly zero in between: same summation order as W)
+  double wsum = 0.0;
+  for (int k = k_lo; k < k_hi; ++k) wsum += w[k];
+  pl.wsum = wsum;
+  const int zone = std::min(F / 2, pl.e_l + pl.e_r + 4);
+  auto d_of = [&](int s) {
+    double g = 0.0;
+    for (int k = k_lo; k < k_hi; ++k) {
+      const int j = s - o + k;
+      if (j >= 0 && j < F) g += ((j == 0 || j == F - 1) ? 0.5 : 1.0) * w[k];
+    }
+    return g - wsum * ((s == 0 || s == F - 1) ? 0.5 : 1.0);
+  };
+  std::vector<double> dl(zone), dr(zone);
+  for (int s = 0; s < zone; ++s) { dl[s] = d_of(s); dr[s] = d_of(F - zone + s); }
+  pl.n_dl = zone;
+  while (pl.n_dl > 0 && dl[pl.n_dl - 1] == 0.0) --pl.n_dl;
+  int first = 0;
+  while (first < zone && dr[first] == 0.0) ++first;
+  pl.n_dr = zone - first;
+  pl.dtab.assign(dl.begin(), dl.begin() + pl.n_dl);
+  pl.dtab.insert(pl.dtab.end(), dr.begin() + first, dr.end());
+  // column-sum identity per folded tile (bias correction of the truncating TMEM accumulation, pixel_fold_kernel):
+  //   sum_{c in tile} C[c] = sum_s S_s bbar_s,  bbar_s = sum_{c in tile} B[s, c] over the tile's band (padding
+  //   columns repeat the last pixel and are part of both sides)
+  pl.n_fold_tiles = pl.col_left0 / tn;
+  pl.tile_boff.assign(pl.n_col_tiles, -1);
+  if (pl.n_fold_tiles <= 64) {
+    for (int t = 0; t < pl.n_fold_tiles; ++t) {
+      pl.tile_boff[t] = (int)pl.bbar.size();
+      const int len = ifc::TILE_K * pl.tile_nkb[t];
+      std::vector<double> bb(len, 0.0);
+      for (int c = t * tn; c < (t + 1) * tn; ++c)
+        for (int x = 0; x < len; ++x) {
+          const int idx = pl.col_idx[c] - x;  // the builders' index arithmetic
+          bb[x] += (double)pl.wtab[idx] + (double)pl.col_frac[c] * ((double)pl.wtab[idx + 1] - (double)pl.wtab[idx]);
+        }
+      for (int x = 0; x < len; ++x) pl.bbar.push_back((float)bb[x]);
+    }
+  }
+  if (pl.bbar.empty()) pl.bbar.push_back(0.f);
+  if (pl.dtab.empty()) pl.dtab.push_back(0.0);
+  pl.ring = tn == 64 ? pxc::ring_stages<64>(pl.wlen) : pxc::ring_stages<128>(pl.wlen);
+  pl.on = pl.ring >= 2 && pl.n_col_tiles < 32768;
+  return pl;
+}
+
+template <class T>
+int upload(T** dst, const std::vector<T>& v) {
+  CUDA_OK(cudaMalloc(dst, sizeof(T) * v.size()));
+  CUDA_OK(cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+int upload_pxc_plan(PxcPlan& pl) {
+  if (upload(&pl.d_tile_kcol0, pl.tile_kcol0) || upload(&pl.d_tile_nkb, pl.tile_nkb) || upload(&pl.d_col_idx, pl.col_idx) ||
+      upload(&pl.d_tile_boff, pl.tile_boff) ||
+      upload(&pl.d_pix_col, pl.pix_col) || upload(&pl.d_col_frac, pl.col_frac) || upload(&pl.d_wtab, pl.wtab) ||
+      upload(&pl.d_dtab, pl.dtab) || upload(&pl.d_bbar, pl.bbar))
+    return 1;
+  return 0;
+}
+void free_pxc_plan(PxcPlan& pl) {
+  cudaFree(pl.d_tile_kcol0); cudaFree(pl.d_tile_nkb); cudaFree(pl.d_tile_boff); cudaFree(pl.d_col_idx); cudaFree(pl.d_pix_col);
+  cudaFree(pl.d_col_frac); cudaFree(pl.d_wtab); cudaFree(pl.d_dtab); cudaFree(pl.d_bbar);
+  for (auto& kv : pl.schedules) { cudaFree(kv.second.d_sched); cudaFree(kv.second.d_cnt); }
+  pl.schedules.clear();
+}
+
+// Longest-first deal of the (column tile, theta block) pairs to `sms` persistent CTAs (cost = k-blocks + a constant
+// for the epilogue); a CTA runs its tiles in the order dealt.  Cached per number of theta blocks.
+int pxc_schedule(PxcPlan& pl, int n_rb, int sms, const PxcSchedule** out) {
+  auto it = pl.schedules.find(n_rb);
+  if (it == pl.schedules.end()) {
+    std::vector<int> order(pl.n_col_tiles);
+    for (int t = 0; t < pl.n_col_tiles; ++t) order[t] = t;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pl.tile_nkb[a] > pl.tile_nkb[b]; });
+    const int64_t tiles = (int64_t)n_rb * pl.n_col_tiles;
+    PxcSchedule sc;
+    sc.ctas = (int)std::min<int64_t>(tiles, sms);
+    std::vector<std::vector<int>> lists(sc.ctas);
+    std::vector<int64_t> load(sc.ctas, 0);
+    for (int t : order)
+      for (int rb = 0; rb < n_rb; ++rb) {
+        int best = 0;
+        for (int c = 1; c < sc.ctas; ++c)
+          if (load[c] < load[best]) best = c;
+        lists[best].push_back((t << 16) | rb);
+        load[best] += pl.tile_nkb[t] + 10;
+      }
+    for (auto& l : lists) sc.slots = std::max(sc.slots, (int)l.size());
+    std::vector<int> flat((size_t)sc.ctas * sc.slots, 0), cnt(sc.ctas);
+    for (int c = 0; c < sc.ctas; ++c) {
+      cnt[c] = (int)lists[c].size();
+      std::copy(lists[c].begin(), lists[c].end(), flat.begin() + (size_t)c * sc.slots);
+    }
+    if (upload(&sc.d_sched, flat) || upload(&sc.d_cnt, cnt)) return 1;
+    it = pl.schedules.emplace(n_rb, sc).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+template <int TN, bool TRACE>
+int launch_pxc_t(const pxc::Params& p, int ctas, size_t smem, cudaStream_t stream) {
+  CUDA_OK(cudaFuncSetAttribute(pxc::pix_contract_kernel<TN, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pxc::pix_contract_kernel<TN, TRACE><<<ctas, pxc::THREADS, smem, stream>>>(p);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_pxc(PxcPlan& pl, const float* spec, int n_rb, float* out, double* tsum, int sms, cudaStream_t stream,
+               long long* dbg_cycles = nullptr) {
+  if (n_rb > 65535) return fail("too many theta blocks for one folded contraction launch");
+  const PxcSchedule* sc = nullptr;
+  if (pxc_schedule(pl, n_rb, sms, &sc)) return 1;
+  pxc::Params p{};
+  p.s = spec; p.pitch = pl.pitch; p.tile_kcol0 = pl.d_tile_kcol0; p.tile_nkb = pl.d_tile_nkb; p.col_idx = pl.d_col_idx;
+  p.col_frac = pl.d_col_frac; p.wtab = pl.d_wtab; p.wlen = pl.wlen; p.sched = sc->d_sched; p.sched_cnt = sc->d_cnt;
+  p.sched_slots = sc->slots; p.out = out; p.out_pitch = pl.out_pitch; p.ring = pl.ring; p.dbg_cycles = dbg_cycles;
+  p.bbar = (tsum && pl.n_fold_tiles <= 64) ? pl.d_bbar : nullptr; p.tile_boff = pl.d_tile_boff; p.tsum = tsum;
+  p.n_col_tiles = pl.n_col_tiles;
+  if (pl.tn == 64) {
+    const size_t smem = pxc::smem_bytes<64>(pl.ring, pl.wlen);
+    return dbg_cycles ? launch_pxc_t<64, true>(p, sc->ctas, smem, stream) : launch_pxc_t<64, false>(p, sc->ctas, smem, stream);
+  }
+  const size_t smem = pxc::smem_bytes<128>(pl.ring, pl.wlen);
+  return dbg_cycles ? launch_pxc_t<128, true>(p, sc->ctas, smem, stream) : launch_pxc_t<128, false>(p, sc->ctas, smem, stream);
+}
+
 int ensure_workspace(baysar_model* m, int64_t n) {
   if (n <= m->cap) return 0;
   int64_t cap = n < 1024 ? 1024 : n;
@@ -340,10 +570,29 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
       a.lines = lines + r0 * m->I[I_N_ULINES] * BAYSAR_LINE_STRIDE;
       a.components = comps + r0 * ncols; a.spectra = nullptr;
       a.fine_pre = fine_pre ? fine_pre + r0 * F : nullptr; a.fine_post = nullptr; a.status = status + r0;
-      a.spec = m->spec; a.split_pitch = pl.pitch; a.split_pad = pl.pad_left;
+      PxcPlan& fx = m->pxc[c];
+      const bool folded = fx.on && !fine_post;  // the fine-grid diagnostic needs every convolved column
+      a.spec = m->spec; a.split_pitch = folded ? fx.pitch : pl.pitch; a.split_pad = folded ? fx.pad_left : pl.pad_left;
       a.aux = m->aux;
       if (launch_chord_kernel<1>(m, a, dim3((unsigned)rows, 1), m->chord_smem[c], stream)) return 1;
       if (mark(m, ST_CHORD, stream)) return 1;
+      if (folded) {
+        // K2b': instrument function and wavelength map as one tcgen05 contraction; K2c': area identity + likelihood
+        if (launch_pxc(fx, m->spec, (int)(rows128 / ifc::TILE_M), m->conv, m->trapz_part, m->sm_count, stream)) return 1;
+        if (mark(m, ST_CONTRACT, stream)) return 1;
+        PixelFoldArgs pf{};
+        pf.theta = theta + r0 * n_params; pf.n = rows; pf.chord = c; pf.cp = m->conv; pf.cp_pitch = fx.out_pitch;
+        pf.pix_col = fx.d_pix_col; pf.col_left0 = fx.col_left0; pf.x_l = fx.x_l; pf.col_right0 = fx.col_right0; pf.x_r = fx.x_r;
+        pf.spec = m->spec; pf.spec_pitch = fx.pitch; pf.spec_pad = fx.pad_left; pf.dtab = fx.d_dtab; pf.n_dl = fx.n_dl;
+        pf.n_dr = fx.n_dr; pf.wsum = fx.wsum; pf.tsum = fx.n_fold_tiles <= 64 ? m->trapz_part : nullptr;
+        pf.n_col_tiles = fx.n_col_tiles; pf.n_fold_tiles = fx.n_fold_tiles <= 64 ? fx.n_fold_tiles : 0; pf.tile_n = fx.tn; pf.aux = m->aux; pf.components = comps + r0 * ncols;
+        pf.spectra = spectra ? spectra + r0 * P : nullptr; pf.status = status + r0;
+        pixel_fold_kernel<128><<<(unsigned)rows, 128, 0, stream>>>(m->dev, pf);
+        CUDA_OK(cudaGetLastError());
+        if (mark(m, ST_PIXEL, stream)) return 1;
+        m->last_launches += 3;
+        continue;
+      }
       // K2b: tcgen05 contraction with the banded-Toeplitz instrument matrix
       ifc::Params p{};
       p.s = m->spec; p.pitch = pl.pitch; p.pad_left = pl.pad_left; p.F = F;
@@ -480,6 +729,10 @@ int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar
   const int min_taps = env_taps ? atoi(env_taps) : 160;
   const char* env_budget = getenv("BAYSAR_IFC_BUDGET_MB");
   if (env_budget) m->ifc_budget_bytes = (int64_t)atoll(env_budget) << 20;
+  const char* env_pxc = getenv("BAYSAR_PXC");  // 0: keep the every-column contraction; 64 / 128: column tile width
+  const bool pxc_enabled = !(env_pxc && env_pxc[0] == '0');
+  const int pxc_tn = (env_pxc && atoi(env_pxc) == 64) ? 64 : 128;
+  m->pxc.resize(n_chords);
   m->ifc.resize(n_chords);
   m->ifc_taps_dev.assign(n_chords, nullptr);
   m->ifc_cmask_dev.assign(n_chords, nullptr);
@@ -526,6 +779,18 @@ int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar
       if (e3 != cudaSuccess) { baysar_model_destroy(m); return fail(std::string("compact map upload: ") + cudaGetErrorString(e3)); }
       m->conv_c_pitch_max = plw.c_pitch > m->conv_c_pitch_max ? plw.c_pitch : m->conv_c_pitch_max;
     }
+    if (ch[CH_CALWAVE_IDX] < 0 && pxc_enabled) {  // static wavelength map: fold interp1d into the contraction
+      const double* pix_frac_host = static_cast<const double*>(host.ptr(SEC_PIX_FRAC));
+      PxcPlan fx = make_pxc_plan(ifn_host + ch[CH_IF_OFF], ch[CH_KI], ch[CH_IF_KLO], ch[CH_IF_KHI], ch[CH_F], ch[CH_P],
+                                 pix_idx_host + ch[CH_PIX_OFF], pix_frac_host + ch[CH_PIX_OFF], pxc_tn);
+      if (fx.on) {
+        if (upload_pxc_plan(fx)) { free_pxc_plan(fx); baysar_model_destroy(m); return 1; }
+        m->pxc[c] = fx;
+        m->split_pitch_max = fx.pitch > m->split_pitch_max ? fx.pitch : m->split_pitch_max;
+        m->conv_pitch_max = fx.out_pitch > m->conv_pitch_max ? fx.out_pitch : m->conv_pitch_max;
+        m->tiles_max = 2 * fx.n_col_tiles > m->tiles_max ? 2 * fx.n_col_tiles : m->tiles_max;  // tsum lives in trapz_part
+      }
+    }
     m->split_pitch_max = pl.pitch > m->split_pitch_max ? pl.pitch : m->split_pitch_max;
     m->conv_pitch_max = pl.out_pitch > m->conv_pitch_max ? pl.out_pitch : m->conv_pitch_max;
     m->tiles_max = pl.n_tiles > m->tiles_max ? pl.n_tiles : m->tiles_max;
@@ -543,6 +808,7 @@ void baysar_model_destroy(baysar_model_t* m) {
   for (float* t : m->ifc_taps_dev) cudaFree(t);
   for (uint32_t* t : m->ifc_cmask_dev) cudaFree(t);
   for (int* t : m->ifc_cbase_dev) cudaFree(t);
+  for (PxcPlan& fx : m->pxc) free_pxc_plan(fx);
   for (cudaEvent_t ev : m->prof_events) cudaEventDestroy(ev);
   delete m;
 }
@@ -734,6 +1000,165 @@ int baysar_debug_if_contract(const float* spectra_dev, int64_t n_rows, int F, co
     cudaFree(dbg);
   }
   cudaFree(spec); cudaFree(taps);
+  return 0;
+}
+
+int baysar_debug_pix_contract(const float* spectra_dev, int64_t n_rows, int F, const double* taps_host, int KI,
+                              const int* pix_idx_host, const double* pix_frac_host, int P, int tile_n, float* out_dev,
+                              int64_t out_capacity, double* tsum_dev, int64_t tsum_capacity, int64_t* info,
+                              int* pix_col_host, float* elapsed_ms) {
+  // Unit-test hook for the folded contraction: out[r][c] for the plan's columns (see include/baysar_b200.h).
+  if (!spectra_dev || !taps_host || !pix_idx_host || !pix_frac_host || !info) return fail("null argument");
+  if (n_rows % ifc::TILE_M != 0) return fail("n_rows must be a multiple of 128");
+  double wmax = 0.0;
+  for (int k = 0; k < KI; ++k) wmax = fabs(taps_host[k]) > wmax ? fabs(taps_host[k]) : wmax;
+  int k_lo = KI, k_hi = 0;
+  for (int k = 0; k < KI; ++k)
+    if (fabs(taps_host[k]) > 1e-17 * wmax) { k_lo = k < k_lo ? k : k_lo; k_hi = k + 1; }
+  PxcPlan pl = make_pxc_plan(taps_host, KI, k_lo, k_hi, F, P, pix_idx_host, pix_frac_host, tile_n == 64 ? 64 : 128);
+  if (!pl.on) return fail("no folded-contraction plan for this instrument function / grid");
+  int64_t kb_total = 0;
+  for (int t = 0; t < pl.n_col_tiles; ++t) kb_total += pl.tile_nkb[t];
+  info[0] = pl.out_pitch; info[1] = pl.col_left0; info[2] = pl.x_l; info[3] = pl.col_right0; info[4] = pl.x_r;
+  info[5] = pl.n_col_tiles; info[6] = kb_total; info[7] = pl.ring;
+  if (pix_col_host) memcpy(pix_col_host, pl.pix_col.data(), sizeof(int) * P);
+  if (!out_dev) return 0;  // layout query only
+  if (out_capacity < n_rows * pl.out_pitch) return fail("output buffer too small");
+  if (upload_pxc_plan(pl)) { free_pxc_plan(pl); return 1; }
+  float* spec = nullptr;
+  if (tsum_dev && tsum_capacity < n_rows * pl.n_col_tiles * 2) return fail("tsum buffer too small");
+  cudaError_t e = cudaMalloc(&spec, sizeof(float) * n_rows * pl.pitch);
+  if (e == cudaSuccess) e = cudaMemset(spec, 0, sizeof(float) * n_rows * pl.pitch);
+  if (e != cudaSuccess) { free_pxc_plan(pl); return fail(std::string("debug spectra: ") + cudaGetErrorString(e)); }
+  ifc::pad_rows_kernel<<<dim3(8, (unsigned)n_rows), 256>>>(spectra_dev, n_rows, F, spec, pl.pitch, pl.pad_left);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  int rc = 0;
+  long long* dbg = nullptr;
+  if (getenv("BAYSAR_PXC_TRACE")) {
+    cudaMalloc(&dbg, sizeof(long long) * 16 * 256);
+    cudaMemset(dbg, 0, sizeof(long long) * 16 * 256);
+  }
+  for (int rep = 0; rep < 2 && rc == 0; ++rep) {
+    cudaEventRecord(e0, 0);
+    rc = launch_pxc(pl, spec, (int)(n_rows / ifc::TILE_M), out_dev, tsum_dev, sms, 0, dbg);
+    cudaEventRecord(e1, 0);
+    if (rc == 0 && cudaEventSynchronize(e1) != cudaSuccess) rc = fail(std::string("folded contraction: ") + cudaGetErrorString(cudaGetLastError()));
+  }
+  float ms = 0.f;
+  if (rc == 0) cudaEventElapsedTime(&ms, e0, e1);
+  if (elapsed_ms) *elapsed_ms = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (dbg && rc == 0) {
+    std::vector<long long> h(16 * 256);
+    cudaMemcpy(h.data(), dbg, sizeof(long long) * 16 * 256, cudaMemcpyDeviceToHost);
+    const char* names[13] = {"conv.wait_landed", "conv.wait_empty", "conv.total", "load.wait_consumed", "build.wait_bempty",
+                             "build.total", "epi.wait_acc_full", "epi.drain", "mma.wait_full", "mma.wait_bfull",
+                             "mma.wait_acc_free", "mma.total", "mma.k_blocks"};
+    const int ctas = (int)std::min<int64_t>(sms, (n_rows / ifc::TILE_M) * pl.n_col_tiles);
+    for (int k = 0; k < 13; ++k) {
+      double mean = 0, mx = 0;
+      for (int b = 0; b < ctas; ++b) { mean += (double)h[b * 16 + k]; mx = std::max(mx, (double)h[b * 16 + k]); }
+      fprintf(stderr, "[pxc trace] %-20s mean %.0f max %.0f (CTA0 %lld)\n", names[k], mean / ctas, mx, h[k]);
+    }
+  }
+  cudaFree(dbg);
+  cudaFree(spec);
+  free_pxc_plan(pl);
+  return rc;
+}
+
+int baysar_debug_pix_plan_check(const double* spectrum_host, int F, const double* taps_host, int KI,
+                                const int* pix_idx_host, const double* pix_frac_host, int P, int tile_n, double* result) {
+  // Host-only self check of the folded-contraction plan (no GPU needed): evaluates every column through the plan's
+  // tables with the kernel's index arithmetic (float64 products) against the definition, and the area identity of
+  // pixel_fold_kernel against the direct trapz of the clipped convolution.
+  if (!spectrum_host || !taps_host || !pix_idx_host || !pix_frac_host || !result) return fail("null argument");
+  double wmax = 0.0;
+  for (int k = 0; k < KI; ++k) wmax = fabs(taps_host[k]) > wmax ? fabs(taps_host[k]) : wmax;
+  int k_lo = KI, k_hi = 0;
+  for (int k = 0; k < KI; ++k)
+    if (fabs(taps_host[k]) > 1e-17 * wmax) { k_lo = k < k_lo ? k : k_lo; k_hi = k + 1; }
+  PxcPlan pl = make_pxc_plan(taps_host, KI, k_lo, k_hi, F, P, pix_idx_host, pix_frac_host, tile_n == 64 ? 64 : 128);
+  if (!pl.on) return fail("no folded-contraction plan for this instrument function / grid");
+  const int o = (KI - 1) / 2, tn = pl.tn;
+  std::vector<double> conv(F);
+  double mn = spectrum_host[0], cmax = 0.0;
+  for (int j = 0; j < F; ++j) {
+    mn = spectrum_host[j] < mn ? spectrum_host[j] : mn;
+    double acc = 0.0;
+    for (int k = k_lo; k < k_hi; ++k) {
+      const int sidx = j + o - k;
+      if (sidx >= 0 && sidx < F) acc += (double)(float)taps_host[k] * spectrum_host[sidx];
+    }
+    conv[j] = acc;
+    cmax = fabs(acc) > cmax ? fabs(acc) : cmax;
+  }
+  auto padded = [&](int64_t col) {  // the zero-padded row the kernel reads
+    const int64_t sidx = col - pl.pad_left;
+    return (sidx >= 0 && sidx < F) ? spectrum_host[sidx] : 0.0;
+  };
+  std::vector<double> out(pl.out_pitch);
+  for (int t = 0; t < pl.n_col_tiles; ++t)
+    for (int c = t * tn; c < (t + 1) * tn; ++c) {
+      double acc = 0.0;
+      for (int kb = 0; kb < pl.tile_nkb[t]; ++kb)
+        for (int e = 0; e < ifc::TILE_K; ++e) {
+          const int x = pl.col_idx[c] - ifc::TILE_K * kb - e;
+          if (x - 3 < 0 || x + 1 >= pl.wlen) return fail("tap table index out of range");
+          const double b = (double)pl.wtab[x] + (double)pl.col_frac[c] * ((double)pl.wtab[x + 1] - (double)pl.wtab[x]);
+          acc += padded((int64_t)pl.tile_kcol0[t] + ifc::TILE_K * kb + e) * b;
+        }
+      out[c] = acc;
+    }
+  double err_pix = 0.0, err_edge = 0.0;
+  int n_folded = 0;
+  for (int p = 0; p < P; ++p) {
+    if (pl.pix_col[p] < 0) continue;
+    ++n_folded;
+    const int i = pix_idx_host[p];
+    const double ref = conv[i] + (double)(float)pix_frac_host[p] * (conv[i + 1] - conv[i]);
+    err_pix = std::max(err_pix, fabs(out[pl.pix_col[p]] - ref) / cmax);
+  }
+  for (int j = 0; j < pl.x_l; ++j) err_edge = std::max(err_edge, fabs(out[pl.col_left0 + j] - conv[j]) / cmax);
+  for (int j = F - pl.x_r; j < F; ++j) err_edge = std::max(err_edge, fabs(out[pl.col_right0 + j - (F - pl.x_r)] - conv[j]) / cmax);
+  // area identity
+  double pre = 0.0, post_direct = 0.0, part = 0.0;
+  for (int j = 0; j < F; ++j) {
+    const double cj = (j == 0 || j == F - 1) ? 0.5 : 1.0;
+    pre += cj * spectrum_host[j];
+    post_direct += cj * (conv[j] < mn ? mn : conv[j]);
+  }
+  for (int t = 0; t < pl.x_l + pl.x_r; ++t) {
+    const int j = t < pl.x_l ? t : F - pl.x_r + (t - pl.x_l);
+    const double v = t < pl.x_l ? out[pl.col_left0 + t] : out[pl.col_right0 + (t - pl.x_l)];
+    if (v < mn) part += ((j == 0 || j == F - 1) ? 0.5 : 1.0) * (mn - v);
+  }
+  for (int t = 0; t < pl.n_dl + pl.n_dr; ++t) {
+    const int sidx = t < pl.n_dl ? t : F - pl.n_dr + (t - pl.n_dl);
+    part += spectrum_host[sidx] * pl.dtab[t];
+  }
+  // column-sum identity per folded tile
+  double err_cs = 0.0;
+  for (int t = 0; t < pl.n_fold_tiles && pl.tile_boff[t] >= 0; ++t) {
+    double col_sum = 0.0, t_id = 0.0;
+    for (int c = t * tn; c < (t + 1) * tn; ++c) col_sum += out[c];
+    for (int x = 0; x < ifc::TILE_K * pl.tile_nkb[t]; ++x)
+      t_id += padded((int64_t)pl.tile_kcol0[t] + x) * (double)pl.bbar[pl.tile_boff[t] + x];
+    err_cs = std::max(err_cs, fabs(t_id - col_sum) / fabs(col_sum));
+  }
+  result[8] = err_cs;
+  // interior columns must not need the clip
+  double clip_violation = 0.0;
+  for (int j = pl.e_l; j < F - pl.e_r; ++j) clip_violation = std::max(clip_violation, (mn - conv[j]) / cmax);
+  int64_t kb_total = 0;
+  for (int t = 0; t < pl.n_col_tiles; ++t) kb_total += pl.tile_nkb[t];
+  result[0] = err_pix; result[1] = err_edge; result[2] = fabs((pl.wsum * pre + part) - post_direct) / fabs(post_direct);
+  result[3] = (double)kb_total; result[4] = (double)n_folded; result[5] = clip_violation; result[6] = (double)pl.wlen;
+  result[7] = (double)pl.ring;
   return 0;
 }
 

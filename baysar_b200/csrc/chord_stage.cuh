@@ -164,6 +164,36 @@ struct FetchCompact {
   }
 };
 
+// Folded rows of pix_contract.cuh: one column per pixel (instrument convolution and interp1d in one contraction) plus
+// the explicit fine-grid columns of the two edge zones, where the clip at the pre-convolution minimum can bite.
+struct FetchFolded {
+  const float* row;        // [out_pitch] contraction output of this theta
+  const int* pix_col;      // [P] column of pixel p, or -1: pixel reads the explicit edge columns
+  int col_left0, x_l;      // explicit columns j = 0 .. x_l - 1 at row[col_left0 + j]
+  int col_right0, x_r, F;  // explicit columns j = F - x_r .. F - 1 at row[col_right0 + j - (F - x_r)]
+  float mn;                // clip level
+  const float* kappa;      // [column tiles] bias correction of the folded columns (shared memory)
+  int tile_shift;          // log2 of the column tile width
+  BAYSAR_DEV double operator()(int i) const {
+    const float v = i < x_l ? row[col_left0 + i] : row[col_right0 + (i - (F - x_r))];
+    return (double)(v < mn ? mn : v);
+  }
+};
+
+// Convolved spectrum at pixel p: interp1d between fine-grid points i and i + 1 (the four end outputs in float64)
+template <class Fetch>
+BAYSAR_DEV double pixel_value(const Fetch& fetch, int p, int i, double w, const double* edge64, int F) {
+  const double v0 = (i < 2) ? edge64[i] : (i >= F - 2 ? edge64[i - (F - 4)] : fetch(i));
+  const int i1 = i + 1;
+  const double v1 = (i1 < 2) ? edge64[i1] : (i1 >= F - 2 ? edge64[i1 - (F - 4)] : fetch(i1));
+  return v0 + w * (v1 - v0);
+}
+BAYSAR_DEV double pixel_value(const FetchFolded& fetch, int p, int i, double w, const double* edge64, int F) {
+  const int col = fetch.pix_col[p];
+  if (col >= 0) return (double)fetch.kappa[col >> fetch.tile_shift] * (double)fetch.row[col];
+  return pixel_value<FetchFolded>(fetch, p, i, w, edge64, F);
+}
+
 // Area renormalisation, + background, wavelength map, clip, Cauchy likelihood (spectrometers.py:286-310, :154-195).
 // `post` and `pre` are the trapz integrals after / before the instrument convolution; edge64 the four end outputs.
 template <int NT, class Fetch>
@@ -202,10 +232,7 @@ BAYSAR_DEV void pixel_likelihood(const ModelDev& m, const int* ch, const double*
       i = m.pix_idx[poff + p];
       w = m.pix_frac[poff + p];
     }
-    double v0 = (i < 2) ? edge64[i] : (i >= F - 2 ? edge64[i - (F - 4)] : fetch(i));
-    int i1 = i + 1;
-    double v1 = (i1 < 2) ? edge64[i1] : (i1 >= F - 2 ? edge64[i1 - (F - 4)] : fetch(i1));
-    double fm = (v0 + w * (v1 - v0)) / ratio + bg;
+    double fm = pixel_value(fetch, p, i, w, edge64, F) / ratio + bg;
     fm = fm < bg ? bg : fm;
     if (!(fm - fm == 0.0)) st |= 1u << 10;
     if (spectra) spectra[n * (int64_t)P + p] = fm;
@@ -855,6 +882,101 @@ __global__ void __launch_bounds__(NT) pixel_stage_kernel(ModelDev m, PixelArgs a
     pixel_likelihood<NT>(m, ch, chd, th, n, c, ncomp_cols, ax[0], post, ax + 2, fetch, scratch, a.components, a.spectra,
                          a.fine_post, st);
   }
+  st = __syncthreads_or((int)st);
+  if (tid == 0 && st) atomicOr(&a.status[n], st);
+}
+
+// K2c' — pixel / likelihood stage behind pix_contract.cuh: one CTA per (theta, chord).
+// The trapz of the clipped, convolved spectrum is not summed from fine-grid columns (they are never formed) but from
+// the identity  sum_j c_j conv_j = sum_s S_s G_s,  G_s = sum_j c_j w[j + o - s]  (c = trapz weights):  G equals the
+// tap sum W times c_s except within a tap half-width of the two ends, so
+//     post / dl = W pre / dl + sum_{s in end zones} S_s (G_s - W c_s) + sum_{j in edge zones} c_j (clip(conv_j) - conv_j)
+// with the explicit edge columns of the contraction for the last sum (the clip is inactive elsewhere: w >= 0).
+// Bias correction: tensor-memory accumulation truncates, so every folded column comes out low by a few 1e-7 .. 1e-6
+// (relative).  The reference's renormalisation by the convolved area cancelled the common part of that in the
+// every-column path; here the same is achieved per column tile with the column-sum identity
+//     sum_{c in tile} C_c = sum_s S_s bbar_s,   bbar_s = sum_{c in tile} B[s, c]
+// whose right-hand side the contraction's converter threads accumulate from the A operand they hold anyway (float32
+// products, float64 sums): kappa_tile = (exact sum) / (sum of the contraction's columns) multiplies the tile's columns.
+struct PixelFoldArgs {
+  const double* theta;
+  int64_t n;
+  int chord;
+  const float* cp;          // [rows][cp_pitch] contraction output
+  int64_t cp_pitch;
+  const int* pix_col;       // [P]
+  int col_left0, x_l, col_right0, x_r;
+  const float* spec;        // [rows][spec_pitch] pre-convolution spectra, element s at spec_pad + s
+  int64_t spec_pitch;
+  int spec_pad;
+  const double* dtab;       // [n_dl + n_dr]: G_s - W c_s for s = 0 .. n_dl - 1, then s = F - n_dr .. F - 1
+  int n_dl, n_dr;
+  double wsum;              // W
+  const double* tsum;       // [rows][n_col_tiles][2] exact column sums per tile (converter groups), may be nullptr
+  int n_col_tiles, n_fold_tiles, tile_n;
+  const double* aux;        // [N][BAYSAR_AUX_STRIDE]
+  double* components;
+  double* spectra;          // optional [N][P]
+  uint32_t* status;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) pixel_fold_kernel(ModelDev m, PixelFoldArgs a) {
+#ifdef BAYSAR_CPU_EMU
+  double* scratch = reinterpret_cast<double*>(emu_dynamic_smem());
+#else
+  __shared__ double scratch[64 + 32];  // reductions + 64 float tile corrections
+#endif
+  const int tid = threadIdx.x;
+  const int64_t n = blockIdx.x;
+  const int c = a.chord;
+  const int64_t* I = m.I;
+  const int n_params = (int)I[I_N_PARAMS];
+  const int ncomp_cols = (int)I[I_N_CHORDS] + (int)I[I_N_PRIORS];
+  const int* ch = m.ch_i + c * CH_I_COUNT;
+  const double* chd = m.ch_d + c * CH_D_COUNT;
+  const double* th = a.theta + n * n_params;
+  const double* ax = a.aux + n * BAYSAR_AUX_STRIDE;
+  const int F = ch[CH_F];
+  const float mn = (float)ax[1];
+  const float* row = a.cp + n * a.cp_pitch;
+  const float* sp = a.spec + n * a.spec_pitch + a.spec_pad;
+  uint32_t st = 0;
+  double part = 0.0;
+  for (int t = tid; t < a.x_l + a.x_r; t += NT) {  // clip correction of the explicit edge columns
+    const int j = t < a.x_l ? t : F - a.x_r + (t - a.x_l);
+    const float v = t < a.x_l ? row[a.col_left0 + t] : row[a.col_right0 + (t - a.x_l)];
+    if (!(v - v == 0.f)) st |= 1u << 8;
+    if (v < mn) part += ((j == 0 || j == F - 1) ? 0.5 : 1.0) * ((double)mn - (double)v);
+  }
+  for (int t = tid; t < a.n_dl + a.n_dr; t += NT) {  // end zones of the pulled-back trapz weights
+    const int s = t < a.n_dl ? t : F - a.n_dr + (t - a.n_dl);
+    part += (double)sp[s] * a.dtab[t];
+  }
+  double red_p[1] = {part};
+  block_sum<NT, 1>(red_p, scratch);
+  const double pre = ax[0];
+  const double post = a.wsum * pre + chd[CH_DL] * red_p[0];
+  if (!(post - post == 0.0)) st |= 1u << 8;
+  // per-tile bias correction: one warp per folded column tile
+  float* kappa_s = reinterpret_cast<float*>(scratch + 64);
+  const int tile_shift = a.tile_n == 64 ? 6 : 7;
+  for (int t = tid >> 5; t < a.n_fold_tiles; t += NT / 32) {
+    float kap = 1.f;
+    if (a.tsum) {
+      double cs = 0.0;
+      for (int e = tid & 31; e < a.tile_n; e += 32) cs += (double)row[t * a.tile_n + e];
+      cs = warp_sum(cs);
+      const double* ts = a.tsum + (n * a.n_col_tiles + t) * 2;
+      const double k = (ts[0] + ts[1]) / cs;
+      if (fabs(k - 1.0) < 1e-4) kap = (float)k;  // a correction, not a repair: anything larger is not truncation bias
+    }
+    if ((tid & 31) == 0) kappa_s[t] = kap;
+  }
+  __syncthreads();
+  FetchFolded fetch{row, a.pix_col, a.col_left0, a.x_l, a.col_right0, a.x_r, F, mn, kappa_s, tile_shift};
+  pixel_likelihood<NT>(m, ch, chd, th, n, c, ncomp_cols, pre, post, ax + 2, fetch, scratch, a.components, a.spectra,
+                       nullptr, st);
   st = __syncthreads_or((int)st);
   if (tid == 0 && st) atomicOr(&a.status[n], st);
 }

@@ -71,6 +71,11 @@ def library():
     lib.baysar_debug_if_contract.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp, ctypes.POINTER(i64),
                                              ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_float)]
     lib.baysar_debug_if_contract.restype = i32
+    lib.baysar_debug_pix_contract.argtypes = [vp, i64, i32, vp, i32, vp, vp, i32, i32, vp, i64, vp, i64, vp, vp,
+                                              ctypes.POINTER(ctypes.c_float)]
+    lib.baysar_debug_pix_contract.restype = i32
+    lib.baysar_debug_pix_plan_check.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, vp]
+    lib.baysar_debug_pix_plan_check.restype = i32
     lib.baysar_debug_mma_probe.argtypes = [i32, i32, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_double)]
     lib.baysar_debug_mma_probe.restype = i32
     u64 = ctypes.c_uint64
@@ -87,7 +92,8 @@ def library():
 EXPORTED_SYMBOLS = ["baysar_model_create", "baysar_model_destroy", "baysar_model_query", "baysar_eval_logp",
                     "baysar_eval_spectra", "baysar_eval_lines", "baysar_eval_logp_host", "baysar_last_error",
                     "baysar_version", "baysar_stretch_propose", "baysar_stretch_accept", "baysar_model_set_profiling", "baysar_model_get_profile", "baysar_microbench", "baysar_debug_if_contract",
-                    "baysar_debug_mma_probe"]
+                    "baysar_debug_mma_probe", "baysar_debug_pix_contract",
+                    "baysar_debug_pix_plan_check"]
 
 
 def microbench(device=0):
@@ -124,6 +130,59 @@ def debug_if_contract(spectra, taps, row_min=None):
         raise RuntimeError("baysar_b200: " + lib.baysar_last_error().decode())
     torch.cuda.synchronize()
     return out[:, :F], part.sum(dim=1), ms.value
+
+
+def debug_pix_contract(spectra, taps, pix_idx, pix_frac, tile_n=128):
+    """Run the folded pixel contraction (instrument convolution + static wavelength map) on a CUDA float32 tensor
+    [n_rows (multiple of 128), F].  -> dict(out [n_rows, out_pitch] float32, pix_col [P], col_left0, x_l, col_right0,
+    x_r, n_col_tiles, k_blocks, ring, ms)."""
+    import numpy as np
+    import torch
+
+    lib = library()
+    spectra = spectra.contiguous()
+    n, F = spectra.shape
+    taps = np.ascontiguousarray(taps, dtype=np.float64)
+    pix_idx = np.ascontiguousarray(pix_idx, dtype=np.int32)
+    pix_frac = np.ascontiguousarray(pix_frac, dtype=np.float64)
+    P = len(pix_idx)
+    info = (ctypes.c_int64 * 8)()
+    pix_col = np.zeros(P, dtype=np.int32)
+    ms = ctypes.c_float()
+    args = [spectra.data_ptr(), n, F, taps.ctypes.data, len(taps), pix_idx.ctypes.data, pix_frac.ctypes.data, P, tile_n]
+    rc = lib.baysar_debug_pix_contract(*args, None, 0, None, 0, ctypes.cast(info, ctypes.c_void_p), pix_col.ctypes.data,
+                                       ctypes.byref(ms))
+    if rc != 0:
+        raise RuntimeError("baysar_b200: " + lib.baysar_last_error().decode())
+    out = torch.empty((n, info[0]), dtype=torch.float32, device=spectra.device)
+    tsum = torch.zeros((n, info[5], 2), dtype=torch.float64, device=spectra.device)
+    rc = lib.baysar_debug_pix_contract(*args, out.data_ptr(), out.numel(), tsum.data_ptr(), tsum.numel(),
+                                       ctypes.cast(info, ctypes.c_void_p), pix_col.ctypes.data, ctypes.byref(ms))
+    if rc != 0:
+        raise RuntimeError("baysar_b200: " + lib.baysar_last_error().decode())
+    torch.cuda.synchronize()
+    keys = ("out_pitch", "col_left0", "x_l", "col_right0", "x_r", "n_col_tiles", "k_blocks", "ring")
+    res = {k: int(info[i]) for i, k in enumerate(keys)}
+    res.update(out=out, tsum=tsum.sum(dim=2), pix_col=pix_col, ms=ms.value, tile_n=tile_n)
+    return res
+
+
+def debug_pix_plan_check(spectrum, taps, pix_idx, pix_frac, tile_n=128):
+    """Host-only check of the folded-contraction plan (no GPU): see baysar_debug_pix_plan_check in the header."""
+    import numpy as np
+
+    lib = library()
+    spectrum = np.ascontiguousarray(spectrum, dtype=np.float64)
+    taps = np.ascontiguousarray(taps, dtype=np.float64)
+    pix_idx = np.ascontiguousarray(pix_idx, dtype=np.int32)
+    pix_frac = np.ascontiguousarray(pix_frac, dtype=np.float64)
+    res = np.zeros(9)
+    rc = lib.baysar_debug_pix_plan_check(spectrum.ctypes.data, len(spectrum), taps.ctypes.data, len(taps),
+                                         pix_idx.ctypes.data, pix_frac.ctypes.data, len(pix_idx), tile_n, res.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("baysar_b200: " + lib.baysar_last_error().decode())
+    keys = ("err_pixels", "err_edges", "err_area", "k_blocks", "n_folded", "clip_violation", "wlen", "ring", "err_colsum")
+    return dict(zip(keys, res.tolist()))
 
 
 class DeviceModel:

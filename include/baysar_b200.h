@@ -108,6 +108,26 @@ int baysar_debug_if_contract(const float* spectra_dev, int64_t n_rows, int F, co
                              const float* row_min_dev, float* out_dev, double* trapz_dev, int64_t* out_pitch,
                              int* n_tiles, float* elapsed_ms);
 
+/* Unit-test hook for the folded pixel contraction (csrc/pix_contract.cuh): instrument convolution and the static
+ * wavelength map (interp1d between fine-grid points pix_idx[p], pix_idx[p] + 1 with weight pix_frac[p]) as one
+ * contraction.  out[r][c]: column pix_col[p] (>= 0) holds pixel p; explicit (unclipped) fine-grid columns
+ * j = 0 .. x_l - 1 at col_left0 + j and j = F - x_r .. F - 1 at col_right0 + j - (F - x_r).
+ * info[8] = out_pitch, col_left0, x_l, col_right0, x_r, column tiles, k-blocks per theta block, A ring stages.
+ * tsum_dev (optional, n_rows * column tiles * 2 doubles): exact column sums per (row, folded tile, converter group).
+ * out_dev == NULL: layout query only. */
+int baysar_debug_pix_contract(const float* spectra_dev, int64_t n_rows, int F, const double* taps_host, int KI,
+                              const int* pix_idx_host, const double* pix_frac_host, int P, int tile_n, float* out_dev,
+                              int64_t out_capacity, double* tsum_dev, int64_t tsum_capacity, int64_t* info,
+                              int* pix_col_host, float* elapsed_ms);
+
+/* Host-only self check of the folded-contraction plan (runs without a GPU): one float64 spectrum through the plan's
+ * tables with the kernel's index arithmetic.  result[9] = max |error| / max|conv| of the pixel columns, of the explicit
+ * edge columns, relative error of the area identity, k-blocks per theta block, folded pixels, largest interior clip
+ * violation / max|conv| (<= 0: the clip is inactive there), tap-table floats, A ring stages, relative error of the
+ * column-sum identity (float32 bbar table against the float64 column sum). */
+int baysar_debug_pix_plan_check(const double* spectrum_host, int F, const double* taps_host, int KI,
+                                const int* pix_idx_host, const double* pix_frac_host, int P, int tile_n, double* result);
+
 /* Issue-rate probe of kind::tf32 tcgen05.mma (csrc/mma_probe.cuh): cycles per 128 x tile_n x 8 MMA, slowest SM, for the
  * contraction kernels' issue pattern on constant operands.  form 0 = A from tensor memory, 1 = A from shared memory;
  * pattern 0 = kernels' pattern, 1 = one accumulator, 2 = hi*hi only. */
