@@ -416,10 +416,34 @@ int pxc_schedule(PxcPlan& pl, int n_rb, int sms, const PxcSchedule** out) {
 }
 
 template <int TN, bool TRACE>
-int launch_pxc_t(const pxc::Params& p, int ctas, size_t smem, cudaStream_t stream) {
+int launch_pxc_t(const pxc::Params& p, const CUtensorMap& tmap, int ctas, size_t smem, cudaStream_t stream) {
   CUDA_OK(cudaFuncSetAttribute(pxc::pix_contract_kernel<TN, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pxc::pix_contract_kernel<TN, TRACE><<<ctas, pxc::THREADS, smem, stream>>>(p);
+  pxc::pix_contract_kernel<TN, TRACE><<<ctas, pxc::THREADS, smem, stream>>>(p, tmap);
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Tensor map of the zero-padded spectra for the contraction's A loads: float32 {pitch, rows}, box {16, 128}, SWIZZLE_64B
+int make_spec_tmap(const float* spec, int64_t pitch, int64_t rows, CUtensorMap* out) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled not available in this driver");
+    encode = reinterpret_cast<encode_fn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)ifc::TILE_K, (cuuint32_t)ifc::TILE_M};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(spec), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
   return 0;
 }
 
@@ -434,12 +458,20 @@ int launch_pxc(PxcPlan& pl, const float* spec, int n_rb, float* out, double* tsu
   p.sched_slots = sc->slots; p.out = out; p.out_pitch = pl.out_pitch; p.ring = pl.ring; p.dbg_cycles = dbg_cycles;
   p.bbar = (tsum && pl.n_fold_tiles <= 64) ? pl.d_bbar : nullptr; p.tile_boff = pl.d_tile_boff; p.tsum = tsum;
   p.n_col_tiles = pl.n_col_tiles;
+  // A loader: 0 = cp.async by two loader warps (default), 1 = one TMA box per k-block (opt-in: 2 % faster on the Balmer
+  // demo, but one build of it was seen to deliver stale A rows in cold first launches; not root-caused)
+  static const int loader = getenv("BAYSAR_PXC_LOADER") ? atoi(getenv("BAYSAR_PXC_LOADER")) : 0;
+  p.use_tma = loader;
+  CUtensorMap tmap;
+  if (make_spec_tmap(spec, pl.pitch, (int64_t)n_rb * ifc::TILE_M, &tmap)) return 1;
   if (pl.tn == 64) {
     const size_t smem = pxc::smem_bytes<64>(pl.ring, pl.wlen);
-    return dbg_cycles ? launch_pxc_t<64, true>(p, sc->ctas, smem, stream) : launch_pxc_t<64, false>(p, sc->ctas, smem, stream);
+    return dbg_cycles ? launch_pxc_t<64, true>(p, tmap, sc->ctas, smem, stream)
+                      : launch_pxc_t<64, false>(p, tmap, sc->ctas, smem, stream);
   }
   const size_t smem = pxc::smem_bytes<128>(pl.ring, pl.wlen);
-  return dbg_cycles ? launch_pxc_t<128, true>(p, sc->ctas, smem, stream) : launch_pxc_t<128, false>(p, sc->ctas, smem, stream);
+  return dbg_cycles ? launch_pxc_t<128, true>(p, tmap, sc->ctas, smem, stream)
+                    : launch_pxc_t<128, false>(p, tmap, sc->ctas, smem, stream);
 }
 
 int ensure_workspace(baysar_model* m, int64_t n) {
@@ -827,6 +859,13 @@ int64_t baysar_model_query(const baysar_model_t* m, int what, int arg) {
     case 8: return m->I[I_L];
     case 9: return m->last_launches;
     case 11: return m->any_ifc ? 1 : 0;
+    case 12: {  // folded pixel contraction of chord `arg`: k-blocks per theta block (0: not folded)
+      if (arg < 0 || arg >= m->I[I_N_CHORDS] || !m->pxc[arg].on) return 0;
+      int64_t kb = 0;
+      for (int t : m->pxc[arg].tile_nkb) kb += t;
+      return kb;
+    }
+    case 13: return (arg >= 0 && arg < m->I[I_N_CHORDS] && m->pxc[arg].on) ? m->pxc[arg].tn : 0;
     case 10: return (int64_t)m->chord_smem_max;
     default: return -1;
   }

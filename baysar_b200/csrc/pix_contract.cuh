@@ -29,8 +29,10 @@
 //   cancels a common bias (the post-convolution area comes from an exact identity, see pixel_fold_kernel), so the
 //   hi*hi products rotate over N_ACC_HI accumulators (4 at TN = 64, 2 at TN = 128: a column sees 1/4 or 1/2 of the
 //   truncating additions per accumulator) and the 2^-11-sized cross terms get their own; the epilogue adds them.
-// * Warp roles: 0-7 A converters, 8-11 epilogue, 12 MMA issue, 13 A loader, 14-17 B builders.
+// * Warp roles: 0-7 A converters, 8-11 epilogue, 12 MMA issue, 13-14 A loaders, 15-22 B builders (four teams of two).
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "if_contract.cuh"
 
 namespace pxc {
@@ -40,8 +42,9 @@ using ifc::RING_MAX;
 using ifc::TILE_K;
 using ifc::TILE_M;
 
-constexpr int CONVERTER_WARPS = 8, EPILOGUE_WARPS = 4, BUILDER_WARPS = 4;
-constexpr int WARP_MMA = CONVERTER_WARPS + EPILOGUE_WARPS, WARP_LOADER = WARP_MMA + 1, WARP_BUILDER0 = WARP_LOADER + 1;
+constexpr int CONVERTER_WARPS = 8, EPILOGUE_WARPS = 4, BUILDER_WARPS = 8, BUILDER_TEAMS = 4;
+constexpr int LOADER_WARPS = 2;  // cp.async mode: each loader warp copies half of the rows of a k-block
+constexpr int WARP_MMA = CONVERTER_WARPS + EPILOGUE_WARPS, WARP_LOADER = WARP_MMA + 1, WARP_BUILDER0 = WARP_LOADER + LOADER_WARPS;
 constexpr int THREADS = (WARP_BUILDER0 + BUILDER_WARPS) * 32;
 
 template <int TN>
@@ -53,7 +56,7 @@ struct Cfg {
   static constexpr int B_STAGE_BYTES = TN * 128;              // TN rows x (16 hi + 16 lo) floats
   static constexpr int STAGING_BYTES = TILE_M * TN * 4;
   static_assert(A_STAGES % 2 == 0, "the two converter groups take alternate stages");
-  static_assert(TN % 32 == 0 && B_STAGES > BUILDER_WARPS, "every builder warp owns a stage in flight, the MMAs read another");
+  static_assert(TN % 64 == 0 && B_STAGES > BUILDER_TEAMS, "every builder team owns a stage in flight, the MMAs read another");
 };
 constexpr int MIN_KB = 4;  // every accumulator of a tile is initialised by its own first k-block
 
@@ -72,6 +75,7 @@ struct Params {
   float* out;              // [rows][out_pitch], column tile ct at ct * TN
   int64_t out_pitch;
   int ring;                // shared-memory stages of raw A tiles
+  int use_tma;             // A loader: 1 = one TMA box per k-block, 0 = sixteen cp.async per lane (fallback / experiments)
   // column-sum identity (bias correction in pixel_fold_kernel): tsum[row][ct][grp] = this converter group's share of
   // sum_s S[row, s] * bbar[tile_boff[ct] + (s - k0)], bbar = sum over the tile's folded columns of B[s, c]
   const float* bbar;       // may be nullptr (no sums)
@@ -158,8 +162,11 @@ __device__ __forceinline__ void split_fast(float v, uint32_t& hi, uint32_t& lo) 
 }
 
 // TRACE: per-role wait-cycle counters into p.dbg_cycles[cta][16] (measurement builds only)
+// tmap: the zero-padded spectra as a 2-D float32 tensor {pitch, rows}, box {16, 128}, SWIZZLE_64B — the swizzle is
+// exactly ifc::ring_off (16-byte chunk ^ ((row >> 1) & 3)), so one TMA instruction per k-block replaces the sixteen
+// cp.async instructions per lane with which a single loader warp could not keep up (measured: ~790 cycles per k-block).
 template <int TN, bool TRACE>
-__global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p) {
+__global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p, const __grid_constant__ CUtensorMap tmap) {
   using C = Cfg<TN>;
   extern __shared__ unsigned char smem_dyn[];
   // shared-window addresses (1024-byte aligned carve): B ring | epilogue staging | A ring | tap table | barriers | TMEM slot
@@ -186,10 +193,10 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p) {
   if (tid == 0) {
     auto init = [](uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); };
     for (int s = 0; s < C::A_STAGES; ++s) { init(full + 8 * s, CONVERTER_WARPS / 2); init(empty + 8 * s, 1); }
-    for (int s = 0; s < C::B_STAGES; ++s) { init(bfull + 8 * s, 1); init(bempty + 8 * s, 1); }
+    for (int s = 0; s < C::B_STAGES; ++s) { init(bfull + 8 * s, BUILDER_WARPS / BUILDER_TEAMS); init(bempty + 8 * s, 1); }
     init(acc_full, 1);
     init(acc_free, EPILOGUE_WARPS);
-    for (int r = 0; r < RING_MAX; ++r) { init(landed + 8 * r, 32); init(consumed + 8 * r, CONVERTER_WARPS / 2); }
+    for (int r = 0; r < RING_MAX; ++r) { init(landed + 8 * r, p.use_tma ? 1 : 32 * LOADER_WARPS); init(consumed + 8 * r, CONVERTER_WARPS / 2); }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   if (warp == WARP_MMA) {
@@ -283,41 +290,54 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p) {
       long long* o = p.dbg_cycles + (int64_t)blockIdx.x * 16;
       o[0] = w0; o[1] = w1; o[2] = clock64() - t_begin;
     }
-  } else if (warp == WARP_LOADER) {
-    // ===================== A loader: global -> ring with coalesced 16-byte cp.async =====================
+  } else if (warp >= WARP_LOADER && warp < WARP_BUILDER0) {
+    // ===================== A loader: one TMA box (128 rows x 16 floats, SWIZZLE_64B) per k-block =====================
     int r = 0;
     uint32_t r_phase = 0;
     int64_t g = 0;
     long long w0 = 0;
+    if (p.use_tma && lane == 0 && warp == WARP_LOADER) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
     for (int q = 0; q < my_tiles; ++q) {
       const int ct = my_sched[q] >> 16, rb = my_sched[q] & 0xffff;
       const int n_kb = p.tile_nkb[ct];
-      const float* base = p.s + (int64_t)(rb * TILE_M + (lane >> 2)) * p.pitch + p.tile_kcol0[ct] + 4 * (lane & 3);
+      const int col0 = p.tile_kcol0[ct], row0 = rb * TILE_M;
       for (int i = 0; i < n_kb; ++i, ++g) {
         if (g >= p.ring) mbar_wait32_timed<TRACE>(consumed + 8 * r, r_phase ^ 1u, w0);
-        const float* src = base + TILE_K * ifc::kb_order(i, n_kb);
-        const uint32_t dst = ring + (uint32_t)r * A_TILE_BYTES;
-#pragma unroll 8
-        for (int qq = 0; qq < 16; ++qq) {
-          const int row = (lane >> 2) + 8 * qq;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + ifc::ring_off(row, lane & 3)),
-                       "l"(src + (int64_t)(8 * qq) * p.pitch) : "memory");
+        if (!p.use_tma) {  // loader warp lw: rows 64 lw .. 64 lw + 63, lane = (row & 7, 16-byte chunk)
+          const int lw = warp - WARP_LOADER;
+          const float* src = p.s + (int64_t)(row0 + 64 * lw + (lane >> 2)) * p.pitch + col0 + 4 * (lane & 3) + TILE_K * ifc::kb_order(i, n_kb);
+          const uint32_t dst = ring + (uint32_t)r * A_TILE_BYTES;
+#pragma unroll
+          for (int qq = 0; qq < 8; ++qq) {
+            const int row = 64 * lw + (lane >> 2) + 8 * qq;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + ifc::ring_off(row, lane & 3)),
+                         "l"(src + (int64_t)(8 * qq) * p.pitch) : "memory");
+          }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(landed + 8 * r) : "memory");
+        } else if (lane == 0 && warp == WARP_LOADER) {
+          const uint32_t bar = landed + 8 * r, dst = ring + (uint32_t)r * A_TILE_BYTES;
+          const int col = col0 + TILE_K * ifc::kb_order(i, n_kb);
+          asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(A_TILE_BYTES) : "memory");
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+              "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(col), "r"(row0), "r"(bar) : "memory");
         }
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(landed + 8 * r) : "memory");
+        __syncwarp();
         if (++r == p.ring) { r = 0; r_phase ^= 1u; }
       }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    if (TRACE && lane == 0) p.dbg_cycles[(int64_t)blockIdx.x * 16 + 3] = w0;
+    if (!p.use_tma) asm volatile("cp.async.wait_all;" ::: "memory");
+    if (TRACE && lane == 0 && warp == WARP_LOADER) p.dbg_cycles[(int64_t)blockIdx.x * 16 + 3] = w0;
   } else if (warp >= WARP_BUILDER0) {
     // ===================== B builders: tap table -> interpolated, TF32-split k-block tiles =====================
-    // Builder warp wb owns the k-blocks g = wb (mod 4) of this CTA's sequence and builds each of them alone: the
-    // generic -> async proxy fence a stage needs before the tensor core may read it (a MEMBAR) is paid once per warp and
-    // four k-blocks.  Lane = (column j of a group of eight, 16-byte k chunk qc): five tap reads give the four
-    // interpolated elements 4 qc .. 4 qc + 3 of column n, stored as one 16-byte vector of hi parts and one of lo parts.
-    // The eight rows of a group are one swizzle atom: a warp's 32 stores spread evenly over the eight bank groups.
-    constexpr int ITS = TN / 8;
-    const int wb = warp - WARP_BUILDER0, j = lane >> 2, qc = lane & 3;
+    // Builder team tm (two warps, each half of the columns) owns the k-blocks g = tm (mod 4) of this CTA's sequence:
+    // the generic -> async proxy fence a stage needs before the tensor core may read it (a MEMBAR) is paid once per
+    // warp and four k-blocks, and a single warp's dependent-issue latency is spread over eight warps.
+    // Lane = (column j of a group of eight, 16-byte k chunk qc): five tap reads give the four interpolated elements
+    // 4 qc .. 4 qc + 3 of column n, stored as one 16-byte vector of hi parts and one of lo parts.  The eight rows of a
+    // group are one swizzle atom: a warp's 32 stores spread evenly over the eight bank groups.
+    constexpr int ITS = TN / 16;  // column groups of this warp's half
+    const int wb = warp - WARP_BUILDER0, tm = wb >> 1, it_base = (wb & 1) * ITS, j = lane >> 2, qc = lane & 3;
     const uint32_t soff0 = (uint32_t)(j * 128 + ((qc ^ j) << 4));
     int64_t g = 0;
     long long w0 = 0;
@@ -329,11 +349,11 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p) {
       float cf[ITS];
       bool loaded = false;
       for (int i = 0; i < n_kb; ++i, ++g) {
-        if ((int)(g & 3) != wb) continue;
+        if ((int)(g & 3) != tm) continue;
         if (!loaded) {
 #pragma unroll
           for (int it = 0; it < ITS; ++it) {
-            const int n = it * 8 + j;
+            const int n = (it_base + it) * 8 + j;
             cx[it] = wtab + 4u * (uint32_t)(p.col_idx[ct * TN + n] - 4 * qc - 3);
             cf[it] = p.col_frac[ct * TN + n];
           }
@@ -342,7 +362,7 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p) {
         const int kb = ifc::kb_order(i, n_kb);
         const int sb = (int)(g % C::B_STAGES);
         if (g >= C::B_STAGES) mbar_wait32_timed<TRACE>(bempty + 8 * sb, (uint32_t)(((g / C::B_STAGES) - 1) & 1), w0);
-        const uint32_t st = bring + (uint32_t)sb * C::B_STAGE_BYTES + soff0;
+        const uint32_t st = bring + (uint32_t)sb * C::B_STAGE_BYTES + soff0 + (uint32_t)(it_base * 1024);
         const uint32_t koff = (uint32_t)(4 * TILE_K * kb);
         // groups of four column groups: all twenty tap reads first (ptxas keeps shared loads behind earlier shared
         // stores), then the arithmetic, then the eight stores

@@ -163,7 +163,7 @@ def debug_pix_contract(spectra, taps, pix_idx, pix_frac, tile_n=128):
     torch.cuda.synchronize()
     keys = ("out_pitch", "col_left0", "x_l", "col_right0", "x_r", "n_col_tiles", "k_blocks", "ring")
     res = {k: int(info[i]) for i, k in enumerate(keys)}
-    res.update(out=out, tsum=tsum.sum(dim=2), pix_col=pix_col, ms=ms.value, tile_n=tile_n)
+    res.update(out=out, tsum=tsum.sum(dim=2), tsum_groups=tsum, pix_col=pix_col, ms=ms.value, tile_n=tile_n)
     return res
 
 
@@ -207,6 +207,8 @@ class DeviceModel:
         self.pixels = [q(6, c) for c in range(self.n_chords)]
         self.fine = [q(7, c) for c in range(self.n_chords)]
         self.uses_tensor_cores = bool(q(11))
+        # folded pixel contraction (csrc/pix_contract.cuh) per chord: (k-blocks per theta block, column tile width)
+        self.folded_contraction = [(q(12, c), q(13, c)) for c in range(q(1))]
 
     @property
     def launches_last_eval(self):

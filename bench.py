@@ -168,13 +168,14 @@ def flop_model(post):
     (dense +-256-point window, every 16th point on the tails) and 14 flop + 1 MUFU per fine-grid point in sweep 2;
     Balmer lines with a multi-tap Doppler kernel 18 F + 2 taps F flop and 3 F MUFU; Gaussian components 8 flop + 1
     MUFU per point of their +-8.85 sigma window; 14 F + 12 P of bookkeeping and (fused path only) the instrument
-    convolution at 2 flop per tap and output.  contract (tensor pipe, 3xTF32): per 128x128 output tile and 16-wide
-    k-block three 128x128x8 MMAs per 8-deep k-step, including the zero part of the Toeplitz tiles."""
+    convolution at 2 flop per tap and output.  contract (tensor pipe, 3xTF32): three 128 x TN x 8 MMAs per 8-deep
+    k-step and 16-wide k-block, zero parts of the banded tiles included — k-blocks of the folded pixel contraction as
+    the library planned them (static wavelength map), else of the every-column Toeplitz contraction."""
     from baysar_b200.spectrometers import BalmerHydrogenLine
 
     tensor_path = post.model.uses_tensor_cores
     chord = contract = dense = mufu = 0.0
-    for ch in post.chords:
+    for c_idx, ch in enumerate(post.chords):
         F, P = len(ch.x_data_fm), len(ch.x_data)
         n_b = sum(isinstance(l, BalmerHydrogenLine) for l in ch.lines)
         gauss = [l for l in ch.lines if not isinstance(l, BalmerHydrogenLine)]
@@ -201,7 +202,10 @@ def flop_model(post):
         pts_g = n_g * (2 * 8.85 * max(sig_g, dl / 4) / dl + 1)
         chord += 8.0 * pts_g + 14.0 * F + 12.0 * P
         mufu += pts_g + P
-        if tensor_path:
+        kb_folded, tn_folded = post.model.folded_contraction[c_idx]
+        if tensor_path and kb_folded > 0:
+            contract += kb_folded * 2 * 3 * 2.0 * (128 * tn_folded * 8) / 128.0
+        elif tensor_path:
             o = (len(inst) - 1) // 2
             n_kb = (127 + o - k_lo) // 16 - (o - k_hi + 1) // 16 + 1   # 16-wide k-blocks per 128-output tile
             n_tiles = -(-F // 128)
@@ -369,12 +373,13 @@ def main():
         pass
     fp32_peak = peaks["fp32_fma_flops"] / 1e12
     tf32_peak = measured.get("bf16_tflops", 1590.0) / 2.0
+    contract_name = "pix_contract_kernel" if any(k for k, _ in post.model.folded_contraction) else "if_contract_kernel"
     kernels = {
         "chord_stage_kernel": {"bound": "fp32", "ms": per_call["chord"], "flop_per_eval": flops["chord"],
                                "peak": fp32_peak,
                                "peak_source": "FP32 FMA micro-benchmark in this run (baysar_microbench); "
                                               "MEASURED_PEAKS.json has no FP32 figure"},
-        "if_contract_kernel": {"bound": "tensor", "ms": per_call["contract"], "flop_per_eval": flops["contract"],
+        contract_name: {"bound": "tensor", "ms": per_call["contract"], "flop_per_eval": flops["contract"],
                                "peak": tf32_peak,
                                "peak_source": "TF32 dense = half of MEASURED_PEAKS.json bf16_tflops (burst)"
                                if measured else "TF32 dense = half of the fallback 1.59 PFLOP/s bf16"},
@@ -397,8 +402,9 @@ def main():
     dom = max(kernels, key=lambda name: kernels[name]["ms"])
     hbm_bytes = batch * (8.0 * n_params + 8.0 + 4.0 + 8.0 * (len(post.chords) + len(post.priors))
                          + 2 * 8.0 * 16 * post.model.n_ulines)
-    if post.model.uses_tensor_cores:  # FP32 spectra and convolved spectra, each written and read once
-        hbm_bytes += batch * sum(len(c.x_data_fm) for c in post.chords) * (4.0 + 4.0 + 4.0 + 4.0)
+    if post.model.uses_tensor_cores:  # FP32 spectra and convolved spectra (folded: pixel columns), written and read once
+        hbm_bytes += batch * sum(len(c.x_data_fm) * 8.0 + (len(c.x_data) if post.model.folded_contraction[i][0] else
+                                                           len(c.x_data_fm)) * 8.0 for i, c in enumerate(post.chords))
     roofline = dict(kernels[dom])
     roofline.update({
         "kernel": dom, "traffic": None, "kernels": kernels,

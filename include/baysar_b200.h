@@ -66,7 +66,8 @@ void baysar_model_destroy(baysar_model_t* model);
 
 /* Sizes a caller needs to allocate outputs. what: 0 n_params, 1 n_chords, 2 n_unique_lines, 3 n_priors,
  * 4 max pixels per chord, 5 max fine-grid points per chord, 6 pixels of chord `arg`, 7 fine points of chord `arg`,
- * 8 LOS points, 9 kernels launched per baysar_eval_logp call. */
+ * 8 LOS points, 9 kernels launched per baysar_eval_logp call, 11 any chord on the tensor-core path, 12 k-blocks per
+ * theta block of chord `arg`'s folded pixel contraction (0: not folded), 13 its column tile width. */
 int64_t baysar_model_query(const baysar_model_t* model, int what, int arg);
 
 /* logp[n] = BaysarPosterior.__call__(theta[n])  (posterior.py:219-235): theta [N][n_params] row-major doubles.
