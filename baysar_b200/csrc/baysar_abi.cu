@@ -57,6 +57,8 @@ struct PxcPlan {
   double wsum = 0.0;
   std::vector<int> tile_kcol0, tile_nkb, tile_boff, col_idx, pix_col;
   int n_fold_tiles = 0;
+  std::vector<float> inv_err;  // 1 / err of the chord's pixels (pixel_fold_kernel's log-posterior loop)
+  float* d_inv_err = nullptr;
   std::vector<float> col_frac, wtab, bbar;  // bbar: per folded tile, sum over its columns of B[s, c] (bias correction)
   std::vector<double> dtab;
   int *d_tile_kcol0 = nullptr, *d_tile_nkb = nullptr, *d_tile_boff = nullptr, *d_col_idx = nullptr, *d_pix_col = nullptr;
@@ -372,11 +374,12 @@ int upload_pxc_plan(PxcPlan& pl) {
       upload(&pl.d_pix_col, pl.pix_col) || upload(&pl.d_col_frac, pl.col_frac) || upload(&pl.d_wtab, pl.wtab) ||
       upload(&pl.d_dtab, pl.dtab) || upload(&pl.d_bbar, pl.bbar))
     return 1;
+  if (!pl.inv_err.empty() && upload(&pl.d_inv_err, pl.inv_err)) return 1;
   return 0;
 }
 void free_pxc_plan(PxcPlan& pl) {
   cudaFree(pl.d_tile_kcol0); cudaFree(pl.d_tile_nkb); cudaFree(pl.d_tile_boff); cudaFree(pl.d_col_idx); cudaFree(pl.d_pix_col);
-  cudaFree(pl.d_col_frac); cudaFree(pl.d_wtab); cudaFree(pl.d_dtab); cudaFree(pl.d_bbar);
+  cudaFree(pl.d_col_frac); cudaFree(pl.d_wtab); cudaFree(pl.d_dtab); cudaFree(pl.d_bbar); cudaFree(pl.d_inv_err);
   for (auto& kv : pl.schedules) { cudaFree(kv.second.d_sched); cudaFree(kv.second.d_cnt); }
   pl.schedules.clear();
 }
@@ -500,7 +503,9 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
   static const int minb = getenv("BAYSAR_LOS_MINB") ? atoi(getenv("BAYSAR_LOS_MINB")) : 4;  // register cap experiment
   if (4 * per_warp <= 200 * 1024) {
     size_t smem = 4 * per_warp;
+    static const int unr = getenv("BAYSAR_LOS_UNROLL") ? atoi(getenv("BAYSAR_LOS_UNROLL")) : 1;
     auto kern = minb >= 6 ? los_stage_kernel<4, 6> : (minb == 5 ? los_stage_kernel<4, 5> : los_stage_kernel<4, 4>);
+    if (unr == 2) kern = minb >= 5 ? los_stage_kernel<4, 5, 2> : (minb == 3 ? los_stage_kernel<4, 3, 2> : los_stage_kernel<4, 4, 2>);
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)((n + 3) / 4), 128, smem, stream>>>(m->dev, a);
   } else {
@@ -616,7 +621,7 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
         pf.theta = theta + r0 * n_params; pf.n = rows; pf.chord = c; pf.cp = m->conv; pf.cp_pitch = fx.out_pitch;
         pf.pix_col = fx.d_pix_col; pf.col_left0 = fx.col_left0; pf.x_l = fx.x_l; pf.col_right0 = fx.col_right0; pf.x_r = fx.x_r;
         pf.spec = m->spec; pf.spec_pitch = fx.pitch; pf.spec_pad = fx.pad_left; pf.dtab = fx.d_dtab; pf.n_dl = fx.n_dl;
-        pf.n_dr = fx.n_dr; pf.wsum = fx.wsum; pf.tsum = fx.n_fold_tiles <= 64 ? m->trapz_part : nullptr;
+        pf.n_dr = fx.n_dr; pf.wsum = fx.wsum; pf.inv_err = fx.d_inv_err; pf.tsum = fx.n_fold_tiles <= 64 ? m->trapz_part : nullptr;
         pf.n_col_tiles = fx.n_col_tiles; pf.n_fold_tiles = fx.n_fold_tiles <= 64 ? fx.n_fold_tiles : 0; pf.tile_n = fx.tn; pf.aux = m->aux; pf.components = comps + r0 * ncols;
         pf.spectra = spectra ? spectra + r0 * P : nullptr; pf.status = status + r0;
         pixel_fold_kernel<128><<<(unsigned)rows, 128, 0, stream>>>(m->dev, pf);
@@ -816,6 +821,9 @@ int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar
       PxcPlan fx = make_pxc_plan(ifn_host + ch[CH_IF_OFF], ch[CH_KI], ch[CH_IF_KLO], ch[CH_IF_KHI], ch[CH_F], ch[CH_P],
                                  pix_idx_host + ch[CH_PIX_OFF], pix_frac_host + ch[CH_PIX_OFF], pxc_tn);
       if (fx.on) {
+        const double* err_host = static_cast<const double*>(host.ptr(SEC_ERR)) + ch[CH_PIX_OFF];
+        fx.inv_err.resize(ch[CH_P]);
+        for (int px = 0; px < ch[CH_P]; ++px) fx.inv_err[px] = (float)(1.0 / err_host[px]);
         if (upload_pxc_plan(fx)) { free_pxc_plan(fx); baysar_model_destroy(m); return 1; }
         m->pxc[c] = fx;
         m->split_pitch_max = fx.pitch > m->split_pitch_max ? fx.pitch : m->split_pitch_max;

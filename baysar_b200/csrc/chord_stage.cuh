@@ -46,6 +46,7 @@ struct ChordArgs {
 };
 
 #define BAYSAR_AUX_STRIDE 8
+#define BAYSAR_BG_SLOT 60  // scratch slot of 10^theta_background (block_sum uses the first NV * NT / 32 <= 24 slots)
 
 // Per-line constants of the fused narrow-Doppler Balmer passes (one 64-byte record per line, shared memory)
 struct FusedLine {
@@ -195,10 +196,12 @@ BAYSAR_DEV double pixel_value(const FetchFolded& fetch, int p, int i, double w, 
 }
 
 // Area renormalisation, + background, wavelength map, clip, Cauchy likelihood (spectrometers.py:286-310, :154-195).
-// `post` and `pre` are the trapz integrals after / before the instrument convolution; edge64 the four end outputs.
+// `post` and `pre` are the trapz integrals after / before the instrument convolution; edge64 the four end outputs;
+// bg = 10^theta_background (computed once per CTA by the caller: a float64 pow per thread was a fifth of the pixel
+// kernels' instructions).
 template <int NT, class Fetch>
 BAYSAR_DEV void pixel_likelihood(const ModelDev& m, const int* ch, const double* chd, const double* th, int64_t n, int c,
-                                 int ncomp_cols, double pre, double post, const double* edge64, Fetch fetch,
+                                 int ncomp_cols, double pre, double post, double bg, const double* edge64, Fetch fetch,
                                  double* scratch, double* components, double* spectra, float* fine_post, uint32_t& st) {
   const int tid = threadIdx.x;
   const int F = ch[CH_F], P = ch[CH_P];
@@ -207,7 +210,6 @@ BAYSAR_DEV void pixel_likelihood(const ModelDev& m, const int* ch, const double*
   const double inv_ratio = 1.0 / ratio;
   const double ratio2 = (post / ratio) / pre;
   if (!(fabs(ratio2 - 1.0) <= 1e-8 + 1e-2)) st |= 1u << 9;  // np.isclose(ratio2, 1, rtol=1e-2)
-  const double bg = pow(10.0, th[ch[CH_BG_IDX]]);
   if (fine_post) {
     float* o_ = fine_post + n * (int64_t)F;
     for (int j = tid; j < F; j += NT) o_[j] = (float)(fetch(j) / ratio + bg);
@@ -824,13 +826,14 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
     *reinterpret_cast<float4*>(bufB + pad_index(HALO + j0)) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     *reinterpret_cast<float4*>(bufB + pad_index(HALO + j0 + 4)) = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
+  if (tid == 0) scratch[BAYSAR_BG_SLOT] = pow(10.0, th[ch[CH_BG_IDX]]);
   double red3[1] = {post_s};
   block_sum<NT, 1>(red3, scratch);
   if (__syncthreads_or(bad)) st |= 1u << 8;
   const double post = dl * red3[0];
   FetchSmem fetch{bufB, HALO};
-  pixel_likelihood<NT>(m, ch, chd, th, n, c, ncomp_cols, pre, post, edge64, fetch, scratch, a.components, a.spectra,
-                       a.fine_post, st);
+  pixel_likelihood<NT>(m, ch, chd, th, n, c, ncomp_cols, pre, post, scratch[BAYSAR_BG_SLOT], edge64, fetch, scratch,
+                       a.components, a.spectra, a.fine_post, st);
   st = __syncthreads_or((int)st);
   if (tid == 0 && st) atomicOr(&a.status[n], st);
 #undef A_AT
@@ -878,20 +881,22 @@ __global__ void __launch_bounds__(NT) pixel_stage_kernel(ModelDev m, PixelArgs a
   // trapz of the convolved spectrum: the contraction's per-tile partial sums, one per thread, reduced in a fixed
   // order (deterministic)
   const double* part = a.trapz_part + n * (int64_t)a.n_tiles;
+  if (tid == 0) scratch[BAYSAR_BG_SLOT] = pow(10.0, th[ch[CH_BG_IDX]]);
   double red_p[1] = {0.0};
   for (int t = tid; t < a.n_tiles; t += NT) red_p[0] += part[t];
   block_sum<NT, 1>(red_p, scratch);
+  const double bg = scratch[BAYSAR_BG_SLOT];
   const double post_s = red_p[0];
   if (!(post_s - post_s == 0.0)) st |= 1u << 8;
   const double post = chd[CH_DL] * post_s;
   if (a.cmask) {
     FetchCompact fetch{a.conv + n * a.conv_pitch, a.cmask, a.cbase};
-    pixel_likelihood<NT>(m, ch, chd, th, n, c, ncomp_cols, ax[0], post, ax + 2, fetch, scratch, a.components, a.spectra,
-                         nullptr, st);
+    pixel_likelihood<NT>(m, ch, chd, th, n, c, ncomp_cols, ax[0], post, bg, ax + 2, fetch, scratch, a.components,
+                         a.spectra, nullptr, st);
   } else {
     FetchGlobal fetch{a.conv + n * a.conv_pitch};
-    pixel_likelihood<NT>(m, ch, chd, th, n, c, ncomp_cols, ax[0], post, ax + 2, fetch, scratch, a.components, a.spectra,
-                         a.fine_post, st);
+    pixel_likelihood<NT>(m, ch, chd, th, n, c, ncomp_cols, ax[0], post, bg, ax + 2, fetch, scratch, a.components,
+                         a.spectra, a.fine_post, st);
   }
   st = __syncthreads_or((int)st);
   if (tid == 0 && st) atomicOr(&a.status[n], st);
@@ -923,6 +928,7 @@ struct PixelFoldArgs {
   const double* dtab;       // [n_dl + n_dr]: G_s - W c_s for s = 0 .. n_dl - 1, then s = F - n_dr .. F - 1
   int n_dl, n_dr;
   double wsum;              // W
+  const float* inv_err;     // [P] float32 1 / err of the chord's pixels (log-posterior-only fast loop), may be nullptr
   const double* tsum;       // [rows][n_col_tiles][2] exact column sums per tile (converter groups), may be nullptr
   int n_col_tiles, n_fold_tiles, tile_n;
   const double* aux;        // [N][BAYSAR_AUX_STRIDE]
@@ -936,7 +942,7 @@ __global__ void __launch_bounds__(NT) pixel_fold_kernel(ModelDev m, PixelFoldArg
 #ifdef BAYSAR_CPU_EMU
   double* scratch = reinterpret_cast<double*>(emu_dynamic_smem());
 #else
-  __shared__ double scratch[64 + 32];  // reductions + 64 float tile corrections
+  __shared__ double scratch[64 + 32 + 64];  // reductions, 64 float tile corrections, 64 float64 tile scales
 #endif
   const int tid = threadIdx.x;
   const int64_t n = blockIdx.x;
@@ -964,8 +970,10 @@ __global__ void __launch_bounds__(NT) pixel_fold_kernel(ModelDev m, PixelFoldArg
     const int s = t < a.n_dl ? t : F - a.n_dr + (t - a.n_dl);
     part += (double)sp[s] * a.dtab[t];
   }
+  if (tid == 0) scratch[BAYSAR_BG_SLOT] = pow(10.0, th[ch[CH_BG_IDX]]);
   double red_p[1] = {part};
   block_sum<NT, 1>(red_p, scratch);
+  const double bg = scratch[BAYSAR_BG_SLOT];
   const double pre = ax[0];
   const double post = a.wsum * pre + chd[CH_DL] * red_p[0];
   if (!(post - post == 0.0)) st |= 1u << 8;
@@ -986,8 +994,47 @@ __global__ void __launch_bounds__(NT) pixel_fold_kernel(ModelDev m, PixelFoldArg
   }
   __syncthreads();
   FetchFolded fetch{row, a.pix_col, a.col_left0, a.x_l, a.col_right0, a.x_r, F, mn, kappa_s, tile_shift};
-  pixel_likelihood<NT>(m, ch, chd, th, n, c, ncomp_cols, pre, post, ax + 2, fetch, scratch, a.components, a.spectra,
-                       nullptr, st);
+  if (a.spectra || !a.inv_err) {
+    pixel_likelihood<NT>(m, ch, chd, th, n, c, ncomp_cols, pre, post, bg, ax + 2, fetch, scratch, a.components, a.spectra,
+                         nullptr, st);
+  } else {
+    // log-posterior only: the same arithmetic as pixel_likelihood with the per-pixel constants folded (tile scale
+    // kappa / ratio in shared memory, float32 1 / err table) — 4 M pixels per step make this loop a kernel of its own
+    const double ratio = post / pre, inv_ratio = 1.0 / ratio;
+    const double ratio2 = (post / ratio) / pre;
+    if (!(fabs(ratio2 - 1.0) <= 1e-8 + 1e-2)) st |= 1u << 9;
+    double* scale_s = scratch + 96;
+    if (tid < a.n_fold_tiles) scale_s[tid] = (double)kappa_s[tid] * inv_ratio;
+    __syncthreads();
+    const int P = ch[CH_P], poff = ch[CH_PIX_OFF];
+    double acc = 0.0;
+    for (int p = tid; p < P; p += NT) {
+      const int col = a.pix_col[p];
+      double fm;
+      if (col >= 0) {
+        fm = (double)row[col] * scale_s[col >> tile_shift] + bg;
+      } else {
+        fm = pixel_value<FetchFolded>(fetch, p, m.pix_idx[poff + p], m.pix_frac[poff + p], ax + 2, F) * inv_ratio + bg;
+      }
+      fm = fm < bg ? bg : fm;
+      const double d = m.y[poff + p] - fm;
+      if (!(d - d == 0.0)) st |= 1u << 10;
+      const float rf = (float)d * a.inv_err[p];
+      const float ar = fabsf(rf);
+      if (ar < 1e15f) {
+        if (d == 0.0 || ar == 0.f) st |= 1u << 11;
+        acc += (double)log1pf(ar * ar);
+      } else {
+        const double r = d / m.err[poff + p], r2 = r * r;
+        if (r2 == 0.0) st |= 1u << 11;
+        if (!(r2 - r2 == 0.0)) st |= 1u << 12;
+        acc += log(1.0 + r2);
+      }
+    }
+    double red4[1] = {acc};
+    block_sum<NT, 1>(red4, scratch);
+    if (tid == 0) a.components[n * (int64_t)ncomp_cols + c] = -red4[0];
+  }
   st = __syncthreads_or((int)st);
   if (tid == 0 && st) atomicOr(&a.status[n], st);
 }

@@ -27,7 +27,9 @@ __host__ __device__ static inline size_t los_smem_per_warp(int L, int n_params) 
   return (size_t)L * (14 * sizeof(double) + 4 * sizeof(int)) + (size_t)(2 * n_params + (L & 1)) * sizeof(double);
 }
 
-template <int WARPS, int MINB = 1>
+// UNR: unroll factor of the per-line loops over line-of-sight points (two points of a lane in flight give the FP64
+// dependency chains some instruction-level parallelism; the kernel is latency-bound at 16 warps per SM)
+template <int WARPS, int MINB = 1, int UNR = 1>
 __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m, LosArgs a) {
 #ifdef BAYSAR_CPU_EMU
   unsigned char* los_smem_raw = emu_dynamic_smem();
@@ -45,20 +47,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
   const double* th = a.theta + n * n_params;
 
   unsigned char* base = los_smem_raw + (size_t)warp * los_smem_per_warp(L, n_params);
-  double* p10 = (double*)base;        // 10^theta[k]: every pow(10, theta) of the reference, one lane per parameter
-  double* l10 = p10 + n_params;       // log10(10^theta[k]) (the reference takes log10 of the transformed tau)
-  double* ne_s = l10 + n_params;
-  double* te_s = ne_s + L;
-  double* nm_s = te_s + L;   // main ion density
-  double* n0_s = nm_s + L;   // neutral density profile
-  double* ha_s = n0_s + L;   // adf15-grid cell weights
-  double* hb_s = ha_s + L;
-  double* bx_s = hb_s + L;   // [4][L] spline basis in ne (structure of arrays: conflict-free across lanes)
-  double* by_s = bx_s + 4 * L;
-  int* hi_s = (int*)(by_s + 4 * L);
-  int* hj_s = hi_s + L;
-  int* lx_s = hj_s + L;
-  int* ly_s = lx_s + L;
+  double* __restrict__ p10 = (double*)base;        // 10^theta[k]: every pow(10, theta) of the reference, one lane per parameter
+  double* __restrict__ l10 = p10 + n_params;       // log10(10^theta[k]) (the reference takes log10 of the transformed tau)
+  double* __restrict__ ne_s = l10 + n_params;
+  double* __restrict__ te_s = ne_s + L;
+  double* __restrict__ nm_s = te_s + L;   // main ion density
+  double* __restrict__ n0_s = nm_s + L;   // neutral density profile
+  double* __restrict__ ha_s = n0_s + L;   // adf15-grid cell weights
+  double* __restrict__ hb_s = ha_s + L;
+  double* __restrict__ bx_s = hb_s + L;   // [4][L] spline basis in ne (structure of arrays: conflict-free across lanes)
+  double* __restrict__ by_s = bx_s + 4 * L;
+  int* __restrict__ hi_s = (int*)(by_s + 4 * L);
+  int* __restrict__ hj_s = hi_s + L;
+  int* __restrict__ lx_s = hj_s + L;
+  int* __restrict__ ly_s = lx_s + L;
 
   uint32_t st = 0;
   for (int k = lane; k < n_params; k += 32) {
@@ -232,6 +234,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       double s[12];
 #pragma unroll
       for (int q = 0; q < 12; ++q) s[q] = 0.0;
+#pragma unroll UNR
       for (int l = lane; l < L; l += 32) {
         double ne = ne_s[l], te = te_s[l], w = m.los_w[l];
         double pe = exp(bilinear(texc, hte, hi_s[l], hj_s[l], ha_s[l], hb_s[l]));
@@ -282,6 +285,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       const int pair = j > 0 ? j - 1 : 0;
       const double* cpair = m.spl_c + ((int64_t)ul[UL_TAB_A] * (n_tau - 1) + pair) * ncx * ncy * 2;
       double s[5] = {0, 0, 0, 0, 0};
+#pragma unroll UNR
       for (int l = lane; l < L; l += 32) {
         double ne = ne_s[l], te = te_s[l];
         double n0 = dens * (ne / nemax);
