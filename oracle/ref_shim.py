@@ -49,6 +49,13 @@ class DataArray:
         self.name = name
         self.attrs = attrs or {}
 
+    def __getattr__(self, name):
+        # coordinate access as an attribute (`block_array.ne.data`, OpenADAS/read_adf15.py:96-97)
+        coords = self.__dict__.get("coords", {})
+        if name in coords:
+            return DataArray(coords[name])
+        raise AttributeError(name)
+
     def sel(self, block):
         i = int(np.where(self.coords["block"] == block)[0][0])
         rest = {k: v for k, v in self.coords.items() if k != "block"}
