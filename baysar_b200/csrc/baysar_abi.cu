@@ -569,7 +569,7 @@ int mark(baysar_model* m, int slot, cudaStream_t stream) {
 
 int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_begin, int n_chords,
                   const double* lines, double* comps, double* spectra, float* fine_pre, float* fine_post,
-                  uint32_t* status, cudaStream_t stream) {
+                  uint32_t* status, cudaStream_t stream, double* logp = nullptr, bool* finalized = nullptr) {
   constexpr int NT = 256;
   const int n_params = (int)m->I[I_N_PARAMS];
   const int ncols = (int)(m->I[I_N_CHORDS] + m->I[I_N_PRIORS]);
@@ -624,7 +624,16 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
         pf.n_dr = fx.n_dr; pf.wsum = fx.wsum; pf.inv_err = fx.d_inv_err; pf.tsum = fx.n_fold_tiles <= 64 ? m->trapz_part : nullptr;
         pf.n_col_tiles = fx.n_col_tiles; pf.n_fold_tiles = fx.n_fold_tiles <= 64 ? fx.n_fold_tiles : 0; pf.tile_n = fx.tn; pf.aux = m->aux; pf.components = comps + r0 * ncols;
         pf.spectra = spectra ? spectra + r0 * P : nullptr; pf.status = status + r0;
-        pixel_fold_kernel<128><<<(unsigned)rows, 128, 0, stream>>>(m->dev, pf);
+        {
+          // a single-chord model gets its logP from the same kernel (no finalize launch)
+          const bool fuse = logp && !pf.spectra && pf.inv_err && m->I[I_N_CHORDS] == 1;
+          pf.logp = fuse ? logp + r0 : nullptr;
+          if (fuse && finalized) *finalized = true;
+          const size_t row_bytes = sizeof(float) * (size_t)fx.out_pitch;
+          if (row_bytes > 160 * 1024) return fail("contraction row too long for the pixel stage's shared-memory copy");
+          CUDA_OK(cudaFuncSetAttribute(pixel_fold_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes));
+          pixel_fold_kernel<128><<<(unsigned)rows, 128, row_bytes, stream>>>(m->dev, pf);
+        }
         CUDA_OK(cudaGetLastError());
         if (mark(m, ST_PIXEL, stream)) return 1;
         m->last_launches += 3;
@@ -893,12 +902,16 @@ int baysar_eval_logp(baysar_model_t* m, const double* theta, int64_t n, double* 
   if (launch_los(m, theta, n, m->lines, comps, nullptr, st, stream)) return 1;
   m->last_launches += 1;
   if (mark(m, ST_LOS, stream)) return 1;
-  if (launch_chords(m, theta, n, 0, (int)m->I[I_N_CHORDS], m->lines, comps, nullptr, nullptr, nullptr, st, stream))
+  bool finalized = false;
+  if (launch_chords(m, theta, n, 0, (int)m->I[I_N_CHORDS], m->lines, comps, nullptr, nullptr, nullptr, st, stream, logp,
+                    &finalized))
     return 1;
-  const int ncols = (int)(m->I[I_N_CHORDS] + m->I[I_N_PRIORS]);
-  finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(comps, ncols, n, logp, st);
-  CUDA_OK(cudaGetLastError());
-  m->last_launches += 1;
+  if (!finalized) {
+    const int ncols = (int)(m->I[I_N_CHORDS] + m->I[I_N_PRIORS]);
+    finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(comps, ncols, n, logp, st);
+    CUDA_OK(cudaGetLastError());
+    m->last_launches += 1;
+  }
   if (mark(m, ST_FINAL, stream)) return 1;
   return 0;
 }

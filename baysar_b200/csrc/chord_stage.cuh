@@ -931,6 +931,7 @@ struct PixelFoldArgs {
   const float* inv_err;     // [P] float32 1 / err of the chord's pixels (log-posterior-only fast loop), may be nullptr
   const double* tsum;       // [rows][n_col_tiles][2] exact column sums per tile (converter groups), may be nullptr
   int n_col_tiles, n_fold_tiles, tile_n;
+  double* logp;             // log-posterior path of single-chord models: also do K3's job (sum of components, flags)
   const double* aux;        // [N][BAYSAR_AUX_STRIDE]
   double* components;
   double* spectra;          // optional [N][P]
@@ -941,8 +942,10 @@ template <int NT>
 __global__ void __launch_bounds__(NT) pixel_fold_kernel(ModelDev m, PixelFoldArgs a) {
 #ifdef BAYSAR_CPU_EMU
   double* scratch = reinterpret_cast<double*>(emu_dynamic_smem());
+  float* row = reinterpret_cast<float*>(scratch + 160);
 #else
   __shared__ double scratch[64 + 32 + 64];  // reductions, 64 float tile corrections, 64 float64 tile scales
+  extern __shared__ __align__(16) float row[];  // this theta's contraction output (cp_pitch floats)
 #endif
   const int tid = threadIdx.x;
   const int64_t n = blockIdx.x;
@@ -956,21 +959,29 @@ __global__ void __launch_bounds__(NT) pixel_fold_kernel(ModelDev m, PixelFoldArg
   const double* ax = a.aux + n * BAYSAR_AUX_STRIDE;
   const int F = ch[CH_F];
   const float mn = (float)ax[1];
-  const float* row = a.cp + n * a.cp_pitch;
   const float* sp = a.spec + n * a.spec_pitch + a.spec_pad;
   uint32_t st = 0;
+  // Stage the row in shared memory with one round of coalesced 16-byte loads: everything below reads it several times
+  // (edge columns, tile sums, pixels through the pixel -> column map), and as dependent global loads those reads
+  // made the kernel latency-bound.
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.cp + n * a.cp_pitch);
+    float4* dst = reinterpret_cast<float4*>(row);
+    for (int i = tid; i < (int)(a.cp_pitch / 4); i += NT) dst[i] = src[i];
+  }
   double part = 0.0;
+  for (int t = tid; t < a.n_dl + a.n_dr; t += NT) {  // end zones of the pulled-back trapz weights
+    const int s = t < a.n_dl ? t : F - a.n_dr + (t - a.n_dl);
+    part += (double)sp[s] * a.dtab[t];
+  }
+  if (tid == 0) scratch[BAYSAR_BG_SLOT] = pow(10.0, th[ch[CH_BG_IDX]]);
+  __syncthreads();
   for (int t = tid; t < a.x_l + a.x_r; t += NT) {  // clip correction of the explicit edge columns
     const int j = t < a.x_l ? t : F - a.x_r + (t - a.x_l);
     const float v = t < a.x_l ? row[a.col_left0 + t] : row[a.col_right0 + (t - a.x_l)];
     if (!(v - v == 0.f)) st |= 1u << 8;
     if (v < mn) part += ((j == 0 || j == F - 1) ? 0.5 : 1.0) * ((double)mn - (double)v);
   }
-  for (int t = tid; t < a.n_dl + a.n_dr; t += NT) {  // end zones of the pulled-back trapz weights
-    const int s = t < a.n_dl ? t : F - a.n_dr + (t - a.n_dl);
-    part += (double)sp[s] * a.dtab[t];
-  }
-  if (tid == 0) scratch[BAYSAR_BG_SLOT] = pow(10.0, th[ch[CH_BG_IDX]]);
   double red_p[1] = {part};
   block_sum<NT, 1>(red_p, scratch);
   const double bg = scratch[BAYSAR_BG_SLOT];
@@ -1008,6 +1019,7 @@ __global__ void __launch_bounds__(NT) pixel_fold_kernel(ModelDev m, PixelFoldArg
     __syncthreads();
     const int P = ch[CH_P], poff = ch[CH_PIX_OFF];
     double acc = 0.0;
+#pragma unroll 4
     for (int p = tid; p < P; p += NT) {
       const int col = a.pix_col[p];
       double fm;
@@ -1034,6 +1046,20 @@ __global__ void __launch_bounds__(NT) pixel_fold_kernel(ModelDev m, PixelFoldArg
     double red4[1] = {acc};
     block_sum<NT, 1>(red4, scratch);
     if (tid == 0) a.components[n * (int64_t)ncomp_cols + c] = -red4[0];
+    st = __syncthreads_or((int)st);
+    if (tid == 0) {
+      if (a.logp) {  // single-chord model: logP = sum of the components in list order, output flags (finalize.cuh)
+        const double* comp = a.components + n * (int64_t)ncomp_cols;
+        double s = 0.0;
+        for (int k = 0; k < ncomp_cols; ++k) s = s + (k == c ? -red4[0] : comp[k]);
+        if (s != s) st |= 1u << 13;
+        else if (s - s != 0.0) st |= 1u << 14;
+        else if (s >= 0.0) st |= 1u << 15;
+        a.logp[n] = s;
+      }
+      if (st) atomicOr(&a.status[n], st);
+    }
+    return;
   }
   st = __syncthreads_or((int)st);
   if (tid == 0 && st) atomicOr(&a.status[n], st);
