@@ -49,7 +49,10 @@ constexpr int THREADS = (WARP_BUILDER0 + BUILDER_WARPS) * 32;
 
 template <int TN>
 struct Cfg {
-  static constexpr int N_ACC_HI = TN == 64 ? 4 : 2;
+#ifndef BAYSAR_PXC_NACC128
+#define BAYSAR_PXC_NACC128 2
+#endif
+  static constexpr int N_ACC_HI = TN == 64 ? 4 : BAYSAR_PXC_NACC128;
   static constexpr int ACC_COLS = (N_ACC_HI + 1) * TN;        // 320 / 384 TMEM columns of accumulators
   static constexpr int A_STAGES = (512 - ACC_COLS) / 32;      // 6 / 4 tensor-memory stages of the split A operand
   static constexpr int B_STAGES = TN == 64 ? 8 : 6;           // shared-memory stages of generated B tiles
@@ -420,8 +423,9 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p, cons
           float f[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float hh = __uint_as_float(v[0][e4 + e]) + __uint_as_float(v[1][e4 + e]);
-            if (C::N_ACC_HI == 4) hh += __uint_as_float(v[2][e4 + e]) + __uint_as_float(v[C::N_ACC_HI - 1][e4 + e]);
+            float hh = __uint_as_float(v[0][e4 + e]);
+            if (C::N_ACC_HI >= 2) hh += __uint_as_float(v[C::N_ACC_HI >= 2 ? 1 : 0][e4 + e]);
+            if (C::N_ACC_HI == 4) hh += __uint_as_float(v[C::N_ACC_HI == 4 ? 2 : 0][e4 + e]) + __uint_as_float(v[C::N_ACC_HI - 1][e4 + e]);
             f[e] = hh + __uint_as_float(v[C::N_ACC_HI][e4 + e]);
           }
           const int chunk = (c0 + e4) >> 2;

@@ -26,7 +26,8 @@ def build_library(force=False, verbose=False):
         if LIB_PATH.stat().st_mtime >= newest:
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-Xptxas", "-v", "-o", str(LIB_PATH), str(CSRC / "baysar_abi.cu")]
+    extra = os.environ.get("BAYSAR_NVCC_EXTRA", "").split()  # experiments only (e.g. -DBAYSAR_PXC_NACC128=1)
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-Xptxas", "-v", "-o", str(LIB_PATH), str(CSRC / "baysar_abi.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

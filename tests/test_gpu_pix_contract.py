@@ -47,3 +47,22 @@ def test_pix_contract_matches_float64(F, K, sigma, P, tile_n):
     assert err_l.abs().max().item() < 6e-6 and err_r.abs().max().item() < 6e-6
     assert (kappa - 1).abs().max().item() < 1e-5
     assert err_k.abs().max().item() < 4e-6 and abs(err_k.mean().item()) < 2e-7
+
+
+def test_pix_contract_is_bit_reproducible():
+    """Same input, same schedule, same accumulation order: outputs and exact tile sums must not change run to run
+    (a timing-dependent hazard in the A pipeline shows up here as stale rows)."""
+    import torch
+
+    from baysar_b200 import runtime
+
+    F, K, sigma, P = CASES[0]
+    s, taps, idx, frac = make_case(F, K, sigma, P)
+    s = np.tile(s, (8, 1)) * (1.0 + 1e-3 * np.arange(2048)[:, None] / 2048)
+    sd = torch.as_tensor(s, dtype=torch.float32, device="cuda")
+    for tile_n in (128, 64):
+        ref = runtime.debug_pix_contract(sd, taps, idx, frac, tile_n)
+        for _ in range(4):
+            res = runtime.debug_pix_contract(sd, taps, idx, frac, tile_n)
+            assert torch.equal(res["out"], ref["out"])
+            assert torch.equal(res["tsum_groups"], ref["tsum_groups"])
