@@ -20,7 +20,8 @@ X_TRIPLET = [[[4024.78, 4025.33, 4026.33]], [[0.541, 0.373, 0.086]]]
 
 
 class Workload:
-    def __init__(self, name, input_kwargs, los, reference_theta, description, profile=None, curvature=None):
+    def __init__(self, name, input_kwargs, los, reference_theta, description, profile=None, curvature=None,
+                 extra_priors=()):
         self.name = name
         self.input_kwargs = input_kwargs
         self.los = los  # None -> profile default linspace(-10, 25, 50)
@@ -28,6 +29,13 @@ class Workload:
         self.description = description
         self.profile = profile      # None -> EsymmtricCauchyPlasma; {"family": "bowman_tee" | "mesh", ...kwargs}
         self.curvature = curvature  # BaysarPosterior(curvature=...) (CurvatureCost needs the mesh family)
+        # optional priors appended after the default components: [(class name in priors.py, keyword arguments)]
+        self.extra_priors = list(extra_priors)
+
+    def make_priors(self, ns, plasma=None, plasma_state=None):
+        """Instances of the optional priors from the namespace ``ns`` (the reference's ``baysar.priors`` or
+        ``baysar_b200.priors``: same class names and signatures; TeMinPrior takes the plasma_state, the others the plasma)."""
+        return [getattr(ns, name)(plasma_state if name == "TeMinPrior" else plasma, **kw) for name, kw in self.extra_priors]
 
     def make_profile(self, ns):
         """Profile-function object from the namespace ``ns`` — the reference's ``baysar.lineshapes`` module,
@@ -136,6 +144,28 @@ def multi_species_bowman(background=False):
     ref["electron_temperature"] = [0.9, 3.0, 2.0, 3.0, 5.0, 0.5] + ([-0.5] if background else [])
     return Workload("multi_bowman" + ("_bg" if background else ""), wl.input_kwargs, np.linspace(-15.0, 25.0, 120), ref,
                     "multi-species chord, BowmanTee ne/Te profiles", profile=dict(family="bowman_tee", background=background))
+
+
+OPTIONAL_PRIORS = [("ElectronDensityTDVCost", dict(threshold=2.0, sigma=0.3)), ("PeakTePrior", dict(te_min=8.0, te_err=1.5)),
+                   ("TauPrior", dict(mean=0.5, sigma=0.4)), ("WallConditionsPrior", dict(te_min=0.6, ne_min=3e12)),
+                   ("SimpleWallPrior", dict(te_min=0.6, ne_min=3e12)), ("TeMinPrior", dict(ratio=12.0, sigma=2.5)),
+                   ("TeTauPrior", dict(sigma=0.4)), ("ImpurityTauPrior", dict(sigma=0.6))]
+
+
+def multi_species_priors():
+    """The multi-species chord with the optional priors of priors.py that only read the plasma state (TDV cost, peak /
+    wall / minimum temperature, tau ordering priors), appended after the default components."""
+    wl = multi_species(1)
+    return Workload("multi_priors", wl.input_kwargs, wl.los, wl.reference_theta, wl.description + ", optional priors",
+                    extra_priors=OPTIONAL_PRIORS)
+
+
+def multi_species_bowman_priors():
+    """BowmanTee profiles with BowmanTeePrior (priors.py:484-507) and two of the state priors."""
+    wl = multi_species_bowman()
+    return Workload("multi_bowman_priors", wl.input_kwargs, wl.los, wl.reference_theta, wl.description + ", optional priors",
+                    profile=wl.profile, extra_priors=[("BowmanTeePrior", dict(sigma_err=0.3)), ("PeakTePrior", {}),
+                                                      ("TeMinPrior", {})])
 
 
 def multi_species_mesh(curvature=None):

@@ -744,6 +744,7 @@ int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar
   d.pix_frac = static_cast<const double*>(dev.ptr(SEC_PIX_FRAC));
   d.mesh_x = static_cast<const double*>(dev.ptr(SEC_MESH_X));
   d.mesh_lo = static_cast<const int*>(dev.ptr(SEC_MESH_LO));
+  d.pr_aux = static_cast<const int*>(dev.ptr(SEC_PR_AUX));
 
   // shared memory the chord kernel needs: the largest chord decides (one launch covers all chords)
   const int n_chords = (int)m->I[I_N_CHORDS];

@@ -53,6 +53,7 @@ struct ModelDev {
   const double* pix_frac;
   const double* mesh_x;
   const int* mesh_lo;
+  const int* pr_aux;
 };
 
 // approximate reciprocal / square root (one MUFU op each, ~1 ulp): the float32 spectral sweeps do not need IEEE rounding

@@ -9,7 +9,7 @@
 #define BAYSAR_LAYOUT_H
 
 #define BAYSAR_BLOB_MAGIC 0x4252415359534142LL /* "BAYSYSAB" */
-#define BAYSAR_BLOB_VERSION 7
+#define BAYSAR_BLOB_VERSION 8
 
 enum BaysarSection {
   SEC_I,              /* int64  [I_COUNT]           model-wide integer scalars                         */
@@ -49,6 +49,7 @@ enum BaysarSection {
   SEC_PIX_FRAC,       /* double [sum P]             default wavelength map: interpolation weight        */
   SEC_MESH_X,         /* double [mesh_ne_n + mesh_te_n]  MeshLine knot positions (density, then temperature)  */
   SEC_MESH_LO,        /* int32  [2][L]              MeshLine: lower knot of every LOS point (density, temperature) */
+  SEC_PR_AUX,         /* int32  [..]                index lists of the optional priors (theta indices; PR_I0 = offset, PR_I1 = count) */
   SEC_COUNT
 };
 
@@ -135,6 +136,15 @@ enum BaysarPriorKind {
   PRIOR_INTENSITY_CAL,
   PRIOR_GAUSSIAN_IF,
   PRIOR_CURVATURE,
+  PRIOR_TDV,              /* optional priors (passed in priors=[...], reference priors.py): ElectronDensityTDVCost */
+  PRIOR_PEAK_TE,          /* PeakTePrior                                                                          */
+  PRIOR_TAU,              /* TauPrior: aux = pairs of tau theta indices (consecutive ions of an element)          */
+  PRIOR_WALL_CONDITIONS,  /* WallConditionsPrior                                                                  */
+  PRIOR_SIMPLE_WALL,      /* SimpleWallPrior                                                                      */
+  PRIOR_TE_MIN,           /* TeMinPrior                                                                           */
+  PRIOR_TE_TAU,           /* TeTauPrior: aux = tau theta index of every impurity species                          */
+  PRIOR_IMPURITY_TAU,     /* ImpurityTauPrior: aux = pairs of tau theta indices (equal charge, consecutive elements) */
+  PRIOR_BOWMAN_TEE,       /* BowmanTeePrior                                                                       */
   PRIOR_KIND_COUNT
 };
 enum BaysarPrI { PR_KIND, PR_I0, PR_I1, PR_I_COUNT };

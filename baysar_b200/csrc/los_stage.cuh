@@ -431,6 +431,68 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     } else if (kind == PRIOR_GAUSSIAN_IF) {  // priors.py:1079-1089
       double t0 = (p10[pi[PR_I0]] - 0.8) / 0.1;
       val = -0.5 * (t0 * t0);
+    } else if (kind == PRIOR_TDV) {  // ElectronDensityTDVCost, priors.py:67-80: d0 threshold, d1 sigma
+      double s = 0.0;
+      for (int l = lane; l + 1 < L; l += 32) {
+        const double ne_tdv = fabs(ne_s[l + 1] - ne_s[l]), ni_tdv = fabs(nm_s[l + 1] - nm_s[l]);
+        s += (ne_tdv - ni_tdv) / ni_tdv;
+      }
+      val = low_pass(warp_sum(s) / pd[PR_D0], 1.0, pd[PR_D1]);
+    } else if (kind == PRIOR_PEAK_TE || kind == PRIOR_TE_MIN || kind == PRIOR_TE_TAU) {
+      double tmax = -1.7976931348623157e308, tmin = 1.7976931348623157e308;
+      for (int l = lane; l < L; l += 32) {
+        tmax = te_s[l] > tmax ? te_s[l] : tmax;
+        tmin = te_s[l] < tmin ? te_s[l] : tmin;
+      }
+      tmax = warp_max(tmax);
+      tmin = -warp_max(-tmin);
+      if (kind == PRIOR_PEAK_TE) {  // priors.py:241-251: d0 te_min, d1 te_err
+        val = low_pass(tmax, pd[PR_D0], pd[PR_D1]);
+      } else if (kind == PRIOR_TE_MIN) {  // priors.py:670-680: d0 ratio, d1 sigma
+        val = high_pass(tmax / tmin, pd[PR_D0], pd[PR_D1]);
+      } else {  // TeTauPrior, priors.py:696-727: log10 tau of every impurity species inside te_max-dependent bounds
+        const double b0 = tmax > 5.0 ? -5.0 : (tmax < 3.0 ? 3.0 : -3.0), b1 = tmax > 5.0 ? 0.0 : 7.0;
+        double cost = 0.0;
+        for (int q = 0; q < pi[PR_I1]; ++q) {  // sequential, like the reference's loop
+          const double lt = l10[m.pr_aux[pi[PR_I0] + q]];
+          cost += 0.0 + high_pass(lt, b0, pd[PR_D0]) + low_pass(lt, b1, pd[PR_D0]);
+        }
+        val = cost;
+      }
+    } else if (kind == PRIOR_TAU) {  // TauPrior, priors.py:254-301: -diff(log10 tau) of consecutive ions; d0 mean, d1 sigma
+      double cost = 0.0;
+      for (int q = 0; q < pi[PR_I1]; ++q) {
+        const int* pr = m.pr_aux + pi[PR_I0] + 2 * q;
+        cost += low_pass(-(l10[pr[1]] - l10[pr[0]]), pd[PR_D0], pd[PR_D1]);
+      }
+      val = cost;
+    } else if (kind == PRIOR_WALL_CONDITIONS) {  // priors.py:432-456: d0 te_min, d1 ne_min, d2 te_err, d3 ne_err
+      double cost = 0.0;
+      cost += low_pass(te_s[0] / pd[PR_D0], 1.0, pd[PR_D2]);
+      cost += low_pass(te_s[L - 1] / pd[PR_D0], 1.0, pd[PR_D2]);
+      cost += low_pass(ne_s[0] / pd[PR_D1], 1.0, pd[PR_D3]);
+      cost += low_pass(ne_s[L - 1] / pd[PR_D1], 1.0, pd[PR_D3]);
+      val = cost;
+    } else if (kind == PRIOR_SIMPLE_WALL) {  // priors.py:459-481
+      val = 0.0 + low_pass(te_s[L - 1], pd[PR_D0], pd[PR_D2]) + low_pass(ne_s[L - 1], pd[PR_D1], pd[PR_D3]);
+    } else if (kind == PRIOR_IMPURITY_TAU) {  // priors.py:395-429: raw tau parameters of equal charge states; d0 sigma
+      double cost = 0.0;
+      int group = -1;
+      double gsum = 0.0;
+      for (int q = 0; q < pi[PR_I1]; ++q) {  // aux triples (group, idx_a, idx_b): -0.5 * sum over a group, added per group
+        const int* pr = m.pr_aux + pi[PR_I0] + 3 * q;
+        if (pr[0] != group) {
+          if (group >= 0) cost += -0.5 * gsum;
+          group = pr[0];
+          gsum = 0.0;
+        }
+        const double t = (th[pr[2]] - th[pr[1]]) / pd[PR_D0];
+        gsum += t * t;
+      }
+      if (group >= 0) cost += -0.5 * gsum;
+      val = cost;
+    } else if (kind == PRIOR_BOWMAN_TEE) {  // priors.py:484-506: Te width parameter not above the ne one; d0 sigma_err
+      val = 0.0 + low_pass(th[te_idx + 1] - th[ne_idx + 2], 0.0, pd[PR_D0]);
     }
     if (lane == 0) comp[k] = val;
   }

@@ -31,7 +31,7 @@ def _parse_layout():
 
 ENUMS, BLOB_MAGIC, BLOB_VERSION = _parse_layout()
 SEC = ENUMS["BaysarSection"]
-_DTYPES = {"SEC_MESH_LO": np.int32, "SEC_I": np.int64, "SEC_SP_I": np.int32, "SEC_ELEM_DENS_IDX": np.int32, "SEC_UL_I": np.int32,
+_DTYPES = {"SEC_PR_AUX": np.int32, "SEC_MESH_LO": np.int32, "SEC_I": np.int64, "SEC_SP_I": np.int32, "SEC_ELEM_DENS_IDX": np.int32, "SEC_UL_I": np.int32,
            "SEC_PR_I": np.int32, "SEC_CSO_OFF": np.int32, "SEC_CSO_UL": np.int32, "SEC_CH_I": np.int32,
            "SEC_CL_I": np.int32, "SEC_PIX_IDX": np.int32}
 
@@ -315,6 +315,7 @@ def compile_model(plasma, chords, priors):
     pr_i = np.zeros((max(len(priors), 1), e["BaysarPrI"]["PR_I_COUNT"]), dtype=np.int32)
     pr_d = np.zeros((max(len(priors), 1), e["BaysarPrD"]["PR_D_COUNT"]))
     cso_off, cso_ul = [0] * (len(plasma.impurities) + 1), []
+    pr_aux = []  # index lists of the optional priors
     for k, p in enumerate(priors):
         pr_i[k, 0] = E_PR[p.kind]
         if p.kind == "PRIOR_STARK_TO_PEAK":
@@ -333,7 +334,40 @@ def compile_model(plasma, chords, priors):
             pr_i[k, 1] = _theta_index(plasma, "calint_func_0")
         elif p.kind == "PRIOR_CURVATURE":
             pr_d[k, 0] = p.scale
+        elif p.kind == "PRIOR_TDV":
+            pr_d[k, :2] = [p.threshold, p.sigma]
+        elif p.kind == "PRIOR_PEAK_TE":
+            pr_d[k, :2] = [p.te_min, p.te_err]
+        elif p.kind == "PRIOR_TE_MIN":
+            pr_d[k, :2] = [p.ratio, p.sigma]
+        elif p.kind in ("PRIOR_WALL_CONDITIONS", "PRIOR_SIMPLE_WALL"):
+            pr_d[k, :4] = [p.te_min, p.ne_min, p.te_err, p.ne_err]
+        elif p.kind == "PRIOR_TAU":
+            pairs = p.tau_pairs(plasma)
+            pr_i[k, 1], pr_i[k, 2] = len(pr_aux), len(pairs)
+            for a_tag, b_tag in pairs:
+                pr_aux += [_theta_index(plasma, a_tag), _theta_index(plasma, b_tag)]
+            pr_d[k, :2] = [p.mean, p.sigma]
+        elif p.kind == "PRIOR_TE_TAU":
+            tags = [f"{z}_tau" for z in plasma.impurity_species]
+            pr_i[k, 1], pr_i[k, 2] = len(pr_aux), len(tags)
+            pr_aux += [_theta_index(plasma, t) for t in tags]
+            pr_d[k, 0] = p.sigma
+        elif p.kind == "PRIOR_IMPURITY_TAU":
+            triples = []
+            for g, tags in enumerate(p.tau_groups(plasma)):
+                triples += [[g, _theta_index(plasma, a_tag), _theta_index(plasma, b_tag)]
+                            for a_tag, b_tag in zip(tags[:-1], tags[1:])]
+            pr_i[k, 1], pr_i[k, 2] = len(pr_aux), len(triples)
+            for t in triples:
+                pr_aux += t
+            pr_d[k, 0] = p.sigma
+        elif p.kind == "PRIOR_BOWMAN_TEE":
+            if profile_kind != 1:
+                raise AttributeError("BowmanTeePrior needs the BowmanTee profile family")
+            pr_d[k, 0] = p.sigma_err
     sec["SEC_PR_I"], sec["SEC_PR_D"] = pr_i, pr_d
+    sec["SEC_PR_AUX"] = np.array(pr_aux or [0], dtype=np.int32)
     sec["SEC_CSO_OFF"] = np.array(cso_off, dtype=np.int32)
     sec["SEC_CSO_UL"] = np.array(cso_ul or [0], dtype=np.int32)
 

@@ -68,8 +68,8 @@ def build_components(plasma, input_dict, curvature=None, passed_priors=()):
         if not isinstance(p, _DevicePrior):
             raise NotImplementedError(f"user prior {type(p).__name__} has no device implementation; only the default "
                                       "components of posterior.py:108-161 run on the CUDA path")
-        if not any(type(q) is type(p) for q in priors):
-            priors.append(p)
+        # posterior.py:163-165: `got_p(p)` compares types with the INSTANCE p, so a passed prior is always appended
+        priors.append(p)
     return chords, priors
 
 

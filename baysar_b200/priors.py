@@ -111,3 +111,101 @@ class CalibrationPrior(_DevicePrior):
 
 class GaussianInstrumentFunctionPrior(_DevicePrior):
     kind = "PRIOR_GAUSSIAN_IF"  # priors.py:1079-1089 (mean 0.8, std 0.1)
+
+
+# ---- optional priors (reference priors.py), passed as ``BaysarPosterior(..., priors=[...])``.  Constructor signatures
+# follow the reference (first argument: the plasma, or its plasma_state for TeMinPrior); the argument is not used here —
+# the model compiler resolves parameter indices from the posterior's own plasma — so ``None`` may be passed when the
+# prior is created before the posterior exists.
+class ElectronDensityTDVCost(_DevicePrior):
+    kind = "PRIOR_TDV"  # priors.py:67-80
+
+    def __init__(self, plasma=None, threshold=1, sigma=0.2):
+        super().__init__()
+        self.threshold, self.sigma = threshold, sigma
+
+
+class PeakTePrior(_DevicePrior):
+    kind = "PRIOR_PEAK_TE"  # priors.py:241-251
+
+    def __init__(self, plasma=None, te_min=1, te_err=1):
+        super().__init__()
+        self.te_min, self.te_err = te_min, te_err
+
+
+class TauPrior(_DevicePrior):
+    kind = "PRIOR_TAU"  # priors.py:254-301
+
+    def __init__(self, plasma=None, mean=0, sigma=0.2):
+        super().__init__()
+        self.mean, self.sigma = mean, sigma
+
+    @staticmethod
+    def tau_pairs(plasma):
+        """(tag_a, tag_b) of consecutive ions of every impurity element, in ``tau_difference`` order (priors.py:269-284)."""
+        pairs = []
+        for imp in plasma.impurities:
+            tags = [f"{imp}_{ion.split('_')[1]}_tau" for ion in plasma.species if imp + "_" in ion]
+            pairs += list(zip(tags[:-1], tags[1:]))
+        return pairs
+
+
+class WallConditionsPrior(_DevicePrior):
+    kind = "PRIOR_WALL_CONDITIONS"  # priors.py:432-456
+
+    def __init__(self, plasma=None, te_min=0.5, ne_min=2e12, te_err=None, ne_err=None):
+        super().__init__()
+        self.te_min, self.ne_min = te_min, ne_min
+        self.te_err = 0.2 if te_err is None else te_err
+        self.ne_err = 0.2 if ne_err is None else ne_err
+
+
+class SimpleWallPrior(_DevicePrior):
+    kind = "PRIOR_SIMPLE_WALL"  # priors.py:459-481
+
+    def __init__(self, plasma=None, te_min=0.5, ne_min=2e12, te_err=None, ne_err=None):
+        super().__init__()
+        self.te_min, self.ne_min = te_min, ne_min
+        self.te_err = 0.5 * te_min if te_err is None else te_err
+        self.ne_err = 0.5 * ne_min if ne_err is None else ne_err
+
+
+class TeMinPrior(_DevicePrior):
+    kind = "PRIOR_TE_MIN"  # priors.py:670-680 (takes the plasma_state in the reference)
+
+    def __init__(self, plasma_state=None, ratio=2.0, sigma=0.05):
+        super().__init__()
+        self.ratio, self.sigma = ratio, sigma
+
+
+class TeTauPrior(_DevicePrior):
+    kind = "PRIOR_TE_TAU"  # priors.py:696-727
+
+    def __init__(self, plasma=None, sigma=0.3):
+        super().__init__()
+        self.sigma = sigma
+
+
+class ImpurityTauPrior(_DevicePrior):
+    kind = "PRIOR_IMPURITY_TAU"  # priors.py:395-429
+
+    def __init__(self, plasma=None, sigma=0.3):
+        super().__init__()
+        self.sigma = sigma
+
+    @staticmethod
+    def tau_groups(plasma):
+        """Per charge state seen in more than one element: the tau tags of those elements' ions, in species order."""
+        groups = {}
+        for sp in plasma.impurity_species:
+            z0, z = sp.split("_")
+            groups.setdefault(z, []).append(z0)
+        return [[f"{z0}_{z}_tau" for z0 in elems] for z, elems in groups.items() if len(elems) > 1]
+
+
+class BowmanTeePrior(_DevicePrior):
+    kind = "PRIOR_BOWMAN_TEE"  # priors.py:484-506
+
+    def __init__(self, plasma=None, sigma_err=0.2, nu_err=0.2):
+        super().__init__()
+        self.sigma_err, self.nu_err = sigma_err, nu_err

@@ -96,6 +96,8 @@ def main():
         ("multi_bowman", configs.multi_species_bowman(), 10, 1, {}),
         ("multi_bowman_bg", configs.multi_species_bowman(background=True), 8, 0, {}),
         ("multi_mesh_curv", configs.multi_species_mesh(curvature=50.0), 10, 1, {}),
+        ("multi_priors", configs.multi_species_priors(), 12, 0, {}),
+        ("multi_bowman_priors", configs.multi_species_bowman_priors(), 8, 0, {}),
     ]
     only = sys.argv[1:]
     for name, wl, n, nfine, attrs in jobs:

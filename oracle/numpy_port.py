@@ -247,9 +247,10 @@ def curvature(profile):
 class OraclePosterior:
     """Stateless restatement of ``BaysarPosterior`` for the default component set."""
 
-    def __init__(self, input_dict, provider, profile_function=None, curvature=None):
+    def __init__(self, input_dict, provider, profile_function=None, curvature=None, extra_priors=()):
         self.input_dict = input_dict
         self.curvature = curvature
+        self.extra_priors = list(extra_priors)  # [(class name, kwargs)] appended after the default components
         self.provider = provider
         d = input_dict
         # ---- PlasmaLine.__init__ (plasmas.py:295-406)
@@ -548,6 +549,9 @@ class OraclePosterior:
                     if "species" in l and l["species"] in self.impurity_species and l["species"] not in index:
                         index[l["species"]] = (c, k)
             p.append(("ChargeStateOrderPrior", dict(index=index)))
+        # posterior.py:163-165: passed priors come last (`got_p` compares a type with an instance, so they are
+        # appended even when a default component of the same class exists)
+        p.extend((name, dict(args)) for name, args in self.extra_priors)
         self.priors = p
         self.component_names = ["SpectrometerChord"] * self.num_chords + [n for n, _ in p]
 
@@ -620,6 +624,7 @@ class OraclePosterior:
             else:  # cal, calint_func, background, species dens/Ti/tau, X lines -> 10**theta
                 v = np.power(10, v)
             st[p] = v
+            st.setdefault("_plasma_theta", {})[p] = theta[slc].flatten()  # plasma.plasma_theta (raw slices)
         ne = st["electron_density"]
         total = 0
         for elem in self.impurities:  # plasmas.py:876-889 (concstar)
@@ -843,6 +848,64 @@ class OraclePosterior:
             return (-0.5 * np.square((1 - st["cal_0"]) / 0.2)).sum()
         if name == "GaussianInstrumentFunctionPrior":  # priors.py:1079-1089
             return -0.5 * np.square((st["calint_func_0"][0] - 0.8) / 0.1)
+        # ---- optional priors a user passes in `priors=[...]` (posterior.py:163-165); defaults from their signatures
+        raw = st["_plasma_theta"]
+        if name == "ElectronDensityTDVCost":  # priors.py:67-80
+            ne_tdv = abs(np.diff(ne))
+            ni_tdv = abs(np.diff(st["main_ion_density"]))
+            mean = (ne_tdv - ni_tdv) / ni_tdv
+            return low_pass(mean.sum() / args.get("threshold", 1), 1, args.get("sigma", 0.2))
+        if name == "PeakTePrior":  # priors.py:241-251
+            return low_pass(te.max(), args.get("te_min", 1), args.get("te_err", 1))
+        if name == "TauPrior":  # priors.py:254-301 (tau_difference: -diff(log10 tau) between consecutive ions of an element)
+            taus, diffs = [], []
+            for imp in self.impurities:
+                ions = [ion for ion in self.species if imp + "_" in ion]
+                for ion in ions:
+                    charge = ion.split("_")[1]
+                    taus.append(st[imp + "_" + str(charge) + "_tau"][0])
+                for dtau in -np.diff(np.log10(taus[-len(ions):])):
+                    diffs.append(dtau)
+            return np.array([low_pass(d, args.get("mean", 0), args.get("sigma", 0.2)) for d in diffs]).sum()
+        if name == "WallConditionsPrior":  # priors.py:432-456
+            te_err = 0.2 if args.get("te_err") is None else args["te_err"]
+            ne_err = 0.2 if args.get("ne_err") is None else args["ne_err"]
+            cost = 0
+            for t in [te[0], te[-1]]:
+                cost += low_pass(t / args.get("te_min", 0.5), 1, te_err)
+            for nn in [ne[0], ne[-1]]:
+                cost += low_pass(nn / args.get("ne_min", 2e12), 1, ne_err)
+            return cost
+        if name == "SimpleWallPrior":  # priors.py:459-481
+            te_min, ne_min = args.get("te_min", 0.5), args.get("ne_min", 2e12)
+            te_err = 0.5 * te_min if args.get("te_err") is None else args["te_err"]
+            ne_err = 0.5 * ne_min if args.get("ne_err") is None else args["ne_err"]
+            return 0 + low_pass(te[-1], te_min, te_err) + low_pass(ne[-1], ne_min, ne_err)
+        if name == "TeMinPrior":  # priors.py:670-680
+            return high_pass(te.max() / te.min(), args.get("ratio", 2.0), args.get("sigma", 0.05))
+        if name == "TeTauPrior":  # priors.py:696-727
+            te_max = te.max()
+            bounds = [-5, 0] if te_max > 5 else ([3, 7] if te_max < 3 else [-3, 7])
+            sig = args.get("sigma", 0.3)
+            cost = 0
+            for z in self.impurity_species:
+                log_tau = np.log10(st[z + "_tau"][0])
+                cost += 0 + high_pass(log_tau, bounds[0], sig) + low_pass(log_tau, bounds[1], sig)
+            return cost
+        if name == "ImpurityTauPrior":  # priors.py:395-429 (raw tau parameters of equal charge states across elements)
+            groups = {}
+            for sp in self.impurity_species:
+                z0, z = sp.split("_")
+                groups.setdefault(z, []).append(z0)
+            cost = 0
+            for charge, elems in groups.items():
+                if len(elems) > 1:
+                    vals = [raw[z0 + f"_{charge}" + "_tau"][0] for z0 in elems]
+                    cost += -0.5 * (np.square(np.diff(vals) / args.get("sigma", 0.3))).sum()
+            return cost
+        if name == "BowmanTeePrior":  # priors.py:484-506
+            sigma_diff = raw["electron_temperature"][1] - raw["electron_density"][2]
+            return 0.0 + low_pass(sigma_diff, 0.0, args.get("sigma_err", 0.2))
         raise KeyError(name)
 
     def evaluate(self, theta, details=False):

@@ -23,6 +23,12 @@ def build_reference_posterior(workload, provider=None, seed=0, plasma_attrs=None
                                                  curvature=getattr(workload, "curvature", None))
     for k, v in (plasma_attrs or {}).items():
         setattr(post.plasma, k, v)
+    # optional priors: the reference appends passed priors after the defaults (posterior.py:163-165); they need the
+    # posterior's own plasma, so they are appended here the way a user script does
+    if getattr(workload, "extra_priors", None):
+        post(list(workload.theta_from_tags(post.plasma.slices, post.random_start())), True)  # fills plasma_state
+        post.posterior_components.extend(workload.make_priors(mods["priors"], plasma=post.plasma,
+                                                              plasma_state=post.plasma.plasma_state))
     return post
 
 

@@ -20,7 +20,7 @@ static ModelDev view(const unsigned char* blob) {
   d.ch_d = (const double*)P(SEC_CH_D); d.cl_i = (const int*)P(SEC_CL_I); d.cl_d = (const double*)P(SEC_CL_D);
   d.comp_d = (const double*)P(SEC_COMP_D); d.y = (const double*)P(SEC_Y); d.err = (const double*)P(SEC_ERR);
   d.ifn = (const double*)P(SEC_IF); d.pix_idx = (const int*)P(SEC_PIX_IDX); d.pix_frac = (const double*)P(SEC_PIX_FRAC);
-  d.mesh_x = (const double*)P(SEC_MESH_X); d.mesh_lo = (const int*)P(SEC_MESH_LO);
+  d.mesh_x = (const double*)P(SEC_MESH_X); d.mesh_lo = (const int*)P(SEC_MESH_LO); d.pr_aux = (const int*)P(SEC_PR_AUX);
   return d;
 }
 

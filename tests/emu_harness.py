@@ -37,7 +37,10 @@ def host_model(workload, atomic_data=None):
 
     d = make_input_dict(**workload.input_kwargs)
     plasma = PlasmaLine(d, profile_function=workload.make_profile(host_ns), atomic_data=atomic_data or SyntheticADAS())
-    chords, priors = build_components(plasma, d, curvature=workload.curvature)
+    import baysar_b200.priors as host_priors
+
+    chords, priors = build_components(plasma, d, curvature=workload.curvature,
+                                      passed_priors=workload.make_priors(host_priors))
     set_sensible_bounds(plasma, chords)
     blob, info = compile_model(plasma, chords, priors)
     return plasma, chords, priors, blob, info

@@ -22,8 +22,11 @@ def gpu_posterior(name):
 
     wl = WORKLOADS[name]()
     np.random.seed(3)
+    import baysar_b200.priors as host_priors
+
     return BaysarPosterior(make_input_dict(**wl.input_kwargs), profile_function=wl.make_profile(host_ns),
-                           atomic_data=SyntheticADAS(), skip_test=True, curvature=wl.curvature), wl
+                           atomic_data=SyntheticADAS(), skip_test=True, curvature=wl.curvature,
+                           priors=wl.make_priors(host_priors)), wl
 
 
 def oracle_posterior(name):

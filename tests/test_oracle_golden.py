@@ -21,7 +21,7 @@ RTOL = 1e-12
 def build(name):
     wl = WORKLOADS[name]()
     return OraclePosterior(make_input_dict(**wl.input_kwargs), SyntheticADAS(), wl.make_profile(oracle_ns),
-                           curvature=wl.curvature)
+                           curvature=wl.curvature, extra_priors=wl.extra_priors)
 
 
 @pytest.mark.parametrize("name", sorted(WORKLOADS))

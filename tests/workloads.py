@@ -15,4 +15,6 @@ WORKLOADS = {
     "multi_bowman": lambda: configs.multi_species_bowman(),
     "multi_bowman_bg": lambda: configs.multi_species_bowman(background=True),
     "multi_mesh_curv": lambda: configs.multi_species_mesh(curvature=50.0),
+    "multi_priors": lambda: configs.multi_species_priors(),
+    "multi_bowman_priors": lambda: configs.multi_species_bowman_priors(),
 }
