@@ -96,7 +96,8 @@ struct baysar_model {
   double* hdr = nullptr;
   uint32_t* status = nullptr;
   double* theta_stage = nullptr;  // for the *_host entry point
-  double* logp_stage = nullptr;
+  double* logp_stage = nullptr;     // [n] float64 logP, then [n] uint32 status
+  void* out_pinned = nullptr;       // pinned host mirror of logp_stage
   int64_t stage_cap = 0;
   size_t chord_smem_max = 0;            // fused launches covering several chords
   std::vector<size_t> chord_smem;       // per chord (the tensor path's spectral stage may drop buffer B)
@@ -853,7 +854,7 @@ void baysar_model_destroy(baysar_model_t* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   cudaFree(m->blob_dev); cudaFree(m->lines); cudaFree(m->comps); cudaFree(m->hdr); cudaFree(m->status);
-  cudaFree(m->theta_stage); cudaFree(m->logp_stage);
+  cudaFree(m->theta_stage); cudaFree(m->logp_stage); cudaFreeHost(m->out_pinned);
   cudaFree(m->spec); cudaFree(m->conv); cudaFree(m->conv_c); cudaFree(m->trapz_part); cudaFree(m->aux);
   for (float* t : m->ifc_taps_dev) cudaFree(t);
   for (uint32_t* t : m->ifc_cmask_dev) cudaFree(t);
@@ -948,19 +949,24 @@ int baysar_eval_logp_host(baysar_model_t* m, const double* theta_host, int64_t n
   CUDA_OK(cudaSetDevice(m->device));
   const int64_t np = m->I[I_N_PARAMS];
   if (n > m->stage_cap) {
-    cudaFree(m->theta_stage); cudaFree(m->logp_stage);
-    m->theta_stage = nullptr; m->logp_stage = nullptr; m->stage_cap = 0;
+    cudaFree(m->theta_stage); cudaFree(m->logp_stage); cudaFreeHost(m->out_pinned);
+    m->theta_stage = nullptr; m->logp_stage = nullptr; m->out_pinned = nullptr; m->stage_cap = 0;
     int64_t cap = n < 1024 ? 1024 : n;
     CUDA_OK(cudaMalloc(&m->theta_stage, sizeof(double) * cap * np));
-    CUDA_OK(cudaMalloc(&m->logp_stage, sizeof(double) * cap));
+    // logP and the status words of one call sit back to back ([n] float64, [n] uint32): one device-to-host copy into a
+    // pinned staging buffer (a copy into the caller's pageable arrays is staged by the driver, twice)
+    CUDA_OK(cudaMalloc(&m->logp_stage, (sizeof(double) + sizeof(uint32_t)) * cap));
+    CUDA_OK(cudaHostAlloc(&m->out_pinned, (sizeof(double) + sizeof(uint32_t)) * cap, cudaHostAllocDefault));
     m->stage_cap = cap;
   }
+  uint32_t* status_dev = reinterpret_cast<uint32_t*>(m->logp_stage + n);
   CUDA_OK(cudaMemcpyAsync(m->theta_stage, theta_host, sizeof(double) * n * np, cudaMemcpyHostToDevice, 0));
-  if (baysar_eval_logp(m, m->theta_stage, n, m->logp_stage, nullptr, nullptr, nullptr)) return 1;
-  CUDA_OK(cudaMemcpyAsync(logp_host, m->logp_stage, sizeof(double) * n, cudaMemcpyDeviceToHost, 0));
-  if (status_host)
-    CUDA_OK(cudaMemcpyAsync(status_host, m->status, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, 0));
+  if (baysar_eval_logp(m, m->theta_stage, n, m->logp_stage, status_dev, nullptr, nullptr)) return 1;
+  const size_t out_bytes = (sizeof(double) + (status_host ? sizeof(uint32_t) : 0)) * (size_t)n;
+  CUDA_OK(cudaMemcpyAsync(m->out_pinned, m->logp_stage, out_bytes, cudaMemcpyDeviceToHost, 0));
   CUDA_OK(cudaStreamSynchronize(0));
+  memcpy(logp_host, m->out_pinned, sizeof(double) * n);
+  if (status_host) memcpy(status_host, static_cast<unsigned char*>(m->out_pinned) + sizeof(double) * n, sizeof(uint32_t) * n);
   return 0;
 }
 
