@@ -29,6 +29,7 @@ class ShardedEvaluator:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._side = None  # side stream + receive buffers of the overlapped all-gather (evaluate_local(overlap=True))
 
     def local_rows(self, n_total):
         return shard_bounds(n_total, self.world, self.rank)
@@ -51,14 +52,44 @@ class ShardedEvaluator:
             parts.append(recv[r * width: r * width + (rhi - rlo)])
         return torch.cat(parts)
 
-    def evaluate_local(self, theta_rows):
-        """Weak-scaling form used by bench.py: every rank brings its own rows; returns the gathered vector."""
+    def evaluate_local(self, theta_rows, overlap=False):
+        """Weak-scaling form used by bench.py: every rank brings its own rows; returns the gathered vector.
+
+        ``overlap=True``: the all-gather runs on a side stream behind an event, so that it overlaps with whatever the
+        caller enqueues next on the current stream (the next batch of an independent-walker ensemble does not depend on
+        it); the returned tensor is valid once :meth:`wait` has been called (or the device synchronised).  Two receive
+        buffers alternate, so at most one gather may be outstanding when the next one is issued — `evaluate_local`
+        makes the side stream wait for that itself.
+        """
         local = self.eval_fn(theta_rows)
         if self.world == 1:
             return local
-        recv = local.new_empty(self.world * local.shape[0])
-        dist.all_gather_into_tensor(recv, local.contiguous(), group=self.group)
-        return recv
+        if not overlap:
+            recv = local.new_empty(self.world * local.shape[0])
+            dist.all_gather_into_tensor(recv, local.contiguous(), group=self.group)
+            return recv
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=local.device)
+            self._recv = [None, None]
+            self._turn = 0
+        n = self.world * local.shape[0]
+        k = self._turn
+        if self._recv[k] is None or self._recv[k].numel() != n:
+            self._recv[k] = local.new_empty(n)
+        ready = torch.cuda.Event()
+        ready.record()                       # local logP complete on the current stream
+        local = local.contiguous()
+        local.record_stream(self._side)      # keep the allocator from recycling it before the gather has read it
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ready)
+            dist.all_gather_into_tensor(self._recv[k], local, group=self.group)
+        self._turn ^= 1
+        return self._recv[k]
+
+    def wait(self):
+        """Make the current stream wait for the outstanding overlapped all-gathers."""
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
 
 
 def stretch_move_proposal(walkers, complement, generator=None, a=2.0):

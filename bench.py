@@ -302,8 +302,13 @@ def main():
 
     sharded = ShardedEvaluator(post.logp_batch)  # world 1: plain call; world > 1: + NCCL all-gather of logP
 
+    # N > 1: the all-gather of a step's logP (8 B per theta) runs on a side stream and overlaps with the next step: the
+    # ranks' theta shards are independent walkers, so nothing on the critical path waits for it (BAYSAR_BENCH_SYNC_GATHER=1
+    # puts it back on the compute stream).  The tail of the last gather is added to the timed total below.
+    overlap = world > 1 and os.environ.get("BAYSAR_BENCH_SYNC_GATHER") != "1"
+
     def step(i):
-        return sharded.evaluate_local(thetas_dev[i])
+        return sharded.evaluate_local(thetas_dev[i], overlap=overlap)
 
     for i in range(args.warmup):
         step(i)
@@ -320,6 +325,10 @@ def main():
         starts[k].record()
         out = step(args.warmup + k)
         ends[k].record()
+    tail0, tail1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tail0.record()
+    sharded.wait()      # outstanding overlapped all-gathers
+    tail1.record()
     torch.cuda.synchronize()
     t_wall1 = time.time()
     if world > 1:
@@ -328,7 +337,7 @@ def main():
     post.model.set_profiling(False)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
-    total_ms = torch.tensor([float(step_ms.sum())], dtype=torch.float64, device="cuda")
+    total_ms = torch.tensor([float(step_ms.sum()) + float(tail0.elapsed_time(tail1))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
@@ -433,7 +442,10 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 element-wise / f64 line-of-sight, reductions and likelihood", "data": "synthetic",
-            "config": dict(config, tensor_core_contraction=post.model.uses_tensor_cores), "clocks": clocks,
+            "config": dict(config, tensor_core_contraction=post.model.uses_tensor_cores,
+                           logp_all_gather=("none (1 GPU)" if world == 1 else
+                                            "NCCL, side stream, overlapped with the next step" if overlap else
+                                            "NCCL on the compute stream")), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch * n_params * 8,
                     "d2h_bytes_per_step": batch * (8 + 4), "steps": e2e_steps},
             "gpu_launches": post.model.launches_last_eval * args.steps, "roofline": roofline, "cpu_baseline": cpu,
