@@ -217,6 +217,27 @@ def flop_model(post):
     return {"chord": chord, "contract": contract, "dense": dense, "chord_mufu": mufu}
 
 
+def ncu_dram_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` (bytes per launch) from the committed `ncu --set full`
+    summary of the same bench command (profiles/r1_s3_<workload>_ncu_full.txt, written by tools/ncu_hotspots.py), or
+    None when no capture of this workload / kernel is committed.  Never measured under the profiler in this run."""
+    path = os.path.join(ROOT, "profiles", f"r1_s3_{workload}_ncu_full.txt")
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        lines = open(path).read().splitlines()
+    except OSError:
+        return None, None
+    total, inside, seen = 0.0, False, 0
+    for line in lines:
+        if line.startswith("## "):
+            inside = line.startswith("## void") and kernel in line
+        elif inside and line.startswith(("dram__bytes_read.sum =", "dram__bytes_write.sum =")):
+            parts = line.split("=")[1].split()
+            total += float(parts[0]) * unit.get(parts[1] if len(parts) > 1 else "byte", 1.0)
+            seen += 1
+    return (total, os.path.relpath(path, ROOT)) if seen == 2 else (None, None)
+
+
 # ----------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -415,8 +436,10 @@ def main():
         hbm_bytes += batch * sum(len(c.x_data_fm) * 8.0 + (len(c.x_data) if post.model.folded_contraction[i][0] else
                                                            len(c.x_data_fm)) * 8.0 for i, c in enumerate(post.chords))
     roofline = dict(kernels[dom])
+    traffic, traffic_src = ncu_dram_traffic(args.workload, dom)
     roofline.update({
-        "kernel": dom, "traffic": None, "kernels": kernels,
+        "kernel": dom, "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
+        "traffic_source": traffic_src, "kernels": kernels,
         "dense_reference_flop_per_eval": flops["dense"],
         "dense_equivalent_tflops": flops["dense"] * batch / (float(step_ms.mean()) * 1e-3) / 1e12,
         "stage_ms": per_call, "kernel_share_of_step": kernels[dom]["ms"] / float(step_ms.mean()),
