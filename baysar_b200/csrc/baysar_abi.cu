@@ -543,12 +543,15 @@ int ensure_ifc_workspace(baysar_model* m, int64_t n) {
 
 // Launch the chord kernel with the register budget that matches how many CTAs the shared-memory footprint lets an SM hold
 template <int MODE>
-int launch_chord_kernel(baysar_model* m, const ChordArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
+int launch_chord_kernel(baysar_model* m, const ChordArgs& a, dim3 grid, size_t smem, cudaStream_t stream, bool single_tap_only = false) {
   constexpr int NT = 256;
   static const int cap = getenv("BAYSAR_CHORD_MINB") ? atoi(getenv("BAYSAR_CHORD_MINB")) : 5;
   const int by_smem = (int)((size_t)232448 / (smem + 1024));
   const int minb = by_smem < cap ? by_smem : cap;
   auto kern = minb >= 5 ? chord_stage_kernel<NT, MODE, 5> : (minb == 4 ? chord_stage_kernel<NT, MODE, 4> : chord_stage_kernel<NT, MODE, 3>);
+  if (single_tap_only)  // every Balmer line of the chord is a guaranteed single Doppler tap: leaner build
+    kern = minb >= 5 ? chord_stage_kernel<NT, MODE, 5, false>
+                     : (minb == 4 ? chord_stage_kernel<NT, MODE, 4, false> : chord_stage_kernel<NT, MODE, 3, false>);
   CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, NT, smem, stream>>>(m->dev, a);
   CUDA_OK(cudaGetLastError());
@@ -612,7 +615,9 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
       const bool folded = fx.on && !fine_post;  // the fine-grid diagnostic needs every convolved column
       a.spec = m->spec; a.split_pitch = folded ? fx.pitch : pl.pitch; a.split_pad = folded ? fx.pad_left : pl.pad_left;
       a.aux = m->aux;
-      if (launch_chord_kernel<1>(m, a, dim3((unsigned)rows, 1), m->chord_smem[c], stream)) return 1;
+      if (launch_chord_kernel<1>(m, a, dim3((unsigned)rows, 1), m->chord_smem[c], stream,
+                                 m->ch_i[c * CH_I_COUNT + CH_B_OPTIONAL] != 0))
+        return 1;
       if (mark(m, ST_CHORD, stream)) return 1;
       if (folded) {
         // K2b': instrument function and wavelength map as one tcgen05 contraction; K2c': area identity + likelihood

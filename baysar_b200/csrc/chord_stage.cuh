@@ -83,7 +83,8 @@ __host__ __device__ static inline ChordSmem chord_smem_layout(int F, int halo, i
   s.taps_floats = (size_t)(taps_max + 8 + 3) / 4 * 4;
   s.tapd_doubles = 2 * (size_t)kd_max + 4;
   s.total = (need_b ? 2 : 1) * s.buf_floats * sizeof(float) + s.taps_floats * sizeof(float) + s.tapd_doubles * sizeof(double) +
-            192 * sizeof(double) + 16 * sizeof(int) + 8 * BAYSAR_MAX_FUSED_LINES * sizeof(double);
+            192 * sizeof(double) + 16 * sizeof(int) + 8 * BAYSAR_MAX_FUSED_LINES * sizeof(double) +
+            4 * BAYSAR_MAX_FUSED_LINES * sizeof(float);
   s.total = (s.total + 15) / 16 * 16;
   return s;
 }
@@ -260,12 +261,51 @@ BAYSAR_DEV void pixel_likelihood(const ModelDev& m, const int* ch, const double*
   if (tid == 0) components[n * (int64_t)ncomp_cols + c] = -red4[0];
 }
 
+// Sweep 2 of the fused narrow-Doppler passes for two fine-grid points (packed): v2 += wt * (s_r / (a + g_r) + s_e / (a + g_e)),
+// a = |d|^2.5 at the grid offsets kf2 from the line centre; far field as a three-term series through the packed FP32
+// pipe, the exact form next to the centre.  WEIGHTED = false: wt2 == (1, 1) (single-tap lines).
+template <bool WEIGHTED>
+BAYSAR_DEV void fused_pair_eval(f32x2 kf2, f32x2& v2, const float4& cst, const float4& ser, const float2& far, f32x2 c0p,
+                                f32x2 mc1p, f32x2 c2p, f32x2 dhi2, f32x2 dlo2, f32x2 r2, f32x2 wt2) {
+  const f32x2 d2 = fma2(kf2, dhi2, fma2(kf2, dlo2, r2));
+  float dx, dy;
+  unpack2(d2, dx, dy);
+  dx = fabsf(dx); dy = fabsf(dy);
+  if (dx >= far.y && dy >= far.y) {
+    const f32x2 rs = pack2(rsqrt_approx(dx), rsqrt_approx(dy));
+    const f32x2 rs2 = mul2(rs, rs);
+    f32x2 ia = mul2(mul2(rs2, rs2), rs);
+    const f32x2 poly = fma2(ia, fma2(ia, c2p, mc1p), c0p);
+    if (WEIGHTED) ia = mul2(ia, wt2);
+    v2 = fma2(ia, poly, v2);   // ia (c0 - ia (c1 - ia c2))
+  } else {
+    float vx, vy, wx = 1.f, wy = 1.f;
+    unpack2(v2, vx, vy);
+    if (WEIGHTED) unpack2(wt2, wx, wy);
+    {
+      const float a25 = dx * dx * sqrt_approx(dx);
+      const float dr = a25 + cst.z, de = a25 + cst.w;
+      const float num = fmaf(ser.x, de, ser.y * dr);
+      vx = fmaf(WEIGHTED ? num * wx : num, rcp_approx(dr * de), vx);
+    }
+    {
+      const float a25 = dy * dy * sqrt_approx(dy);
+      const float dr = a25 + cst.z, de = a25 + cst.w;
+      const float num = fmaf(ser.x, de, ser.y * dr);
+      vy = fmaf(WEIGHTED ? num * wy : num, rcp_approx(dr * de), vy);
+    }
+    v2 = pack2(vx, vy);
+  }
+}
+
 // MINB = resident CTAs per SM the register allocation aims at: 3 (80 registers) when the shared-memory footprint allows
 // no more (long fine grids), 4 (64 registers, no spills) or 5 (48 registers, 16 bytes of spills) for short grids.
 // MODE 0: fused (spectrum -> instrument convolution on the FP32 pipe -> likelihood, everything in shared memory).
 // MODE 1: spectral stage only: writes the pre-convolution spectrum and the per-theta scalars for the tensor-core
 //         contraction (if_contract.cuh) and the pixel stage (pixel_stage_kernel below).
-template <int NT, int MODE, int MINB = 3>
+// FUSED3 = false compiles the three-tap variant of the fused Balmer passes out (chords whose Balmer lines are all
+// guaranteed single taps, CH_B_OPTIONAL: the extra code costs the 48-register MINB = 5 build spills).
+template <int NT, int MODE, int MINB = 3, bool FUSED3 = true>
 __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, ChordArgs a) {
 #ifdef BAYSAR_CPU_EMU
   unsigned char* chord_smem_raw = emu_dynamic_smem();
@@ -304,6 +344,9 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
   int* iscr = reinterpret_cast<int*>(scratch + 192);  // 16 ints
   // constants of the Balmer lines handled by the fused narrow-Doppler passes (BAYSAR_MAX_FUSED_LINES x 64 bytes)
   FusedLine* fl = reinterpret_cast<FusedLine*>(iscr + 16);
+  // Doppler taps of the fused lines, normalised to sum 1: weights of stark[j - 1], stark[j], stark[j + 1]; [3] != 0 marks
+  // a three-tap line (the Doppler kernel of a cold neutral on a fine grid: central tap + two ~1e-7 neighbours)
+  float* fw = reinterpret_cast<float*>(fl + BAYSAR_MAX_FUSED_LINES);
   double* edge64 = scratch + 128;
 #define A_AT(j) bufA[pad_index(HALO + (j))]
 #define B_AT(j) bufB[pad_index(HALO + (j))]
@@ -430,33 +473,21 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
         const float2 far = *reinterpret_cast<const float2*>(&fl[b].c2);    // c2, d_far
         const f32x2 mjc2 = pack2(-cst.x, -cst.x), r2 = pack2(cst.y, cst.y);
         const f32x2 c0p = pack2(ser.z, ser.z), mc1p = pack2(-ser.w, -ser.w), c2p = pack2(far.x, far.x);
+        const float4 w4 = *reinterpret_cast<const float4*>(fw + 4 * b);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           f32x2& v2 = h == 0 ? v01 : v23;
           const f32x2 kf2 = add2(h == 0 ? jf01 : jf23, mjc2);
-          const f32x2 d2 = fma2(kf2, dhi2, fma2(kf2, dlo2, r2));
-          float dx, dy;
-          unpack2(d2, dx, dy);
-          dx = fabsf(dx); dy = fabsf(dy);
-          if (dx >= far.y && dy >= far.y) {
-            const f32x2 rs = pack2(rsqrt_approx(dx), rsqrt_approx(dy));
-            const f32x2 rs2 = mul2(rs, rs);
-            const f32x2 ia = mul2(mul2(rs2, rs2), rs);
-            v2 = fma2(ia, fma2(ia, fma2(ia, c2p, mc1p), c0p), v2);   // ia (c0 - ia (c1 - ia c2))
-          } else {
-            float vx, vy;
-            unpack2(v2, vx, vy);
-            {
-              const float a25 = dx * dx * sqrt_approx(dx);
-              const float dr = a25 + cst.z, de = a25 + cst.w;
-              vx = fmaf(fmaf(ser.x, de, ser.y * dr), rcp_approx(dr * de), vx);
-            }
-            {
-              const float a25 = dy * dy * sqrt_approx(dy);
-              const float dr = a25 + cst.z, de = a25 + cst.w;
-              vy = fmaf(fmaf(ser.x, de, ser.y * dr), rcp_approx(dr * de), vy);
-            }
-            v2 = pack2(vx, vy);
+          if (!FUSED3 || w4.w == 0.f) {
+            fused_pair_eval<false>(kf2, v2, cst, ser, far, c0p, mc1p, c2p, dhi2, dlo2, r2, pack2(1.f, 1.f));
+          } else {  // three Doppler taps: Stark profile at j - 1, j, j + 1; the taps past the two grid ends are zero
+                    // padding ("same" convolution), which matters when a line sits at the end of the chord
+            const int jx = jb + 2 * h * NT, jy = jx + NT;
+            fused_pair_eval<true>(add2(kf2, pack2(-1.f, -1.f)), v2, cst, ser, far, c0p, mc1p, c2p, dhi2, dlo2, r2,
+                                  pack2(jx > 0 ? w4.x : 0.f, jy > 0 ? w4.x : 0.f));
+            fused_pair_eval<true>(kf2, v2, cst, ser, far, c0p, mc1p, c2p, dhi2, dlo2, r2, pack2(w4.y, w4.y));
+            fused_pair_eval<true>(add2(kf2, pack2(1.f, 1.f)), v2, cst, ser, far, c0p, mc1p, c2p, dhi2, dlo2, r2,
+                                  pack2(jx < F - 1 ? w4.z : 0.f, jy < F - 1 ? w4.z : 0.f));
           }
         }
       }
@@ -562,15 +593,18 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
       const int KD = cl[CL_KD], o = (KD - 1) / 2;
       const double dshift = cwl - cwl0;
       {
-        // single-tap test (block-uniform): the tap at the "same"-alignment centre is inside the cut, its neighbours not
-        double zc[3];
+        // single- / three-tap test (block-uniform): the tap at the "same"-alignment centre is inside the cut and either
+        // its neighbours are not, or they are and the next ones are not
+        double zc[5];
         const double zlim = BAYSAR_Z_CUT_DOPPLER * sigma;
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
-          double xk = __dadd_rn(cld[CL_DOP_START], __dmul_rn((double)(o - 1 + t), cld[CL_DOP_DELTA]));
+        for (int t = 0; t < 5; ++t) {
+          double xk = __dadd_rn(cld[CL_DOP_START], __dmul_rn((double)(o - 2 + t), cld[CL_DOP_DELTA]));
           zc[t] = fabs((xk + dshift) - cwl);
         }
-        if (KD >= 3 && zc[1] <= zlim && zc[0] > zlim && zc[2] > zlim) {
+        const bool one_tap = KD >= 3 && zc[2] <= zlim && zc[1] > zlim && zc[3] > zlim;
+        const bool three_taps = FUSED3 && KD >= 5 && zc[2] <= zlim && zc[1] <= zlim && zc[3] <= zlim && zc[0] > zlim && zc[4] > zlim;
+        if (one_tap || three_taps) {
           if (tid == 0) {
             const double c0 = x0 - cwl;
             const int jc = (int)rint(-c0 / delta);
@@ -583,6 +617,18 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
             if (jL > 0) jL -= jL % BAYSAR_EM_STRIDE;                    // both tails: a whole number of strides
             if (jR < F - 1) jR += (F - 1 - jR) % BAYSAR_EM_STRIDE;
             L.jL = jL; L.jR = jR;
+            float* w = fw + 4 * nf;
+            if (three_taps) {
+              // out[j] = g[o - 1] stark[j + 1] + g[o] stark[j] + g[o + 1] stark[j - 1], normalised by the tap sum (the
+              // trapz of the convolved profile is the tap sum times the trapz of the Stark profile up to ~1e-12: the
+              // end-point terms are g[o +- 1] / g[o] ~ 1e-7 times the far wing)
+              const double gm = exp(-0.5 * (zc[1] / sigma) * (zc[1] / sigma)), g0 = exp(-0.5 * (zc[2] / sigma) * (zc[2] / sigma)),
+                           gp = exp(-0.5 * (zc[3] / sigma) * (zc[3] / sigma));
+              const double gs = gm + g0 + gp;
+              w[0] = (float)(gp / gs); w[1] = (float)(g0 / gs); w[2] = (float)(gm / gs); w[3] = 1.f;
+            } else {
+              w[0] = 0.f; w[1] = 1.f; w[2] = 0.f; w[3] = 0.f;
+            }
           }
           if (++nf == BAYSAR_MAX_FUSED_LINES) flush_fused(false);
           continue;
