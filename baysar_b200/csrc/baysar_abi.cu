@@ -501,11 +501,26 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
   const int L = (int)m->I[I_L];
   const size_t per_warp = los_smem_per_warp(L, (int)m->I[I_N_PARAMS]);
   if (per_warp > 200 * 1024) return fail("line-of-sight grid too long for the shared-memory LOS stage");
-  static const int minb = getenv("BAYSAR_LOS_MINB") ? atoi(getenv("BAYSAR_LOS_MINB")) : 4;  // register cap experiment
+  // Register budget by batch size.  The kernel is latency-bound at 16 warps per SM (4 CTAs, 128 registers, no spills):
+  // the best choice for many waves.  A batch of a few thousand thetas, though, is one or two waves, and then fitting
+  // every CTA into ONE wave beats the spills of a tighter budget (4096 thetas: 1024 CTAs = 1.7 waves of 592 at 0.080 ms,
+  // one wave of 7 CTAs per SM at 72 registers at 0.068 ms).  BAYSAR_LOS_MINB overrides.
+  static const int minb_env = getenv("BAYSAR_LOS_MINB") ? atoi(getenv("BAYSAR_LOS_MINB")) : 0;
+  int minb = 4;
+  if (minb_env > 0) {
+    minb = minb_env;
+  } else {
+    const int64_t ctas = (n + 3) / 4;
+    if (ctas > (int64_t)4 * m->sm_count)
+      for (int b = 5; b <= 7; ++b)
+        if (ctas <= (int64_t)b * m->sm_count) { minb = b; break; }
+  }
   if (4 * per_warp <= 200 * 1024) {
     size_t smem = 4 * per_warp;
     static const int unr = getenv("BAYSAR_LOS_UNROLL") ? atoi(getenv("BAYSAR_LOS_UNROLL")) : 1;
     auto kern = minb >= 6 ? los_stage_kernel<4, 6> : (minb == 5 ? los_stage_kernel<4, 5> : los_stage_kernel<4, 4>);
+    if (minb == 7) kern = los_stage_kernel<4, 7>;
+    if (minb >= 8) kern = los_stage_kernel<4, 8>;
     if (unr == 2) kern = minb >= 5 ? los_stage_kernel<4, 5, 2> : (minb == 3 ? los_stage_kernel<4, 3, 2> : los_stage_kernel<4, 4, 2>);
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)((n + 3) / 4), 128, smem, stream>>>(m->dev, a);
