@@ -466,6 +466,9 @@ int launch_pxc(PxcPlan& pl, const float* spec, int n_rb, float* out, double* tsu
   // demo, but one build of it was seen to deliver stale A rows in cold first launches; not root-caused)
   static const int loader = getenv("BAYSAR_PXC_LOADER") ? atoi(getenv("BAYSAR_PXC_LOADER")) : 0;
   p.use_tma = loader;
+  static const int sleep_epi = getenv("BAYSAR_PXC_SLEEP_EPI") ? atoi(getenv("BAYSAR_PXC_SLEEP_EPI")) : 0;
+  static const int sleep_build = getenv("BAYSAR_PXC_SLEEP_BUILD") ? atoi(getenv("BAYSAR_PXC_SLEEP_BUILD")) : 0;
+  p.sleep_epi = (unsigned)sleep_epi; p.sleep_build = (unsigned)sleep_build;
   CUtensorMap tmap;
   if (make_spec_tmap(spec, pl.pitch, (int64_t)n_rb * ifc::TILE_M, &tmap)) return 1;
   if (pl.tn == 64) {
