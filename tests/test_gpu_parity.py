@@ -221,6 +221,34 @@ def test_tensor_core_path_agrees_with_fused_path():
             np.testing.assert_allclose(sa[i], ref["spectra"][0], rtol=SPECTRA_RTOL)
 
 
+def test_contraction_variants_agree():
+    """The folded pixel contraction (default, 128-column tiles), its 64-column variant and the every-column Toeplitz
+    contraction (the path a sampled wavelength map takes) evaluate the same chord: logP within the north-star
+    tolerance of each other and of the oracle, spectra within 1e-5 per pixel."""
+    from baysar_b200 import configs
+
+    wl = configs.balmer_series()
+    folded = _fresh_posterior(wl, {"BAYSAR_IFC": "1"})
+    folded64 = _fresh_posterior(wl, {"BAYSAR_IFC": "1", "BAYSAR_PXC": "64"})
+    toeplitz = _fresh_posterior(wl, {"BAYSAR_IFC": "1", "BAYSAR_PXC": "0"})
+    assert folded.model.folded_contraction[0][1] == 128 and folded64.model.folded_contraction[0][1] == 64
+    assert toeplitz.model.folded_contraction[0][0] == 0 and toeplitz.model.uses_tensor_cores
+    rng = np.random.default_rng(21)
+    lo, hi = folded.plasma.theta_bounds[:, 0], folded.plasma.theta_bounds[:, 1]
+    theta = lo + rng.random((512, folded.plasma.n_params)) * (hi - lo)
+    a, b, c = folded(theta), folded64(theta), toeplitz(theta)
+    ok = (folded.last_status == 0) & (folded64.last_status == 0) & (toeplitz.last_status == 0)
+    assert ok.mean() > 0.9
+    np.testing.assert_allclose(a[ok], c[ok], rtol=LOGP_RTOL)
+    np.testing.assert_allclose(b[ok], c[ok], rtol=LOGP_RTOL)
+    sa, _ = folded.spectra_batch(theta[:32], 0)
+    sc, _ = toeplitz.spectra_batch(theta[:32], 0)
+    np.testing.assert_allclose(sa, sc, rtol=SPECTRA_RTOL)
+    oracle = oracle_posterior("balmer_series")
+    for i in np.where(ok)[0][:8]:
+        np.testing.assert_allclose(b[i], oracle.evaluate(theta[i])["logp"], rtol=LOGP_RTOL)
+
+
 def test_tensor_core_path_multi_chord_and_row_chunks():
     """Two chords through the tensor path with a workspace budget that forces several row chunks per chord."""
     from baysar_b200 import configs
