@@ -518,7 +518,17 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
       for (int b = 5; b <= 7; ++b)
         if (ctas <= (int64_t)b * m->sm_count) { minb = b; break; }
   }
-  if (4 * per_warp <= 200 * 1024) {
+  // Long lines of sight: the per-point cache (128 B per point and theta) starves the warp-per-theta form of occupancy
+  // (L = 1000: one warp per SM).  From BAYSAR_LOS_TEAM_L points on (default: as soon as four thetas no longer fit one
+  // CTA's 200 KB) one CTA of four warps works on ONE theta, the points spread over its 128 threads.
+  static const int team_l = getenv("BAYSAR_LOS_TEAM_L") ? atoi(getenv("BAYSAR_LOS_TEAM_L")) : 0;
+  const bool team = (team_l > 0 && L >= team_l) || 4 * per_warp > 200 * 1024;
+  if (team && per_warp + 64 <= 200 * 1024) {
+    const size_t smem = per_warp + 64;
+    auto kern = los_stage_kernel<4, 1, 1, 4>;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)n, 128, smem, stream>>>(m->dev, a);
+  } else if (4 * per_warp <= 200 * 1024) {
     size_t smem = 4 * per_warp;
     static const int unr = getenv("BAYSAR_LOS_UNROLL") ? atoi(getenv("BAYSAR_LOS_UNROLL")) : 1;
     auto kern = minb >= 6 ? los_stage_kernel<4, 6> : (minb == 5 ? los_stage_kernel<4, 5> : los_stage_kernel<4, 4>);

@@ -27,18 +27,74 @@ __host__ __device__ static inline size_t los_smem_per_warp(int L, int n_params) 
   return (size_t)L * (14 * sizeof(double) + 4 * sizeof(int)) + (size_t)(2 * n_params + (L & 1)) * sizeof(double);
 }
 
+// TW warps cooperate on one theta.  TW = 1 is the warp-per-theta form (reductions are warp shuffles); TW = 4 runs one CTA
+// per theta with the line-of-sight points spread over 128 threads, for long lines of sight whose per-point cache
+// (128 bytes per point) would otherwise leave a single warp per SM (L = 1000: 128 KB per theta).
+template <int TW>
+struct LosTeam {
+  double* xch;  // [TW] exchange slots in shared memory (TW > 1)
+  BAYSAR_DEV void sync() const {
+    if (TW == 1) __syncwarp();
+    else __syncthreads();
+  }
+  template <class Combine>
+  BAYSAR_DEV double reduce(double v, Combine comb) const {  // v: already reduced over the warp
+    if (TW == 1) return v;
+    __syncthreads();  // the slots' previous use
+    if ((threadIdx.x & 31) == 0) xch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = xch[0];
+#pragma unroll
+    for (int i = 1; i < TW; ++i) r = comb(r, xch[i]);
+    return r;
+  }
+  BAYSAR_DEV double sum(double v) const { return reduce(warp_sum(v), [](double a, double b) { return a + b; }); }
+  BAYSAR_DEV double max(double v) const { return reduce(warp_max(v), [](double a, double b) { return a > b ? a : b; }); }
+  BAYSAR_DEV uint32_t or_bits(uint32_t v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+    if (TW == 1) return v;
+    // exact in a double: 32 bits
+    return (uint32_t)reduce((double)v, [](double a, double b) { return (double)((uint32_t)a | (uint32_t)b); });
+  }
+  BAYSAR_DEV int any(int pred) const { return or_bits(pred ? 1u : 0u) != 0u; }
+  // largest value, lowest index among equals (numpy.argmax)
+  BAYSAR_DEV void argmax(double& best, int& bi) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (TW == 1) return;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { xch[threadIdx.x >> 5] = best; xch[TW + (threadIdx.x >> 5)] = (double)bi; }
+    __syncthreads();
+    best = xch[0]; bi = (int)xch[TW];
+#pragma unroll
+    for (int i = 1; i < TW; ++i) {
+      const double ob = xch[i];
+      const int oi = (int)xch[TW + i];
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+  }
+};
+
 // UNR: unroll factor of the per-line loops over line-of-sight points (two points of a lane in flight give the FP64
 // dependency chains some instruction-level parallelism; the kernel is latency-bound at 16 warps per SM)
-template <int WARPS, int MINB = 1, int UNR = 1>
+template <int WARPS, int MINB = 1, int UNR = 1, int TW = 1>
 __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m, LosArgs a) {
+  static_assert(TW == 1 || TW == WARPS, "team mode: the whole CTA works on one theta");
 #ifdef BAYSAR_CPU_EMU
   unsigned char* los_smem_raw = emu_dynamic_smem();
 #else
   extern __shared__ __align__(16) unsigned char los_smem_raw[];
 #endif
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t n = (int64_t)blockIdx.x * WARPS + warp;
-  if (n >= a.n) return;  // whole warp exits together; no block-level barrier is used in this kernel
+  // `lane`: index of this thread in its team (TW = 1: the warp lane), TS: threads per team
+  constexpr int TS = 32 * TW;
+  const int lane = TW == 1 ? (threadIdx.x & 31) : threadIdx.x, warp = TW == 1 ? (threadIdx.x >> 5) : 0;
+  const int64_t n = TW == 1 ? (int64_t)blockIdx.x * WARPS + warp : (int64_t)blockIdx.x;
+  if (n >= a.n) return;  // whole teams exit together (TW = 1: no block-level barrier is used in this kernel)
 
   const int64_t* I = m.I;
   const int L = (int)I[I_L], n_params = (int)I[I_N_PARAMS], n_elem = (int)I[I_N_ELEM];
@@ -61,9 +117,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
   int* __restrict__ hj_s = hi_s + L;
   int* __restrict__ lx_s = hj_s + L;
   int* __restrict__ ly_s = lx_s + L;
+  LosTeam<TW> team{reinterpret_cast<double*>(los_smem_raw + (size_t)(TW == 1 ? WARPS : 1) * los_smem_per_warp(L, n_params))};
 
   uint32_t st = 0;
-  for (int k = lane; k < n_params; k += 32) {
+  for (int k = lane; k < n_params; k += TS) {
     double v = th[k];
     if (v != v) st |= 1u << 0;
     if (v - v != 0.0 && v == v) st |= 1u << 1;  // +-inf
@@ -71,7 +128,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     p10[k] = p;
     l10[k] = log10(p);
   }
-  __syncwarp();
+  team.sync();
 
   // ---- electron density / temperature profiles
   const int ne_idx = (int)I[I_NE_IDX], te_idx = (int)I[I_TE_IDX];
@@ -88,7 +145,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     (void)ne_A;
     const double te_f = th[te_idx + 1], te_floor = th[te_idx + 2], te_c = m.prof_d[PROF_TE_CENTRE];
     const double ne_pk = p10[ne_idx], te_pk = p10[te_idx];
-    for (int l = lane; l < L; l += 32) {
+    for (int l = lane; l < L; l += TS) {
       double x = m.los_x[l];
       double dx = x - ne_c;
       double sg = 0.2 * ne_f + ne_f / (1.0 + exp(-dx));
@@ -109,7 +166,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
                  nk = th[ne_idx + 5], nf = th[ne_idx + 6], nb = bgf ? p10[ne_idx + 7] : 0.0;
     const double tA = p10[te_idx], ts0 = th[te_idx + 1], tq = th[te_idx + 2], tnu = th[te_idx + 3], tk = th[te_idx + 4],
                  tf = th[te_idx + 5], tb = bgf ? p10[te_idx + 6] : 0.0;
-    for (int l = lane; l < L; l += 32) {
+    for (int l = lane; l < L; l += TS) {
       const double x = m.los_x[l];
       double sg = ns0 * exp(nf * tanh(nk * (x - nx0)));
       double z = pow(fabs((x - nx0) / sg), nq);
@@ -127,7 +184,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     const int ne_log = m.prof_d[PROF_MESH_NE_LOG] != 0.0, te_log = m.prof_d[PROF_MESH_TE_LOG] != 0.0;
     const double* xk_ne = m.mesh_x;
     const double* xk_te = m.mesh_x + n_ne;
-    for (int l = lane; l < L; l += 32) {
+    for (int l = lane; l < L; l += TS) {
       const double x = m.los_x[l];
       int lo = m.mesh_lo[l];
       double y0 = ne_log ? p10[ne_idx + lo] : th[ne_idx + lo], y1 = ne_log ? p10[ne_idx + lo + 1] : th[ne_idx + lo + 1];
@@ -141,10 +198,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       te_s[l] = __dadd_rn(__dmul_rn(slope, x - xk_te[lo]), y0);
     }
   }
-  nemax = warp_max(nemax);
+  nemax = team.max(nemax);
 
   // ---- impurity electrons, main ion density (plasmas.py:876-889, :673)
-  for (int l = lane; l < L; l += 32) {
+  for (int l = lane; l < L; l += TS) {
     double ne = ne_s[l], tot = 0.0;
     for (int e = 0; e < n_elem; ++e) {
       double dens = p10[m.elem_dens_idx[e]];
@@ -156,7 +213,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
 
   // ---- impurity tau must index the ADAS tau grid (plasmas.py:1410-1429 raise; linemodels.py:454-467)
   const int n_tau = (int)I[I_N_TAU];
-  for (int s = lane; s < n_species; s += 32) {
+  for (int s = lane; s < n_species; s += TS) {
     const int* sp = m.sp_i + s * SP_I_COUNT;
     if (sp[SP_IS_IMPURITY]) {
       double lt = l10[sp[SP_TAU_IDX]];
@@ -172,7 +229,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     const double tau_h = p10[sp[SP_TAU_IDX]];
     const double n0_sampled = dens_idx >= 0 ? p10[dens_idx] : 0.0;
     const int nne = (int)I[I_A11_NNE], nte = (int)I[I_A11_NTE];
-    for (int l = lane; l < L; l += 32) {
+    for (int l = lane; l < L; l += TS) {
       double ne = ne_s[l], te = te_s[l];
       int ci, cj; double ca, cb;
       linear_cell(m.a11_ne, nne, ne, ci, ca);
@@ -186,21 +243,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     }
     // adf15 grid cells, shared by every Balmer line
     const int hne = (int)I[I_H_NNE], hte = (int)I[I_H_NTE];
-    for (int l = lane; l < L; l += 32) {
+    for (int l = lane; l < L; l += TS) {
       int ci, cj; double ca, cb;
       linear_cell(m.h_ne, hne, ne_s[l], ci, ca);
       linear_cell(m.h_te, hte, te_s[l], cj, cb);
       hi_s[l] = ci; hj_s[l] = cj; ha_s[l] = ca; hb_s[l] = cb;
     }
   } else {
-    for (int l = lane; l < L; l += 32) n0_s[l] = 0.0;
+    for (int l = lane; l < L; l += TS) n0_s[l] = 0.0;
   }
 
   // ---- bicubic B-spline basis per LOS point, shared by every impurity line and tau slice
   const int n_tec = (int)I[I_N_TEC];
   const int snx = (int)I[I_SPL_NX], sny = (int)I[I_SPL_NY];
   if (n_tec > 0) {
-    for (int l = lane; l < L; l += 32) {
+    for (int l = lane; l < L; l += TS) {
       int lx, ly; double hx[4], hy[4];
       bspline_basis3(m.spl_tx, snx, ne_s[l], lx, hx);
       bspline_basis3(m.spl_ty, sny, te_s[l], ly, hy);
@@ -209,11 +266,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       for (int q = 0; q < 4; ++q) { bx_s[q * L + l] = hx[q]; by_s[q * L + l] = hy[q]; }
     }
   }
-  __syncwarp();
+  team.sync();
 
   if (a.profiles) {
     double* p = a.profiles + n * 4 * (int64_t)L;
-    for (int l = lane; l < L; l += 32) {
+    for (int l = lane; l < L; l += TS) {
       p[l] = ne_s[l]; p[L + l] = te_s[l]; p[2 * L + l] = nm_s[l]; p[3 * L + l] = n0_s[l];
     }
   }
@@ -235,7 +292,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
 #pragma unroll
       for (int q = 0; q < 12; ++q) s[q] = 0.0;
 #pragma unroll UNR
-      for (int l = lane; l < L; l += 32) {
+      for (int l = lane; l < L; l += TS) {
         double ne = ne_s[l], te = te_s[l], w = m.los_w[l];
         double pe = exp(bilinear(texc, hte, hi_s[l], hj_s[l], ha_s[l], hb_s[l]));
         double pr = exp(bilinear(trec, hte, hi_s[l], hj_s[l], ha_s[l], hb_s[l]));
@@ -248,7 +305,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
         s[8] += tp; s[9] += w * tp; s[10] += tp * ne; s[11] += tp * te;
       }
 #pragma unroll
-      for (int q = 0; q < 12; ++q) s[q] = warp_sum(s[q]);
+      for (int q = 0; q < 12; ++q) s[q] = team.sum(s[q]);
       double rec_sum = s[2] / four_pi, exc_sum = s[3] / four_pi, ems = s[9] / four_pi;
       double rec_ne = s[4] / s[0], rec_te = s[5] / s[0], exc_ne = s[6] / s[1], exc_te = s[7] / s[1];
       double f_rec = rec_sum / ems;
@@ -286,7 +343,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       const double* cpair = m.spl_c + ((int64_t)ul[UL_TAB_A] * (n_tau - 1) + pair) * ncx * ncy * 2;
       double s[5] = {0, 0, 0, 0, 0};
 #pragma unroll UNR
-      for (int l = lane; l < L; l += 32) {
+      for (int l = lane; l < L; l += TS) {
         double ne = ne_s[l], te = te_s[l];
         double n0 = dens * (ne / nemax);
         double vi, vj;
@@ -296,7 +353,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
         s[0] += p; s[1] += m.los_w[l] * p; s[2] += p * ne; s[3] += p * (n0 / ne); s[4] += p * te;
       }
 #pragma unroll
-      for (int q = 0; q < 5; ++q) s[q] = warp_sum(s[q]);
+      for (int q = 0; q < 5; ++q) s[q] = team.sum(s[q]);
       double ems_te = s[4] / s[0];
       double ti;
       if (cold_ions) ti = 0.01;
@@ -313,10 +370,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       }
     }
   }
-  __syncwarp();
+  team.sync();
   // Stark half-widths gamma^2.5 of every Balmer line (stehle_param, linemodels.py:554-566): lane 2q / 2q+1 take the
   // recombination / excitation width of the q-th Balmer line, so that all the pow() calls run side by side
-  for (int idx = lane; idx < 2 * n_ul; idx += 32) {
+  for (int idx = lane; idx < 2 * n_ul; idx += TS) {
     const int u = idx >> 1, which = idx & 1;
     if (m.ul_i[u * UL_I_COUNT + UL_KIND] != 0) continue;
     const double* ud = m.ul_d + u * UL_D_COUNT;
@@ -326,7 +383,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     const double g = (10.0 * lc * (pow(1e6 * wne, la) / pow(wte, lb))) / 2.0;
     rec[11 + which] = pow(g, 2.5);
   }
-  __syncwarp();
+  team.sync();
 
   // ---- priors, in posterior_components order (posterior.py:108-161)
   double* comp = a.components + n * (int64_t)(n_chords + n_pr) + n_chords;
@@ -341,15 +398,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       double* g1 = bx_s;  // scratch (the spline bases are dead by now)
       double vmax = -1.7976931348623157e308;
       for (int q = 0; q < nk; ++q) vmax = th[ne_idx + q] > vmax ? th[ne_idx + q] : vmax;
-      __syncwarp();
-      for (int q = lane; q < nk; q += 32) {
+      team.sync();
+      for (int q = lane; q < nk; q += TS) {
         const double c = th[ne_idx + q] / vmax;
         if (nk == 1) g1[q] = 0.0;
         else if (q == 0) g1[q] = th[ne_idx + 1] / vmax - c;
         else if (q == nk - 1) g1[q] = c - th[ne_idx + nk - 2] / vmax;
         else g1[q] = (th[ne_idx + q + 1] / vmax - th[ne_idx + q - 1] / vmax) / 2.0;
       }
-      __syncwarp();
+      team.sync();
       double cv = 0.0;
       for (int q = 0; q < nk; ++q) {  // sequential sum like Python's sum()
         double g2;
@@ -361,21 +418,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
         cv += (g2 * g2) / (den * den * den);
       }
       val = -cv * pd[PR_D0];
-      __syncwarp();
+      team.sync();
     } else if (kind == PRIOR_STATIC_PRESSURE) {  // priors.py:51-64
       double s = 0.0;
-      for (int l = lane; l < L; l += 32) {
+      for (int l = lane; l < L; l += TS) {
         double pe = clip_lo(te_s[l], 0.01) * clip_lo(ne_s[l], 1.0);
         s += low_pass(pe / 5e15, 1.0, 0.1);
       }
-      val = warp_sum(s);
+      val = team.sum(s);
     } else if (kind == PRIOR_NEUTRAL_FRACTION) {  // priors.py:83-101
       double s = 0.0;
-      for (int l = lane; l < L; l += 32) {
+      for (int l = lane; l < L; l += TS) {
         double f0 = clip_lo(n0_s[l], 1.0) / ne_s[l];
         s += high_pass(f0 / 5e-3, 1.0, 0.1);
       }
-      val = warp_sum(s);
+      val = team.sum(s);
     } else if (kind == PRIOR_STARK_TO_PEAK) {  // priors.py:646-667
       const double* r = lines_n + pi[PR_I0] * BAYSAR_LINE_STRIDE;
       double exc = high_pass(r[4] / nemax, 0.65, 0.075) * (1 - r[7]);
@@ -383,34 +440,29 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       val = exc + rc;
     } else if (kind == PRIOR_ANTIPROTON) {  // priors.py:14-24
       double s = 0.0; int any_neg = 0;
-      for (int l = lane; l < L; l += 32) {
+      for (int l = lane; l < L; l += TS) {
         double ni = nm_s[l];
         if (ni < 0) { any_neg = 1; double t = ni / 1e11; s += t * t; }
       }
-      s = warp_sum(s);
-      any_neg = __any_sync(0xffffffffu, any_neg);
+      s = team.sum(s);
+      any_neg = team.any(any_neg);
       val = any_neg ? -0.5 * s : 0.0;
     } else if (kind == PRIOR_MAIN_ION_FRACTION) {  // priors.py:27-48
       double best = -1.7976931348623157e308; int bi = 0x7fffffff;
-      for (int l = lane; l < L; l += 32) {
+      for (int l = lane; l < L; l += TS) {
         double v = nm_s[l];
         if (v > best) { best = v; bi = l; }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
+      team.argmax(best, bi);
       if (bi >= L) bi = 0;
       const double ref = clip_lo(ne_s[bi], 1.0);
       double s = 0.0;
-      for (int l = lane; l < L; l += 32) {
+      for (int l = lane; l < L; l += TS) {
         double nec = clip_lo(ne_s[l], 1.0);
         double factor = clip_lo(nec / ref, 0.3);
         s += high_pass(nm_s[l] / nec, factor * 0.8, 0.1);
       }
-      val = warp_sum(s);
+      val = team.sum(s);
     } else if (kind == PRIOR_CHARGE_STATE_ORDER) {  // priors.py:509-556
       double cost = 0.0;
       for (int e = 0; e < n_elem; ++e) {
@@ -433,19 +485,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       val = -0.5 * (t0 * t0);
     } else if (kind == PRIOR_TDV) {  // ElectronDensityTDVCost, priors.py:67-80: d0 threshold, d1 sigma
       double s = 0.0;
-      for (int l = lane; l + 1 < L; l += 32) {
+      for (int l = lane; l + 1 < L; l += TS) {
         const double ne_tdv = fabs(ne_s[l + 1] - ne_s[l]), ni_tdv = fabs(nm_s[l + 1] - nm_s[l]);
         s += (ne_tdv - ni_tdv) / ni_tdv;
       }
-      val = low_pass(warp_sum(s) / pd[PR_D0], 1.0, pd[PR_D1]);
+      val = low_pass(team.sum(s) / pd[PR_D0], 1.0, pd[PR_D1]);
     } else if (kind == PRIOR_PEAK_TE || kind == PRIOR_TE_MIN || kind == PRIOR_TE_TAU) {
       double tmax = -1.7976931348623157e308, tmin = 1.7976931348623157e308;
-      for (int l = lane; l < L; l += 32) {
+      for (int l = lane; l < L; l += TS) {
         tmax = te_s[l] > tmax ? te_s[l] : tmax;
         tmin = te_s[l] < tmin ? te_s[l] : tmin;
       }
-      tmax = warp_max(tmax);
-      tmin = -warp_max(-tmin);
+      tmax = team.max(tmax);
+      tmin = -team.max(-tmin);
       if (kind == PRIOR_PEAK_TE) {  // priors.py:241-251: d0 te_min, d1 te_err
         val = low_pass(tmax, pd[PR_D0], pd[PR_D1]);
       } else if (kind == PRIOR_TE_MIN) {  // priors.py:670-680: d0 ratio, d1 sigma
@@ -497,8 +549,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     if (lane == 0) comp[k] = val;
   }
 
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) st |= __shfl_xor_sync(0xffffffffu, st, o);
+  st = team.or_bits(st);
   if (lane == 0) {
     a.status[n] = st;
     double* h = a.hdr + n * BAYSAR_HDR_STRIDE;

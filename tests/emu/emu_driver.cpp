@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE ONLY — runs the product's kernel sources on CPU threads (see cpu_emu.h) for one model blob.
 #define BAYSAR_CPU_EMU 1
+#include <cstdlib>
 #include "../../baysar_b200/csrc/chord_stage.cuh"
 #include "../../baysar_b200/csrc/finalize.cuh"
 #include "../../baysar_b200/csrc/los_stage.cuh"
@@ -98,8 +99,13 @@ extern "C" int emu_eval(const unsigned char* blob, const double* theta, long n, 
   std::vector<double> hdr(n * BAYSAR_HDR_STRIDE);
   LosArgs la{theta, n, lines, comps, hdr.data(), profiles, status};
   EmuDim3 g;
-  g.x = (unsigned)((n + 3) / 4);
-  emu_launch(los_stage_kernel<4>, g, 128u, 4 * los_smem_per_warp(L, (int)I[I_N_PARAMS]), m, la);
+  if (getenv("BAYSAR_EMU_LOS_TEAM")) {  // the one-CTA-per-theta form the product uses for long lines of sight
+    g.x = (unsigned)n;
+    emu_launch(los_stage_kernel<4, 1, 1, 4>, g, 128u, los_smem_per_warp(L, (int)I[I_N_PARAMS]) + 64, m, la);
+  } else {
+    g.x = (unsigned)((n + 3) / 4);
+    emu_launch(los_stage_kernel<4>, g, 128u, 4 * los_smem_per_warp(L, (int)I[I_N_PARAMS]), m, la);
+  }
   for (int c = 0; c < n_chords; ++c) {
     const int* ch = m.ch_i + c * CH_I_COUNT;
     int kd_max = 0;

@@ -87,3 +87,24 @@ def test_split_path_stages_in_emulation(name):
     assert (o["status"] == 0).all()
     np.testing.assert_allclose(o["logp"], z["logp"][:2], rtol=1e-6)
     np.testing.assert_allclose(o["spectra"], z["c0_spectra"][:2], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["multi_species", "multi_bowman", "multi_mesh_curv", "multi_priors", "balmer_series"])
+def test_emulated_los_team_mode(name, monkeypatch):
+    """K1 with one CTA (four warps) per theta — the form the product launches for long lines of sight, forced here
+    for the fixtures' shorter ones: log-posterior, prior components and line scalars as in the warp-per-theta form."""
+    monkeypatch.setenv("BAYSAR_EMU_LOS_TEAM", "1")
+    z = np.load(GOLDEN / f"{name}.npz")
+    plasma, chords, priors, blob, info = host_model(WORKLOADS[name]())
+    th = z["theta"][:4]
+    o = emu_eval(blob, th, chord=0, n_chords=len(chords), n_priors=len(priors), n_ul=info["n_ulines"],
+                 L=len(plasma.los), P=len(chords[0].x_data), F=len(chords[0].x_data_fm))
+    assert (o["status"] == 0).all()
+    np.testing.assert_allclose(o["logp"], z["logp"][:4], rtol=1e-6)
+    np.testing.assert_allclose(o["comps"], z["components"][:4], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(o["profiles"][:, 0], z["ne"][:4], rtol=1e-12)
+    ref = z["c0_line_scalars"][:4]
+    for k, u in enumerate(info["chord_line_uline"][0]):
+        kind = str(z["setup_c0_line_types"][k])
+        if kind == "ADAS406Lines":
+            np.testing.assert_allclose(o["lines"][:, u][:, :5], ref[:, k, :5], rtol=1e-11)
