@@ -523,11 +523,17 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
   // CTA's 200 KB) one CTA of four warps works on ONE theta, the points spread over its 128 threads.
   static const int team_l = getenv("BAYSAR_LOS_TEAM_L") ? atoi(getenv("BAYSAR_LOS_TEAM_L")) : 0;
   const bool team = (team_l > 0 && L >= team_l) || 4 * per_warp > 200 * 1024;
-  if (team && per_warp + 64 <= 200 * 1024) {
-    const size_t smem = per_warp + 64;
-    auto kern = los_stage_kernel<4, 1, 1, 4>;
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)n, 128, smem, stream>>>(m->dev, a);
+  if (team && per_warp + 128 <= 200 * 1024) {
+    const size_t smem = per_warp + 128;
+    if (2 * smem > 200 * 1024) {  // one CTA per SM anyway: eight warps per theta
+      auto kern = los_stage_kernel<8, 1, 1, 8>;
+      CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<(unsigned)n, 256, smem, stream>>>(m->dev, a);
+    } else {
+      auto kern = los_stage_kernel<4, 1, 1, 4>;
+      CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<(unsigned)n, 128, smem, stream>>>(m->dev, a);
+    }
   } else if (4 * per_warp <= 200 * 1024) {
     size_t smem = 4 * per_warp;
     static const int unr = getenv("BAYSAR_LOS_UNROLL") ? atoi(getenv("BAYSAR_LOS_UNROLL")) : 1;

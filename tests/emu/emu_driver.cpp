@@ -101,7 +101,7 @@ extern "C" int emu_eval(const unsigned char* blob, const double* theta, long n, 
   EmuDim3 g;
   if (getenv("BAYSAR_EMU_LOS_TEAM")) {  // the one-CTA-per-theta form the product uses for long lines of sight
     g.x = (unsigned)n;
-    emu_launch(los_stage_kernel<4, 1, 1, 4>, g, 128u, los_smem_per_warp(L, (int)I[I_N_PARAMS]) + 64, m, la);
+    emu_launch(los_stage_kernel<4, 1, 1, 4>, g, 128u, los_smem_per_warp(L, (int)I[I_N_PARAMS]) + 128, m, la);
   } else {
     g.x = (unsigned)((n + 3) / 4);
     emu_launch(los_stage_kernel<4>, g, 128u, 4 * los_smem_per_warp(L, (int)I[I_N_PARAMS]), m, la);

@@ -249,6 +249,42 @@ def test_contraction_variants_agree():
         np.testing.assert_allclose(b[i], oracle.evaluate(theta[i])["logp"], rtol=LOGP_RTOL)
 
 
+@pytest.mark.parametrize("n_los", [500, 1000])
+def test_long_line_of_sight_team_kernels(n_los):
+    """Long lines of sight run K1 with one CTA per theta (four warps at L = 500, eight at L = 1000): log-posterior and
+    spectra against the oracle on a shape-sweep chord (BASELINE configs[4])."""
+    import baysar_b200.lineshapes as host_ns
+    import oracle.numpy_port as oracle_ns
+    from baysar_b200 import configs
+    from baysar_b200.atomic_data import SyntheticADAS
+    from baysar_b200.input_functions import make_input_dict
+    from baysar_b200.posterior import BaysarPosterior
+    from oracle.numpy_port import OracleError, OraclePosterior
+
+    wl = configs.synthetic_sweep(n_los, 10, 512, balmer=True)
+    np.random.seed(0)
+    post = BaysarPosterior(make_input_dict(**wl.input_kwargs), profile_function=wl.make_profile(host_ns),
+                           atomic_data=SyntheticADAS(), skip_test=True)
+    oracle = OraclePosterior(make_input_dict(**wl.input_kwargs), SyntheticADAS(), wl.make_profile(oracle_ns))
+    rng = np.random.default_rng(31)
+    lo, hi = post.plasma.theta_bounds[:, 0], post.plasma.theta_bounds[:, 1]
+    theta = lo + rng.random((6, post.plasma.n_params)) * (hi - lo)
+    logp = post(theta)
+    spectra, _ = post.spectra_batch(theta, chord=0)
+    checked = 0
+    for i, th in enumerate(theta):
+        try:
+            ref = oracle.evaluate(th)
+        except OracleError:
+            assert post.last_status[i] != 0
+            continue
+        assert post.last_status[i] == 0
+        np.testing.assert_allclose(logp[i], ref["logp"], rtol=LOGP_RTOL)
+        np.testing.assert_allclose(spectra[i], ref["spectra"][0], rtol=SPECTRA_RTOL)
+        checked += 1
+    assert checked >= 3
+
+
 def test_tensor_core_path_multi_chord_and_row_chunks():
     """Two chords through the tensor path with a workspace budget that forces several row chunks per chord."""
     from baysar_b200 import configs
