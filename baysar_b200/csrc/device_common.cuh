@@ -162,7 +162,7 @@ BAYSAR_DEV void bspline_basis3(const double* t, int n, double x, int& l, double*
 // Two tau slices at once: c holds (slice i, slice i + 1) coefficient pairs.  sum_i hx[i] (sum_j c[i][j] hy[j]) per slice:
 // 2 x 20 fused multiply-adds from 16 sixteen-byte loads (FITPACK's fpbisp forms the same sums term by term).
 // hx / hy are strided (structure-of-arrays basis cache: element q of LOS point l at q * stride + l).
-struct Double2 { double x, y; };
+struct alignas(16) Double2 { double x, y; };  // 16-byte aligned: one LDG.128 per pair (unaligned it was two LDG.64)
 BAYSAR_DEV void bspline_eval_pair(const double* c, int ncy, int lx, int ly, const double* hx, const double* hy, int stride,
                                   double& vi, double& vj) {
   const Double2* base = reinterpret_cast<const Double2*>(c) + (int64_t)(lx - 3) * ncy + (ly - 3);
