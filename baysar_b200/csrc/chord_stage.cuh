@@ -57,7 +57,7 @@ struct FusedLine {
   double sum_r, sum_e;       // line-of-sight integrals (recombination, excitation)
 };
 // Parameters of one Gaussian component, computed once per (theta, chord) (32 bytes)
-struct GaussComp {
+struct alignas(16) GaussComp {
   double cw, inv_sigma;  // (Doppler-shifted) centre, 1 / sigma
   float amp;             // area-normalised amplitude over the intensity calibration
   int j_lo, j_hi, pad;   // fine-grid window |z| <= BAYSAR_Z_CUT
