@@ -199,14 +199,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     }
   }
   nemax = team.max(nemax);
+  const double inv_nemax = 1.0 / nemax;
 
   // ---- impurity electrons, main ion density (plasmas.py:876-889, :673)
   for (int l = lane; l < L; l += TS) {
     double ne = ne_s[l], tot = 0.0;
     for (int e = 0; e < n_elem; ++e) {
       double dens = p10[m.elem_dens_idx[e]];
-      double conc = (dens / nemax) * ne;
-      tot += (conc / nemax) * ne;
+      double conc = (dens * inv_nemax) * ne;
+      tot += (conc * inv_nemax) * ne;
     }
     nm_s[l] = ne - nan_to_num(tot);
   }
@@ -288,9 +289,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       const int hne = (int)I[I_H_NNE], hte = (int)I[I_H_NTE];
       const double* texc = m.h_tab + (int64_t)ul[UL_TAB_A] * hne * hte;
       const double* trec = m.h_tab + (int64_t)ul[UL_TAB_B] * hne * hte;
+      // s[8..11] (the sums over recombination + excitation) are formed from the partial sums after the reduction
       double s[12];
 #pragma unroll
-      for (int q = 0; q < 12; ++q) s[q] = 0.0;
+      for (int q = 0; q < 8; ++q) s[q] = 0.0;
 #pragma unroll UNR
       for (int l = lane; l < L; l += TS) {
         double ne = ne_s[l], te = te_s[l], w = m.los_w[l];
@@ -299,13 +301,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
         if (pe != pe || pr != pr) st |= 1u << 4;
         double rp = clip_lo(nm_s[l], 1.0) * ne * pr;
         double ep = n0_s[l] * ne * pe;
-        double tp = rp + ep;
         s[0] += rp; s[1] += ep; s[2] += w * rp; s[3] += w * ep;
         s[4] += rp * ne; s[5] += rp * te; s[6] += ep * ne; s[7] += ep * te;
-        s[8] += tp; s[9] += w * tp; s[10] += tp * ne; s[11] += tp * te;
       }
 #pragma unroll
-      for (int q = 0; q < 12; ++q) s[q] = team.sum(s[q]);
+      for (int q = 0; q < 8; ++q) s[q] = team.sum(s[q]);
+      s[8] = s[0] + s[1]; s[9] = s[2] + s[3]; s[10] = s[4] + s[6]; s[11] = s[5] + s[7];
       double rec_sum = s[2] / four_pi, exc_sum = s[3] / four_pi, ems = s[9] / four_pi;
       double rec_ne = s[4] / s[0], rec_te = s[5] / s[0], exc_ne = s[6] / s[1], exc_te = s[7] / s[1];
       double f_rec = rec_sum / ems;
@@ -342,15 +343,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       const int pair = j > 0 ? j - 1 : 0;
       const double* cpair = m.spl_c + ((int64_t)ul[UL_TAB_A] * (n_tau - 1) + pair) * ncx * ncy * 2;
       double s[5] = {0, 0, 0, 0, 0};
+      // n0 = dens * (ne / ne_max) and the concentration weight n0 / ne = dens / ne_max (linemodels.py:392-394, :411):
+      // the two float64 divisions per point and line become one reciprocal per theta (relative difference ~1e-16)
+      const double dens_over_max = dens * inv_nemax;
 #pragma unroll UNR
       for (int l = lane; l < L; l += TS) {
         double ne = ne_s[l], te = te_s[l];
-        double n0 = dens * (ne / nemax);
+        double n0 = dens_over_max * ne;
         double vi, vj;
         bspline_eval_pair(cpair, ncy, lx_s[l], ly_s[l], bx_s + l, by_s + l, L, vi, vj);
         double tec = nan_to_num(exp(vi) * i_w + exp(vj) * j_w);
         double p = clip_lo(n0 * tec, 1.0);
-        s[0] += p; s[1] += m.los_w[l] * p; s[2] += p * ne; s[3] += p * (n0 / ne); s[4] += p * te;
+        s[0] += p; s[1] += m.los_w[l] * p; s[2] += p * ne; s[3] += p * dens_over_max; s[4] += p * te;
       }
 #pragma unroll
       for (int q = 0; q < 5; ++q) s[q] = team.sum(s[q]);
