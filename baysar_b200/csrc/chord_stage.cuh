@@ -530,36 +530,44 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
     for (int base = 0; base < total; base += gcap) {
       const int nb = total - base < gcap ? total - base : gcap;
       for (int g = tid; g < nb; g += NT) {
-        // locate the line object of component base + g
-        int k = 0, first = 0;
-        const int* cl = nullptr;
-        for (; k < ch[CH_N_LINES]; ++k) {
-          cl = m.cl_i + (ch[CH_LINE_OFF] + k) * CL_I_COUNT;
-          if (cl[CL_KIND] == 0) continue;
-          if (base + g < first + cl[CL_NCOMP]) break;
-          first += cl[CL_NCOMP];
+        // This chain runs on a few threads while the rest of the block waits at the barrier below, so it is kept
+        // short: the line object of component base + g is found by a branch-free scan (the table reads of different
+        // lines overlap), the reciprocals that do not depend on the line record are formed while its loads are in
+        // flight, and the remaining divisions are multiplications by them (relative difference ~1e-16).
+        const int idx = base + g, n_lines = ch[CH_N_LINES], line_off = ch[CH_LINE_OFF];
+        int k = 0, first = 0, run = 0;
+        for (int kk = 0; kk < n_lines; ++kk) {
+          const int* clk = m.cl_i + (line_off + kk) * CL_I_COUNT;
+          const int nc = clk[CL_KIND] != 0 ? clk[CL_NCOMP] : 0;
+          if (idx >= run && idx < run + nc) { k = kk; first = run; }
+          run += nc;
         }
-        const double* cld = m.cl_d + (ch[CH_LINE_OFF] + k) * CL_D_COUNT;
+        const int* cl = m.cl_i + (line_off + k) * CL_I_COUNT;
+        const double* cld = m.cl_d + (line_off + k) * CL_D_COUNT;
         const double* rec = lines_n + cl[CL_ULINE] * BAYSAR_LINE_STRIDE;
-        const double* cp = m.comp_d + (cl[CL_COMP_OFF] + (base + g - first)) * 2;
+        const double* cp = m.comp_d + (cl[CL_COMP_OFF] + (idx - first)) * 2;
+        const double rec0 = rec[0], rec4 = rec[4];
+        const double inv_cal = 1.0 / cal, inv_delta = 1.0 / delta;
         double cw = cp[0], fwhm;
         if (cl[CL_KIND] == 1) {
+          const double inv_mass = 1.0 / cld[CL_MASS];
           if (cl[CL_SPECIES] >= 0) {
             const int vi = m.sp_i[cl[CL_SPECIES] * SP_I_COUNT + SP_VEL_IDX];
-            if (vi >= 0) cw = cw * ((1e3 * th[vi]) / c_light + 1.0);
+            if (vi >= 0) cw = cw * ((1e3 * th[vi]) * (1.0 / c_light) + 1.0);
           }
-          fwhm = cw * 7.715e-5 * sqrt(rec[4] / cld[CL_MASS]);
+          fwhm = cw * 7.715e-5 * sqrt(rec4 * inv_mass);
         } else {
           fwhm = cld[CL_FWHM];
         }
         if (!(fwhm > 0.0) || !(cp[1] > 0.0)) st |= 1u << 5;
         const double sigma = fwhm * fwhm_to_sigma;
-        const double amp = (rec[0] * (cp[1] / (2.5066282746310002 * sigma))) / cal;
+        const double inv_sigma = 1.0 / sigma;
+        const double amp = (rec0 * (cp[1] * (inv_sigma * (1.0 / 2.5066282746310002)))) * inv_cal;
         if (!(amp - amp == 0.0)) st |= 1u << 6;
         const double half = BAYSAR_Z_CUT * sigma;
-        const double jl = ceil((cw - half - x0) / delta - 1e-9), jh = floor((cw + half - x0) / delta + 1e-9);
+        const double jl = ceil((cw - half - x0) * inv_delta - 1e-9), jh = floor((cw + half - x0) * inv_delta + 1e-9);
         GaussComp c;
-        c.cw = cw; c.inv_sigma = 1.0 / sigma; c.amp = (float)amp;
+        c.cw = cw; c.inv_sigma = inv_sigma; c.amp = (float)amp;
         c.j_lo = jl < 0.0 ? 0 : (jl > (double)F ? F : (int)jl);
         c.j_hi = jh < -1.0 ? -1 : (jh > (double)(F - 1) ? F - 1 : (int)jh);
         if (!(jl == jl) || !(jh == jh)) { c.j_lo = 0; c.j_hi = -1; }
