@@ -56,6 +56,18 @@ class DataArray:
             return DataArray(coords[name])
         raise AttributeError(name)
 
+    @property
+    def shape(self):
+        return self.data.shape
+
+    def __array__(self, dtype=None, copy=None):
+        return self.data if dtype is None else self.data.astype(dtype)
+
+    def __rmul__(self, other):  # `tau * scd` (gcr/ionisation_balance.py:37)
+        return DataArray(other * self.data, dims=self.dims, coords=self.coords, name=self.name, attrs=self.attrs)
+
+    __mul__ = __rmul__
+
     def sel(self, block):
         i = int(np.where(self.coords["block"] == block)[0][0])
         rest = {k: v for k, v in self.coords.items() if k != "block"}
