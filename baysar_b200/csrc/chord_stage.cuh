@@ -992,8 +992,14 @@ struct PixelFoldArgs {
   uint32_t* status;
 };
 
+// Register budget: the kernel waits on global-load latency (row staging, per-pixel tables), so resident CTAs matter more
+// than registers: 14 CTAs of 128 threads per SM (32 registers, ~100 bytes of spills) run the 4096-theta demo step in 2 waves
+// instead of 4 at the compiler's own 64 registers (measured 49.7 -> 45.1 us at 10 CTAs -> 40.6 us at 14).
+#ifndef BAYSAR_PIXFOLD_MINB
+#define BAYSAR_PIXFOLD_MINB 14
+#endif
 template <int NT>
-__global__ void __launch_bounds__(NT) pixel_fold_kernel(ModelDev m, PixelFoldArgs a) {
+__global__ void __launch_bounds__(NT, BAYSAR_PIXFOLD_MINB) pixel_fold_kernel(ModelDev m, PixelFoldArgs a) {
 #ifdef BAYSAR_CPU_EMU
   double* scratch = reinterpret_cast<double*>(emu_dynamic_smem());
   float* row = reinterpret_cast<float*>(scratch + 160);
