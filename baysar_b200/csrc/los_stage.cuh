@@ -306,27 +306,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) s[q] = team.sum(s[q]);
-      s[8] = s[0] + s[1]; s[9] = s[2] + s[3]; s[10] = s[4] + s[6]; s[11] = s[5] + s[7];
-      double rec_sum = s[2] / four_pi, exc_sum = s[3] / four_pi, ems = s[9] / four_pi;
-      double rec_ne = s[4] / s[0], rec_te = s[5] / s[0], exc_ne = s[6] / s[1], exc_te = s[7] / s[1];
-      double f_rec = rec_sum / ems;
-      double ti;
-      const int* sp = m.sp_i + ul[UL_SPECIES] * SP_I_COUNT;
-      if (cold_neutrals) ti = 0.01;
-      else if (thermalised) ti = (1 - f_rec) * exc_te + f_rec * rec_te;
-      else ti = p10[sp[SP_TI_IDX]];
-      // shape constants shared by every chord that sees this line: Doppler-shifted centre (linemodels.py:239-241) and
-      // Doppler sigma (:298, lineshapes.py:128); the pow-heavy Stark half-widths follow after the line loop, one
-      // lane per (line, recombination / excitation)
-      const double* ud = m.ul_d + u * UL_D_COUNT;
+      // The line's scalars (seven divisions, a square root) are uniform across the warp, so forming them here would run
+      // them once per line, one line after the other; the raw sums wait in the record instead and one lane per line
+      // forms all lines' scalars side by side after the loop.
       if (lane == 2) {
-        rec[0] = rec_sum; rec[1] = exc_sum; rec[2] = rec_ne; rec[3] = rec_te; rec[4] = exc_ne; rec[5] = exc_te;
-        rec[6] = ti; rec[7] = f_rec; rec[8] = s[10] / s[8]; rec[9] = s[11] / s[8]; rec[10] = ems;
-        const int vi = sp[SP_VEL_IDX];
-        const double cwl = vi >= 0 ? ud[UL_CWL0] * ((1e3 * th[vi]) / 299792458.0 + 1.0) : ud[UL_CWL0];
-        rec[13] = cwl;
-        rec[14] = cwl * 7.715e-5 * sqrt(ti / ud[UL_MASS]) * 0.42466090014400953;
-        rec[15] = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) rec[q] = s[q];
       }
     } else if (kind == 1) {  // ADAS406 (linemodels.py:386-426, :445-494)
       const int* sp = m.sp_i + ul[UL_SPECIES] * SP_I_COUNT;
@@ -373,6 +358,36 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
         for (int q = 1; q < BAYSAR_LINE_STRIDE; ++q) rec[q] = 0.0;
       }
     }
+  }
+  team.sync();
+  // Balmer line scalars from the raw sums, one lane per line (linemodels.py:796-836)
+  for (int u = lane; u < n_ul; u += TS) {
+    const int* ul = m.ul_i + u * UL_I_COUNT;
+    if (ul[UL_KIND] != 0) continue;
+    double* rec = lines_n + u * BAYSAR_LINE_STRIDE;
+    double s[12];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[q] = rec[q];
+    s[8] = s[0] + s[1]; s[9] = s[2] + s[3]; s[10] = s[4] + s[6]; s[11] = s[5] + s[7];
+    double rec_sum = s[2] / four_pi, exc_sum = s[3] / four_pi, ems = s[9] / four_pi;
+    double rec_ne = s[4] / s[0], rec_te = s[5] / s[0], exc_ne = s[6] / s[1], exc_te = s[7] / s[1];
+    double f_rec = rec_sum / ems;
+    double ti;
+    const int* sp = m.sp_i + ul[UL_SPECIES] * SP_I_COUNT;
+    if (cold_neutrals) ti = 0.01;
+    else if (thermalised) ti = (1 - f_rec) * exc_te + f_rec * rec_te;
+    else ti = p10[sp[SP_TI_IDX]];
+    // shape constants shared by every chord that sees this line: Doppler-shifted centre (linemodels.py:239-241) and
+    // Doppler sigma (:298, lineshapes.py:128); the pow-heavy Stark half-widths follow, one lane per (line,
+    // recombination / excitation)
+    const double* ud = m.ul_d + u * UL_D_COUNT;
+    rec[0] = rec_sum; rec[1] = exc_sum; rec[2] = rec_ne; rec[3] = rec_te; rec[4] = exc_ne; rec[5] = exc_te;
+    rec[6] = ti; rec[7] = f_rec; rec[8] = s[10] / s[8]; rec[9] = s[11] / s[8]; rec[10] = ems;
+    const int vi = sp[SP_VEL_IDX];
+    const double cwl = vi >= 0 ? ud[UL_CWL0] * ((1e3 * th[vi]) / 299792458.0 + 1.0) : ud[UL_CWL0];
+    rec[13] = cwl;
+    rec[14] = cwl * 7.715e-5 * sqrt(ti / ud[UL_MASS]) * 0.42466090014400953;
+    rec[15] = 0.0;
   }
   team.sync();
   // Stark half-widths gamma^2.5 of every Balmer line (stehle_param, linemodels.py:554-566): lane 2q / 2q+1 take the
