@@ -343,14 +343,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       }
 #pragma unroll
       for (int q = 0; q < 5; ++q) s[q] = team.sum(s[q]);
-      double ems_te = s[4] / s[0];
-      double ti;
-      if (cold_ions) ti = 0.01;
-      else if (thermalised) ti = ems_te;
-      else ti = p10[sp[SP_TI_IDX]];
-      if (lane == 0) {
-        rec[0] = s[1] / four_pi; rec[1] = s[2] / s[0]; rec[2] = s[3] / s[0]; rec[3] = ems_te; rec[4] = ti;
-        for (int q = 5; q < BAYSAR_LINE_STRIDE; ++q) rec[q] = 0.0;
+      if (lane == 0) {  // raw sums; the scalars follow after the loop, one lane per line (as for the Balmer lines)
+#pragma unroll
+        for (int q = 0; q < 5; ++q) rec[q] = s[q];
       }
     } else {  // XLine (linemodels.py:228-230)
       if (lane == 0) {
@@ -360,11 +355,25 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     }
   }
   team.sync();
-  // Balmer line scalars from the raw sums, one lane per line (linemodels.py:796-836)
+  // line scalars from the raw sums, one lane per line (Balmer: linemodels.py:796-836)
   for (int u = lane; u < n_ul; u += TS) {
     const int* ul = m.ul_i + u * UL_I_COUNT;
-    if (ul[UL_KIND] != 0) continue;
     double* rec = lines_n + u * BAYSAR_LINE_STRIDE;
+    if (ul[UL_KIND] == 1) {  // ADAS406 (linemodels.py:405-426)
+      const int* sp = m.sp_i + ul[UL_SPECIES] * SP_I_COUNT;
+      double s[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) s[q] = rec[q];
+      const double ems_te = s[4] / s[0];
+      double ti;
+      if (cold_ions) ti = 0.01;
+      else if (thermalised) ti = ems_te;
+      else ti = p10[sp[SP_TI_IDX]];
+      rec[0] = s[1] / four_pi; rec[1] = s[2] / s[0]; rec[2] = s[3] / s[0]; rec[3] = ems_te; rec[4] = ti;
+      for (int q = 5; q < BAYSAR_LINE_STRIDE; ++q) rec[q] = 0.0;
+      continue;
+    }
+    if (ul[UL_KIND] != 0) continue;
     double s[12];
 #pragma unroll
     for (int q = 0; q < 8; ++q) s[q] = rec[q];
