@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     double v = th[k];
     if (v != v) st |= 1u << 0;
     if (v - v != 0.0 && v == v) st |= 1u << 1;  // +-inf
-    const double p = pow(10.0, v);
+    const double p = exp10(v);  // numpy's 10 ** theta; pow(10, v) is three times the instructions for the same ~1 ulp
     p10[k] = p;
     l10[k] = log10(p);
   }
@@ -408,8 +408,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     double* rec = lines_n + u * BAYSAR_LINE_STRIDE;
     const double la = ud[UL_LOMAN_A], lb = ud[UL_LOMAN_B], lc = ud[UL_LOMAN_C];
     const double wne = rec[2 + 2 * which], wte = rec[3 + 2 * which];
-    const double g = (10.0 * lc * (pow(1e6 * wne, la) / pow(wte, lb))) / 2.0;
-    rec[11 + which] = pow(g, 2.5);
+    // 10 c (1e6 ne)^a / Te^b / 2 with the two general powers as one exponential of logarithms, and g^2.5 = g^2 sqrt(g):
+    // ~1e-14 relative against three pow() calls, a third of their instructions (the widths end up in float32)
+    const double g = (10.0 * lc * exp(la * log(1e6 * wne) - lb * log(wte))) / 2.0;
+    rec[11 + which] = g * g * sqrt(g);
   }
   team.sync();
 
