@@ -502,7 +502,7 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
   a.theta = theta; a.n = n; a.lines = lines; a.components = comps; a.hdr = m->hdr; a.profiles = profiles;
   a.status = status;
   const int L = (int)m->I[I_L];
-  const size_t per_warp = los_smem_per_warp(L, (int)m->I[I_N_PARAMS]);
+  const size_t per_warp = los_smem_per_warp(L, (int)m->I[I_N_PARAMS], (int)m->I[I_N_SPECIES]);
   if (per_warp > 200 * 1024) return fail("line-of-sight grid too long for the shared-memory LOS stage");
   // Register budget by batch size.  The kernel is latency-bound at 16 warps per SM (4 CTAs, 128 registers, no spills):
   // the best choice for many waves.  A batch of a few thousand thetas, though, is one or two waves, and then fitting

@@ -23,8 +23,9 @@ struct LosArgs {
 };
 
 // bytes of dynamic shared memory one warp needs for L line-of-sight points
-__host__ __device__ static inline size_t los_smem_per_warp(int L, int n_params) {
-  return (size_t)L * (14 * sizeof(double) + 4 * sizeof(int)) + (size_t)(2 * n_params + (L & 1)) * sizeof(double);
+__host__ __device__ static inline size_t los_smem_per_warp(int L, int n_params, int n_species) {
+  return (size_t)L * (14 * sizeof(double) + 4 * sizeof(int)) +
+         (size_t)(2 * n_params + 3 * n_species + (L & 1)) * sizeof(double);
 }
 
 // TW warps cooperate on one theta.  TW = 1 is the warp-per-theta form (reductions are warp shuffles); TW = 4 runs one CTA
@@ -102,10 +103,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
   const int n_chords = (int)I[I_N_CHORDS];
   const double* th = a.theta + n * n_params;
 
-  unsigned char* base = los_smem_raw + (size_t)warp * los_smem_per_warp(L, n_params);
+  unsigned char* base = los_smem_raw + (size_t)warp * los_smem_per_warp(L, n_params, n_species);
   double* __restrict__ p10 = (double*)base;        // 10^theta[k]: every pow(10, theta) of the reference, one lane per parameter
   double* __restrict__ l10 = p10 + n_params;       // log10(10^theta[k]) (the reference takes log10 of the transformed tau)
-  double* __restrict__ ne_s = l10 + n_params;
+  double* __restrict__ spw = l10 + n_params;       // per species: ADAS tau-slice pair index and its two weights
+  double* __restrict__ ne_s = spw + 3 * n_species;
   double* __restrict__ te_s = ne_s + L;
   double* __restrict__ nm_s = te_s + L;   // main ion density
   double* __restrict__ n0_s = nm_s + L;   // neutral density profile
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
   int* __restrict__ hj_s = hi_s + L;
   int* __restrict__ lx_s = hj_s + L;
   int* __restrict__ ly_s = lx_s + L;
-  LosTeam<TW> team{reinterpret_cast<double*>(los_smem_raw + (size_t)(TW == 1 ? WARPS : 1) * los_smem_per_warp(L, n_params))};
+  LosTeam<TW> team{reinterpret_cast<double*>(los_smem_raw + (size_t)(TW == 1 ? WARPS : 1) * los_smem_per_warp(L, n_params, n_species))};
 
   uint32_t st = 0;
   for (int k = lane; k < n_params; k += TS) {
@@ -219,6 +221,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     if (sp[SP_IS_IMPURITY]) {
       double lt = l10[sp[SP_TAU_IDX]];
       if (!(lt > m.tau_grid[0] && lt <= m.tau_grid[n_tau - 1])) st |= 1u << 2;
+      // tau slices (j - 1, j) and their weights (linemodels.py:450-451, :469-473), once per species, lanes side by side:
+      // every line of the species reads them back instead of repeating the search and the two divisions
+      int j = lower_bound(m.tau_grid, n_tau, lt);
+      if (j >= n_tau) j = n_tau - 1;  // flagged above
+      int i = j - 1;
+      if (i < 0) i = n_tau - 1;  // python's negative index (flagged above)
+      const double ti_ = m.tau_grid[i], tj_ = m.tau_grid[j];
+      spw[3 * s] = (double)(j > 0 ? j - 1 : 0);  // the out-of-grid case j = 0 reads pair 0
+      spw[3 * s + 1] = 1.0 + (lt - ti_) / (ti_ - tj_);
+      spw[3 * s + 2] = 1.0 + (tj_ - lt) / (ti_ - tj_);
     }
   }
 
@@ -316,16 +328,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     } else if (kind == 1) {  // ADAS406 (linemodels.py:386-426, :445-494)
       const int* sp = m.sp_i + ul[UL_SPECIES] * SP_I_COUNT;
       const double dens = p10[sp[SP_DENS_IDX]];
-      const double lt = l10[sp[SP_TAU_IDX]];
-      int j = lower_bound(m.tau_grid, n_tau, lt);
-      if (j >= n_tau) { st |= 1u << 2; j = n_tau - 1; }
-      int i = j - 1;
-      if (i < 0) i = n_tau - 1;  // python's negative index (already flagged above)
-      const double ti_ = m.tau_grid[i], tj_ = m.tau_grid[j];
-      const double i_w = 1.0 + (lt - ti_) / (ti_ - tj_), j_w = 1.0 + (tj_ - lt) / (ti_ - tj_);
+      const double* w3 = spw + 3 * ul[UL_SPECIES];
+      const int pair = (int)w3[0];
+      const double i_w = w3[1], j_w = w3[2];
       const int ncx = snx - 4, ncy = sny - 4;
-      // coefficient pairs of tau slices (j - 1, j); the out-of-grid case j = 0 (flagged) reads pair 0
-      const int pair = j > 0 ? j - 1 : 0;
       const double* cpair = m.spl_c + ((int64_t)ul[UL_TAB_A] * (n_tau - 1) + pair) * ncx * ncy * 2;
       double s[5] = {0, 0, 0, 0, 0};
       // n0 = dens * (ne / ne_max) and the concentration weight n0 / ne = dens / ne_max (linemodels.py:392-394, :411):

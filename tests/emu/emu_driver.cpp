@@ -37,7 +37,7 @@ extern "C" int emu_eval_split(const unsigned char* blob, const double* theta, lo
   LosArgs la{theta, n, lines, comps, hdr.data(), nullptr, status};
   EmuDim3 g;
   g.x = (unsigned)((n + 3) / 4);
-  emu_launch(los_stage_kernel<4>, g, 128u, 4 * los_smem_per_warp(L, (int)I[I_N_PARAMS]), m, la);
+  emu_launch(los_stage_kernel<4>, g, 128u, 4 * los_smem_per_warp(L, (int)I[I_N_PARAMS], (int)I[I_N_SPECIES]), m, la);
   for (int c = 0; c < n_chords; ++c) {
     const int* ch = m.ch_i + c * CH_I_COUNT;
     const int F = ch[CH_F], KI = ch[CH_KI], k_lo = ch[CH_IF_KLO], k_hi = ch[CH_IF_KHI], o = (KI - 1) / 2;
@@ -101,10 +101,10 @@ extern "C" int emu_eval(const unsigned char* blob, const double* theta, long n, 
   EmuDim3 g;
   if (getenv("BAYSAR_EMU_LOS_TEAM")) {  // the one-CTA-per-theta form the product uses for long lines of sight
     g.x = (unsigned)n;
-    emu_launch(los_stage_kernel<4, 1, 1, 4>, g, 128u, los_smem_per_warp(L, (int)I[I_N_PARAMS]) + 128, m, la);
+    emu_launch(los_stage_kernel<4, 1, 1, 4>, g, 128u, los_smem_per_warp(L, (int)I[I_N_PARAMS], (int)I[I_N_SPECIES]) + 128, m, la);
   } else {
     g.x = (unsigned)((n + 3) / 4);
-    emu_launch(los_stage_kernel<4>, g, 128u, 4 * los_smem_per_warp(L, (int)I[I_N_PARAMS]), m, la);
+    emu_launch(los_stage_kernel<4>, g, 128u, 4 * los_smem_per_warp(L, (int)I[I_N_PARAMS], (int)I[I_N_SPECIES]), m, la);
   }
   for (int c = 0; c < n_chords; ++c) {
     const int* ch = m.ch_i + c * CH_I_COUNT;
