@@ -97,12 +97,14 @@ BAYSAR_DEV double nan_to_num(double v) {
 
 // max([0, x]) of the reference's gaussian_{high,low}_pass_cost (priors.py:4-11): NaN -> 0
 BAYSAR_DEV double pos_part(double x) { return x > 0.0 ? x : 0.0; }
+// (the division by the width is a multiplication by its reciprocal: inside a loop over line-of-sight points the
+// reciprocal is loop-invariant and leaves the loop; relative difference ~1e-16)
 BAYSAR_DEV double high_pass(double v, double thr, double err) {
-  double t = pos_part(thr - v) / err;
+  double t = pos_part(thr - v) * (1.0 / err);
   return -0.5 * (t * t);
 }
 BAYSAR_DEV double low_pass(double v, double thr, double err) {
-  double t = pos_part(v - thr) / err;
+  double t = pos_part(v - thr) * (1.0 / err);
   return -0.5 * (t * t);
 }
 

@@ -459,14 +459,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       double s = 0.0;
       for (int l = lane; l < L; l += TS) {
         double pe = clip_lo(te_s[l], 0.01) * clip_lo(ne_s[l], 1.0);
-        s += low_pass(pe / 5e15, 1.0, 0.1);
+        s += low_pass(pe * (1.0 / 5e15), 1.0, 0.1);
       }
       val = team.sum(s);
     } else if (kind == PRIOR_NEUTRAL_FRACTION) {  // priors.py:83-101
       double s = 0.0;
       for (int l = lane; l < L; l += TS) {
         double f0 = clip_lo(n0_s[l], 1.0) / ne_s[l];
-        s += high_pass(f0 / 5e-3, 1.0, 0.1);
+        s += high_pass(f0 * (1.0 / 5e-3), 1.0, 0.1);
       }
       val = team.sum(s);
     } else if (kind == PRIOR_STARK_TO_PEAK) {  // priors.py:646-667
