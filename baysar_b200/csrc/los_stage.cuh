@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       double s = 0.0; int any_neg = 0;
       for (int l = lane; l < L; l += TS) {
         double ni = nm_s[l];
-        if (ni < 0) { any_neg = 1; double t = ni / 1e11; s += t * t; }
+        if (ni < 0) { any_neg = 1; double t = ni * (1.0 / 1e11); s += t * t; }
       }
       s = team.sum(s);
       any_neg = team.any(any_neg);
@@ -491,11 +491,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       }
       team.argmax(best, bi);
       if (bi >= L) bi = 0;
-      const double ref = clip_lo(ne_s[bi], 1.0);
+      const double inv_ref = 1.0 / clip_lo(ne_s[bi], 1.0);
       double s = 0.0;
       for (int l = lane; l < L; l += TS) {
         double nec = clip_lo(ne_s[l], 1.0);
-        double factor = clip_lo(nec / ref, 0.3);
+        double factor = clip_lo(nec * inv_ref, 0.3);
         s += high_pass(nm_s[l] / nec, factor * 0.8, 0.1);
       }
       val = team.sum(s);
