@@ -74,8 +74,10 @@ def gaussian_if(npix=31, sigma_px=1.2):
     return np.exp(-0.5 * ((x - (npix - 1) / 2.0) / sigma_px) ** 2)
 
 
-def balmer_series(data="selfconsistent"):
-    """configs[1]: `demo/balmer_series.py` — H Balmer n=5..9->2, 1024 px, refine 0.1, L=50, n=10."""
+def balmer_series(data="selfconsistent", flags=None):
+    """configs[1]: `demo/balmer_series.py` — H Balmer n=5..9->2, 1024 px, refine 0.1, L=50, n=10.
+    ``flags``: extra `make_input_dict` keywords (e.g. ``cold_neutrals=False``: thermalised neutrals, whose Doppler kernels
+    span 30-200 taps of the 0.1 A grid — the multi-tap Stark (x) Doppler path)."""
     wave = _stored("balmer_wave")
     if data == "zero_fit":
         ems = _stored("balmer_zero_fit_ems")
@@ -85,9 +87,14 @@ def balmer_series(data="selfconsistent"):
               emission_constant=[1e11], noise_region=[[4150.0, 4250.0]], species=["H"], ions=[["0"]],
               mystery_lines=None, refine=0.1, no_sample_neutrals=False, ion_resolved_temperatures=False,
               ion_resolved_tau=False)
+    if flags:
+        kw.update(flags)
     ref = {"electron_density": [np.log10(8e13), 0.0, 3.0], "electron_temperature": [np.log10(5.0), 3.0, 1.0],
            "H_0_dens": [np.log10(8e13)], "H_0_tau": [-8.0], "H_0_velocity": [0.0], "background_0": [12.05]}
-    return Workload("balmer_series", kw, None, ref, "H Balmer series with Stark broadening (demo/balmer_series.py)")
+    hot = bool(flags) and flags.get("cold_neutrals") is False
+    return Workload("balmer_hot" if hot else "balmer_series", kw, None, ref,
+                    "H Balmer series with Stark broadening (demo/balmer_series.py)" +
+                    (", thermalised neutrals (multi-tap Doppler kernels)" if hot else ""))
 
 
 def balmer_two_chords():

@@ -1,84 +1,10 @@
 // C ABI of the B200-native BaySAR posterior path (include/baysar_b200.h): model upload, workspace, launches.
-#include <cuda_runtime.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-
-#include <algorithm>
-#include <map>
-#include <new>
-#include <string>
-#include <vector>
-
 #include "../../include/baysar_b200.h"
 #include "chord_stage.cuh"
 #include "ensemble.cuh"
 #include "finalize.cuh"
-#include "if_contract.cuh"
+#include "host_plans.h"
 #include "los_stage.cuh"
-#include "mma_probe.cuh"
-#include "pix_contract.cuh"
-
-static thread_local std::string g_last_error;
-
-static int fail(const std::string& msg) {
-  g_last_error = msg;
-  return 1;
-}
-#define CUDA_OK(expr)                                                                          \
-  do {                                                                                         \
-    cudaError_t e_ = (expr);                                                                   \
-    if (e_ != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));    \
-  } while (0)
-
-namespace {
-// Host-side packing of one chord's instrument function for the tensor-core contraction (if_contract.cuh).
-struct IfcPlan {
-  int m_lo = 0, m_hi = 0, pad_left = 0, n_tiles = 0, taps_len = 0;
-  int64_t pitch = 0, out_pitch = 0;
-  std::vector<float> taps_rev;  // [2][4][taps_len]
-  // compact output for a static wavelength map: needed-column bit mask / running count per 32 columns
-  std::vector<uint32_t> cmask;
-  std::vector<int> cbase;
-  int64_t c_pitch = 0;
-};
-
-// Host-side plan of the folded pixel contraction (pix_contract.cuh) of one chord: column tiles with their bands, the
-// zero-padded tap table, the end-zone weights of the area identity, and per-batch-size schedules.
-struct PxcSchedule {
-  int ctas = 0, slots = 0;
-  int *d_sched = nullptr, *d_cnt = nullptr;
-};
-struct PxcPlan {
-  bool on = false;
-  int tn = 128, pad_left = 0, n_col_tiles = 0, wlen = 0, ring = 0;
-  int e_l = 0, e_r = 0, x_l = 0, x_r = 0, col_left0 = 0, col_right0 = 0, n_dl = 0, n_dr = 0;
-  int64_t pitch = 0, out_pitch = 0;
-  double wsum = 0.0;
-  std::vector<int> tile_kcol0, tile_nkb, tile_boff, col_idx, pix_col;
-  int n_fold_tiles = 0;
-  std::vector<float> inv_err;  // 1 / err of the chord's pixels (pixel_fold_kernel's log-posterior loop)
-  float* d_inv_err = nullptr;
-  std::vector<float> col_frac, wtab, bbar;  // bbar: per folded tile, sum over its columns of B[s, c] (bias correction)
-  std::vector<double> dtab;
-  int *d_tile_kcol0 = nullptr, *d_tile_nkb = nullptr, *d_tile_boff = nullptr, *d_col_idx = nullptr, *d_pix_col = nullptr;
-  float *d_col_frac = nullptr, *d_wtab = nullptr, *d_bbar = nullptr;
-  double* d_dtab = nullptr;
-  std::map<int, PxcSchedule> schedules;  // by number of theta blocks
-};
-
-static float tf32_round(float v) {  // round to nearest, ties away from zero, 10-bit mantissa (cvt.rna.tf32.f32)
-  uint32_t u;
-  memcpy(&u, &v, 4);
-  u = (u + 0x1000u) & 0xFFFFE000u;
-  float r;
-  memcpy(&r, &u, 4);
-  return r;
-}
-
-static inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
-
-}  // namespace
 
 struct baysar_model {
   int device = 0;
@@ -118,10 +44,18 @@ struct baysar_model {
   int64_t split_pitch_max = 0, conv_pitch_max = 0;
   int tiles_max = 0;
   int last_launches = 3;
-  // optional per-stage timing (bench.py roofline): events tagged with the stage that ends at them
+  baysar_options_t opt{};  // tuning options given at creation (0 = default everywhere)
+  // optional per-stage timing (bench.py roofline): events tagged with the stage that ends at them.  The events are a pool
+  // that only grows (first profiled calls) and is reused after every baysar_model_get_profile
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
-  std::vector<int> prof_slots;
+  std::vector<int> prof_slots;  // stage tags of the prof_used recorded events
+  size_t prof_used = 0;
+  // host-buffer entry point: its own non-blocking stream (the legacy default stream would serialise with every other
+  // stream of the process)
+  cudaStream_t host_stream = nullptr;
+  // one workspace per model: every evaluation waits for the previous one (whatever stream it ran on) before it starts
+  cudaEvent_t last_done = nullptr;
 };
 
 namespace {
@@ -132,354 +66,6 @@ struct SectionTable {
   const void* ptr(int s) const { return base + hdr[3 + 2 * s]; }
   int64_t count(int s) const { return hdr[3 + 2 * s + 1]; }
 };
-
-// Peak-rate probes for the roofline denominators MEASURED_PEAKS.json does not carry (FP32 FMA, MUFU, FP64 FMA):
-// 16 independent dependency chains per thread, enough resident warps to saturate the pipe.
-__global__ void microbench_ffma_kernel(float* out, int iters, float a) {
-  float v[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) v[k] = threadIdx.x * 1e-3f + k;
-  for (int i = 0; i < iters; ++i) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) v[k] = fmaf(v[k], a, 0.5f);
-  }
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) s += v[k];
-  if (s == 12345.678f) out[threadIdx.x] = s;
-}
-__global__ void microbench_mufu_kernel(float* out, int iters, float a) {
-  float v[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) v[k] = threadIdx.x * 1e-3f + k + 1.f;
-  for (int i = 0; i < iters; ++i) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(v[k]) : "f"(v[k]));
-  }
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) s += v[k];
-  if (s == 12345.678f) out[threadIdx.x] = s * a;
-}
-// FFMA with all three operands in registers (the form real kernels issue; the immediate form above is the pipe's
-// best case) and the packed FFMA2 (fma.rn.f32x2, two FMAs per lane and instruction, sm_100+)
-__global__ void microbench_ffma_reg_kernel(float* out, int iters, float a, float b) {
-  float v[16];
-  const float ar = a + (float)(threadIdx.x & 1) * 1e-9f, br = b + (float)(threadIdx.x & 2) * 1e-9f;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) v[k] = threadIdx.x * 1e-3f + k;
-  for (int i = 0; i < iters; ++i) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) v[k] = fmaf(v[k], ar, br);
-  }
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) s += v[k];
-  if (s == 12345.678f) out[threadIdx.x] = s;
-}
-__global__ void microbench_ffma2_kernel(float* out, int iters, float a, float b) {
-  unsigned long long v[16], ar, br;
-  const float a0 = a + (float)(threadIdx.x & 1) * 1e-9f, b0 = b + (float)(threadIdx.x & 2) * 1e-9f;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ar) : "f"(a0), "f"(a0));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(br) : "f"(b0), "f"(b0));
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const float x = threadIdx.x * 1e-3f + k;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(v[k]) : "f"(x), "f"(x + 0.5f));
-  }
-  for (int i = 0; i < iters; ++i) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v[k]) : "l"(ar), "l"(br));
-  }
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v[k]));
-    s += lo + hi;
-  }
-  if (s == 12345.678f) out[threadIdx.x] = s;
-}
-__global__ void microbench_dfma_kernel(double* out, int iters, double a) {
-  double v[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) v[k] = threadIdx.x * 1e-3 + k;
-  for (int i = 0; i < iters; ++i) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) v[k] = fma(v[k], a, 0.5);
-  }
-  double s = 0.0;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) s += v[k];
-  if (s == 12345.678) out[threadIdx.x] = s;
-}
-
-IfcPlan make_ifc_plan(const double* w, int KI, int k_lo, int k_hi, int F) {
-  IfcPlan pl;
-  const int o = (KI - 1) / 2;
-  pl.m_lo = floor_div(o - k_hi + 1, ifc::TILE_K);
-  pl.m_hi = floor_div(ifc::TILE_N - 1 + o - k_lo, ifc::TILE_K);
-  pl.pad_left = -ifc::TILE_K * pl.m_lo;
-  if (pl.pad_left < 0) pl.pad_left = 0;
-  pl.n_tiles = (F + ifc::TILE_N - 1) / ifc::TILE_N;
-  int64_t last_col = (int64_t)pl.pad_left + (int64_t)(pl.n_tiles - 1) * ifc::TILE_N + ifc::TILE_K * pl.m_hi + ifc::TILE_K;
-  if (last_col < pl.pad_left + F) last_col = pl.pad_left + F;
-  pl.pitch = (last_col + 31) / 32 * 32;
-  pl.out_pitch = (int64_t)pl.n_tiles * ifc::TILE_N;
-  pl.taps_len = (164 + ifc::TILE_K * (pl.m_hi - pl.m_lo) + 3) / 4 * 4;
-  const int x_max = ifc::TILE_N - 1 + o - ifc::TILE_K * pl.m_lo;
-  pl.taps_rev.assign((size_t)8 * pl.taps_len, 0.f);
-  for (int s = 0; s < 4; ++s) {
-    for (int i = 0; i < pl.taps_len; ++i) {
-      const int x = x_max - (i + s);  // copy_s[i] = rev[i + s] = w[x_max - i - s]
-      float v = (x >= k_lo && x < k_hi) ? (float)w[x] : 0.f;
-      float hi = tf32_round(v), lo = tf32_round(v - hi);
-      pl.taps_rev[(size_t)s * pl.taps_len + i] = hi;
-      pl.taps_rev[(size_t)(4 + s) * pl.taps_len + i] = lo;
-    }
-  }
-  return pl;
-}
-
-// Columns of the folded contraction: one per pixel (i_p, a_p), then the explicit fine-grid columns of the two edge
-// zones; every group padded to whole tiles by repeating its last column.
-PxcPlan make_pxc_plan(const double* w, int KI, int k_lo, int k_hi, int F, int P, const int* pix_idx, const double* pix_frac,
-                      int tn) {
-  PxcPlan pl;
-  pl.tn = tn;
-  const int o = (KI - 1) / 2;
-  for (int k = k_lo; k < k_hi; ++k)
-    if (!(w[k] >= 0.0)) return pl;  // the clip argument needs non-negative taps
-  pl.e_l = std::max(0, k_hi - 1 - o);
-  pl.e_r = std::max(0, o - k_lo);
-  pl.x_l = pl.e_l + 1;
-  pl.x_r = pl.e_r + 1;
-  if (F < 4 * (pl.e_l + pl.e_r + 2) + 2 * tn || P < 1) return pl;
-  std::vector<int> ci;
-  std::vector<double> ca;
-  auto pad_group = [&]() { while (ci.size() % tn) { ci.push_back(ci.back()); ca.push_back(ca.back()); } };
-  pl.pix_col.assign(P, -1);
-  for (int p = 0; p < P; ++p) {
-    const int i = std::min(std::max(pix_idx[p], 0), F - 2);
-    const bool edge = pix_idx[p] != i || i < pl.e_l || i + 1 >= F - pl.e_r;
-    if (!edge) pl.pix_col[p] = (int)ci.size();
-    ci.push_back(i);
-    ca.push_back(edge ? 0.0 : pix_frac[p]);
-  }
-  pad_group();
-  pl.col_left0 = (int)ci.size();
-  for (int j = 0; j < pl.x_l; ++j) { ci.push_back(j); ca.push_back(0.0); }
-  pad_group();
-  pl.col_right0 = (int)ci.size();
-  for (int j = F - pl.x_r; j < F; ++j) { ci.push_back(j); ca.push_back(0.0); }
-  pad_group();
-  pl.n_col_tiles = (int)ci.size() / tn;
-  pl.out_pitch = (int64_t)ci.size();
-  std::vector<int> k0(pl.n_col_tiles);
-  pl.tile_nkb.assign(pl.n_col_tiles, 0);
-  int min_k0 = 0, max_end = F;
-  for (int t = 0; t < pl.n_col_tiles; ++t) {
-    int i_min = F, i_max = 0;
-    for (int c = t * tn; c < (t + 1) * tn; ++c) {
-      i_min = std::min(i_min, ci[c]);
-      i_max = std::max(i_max, ci[c] + (ca[c] != 0.0 ? 1 : 0));
-    }
-    const int s_min = i_min + o - (k_hi - 1), s_max = i_max + o - k_lo;
-    k0[t] = floor_div(s_min, ifc::TILE_K) * ifc::TILE_K;
-    pl.tile_nkb[t] = std::max((s_max - k0[t]) / ifc::TILE_K + 1, pxc::MIN_KB);
-    min_k0 = std::min(min_k0, k0[t]);
-    max_end = std::max(max_end, k0[t] + ifc::TILE_K * pl.tile_nkb[t]);
-  }
-  pl.pad_left = -min_k0;  // multiple of 16
-  pl.pitch = ((int64_t)pl.pad_left + max_end + 31) / 32 * 32;
-  pl.tile_kcol0.resize(pl.n_col_tiles);
-  // tap index of (column c, source s): u = i_c + o - s; the table holds u in [u_base, u_base + wlen)
-  int u_base = 1 << 30, u_top = -(1 << 30);
-  for (int t = 0; t < pl.n_col_tiles; ++t) {
-    pl.tile_kcol0[t] = pl.pad_left + k0[t];
-    for (int c = t * tn; c < (t + 1) * tn; ++c) {
-      u_base = std::min(u_base, ci[c] + o - (k0[t] + ifc::TILE_K * pl.tile_nkb[t] - 1));
-      u_top = std::max(u_top, ci[c] + 1 + o - k0[t]);
-    }
-  }
-  u_base -= 4;  // the builders read five consecutive taps from x - 3
-  pl.wlen = (u_top - u_base + 1 + 4 + 3) / 4 * 4;
-  pl.wtab.assign(pl.wlen, 0.f);
-  for (int x = 0; x < pl.wlen; ++x) {
-    const int u = x + u_base;
-    if (u >= k_lo && u < k_hi) pl.wtab[x] = (float)w[u];
-  }
-  pl.col_idx.resize(ci.size());
-  pl.col_frac.resize(ci.size());
-  for (int t = 0; t < pl.n_col_tiles; ++t)
-    for (int c = t * tn; c < (t + 1) * tn; ++c) {
-      pl.col_idx[c] = ci[c] + o - k0[t] - u_base;
-      pl.col_frac[c] = (float)ca[c];
-    }
-  // area identity: G_s - W c_s at the two ends (exactly zero in between: same summation order as W)
-  double wsum = 0.0;
-  for (int k = k_lo; k < k_hi; ++k) wsum += w[k];
-  pl.wsum = wsum;
-  const int zone = std::min(F / 2, pl.e_l + pl.e_r + 4);
-  auto d_of = [&](int s) {
-    double g = 0.0;
-    for (int k = k_lo; k < k_hi; ++k) {
-      const int j = s - o + k;
-      if (j >= 0 && j < F) g += ((j == 0 || j == F - 1) ? 0.5 : 1.0) * w[k];
-    }
-    return g - wsum * ((s == 0 || s == F - 1) ? 0.5 : 1.0);
-  };
-  std::vector<double> dl(zone), dr(zone);
-  for (int s = 0; s < zone; ++s) { dl[s] = d_of(s); dr[s] = d_of(F - zone + s); }
-  pl.n_dl = zone;
-  while (pl.n_dl > 0 && dl[pl.n_dl - 1] == 0.0) --pl.n_dl;
-  int first = 0;
-  while (first < zone && dr[first] == 0.0) ++first;
-  pl.n_dr = zone - first;
-  pl.dtab.assign(dl.begin(), dl.begin() + pl.n_dl);
-  pl.dtab.insert(pl.dtab.end(), dr.begin() + first, dr.end());
-  // column-sum identity per folded tile (bias correction of the truncating TMEM accumulation, pixel_fold_kernel):
-  //   sum_{c in tile} C[c] = sum_s S_s bbar_s,  bbar_s = sum_{c in tile} B[s, c] over the tile's band (padding
-  //   columns repeat the last pixel and are part of both sides)
-  pl.n_fold_tiles = pl.col_left0 / tn;
-  pl.tile_boff.assign(pl.n_col_tiles, -1);
-  if (pl.n_fold_tiles <= 64) {
-    for (int t = 0; t < pl.n_fold_tiles; ++t) {
-      pl.tile_boff[t] = (int)pl.bbar.size();
-      const int len = ifc::TILE_K * pl.tile_nkb[t];
-      std::vector<double> bb(len, 0.0);
-      for (int c = t * tn; c < (t + 1) * tn; ++c)
-        for (int x = 0; x < len; ++x) {
-          const int idx = pl.col_idx[c] - x;  // the builders' index arithmetic
-          bb[x] += (double)pl.wtab[idx] + (double)pl.col_frac[c] * ((double)pl.wtab[idx + 1] - (double)pl.wtab[idx]);
-        }
-      for (int x = 0; x < len; ++x) pl.bbar.push_back((float)bb[x]);
-    }
-  }
-  if (pl.bbar.empty()) pl.bbar.push_back(0.f);
-  if (pl.dtab.empty()) pl.dtab.push_back(0.0);
-  pl.ring = tn == 64 ? pxc::ring_stages<64>(pl.wlen) : pxc::ring_stages<128>(pl.wlen);
-  pl.on = pl.ring >= 2 && pl.n_col_tiles < 32768;
-  return pl;
-}
-
-template <class T>
-int upload(T** dst, const std::vector<T>& v) {
-  CUDA_OK(cudaMalloc(dst, sizeof(T) * v.size()));
-  CUDA_OK(cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
-  return 0;
-}
-int upload_pxc_plan(PxcPlan& pl) {
-  if (upload(&pl.d_tile_kcol0, pl.tile_kcol0) || upload(&pl.d_tile_nkb, pl.tile_nkb) || upload(&pl.d_col_idx, pl.col_idx) ||
-      upload(&pl.d_tile_boff, pl.tile_boff) ||
-      upload(&pl.d_pix_col, pl.pix_col) || upload(&pl.d_col_frac, pl.col_frac) || upload(&pl.d_wtab, pl.wtab) ||
-      upload(&pl.d_dtab, pl.dtab) || upload(&pl.d_bbar, pl.bbar))
-    return 1;
-  if (!pl.inv_err.empty() && upload(&pl.d_inv_err, pl.inv_err)) return 1;
-  return 0;
-}
-void free_pxc_plan(PxcPlan& pl) {
-  cudaFree(pl.d_tile_kcol0); cudaFree(pl.d_tile_nkb); cudaFree(pl.d_tile_boff); cudaFree(pl.d_col_idx); cudaFree(pl.d_pix_col);
-  cudaFree(pl.d_col_frac); cudaFree(pl.d_wtab); cudaFree(pl.d_dtab); cudaFree(pl.d_bbar); cudaFree(pl.d_inv_err);
-  for (auto& kv : pl.schedules) { cudaFree(kv.second.d_sched); cudaFree(kv.second.d_cnt); }
-  pl.schedules.clear();
-}
-
-// Longest-first deal of the (column tile, theta block) pairs to `sms` persistent CTAs (cost = k-blocks + a constant
-// for the epilogue); a CTA runs its tiles in the order dealt.  Cached per number of theta blocks.
-int pxc_schedule(PxcPlan& pl, int n_rb, int sms, const PxcSchedule** out) {
-  auto it = pl.schedules.find(n_rb);
-  if (it == pl.schedules.end()) {
-    std::vector<int> order(pl.n_col_tiles);
-    for (int t = 0; t < pl.n_col_tiles; ++t) order[t] = t;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pl.tile_nkb[a] > pl.tile_nkb[b]; });
-    const int64_t tiles = (int64_t)n_rb * pl.n_col_tiles;
-    PxcSchedule sc;
-    sc.ctas = (int)std::min<int64_t>(tiles, sms);
-    std::vector<std::vector<int>> lists(sc.ctas);
-    std::vector<int64_t> load(sc.ctas, 0);
-    for (int t : order)
-      for (int rb = 0; rb < n_rb; ++rb) {
-        int best = 0;
-        for (int c = 1; c < sc.ctas; ++c)
-          if (load[c] < load[best]) best = c;
-        lists[best].push_back((t << 16) | rb);
-        load[best] += pl.tile_nkb[t] + 10;
-      }
-    for (auto& l : lists) sc.slots = std::max(sc.slots, (int)l.size());
-    std::vector<int> flat((size_t)sc.ctas * sc.slots, 0), cnt(sc.ctas);
-    for (int c = 0; c < sc.ctas; ++c) {
-      cnt[c] = (int)lists[c].size();
-      std::copy(lists[c].begin(), lists[c].end(), flat.begin() + (size_t)c * sc.slots);
-    }
-    if (upload(&sc.d_sched, flat) || upload(&sc.d_cnt, cnt)) return 1;
-    it = pl.schedules.emplace(n_rb, sc).first;
-  }
-  *out = &it->second;
-  return 0;
-}
-
-template <int TN, bool TRACE>
-int launch_pxc_t(const pxc::Params& p, const CUtensorMap& tmap, int ctas, size_t smem, cudaStream_t stream) {
-  CUDA_OK(cudaFuncSetAttribute(pxc::pix_contract_kernel<TN, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pxc::pix_contract_kernel<TN, TRACE><<<ctas, pxc::THREADS, smem, stream>>>(p, tmap);
-  CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-// Tensor map of the zero-padded spectra for the contraction's A loads: float32 {pitch, rows}, box {16, 128}, SWIZZLE_64B
-int make_spec_tmap(const float* spec, int64_t pitch, int64_t rows, CUtensorMap* out) {
-  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static encode_fn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    if (!fn || qres != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled not available in this driver");
-    encode = reinterpret_cast<encode_fn>(fn);
-  }
-  const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)ifc::TILE_K, (cuuint32_t)ifc::TILE_M};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(spec), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
-  return 0;
-}
-
-int launch_pxc(PxcPlan& pl, const float* spec, int n_rb, float* out, double* tsum, int sms, cudaStream_t stream,
-               long long* dbg_cycles = nullptr) {
-  if (n_rb > 65535) return fail("too many theta blocks for one folded contraction launch");
-  const PxcSchedule* sc = nullptr;
-  if (pxc_schedule(pl, n_rb, sms, &sc)) return 1;
-  pxc::Params p{};
-  p.s = spec; p.pitch = pl.pitch; p.tile_kcol0 = pl.d_tile_kcol0; p.tile_nkb = pl.d_tile_nkb; p.col_idx = pl.d_col_idx;
-  p.col_frac = pl.d_col_frac; p.wtab = pl.d_wtab; p.wlen = pl.wlen; p.sched = sc->d_sched; p.sched_cnt = sc->d_cnt;
-  p.sched_slots = sc->slots; p.out = out; p.out_pitch = pl.out_pitch; p.ring = pl.ring; p.dbg_cycles = dbg_cycles;
-  p.bbar = (tsum && pl.n_fold_tiles <= 64) ? pl.d_bbar : nullptr; p.tile_boff = pl.d_tile_boff; p.tsum = tsum;
-  p.n_col_tiles = pl.n_col_tiles;
-  // A loader: 0 = cp.async by two loader warps (default), 1 = one TMA box per k-block (opt-in: 2 % faster on the Balmer
-  // demo, but one build of it was seen to deliver stale A rows in cold first launches; not root-caused)
-  static const int loader = getenv("BAYSAR_PXC_LOADER") ? atoi(getenv("BAYSAR_PXC_LOADER")) : 0;
-  p.use_tma = loader;
-  static const int sleep_epi = getenv("BAYSAR_PXC_SLEEP_EPI") ? atoi(getenv("BAYSAR_PXC_SLEEP_EPI")) : 0;
-  static const int sleep_build = getenv("BAYSAR_PXC_SLEEP_BUILD") ? atoi(getenv("BAYSAR_PXC_SLEEP_BUILD")) : 0;
-  p.sleep_epi = (unsigned)sleep_epi; p.sleep_build = (unsigned)sleep_build;
-  CUtensorMap tmap;
-  if (make_spec_tmap(spec, pl.pitch, (int64_t)n_rb * ifc::TILE_M, &tmap)) return 1;
-  if (pl.tn == 64) {
-    const size_t smem = pxc::smem_bytes<64>(pl.ring, pl.wlen);
-    return dbg_cycles ? launch_pxc_t<64, true>(p, tmap, sc->ctas, smem, stream)
-                      : launch_pxc_t<64, false>(p, tmap, sc->ctas, smem, stream);
-  }
-  const size_t smem = pxc::smem_bytes<128>(pl.ring, pl.wlen);
-  return dbg_cycles ? launch_pxc_t<128, true>(p, tmap, sc->ctas, smem, stream)
-                    : launch_pxc_t<128, false>(p, tmap, sc->ctas, smem, stream);
-}
 
 int ensure_workspace(baysar_model* m, int64_t n) {
   if (n <= m->cap) return 0;
@@ -507,11 +93,10 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
   // Register budget by batch size.  The kernel is latency-bound at 16 warps per SM (4 CTAs, 128 registers, no spills):
   // the best choice for many waves.  A batch of a few thousand thetas, though, is one or two waves, and then fitting
   // every CTA into ONE wave beats the spills of a tighter budget (4096 thetas: 1024 CTAs = 1.7 waves of 592 at 0.080 ms,
-  // one wave of 7 CTAs per SM at 72 registers at 0.068 ms).  BAYSAR_LOS_MINB overrides.
-  static const int minb_env = getenv("BAYSAR_LOS_MINB") ? atoi(getenv("BAYSAR_LOS_MINB")) : 0;
+  // one wave of 7 CTAs per SM at 72 registers at 0.068 ms).  options.los_min_blocks overrides.
   int minb = 4;
-  if (minb_env > 0) {
-    minb = minb_env;
+  if (m->opt.los_min_blocks > 0) {
+    minb = m->opt.los_min_blocks;
   } else {
     const int64_t ctas = (n + 3) / 4;
     if (ctas > (int64_t)4 * m->sm_count)
@@ -519,34 +104,24 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
         if (ctas <= (int64_t)b * m->sm_count) { minb = b; break; }
   }
   // Long lines of sight: the per-point cache (128 B per point and theta) starves the warp-per-theta form of occupancy
-  // (L = 1000: one warp per SM).  From BAYSAR_LOS_TEAM_L points on (default: as soon as four thetas no longer fit one
-  // CTA's 200 KB) one CTA of four warps works on ONE theta, the points spread over its 128 threads.
-  static const int team_l = getenv("BAYSAR_LOS_TEAM_L") ? atoi(getenv("BAYSAR_LOS_TEAM_L")) : 0;
+  // (L = 1000: one warp per SM).  From options.los_team_points points on (default: as soon as four thetas no longer fit
+  // one CTA's 200 KB) one CTA of four warps works on ONE theta, the points spread over its 128 threads.
+  const int team_l = m->opt.los_team_points;
   const bool team = (team_l > 0 && L >= team_l) || 4 * per_warp > 200 * 1024;
   if (team && per_warp + 128 <= 200 * 1024) {
     const size_t smem = per_warp + 128;
-    if (2 * smem > 200 * 1024) {  // one CTA per SM anyway: eight warps per theta
-      auto kern = los_stage_kernel<8, 1, 1, 8>;
-      CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<(unsigned)n, 256, smem, stream>>>(m->dev, a);
-    } else {
-      auto kern = los_stage_kernel<4, 1, 1, 4>;
-      CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<(unsigned)n, 128, smem, stream>>>(m->dev, a);
-    }
+    if (2 * smem > 200 * 1024)  // one CTA per SM anyway: eight warps per theta
+      los_stage_kernel<8, 1, 1, 8><<<(unsigned)n, 256, smem, stream>>>(m->dev, a);
+    else
+      los_stage_kernel<4, 1, 1, 4><<<(unsigned)n, 128, smem, stream>>>(m->dev, a);
   } else if (4 * per_warp <= 200 * 1024) {
-    size_t smem = 4 * per_warp;
-    static const int unr = getenv("BAYSAR_LOS_UNROLL") ? atoi(getenv("BAYSAR_LOS_UNROLL")) : 1;
+    const size_t smem = 4 * per_warp;
     auto kern = minb >= 6 ? los_stage_kernel<4, 6> : (minb == 5 ? los_stage_kernel<4, 5> : los_stage_kernel<4, 4>);
     if (minb == 7) kern = los_stage_kernel<4, 7>;
     if (minb >= 8) kern = los_stage_kernel<4, 8>;
-    if (unr == 2) kern = minb >= 5 ? los_stage_kernel<4, 5, 2> : (minb == 3 ? los_stage_kernel<4, 3, 2> : los_stage_kernel<4, 4, 2>);
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)((n + 3) / 4), 128, smem, stream>>>(m->dev, a);
   } else {
-    size_t smem = per_warp;
-    CUDA_OK(cudaFuncSetAttribute(los_stage_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    los_stage_kernel<1><<<(unsigned)n, 32, smem, stream>>>(m->dev, a);
+    los_stage_kernel<1><<<(unsigned)n, 32, per_warp, stream>>>(m->dev, a);
   }
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -579,14 +154,13 @@ int ensure_ifc_workspace(baysar_model* m, int64_t n) {
 template <int MODE>
 int launch_chord_kernel(baysar_model* m, const ChordArgs& a, dim3 grid, size_t smem, cudaStream_t stream, bool single_tap_only = false) {
   constexpr int NT = 256;
-  static const int cap = getenv("BAYSAR_CHORD_MINB") ? atoi(getenv("BAYSAR_CHORD_MINB")) : 5;
+  const int cap = m->opt.chord_min_blocks > 0 ? m->opt.chord_min_blocks : 5;
   const int by_smem = (int)((size_t)232448 / (smem + 1024));
   const int minb = by_smem < cap ? by_smem : cap;
   auto kern = minb >= 5 ? chord_stage_kernel<NT, MODE, 5> : (minb == 4 ? chord_stage_kernel<NT, MODE, 4> : chord_stage_kernel<NT, MODE, 3>);
   if (single_tap_only)  // every Balmer line of the chord is a guaranteed single Doppler tap: leaner build
     kern = minb >= 5 ? chord_stage_kernel<NT, MODE, 5, false>
                      : (minb == 4 ? chord_stage_kernel<NT, MODE, 4, false> : chord_stage_kernel<NT, MODE, 3, false>);
-  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, NT, smem, stream>>>(m->dev, a);
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -597,12 +171,32 @@ enum { ST_BEGIN = -1, ST_LOS = 0, ST_CHORD = 1, ST_CONTRACT = 2, ST_PIXEL = 3, S
 
 int mark(baysar_model* m, int slot, cudaStream_t stream) {
   if (!m->profiling) return 0;
-  cudaEvent_t ev;
-  CUDA_OK(cudaEventCreate(&ev));
-  CUDA_OK(cudaEventRecord(ev, stream));
-  m->prof_events.push_back(ev);
-  m->prof_slots.push_back(slot);
+  if (m->prof_used == m->prof_events.size()) {  // pool growth: first profiled calls only
+    cudaEvent_t ev;
+    CUDA_OK(cudaEventCreate(&ev));
+    m->prof_events.push_back(ev);
+  }
+  CUDA_OK(cudaEventRecord(m->prof_events[m->prof_used], stream));
+  if (m->prof_slots.size() <= m->prof_used) m->prof_slots.resize(m->prof_used + 1);
+  m->prof_slots[m->prof_used++] = slot;
   return 0;
+}
+
+// Opt-in shared-memory limits of every kernel variant the launchers can pick: once per model creation
+int set_kernel_attributes() {
+  if (allow_max_smem(los_stage_kernel<8, 1, 1, 8>) || allow_max_smem(los_stage_kernel<4, 1, 1, 4>) ||
+      allow_max_smem(los_stage_kernel<4, 4>) || allow_max_smem(los_stage_kernel<4, 5>) ||
+      allow_max_smem(los_stage_kernel<4, 6>) || allow_max_smem(los_stage_kernel<4, 7>) ||
+      allow_max_smem(los_stage_kernel<4, 8>) || allow_max_smem(los_stage_kernel<1>))
+    return 1;
+  if (allow_max_smem(chord_stage_kernel<256, 0, 3>) || allow_max_smem(chord_stage_kernel<256, 0, 4>) ||
+      allow_max_smem(chord_stage_kernel<256, 0, 5>) || allow_max_smem(chord_stage_kernel<256, 1, 3>) ||
+      allow_max_smem(chord_stage_kernel<256, 1, 4>) || allow_max_smem(chord_stage_kernel<256, 1, 5>) ||
+      allow_max_smem(chord_stage_kernel<256, 0, 3, false>) || allow_max_smem(chord_stage_kernel<256, 0, 4, false>) ||
+      allow_max_smem(chord_stage_kernel<256, 0, 5, false>) || allow_max_smem(chord_stage_kernel<256, 1, 3, false>) ||
+      allow_max_smem(chord_stage_kernel<256, 1, 4, false>) || allow_max_smem(chord_stage_kernel<256, 1, 5, false>))
+    return 1;
+  return allow_max_smem(pixel_fold_kernel<128>) || contraction_kernel_attributes();
 }
 
 int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_begin, int n_chords,
@@ -661,8 +255,8 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
         pf.theta = theta + r0 * n_params; pf.n = rows; pf.chord = c; pf.cp = m->conv; pf.cp_pitch = fx.out_pitch;
         pf.pix_col = fx.d_pix_col; pf.col_left0 = fx.col_left0; pf.x_l = fx.x_l; pf.col_right0 = fx.col_right0; pf.x_r = fx.x_r;
         pf.spec = m->spec; pf.spec_pitch = fx.pitch; pf.spec_pad = fx.pad_left; pf.dtab = fx.d_dtab; pf.n_dl = fx.n_dl;
-        pf.n_dr = fx.n_dr; pf.wsum = fx.wsum; pf.inv_err = fx.d_inv_err; pf.tsum = fx.n_fold_tiles <= 64 ? m->trapz_part : nullptr;
-        pf.n_col_tiles = fx.n_col_tiles; pf.n_fold_tiles = fx.n_fold_tiles <= 64 ? fx.n_fold_tiles : 0; pf.tile_n = fx.tn; pf.aux = m->aux; pf.components = comps + r0 * ncols;
+        pf.n_dr = fx.n_dr; pf.wsum = fx.wsum; pf.inv_err = fx.d_inv_err; pf.tsum = m->trapz_part;
+        pf.n_col_tiles = fx.n_col_tiles; pf.n_fold_tiles = fx.n_fold_tiles; pf.tile_n = fx.tn; pf.aux = m->aux; pf.components = comps + r0 * ncols;
         pf.spectra = spectra ? spectra + r0 * P : nullptr; pf.status = status + r0;
         {
           // a single-chord model gets its logP from the same kernel (no finalize launch)
@@ -671,7 +265,6 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
           if (fuse && finalized) *finalized = true;
           const size_t row_bytes = sizeof(float) * (size_t)fx.out_pitch;
           if (row_bytes > 160 * 1024) return fail("contraction row too long for the pixel stage's shared-memory copy");
-          CUDA_OK(cudaFuncSetAttribute(pixel_fold_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes));
           pixel_fold_kernel<128><<<(unsigned)rows, 128, row_bytes, stream>>>(m->dev, pf);
         }
         CUDA_OK(cudaGetLastError());
@@ -692,7 +285,6 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
         p.cmask = m->ifc_cmask_dev[c]; p.cbase = m->ifc_cbase_dev[c]; p.out_c = m->conv_c; p.out_c_pitch = pl.c_pitch;
       }
       const size_t smem = ifc::smem_bytes(pl.m_hi - pl.m_lo + 1);
-      CUDA_OK(cudaFuncSetAttribute(ifc::if_contract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const int64_t tiles = (int64_t)p.n_row_blocks * pl.n_tiles;
       const unsigned ctas = (unsigned)(tiles < m->sm_count ? tiles : m->sm_count);  // persistent: one CTA per SM
       ifc::if_contract_kernel<false><<<ctas, ifc::THREADS, smem, stream>>>(p);
@@ -714,6 +306,76 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
   return 0;
 }
 
+// Structural validation of a descriptor blob before anything indexes it (a truncated or stale blob must fail here, not
+// as an out-of-bounds read on the host or the device).
+int validate_blob(const void* desc_blob, size_t nbytes) {
+  if (!desc_blob || nbytes < (size_t)8 * (3 + 2 * SEC_COUNT)) return fail("bad descriptor blob");
+  const int64_t* hdr = static_cast<const int64_t*>(desc_blob);
+  if (hdr[0] != BAYSAR_BLOB_MAGIC) return fail("descriptor magic mismatch");
+  if (hdr[1] != BAYSAR_BLOB_VERSION) return fail("descriptor version mismatch (rebuild the model with this library)");
+  if (hdr[2] != SEC_COUNT) return fail("descriptor section count mismatch");
+  auto elem = [](int sec) -> size_t {
+    switch (sec) {
+      case SEC_SP_I: case SEC_ELEM_DENS_IDX: case SEC_UL_I: case SEC_PR_I: case SEC_CSO_OFF: case SEC_CSO_UL:
+      case SEC_CH_I: case SEC_CL_I: case SEC_PIX_IDX: case SEC_MESH_LO: case SEC_PR_AUX: return 4;
+      default: return 8;
+    }
+  };
+  for (int sc = 0; sc < SEC_COUNT; ++sc) {
+    const int64_t off = hdr[3 + 2 * sc], cnt = hdr[3 + 2 * sc + 1];
+    if (off < 0 || cnt < 0 || (off & 15) != 0 || (size_t)off > nbytes || (size_t)cnt > (nbytes - (size_t)off) / elem(sc))
+      return fail("descriptor section " + std::to_string(sc) + " out of range or misaligned");
+  }
+  SectionTable t{hdr, static_cast<const unsigned char*>(desc_blob)};
+  if (t.count(SEC_I) != I_COUNT) return fail("descriptor I_COUNT mismatch");
+  const int64_t* I = static_cast<const int64_t*>(t.ptr(SEC_I));
+  const int64_t np = I[I_N_PARAMS], L = I[I_L], nc = I[I_N_CHORDS], nsp = I[I_N_SPECIES], nul = I[I_N_ULINES],
+                npr = I[I_N_PRIORS], ncl = I[I_N_CLINES];
+  if (np < 1 || L < 2 || nc < 0 || nsp < 0 || nul < 0 || npr < 0 || ncl < 0) return fail("descriptor scalar out of range");
+  auto need = [&](int sec, int64_t cnt, const char* what) {
+    return t.count(sec) < cnt ? fail(std::string("descriptor section too short: ") + what) : 0;
+  };
+  if (need(SEC_LOS_X, L, "LOS_X") || need(SEC_LOS_W, L, "LOS_W") || need(SEC_PROF_D, PROF_D_COUNT, "PROF_D") ||
+      need(SEC_SP_I, nsp * SP_I_COUNT, "SP_I") || need(SEC_SP_D, nsp * SP_D_COUNT, "SP_D") ||
+      need(SEC_ELEM_DENS_IDX, I[I_N_ELEM], "ELEM_DENS_IDX") || need(SEC_UL_I, nul * UL_I_COUNT, "UL_I") ||
+      need(SEC_UL_D, nul * UL_D_COUNT, "UL_D") || need(SEC_PR_I, npr * PR_I_COUNT, "PR_I") ||
+      need(SEC_PR_D, npr * PR_D_COUNT, "PR_D") || need(SEC_CSO_OFF, I[I_N_ELEM] + 1, "CSO_OFF") ||
+      need(SEC_CH_I, nc * CH_I_COUNT, "CH_I") || need(SEC_CH_D, nc * CH_D_COUNT, "CH_D") ||
+      need(SEC_CL_I, ncl * CL_I_COUNT, "CL_I") || need(SEC_CL_D, ncl * CL_D_COUNT, "CL_D") ||
+      need(SEC_A11_NE, I[I_A11_NNE], "A11_NE") || need(SEC_A11_TE, I[I_A11_NTE], "A11_TE") ||
+      need(SEC_A11_SCD, I[I_A11_NNE] * I[I_A11_NTE], "A11_SCD") || need(SEC_H_NE, I[I_H_NNE], "H_NE") ||
+      need(SEC_H_TE, I[I_H_NTE], "H_TE") || need(SEC_H_TAB, I[I_N_HTAB] * I[I_H_NNE] * I[I_H_NTE], "H_TAB") ||
+      need(SEC_TAU_GRID, I[I_N_TAU], "TAU_GRID") || need(SEC_SPL_TX, I[I_SPL_NX], "SPL_TX") ||
+      need(SEC_SPL_TY, I[I_SPL_NY], "SPL_TY") ||
+      need(SEC_SPL_C, I[I_N_TEC] * (I[I_N_TAU] - 1) * (I[I_SPL_NX] - 4) * (I[I_SPL_NY] - 4) * 2, "SPL_C") ||
+      need(SEC_MESH_X, I[I_MESH_NE_N] + I[I_MESH_TE_N], "MESH_X") ||
+      need(SEC_MESH_LO, I[I_PROFILE_KIND] == 2 ? 2 * L : 0, "MESH_LO") || need(SEC_PIX_FRAC, t.count(SEC_PIX_IDX), "PIX_FRAC") ||
+      need(SEC_ERR, t.count(SEC_Y), "ERR") || need(SEC_PIX_IDX, t.count(SEC_Y), "PIX_IDX"))
+    return 1;
+  const int* ch_i = static_cast<const int*>(t.ptr(SEC_CH_I));
+  const int* cl_i = static_cast<const int*>(t.ptr(SEC_CL_I));
+  const int64_t n_comps = t.count(SEC_COMP_D) / 2;
+  auto theta_ok = [&](int idx) { return idx >= -1 && idx < np; };
+  for (int64_t c = 0; c < nc; ++c) {
+    const int* ch = ch_i + c * CH_I_COUNT;
+    if (ch[CH_P] < 1 || ch[CH_F] < 8 || ch[CH_KI] < 1 || ch[CH_N_LINES] < 0 || ch[CH_LINE_OFF] < 0 ||
+        (int64_t)ch[CH_LINE_OFF] + ch[CH_N_LINES] > ncl || ch[CH_PIX_OFF] < 0 ||
+        (int64_t)ch[CH_PIX_OFF] + ch[CH_P] > t.count(SEC_Y) || ch[CH_IF_OFF] < 0 ||
+        (int64_t)ch[CH_IF_OFF] + ch[CH_KI] > t.count(SEC_IF) || ch[CH_IF_KLO] < 0 || ch[CH_IF_KLO] >= ch[CH_IF_KHI] ||
+        ch[CH_IF_KHI] > ch[CH_KI] || ch[CH_HALO] < 0 || ch[CH_HALO] % 4 != 0 || ch[CH_TAPS_MAX] < 0 ||
+        ch[CH_BG_IDX] < 0 || !theta_ok(ch[CH_BG_IDX]) || !theta_ok(ch[CH_CAL_IDX]) || !theta_ok(ch[CH_CALWAVE_IDX] + (ch[CH_CALWAVE_IDX] >= 0)) ||
+        !theta_ok(ch[CH_CALINT_IDX]))
+      return fail("descriptor chord record " + std::to_string(c) + " inconsistent with the section sizes");
+  }
+  for (int64_t k = 0; k < ncl; ++k) {
+    const int* cl = cl_i + k * CL_I_COUNT;
+    if (cl[CL_KIND] < 0 || cl[CL_KIND] > 2 || cl[CL_ULINE] < 0 || cl[CL_ULINE] >= nul || cl[CL_NCOMP] < 0 ||
+        cl[CL_COMP_OFF] < 0 || (int64_t)cl[CL_COMP_OFF] + cl[CL_NCOMP] > n_comps || cl[CL_KD] < 0 || cl[CL_SPECIES] >= nsp)
+      return fail("descriptor line record " + std::to_string(k) + " inconsistent with the section sizes");
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -722,18 +384,18 @@ const char* baysar_last_error(void) { return g_last_error.c_str(); }
 const char* baysar_version(void) { return "baysar_b200 0.1 (sm_100a)"; }
 
 int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar_model_t** out) {
-  if (!desc_blob || !out || nbytes < 3 * sizeof(int64_t)) return fail("bad descriptor blob");
-  const int64_t* hdr = static_cast<const int64_t*>(desc_blob);
-  if (hdr[0] != BAYSAR_BLOB_MAGIC) return fail("descriptor magic mismatch");
-  if (hdr[1] != BAYSAR_BLOB_VERSION) return fail("descriptor version mismatch (rebuild the model with this library)");
-  if (hdr[2] != SEC_COUNT) return fail("descriptor section count mismatch");
-  for (int s = 0; s < SEC_COUNT; ++s) {
-    if (hdr[3 + 2 * s] < 0 || (size_t)hdr[3 + 2 * s] > nbytes) return fail("descriptor section offset out of range");
-  }
+  return baysar_model_create_ex(desc_blob, nbytes, device, nullptr, out);
+}
+
+int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, const baysar_options_t* options,
+                           baysar_model_t** out) {
+  if (!out) return fail("null output pointer");
+  if (validate_blob(desc_blob, nbytes)) return 1;
   CUDA_OK(cudaSetDevice(device));
   baysar_model* m = new (std::nothrow) baysar_model();
   if (!m) return fail("out of host memory");
   m->device = device;
+  if (options) m->opt = *options;
   m->blob_bytes = nbytes;
   m->blob_host.assign(static_cast<const unsigned char*>(desc_blob), static_cast<const unsigned char*>(desc_blob) + nbytes);
   cudaError_t e = cudaMalloc(&m->blob_dev, nbytes);
@@ -743,7 +405,12 @@ int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar
 
   SectionTable host{reinterpret_cast<const int64_t*>(m->blob_host.data()), m->blob_host.data()};
   SectionTable dev{reinterpret_cast<const int64_t*>(m->blob_host.data()), m->blob_dev};
-  if (host.count(SEC_I) != I_COUNT) { baysar_model_destroy(m); return fail("descriptor I_COUNT mismatch"); }
+  if (set_kernel_attributes()) { baysar_model_destroy(m); return 1; }
+  {
+    cudaError_t es = cudaStreamCreateWithFlags(&m->host_stream, cudaStreamNonBlocking);
+    if (es == cudaSuccess) es = cudaEventCreateWithFlags(&m->last_done, cudaEventDisableTiming);
+    if (es != cudaSuccess) { baysar_model_destroy(m); return fail(std::string("cudaStreamCreate: ") + cudaGetErrorString(es)); }
+  }
   m->I = static_cast<const int64_t*>(host.ptr(SEC_I));
   m->ch_i = static_cast<const int*>(host.ptr(SEC_CH_I));
   m->cl_i = static_cast<const int*>(host.ptr(SEC_CL_I));
@@ -810,15 +477,11 @@ int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar
   cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (m->sm_count <= 0) m->sm_count = 148;
   // tensor-core contraction for chords with a long, theta-independent instrument function
-  const char* env = getenv("BAYSAR_IFC");
-  const bool ifc_enabled = !(env && env[0] == '0');
-  const char* env_taps = getenv("BAYSAR_IFC_MIN_TAPS");
-  const int min_taps = env_taps ? atoi(env_taps) : 160;
-  const char* env_budget = getenv("BAYSAR_IFC_BUDGET_MB");
-  if (env_budget) m->ifc_budget_bytes = (int64_t)atoll(env_budget) << 20;
-  const char* env_pxc = getenv("BAYSAR_PXC");  // 0: keep the every-column contraction; 64 / 128: column tile width
-  const bool pxc_enabled = !(env_pxc && env_pxc[0] == '0');
-  const int pxc_tn = (env_pxc && atoi(env_pxc) == 64) ? 64 : 128;
+  const bool ifc_enabled = m->opt.tensor_cores >= 0;
+  const int min_taps = m->opt.tensor_cores > 0 ? 1 : (m->opt.ifc_min_taps > 0 ? m->opt.ifc_min_taps : 160);
+  if (m->opt.ifc_budget_mb > 0) m->ifc_budget_bytes = (int64_t)m->opt.ifc_budget_mb << 20;
+  const bool pxc_enabled = m->opt.folded_tile >= 0;  // -1: keep the every-column contraction
+  const int pxc_tn = m->opt.folded_tile == 64 ? 64 : 128;
   m->pxc.resize(n_chords);
   m->ifc.resize(n_chords);
   m->ifc_taps_dev.assign(n_chords, nullptr);
@@ -894,6 +557,8 @@ void baysar_model_destroy(baysar_model_t* m) {
   cudaSetDevice(m->device);
   cudaFree(m->blob_dev); cudaFree(m->lines); cudaFree(m->comps); cudaFree(m->hdr); cudaFree(m->status);
   cudaFree(m->theta_stage); cudaFree(m->logp_stage); cudaFreeHost(m->out_pinned);
+  if (m->host_stream) cudaStreamDestroy(m->host_stream);
+  if (m->last_done) cudaEventDestroy(m->last_done);
   cudaFree(m->spec); cudaFree(m->conv); cudaFree(m->conv_c); cudaFree(m->trapz_part); cudaFree(m->aux);
   for (float* t : m->ifc_taps_dev) cudaFree(t);
   for (uint32_t* t : m->ifc_cmask_dev) cudaFree(t);
@@ -935,6 +600,7 @@ int baysar_eval_logp(baysar_model_t* m, const double* theta, int64_t n, double* 
   if (n <= 0) return 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUDA_OK(cudaSetDevice(m->device));
+  CUDA_OK(cudaStreamWaitEvent(stream, m->last_done, 0));
   if (ensure_workspace(m, n)) return 1;
   uint32_t* st = status ? status : m->status;
   double* comps = components ? components : m->comps;
@@ -954,6 +620,7 @@ int baysar_eval_logp(baysar_model_t* m, const double* theta, int64_t n, double* 
     m->last_launches += 1;
   }
   if (mark(m, ST_FINAL, stream)) return 1;
+  CUDA_OK(cudaEventRecord(m->last_done, stream));
   return 0;
 }
 
@@ -964,10 +631,13 @@ int baysar_eval_spectra(baysar_model_t* m, const double* theta, int64_t n, int c
   if (n <= 0) return 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUDA_OK(cudaSetDevice(m->device));
+  CUDA_OK(cudaStreamWaitEvent(stream, m->last_done, 0));
   if (ensure_workspace(m, n)) return 1;
   uint32_t* st = status ? status : m->status;
   if (launch_los(m, theta, n, m->lines, m->comps, nullptr, st, stream)) return 1;
-  return launch_chords(m, theta, n, chord, 1, m->lines, m->comps, spectra, fine_pre, fine_post, st, stream);
+  if (launch_chords(m, theta, n, chord, 1, m->lines, m->comps, spectra, fine_pre, fine_post, st, stream)) return 1;
+  CUDA_OK(cudaEventRecord(m->last_done, stream));
+  return 0;
 }
 
 int baysar_eval_lines(baysar_model_t* m, const double* theta, int64_t n, double* lines, double* profiles,
@@ -976,9 +646,12 @@ int baysar_eval_lines(baysar_model_t* m, const double* theta, int64_t n, double*
   if (n <= 0) return 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUDA_OK(cudaSetDevice(m->device));
+  CUDA_OK(cudaStreamWaitEvent(stream, m->last_done, 0));
   if (ensure_workspace(m, n)) return 1;
   uint32_t* st = status ? status : m->status;
-  return launch_los(m, theta, n, lines, m->comps, profiles, st, stream);
+  if (launch_los(m, theta, n, lines, m->comps, profiles, st, stream)) return 1;
+  CUDA_OK(cudaEventRecord(m->last_done, stream));
+  return 0;
 }
 
 int baysar_eval_logp_host(baysar_model_t* m, const double* theta_host, int64_t n, double* logp_host,
@@ -999,11 +672,11 @@ int baysar_eval_logp_host(baysar_model_t* m, const double* theta_host, int64_t n
     m->stage_cap = cap;
   }
   uint32_t* status_dev = reinterpret_cast<uint32_t*>(m->logp_stage + n);
-  CUDA_OK(cudaMemcpyAsync(m->theta_stage, theta_host, sizeof(double) * n * np, cudaMemcpyHostToDevice, 0));
-  if (baysar_eval_logp(m, m->theta_stage, n, m->logp_stage, status_dev, nullptr, nullptr)) return 1;
+  CUDA_OK(cudaMemcpyAsync(m->theta_stage, theta_host, sizeof(double) * n * np, cudaMemcpyHostToDevice, m->host_stream));
+  if (baysar_eval_logp(m, m->theta_stage, n, m->logp_stage, status_dev, nullptr, m->host_stream)) return 1;
   const size_t out_bytes = (sizeof(double) + (status_host ? sizeof(uint32_t) : 0)) * (size_t)n;
-  CUDA_OK(cudaMemcpyAsync(m->out_pinned, m->logp_stage, out_bytes, cudaMemcpyDeviceToHost, 0));
-  CUDA_OK(cudaStreamSynchronize(0));
+  CUDA_OK(cudaMemcpyAsync(m->out_pinned, m->logp_stage, out_bytes, cudaMemcpyDeviceToHost, m->host_stream));
+  CUDA_OK(cudaStreamSynchronize(m->host_stream));
   memcpy(logp_host, m->out_pinned, sizeof(double) * n);
   if (status_host) memcpy(status_host, static_cast<unsigned char*>(m->out_pinned) + sizeof(double) * n, sizeof(uint32_t) * n);
   return 0;
@@ -1011,9 +684,7 @@ int baysar_eval_logp_host(baysar_model_t* m, const double* theta_host, int64_t n
 
 int baysar_model_set_profiling(baysar_model_t* m, int on) {
   if (!m) return fail("null model");
-  for (cudaEvent_t ev : m->prof_events) cudaEventDestroy(ev);
-  m->prof_events.clear();
-  m->prof_slots.clear();
+  m->prof_used = 0;
   m->profiling = on != 0;
   return 0;
 }
@@ -1023,248 +694,14 @@ int baysar_model_get_profile(baysar_model_t* m, double* stage_ms, int64_t* calls
   CUDA_OK(cudaSetDevice(m->device));
   for (int k = 0; k < ST_COUNT; ++k) stage_ms[k] = 0.0;
   *calls = 0;
-  for (size_t e = 0; e < m->prof_events.size(); ++e) {
+  for (size_t e = 0; e < m->prof_used; ++e) {
     if (m->prof_slots[e] == ST_BEGIN) { *calls += 1; continue; }
     CUDA_OK(cudaEventSynchronize(m->prof_events[e]));
     float ms = 0.f;
     CUDA_OK(cudaEventElapsedTime(&ms, m->prof_events[e - 1], m->prof_events[e]));
     stage_ms[m->prof_slots[e]] += ms;
   }
-  for (cudaEvent_t ev : m->prof_events) cudaEventDestroy(ev);
-  m->prof_events.clear();
-  m->prof_slots.clear();
-  return 0;
-}
-
-int baysar_debug_if_contract(const float* spectra_dev, int64_t n_rows, int F, const double* taps_host, int KI,
-                             const float* row_min_dev, float* out_dev, double* trapz_dev, int64_t* out_pitch,
-                             int* n_tiles, float* elapsed_ms) {
-  // Unit-test hook for the tcgen05 contraction: out[r][j] = max(sum_k w[k] S[r][j + (KI-1)/2 - k], row_min[r]).
-  if (!spectra_dev || !taps_host || !out_dev) return fail("null argument");
-  if (n_rows % ifc::TILE_M != 0) return fail("n_rows must be a multiple of 128");
-  double wmax = 0.0;
-  for (int k = 0; k < KI; ++k) wmax = fabs(taps_host[k]) > wmax ? fabs(taps_host[k]) : wmax;
-  int k_lo = KI, k_hi = 0;
-  for (int k = 0; k < KI; ++k)
-    if (fabs(taps_host[k]) > 1e-17 * wmax) { k_lo = k < k_lo ? k : k_lo; k_hi = k + 1; }
-  IfcPlan pl = make_ifc_plan(taps_host, KI, k_lo, k_hi, F);
-  if (out_pitch) *out_pitch = pl.out_pitch;
-  if (n_tiles) *n_tiles = pl.n_tiles;
-  if (pl.m_hi - pl.m_lo + 1 > ifc::MAX_KB) return fail("instrument function too wide for the tensor-core contraction");
-  float *spec = nullptr, *taps = nullptr;
-  CUDA_OK(cudaMalloc(&spec, sizeof(float) * n_rows * pl.pitch));
-  CUDA_OK(cudaMalloc(&taps, sizeof(float) * pl.taps_rev.size()));
-  CUDA_OK(cudaMemset(spec, 0, sizeof(float) * n_rows * pl.pitch));
-  CUDA_OK(cudaMemcpy(taps, pl.taps_rev.data(), sizeof(float) * pl.taps_rev.size(), cudaMemcpyHostToDevice));
-  ifc::pad_rows_kernel<<<dim3(8, (unsigned)n_rows), 256>>>(spectra_dev, n_rows, F, spec, pl.pitch, pl.pad_left);
-  CUDA_OK(cudaGetLastError());
-  ifc::Params p{};
-  p.s = spec; p.pitch = pl.pitch; p.pad_left = pl.pad_left; p.F = F; p.n_row_blocks = (int)(n_rows / ifc::TILE_M);
-  p.m_lo = pl.m_lo; p.m_hi = pl.m_hi; p.taps_rev = taps; p.taps_len = pl.taps_len; p.row_min = row_min_dev; p.aux = nullptr; p.aux_rows = 0;
-  p.out = out_dev; p.out_pitch = pl.out_pitch; p.trapz_part = trapz_dev; p.n_tiles = pl.n_tiles;
-  p.ring = ifc::ring_stages(pl.m_hi - pl.m_lo + 1);
-  p.debug = getenv("BAYSAR_IFC_DEBUG") ? atoi(getenv("BAYSAR_IFC_DEBUG")) : 0;
-  long long* dbg = nullptr;
-  if (getenv("BAYSAR_IFC_TRACE")) {
-    CUDA_OK(cudaMalloc(&dbg, sizeof(long long) * 8 * 256));
-    CUDA_OK(cudaMemset(dbg, 0, sizeof(long long) * 8 * 256));
-    p.dbg_cycles = dbg;
-  }
-  const size_t smem = ifc::smem_bytes(pl.m_hi - pl.m_lo + 1);
-  const bool dbg_kernel = p.debug != 0 || dbg != nullptr;
-  CUDA_OK(cudaFuncSetAttribute(ifc::if_contract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_OK(cudaFuncSetAttribute(ifc::if_contract_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaEvent_t e0, e1;
-  CUDA_OK(cudaEventCreate(&e0));
-  CUDA_OK(cudaEventCreate(&e1));
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  const int64_t tiles = (int64_t)p.n_row_blocks * pl.n_tiles;
-  const unsigned ctas = (unsigned)(tiles < sms ? tiles : sms);
-  for (int rep = 0; rep < 2; ++rep) {
-    CUDA_OK(cudaEventRecord(e0, 0));
-    if (dbg_kernel) ifc::if_contract_kernel<true><<<ctas, ifc::THREADS, smem>>>(p);
-    else ifc::if_contract_kernel<false><<<ctas, ifc::THREADS, smem>>>(p);
-    CUDA_OK(cudaEventRecord(e1, 0));
-    CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaEventSynchronize(e1));
-  }
-  float ms = 0.f;
-  CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
-  if (elapsed_ms) *elapsed_ms = ms;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  if (dbg) {
-    std::vector<long long> h(8 * 256);
-    cudaMemcpy(h.data(), dbg, sizeof(long long) * 8 * 256, cudaMemcpyDeviceToHost);
-    const char* names[8] = {"conv.wait_landed", "conv.wait_empty", "conv.wait_st", "conv.total", "load.wait_consumed",
-                            "epi.wait_acc_full", "mma.wait_full", "mma.wait_acc_free"};
-    for (int k = 0; k < 8; ++k) {
-      double mean = 0;
-      for (unsigned b = 0; b < ctas; ++b) mean += (double)h[b * 8 + k];
-      fprintf(stderr, "[ifc trace] %-20s mean %.0f cycles per CTA (CTA0 %lld)\n", names[k], mean / ctas, h[k]);
-    }
-    cudaFree(dbg);
-  }
-  cudaFree(spec); cudaFree(taps);
-  return 0;
-}
-
-int baysar_debug_pix_contract(const float* spectra_dev, int64_t n_rows, int F, const double* taps_host, int KI,
-                              const int* pix_idx_host, const double* pix_frac_host, int P, int tile_n, float* out_dev,
-                              int64_t out_capacity, double* tsum_dev, int64_t tsum_capacity, int64_t* info,
-                              int* pix_col_host, float* elapsed_ms) {
-  // Unit-test hook for the folded contraction: out[r][c] for the plan's columns (see include/baysar_b200.h).
-  if (!spectra_dev || !taps_host || !pix_idx_host || !pix_frac_host || !info) return fail("null argument");
-  if (n_rows % ifc::TILE_M != 0) return fail("n_rows must be a multiple of 128");
-  double wmax = 0.0;
-  for (int k = 0; k < KI; ++k) wmax = fabs(taps_host[k]) > wmax ? fabs(taps_host[k]) : wmax;
-  int k_lo = KI, k_hi = 0;
-  for (int k = 0; k < KI; ++k)
-    if (fabs(taps_host[k]) > 1e-17 * wmax) { k_lo = k < k_lo ? k : k_lo; k_hi = k + 1; }
-  PxcPlan pl = make_pxc_plan(taps_host, KI, k_lo, k_hi, F, P, pix_idx_host, pix_frac_host, tile_n == 64 ? 64 : 128);
-  if (!pl.on) return fail("no folded-contraction plan for this instrument function / grid");
-  int64_t kb_total = 0;
-  for (int t = 0; t < pl.n_col_tiles; ++t) kb_total += pl.tile_nkb[t];
-  info[0] = pl.out_pitch; info[1] = pl.col_left0; info[2] = pl.x_l; info[3] = pl.col_right0; info[4] = pl.x_r;
-  info[5] = pl.n_col_tiles; info[6] = kb_total; info[7] = pl.ring;
-  if (pix_col_host) memcpy(pix_col_host, pl.pix_col.data(), sizeof(int) * P);
-  if (!out_dev) return 0;  // layout query only
-  if (out_capacity < n_rows * pl.out_pitch) return fail("output buffer too small");
-  if (upload_pxc_plan(pl)) { free_pxc_plan(pl); return 1; }
-  float* spec = nullptr;
-  if (tsum_dev && tsum_capacity < n_rows * pl.n_col_tiles * 2) return fail("tsum buffer too small");
-  cudaError_t e = cudaMalloc(&spec, sizeof(float) * n_rows * pl.pitch);
-  if (e == cudaSuccess) e = cudaMemset(spec, 0, sizeof(float) * n_rows * pl.pitch);
-  if (e != cudaSuccess) { free_pxc_plan(pl); return fail(std::string("debug spectra: ") + cudaGetErrorString(e)); }
-  ifc::pad_rows_kernel<<<dim3(8, (unsigned)n_rows), 256>>>(spectra_dev, n_rows, F, spec, pl.pitch, pl.pad_left);
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
-  int rc = 0;
-  long long* dbg = nullptr;
-  if (getenv("BAYSAR_PXC_TRACE")) {
-    cudaMalloc(&dbg, sizeof(long long) * 16 * 256);
-    cudaMemset(dbg, 0, sizeof(long long) * 16 * 256);
-  }
-  for (int rep = 0; rep < 2 && rc == 0; ++rep) {
-    cudaEventRecord(e0, 0);
-    rc = launch_pxc(pl, spec, (int)(n_rows / ifc::TILE_M), out_dev, tsum_dev, sms, 0, dbg);
-    cudaEventRecord(e1, 0);
-    if (rc == 0 && cudaEventSynchronize(e1) != cudaSuccess) rc = fail(std::string("folded contraction: ") + cudaGetErrorString(cudaGetLastError()));
-  }
-  float ms = 0.f;
-  if (rc == 0) cudaEventElapsedTime(&ms, e0, e1);
-  if (elapsed_ms) *elapsed_ms = ms;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  if (dbg && rc == 0) {
-    std::vector<long long> h(16 * 256);
-    cudaMemcpy(h.data(), dbg, sizeof(long long) * 16 * 256, cudaMemcpyDeviceToHost);
-    const char* names[13] = {"conv.wait_landed", "conv.wait_empty", "conv.total", "load.wait_consumed", "build.wait_bempty",
-                             "build.total", "epi.wait_acc_full", "epi.drain", "mma.wait_full", "mma.wait_bfull",
-                             "mma.wait_acc_free", "mma.total", "mma.k_blocks"};
-    const int ctas = (int)std::min<int64_t>(sms, (n_rows / ifc::TILE_M) * pl.n_col_tiles);
-    for (int k = 0; k < 13; ++k) {
-      double mean = 0, mx = 0;
-      for (int b = 0; b < ctas; ++b) { mean += (double)h[b * 16 + k]; mx = std::max(mx, (double)h[b * 16 + k]); }
-      fprintf(stderr, "[pxc trace] %-20s mean %.0f max %.0f (CTA0 %lld)\n", names[k], mean / ctas, mx, h[k]);
-    }
-  }
-  cudaFree(dbg);
-  cudaFree(spec);
-  free_pxc_plan(pl);
-  return rc;
-}
-
-int baysar_debug_pix_plan_check(const double* spectrum_host, int F, const double* taps_host, int KI,
-                                const int* pix_idx_host, const double* pix_frac_host, int P, int tile_n, double* result) {
-  // Host-only self check of the folded-contraction plan (no GPU needed): evaluates every column through the plan's
-  // tables with the kernel's index arithmetic (float64 products) against the definition, and the area identity of
-  // pixel_fold_kernel against the direct trapz of the clipped convolution.
-  if (!spectrum_host || !taps_host || !pix_idx_host || !pix_frac_host || !result) return fail("null argument");
-  double wmax = 0.0;
-  for (int k = 0; k < KI; ++k) wmax = fabs(taps_host[k]) > wmax ? fabs(taps_host[k]) : wmax;
-  int k_lo = KI, k_hi = 0;
-  for (int k = 0; k < KI; ++k)
-    if (fabs(taps_host[k]) > 1e-17 * wmax) { k_lo = k < k_lo ? k : k_lo; k_hi = k + 1; }
-  PxcPlan pl = make_pxc_plan(taps_host, KI, k_lo, k_hi, F, P, pix_idx_host, pix_frac_host, tile_n == 64 ? 64 : 128);
-  if (!pl.on) return fail("no folded-contraction plan for this instrument function / grid");
-  const int o = (KI - 1) / 2, tn = pl.tn;
-  std::vector<double> conv(F);
-  double mn = spectrum_host[0], cmax = 0.0;
-  for (int j = 0; j < F; ++j) {
-    mn = spectrum_host[j] < mn ? spectrum_host[j] : mn;
-    double acc = 0.0;
-    for (int k = k_lo; k < k_hi; ++k) {
-      const int sidx = j + o - k;
-      if (sidx >= 0 && sidx < F) acc += (double)(float)taps_host[k] * spectrum_host[sidx];
-    }
-    conv[j] = acc;
-    cmax = fabs(acc) > cmax ? fabs(acc) : cmax;
-  }
-  auto padded = [&](int64_t col) {  // the zero-padded row the kernel reads
-    const int64_t sidx = col - pl.pad_left;
-    return (sidx >= 0 && sidx < F) ? spectrum_host[sidx] : 0.0;
-  };
-  std::vector<double> out(pl.out_pitch);
-  for (int t = 0; t < pl.n_col_tiles; ++t)
-    for (int c = t * tn; c < (t + 1) * tn; ++c) {
-      double acc = 0.0;
-      for (int kb = 0; kb < pl.tile_nkb[t]; ++kb)
-        for (int e = 0; e < ifc::TILE_K; ++e) {
-          const int x = pl.col_idx[c] - ifc::TILE_K * kb - e;
-          if (x - 3 < 0 || x + 1 >= pl.wlen) return fail("tap table index out of range");
-          const double b = (double)pl.wtab[x] + (double)pl.col_frac[c] * ((double)pl.wtab[x + 1] - (double)pl.wtab[x]);
-          acc += padded((int64_t)pl.tile_kcol0[t] + ifc::TILE_K * kb + e) * b;
-        }
-      out[c] = acc;
-    }
-  double err_pix = 0.0, err_edge = 0.0;
-  int n_folded = 0;
-  for (int p = 0; p < P; ++p) {
-    if (pl.pix_col[p] < 0) continue;
-    ++n_folded;
-    const int i = pix_idx_host[p];
-    const double ref = conv[i] + (double)(float)pix_frac_host[p] * (conv[i + 1] - conv[i]);
-    err_pix = std::max(err_pix, fabs(out[pl.pix_col[p]] - ref) / cmax);
-  }
-  for (int j = 0; j < pl.x_l; ++j) err_edge = std::max(err_edge, fabs(out[pl.col_left0 + j] - conv[j]) / cmax);
-  for (int j = F - pl.x_r; j < F; ++j) err_edge = std::max(err_edge, fabs(out[pl.col_right0 + j - (F - pl.x_r)] - conv[j]) / cmax);
-  // area identity
-  double pre = 0.0, post_direct = 0.0, part = 0.0;
-  for (int j = 0; j < F; ++j) {
-    const double cj = (j == 0 || j == F - 1) ? 0.5 : 1.0;
-    pre += cj * spectrum_host[j];
-    post_direct += cj * (conv[j] < mn ? mn : conv[j]);
-  }
-  for (int t = 0; t < pl.x_l + pl.x_r; ++t) {
-    const int j = t < pl.x_l ? t : F - pl.x_r + (t - pl.x_l);
-    const double v = t < pl.x_l ? out[pl.col_left0 + t] : out[pl.col_right0 + (t - pl.x_l)];
-    if (v < mn) part += ((j == 0 || j == F - 1) ? 0.5 : 1.0) * (mn - v);
-  }
-  for (int t = 0; t < pl.n_dl + pl.n_dr; ++t) {
-    const int sidx = t < pl.n_dl ? t : F - pl.n_dr + (t - pl.n_dl);
-    part += spectrum_host[sidx] * pl.dtab[t];
-  }
-  // column-sum identity per folded tile
-  double err_cs = 0.0;
-  for (int t = 0; t < pl.n_fold_tiles && pl.tile_boff[t] >= 0; ++t) {
-    double col_sum = 0.0, t_id = 0.0;
-    for (int c = t * tn; c < (t + 1) * tn; ++c) col_sum += out[c];
-    for (int x = 0; x < ifc::TILE_K * pl.tile_nkb[t]; ++x)
-      t_id += padded((int64_t)pl.tile_kcol0[t] + x) * (double)pl.bbar[pl.tile_boff[t] + x];
-    err_cs = std::max(err_cs, fabs(t_id - col_sum) / fabs(col_sum));
-  }
-  result[8] = err_cs;
-  // interior columns must not need the clip
-  double clip_violation = 0.0;
-  for (int j = pl.e_l; j < F - pl.e_r; ++j) clip_violation = std::max(clip_violation, (mn - conv[j]) / cmax);
-  int64_t kb_total = 0;
-  for (int t = 0; t < pl.n_col_tiles; ++t) kb_total += pl.tile_nkb[t];
-  result[0] = err_pix; result[1] = err_edge; result[2] = fabs((pl.wsum * pre + part) - post_direct) / fabs(post_direct);
-  result[3] = (double)kb_total; result[4] = (double)n_folded; result[5] = clip_violation; result[6] = (double)pl.wlen;
-  result[7] = (double)pl.ring;
+  m->prof_used = 0;  // the events stay in the pool
   return 0;
 }
 
@@ -1290,72 +727,6 @@ int baysar_stretch_accept(double* walkers, double* logp, const double* proposal,
   ens::stretch_accept_kernel<<<(unsigned)((n_walkers + 127) / 128), 128, 0, stream>>>(
       walkers, logp, proposal, logp_new, log_factor, status_new, n_params, n_walkers, seed, step, n_accepted);
   CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-int baysar_debug_mma_probe(int device, int tile_n, int form, int n_acc_hi, int b_stages, int pattern, int iters,
-                           double* cycles_per_mma) {
-  if (!cycles_per_mma) return fail("null argument");
-  if (tile_n < 8 || tile_n > 256 || tile_n % 8 || n_acc_hi < 1 || (n_acc_hi + 1) * tile_n > 512 || b_stages < 1 ||
-      b_stages > 4 || iters < 1)
-    return fail("bad probe arguments");
-  CUDA_OK(cudaSetDevice(device));
-  int sms = 0;
-  CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  long long* out = nullptr;
-  CUDA_OK(cudaMalloc(&out, sizeof(long long) * sms));
-  CUDA_OK(cudaMemset(out, 0, sizeof(long long) * sms));
-  const size_t smem = (size_t)4 * 256 * 128 + 128 * 128 + 1024;
-  CUDA_OK(cudaFuncSetAttribute(mmaprobe::mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  for (int rep = 0; rep < 2; ++rep) {
-    mmaprobe::mma_probe_kernel<<<sms, 128, smem>>>(tile_n, form, n_acc_hi, b_stages, pattern, iters, out);
-    CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaDeviceSynchronize());
-  }
-  std::vector<long long> h(sms);
-  CUDA_OK(cudaMemcpy(h.data(), out, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
-  cudaFree(out);
-  double worst = 0.0;
-  for (long long c : h) {
-    if (c < 0) return fail("probe timed out");
-    worst = (double)c > worst ? (double)c : worst;
-  }
-  *cycles_per_mma = worst / ((double)iters * (pattern == 2 ? 2.0 : 6.0));
-  return 0;
-}
-
-int baysar_microbench(int device, int what, double* result) {
-  if (!result) return fail("null argument");
-  CUDA_OK(cudaSetDevice(device));
-  int sms = 0;
-  CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  float* out = nullptr;
-  CUDA_OK(cudaMalloc(&out, sizeof(float) * 1024));
-  const int iters = 4096, blocks = sms * 8, threads = 256;
-  cudaEvent_t e0, e1;
-  CUDA_OK(cudaEventCreate(&e0));
-  CUDA_OK(cudaEventCreate(&e1));
-  double best = 0.0;
-  for (int rep = 0; rep < 5; ++rep) {
-    CUDA_OK(cudaEventRecord(e0, 0));
-    if (what == 0) microbench_ffma_kernel<<<blocks, threads>>>(out, iters, 1.0001f);
-    else if (what == 1) microbench_mufu_kernel<<<blocks, threads>>>(out, iters, 1.0001f);
-    else if (what == 3) microbench_ffma_reg_kernel<<<blocks, threads>>>(out, iters, 1.0001f, 0.5f);
-    else if (what == 4) microbench_ffma2_kernel<<<blocks, threads>>>(out, iters, 1.0001f, 0.5f);
-    else microbench_dfma_kernel<<<blocks, threads>>>(reinterpret_cast<double*>(out), iters, 1.0001);
-    CUDA_OK(cudaEventRecord(e1, 0));
-    CUDA_OK(cudaEventSynchronize(e1));
-    float ms = 0.f;
-    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
-    // ops per thread per iteration: 16 independent chains x 1 instruction
-    double ops = (double)blocks * threads * (double)iters * 16.0 * (what == 4 ? 2.0 : 1.0);
-    double rate = ops / (ms * 1e-3);
-    if (rep > 0 && rate > best) best = rate;
-  }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(out);
-  *result = what == 1 ? best : 2.0 * best;  // FMA = 2 flop; MUFU counted as ops
   return 0;
 }
 

@@ -62,6 +62,7 @@ struct Cfg {
   static_assert(TN % 64 == 0 && B_STAGES > BUILDER_TEAMS, "every builder team owns a stage in flight, the MMAs read another");
 };
 constexpr int MIN_KB = 4;  // every accumulator of a tile is initialised by its own first k-block
+constexpr int MAX_FOLD_TILES = 64;  // folded (pixel) column tiles per chord: pixel_fold_kernel keeps one correction / scale per tile in shared memory
 
 struct Params {
   const float* s;          // [rows][pitch] FP32 spectra, zero padded

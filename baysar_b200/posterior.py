@@ -10,7 +10,8 @@ Same constructor and call protocol as the reference (`/root/reference/baysar/pos
 plus the batched form the reference lacks: ``posterior(theta)`` with a 2-D ``(N, n_params)`` array (numpy, host) or
 CUDA tensor returns N log-posteriors evaluated by three CUDA kernel launches; per-sample failures come back as status
 flags (``posterior.last_status``) instead of exceptions.  Extra keyword arguments: ``atomic_data`` (provider, see
-``baysar_b200.atomic_data``) and ``device``.
+``baysar_b200.atomic_data``), ``device`` and ``options`` (dict of ``baysar_options_t`` fields, include/baysar_b200.h:
+kernel-selection switches such as ``tensor_cores=-1``; every variant computes the same quantities).
 
 There is no CPU path: construction needs a CUDA device and the in-tree ``libbaysar_b200.so``.
 """
@@ -108,7 +109,7 @@ def set_sensible_bounds(plasma, chords, dcwl=2, ddisp=0.005):
 
 class BaysarPosterior:
     def __init__(self, input_dict, profile_function=None, priors=[], check_bounds=False, temper=1.0, curvature=None,
-                 print_errors=False, skip_test=False, atomic_data=None, device=None):
+                 print_errors=False, skip_test=False, atomic_data=None, device=None, options=None):
         self.check_init_inputs(priors, check_bounds, temper, curvature, print_errors)
         self.input_dict = input_dict
         self.plasma = PlasmaLine(input_dict=input_dict, profile_function=profile_function, atomic_data=atomic_data)
@@ -128,7 +129,7 @@ class BaysarPosterior:
 
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
         self.device = int(device)
-        self.model = runtime.DeviceModel(self.blob, self.device)  # raises without a GPU / library: no CPU fallback
+        self.model = runtime.DeviceModel(self.blob, self.device, options)  # raises without a GPU / library: no CPU fallback
         for c in self.chords:
             c._posterior = self
         for k, p in enumerate(self.priors):
@@ -245,6 +246,13 @@ class BaysarPosterior:
         if isinstance(theta, torch.Tensor):
             return theta.to(device=f"cuda:{self.device}", dtype=torch.float64)
         return torch.as_tensor(np.asarray(theta, dtype=float), device=f"cuda:{self.device}")
+
+    @property
+    def op_handle(self):
+        """Integer handle of this posterior's compiled model for ``torch.ops.baysar.eval_logp(handle, theta)``."""
+        from . import torch_ops
+
+        return torch_ops.register_model(self.model)
 
     def logp_batch(self, theta, return_status=False):
         """theta: CUDA float64 tensor (N, n_params) -> CUDA tensor of N log-posteriors (no host round trip)."""

@@ -11,32 +11,57 @@ import subprocess
 
 PKG = pathlib.Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-LIB_PATH = PKG / "libbaysar_b200.so"
+INCLUDE = PKG.parent / "include"
+LIB_PATH = PKG / "libbaysar_b200.so"              # the product: include/baysar_b200.h
+TOOLS_LIB_PATH = PKG / "libbaysar_b200_tools.so"  # measurement / unit-test hooks: include/baysar_b200_tools.h
 LINE_STRIDE = 16  # BAYSAR_LINE_STRIDE (include/baysar_b200.h)
 IFC_TILE_N = 128  # ifc::TILE_N (csrc/if_contract.cuh): fine-grid outputs per contraction tile
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--compiler-options", "-fPIC", "-shared"]
+OPTION_FIELDS = ("tensor_cores", "ifc_min_taps", "ifc_budget_mb", "folded_tile", "los_min_blocks", "los_team_points",
+                 "chord_min_blocks")  # baysar_options_t, in declaration order
 
 
-def build_library(force=False, verbose=False):
-    """Compile csrc/baysar_abi.cu for sm_100a into the package directory (nvcc cross-compiles without a GPU)."""
-    sources = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h"))
-    if LIB_PATH.exists() and not force:
-        newest = max(s.stat().st_mtime for s in sources)
-        if LIB_PATH.stat().st_mtime >= newest:
-            return LIB_PATH
+class Options(ctypes.Structure):
+    """baysar_options_t (include/baysar_b200.h): 0 = library default for every field."""
+    _fields_ = [(name, ctypes.c_int) for name in OPTION_FIELDS] + [("reserved", ctypes.c_int * 9)]
+
+
+def _sources():
+    return (sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) +
+            sorted(INCLUDE.glob("*.h")))
+
+
+def _build_one(target, source, force, verbose, extra=()):
+    if target.exists() and not force:
+        if target.stat().st_mtime >= max(s.stat().st_mtime for s in _sources()):
+            return None
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    extra = os.environ.get("BAYSAR_NVCC_EXTRA", "").split()  # experiments only (e.g. -DBAYSAR_PXC_NACC128=1)
-    cmd = [nvcc, *NVCC_FLAGS, *extra, "-Xptxas", "-v", "-o", str(LIB_PATH), str(CSRC / "baysar_abi.cu")]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    extra = list(extra) + os.environ.get("BAYSAR_NVCC_EXTRA", "").split()  # build experiments only (-D switches)
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-Xptxas", "-v", "-o", str(target), str(source)]
+    return subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+
+
+def build_library(force=False, verbose=False, tools=True):
+    """Compile csrc/baysar_abi.cu (and csrc/baysar_tools.cu) for sm_100a into the package directory; nvcc cross-compiles
+    without a GPU.  The two compilations run side by side.  A library is rebuilt when any source under csrc/ or any
+    header under include/ is newer than it."""
+    jobs = [(LIB_PATH, _build_one(LIB_PATH, CSRC / "baysar_abi.cu", force, verbose))]
+    if tools:
+        jobs.append((TOOLS_LIB_PATH, _build_one(TOOLS_LIB_PATH, CSRC / "baysar_tools.cu", force, verbose)))
+    for target, proc in jobs:
+        if proc is None:
+            continue
+        out, _ = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {target.name}:\n" + out)
+        if verbose:
+            print(out)
     return LIB_PATH
 
 
 _lib = None
+_tools = None
 
 
 def library():
@@ -51,6 +76,8 @@ def library():
     vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
     lib.baysar_model_create.argtypes = [vp, ctypes.c_size_t, i32, ctypes.POINTER(vp)]
     lib.baysar_model_create.restype = i32
+    lib.baysar_model_create_ex.argtypes = [vp, ctypes.c_size_t, i32, ctypes.POINTER(Options), ctypes.POINTER(vp)]
+    lib.baysar_model_create_ex.restype = i32
     lib.baysar_model_destroy.argtypes = [vp]
     lib.baysar_model_destroy.restype = None
     lib.baysar_model_query.argtypes = [vp, i32, i32]
@@ -67,6 +94,26 @@ def library():
     lib.baysar_model_set_profiling.restype = i32
     lib.baysar_model_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     lib.baysar_model_get_profile.restype = i32
+    u64 = ctypes.c_uint64
+    lib.baysar_stretch_propose.argtypes = [vp, vp, i32, i64, i64, ctypes.c_double, u64, u64, vp, vp, vp]
+    lib.baysar_stretch_propose.restype = i32
+    lib.baysar_stretch_accept.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, u64, u64, vp, vp]
+    lib.baysar_stretch_accept.restype = i32
+    lib.baysar_last_error.restype = ctypes.c_char_p
+    lib.baysar_version.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+def tools_library():
+    """Load the measurement / unit-test library (peak-rate probes, contraction hooks)."""
+    global _tools
+    if _tools is not None:
+        return _tools
+    if not TOOLS_LIB_PATH.exists():
+        raise RuntimeError(f"{TOOLS_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = ctypes.CDLL(str(TOOLS_LIB_PATH))
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
     lib.baysar_microbench.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double)]
     lib.baysar_microbench.restype = i32
     lib.baysar_debug_if_contract.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp, ctypes.POINTER(i64),
@@ -79,33 +126,32 @@ def library():
     lib.baysar_debug_pix_plan_check.restype = i32
     lib.baysar_debug_mma_probe.argtypes = [i32, i32, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_double)]
     lib.baysar_debug_mma_probe.restype = i32
-    u64 = ctypes.c_uint64
-    lib.baysar_stretch_propose.argtypes = [vp, vp, i32, i64, i64, ctypes.c_double, u64, u64, vp, vp, vp]
-    lib.baysar_stretch_propose.restype = i32
-    lib.baysar_stretch_accept.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, u64, u64, vp, vp]
-    lib.baysar_stretch_accept.restype = i32
-    lib.baysar_last_error.restype = ctypes.c_char_p
-    lib.baysar_version.restype = ctypes.c_char_p
-    _lib = lib
+    lib.baysar_tools_last_error.restype = ctypes.c_char_p
+    _tools = lib
     return lib
 
 
-EXPORTED_SYMBOLS = ["baysar_model_create", "baysar_model_destroy", "baysar_model_query", "baysar_eval_logp",
-                    "baysar_eval_spectra", "baysar_eval_lines", "baysar_eval_logp_host", "baysar_last_error",
-                    "baysar_version", "baysar_stretch_propose", "baysar_stretch_accept", "baysar_model_set_profiling", "baysar_model_get_profile", "baysar_microbench", "baysar_debug_if_contract",
-                    "baysar_debug_mma_probe", "baysar_debug_pix_contract",
-                    "baysar_debug_pix_plan_check"]
+EXPORTED_SYMBOLS = ["baysar_model_create", "baysar_model_create_ex", "baysar_model_destroy", "baysar_model_query",
+                    "baysar_eval_logp", "baysar_eval_spectra", "baysar_eval_lines", "baysar_eval_logp_host",
+                    "baysar_last_error", "baysar_version", "baysar_stretch_propose", "baysar_stretch_accept",
+                    "baysar_model_set_profiling", "baysar_model_get_profile"]
+TOOLS_EXPORTED_SYMBOLS = ["baysar_tools_last_error", "baysar_microbench", "baysar_debug_if_contract",
+                          "baysar_debug_mma_probe", "baysar_debug_pix_contract", "baysar_debug_pix_plan_check"]
+
+
+def _tools_check(rc):
+    if rc != 0:
+        raise RuntimeError("baysar_b200 tools: " + tools_library().baysar_tools_last_error().decode())
 
 
 def microbench(device=0):
     """Measured FP32-FMA / MUFU / FP64-FMA peak rates of this GPU (flop/s, op/s, flop/s)."""
-    lib = library()
+    lib = tools_library()
     out = {}
     for what, key in ((0, "fp32_fma_flops"), (1, "mufu_ops"), (2, "fp64_fma_flops"), (3, "fp32_fma_reg_flops"),
                       (4, "fp32_fma2_flops")):
         val = ctypes.c_double()
-        if lib.baysar_microbench(int(device), what, ctypes.byref(val)) != 0:
-            raise RuntimeError("baysar_b200: " + lib.baysar_last_error().decode())
+        _tools_check(lib.baysar_microbench(int(device), what, ctypes.byref(val)))
         out[key] = val.value
     return out
 
@@ -116,7 +162,7 @@ def debug_if_contract(spectra, taps, row_min=None):
     import numpy as np
     import torch
 
-    lib = library()
+    lib = tools_library()
     spectra = spectra.contiguous()
     n, F = spectra.shape
     taps = np.ascontiguousarray(taps, dtype=np.float64)
@@ -127,8 +173,7 @@ def debug_if_contract(spectra, taps, row_min=None):
     rc = lib.baysar_debug_if_contract(spectra.data_ptr(), n, F, taps.ctypes.data, len(taps),
                                       row_min.data_ptr() if row_min is not None else None, out.data_ptr(),
                                       part.data_ptr(), ctypes.byref(pitch), ctypes.byref(tiles), ctypes.byref(ms))
-    if rc != 0:
-        raise RuntimeError("baysar_b200: " + lib.baysar_last_error().decode())
+    _tools_check(rc)
     torch.cuda.synchronize()
     return out[:, :F], part.sum(dim=1), ms.value
 
@@ -140,7 +185,7 @@ def debug_pix_contract(spectra, taps, pix_idx, pix_frac, tile_n=128):
     import numpy as np
     import torch
 
-    lib = library()
+    lib = tools_library()
     spectra = spectra.contiguous()
     n, F = spectra.shape
     taps = np.ascontiguousarray(taps, dtype=np.float64)
@@ -153,14 +198,12 @@ def debug_pix_contract(spectra, taps, pix_idx, pix_frac, tile_n=128):
     args = [spectra.data_ptr(), n, F, taps.ctypes.data, len(taps), pix_idx.ctypes.data, pix_frac.ctypes.data, P, tile_n]
     rc = lib.baysar_debug_pix_contract(*args, None, 0, None, 0, ctypes.cast(info, ctypes.c_void_p), pix_col.ctypes.data,
                                        ctypes.byref(ms))
-    if rc != 0:
-        raise RuntimeError("baysar_b200: " + lib.baysar_last_error().decode())
+    _tools_check(rc)
     out = torch.empty((n, info[0]), dtype=torch.float32, device=spectra.device)
     tsum = torch.zeros((n, info[5], 2), dtype=torch.float64, device=spectra.device)
     rc = lib.baysar_debug_pix_contract(*args, out.data_ptr(), out.numel(), tsum.data_ptr(), tsum.numel(),
                                        ctypes.cast(info, ctypes.c_void_p), pix_col.ctypes.data, ctypes.byref(ms))
-    if rc != 0:
-        raise RuntimeError("baysar_b200: " + lib.baysar_last_error().decode())
+    _tools_check(rc)
     torch.cuda.synchronize()
     keys = ("out_pitch", "col_left0", "x_l", "col_right0", "x_r", "n_col_tiles", "k_blocks", "ring")
     res = {k: int(info[i]) for i, k in enumerate(keys)}
@@ -172,7 +215,7 @@ def debug_pix_plan_check(spectrum, taps, pix_idx, pix_frac, tile_n=128):
     """Host-only check of the folded-contraction plan (no GPU): see baysar_debug_pix_plan_check in the header."""
     import numpy as np
 
-    lib = library()
+    lib = tools_library()
     spectrum = np.ascontiguousarray(spectrum, dtype=np.float64)
     taps = np.ascontiguousarray(taps, dtype=np.float64)
     pix_idx = np.ascontiguousarray(pix_idx, dtype=np.int32)
@@ -180,8 +223,7 @@ def debug_pix_plan_check(spectrum, taps, pix_idx, pix_frac, tile_n=128):
     res = np.zeros(9)
     rc = lib.baysar_debug_pix_plan_check(spectrum.ctypes.data, len(spectrum), taps.ctypes.data, len(taps),
                                          pix_idx.ctypes.data, pix_frac.ctypes.data, len(pix_idx), tile_n, res.ctypes.data)
-    if rc != 0:
-        raise RuntimeError("baysar_b200: " + lib.baysar_last_error().decode())
+    _tools_check(rc)
     keys = ("err_pixels", "err_edges", "err_area", "k_blocks", "n_folded", "clip_violation", "wlen", "ring", "err_colsum")
     return dict(zip(keys, res.tolist()))
 
@@ -189,7 +231,8 @@ def debug_pix_plan_check(spectrum, taps, pix_idx, pix_frac, tile_n=128):
 class DeviceModel:
     """One compiled model resident in one GPU's HBM."""
 
-    def __init__(self, blob, device=0):
+    def __init__(self, blob, device=0, options=None):
+        """``options``: dict of baysar_options_t fields (see OPTION_FIELDS; 0 / missing = library default)."""
         import torch
 
         if not torch.cuda.is_available():
@@ -199,8 +242,14 @@ class DeviceModel:
         self.device = int(device)
         self.handle = ctypes.c_void_p()
         buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
-        rc = self.lib.baysar_model_create(ctypes.cast(buf, ctypes.c_void_p), len(blob), self.device,
-                                          ctypes.byref(self.handle))
+        opts = Options()
+        for key, val in (options or {}).items():
+            if key not in OPTION_FIELDS:
+                raise KeyError(f"unknown model option {key!r}; known: {OPTION_FIELDS}")
+            setattr(opts, key, int(val))
+        self.options = dict(options or {})
+        rc = self.lib.baysar_model_create_ex(ctypes.cast(buf, ctypes.c_void_p), len(blob), self.device,
+                                             ctypes.byref(opts), ctypes.byref(self.handle))
         self._check(rc)
         q = lambda what, arg=0: int(self.lib.baysar_model_query(self.handle, what, arg))  # noqa: E731
         self.n_params, self.n_chords, self.n_ulines, self.n_priors = q(0), q(1), q(2), q(3)

@@ -16,8 +16,8 @@
  *     (BAYSAR_ST_*), never as a return code; logp of a failed sample is whatever arithmetic produced (NaN/inf);
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous w.r.t.
  *     the host except the `_host` variants;
- *   - a model is immutable after creation: evaluation is re-entrant across models; one model (and its
- *     workspace) must not be used from two streams at the same time.
+ *   - a model's constants are immutable after creation: evaluation is re-entrant across models; one model owns one
+ *     workspace, so calls on the same model must be ordered on one stream (or separated by events).
  */
 #ifndef BAYSAR_B200_H
 #define BAYSAR_B200_H
@@ -62,6 +62,23 @@ typedef struct baysar_model baysar_model_t;
 /* Build a model from the descriptor blob produced by baysar_b200.model.compile_model (format: csrc/layout.h);
  * copies every constant table to HBM on `device` once.   Replaces BaysarPosterior.__init__'s object graph. */
 int baysar_model_create(const void* desc_blob, size_t nbytes, int device, baysar_model_t** out);
+
+/* Tuning options of a model (every field: 0 = the library's default).  They select between kernels that compute the same
+ * quantities (parity tests compare the variants); none is read from the environment. */
+typedef struct baysar_options {
+  int tensor_cores;      /* 0 auto (tcgen05 contraction for long static instrument functions), 1 force on, -1 off:
+                            every chord stays on the fused FP32 kernel */
+  int ifc_min_taps;      /* shortest significant instrument-function window that takes the tensor-core path (160) */
+  int ifc_budget_mb;     /* HBM budget of the tensor-core path's spectra workspaces in MiB (24576) */
+  int folded_tile;       /* folded pixel contraction: 0 auto (128-column tiles), 64 / 128 tile width, -1 off (the
+                            every-column Toeplitz contraction) */
+  int los_min_blocks;    /* resident CTAs per SM the LOS kernel is compiled for (0 auto by batch size, 4..8) */
+  int los_team_points;   /* LOS points from which one CTA works on one theta (0 auto: when 4 thetas no longer fit) */
+  int chord_min_blocks;  /* upper limit of resident CTAs per SM of the chord kernel (0 auto = 5; 3..5) */
+  int reserved[9];
+} baysar_options_t;
+int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, const baysar_options_t* options,
+                           baysar_model_t** out);
 void baysar_model_destroy(baysar_model_t* model);
 
 /* Sizes a caller needs to allocate outputs. what: 0 n_params, 1 n_chords, 2 n_unique_lines, 3 n_priors,
@@ -93,47 +110,12 @@ int baysar_eval_logp_host(baysar_model_t* model, const double* theta_host, int64
                           uint32_t* status_host);
 
 /* Measurement hooks (no reference counterpart; used by bench.py for the live roofline).  While profiling is on,
- * every baysar_eval_logp call records CUDA events around its three kernels on the caller's stream;
- * baysar_model_get_profile synchronises, returns the summed per-stage milliseconds (LOS, chord, finalize) and the
- * number of calls, and resets the log. */
+ * every baysar_eval_logp call records CUDA events around each of its kernels on the caller's stream (the events come
+ * from a pool that grows during the first profiled calls and is reused afterwards: no event is created inside a
+ * steady-state call); baysar_model_get_profile synchronises, returns the summed per-stage milliseconds
+ * (LOS, chord, contraction, pixel, finalize) and the number of calls, and resets the log. */
 int baysar_model_set_profiling(baysar_model_t* model, int on);
 int baysar_model_get_profile(baysar_model_t* model, double* stage_ms, int64_t* calls);
-/* Peak-rate probe for roofline denominators: what = 0 FP32 FMA flop/s, 1 MUFU (rcp) op/s, 2 FP64 FMA flop/s. */
-int baysar_microbench(int device, int what, double* result);
-
-/* Unit-test hook for the tcgen05 instrument-function contraction (csrc/if_contract.cuh): for n_rows (multiple of 128)
- * rows of F floats, out[r][j] = max(sum_k taps[k] * spectra[r][j + (KI-1)/2 - k], row_min[r]) (zero padded "same"
- * convolution, scipy.signal.fftconvolve semantics of spectrometers.py:269-271).  out_dev must hold
- * n_rows * ceil(F/128)*128 floats; trapz_dev (optional) n_rows * ceil(F/128) doubles. */
-int baysar_debug_if_contract(const float* spectra_dev, int64_t n_rows, int F, const double* taps_host, int KI,
-                             const float* row_min_dev, float* out_dev, double* trapz_dev, int64_t* out_pitch,
-                             int* n_tiles, float* elapsed_ms);
-
-/* Unit-test hook for the folded pixel contraction (csrc/pix_contract.cuh): instrument convolution and the static
- * wavelength map (interp1d between fine-grid points pix_idx[p], pix_idx[p] + 1 with weight pix_frac[p]) as one
- * contraction.  out[r][c]: column pix_col[p] (>= 0) holds pixel p; explicit (unclipped) fine-grid columns
- * j = 0 .. x_l - 1 at col_left0 + j and j = F - x_r .. F - 1 at col_right0 + j - (F - x_r).
- * info[8] = out_pitch, col_left0, x_l, col_right0, x_r, column tiles, k-blocks per theta block, A ring stages.
- * tsum_dev (optional, n_rows * column tiles * 2 doubles): exact column sums per (row, folded tile, converter group).
- * out_dev == NULL: layout query only. */
-int baysar_debug_pix_contract(const float* spectra_dev, int64_t n_rows, int F, const double* taps_host, int KI,
-                              const int* pix_idx_host, const double* pix_frac_host, int P, int tile_n, float* out_dev,
-                              int64_t out_capacity, double* tsum_dev, int64_t tsum_capacity, int64_t* info,
-                              int* pix_col_host, float* elapsed_ms);
-
-/* Host-only self check of the folded-contraction plan (runs without a GPU): one float64 spectrum through the plan's
- * tables with the kernel's index arithmetic.  result[9] = max |error| / max|conv| of the pixel columns, of the explicit
- * edge columns, relative error of the area identity, k-blocks per theta block, folded pixels, largest interior clip
- * violation / max|conv| (<= 0: the clip is inactive there), tap-table floats, A ring stages, relative error of the
- * column-sum identity (float32 bbar table against the float64 column sum). */
-int baysar_debug_pix_plan_check(const double* spectrum_host, int F, const double* taps_host, int KI,
-                                const int* pix_idx_host, const double* pix_frac_host, int P, int tile_n, double* result);
-
-/* Issue-rate probe of kind::tf32 tcgen05.mma (csrc/mma_probe.cuh): cycles per 128 x tile_n x 8 MMA, slowest SM, for the
- * contraction kernels' issue pattern on constant operands.  form 0 = A from tensor memory, 1 = A from shared memory;
- * pattern 0 = kernels' pattern, 1 = one accumulator, 2 = hi*hi only. */
-int baysar_debug_mma_probe(int device, int tile_n, int form, int n_acc_hi, int b_stages, int pattern, int iters,
-                           double* cycles_per_mma);
 
 const char* baysar_last_error(void);
 const char* baysar_version(void);

@@ -1,4 +1,5 @@
-"""The C-ABI library builds for sm_100a, loads, and exports every function include/baysar_b200.h declares."""
+"""The C-ABI libraries build for sm_100a, load, and export every function their headers declare (include/baysar_b200.h:
+the product boundary; include/baysar_b200_tools.h: measurement and unit-test hooks)."""
 import ctypes
 import pathlib
 import re
@@ -10,8 +11,8 @@ from baysar_b200 import model, runtime
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 
 
-def declared_functions():
-    text = (ROOT / "include" / "baysar_b200.h").read_text()
+def declared_functions(header="baysar_b200.h"):
+    text = (ROOT / "include" / header).read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(baysar_\w+)\s*\(", text)))
 
@@ -25,6 +26,39 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     lib.baysar_version.restype = ctypes.c_char_p
     assert b"sm_100a" in lib.baysar_version()
+
+
+def test_tools_library_exports_every_declared_symbol_and_nothing_leaks_into_the_product():
+    runtime.build_library()
+    tools = ctypes.CDLL(str(runtime.TOOLS_LIB_PATH))
+    names = declared_functions("baysar_b200_tools.h")
+    assert sorted(runtime.TOOLS_EXPORTED_SYMBOLS) == names
+    for name in names:
+        assert hasattr(tools, name), name
+    product = ctypes.CDLL(str(runtime.LIB_PATH))
+    for name in names:  # debug hooks, probes and micro-benchmarks are not part of the drop-in boundary
+        assert not hasattr(product, name), name
+
+
+def test_model_create_rejects_malformed_blobs():
+    """baysar_model_create validates the descriptor before anything indexes it (no GPU needed: validation comes first)."""
+    lib = runtime.library()
+    out = ctypes.c_void_p()
+    garbage = (ctypes.c_ubyte * 4096)()
+    assert lib.baysar_model_create(ctypes.cast(garbage, ctypes.c_void_p), 4096, 0, ctypes.byref(out)) != 0
+    assert b"magic" in lib.baysar_last_error()
+    import struct
+
+    n_sec = model.SEC["SEC_COUNT"]
+    # right magic / version / section count, but every section claims more elements than the blob holds
+    table = []
+    for _ in range(n_sec):
+        table += [16 * ((8 * (3 + 2 * n_sec) + 15) // 16), 1 << 20]
+    head = struct.pack(f"<{3 + 2 * n_sec}q", model.BLOB_MAGIC, model.BLOB_VERSION, n_sec, *table)
+    blob = head + b"\0" * 1024
+    buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+    assert lib.baysar_model_create(ctypes.cast(buf, ctypes.c_void_p), len(blob), 0, ctypes.byref(out)) != 0
+    assert b"out of range" in lib.baysar_last_error()
 
 
 def test_layout_header_parses():

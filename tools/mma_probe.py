@@ -7,7 +7,7 @@ from baysar_b200 import runtime  # noqa: E402
 
 
 def probe(tn, form, n_acc, b_stages, pattern, iters=4000):
-    lib = runtime.library()
+    lib = runtime.tools_library()
     out = ctypes.c_double()
     rc = lib.baysar_debug_mma_probe(0, tn, form, n_acc, b_stages, pattern, iters, ctypes.byref(out))
     if rc != 0:
