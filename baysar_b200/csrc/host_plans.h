@@ -290,7 +290,9 @@ int pxc_schedule(PxcPlan& pl, int n_rb, int sms, const PxcSchedule** out) {
 #define BAYSAR_SMEM_OPT_IN 232448
 template <class K>
 int allow_max_smem(K kern) {
-  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BAYSAR_SMEM_OPT_IN));
+  cudaFuncAttributes fa;
+  CUDA_OK(cudaFuncGetAttributes(&fa, kern));  // the opt-in limit covers static + dynamic shared memory
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BAYSAR_SMEM_OPT_IN - (int)fa.sharedSizeBytes));
   return 0;
 }
 int contraction_kernel_attributes() {

@@ -98,6 +98,8 @@ def main():
         ("multi_mesh_curv", configs.multi_species_mesh(curvature=50.0), 10, 1, {}),
         ("multi_priors", configs.multi_species_priors(), 12, 0, {}),
         ("multi_bowman_priors", configs.multi_species_bowman_priors(), 8, 0, {}),
+        ("balmer_hot", configs.balmer_series(flags=dict(cold_neutrals=False)), 10, 1, {}),
+        ("multi_species_32chords", configs.multi_species(32), 3, 0, {}),
     ]
     only = sys.argv[1:]
     for name, wl, n, nfine, attrs in jobs:

@@ -81,7 +81,7 @@ def test_golden_fixtures(name, posteriors):
                 np.testing.assert_allclose(rec[:, :1], ref[:, k, :1], rtol=1e-12)
 
 
-@pytest.mark.parametrize("name", ["balmer_series", "multi_species", "multi_hot", "multi_calibrated"])
+@pytest.mark.parametrize("name", ["balmer_series", "multi_species", "multi_hot", "multi_calibrated", "aug_demo"])
 def test_against_oracle_on_fresh_thetas(name, posteriors):
     post, wl = posteriors(name)
     oracle = oracle_posterior(name)
@@ -322,3 +322,131 @@ def test_batched_finite_difference_gradient(posteriors):
     scale = np.abs(ref).max()
     np.testing.assert_allclose(grad, ref, rtol=2e-3, atol=2e-4 * scale)
     np.testing.assert_allclose(post.cost_gradient(theta), -grad)
+
+
+def _compare_with_oracle(post, oracle, theta, chords=(0,), min_checked=3):
+    """logP, status agreement and per-chord spectra of `post` against the oracle port on the rows of `theta`."""
+    from oracle.numpy_port import OracleError
+
+    logp = post(theta)
+    status = post.last_status.copy()
+    spectra = {c: post.spectra_batch(theta, chord=c)[0] for c in chords}
+    checked = 0
+    for i, th in enumerate(theta):
+        try:
+            ref = oracle.evaluate(th)
+        except OracleError:
+            assert status[i] != 0, f"oracle raised but status is clean for theta {i}"
+            continue
+        assert status[i] == 0, (i, status[i])
+        np.testing.assert_allclose(logp[i], ref["logp"], rtol=LOGP_RTOL)
+        for c in chords:
+            np.testing.assert_allclose(spectra[c][i], ref["spectra"][c], rtol=SPECTRA_RTOL)
+        checked += 1
+    assert checked >= min_checked
+    return logp, status
+
+
+def test_config3_32_chords_against_oracle(posteriors):
+    """BASELINE configs[3]: one posterior with 32 spectrometer chords sharing one plasma (48 parameters): log-posterior,
+    every component and the spectra of four chords against the oracle on fresh thetas near the reference theta
+    (the regime the ensemble workload samples) and across the whole prior box."""
+    post, wl = posteriors("multi_species_32chords")
+    oracle = oracle_posterior("multi_species_32chords")
+    assert len(post.chords) == 32 and post.plasma.n_params == 48
+    rng = np.random.default_rng(41)
+    tb = np.asarray(post.plasma.theta_bounds, dtype=float)
+    np.random.seed(5)
+    centre = wl.theta_from_tags(post.plasma.slices, post.random_start())
+    near = centre + 1e-3 * (tb[:, 1] - tb[:, 0]) * rng.normal(size=(4, len(centre)))
+    wide = tb[:, 0] + rng.random((4, len(centre))) * (tb[:, 1] - tb[:, 0])
+    theta = np.concatenate([near, wide])
+    _compare_with_oracle(post, oracle, theta, chords=(0, 7, 19, 31), min_checked=5)
+    comps, _ = post.components_batch(theta[:2])
+    ref = oracle.evaluate(theta[0])
+    np.testing.assert_allclose(comps[0], ref["components"], rtol=LOGP_RTOL, atol=1e-9)
+
+
+def test_config2_full_batch_sample_against_oracle(posteriors):
+    """BASELINE configs[2] at its full batch (65 536 thetas of the multi-species chord): a seeded sample of 64 thetas
+    against the oracle, plus the size-independent properties (determinism, batch splitting) at that size."""
+    import torch
+
+    post, wl = posteriors("multi_species")
+    oracle = oracle_posterior("multi_species")
+    rng = np.random.default_rng(65536)
+    lo, hi = post.plasma.theta_bounds[:, 0], post.plasma.theta_bounds[:, 1]
+    theta = lo + rng.random((65536, post.plasma.n_params)) * (hi - lo)
+    dev = torch.as_tensor(theta, device="cuda")
+    a, st = post.logp_batch(dev, return_status=True)
+    b = post.logp_batch(dev)
+    assert torch.equal(a, b)
+    parts = torch.cat([post.logp_batch(dev[:30000]), post.logp_batch(dev[30000:])])
+    assert torch.equal(a, parts)
+    a, st = a.cpu().numpy(), st.cpu().numpy()
+    assert (st == 0).mean() > 0.9
+    from oracle.numpy_port import OracleError
+
+    checked = 0
+    for i in rng.choice(65536, 64, replace=False):
+        try:
+            ref = oracle(theta[i])
+        except OracleError:
+            assert st[i] != 0
+            continue
+        assert st[i] == 0
+        np.testing.assert_allclose(a[i], ref, rtol=LOGP_RTOL)
+        checked += 1
+    assert checked >= 56
+
+
+def test_hot_balmer_chord_against_oracle(posteriors):
+    """Thermalised neutrals on the Balmer-series chord: every line takes the multi-tap Stark (x) Doppler path
+    (30-200 taps of the 0.1 A grid), the case SURVEY hard part (e) calls the FLOP sink."""
+    post, wl = posteriors("balmer_hot")
+    oracle = oracle_posterior("balmer_hot")
+    rng = np.random.default_rng(77)
+    lo, hi = post.plasma.theta_bounds[:, 0], post.plasma.theta_bounds[:, 1]
+    theta = lo + rng.random((32, post.plasma.n_params)) * (hi - lo)
+    _compare_with_oracle(post, oracle, theta, min_checked=24)
+
+
+@pytest.mark.parametrize("n_los,n_lines,n_pix,n_theta", [(200, 200, 4096, 4), (1000, 200, 4096, 3), (50, 10, 4096, 4),
+                                                       (100, 200, 512, 4)])
+def test_shape_sweep_corners_against_oracle(n_los, n_lines, n_pix, n_theta):
+    """BASELINE configs[4] corners: the largest pixel count (P = 4096, F = 12 287), the most Gaussian components
+    (n_G = 200) and the longest line of sight (L = 1000) — log-posterior and spectra against the oracle."""
+    import baysar_b200.lineshapes as host_ns
+    import oracle.numpy_port as oracle_ns
+    from baysar_b200 import configs
+    from baysar_b200.atomic_data import SyntheticADAS
+    from baysar_b200.input_functions import make_input_dict
+    from baysar_b200.posterior import BaysarPosterior
+    from oracle.numpy_port import OraclePosterior
+
+    wl = configs.synthetic_sweep(n_los, n_lines, n_pix, balmer=True)
+    np.random.seed(0)
+    post = BaysarPosterior(make_input_dict(**wl.input_kwargs), profile_function=wl.make_profile(host_ns),
+                           atomic_data=SyntheticADAS(), skip_test=True)
+    oracle = OraclePosterior(make_input_dict(**wl.input_kwargs), SyntheticADAS(), wl.make_profile(oracle_ns))
+    rng = np.random.default_rng(n_los + n_lines + n_pix)
+    lo, hi = post.plasma.theta_bounds[:, 0], post.plasma.theta_bounds[:, 1]
+    theta = lo + rng.random((n_theta, post.plasma.n_params)) * (hi - lo)
+    _compare_with_oracle(post, oracle, theta, min_checked=max(2, n_theta - 2))
+
+
+def test_torch_operator_entry_point(posteriors):
+    """torch.ops.baysar.eval_logp is the same call as the C ABI's baysar_eval_logp."""
+    import torch
+
+    import baysar_b200.torch_ops  # noqa: F401  (registers the operator)
+
+    post, wl = posteriors("balmer_series")
+    z = np.load(GOLDEN / "balmer_series.npz")
+    theta = torch.as_tensor(z["theta"], device="cuda")
+    logp = torch.ops.baysar.eval_logp(post.op_handle, theta)
+    np.testing.assert_allclose(logp.cpu().numpy(), z["logp"], rtol=LOGP_RTOL)
+    both, status = torch.ops.baysar.eval_logp_status(post.op_handle, theta)
+    assert torch.equal(both, logp) and int(status.abs().sum()) == 0
+    with pytest.raises(NotImplementedError):
+        torch.ops.baysar.eval_logp(post.op_handle, theta.cpu())  # no CPU implementation: the dispatcher refuses

@@ -17,4 +17,6 @@ WORKLOADS = {
     "multi_mesh_curv": lambda: configs.multi_species_mesh(curvature=50.0),
     "multi_priors": lambda: configs.multi_species_priors(),
     "multi_bowman_priors": lambda: configs.multi_species_bowman_priors(),
+    "balmer_hot": lambda: configs.balmer_series(flags=dict(cold_neutrals=False)),
+    "multi_species_32chords": lambda: configs.multi_species(32),
 }
