@@ -14,6 +14,7 @@ struct baysar_model {
   ModelDev dev;
   const int64_t* I = nullptr;   // host view
   const int* ch_i = nullptr;    // host view
+  const double* ch_d = nullptr;
   const int* cl_i = nullptr;
   // workspace (grows on demand)
   int64_t cap = 0;
@@ -207,23 +208,14 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
   const int ncols = (int)(m->I[I_N_CHORDS] + m->I[I_N_PRIORS]);
   bool any = false;
   for (int c = chord_begin; c < chord_begin + n_chords; ++c) any = any || !m->ifc[c].taps_rev.empty();
-  if (!any) {
-    ChordArgs a{};
-    a.theta = theta; a.n = n; a.chord_begin = chord_begin; a.lines = lines; a.components = comps;
-    a.spectra = spectra; a.fine_pre = fine_pre; a.fine_post = fine_post; a.status = status;
-    dim3 grid((unsigned)n, (unsigned)n_chords);
-    if (launch_chord_kernel<0>(m, a, grid, m->chord_smem_max, stream)) return 1;
-    m->last_launches += 1;
-    if (mark(m, ST_CHORD, stream)) return 1;
-    return 0;
-  }
-  if (ensure_ifc_workspace(m, n)) return 1;
+  if (any && ensure_ifc_workspace(m, n)) return 1;
   for (int c = chord_begin; c < chord_begin + n_chords; ++c) {
     const IfcPlan& pl = m->ifc[c];
     const int P = m->ch_i[c * CH_I_COUNT + CH_P], F = m->ch_i[c * CH_I_COUNT + CH_F];
     if (pl.taps_rev.empty()) {
       ChordArgs a{};
-      a.theta = theta; a.n = n; a.chord_begin = c; a.lines = lines; a.components = comps;
+      chord_args_set_chord(a, m->I, m->ch_i, m->ch_d, m->cl_i, c);
+      a.theta = theta; a.n = n; a.lines = lines; a.components = comps;
       a.spectra = spectra; a.fine_pre = fine_pre; a.fine_post = fine_post; a.status = status;
       if (launch_chord_kernel<0>(m, a, dim3((unsigned)n, 1), m->chord_smem[c], stream)) return 1;
       m->last_launches += 1;
@@ -235,7 +227,8 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
       const int64_t rows128 = (rows + ifc::TILE_M - 1) / ifc::TILE_M * ifc::TILE_M;
       // K2a: spectrum -> TF32-split rows + per-theta scalars
       ChordArgs a{};
-      a.theta = theta + r0 * n_params; a.n = rows; a.chord_begin = c;
+      chord_args_set_chord(a, m->I, m->ch_i, m->ch_d, m->cl_i, c);
+      a.theta = theta + r0 * n_params; a.n = rows;
       a.lines = lines + r0 * m->I[I_N_ULINES] * BAYSAR_LINE_STRIDE;
       a.components = comps + r0 * ncols; a.spectra = nullptr;
       a.fine_pre = fine_pre ? fine_pre + r0 * F : nullptr; a.fine_post = nullptr; a.status = status + r0;
@@ -414,6 +407,7 @@ int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, con
   m->I = static_cast<const int64_t*>(host.ptr(SEC_I));
   m->ch_i = static_cast<const int*>(host.ptr(SEC_CH_I));
   m->cl_i = static_cast<const int*>(host.ptr(SEC_CL_I));
+  m->ch_d = static_cast<const double*>(host.ptr(SEC_CH_D));
   ModelDev& d = m->dev;
   d.I = static_cast<const int64_t*>(dev.ptr(SEC_I));
   d.D = static_cast<const double*>(dev.ptr(SEC_D));
@@ -465,7 +459,7 @@ int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, con
     }
     if (ch[CH_F] < 8) { baysar_model_destroy(m); return fail("fine grid shorter than 8 points"); }
     if (ch[CH_HALO] % 4 != 0) { baysar_model_destroy(m); return fail("CH_HALO must be a multiple of 4"); }
-    ChordSmem s = chord_smem_layout(ch[CH_F], ch[CH_HALO], ch[CH_TAPS_MAX], kd_max);
+    ChordSmem s = chord_smem_layout(ch[CH_F], ch[CH_HALO], ch[CH_TAPS_MAX], kd_max, 1, ch[CH_N_LINES]);
     smem_max = s.total > smem_max ? s.total : smem_max;
     m->chord_smem.push_back(s.total);
   }
@@ -507,7 +501,7 @@ int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, con
         int kd = m->cl_i[(ch[CH_LINE_OFF] + k) * CL_I_COUNT + CL_KD];
         kd_max = kd > kd_max ? kd : kd_max;
       }
-      m->chord_smem[c] = chord_smem_layout(ch[CH_F], ch[CH_HALO], ch[CH_TAPS_MAX], kd_max, 0).total;
+      m->chord_smem[c] = chord_smem_layout(ch[CH_F], ch[CH_HALO], ch[CH_TAPS_MAX], kd_max, 0, ch[CH_N_LINES]).total;
     }
     if (ch[CH_CALWAVE_IDX] < 0) {  // static wavelength map: the pixel stage reads columns i_p and i_p + 1 only
       IfcPlan& plw = m->ifc[c];

@@ -26,15 +26,15 @@
 // Doppler taps are kept while exp(-z^2/2) >= 4.6e-11 of the central tap: next to a Stark profile the neglected taps
 // change a fine-grid sample by < 1.5e-8 relative (adjacent samples differ by at most ~10^2.5), below float32 resolution.
 #define BAYSAR_Z_CUT_DOPPLER 6.9
-#define BAYSAR_MAX_FUSED_LINES 8
+#define BAYSAR_MAX_FUSED_LINES 8    // Balmer lines per pair of fused sweeps
+#define BAYSAR_MAX_BALMER_LINES 16  // Balmer lines per chord (shape records in shared memory; checked by the model compiler)
 
 struct ChordArgs {
   const double* theta;      // [N][n_params]
   int64_t n;
-  int chord_begin;          // blockIdx.y + chord_begin = chord
   const double* lines;      // [N][n_ulines][BAYSAR_LINE_STRIDE]  (K1 output)
   double* components;       // [N][n_chords + n_priors]; this kernel fills column `chord`
-  double* spectra;          // optional [N][P] (single chord launches only)
+  double* spectra;          // optional [N][P]
   float* fine_pre;          // optional [N][F]
   float* fine_post;         // optional [N][F]
   uint32_t* status;         // [N] OR-ed
@@ -43,7 +43,34 @@ struct ChordArgs {
   int64_t split_pitch;
   int split_pad;
   double* aux;              // [N][BAYSAR_AUX_STRIDE]: pre-area, minimum, 4 float64 end outputs
+  // The chord's constant records, copied from the descriptor blob by the host (chord_args_set_chord): as kernel
+  // parameters they are constant-bank operands, where every CTA used to start with a chain of dependent global loads
+  // (model scalars -> chord record -> line records) executed by all of its threads.
+  int chord;
+  int n_params, n_ul, ncomp_cols;
+  int kd_max;               // longest Doppler tap grid of the chord's Balmer lines
+  int n_gauss_comps;        // Gaussian components of the chord's ADAS406 / X lines
+  int ch_i[CH_I_COUNT];
+  double ch_d[CH_D_COUNT];
 };
+
+// Host side: fill the constant part of ChordArgs for chord c from (host views of) the descriptor sections.
+static inline void chord_args_set_chord(ChordArgs& a, const int64_t* I, const int* ch_i_all, const double* ch_d_all,
+                                        const int* cl_i_all, int c) {
+  a.chord = c;
+  a.n_params = (int)I[I_N_PARAMS];
+  a.n_ul = (int)I[I_N_ULINES];
+  a.ncomp_cols = (int)I[I_N_CHORDS] + (int)I[I_N_PRIORS];
+  for (int k = 0; k < CH_I_COUNT; ++k) a.ch_i[k] = ch_i_all[c * CH_I_COUNT + k];
+  for (int k = 0; k < CH_D_COUNT; ++k) a.ch_d[k] = ch_d_all[c * CH_D_COUNT + k];
+  a.kd_max = 0;
+  a.n_gauss_comps = 0;
+  for (int k = 0; k < a.ch_i[CH_N_LINES]; ++k) {
+    const int* cl = cl_i_all + (a.ch_i[CH_LINE_OFF] + k) * CL_I_COUNT;
+    if (cl[CL_KD] > a.kd_max) a.kd_max = cl[CL_KD];
+    if (cl[CL_KIND] != 0) a.n_gauss_comps += cl[CL_NCOMP];
+  }
+}
 
 #define BAYSAR_AUX_STRIDE 8
 #define BAYSAR_BG_SLOT 60  // scratch slot of 10^theta_background (block_sum uses the first NV * NT / 32 <= 24 slots)
@@ -52,7 +79,8 @@ struct ChordArgs {
 struct FusedLine {
   float jc_f, r, g_r, g_e;   // grid point nearest the centre, lambda[jc] - centre, gamma_rec^2.5, gamma_exc^2.5
   float s_r, s_e, c0, c1;    // amplitudes over the profile integrals; far-field series coefficients
-  float c2, d_far;           // far field: |d| >= d_far  <=>  |d|^2.5 >= BAYSAR_FAR_RATIO * max(g_r, g_e)
+  float c2, nfar;            // far field: groups whose points are all >= nfar grid points from the centre, where
+                             // |d|^2.5 >= BAYSAR_FAR_RATIO * max(g_r, g_e) (and a three-tap Doppler kernel is a delta)
   int jL, jR;                // densely integrated window of sweep 1
   double sum_r, sum_e;       // line-of-sight integrals (recombination, excitation)
 };
@@ -65,6 +93,9 @@ struct alignas(16) GaussComp {
 #define BAYSAR_EM_STRIDE 16     // sweep 1 samples the tails at this stride (Euler-Maclaurin corrected)
 #define BAYSAR_EM_WINDOW 256    // ... outside +-this many grid points of the line centre
 #define BAYSAR_FAR_RATIO 500.f  // sweep 2: series in g / |d|^2.5 beyond this ratio (third-order term < 1e-8)
+#ifndef BAYSAR_FUSED_GPT
+#define BAYSAR_FUSED_GPT 4      // sweep 2: groups of four consecutive points a thread keeps in registers per chunk
+#endif
 
 __host__ __device__ static inline int pad_index(int i) { return i ^ ((i >> 3) & 4); }
 
@@ -75,7 +106,8 @@ struct ChordSmem {
   size_t total;        // bytes
 };
 
-__host__ __device__ static inline ChordSmem chord_smem_layout(int F, int halo, int taps_max, int kd_max, int need_b = 1) {
+__host__ __device__ static inline ChordSmem chord_smem_layout(int F, int halo, int taps_max, int kd_max, int need_b = 1,
+                                                              int n_lines = 0) {
   ChordSmem s;
   int f8 = (F + 7) / 8 * 8;
   int logical = f8 + 2 * halo + 16;
@@ -83,8 +115,8 @@ __host__ __device__ static inline ChordSmem chord_smem_layout(int F, int halo, i
   s.taps_floats = (size_t)(taps_max + 8 + 3) / 4 * 4;
   s.tapd_doubles = 2 * (size_t)kd_max + 4;
   s.total = (need_b ? 2 : 1) * s.buf_floats * sizeof(float) + s.taps_floats * sizeof(float) + s.tapd_doubles * sizeof(double) +
-            192 * sizeof(double) + 16 * sizeof(int) + 8 * BAYSAR_MAX_FUSED_LINES * sizeof(double) +
-            4 * BAYSAR_MAX_FUSED_LINES * sizeof(float);
+            192 * sizeof(double) + 16 * sizeof(int) + 8 * BAYSAR_MAX_BALMER_LINES * sizeof(double) +
+            4 * BAYSAR_MAX_BALMER_LINES * sizeof(float) + (size_t)(n_lines + 15) / 16 * 16;  // + one class byte per line
   s.total = (s.total + 15) / 16 * 16;
   return s;
 }
@@ -261,41 +293,24 @@ BAYSAR_DEV void pixel_likelihood(const ModelDev& m, const int* ch, const double*
   if (tid == 0) components[n * (int64_t)ncomp_cols + c] = -red4[0];
 }
 
-// Sweep 2 of the fused narrow-Doppler passes for two fine-grid points (packed): v2 += wt * (s_r / (a + g_r) + s_e / (a + g_e)),
-// a = |d|^2.5 at the grid offsets kf2 from the line centre; far field as a three-term series through the packed FP32
-// pipe, the exact form next to the centre.  WEIGHTED = false: wt2 == (1, 1) (single-tap lines).
-template <bool WEIGHTED>
-BAYSAR_DEV void fused_pair_eval(f32x2 kf2, f32x2& v2, const float4& cst, const float4& ser, const float2& far, f32x2 c0p,
-                                f32x2 mc1p, f32x2 c2p, f32x2 dhi2, f32x2 dlo2, f32x2 r2, f32x2 wt2) {
+// Sweep 2 of the fused narrow-Doppler passes.  Far field, two fine-grid points (packed FP32 pipe, fma.rn.f32x2):
+// v2 += s_r / (a + g_r) + s_e / (a + g_e) as the three-term series ia (c0 - ia (c1 - ia c2)), ia = 1 / a = rsqrt(|d|)^5,
+// a = |d|^2.5 at the grid offsets kf2 from the line centre (one MUFU op per point instead of two).
+BAYSAR_DEV void stark_far2(f32x2 kf2, f32x2& v2, f32x2 dhi2, f32x2 dlo2, f32x2 r2, f32x2 c0p, f32x2 mc1p, f32x2 c2p) {
   const f32x2 d2 = fma2(kf2, dhi2, fma2(kf2, dlo2, r2));
   float dx, dy;
   unpack2(d2, dx, dy);
-  dx = fabsf(dx); dy = fabsf(dy);
-  if (dx >= far.y && dy >= far.y) {
-    const f32x2 rs = pack2(rsqrt_approx(dx), rsqrt_approx(dy));
-    const f32x2 rs2 = mul2(rs, rs);
-    f32x2 ia = mul2(mul2(rs2, rs2), rs);
-    const f32x2 poly = fma2(ia, fma2(ia, c2p, mc1p), c0p);
-    if (WEIGHTED) ia = mul2(ia, wt2);
-    v2 = fma2(ia, poly, v2);   // ia (c0 - ia (c1 - ia c2))
-  } else {
-    float vx, vy, wx = 1.f, wy = 1.f;
-    unpack2(v2, vx, vy);
-    if (WEIGHTED) unpack2(wt2, wx, wy);
-    {
-      const float a25 = dx * dx * sqrt_approx(dx);
-      const float dr = a25 + cst.z, de = a25 + cst.w;
-      const float num = fmaf(ser.x, de, ser.y * dr);
-      vx = fmaf(WEIGHTED ? num * wx : num, rcp_approx(dr * de), vx);
-    }
-    {
-      const float a25 = dy * dy * sqrt_approx(dy);
-      const float dr = a25 + cst.z, de = a25 + cst.w;
-      const float num = fmaf(ser.x, de, ser.y * dr);
-      vy = fmaf(WEIGHTED ? num * wy : num, rcp_approx(dr * de), vy);
-    }
-    v2 = pack2(vx, vy);
-  }
+  const f32x2 rs = pack2(rsqrt_approx(fabsf(dx)), rsqrt_approx(fabsf(dy)));
+  const f32x2 rs2 = mul2(rs, rs);
+  const f32x2 ia = mul2(mul2(rs2, rs2), rs);
+  v2 = fma2(ia, fma2(ia, fma2(ia, c2p, mc1p), c0p), v2);
+}
+// The exact form next to the line centre, one point: kf grid points from the centre.
+BAYSAR_DEV float stark_exact(float kf, float d_hi, float d_lo, float r, float g_r, float g_e, float s_r, float s_e) {
+  const float d = fabsf(fmaf(kf, d_hi, fmaf(kf, d_lo, r)));
+  const float a25 = d * d * sqrt_approx(d);
+  const float dr = a25 + g_r, de = a25 + g_e;
+  return fmaf(s_r, de, s_e * dr) * rcp_approx(dr * de);
 }
 
 // MINB = resident CTAs per SM the register allocation aims at: 3 (80 registers) when the shared-memory footprint allows
@@ -314,26 +329,21 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
 #endif
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n = blockIdx.x;
-  const int c = a.chord_begin + blockIdx.y;
-  const int64_t* I = m.I;
-  const int n_params = (int)I[I_N_PARAMS], n_ul = (int)I[I_N_ULINES];
-  const int ncomp_cols = (int)I[I_N_CHORDS] + (int)I[I_N_PRIORS];
-  const int* ch = m.ch_i + c * CH_I_COUNT;
-  const double* chd = m.ch_d + c * CH_D_COUNT;
+  const int c = a.chord;
+  const int n_params = a.n_params, n_ul = a.n_ul;
+  const int ncomp_cols = a.ncomp_cols;
+  const int* ch = a.ch_i;       // kernel parameters: constant-bank operands
+  const double* chd = a.ch_d;
   const int F = ch[CH_F], HALO = ch[CH_HALO], TAPS_MAX = ch[CH_TAPS_MAX];
   const double x0 = chd[CH_X0], delta = chd[CH_DELTA], dl = chd[CH_DL];
   const double* th = a.theta + n * n_params;
   const double* lines_n = a.lines + n * (int64_t)n_ul * BAYSAR_LINE_STRIDE;
 
   // ---- shared memory carve-up (must match chord_smem_layout)
-  int kd_max = 0;
-  for (int k = 0; k < ch[CH_N_LINES]; ++k) {
-    int kd = m.cl_i[(ch[CH_LINE_OFF] + k) * CL_I_COUNT + CL_KD];
-    kd_max = kd > kd_max ? kd : kd_max;
-  }
+  const int kd_max = a.kd_max;
   // buffer B (scratch / convolved spectrum) is left out when the tensor-core path's spectral stage cannot need it
   const bool need_b = MODE == 0 || ch[CH_B_OPTIONAL] == 0;
-  const ChordSmem lay = chord_smem_layout(F, HALO, TAPS_MAX, kd_max, need_b ? 1 : 0);
+  const ChordSmem lay = chord_smem_layout(F, HALO, TAPS_MAX, kd_max, need_b ? 1 : 0, ch[CH_N_LINES]);
   const int f8 = (F + 7) / 8 * 8;
   float* bufA = reinterpret_cast<float*>(chord_smem_raw);
   float* bufB = bufA + lay.buf_floats;
@@ -342,20 +352,83 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
   double* tappre = tapd + kd_max;
   double* scratch = tappre + kd_max + 4;  // 192 doubles: [0,128) block_sum (up to 16 values x 8 warps), [128,132) edge64
   int* iscr = reinterpret_cast<int*>(scratch + 192);  // 16 ints
-  // constants of the Balmer lines handled by the fused narrow-Doppler passes (BAYSAR_MAX_FUSED_LINES x 64 bytes)
-  FusedLine* fl = reinterpret_cast<FusedLine*>(iscr + 16);
+  // constants of the Balmer lines handled by the fused narrow-Doppler passes (BAYSAR_MAX_BALMER_LINES x 64 bytes, slot =
+  // rank of the line among the chord's Balmer lines); a pair of sweeps covers the slots [fb, fb + nf)
+  FusedLine* fl_all = reinterpret_cast<FusedLine*>(iscr + 16);
   // Doppler taps of the fused lines, normalised to sum 1: weights of stark[j - 1], stark[j], stark[j + 1]; [3] != 0 marks
   // a three-tap line (the Doppler kernel of a cold neutral on a fine grid: central tap + two ~1e-7 neighbours)
-  float* fw = reinterpret_cast<float*>(fl + BAYSAR_MAX_FUSED_LINES);
+  float* fw_all = reinterpret_cast<float*>(fl_all + BAYSAR_MAX_BALMER_LINES);
+  // class of every line object, decided once by one thread per line (parallel across lines) before the serial loop over
+  // the lines: 0 not a Balmer line, 1 single Doppler tap, 3 three taps, 2 multi-tap
+  unsigned char* line_class = reinterpret_cast<unsigned char*>(fw_all + 4 * BAYSAR_MAX_BALMER_LINES);
   double* edge64 = scratch + 128;
 #define A_AT(j) bufA[pad_index(HALO + (j))]
 #define B_AT(j) bufB[pad_index(HALO + (j))]
 
   uint32_t st = 0;
-  for (size_t i = tid; i < lay.buf_floats; i += NT) bufA[i] = 0.f;
+  if (need_b) {
+    for (size_t i = tid; i < lay.buf_floats; i += NT) bufA[i] = 0.f;
+  } else {
+    // only Balmer lines in the fused passes, whose last pass writes every group of four points: zero the haloes only
+    const int interior_end = HALO + 4 * ((F + 3) >> 2);
+    for (int i = tid; i < HALO; i += NT) bufA[pad_index(i)] = 0.f;
+    for (int i = interior_end + tid; i < (int)lay.buf_floats; i += NT) bufA[pad_index(i)] = 0.f;
+  }
   if (need_b) {
     for (int i = tid; i < HALO; i += NT) bufB[pad_index(i)] = 0.f;                       // left halo of B
     for (int i = HALO + F + tid; i < (int)lay.buf_floats; i += NT) bufB[pad_index(i)] = 0.f;  // tail + right halo of B
+  }
+  // ---- class of every Balmer line (block-uniform control flow below reads it back): the tap at the "same"-alignment
+  // centre is inside the Doppler cut and either its neighbours are not (single tap), or they are and the next ones are
+  // not (three taps); anything else takes the multi-tap path
+  for (int k = tid; k < ch[CH_N_LINES]; k += NT) {
+    const int* cl = m.cl_i + (ch[CH_LINE_OFF] + k) * CL_I_COUNT;
+    unsigned char cls = 0;
+    if (cl[CL_KIND] == 0) {
+      const double* cld = m.cl_d + (ch[CH_LINE_OFF] + k) * CL_D_COUNT;
+      const double* rec = lines_n + cl[CL_ULINE] * BAYSAR_LINE_STRIDE;
+      const double cwl = rec[13], sigma = rec[14];
+      const int KD = cl[CL_KD], o = (KD - 1) / 2;
+      const double dshift = cwl - cld[CL_CWL0];
+      double zc[5];
+      const double zlim = BAYSAR_Z_CUT_DOPPLER * sigma;
+#pragma unroll
+      for (int t = 0; t < 5; ++t) {
+        const double xk = __dadd_rn(cld[CL_DOP_START], __dmul_rn((double)(o - 2 + t), cld[CL_DOP_DELTA]));
+        zc[t] = fabs((xk + dshift) - cwl);
+      }
+      const bool one_tap = KD >= 3 && zc[2] <= zlim && zc[1] > zlim && zc[3] > zlim;
+      const bool three_taps = FUSED3 && KD >= 5 && zc[2] <= zlim && zc[1] <= zlim && zc[3] <= zlim && zc[0] > zlim && zc[4] > zlim;
+      cls = one_tap ? 1 : (three_taps ? 3 : 2);
+      if (!(sigma > 0.0)) st |= 1u << 5;
+      if (cls != 2) {
+        // shape record of a fused line: lambda_j - centre = (j - jc) delta + r with jc the grid point nearest the centre
+        const double c0 = x0 - cwl;
+        const int jc = (int)rint(-c0 / delta);
+        FusedLine& L = fl_all[cl[CL_BRANK]];
+        L.jc_f = (float)jc; L.r = (float)fma((double)jc, delta, c0); L.g_r = (float)rec[11]; L.g_e = (float)rec[12];
+        L.sum_r = rec[0]; L.sum_e = rec[1];
+        int jL = jc - BAYSAR_EM_WINDOW, jR = jc + BAYSAR_EM_WINDOW;
+        jL = jL < 0 ? 0 : (jL > F - 1 ? F - 1 : jL);
+        jR = jR < 0 ? 0 : (jR > F - 1 ? F - 1 : jR);
+        if (jL > 0) jL -= jL % BAYSAR_EM_STRIDE;                    // both tails: a whole number of strides
+        if (jR < F - 1) jR += (F - 1 - jR) % BAYSAR_EM_STRIDE;
+        L.jL = jL; L.jR = jR;
+        float* w = fw_all + 4 * cl[CL_BRANK];
+        if (three_taps) {
+          // out[j] = g[o - 1] stark[j + 1] + g[o] stark[j] + g[o + 1] stark[j - 1], normalised by the tap sum (the
+          // trapz of the convolved profile is the tap sum times the trapz of the Stark profile up to ~1e-12: the
+          // end-point terms are g[o +- 1] / g[o] ~ 1e-7 times the far wing)
+          const double gm = exp(-0.5 * (zc[1] / sigma) * (zc[1] / sigma)), g0 = exp(-0.5 * (zc[2] / sigma) * (zc[2] / sigma)),
+                       gp = exp(-0.5 * (zc[3] / sigma) * (zc[3] / sigma));
+          const double gs = gm + g0 + gp;
+          w[0] = (float)(gp / gs); w[1] = (float)(g0 / gs); w[2] = (float)(gm / gs); w[3] = 1.f;
+        } else {
+          w[0] = 0.f; w[1] = 1.f; w[2] = 0.f; w[3] = 0.f;
+        }
+      }
+    }
+    line_class[k] = cls;
   }
   __syncthreads();
 
@@ -370,23 +443,26 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
   // Stark (x) delta = Stark: no convolution, no stash; ALL such lines share two sweeps over the grid and one block
   // reduction: sweep 1 integrates u_rec / u_exc of every line (trapz, half weights at the ends), sweep 2 adds
   // sum_b (rec_sum_b u_rec_b / I_rec_b + exc_sum_b u_exc_b / I_exc_b) to the spectrum.
-  int nf = 0;
+  int nf = 0, fb = 0;  // lines of the current pair of sweeps: shape-record slots [fb, fb + nf)
   // accumulated by the LAST fused pass (which then also owns the pre-convolution area / minimum and, in MODE 1, the
   // hand-over of the spectrum) or by the separate pass further down
   float pre_f = 0.f;
   float mn = 3.402823466e38f;
   int bad = 0;
   bool pre_done = false;
+  // buffer A holds something other than zeros (Gaussian components, an earlier group of lines): block-uniform
+  bool a_dirty = false;
   auto flush_fused = [&](const bool final_pass) {
-    __syncthreads();  // constants written by thread 0
+    FusedLine* fl = fl_all + fb;
+    float* fw = fw_all + 4 * fb;
     // ---- sweep 1: I_rec, I_exc = trapz of the two Stark profiles of every line over the whole grid.
     // Only a window of +-BAYSAR_EM_WINDOW points around the line centre is summed point by point; on the two tails,
     // where 1 / (|d|^2.5 + g) is smooth on the scale of the grid, every BAYSAR_EM_STRIDE-th point is sampled and the
     // difference between the coarse and the fine trapezoid is restored from the Euler-Maclaurin expansion
     //   T_1[a,b] = T_s[a,b] - (s^2 - 1)/12 (f1(b) - f1(a)) + (s^4 - 1)/720 (f3(b) - f3(a)) - ...
     // (f1, f3: first and third derivative per grid index; relative error of the integral < 1e-8 for every width
-    // and centre, checked in tests/test_kernel_model.py).  Per-warp partial sums go to shared memory; one barrier
-    // serves all lines.
+    // and centre, checked in tests/test_kernel_model.py).  Two branch-free loops per line (window, both tails); per-warp
+    // partial sums go to shared memory; one barrier serves all lines.
     constexpr int S = BAYSAR_EM_STRIDE;
     for (int b = 0; b < nf; ++b) {
       const float4 cst = *reinterpret_cast<const float4*>(&fl[b].jc_f);  // jc, r, gamma_rec^2.5, gamma_exc^2.5
@@ -395,11 +471,7 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
       const int n_lt = jL > 0 ? jL / S + 1 : 0;
       const int n_rt = jR < F - 1 ? (F - 1 - jR) / S + 1 : 0;
       float sr = 0.f, se = 0.f;
-      for (int t = tid; t < n_c + n_lt + n_rt; t += NT) {
-        int j; float w;
-        if (t < n_c) { j = jL + t; w = (t == 0 || t == n_c - 1) ? (n_c == 1 ? 0.f : 0.5f) : 1.f; }
-        else if (t < n_c + n_lt) { const int q = t - n_c; j = q * S; w = (q == 0 || q == n_lt - 1) ? 0.5f * S : (float)S; }
-        else { const int q = t - n_c - n_lt; j = jR + q * S; w = (q == 0 || q == n_rt - 1) ? 0.5f * S : (float)S; }
+      auto sample = [&](const int j, const float w) {
         const float kf = (float)j - cst.x;
         const float d = fabsf(fmaf(kf, d_hi, fmaf(kf, d_lo, cst.y)));
         const float a25 = d * d * sqrt_approx(d);
@@ -407,108 +479,178 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
         const float inv = w * rcp_approx(dr * de);
         sr = fmaf(de, inv, sr);
         se = fmaf(dr, inv, se);
+      };
+      const float w_end = n_c == 1 ? 0.f : 0.5f;
+      for (int t = tid; t < n_c; t += NT) sample(jL + t, (t == 0 || t == n_c - 1) ? w_end : 1.f);
+      for (int t = tid; t < n_lt + n_rt; t += NT) {
+        const bool left = t < n_lt;
+        const int q = left ? t : t - n_lt, nq = left ? n_lt : n_rt;
+        sample((left ? 0 : jR) + q * S, (q == 0 || q == nq - 1) ? 0.5f * S : (float)S);
       }
       const double wr = warp_sum((double)sr), we = warp_sum((double)se);
       if (lane == 0) { scratch[(2 * b) * (NT / 32) + warp] = wr; scratch[(2 * b + 1) * (NT / 32) + warp] = we; }
     }
     __syncthreads();
-    // one thread per (line, recombination / excitation): integral, Euler-Maclaurin end terms, amplitude
-    if (tid < 2 * nf) {
-      FusedLine& L = fl[tid >> 1];
-      const int q = tid & 1;
-      double integ = 0.0;
+    if (warp == 0) {
+      // one thread per (line, recombination / excitation): integral, Euler-Maclaurin end terms, amplitude
+      if (tid < 2 * nf) {
+        FusedLine& L = fl[tid >> 1];
+        const int q = tid & 1;
+        double integ = 0.0;
 #pragma unroll
-      for (int w = 0; w < NT / 32; ++w) integ += scratch[tid * (NT / 32) + w];
-      // the end terms are ~1e-6 of the integral: float32 with approximate reciprocals is ample
-      const float g = q == 0 ? L.g_r : L.g_e;
-      const float c1 = (float)(S * S - 1) / 12.f, c3 = ((float)S * S * S * S - 1.f) / 720.f;
-      const float df = (float)delta;
-      float corr = 0.f;
+        for (int w = 0; w < NT / 32; ++w) integ += scratch[tid * (NT / 32) + w];
+        // the end terms are ~1e-6 of the integral: float32 with approximate reciprocals is ample
+        const float g = q == 0 ? L.g_r : L.g_e;
+        const float c1 = (float)(S * S - 1) / 12.f, c3 = ((float)S * S * S * S - 1.f) / 720.f;
+        const float df = (float)delta;
+        float corr = 0.f;
 #pragma unroll
-      for (int side = 0; side < 2; ++side) {
-        const int ja = side == 0 ? 0 : L.jR, jb = side == 0 ? L.jL : F - 1;
-        if (jb > ja) {
-          float f1[2], f3[2];
-          float sgn = 1.f;
+        for (int side = 0; side < 2; ++side) {
+          const int ja = side == 0 ? 0 : L.jR, jb = side == 0 ? L.jL : F - 1;
+          if (jb > ja) {
+            float f1[2], f3[2];
+            float sgn = 1.f;
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float xs = ((float)(e == 0 ? ja : jb) - L.jc_f) * df + L.r;
-            if (e == 0) sgn = xs > 0.f ? 1.f : -1.f;
-            const float x = fabsf(xs), sq = sqrt_approx(x);
-            const float D1 = 2.5f * x * sq, D2 = 3.75f * sq, D3 = 1.875f * rcp_approx(sq);
-            const float iD = rcp_approx(x * x * sq + g), iD2 = iD * iD;
-            f1[e] = -D1 * iD2;
-            f3[e] = -D3 * iD2 + 6.f * D1 * D2 * iD2 * iD - 6.f * D1 * D1 * D1 * iD2 * iD2;
+            for (int e = 0; e < 2; ++e) {
+              const float xs = ((float)(e == 0 ? ja : jb) - L.jc_f) * df + L.r;
+              if (e == 0) sgn = xs > 0.f ? 1.f : -1.f;
+              const float x = fabsf(xs), sq = sqrt_approx(x);
+              const float D1 = 2.5f * x * sq, D2 = 3.75f * sq, D3 = 1.875f * rcp_approx(sq);
+              const float iD = rcp_approx(x * x * sq + g), iD2 = iD * iD;
+              f1[e] = -D1 * iD2;
+              f3[e] = -D3 * iD2 + 6.f * D1 * D2 * iD2 * iD - 6.f * D1 * D1 * D1 * iD2 * iD2;
+            }
+            corr += sgn * (-c1 * df * (f1[1] - f1[0]) + c3 * df * df * df * (f3[1] - f3[0]));
           }
-          corr += sgn * (-c1 * df * (f1[1] - f1[0]) + c3 * df * df * df * (f3[1] - f3[0]));
         }
+        integ += (double)corr;
+        const double amp = (q == 0 ? L.sum_r : L.sum_e) / (dl * integ) / cal;
+        if (!(amp - amp == 0.0)) atomicOr(&a.status[n], 1u << 6);
+        (q == 0 ? L.s_r : L.s_e) = (float)amp;
       }
-      integ += (double)corr;
-      const double amp = (q == 0 ? L.sum_r : L.sum_e) / (dl * integ) / cal;
-      if (!(amp - amp == 0.0)) atomicOr(&a.status[n], 1u << 6);
-      (q == 0 ? L.s_r : L.s_e) = (float)amp;
+      __syncwarp();  // both amplitudes of a line come from neighbouring lanes of this warp
+      if (tid < nf) {
+        // sweep-2 constants: exact form next to the centre, far-field series
+        //   s_r / (a + g_r) + s_e / (a + g_e) = (1/a) (c0 - (1/a) (c1 - (1/a) c2)) + O((g/a)^3),  a = |d|^2.5
+        FusedLine& L = fl[tid];
+        L.c0 = L.s_r + L.s_e;
+        L.c1 = L.s_r * L.g_r + L.s_e * L.g_e;
+        L.c2 = L.s_r * L.g_r * L.g_r + L.s_e * L.g_e * L.g_e;
+        const float gmax = L.g_r > L.g_e ? L.g_r : L.g_e;
+        // |d| >= d_far for every point of a group of four whose nearest point is nfar grid points from the centre
+        // (|r| <= delta / 2)
+        const float d_far = exp2f(0.4f * log2f(BAYSAR_FAR_RATIO * gmax)) * 1.0001f;
+        float nfar = d_far / (float)delta + 0.5f;
+        // Three Doppler taps (w-, w0, w+ ~ 1e-6, normalised): far from the centre the Stark profile S is smooth on the scale
+        // of the grid and  w- S(j-1) + w0 S(j) + w+ S(j+1) = S(j) + (w+ - w-) S' + (w+ + w-) S''/2 + ...  with
+        // |S'/S| <= 2.5 / k and |S''/S| <= 8.75 / k^2 at k grid points from the centre: beyond the k where both terms drop
+        // below 1e-9 the kernel is a delta (one evaluation per point instead of three)
+        const float* w = fw + 4 * tid;
+        if (FUSED3 && w[3] != 0.f) {
+          const float wsum = w[0] + w[2], wdif = fabsf(w[2] - w[0]);
+          const float n2 = sqrt_approx(4.375f * wsum * 1e9f), n1 = 2.5f * wdif * 1e9f;
+          const float n3 = (n2 > n1 ? n2 : n1) + 2.f;
+          nfar = nfar > n3 ? nfar : n3;
+        }
+        L.nfar = nfar;
+      }
     }
     __syncthreads();
-    if (tid < nf) {
-      // sweep-2 constants: exact form next to the centre, far-field series
-      //   s_r / (a + g_r) + s_e / (a + g_e) = (1/a) (c0 - (1/a) (c1 - (1/a) c2)) + O((g/a)^3),  a = |d|^2.5
-      FusedLine& L = fl[tid];
-      L.c0 = L.s_r + L.s_e;
-      L.c1 = L.s_r * L.g_r + L.s_e * L.g_e;
-      L.c2 = L.s_r * L.g_r * L.g_r + L.s_e * L.g_e * L.g_e;
-      const float gmax = L.g_r > L.g_e ? L.g_r : L.g_e;
-      L.d_far = exp2f(0.4f * log2f(BAYSAR_FAR_RATIO * gmax)) * 1.0001f;
-    }
-    __syncthreads();
-    // ---- sweep 2, four points per thread and line: spectrum += sum_b (s_rec_b / den_rec + s_exc_b / den_exc).
-    // Far-field points go two at a time through the packed FP32 pipe (fma.rn.f32x2): one issue slot per two FMAs.
+    // ---- sweep 2: spectrum += sum_b (s_rec_b / den_rec + s_exc_b / den_exc).  Every thread owns GPT groups of four
+    // CONSECUTIVE fine-grid points per chunk (group g = chunk base + tid + i NT) and keeps their sums in registers while it
+    // loops over the lines, so that the line constants are read once per line and thread, the result leaves as one
+    // 128-bit shared-memory store (and one 128-bit global store in MODE 1) per group, and the far / near decision is one
+    // test per group on the integer distance to the line centre.  Far-field points go two at a time through the packed
+    // FP32 pipe (fma.rn.f32x2).
+    constexpr int GPT = BAYSAR_FUSED_GPT;
     float* sp = (MODE == 1) ? a.spec + n * a.split_pitch + a.split_pad : nullptr;
     const f32x2 dhi2 = pack2(d_hi, d_hi), dlo2 = pack2(d_lo, d_lo);
-    for (int jb = tid; jb < F; jb += 4 * NT) {
-      f32x2 v01 = pack2(0.f, 0.f), v23 = pack2(0.f, 0.f);
-      const f32x2 jf01 = pack2((float)jb, (float)(jb + NT)), jf23 = pack2((float)(jb + 2 * NT), (float)(jb + 3 * NT));
-      for (int b = 0; b < nf; ++b) {
-        const float4 cst = *reinterpret_cast<const float4*>(&fl[b].jc_f);
-        const float4 ser = *reinterpret_cast<const float4*>(&fl[b].s_r);   // s_r, s_e, c0, c1
-        const float2 far = *reinterpret_cast<const float2*>(&fl[b].c2);    // c2, d_far
-        const f32x2 mjc2 = pack2(-cst.x, -cst.x), r2 = pack2(cst.y, cst.y);
-        const f32x2 c0p = pack2(ser.z, ser.z), mc1p = pack2(-ser.w, -ser.w), c2p = pack2(far.x, far.x);
-        const float4 w4 = *reinterpret_cast<const float4*>(fw + 4 * b);
+    const int n_groups = (F + 3) >> 2;
+    for (int gbase = 0; gbase < n_groups; gbase += GPT * NT) {
+      f32x2 v01[GPT], v23[GPT];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          f32x2& v2 = h == 0 ? v01 : v23;
-          const f32x2 kf2 = add2(h == 0 ? jf01 : jf23, mjc2);
-          if (!FUSED3 || w4.w == 0.f) {
-            fused_pair_eval<false>(kf2, v2, cst, ser, far, c0p, mc1p, c2p, dhi2, dlo2, r2, pack2(1.f, 1.f));
-          } else {  // three Doppler taps: Stark profile at j - 1, j, j + 1; the taps past the two grid ends are zero
-                    // padding ("same" convolution), which matters when a line sits at the end of the chord
-            const int jx = jb + 2 * h * NT, jy = jx + NT;
-            fused_pair_eval<true>(add2(kf2, pack2(-1.f, -1.f)), v2, cst, ser, far, c0p, mc1p, c2p, dhi2, dlo2, r2,
-                                  pack2(jx > 0 ? w4.x : 0.f, jy > 0 ? w4.x : 0.f));
-            fused_pair_eval<true>(kf2, v2, cst, ser, far, c0p, mc1p, c2p, dhi2, dlo2, r2, pack2(w4.y, w4.y));
-            fused_pair_eval<true>(add2(kf2, pack2(1.f, 1.f)), v2, cst, ser, far, c0p, mc1p, c2p, dhi2, dlo2, r2,
-                                  pack2(jx < F - 1 ? w4.z : 0.f, jy < F - 1 ? w4.z : 0.f));
+      for (int i = 0; i < GPT; ++i) { v01[i] = pack2(0.f, 0.f); v23[i] = pack2(0.f, 0.f); }
+      for (int b = 0; b < nf; ++b) {
+        const float4 cst = *reinterpret_cast<const float4*>(&fl[b].jc_f);  // jc, r, gamma_rec^2.5, gamma_exc^2.5
+        const float4 ser = *reinterpret_cast<const float4*>(&fl[b].s_r);   // s_r, s_e, c0, c1
+        const float2 cf = *reinterpret_cast<const float2*>(&fl[b].c2);     // c2, nfar
+        const f32x2 r2 = pack2(cst.y, cst.y);
+        const f32x2 c0p = pack2(ser.z, ser.z), mc1p = pack2(-ser.w, -ser.w), c2p = pack2(cf.x, cf.x);
+        const float4 w4 = *reinterpret_cast<const float4*>(fw + 4 * b);
+        const bool three = FUSED3 && w4.w != 0.f;
+#pragma unroll
+        for (int i = 0; i < GPT; ++i) {
+          const int g = gbase + tid + i * NT;
+          if (g >= n_groups) continue;
+          const float kf0 = (float)(4 * g) - cst.x;
+          // a three-tap line keeps the exact form in the first and the last group: the taps past the two grid ends are
+          // zero padding ("same" convolution)
+          const bool far = (kf0 >= cf.y || kf0 + 3.f <= -cf.y) && !(three && (g == 0 || g == n_groups - 1));
+          if (far) {
+            stark_far2(pack2(kf0, kf0 + 1.f), v01[i], dhi2, dlo2, r2, c0p, mc1p, c2p);
+            stark_far2(pack2(kf0 + 2.f, kf0 + 3.f), v23[i], dhi2, dlo2, r2, c0p, mc1p, c2p);
+          } else {
+            float o[4];
+            if (!three) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) o[k] = stark_exact(kf0 + (float)k, d_hi, d_lo, cst.y, cst.z, cst.w, ser.x, ser.y);
+            } else {
+              // out[j] = w.x S(j - 1) + w.y S(j) + w.z S(j + 1); S vanishes outside the grid
+              float sv[6];
+#pragma unroll
+              for (int k = 0; k < 6; ++k) {
+                const int j = 4 * g - 1 + k;
+                const float val = stark_exact(kf0 + (float)(k - 1), d_hi, d_lo, cst.y, cst.z, cst.w, ser.x, ser.y);
+                sv[k] = (j >= 0 && j < F) ? val : 0.f;
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) o[k] = fmaf(w4.x, sv[k], fmaf(w4.y, sv[k + 1], w4.z * sv[k + 2]));
+            }
+            v01[i] = add2(v01[i], pack2(o[0], o[1]));
+            v23[i] = add2(v23[i], pack2(o[2], o[3]));
           }
         }
       }
-      float v[4];
-      unpack2(v01, v[0], v[1]);
-      unpack2(v23, v[2], v[3]);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = jb + u * NT;
-        if (j < F) {
-          const float val = A_AT(j) + v[u];
-          A_AT(j) = val;
-          if (final_pass) {  // pre-convolution area / minimum (spectrometers.py:256, :271) and MODE 1 hand-over
-            pre_f += (j == 0 || j == F - 1) ? 0.5f * val : val;
-            mn = val < mn ? val : mn;
-            if (!(val - val == 0.f)) bad = 1;
-            if (MODE == 1) sp[j] = val;
+      for (int i = 0; i < GPT; ++i) {
+        const int g = gbase + tid + i * NT;
+        if (g >= n_groups) continue;
+        const int j = 4 * g;
+        float v[4];
+        unpack2(v01[i], v[0], v[1]);
+        unpack2(v23[i], v[2], v[3]);
+        float4* ap = reinterpret_cast<float4*>(bufA + pad_index(HALO + j));  // HALO and j are multiples of 4
+        if (a_dirty) {
+          const float4 prev = *ap;
+          v[0] += prev.x; v[1] += prev.y; v[2] += prev.z; v[3] += prev.w;
+        }
+        if (j + 3 >= F) {  // last group of a grid that is not a multiple of four: the alignment tail stays zero
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (j + k >= F) v[k] = 0.f;
+        }
+        *ap = make_float4(v[0], v[1], v[2], v[3]);
+        if (final_pass) {  // pre-convolution area / minimum (spectrometers.py:256, :271) and MODE 1 hand-over
+          const float s4 = (v[0] + v[1]) + (v[2] + v[3]);
+          pre_f += s4;
+          if (!(s4 - s4 == 0.f)) bad = 1;
+          if (j == 0) pre_f -= 0.5f * v[0];
+          if (j + 3 >= F - 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (j + k == F - 1) pre_f -= 0.5f * v[k];
+              if (j + k < F) mn = v[k] < mn ? v[k] : mn;
+            }
+          } else {
+            const float m01 = v[0] < v[1] ? v[0] : v[1], m23 = v[2] < v[3] ? v[2] : v[3];
+            const float m4 = m01 < m23 ? m01 : m23;
+            mn = m4 < mn ? m4 : mn;
           }
+          if (MODE == 1) *reinterpret_cast<float4*>(sp + j) = make_float4(v[0], v[1], v[2], v[3]);
         }
       }
     }
+    a_dirty = true;
     if (final_pass) pre_done = true;
     __syncthreads();  // the constants may be overwritten by the next group
     nf = 0;
@@ -522,11 +664,7 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
   {
     GaussComp* gc = reinterpret_cast<GaussComp*>(bufB + ((HALO + 7) & ~7));
     const int gcap = (((HALO + F) & ~7) - ((HALO + 7) & ~7)) * (int)sizeof(float) / (int)sizeof(GaussComp);
-    int total = 0;
-    for (int k = 0; k < ch[CH_N_LINES]; ++k) {
-      const int* cl = m.cl_i + (ch[CH_LINE_OFF] + k) * CL_I_COUNT;
-      if (cl[CL_KIND] != 0) total += cl[CL_NCOMP];
-    }
+    const int total = a.n_gauss_comps;
     for (int base = 0; base < total; base += gcap) {
       const int nb = total - base < gcap ? total - base : gcap;
       for (int g = tid; g < nb; g += NT) {
@@ -585,63 +723,27 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
       }
       __syncthreads();
     }
+    if (total > 0) a_dirty = true;
   }
 
   // ================= line objects ==============================================================================
   for (int k = 0; k < ch[CH_N_LINES]; ++k) {
+    const int cls = line_class[k];
+    if (cls == 0) continue;  // Gaussian multiplets: added above
     const int* cl = m.cl_i + (ch[CH_LINE_OFF] + k) * CL_I_COUNT;
-    const double* cld = m.cl_d + (ch[CH_LINE_OFF] + k) * CL_D_COUNT;
-    const double* rec = lines_n + cl[CL_ULINE] * BAYSAR_LINE_STRIDE;
-    const int kind = cl[CL_KIND];
-    if (kind == 0) {
+    {
       // ---------------- Balmer line: Stark (x) Doppler ----------------
+      if (cls != 2) {  // single / three Doppler taps: its shape record is ready; consecutive ones share a pair of sweeps
+        if (nf == 0) fb = cl[CL_BRANK];
+        if (++nf == BAYSAR_MAX_FUSED_LINES) flush_fused(false);
+        continue;
+      }
+      const double* cld = m.cl_d + (ch[CH_LINE_OFF] + k) * CL_D_COUNT;
+      const double* rec = lines_n + cl[CL_ULINE] * BAYSAR_LINE_STRIDE;
       const double cwl0 = cld[CL_CWL0];
       const double cwl = rec[13], sigma = rec[14];  // shifted centre and Doppler sigma from the LOS stage
-      if (!(sigma > 0.0)) st |= 1u << 5;
       const int KD = cl[CL_KD], o = (KD - 1) / 2;
       const double dshift = cwl - cwl0;
-      {
-        // single- / three-tap test (block-uniform): the tap at the "same"-alignment centre is inside the cut and either
-        // its neighbours are not, or they are and the next ones are not
-        double zc[5];
-        const double zlim = BAYSAR_Z_CUT_DOPPLER * sigma;
-#pragma unroll
-        for (int t = 0; t < 5; ++t) {
-          double xk = __dadd_rn(cld[CL_DOP_START], __dmul_rn((double)(o - 2 + t), cld[CL_DOP_DELTA]));
-          zc[t] = fabs((xk + dshift) - cwl);
-        }
-        const bool one_tap = KD >= 3 && zc[2] <= zlim && zc[1] > zlim && zc[3] > zlim;
-        const bool three_taps = FUSED3 && KD >= 5 && zc[2] <= zlim && zc[1] <= zlim && zc[3] <= zlim && zc[0] > zlim && zc[4] > zlim;
-        if (one_tap || three_taps) {
-          if (tid == 0) {
-            const double c0 = x0 - cwl;
-            const int jc = (int)rint(-c0 / delta);
-            FusedLine& L = fl[nf];
-            L.jc_f = (float)jc; L.r = (float)fma((double)jc, delta, c0); L.g_r = (float)rec[11]; L.g_e = (float)rec[12];
-            L.sum_r = rec[0]; L.sum_e = rec[1];
-            int jL = jc - BAYSAR_EM_WINDOW, jR = jc + BAYSAR_EM_WINDOW;
-            jL = jL < 0 ? 0 : (jL > F - 1 ? F - 1 : jL);
-            jR = jR < 0 ? 0 : (jR > F - 1 ? F - 1 : jR);
-            if (jL > 0) jL -= jL % BAYSAR_EM_STRIDE;                    // both tails: a whole number of strides
-            if (jR < F - 1) jR += (F - 1 - jR) % BAYSAR_EM_STRIDE;
-            L.jL = jL; L.jR = jR;
-            float* w = fw + 4 * nf;
-            if (three_taps) {
-              // out[j] = g[o - 1] stark[j + 1] + g[o] stark[j] + g[o + 1] stark[j - 1], normalised by the tap sum (the
-              // trapz of the convolved profile is the tap sum times the trapz of the Stark profile up to ~1e-12: the
-              // end-point terms are g[o +- 1] / g[o] ~ 1e-7 times the far wing)
-              const double gm = exp(-0.5 * (zc[1] / sigma) * (zc[1] / sigma)), g0 = exp(-0.5 * (zc[2] / sigma) * (zc[2] / sigma)),
-                           gp = exp(-0.5 * (zc[3] / sigma) * (zc[3] / sigma));
-              const double gs = gm + g0 + gp;
-              w[0] = (float)(gp / gs); w[1] = (float)(g0 / gs); w[2] = (float)(gm / gs); w[3] = 1.f;
-            } else {
-              w[0] = 0.f; w[1] = 1.f; w[2] = 0.f; w[3] = 0.f;
-            }
-          }
-          if (++nf == BAYSAR_MAX_FUSED_LINES) flush_fused(false);
-          continue;
-        }
-      }
       if (nf > 0) flush_fused(false);  // keep the (float) summation order of the lines deterministic
       if (!need_b) { st |= 1u << 16; continue; }  // cannot happen: the host guarantees single-tap lines (CH_B_OPTIONAL)
       // tap window |z| <= Z_CUT
@@ -750,10 +852,14 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
       }
       __syncthreads();
       for (int j = F + tid; j < f8; j += NT) A_AT(j) = 0.f;  // keep the alignment tail clean
+      a_dirty = true;
       __syncthreads();
     }
   }
   if (nf > 0) flush_fused(true);
+  if (!need_b && !a_dirty) {  // no line wrote the interior (a chord without lines, or every line flagged): it is zero
+    for (int j = tid; j < 4 * ((F + 3) >> 2); j += NT) A_AT(j) = 0.f;
+  }
   __syncthreads();
 
   // ================= pre-convolution area and minimum (spectrometers.py:256, :271) ===============================

@@ -9,7 +9,7 @@
 #define BAYSAR_LAYOUT_H
 
 #define BAYSAR_BLOB_MAGIC 0x4252415359534142LL /* "BAYSYSAB" */
-#define BAYSAR_BLOB_VERSION 8
+#define BAYSAR_BLOB_VERSION 9
 
 enum BaysarSection {
   SEC_I,              /* int64  [I_COUNT]           model-wide integer scalars                         */
@@ -181,7 +181,17 @@ enum BaysarChD {
   CH_D_COUNT
 };
 
-enum BaysarClI { CL_KIND, CL_ULINE, CL_SPECIES, CL_NCOMP, CL_COMP_OFF, CL_KD, CL_I_COUNT };
+enum BaysarClI {
+  CL_KIND,
+  CL_ULINE,
+  CL_SPECIES,
+  CL_NCOMP,
+  CL_COMP_OFF,
+  CL_KD,
+  CL_BRANK,      /* Balmer lines: rank among the chord's Balmer lines (slot of the line's shape record in shared memory) */
+  CL_PAD,
+  CL_I_COUNT
+};
 enum BaysarClD {
   CL_CWL0,
   CL_LOMAN_A,

@@ -253,6 +253,7 @@ def compile_model(plasma, chords, priors):
         row[E_CH_I["CH_N_LINES"]] = len(chord.lines)
         kd_max = 0
         line_ulines = []
+        n_balmer = 0
         for line in chord.lines:
             ci = np.zeros(E_CL_I["CL_I_COUNT"], dtype=np.int32)
             cd = np.zeros(E_CL_D["CL_D_COUNT"])
@@ -270,6 +271,10 @@ def compile_model(plasma, chords, priors):
                 taps_needed = max(taps_needed, KD)
                 ci[E_CL_I["CL_KIND"]], ci[E_CL_I["CL_ULINE"]], ci[E_CL_I["CL_SPECIES"]] = 0, u, sp
                 ci[E_CL_I["CL_KD"]] = KD
+                ci[E_CL_I["CL_BRANK"]] = n_balmer
+                n_balmer += 1
+                if n_balmer > 16:  # BAYSAR_MAX_BALMER_LINES (csrc/chord_stage.cuh): shape records held in shared memory
+                    raise NotImplementedError("more than 16 hydrogen lines in one chord")
                 cd[E_CL_D["CL_CWL0"]] = line.cwl
                 cd[E_CL_D["CL_LOMAN_A"]], cd[E_CL_D["CL_LOMAN_B"]], cd[E_CL_D["CL_LOMAN_C"]] = line.loman_ij_abc
                 cd[E_CL_D["CL_MASS"]] = line.atomic_mass

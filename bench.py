@@ -488,6 +488,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="only the main workload's line")
     ap.add_argument("--sync-gather", action="store_true", help="N > 1: logP all-gather on the compute stream")
+    ap.add_argument("--options", default="", help="baysar_options_t fields of the main workload's model, key=value,... "
+                                                  "(kernel-selection experiments; default: the library's choices)")
     args = ap.parse_args()
 
     env = Env()
@@ -515,8 +517,9 @@ def main():
     env.peaks = runtime.microbench(env.local_rank) if env.rank == 0 else None
     parity = None if args.no_parity else (256, 16)
 
+    options = {k: int(v) for k, v in (kv.split("=") for kv in args.options.split(",") if kv)} or None
     line = run_workload(env, args.workload, batch, args.steps, args.warmup, sync_gather=args.sync_gather,
-                        scaling=args.scaling, parity=parity)
+                        scaling=args.scaling, parity=parity, options=options)
 
     # ---- further workloads (same shape of line, shorter runs, no CPU baseline)
     extras = []

@@ -46,13 +46,14 @@ extern "C" int emu_eval_split(const unsigned char* blob, const double* theta, lo
       int kd = m.cl_i[(ch[CH_LINE_OFF] + k) * CL_I_COUNT + CL_KD];
       kd_max = kd > kd_max ? kd : kd_max;
     }
-    ChordSmem s = chord_smem_layout(F, ch[CH_HALO], ch[CH_TAPS_MAX], kd_max, ch[CH_B_OPTIONAL] ? 0 : 1);
+    ChordSmem s = chord_smem_layout(F, ch[CH_HALO], ch[CH_TAPS_MAX], kd_max, ch[CH_B_OPTIONAL] ? 0 : 1, ch[CH_N_LINES]);
     const int pad = 64, n_tiles = (F + 127) / 128;
     const int64_t pitch = pad + F + 96, cpitch = (int64_t)n_tiles * 128;
     std::vector<float> spec(n * pitch, 7.f), conv(n * cpitch, 0.f);
     std::vector<double> aux(n * BAYSAR_AUX_STRIDE), part(n * n_tiles, 0.0);
     ChordArgs ca{};
-    ca.theta = theta; ca.n = n; ca.chord_begin = c; ca.lines = lines; ca.components = comps; ca.status = status;
+    chord_args_set_chord(ca, m.I, m.ch_i, m.ch_d, m.cl_i, c);
+    ca.theta = theta; ca.n = n; ca.lines = lines; ca.components = comps; ca.status = status;
     ca.spec = spec.data(); ca.split_pitch = pitch; ca.split_pad = pad; ca.aux = aux.data();
     EmuDim3 gc;
     gc.x = (unsigned)n; gc.y = 1;
@@ -113,10 +114,11 @@ extern "C" int emu_eval(const unsigned char* blob, const double* theta, long n, 
       int kd = m.cl_i[(ch[CH_LINE_OFF] + k) * CL_I_COUNT + CL_KD];
       kd_max = kd > kd_max ? kd : kd_max;
     }
-    ChordSmem s = chord_smem_layout(ch[CH_F], ch[CH_HALO], ch[CH_TAPS_MAX], kd_max);
+    ChordSmem s = chord_smem_layout(ch[CH_F], ch[CH_HALO], ch[CH_TAPS_MAX], kd_max, 1, ch[CH_N_LINES]);
     bool want = c == chord_for_spectra;
     ChordArgs ca{};
-    ca.theta = theta; ca.n = n; ca.chord_begin = c; ca.lines = lines; ca.components = comps;
+    chord_args_set_chord(ca, m.I, m.ch_i, m.ch_d, m.cl_i, c);
+    ca.theta = theta; ca.n = n; ca.lines = lines; ca.components = comps;
     ca.spectra = want ? spectra : nullptr; ca.fine_pre = want ? fine_pre : nullptr;
     ca.fine_post = want ? fine_post : nullptr; ca.status = status;
     EmuDim3 gc;
