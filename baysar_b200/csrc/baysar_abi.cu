@@ -45,6 +45,9 @@ struct baysar_model {
   int64_t split_pitch_max = 0, conv_pitch_max = 0;
   int tiles_max = 0;
   int last_launches = 3;
+  // layout (pitch, pad, fine points) of the spectra rows as the last spectral-stage launch left them, and the rows it
+  // covered: a launch with the same layout finds its zero padding in place
+  int64_t spec_pitch_last = -1; int spec_pad_last = -1, spec_f_last = -1; int64_t spec_rows_last = 0;
   baysar_options_t opt{};  // tuning options given at creation (0 = default everywhere)
   // optional per-stage timing (bench.py roofline): events tagged with the stage that ends at them.  The events are a pool
   // that only grows (first profiled calls) and is reused after every baysar_model_get_profile
@@ -148,12 +151,19 @@ int ensure_ifc_workspace(baysar_model* m, int64_t n) {
   // rows past the end of a batch are multiplied too (M = 128 granularity): keep them finite
   CUDA_OK(cudaMemset(m->spec, 0, sizeof(float) * rows * m->split_pitch_max));
   m->ifc_rows = rows;
+  m->spec_pitch_last = -1; m->spec_rows_last = 0;
   return 0;
 }
 
 // Launch the chord kernel with the register budget that matches how many CTAs the shared-memory footprint lets an SM hold
 template <int MODE>
 int launch_chord_kernel(baysar_model* m, const ChordArgs& a, dim3 grid, size_t smem, cudaStream_t stream, bool single_tap_only = false) {
+  if (m->opt.chord_threads == 128) {  // half the threads per theta: the per-thread fixed costs are paid half as often
+    auto kern = single_tap_only ? chord_stage_kernel<128, MODE, 6, false> : chord_stage_kernel<128, MODE, 6>;
+    kern<<<grid, 128, smem, stream>>>(m->dev, a);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   constexpr int NT = 256;
   const int cap = m->opt.chord_min_blocks > 0 ? m->opt.chord_min_blocks : 5;
   const int by_smem = (int)((size_t)232448 / (smem + 1024));
@@ -195,7 +205,9 @@ int set_kernel_attributes() {
       allow_max_smem(chord_stage_kernel<256, 1, 4>) || allow_max_smem(chord_stage_kernel<256, 1, 5>) ||
       allow_max_smem(chord_stage_kernel<256, 0, 3, false>) || allow_max_smem(chord_stage_kernel<256, 0, 4, false>) ||
       allow_max_smem(chord_stage_kernel<256, 0, 5, false>) || allow_max_smem(chord_stage_kernel<256, 1, 3, false>) ||
-      allow_max_smem(chord_stage_kernel<256, 1, 4, false>) || allow_max_smem(chord_stage_kernel<256, 1, 5, false>))
+      allow_max_smem(chord_stage_kernel<256, 1, 4, false>) || allow_max_smem(chord_stage_kernel<256, 1, 5, false>) ||
+      allow_max_smem(chord_stage_kernel<128, 0, 6>) || allow_max_smem(chord_stage_kernel<128, 1, 6>) ||
+      allow_max_smem(chord_stage_kernel<128, 0, 6, false>) || allow_max_smem(chord_stage_kernel<128, 1, 6, false>))
     return 1;
   return allow_max_smem(pixel_fold_kernel<128>) || contraction_kernel_attributes();
 }
@@ -203,7 +215,6 @@ int set_kernel_attributes() {
 int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_begin, int n_chords,
                   const double* lines, double* comps, double* spectra, float* fine_pre, float* fine_post,
                   uint32_t* status, cudaStream_t stream, double* logp = nullptr, bool* finalized = nullptr) {
-  constexpr int NT = 256;
   const int n_params = (int)m->I[I_N_PARAMS];
   const int ncols = (int)(m->I[I_N_CHORDS] + m->I[I_N_PRIORS]);
   bool any = false;
@@ -236,6 +247,11 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
       const bool folded = fx.on && !fine_post;  // the fine-grid diagnostic needs every convolved column
       a.spec = m->spec; a.split_pitch = folded ? fx.pitch : pl.pitch; a.split_pad = folded ? fx.pad_left : pl.pad_left;
       a.aux = m->aux;
+      // the folded pixel stage reads the float64 end outputs only when a pixel extrapolates beyond the fine grid
+      a.skip_edge64 = folded && fx.no_extrapolation ? 1 : 0;
+      a.keep_padding = (m->spec_pitch_last == a.split_pitch && m->spec_pad_last == a.split_pad && m->spec_f_last == F &&
+                        m->spec_rows_last >= rows) ? 1 : 0;
+      if (!a.keep_padding) { m->spec_pitch_last = a.split_pitch; m->spec_pad_last = a.split_pad; m->spec_f_last = F; m->spec_rows_last = rows; }
       if (launch_chord_kernel<1>(m, a, dim3((unsigned)rows, 1), m->chord_smem[c], stream,
                                  m->ch_i[c * CH_I_COUNT + CH_B_OPTIONAL] != 0))
         return 1;
@@ -249,7 +265,7 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
         pf.pix_col = fx.d_pix_col; pf.col_left0 = fx.col_left0; pf.x_l = fx.x_l; pf.col_right0 = fx.col_right0; pf.x_r = fx.x_r;
         pf.spec = m->spec; pf.spec_pitch = fx.pitch; pf.spec_pad = fx.pad_left; pf.dtab = fx.d_dtab; pf.n_dl = fx.n_dl;
         pf.n_dr = fx.n_dr; pf.wsum = fx.wsum; pf.inv_err = fx.d_inv_err; pf.tsum = m->trapz_part;
-        pf.n_col_tiles = fx.n_col_tiles; pf.n_fold_tiles = fx.n_fold_tiles; pf.tile_n = fx.tn; pf.aux = m->aux; pf.components = comps + r0 * ncols;
+        pf.use_edge64 = fx.no_extrapolation ? 0 : 1; pf.n_col_tiles = fx.n_col_tiles; pf.n_fold_tiles = fx.n_fold_tiles; pf.tile_n = fx.tn; pf.aux = m->aux; pf.components = comps + r0 * ncols;
         pf.spectra = spectra ? spectra + r0 * P : nullptr; pf.status = status + r0;
         {
           // a single-chord model gets its logP from the same kernel (no finalize launch)
@@ -529,6 +545,12 @@ int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, con
                                  pix_idx_host + ch[CH_PIX_OFF], pix_frac_host + ch[CH_PIX_OFF], pxc_tn);
       if (fx.on) {
         const double* err_host = static_cast<const double*>(host.ptr(SEC_ERR)) + ch[CH_PIX_OFF];
+        fx.no_extrapolation = true;
+        for (int px = 0; px < ch[CH_P]; ++px) {
+          const double fr = pix_frac_host[ch[CH_PIX_OFF] + px];
+          if (!(fr >= -1e-6 && fr <= 1.0 + 1e-6)) fx.no_extrapolation = false;
+        }
+        if (fx.x_l < 2 || fx.x_r < 2) fx.no_extrapolation = false;
         fx.inv_err.resize(ch[CH_P]);
         for (int px = 0; px < ch[CH_P]; ++px) fx.inv_err[px] = (float)(1.0 / err_host[px]);
         if (upload_pxc_plan(fx)) { free_pxc_plan(fx); baysar_model_destroy(m); return 1; }

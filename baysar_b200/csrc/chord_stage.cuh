@@ -43,6 +43,8 @@ struct ChordArgs {
   int64_t split_pitch;
   int split_pad;
   double* aux;              // [N][BAYSAR_AUX_STRIDE]: pre-area, minimum, 4 float64 end outputs
+  int skip_edge64;          // MODE 1: the consumer (folded pixel stage, no extrapolating pixel) does not read the float64 end outputs
+  int keep_padding;         // MODE 1: the zero padding of the spectra rows is already in place (same layout as the last writer)
   // The chord's constant records, copied from the descriptor blob by the host (chord_args_set_chord): as kernel
   // parameters they are constant-bank operands, where every CTA used to start with a chain of dependent global loads
   // (model scalars -> chord record -> line records) executed by all of its threads.
@@ -91,7 +93,7 @@ struct alignas(16) GaussComp {
   int j_lo, j_hi, pad;   // fine-grid window |z| <= BAYSAR_Z_CUT
 };
 #define BAYSAR_EM_STRIDE 16     // sweep 1 samples the tails at this stride (Euler-Maclaurin corrected)
-#define BAYSAR_EM_WINDOW 256    // ... outside +-this many grid points of the line centre
+#define BAYSAR_EM_WINDOW 240    // ... outside +-this many grid points of the line centre (window <= 512 points: two trips of 256 threads)
 #define BAYSAR_FAR_RATIO 500.f  // sweep 2: series in g / |d|^2.5 beyond this ratio (third-order term < 1e-8)
 #ifndef BAYSAR_FUSED_GPT
 #define BAYSAR_FUSED_GPT 4      // sweep 2: groups of four consecutive points a thread keeps in registers per chunk
@@ -208,6 +210,7 @@ struct FetchFolded {
   float mn;                // clip level
   const float* kappa;      // [column tiles] bias correction of the folded columns (shared memory)
   int tile_shift;          // log2 of the column tile width
+  int use_edge64;          // 0: the float64 end outputs were not formed (no pixel extrapolates): edge pixels read the columns
   BAYSAR_DEV double operator()(int i) const {
     const float v = i < x_l ? row[col_left0 + i] : row[col_right0 + (i - (F - x_r))];
     return (double)(v < mn ? mn : v);
@@ -225,6 +228,10 @@ BAYSAR_DEV double pixel_value(const Fetch& fetch, int p, int i, double w, const 
 BAYSAR_DEV double pixel_value(const FetchFolded& fetch, int p, int i, double w, const double* edge64, int F) {
   const int col = fetch.pix_col[p];
   if (col >= 0) return (double)fetch.kappa[col >> fetch.tile_shift] * (double)fetch.row[col];
+  if (!fetch.use_edge64) {
+    const double v0 = fetch(i);
+    return v0 + w * (fetch(i + 1) - v0);
+  }
   return pixel_value<FetchFolded>(fetch, p, i, w, edge64, F);
 }
 
@@ -562,7 +569,7 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
     // 128-bit shared-memory store (and one 128-bit global store in MODE 1) per group, and the far / near decision is one
     // test per group on the integer distance to the line centre.  Far-field points go two at a time through the packed
     // FP32 pipe (fma.rn.f32x2).
-    constexpr int GPT = BAYSAR_FUSED_GPT;
+    constexpr int GPT = NT == 128 ? 2 * BAYSAR_FUSED_GPT : BAYSAR_FUSED_GPT;
     float* sp = (MODE == 1) ? a.spec + n * a.split_pitch + a.split_pad : nullptr;
     const f32x2 dhi2 = pack2(d_hi, d_hi), dlo2 = pack2(d_lo, d_lo);
     const int n_groups = (F + 3) >> 2;
@@ -570,6 +577,11 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
       f32x2 v01[GPT], v23[GPT];
 #pragma unroll
       for (int i = 0; i < GPT; ++i) { v01[i] = pack2(0.f, 0.f); v23[i] = pack2(0.f, 0.f); }
+      // group i of this thread starts at grid point 4 (gbase + tid + i NT): an arithmetic progression, so the offsets from
+      // a line centre advance by one packed add per group.  Groups past the end of the grid are evaluated where they
+      // would lie (far field, finite) and never stored: no bounds test inside the line loop.
+      const float j00 = (float)(4 * (gbase + tid));
+      const f32x2 jb2 = pack2(j00, j00 + 1.f), two2 = pack2(2.f, 2.f), step2 = pack2((float)(4 * NT), (float)(4 * NT));
       for (int b = 0; b < nf; ++b) {
         const float4 cst = *reinterpret_cast<const float4*>(&fl[b].jc_f);  // jc, r, gamma_rec^2.5, gamma_exc^2.5
         const float4 ser = *reinterpret_cast<const float4*>(&fl[b].s_r);   // s_r, s_e, c0, c1
@@ -578,17 +590,22 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
         const f32x2 c0p = pack2(ser.z, ser.z), mc1p = pack2(-ser.w, -ser.w), c2p = pack2(cf.x, cf.x);
         const float4 w4 = *reinterpret_cast<const float4*>(fw + 4 * b);
         const bool three = FUSED3 && w4.w != 0.f;
+        const float far_lim = cf.y + 1.5f;  // |offset of the group's middle| from which all four points are >= nfar away
+        f32x2 kfA = add2(jb2, pack2(-cst.x, -cst.x));
 #pragma unroll
         for (int i = 0; i < GPT; ++i) {
-          const int g = gbase + tid + i * NT;
-          if (g >= n_groups) continue;
-          const float kf0 = (float)(4 * g) - cst.x;
-          // a three-tap line keeps the exact form in the first and the last group: the taps past the two grid ends are
-          // zero padding ("same" convolution)
-          const bool far = (kf0 >= cf.y || kf0 + 3.f <= -cf.y) && !(three && (g == 0 || g == n_groups - 1));
+          float kf0, kf1;
+          unpack2(kfA, kf0, kf1);
+          bool far = fabsf(kf0 + 1.5f) >= far_lim;
+          if (FUSED3 && three) {
+            // a three-tap line keeps the exact form in the first and the last group: the taps past the two grid ends are
+            // zero padding ("same" convolution)
+            const int g = gbase + tid + i * NT;
+            far = far && g != 0 && g != n_groups - 1;
+          }
           if (far) {
-            stark_far2(pack2(kf0, kf0 + 1.f), v01[i], dhi2, dlo2, r2, c0p, mc1p, c2p);
-            stark_far2(pack2(kf0 + 2.f, kf0 + 3.f), v23[i], dhi2, dlo2, r2, c0p, mc1p, c2p);
+            stark_far2(kfA, v01[i], dhi2, dlo2, r2, c0p, mc1p, c2p);
+            stark_far2(add2(kfA, two2), v23[i], dhi2, dlo2, r2, c0p, mc1p, c2p);
           } else {
             float o[4];
             if (!three) {
@@ -596,6 +613,7 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
               for (int k = 0; k < 4; ++k) o[k] = stark_exact(kf0 + (float)k, d_hi, d_lo, cst.y, cst.z, cst.w, ser.x, ser.y);
             } else {
               // out[j] = w.x S(j - 1) + w.y S(j) + w.z S(j + 1); S vanishes outside the grid
+              const int g = gbase + tid + i * NT;
               float sv[6];
 #pragma unroll
               for (int k = 0; k < 6; ++k) {
@@ -609,6 +627,7 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
             v01[i] = add2(v01[i], pack2(o[0], o[1]));
             v23[i] = add2(v23[i], pack2(o[2], o[3]));
           }
+          kfA = add2(kfA, step2);
         }
       }
 #pragma unroll
@@ -884,6 +903,23 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
   const double pre = dl * red1[0];
   if (__syncthreads_or(bad)) st |= 1u << 6;
 
+  if (MODE == 1 && a.skip_edge64) {
+    // ================= hand the spectrum to the folded tensor-core contraction (no float64 end outputs needed) =====
+    float* sp = a.spec + n * a.split_pitch + a.split_pad;
+    if (!a.keep_padding) {
+      for (int j = tid - a.split_pad; j < 0; j += NT) sp[j] = 0.f;
+      for (int64_t j = F + tid; j < a.split_pitch - a.split_pad; j += NT) sp[j] = 0.f;
+    }
+    if (!pre_done) for (int j = tid; j < F; j += NT) sp[j] = A_AT(j);
+    if (tid == 0) {
+      double* ax = a.aux + n * BAYSAR_AUX_STRIDE;
+      ax[0] = pre; ax[1] = (double)mn; ax[2] = 0.0; ax[3] = 0.0; ax[4] = 0.0; ax[5] = 0.0; ax[6] = 0.0; ax[7] = 0.0;
+    }
+    st = __syncthreads_or((int)st);
+    if (tid == 0 && st) atomicOr(&a.status[n], st);
+    return;
+  }
+
   // ================= instrument function taps (spectrometers.py:229-253) ========================================
   int KI, k_lo, k_hi;
   if (ch[CH_CALINT_IDX] >= 0) {
@@ -954,8 +990,10 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
     __syncthreads();
     float* sp = a.spec + n * a.split_pitch + a.split_pad;
     // the workspace is shared by chords with different paddings: (re)write this row's zero padding as well
-    for (int j = tid - a.split_pad; j < 0; j += NT) sp[j] = 0.f;
-    for (int64_t j = F + tid; j < a.split_pitch - a.split_pad; j += NT) sp[j] = 0.f;
+    if (!a.keep_padding) {
+      for (int j = tid - a.split_pad; j < 0; j += NT) sp[j] = 0.f;
+      for (int64_t j = F + tid; j < a.split_pitch - a.split_pad; j += NT) sp[j] = 0.f;
+    }
     if (!pre_done) for (int j = tid; j < F; j += NT) sp[j] = A_AT(j);
     if (tid == 0) {
       double* ax = a.aux + n * BAYSAR_AUX_STRIDE;
@@ -1093,6 +1131,7 @@ struct PixelFoldArgs {
   int n_col_tiles, n_fold_tiles, tile_n;
   double* logp;             // log-posterior path of single-chord models: also do K3's job (sum of components, flags)
   const double* aux;        // [N][BAYSAR_AUX_STRIDE]
+  int use_edge64;           // 1: aux carries the four float64 end outputs of the convolution (some pixel extrapolates)
   double* components;
   double* spectra;          // optional [N][P]
   uint32_t* status;
@@ -1170,7 +1209,7 @@ __global__ void __launch_bounds__(NT, BAYSAR_PIXFOLD_MINB) pixel_fold_kernel(Mod
     if ((tid & 31) == 0) kappa_s[t] = kap;
   }
   __syncthreads();
-  FetchFolded fetch{row, a.pix_col, a.col_left0, a.x_l, a.col_right0, a.x_r, F, mn, kappa_s, tile_shift};
+  FetchFolded fetch{row, a.pix_col, a.col_left0, a.x_l, a.col_right0, a.x_r, F, mn, kappa_s, tile_shift, a.use_edge64};
   if (a.spectra || !a.inv_err) {
     pixel_likelihood<NT>(m, ch, chd, th, n, c, ncomp_cols, pre, post, bg, ax + 2, fetch, scratch, a.components, a.spectra,
                          nullptr, st);
@@ -1192,7 +1231,7 @@ __global__ void __launch_bounds__(NT, BAYSAR_PIXFOLD_MINB) pixel_fold_kernel(Mod
       if (col >= 0) {
         fm = (double)row[col] * scale_s[col >> tile_shift] + bg;
       } else {
-        fm = pixel_value<FetchFolded>(fetch, p, m.pix_idx[poff + p], m.pix_frac[poff + p], ax + 2, F) * inv_ratio + bg;
+        fm = pixel_value(fetch, p, m.pix_idx[poff + p], m.pix_frac[poff + p], ax + 2, F) * inv_ratio + bg;
       }
       fm = fm < bg ? bg : fm;
       const double d = m.y[poff + p] - fm;

@@ -48,6 +48,7 @@ struct PxcSchedule {
 };
 struct PxcPlan {
   bool on = false;
+  bool no_extrapolation = false;  // every pixel of the static wavelength map lies between two fine-grid points
   int tn = 128, pad_left = 0, n_col_tiles = 0, wlen = 0, ring = 0;
   int e_l = 0, e_r = 0, x_l = 0, x_r = 0, col_left0 = 0, col_right0 = 0, n_dl = 0, n_dr = 0;
   int64_t pitch = 0, out_pitch = 0;

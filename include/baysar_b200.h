@@ -75,7 +75,8 @@ typedef struct baysar_options {
   int los_min_blocks;    /* resident CTAs per SM the LOS kernel is compiled for (0 auto by batch size, 4..8) */
   int los_team_points;   /* LOS points from which one CTA works on one theta (0 auto: when 4 thetas no longer fit) */
   int chord_min_blocks;  /* upper limit of resident CTAs per SM of the chord kernel (0 auto = 5; 3..5) */
-  int reserved[9];
+  int chord_threads;     /* threads per CTA (= per theta and chord) of the chord kernel: 0 auto, 128 or 256 */
+  int reserved[8];
 } baysar_options_t;
 int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, const baysar_options_t* options,
                            baysar_model_t** out);

@@ -149,7 +149,7 @@ def chord_forward_model(oracle, ch, st, scalars):
 
 # ---------------------------------------------------------------------------------------------------------------
 # Narrow-Doppler Balmer lines: strided-tail integral (Euler-Maclaurin) and far-field series of the fused sweeps
-EM_STRIDE, EM_WINDOW, FAR_RATIO = 16, 256, 500.0  # keep in sync with csrc/chord_stage.cuh
+EM_STRIDE, EM_WINDOW, FAR_RATIO = 16, 240, 500.0  # keep in sync with csrc/chord_stage.cuh
 
 
 def stark_integral_strided(F, delta, jc, r, g, stride=EM_STRIDE, window=EM_WINDOW):
