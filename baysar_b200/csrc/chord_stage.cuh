@@ -92,8 +92,9 @@ struct alignas(16) GaussComp {
   float amp;             // area-normalised amplitude over the intensity calibration
   int j_lo, j_hi, pad;   // fine-grid window |z| <= BAYSAR_Z_CUT
 };
-#define BAYSAR_EM_STRIDE 16     // sweep 1 samples the tails at this stride (Euler-Maclaurin corrected)
-#define BAYSAR_EM_WINDOW 240    // ... outside +-this many grid points of the line centre (window <= 512 points: two trips of 256 threads)
+#define BAYSAR_WIN_GAMMAS 10.0   // sweep 1 sums +-max(BAYSAR_WIN_MIN, BAYSAR_WIN_GAMMAS gamma / delta) grid points around the
+#define BAYSAR_WIN_MIN 48        // line centre point by point; the two tails beyond are integrated in closed form
+#define BAYSAR_TAIL_TERMS 4      // terms of the tail series in g / |x|^2.5 (<= 1e-2.5 beyond 10 gamma: truncation < 1e-10)
 #define BAYSAR_FAR_RATIO 500.f  // sweep 2: series in g / |d|^2.5 beyond this ratio (third-order term < 1e-8)
 #ifndef BAYSAR_FUSED_GPT
 #define BAYSAR_FUSED_GPT 4      // sweep 2: groups of four consecutive points a thread keeps in registers per chunk
@@ -415,11 +416,15 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
         FusedLine& L = fl_all[cl[CL_BRANK]];
         L.jc_f = (float)jc; L.r = (float)fma((double)jc, delta, c0); L.g_r = (float)rec[11]; L.g_e = (float)rec[12];
         L.sum_r = rec[0]; L.sum_e = rec[1];
-        int jL = jc - BAYSAR_EM_WINDOW, jR = jc + BAYSAR_EM_WINDOW;
+        // densely integrated window of sweep 1: +-10 Stark half-widths (gamma = g^0.4), at least BAYSAR_WIN_MIN points
+        // (float32 with fast powers: any width at or above ~10 gamma holds the tail series' accuracy)
+        const float gmax = L.g_r > L.g_e ? L.g_r : L.g_e;
+        float nw = ceilf((float)BAYSAR_WIN_GAMMAS * 1.001f * __powf(gmax, 0.4f) / (float)delta);
+        nw = nw > (float)BAYSAR_WIN_MIN ? nw : (float)BAYSAR_WIN_MIN;  // NaN -> minimum
+        const int n_w = nw < (float)F ? (int)nw : F;
+        int jL = jc - n_w, jR = jc + n_w;
         jL = jL < 0 ? 0 : (jL > F - 1 ? F - 1 : jL);
         jR = jR < 0 ? 0 : (jR > F - 1 ? F - 1 : jR);
-        if (jL > 0) jL -= jL % BAYSAR_EM_STRIDE;                    // both tails: a whole number of strides
-        if (jR < F - 1) jR += (F - 1 - jR) % BAYSAR_EM_STRIDE;
         L.jL = jL; L.jR = jR;
         float* w = fw_all + 4 * cl[CL_BRANK];
         if (three_taps) {
@@ -463,78 +468,77 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
     FusedLine* fl = fl_all + fb;
     float* fw = fw_all + 4 * fb;
     // ---- sweep 1: I_rec, I_exc = trapz of the two Stark profiles of every line over the whole grid.
-    // Only a window of +-BAYSAR_EM_WINDOW points around the line centre is summed point by point; on the two tails,
-    // where 1 / (|d|^2.5 + g) is smooth on the scale of the grid, every BAYSAR_EM_STRIDE-th point is sampled and the
-    // difference between the coarse and the fine trapezoid is restored from the Euler-Maclaurin expansion
-    //   T_1[a,b] = T_s[a,b] - (s^2 - 1)/12 (f1(b) - f1(a)) + (s^4 - 1)/720 (f3(b) - f3(a)) - ...
-    // (f1, f3: first and third derivative per grid index; relative error of the integral < 1e-8 for every width
-    // and centre, checked in tests/test_kernel_model.py).  Two branch-free loops per line (window, both tails); per-warp
-    // partial sums go to shared memory; one barrier serves all lines.
-    constexpr int S = BAYSAR_EM_STRIDE;
-    for (int b = 0; b < nf; ++b) {
-      const float4 cst = *reinterpret_cast<const float4*>(&fl[b].jc_f);  // jc, r, gamma_rec^2.5, gamma_exc^2.5
-      const int jL = fl[b].jL, jR = fl[b].jR;
-      const int n_c = jR - jL + 1;
-      const int n_lt = jL > 0 ? jL / S + 1 : 0;
-      const int n_rt = jR < F - 1 ? (F - 1 - jR) / S + 1 : 0;
-      float sr = 0.f, se = 0.f;
-      auto sample = [&](const int j, const float w) {
-        const float kf = (float)j - cst.x;
-        const float d = fabsf(fmaf(kf, d_hi, fmaf(kf, d_lo, cst.y)));
-        const float a25 = d * d * sqrt_approx(d);
-        const float dr = a25 + cst.z, de = a25 + cst.w;
-        const float inv = w * rcp_approx(dr * de);
-        sr = fmaf(de, inv, sr);
-        se = fmaf(dr, inv, se);
-      };
-      const float w_end = n_c == 1 ? 0.f : 0.5f;
-      for (int t = tid; t < n_c; t += NT) sample(jL + t, (t == 0 || t == n_c - 1) ? w_end : 1.f);
-      for (int t = tid; t < n_lt + n_rt; t += NT) {
-        const bool left = t < n_lt;
-        const int q = left ? t : t - n_lt, nq = left ? n_lt : n_rt;
-        sample((left ? 0 : jR) + q * S, (q == 0 || q == nq - 1) ? 0.5f * S : (float)S);
-      }
-      const double wr = warp_sum((double)sr), we = warp_sum((double)se);
-      if (lane == 0) { scratch[(2 * b) * (NT / 32) + warp] = wr; scratch[(2 * b + 1) * (NT / 32) + warp] = we; }
-    }
-    __syncthreads();
-    if (warp == 0) {
-      // one thread per (line, recombination / excitation): integral, Euler-Maclaurin end terms, amplitude
-      if (tid < 2 * nf) {
-        FusedLine& L = fl[tid >> 1];
-        const int q = tid & 1;
-        double integ = 0.0;
-#pragma unroll
-        for (int w = 0; w < NT / 32; ++w) integ += scratch[tid * (NT / 32) + w];
-        // the end terms are ~1e-6 of the integral: float32 with approximate reciprocals is ample
-        const float g = q == 0 ? L.g_r : L.g_e;
-        const float c1 = (float)(S * S - 1) / 12.f, c3 = ((float)S * S * S * S - 1.f) / 720.f;
-        const float df = (float)delta;
-        float corr = 0.f;
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-          const int ja = side == 0 ? 0 : L.jR, jb = side == 0 ? L.jL : F - 1;
-          if (jb > ja) {
-            float f1[2], f3[2];
-            float sgn = 1.f;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const float xs = ((float)(e == 0 ? ja : jb) - L.jc_f) * df + L.r;
-              if (e == 0) sgn = xs > 0.f ? 1.f : -1.f;
-              const float x = fabsf(xs), sq = sqrt_approx(x);
-              const float D1 = 2.5f * x * sq, D2 = 3.75f * sq, D3 = 1.875f * rcp_approx(sq);
-              const float iD = rcp_approx(x * x * sq + g), iD2 = iD * iD;
-              f1[e] = -D1 * iD2;
-              f3[e] = -D3 * iD2 + 6.f * D1 * D2 * iD2 * iD - 6.f * D1 * D1 * D1 * iD2 * iD2;
-            }
-            corr += sgn * (-c1 * df * (f1[1] - f1[0]) + c3 * df * df * df * (f3[1] - f3[0]));
-          }
+    // Only a window of +-10 Stark half-widths around the line centre (>= 48 points) is summed point by point.  On the two
+    // tails g / |x|^2.5 <= 10^-2.5 and the integrand is smooth on the scale of the grid, so the trapezoid is the integral
+    // plus the first two Euler-Maclaurin end corrections,
+    //   T_1[a, b] = (1 / delta) (A(x_b) - A(x_a)) + (f1(b) - f1(a)) / 12 - (f3(b) - f3(a)) / 720,
+    //   A(x) = - sum_k (-g)^k x^-(2.5 k + 1.5) / (2.5 k + 1.5)   (antiderivative of 1 / (x^2.5 + g), four terms),
+    // f1, f3 the first and third derivative per grid index: a closed form formed by one thread per (line, profile).
+    // Relative error of the integral < 1e-10 for every width and centre (tests/test_kernel_model.py).
+    // The lines are dealt to the warps (a group of wpl warps per line): every warp pays the per-line set-up once, for
+    // its own line, instead of all warps for all lines.
+    {
+      constexpr int NW = NT / 32;
+      int wpl = 1;
+      while (2 * wpl * nf <= NW) wpl *= 2;
+      for (int b = warp / wpl; b < nf; b += NW / wpl) {
+        const int sw = warp % wpl;
+        const float4 cst = *reinterpret_cast<const float4*>(&fl[b].jc_f);  // jc, r, gamma_rec^2.5, gamma_exc^2.5
+        const int jL = fl[b].jL, n_c = fl[b].jR - jL + 1;
+        const float w_end = n_c == 1 ? 0.f : 0.5f;
+        float sr = 0.f, se = 0.f;
+        for (int t = sw * 32 + lane; t < n_c; t += 32 * wpl) {
+          const float kf = (float)(jL + t) - cst.x;
+          const float d = fabsf(fmaf(kf, d_hi, fmaf(kf, d_lo, cst.y)));
+          const float a25 = d * d * sqrt_approx(d);
+          const float dr = a25 + cst.z, de = a25 + cst.w;
+          const float inv = ((t == 0 || t == n_c - 1) ? w_end : 1.f) * rcp_approx(dr * de);
+          sr = fmaf(de, inv, sr);
+          se = fmaf(dr, inv, se);
         }
-        integ += (double)corr;
-        const double amp = (q == 0 ? L.sum_r : L.sum_e) / (dl * integ) / cal;
-        if (!(amp - amp == 0.0)) atomicOr(&a.status[n], 1u << 6);
-        (q == 0 ? L.s_r : L.s_e) = (float)amp;
+        const double wr = warp_sum((double)sr), we = warp_sum((double)se);
+        if (lane == 0) { scratch[(2 * b) * NW + sw] = wr; scratch[(2 * b + 1) * NW + sw] = we; }
       }
+      __syncthreads();
+      if (warp == 0) {
+        // one thread per (line, recombination / excitation): window sum, closed-form tails, amplitude
+        if (tid < 2 * nf) {
+          FusedLine& L = fl[tid >> 1];
+          const int q = tid & 1;
+          double integ = 0.0;
+          for (int w = 0; w < wpl; ++w) integ += scratch[tid * NW + w];
+          // the two tails are at most a few per cent of the integral: float32 with approximate reciprocals is ample
+          const float g = q == 0 ? L.g_r : L.g_e;
+          const float df = (float)delta, idf = 1.f / df;
+          float tails = 0.f;
+#pragma unroll
+          for (int side = 0; side < 2; ++side) {
+            const int ja = side == 0 ? 0 : L.jR, jb = side == 0 ? L.jL : F - 1;
+            if (jb > ja) {
+              float A[2], f1[2], f3[2];
+              float sgn = 1.f;
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float kf = (float)(e == 0 ? ja : jb) - L.jc_f;
+                const float xs = fmaf(kf, d_hi, fmaf(kf, d_lo, L.r));
+                if (e == 0) sgn = xs > 0.f ? 1.f : -1.f;
+                const float x = fabsf(xs), sq = sqrt_approx(x), x25 = x * x * sq;
+                const float ix15 = rcp_approx(x * sq), u = -g * rcp_approx(x25);  // x^-1.5, -g x^-2.5
+                A[e] = -ix15 * (1.f / 1.5f + u * (1.f / 4.f + u * (1.f / 6.5f + u * (1.f / 9.f))));
+                const float D1 = 2.5f * x * sq, D2 = 3.75f * sq, D3 = 1.875f * rcp_approx(sq);
+                const float iD = rcp_approx(x25 + g), iD2 = iD * iD;
+                f1[e] = -D1 * iD2;
+                f3[e] = -D3 * iD2 + 6.f * D1 * D2 * iD2 * iD - 6.f * D1 * D1 * D1 * iD2 * iD2;
+              }
+              tails += sgn * ((A[1] - A[0]) * idf + df * (f1[1] - f1[0]) * (1.f / 12.f) -
+                              df * df * df * (f3[1] - f3[0]) * (1.f / 720.f));
+            }
+          }
+          integ += (double)tails;
+          const double amp = (q == 0 ? L.sum_r : L.sum_e) / (dl * integ) / cal;
+          if (!(amp - amp == 0.0)) atomicOr(&a.status[n], 1u << 6);
+          (q == 0 ? L.s_r : L.s_e) = (float)amp;
+        }
       __syncwarp();  // both amplitudes of a line come from neighbouring lanes of this warp
       if (tid < nf) {
         // sweep-2 constants: exact form next to the centre, far-field series
@@ -560,6 +564,7 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
           nfar = nfar > n3 ? nfar : n3;
         }
         L.nfar = nfar;
+      }
       }
     }
     __syncthreads();

@@ -103,6 +103,7 @@ inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 inline float __fdividef(float a, float b) { return a / b; }
+inline float __powf(float a, float b) { return std::pow(a, b); }
 inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 using std::ceil; using std::exp; using std::fabs; using std::floor; using std::log; using std::log10; using std::pow;
 using std::rint; using std::sqrt;

@@ -148,22 +148,19 @@ def chord_forward_model(oracle, ch, st, scalars):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# Narrow-Doppler Balmer lines: strided-tail integral (Euler-Maclaurin) and far-field series of the fused sweeps
-EM_STRIDE, EM_WINDOW, FAR_RATIO = 16, 240, 500.0  # keep in sync with csrc/chord_stage.cuh
+# Narrow-Doppler Balmer lines: closed-form tail integral (Euler-Maclaurin) and far-field series of the fused sweeps
+WIN_GAMMAS, WIN_MIN, TAIL_TERMS, FAR_RATIO = 10.0, 48, 4, 500.0  # keep in sync with csrc/chord_stage.cuh
 
 
-def stark_integral_strided(F, delta, jc, r, g, stride=EM_STRIDE, window=EM_WINDOW):
+def stark_integral_closed_tails(F, delta, jc, r, g):
     """trapz (unit spacing, half weights at the two ends of the grid) of 1 / (|x_j|^2.5 + g), x_j = (j - jc) delta + r,
-    the way sweep 1 of the chord kernel forms it: dense inside the window, every `stride`-th point on the tails plus
-    the first two Euler-Maclaurin end corrections.  float64 throughout (the kernel's float32 partial sums are covered
-    by the fixture comparisons)."""
+    the way sweep 1 of the chord kernel forms it: point by point inside +-max(WIN_MIN, WIN_GAMMAS g^0.4 / delta) points
+    of the centre; on each tail the integral of the four-term series in g / |x|^2.5 plus the first two Euler-Maclaurin
+    end corrections.  float64 throughout (the kernel's float32 window samples are covered by the fixture comparisons)."""
     f = lambda x: 1.0 / (np.abs(x) ** 2.5 + g)  # noqa: E731
     x = (np.arange(F) - jc) * delta + r
-    jL, jR = np.clip(jc - window, 0, F - 1), np.clip(jc + window, 0, F - 1)
-    if jL > 0:
-        jL -= jL % stride
-    if jR < F - 1:
-        jR += (F - 1 - jR) % stride
+    n_w = int(min(max(np.ceil(WIN_GAMMAS * g ** 0.4 / delta), WIN_MIN), F))
+    jL, jR = int(np.clip(jc - n_w, 0, F - 1)), int(np.clip(jc + n_w, 0, F - 1))
     tot = 0.0
     if jR > jL:
         w = np.ones(jR - jL + 1)
@@ -172,19 +169,16 @@ def stark_integral_strided(F, delta, jc, r, g, stride=EM_STRIDE, window=EM_WINDO
     for a, b in ((0, jL), (jR, F - 1)):
         if b <= a:
             continue
-        idx = np.arange(a, b + 1, stride)
-        w = np.full(len(idx), float(stride))
-        w[0] = w[-1] = 0.5 * stride
-        tot += np.sum(w * f(x[idx]))
         sgn = 1.0 if x[a] > 0 else -1.0
-        d1, d3 = [], []
+        A, d1, d3 = [], [], []
         for xe in (abs(x[a]), abs(x[b])):
             sq = np.sqrt(xe)
+            u = -g / (xe * xe * sq)
+            A.append(-sum(u ** k / (2.5 * k + 1.5) for k in range(TAIL_TERMS)) / (xe * sq))
             D, D1, D2, D3 = xe * xe * sq + g, 2.5 * xe * sq, 3.75 * sq, 1.875 / sq
             d1.append(-D1 / D ** 2)
             d3.append(-D3 / D ** 2 + 6 * D1 * D2 / D ** 3 - 6 * D1 ** 3 / D ** 4)
-        tot += -(stride ** 2 - 1) / 12 * sgn * delta * (d1[1] - d1[0])
-        tot += (stride ** 4 - 1) / 720 * sgn * delta ** 3 * (d3[1] - d3[0])
+        tot += sgn * ((A[1] - A[0]) / delta + delta * (d1[1] - d1[0]) / 12 - delta ** 3 * (d3[1] - d3[0]) / 720)
     return tot
 
 

@@ -28,10 +28,10 @@ def test_fp32_algorithm_holds_tolerance(name):
     assert worst_l < 1e-6
 
 
-def test_strided_tail_integral_matches_dense_trapz():
-    """Sweep 1 of the narrow-Doppler Balmer passes: dense window + strided tails + Euler-Maclaurin end terms equals
+def test_closed_form_tail_integral_matches_dense_trapz():
+    """Sweep 1 of the narrow-Doppler Balmer passes: dense window + closed-form tails + Euler-Maclaurin end terms equals
     the dense trapz over the whole fine grid to < 1e-8 relative, for every Stark width and line position."""
-    from .kernel_model import stark_integral_strided
+    from .kernel_model import stark_integral_closed_tails
 
     rng = np.random.default_rng(5)
     worst = 0.0
@@ -45,8 +45,8 @@ def test_strided_tail_integral_matches_dense_trapz():
         w = np.ones(F)
         w[0] = w[-1] = 0.5
         dense = np.sum(w / (np.abs(x) ** 2.5 + gamma ** 2.5))
-        worst = max(worst, abs(stark_integral_strided(F, delta, jc, r, gamma ** 2.5) - dense) / dense)
-    print(f"strided-tail integral: worst relative error {worst:.2e}")
+        worst = max(worst, abs(stark_integral_closed_tails(F, delta, jc, r, gamma ** 2.5) - dense) / dense)
+    print(f"closed-form tail integral: worst relative error {worst:.2e}")
     assert worst < 1e-8
 
 
