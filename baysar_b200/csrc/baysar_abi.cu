@@ -5,10 +5,12 @@
 #include "finalize.cuh"
 #include "host_plans.h"
 #include "los_stage.cuh"
+#include "los_tables.h"
 
 struct baysar_model {
   int device = 0;
   unsigned char* blob_dev = nullptr;
+  unsigned char* los_tables_dev = nullptr;  // derived tables of the LOS stage (los_tables.h): doubles, then bucket tables
   size_t blob_bytes = 0;
   std::vector<unsigned char> blob_host;  // header + small tables are read on the host for launch configuration
   ModelDev dev;
@@ -112,12 +114,16 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
   // one CTA's 200 KB) one CTA of four warps works on ONE theta, the points spread over its 128 threads.
   const int team_l = m->opt.los_team_points;
   const bool team = (team_l > 0 && L >= team_l) || 4 * per_warp > 200 * 1024;
-  if (team && per_warp + 128 <= 200 * 1024) {
-    const size_t smem = per_warp + 128;
-    if (2 * smem > 200 * 1024)  // one CTA per SM anyway: eight warps per theta
-      los_stage_kernel<8, 1, 1, 8><<<(unsigned)n, 256, smem, stream>>>(m->dev, a);
+  if (m->opt.los_team_warps == 2 && per_warp + los_team_xch_bytes(2) <= 200 * 1024) {
+    // two warps per theta: the per-point cache (the occupancy limit of the warp-per-theta form) is shared by twice the threads
+    const size_t smem = per_warp + los_team_xch_bytes(2);
+    if (m->opt.los_min_blocks >= 16) los_stage_kernel<2, 16, 1, 2><<<(unsigned)n, 64, smem, stream>>>(m->dev, a);
+    else los_stage_kernel<2, 12, 1, 2><<<(unsigned)n, 64, smem, stream>>>(m->dev, a);
+  } else if (team && per_warp + los_team_xch_bytes(8) <= 200 * 1024) {
+    if (2 * (per_warp + los_team_xch_bytes(4)) > 200 * 1024)  // one CTA per SM anyway: eight warps per theta
+      los_stage_kernel<8, 1, 1, 8><<<(unsigned)n, 256, per_warp + los_team_xch_bytes(8), stream>>>(m->dev, a);
     else
-      los_stage_kernel<4, 1, 1, 4><<<(unsigned)n, 128, smem, stream>>>(m->dev, a);
+      los_stage_kernel<4, 1, 1, 4><<<(unsigned)n, 128, per_warp + los_team_xch_bytes(4), stream>>>(m->dev, a);
   } else if (4 * per_warp <= 200 * 1024) {
     const size_t smem = 4 * per_warp;
     auto kern = minb >= 6 ? los_stage_kernel<4, 6> : (minb == 5 ? los_stage_kernel<4, 5> : los_stage_kernel<4, 4>);
@@ -195,7 +201,8 @@ int mark(baysar_model* m, int slot, cudaStream_t stream) {
 
 // Opt-in shared-memory limits of every kernel variant the launchers can pick: once per model creation
 int set_kernel_attributes() {
-  if (allow_max_smem(los_stage_kernel<8, 1, 1, 8>) || allow_max_smem(los_stage_kernel<4, 1, 1, 4>) ||
+  if (allow_max_smem(los_stage_kernel<2, 12, 1, 2>) || allow_max_smem(los_stage_kernel<2, 16, 1, 2>) ||
+      allow_max_smem(los_stage_kernel<8, 1, 1, 8>) || allow_max_smem(los_stage_kernel<4, 1, 1, 4>) ||
       allow_max_smem(los_stage_kernel<4, 4>) || allow_max_smem(los_stage_kernel<4, 5>) ||
       allow_max_smem(los_stage_kernel<4, 6>) || allow_max_smem(los_stage_kernel<4, 7>) ||
       allow_max_smem(los_stage_kernel<4, 8>) || allow_max_smem(los_stage_kernel<1>))
@@ -326,7 +333,7 @@ int validate_blob(const void* desc_blob, size_t nbytes) {
   auto elem = [](int sec) -> size_t {
     switch (sec) {
       case SEC_SP_I: case SEC_ELEM_DENS_IDX: case SEC_UL_I: case SEC_PR_I: case SEC_CSO_OFF: case SEC_CSO_UL:
-      case SEC_CH_I: case SEC_CL_I: case SEC_PIX_IDX: case SEC_MESH_LO: case SEC_PR_AUX: return 4;
+      case SEC_CH_I: case SEC_CL_I: case SEC_PIX_IDX: case SEC_MESH_LO: case SEC_PR_AUX: case SEC_GR_I: case SEC_GR_UL: return 4;
       default: return 8;
     }
   };
@@ -356,11 +363,33 @@ int validate_blob(const void* desc_blob, size_t nbytes) {
       need(SEC_H_TE, I[I_H_NTE], "H_TE") || need(SEC_H_TAB, I[I_N_HTAB] * I[I_H_NNE] * I[I_H_NTE], "H_TAB") ||
       need(SEC_TAU_GRID, I[I_N_TAU], "TAU_GRID") || need(SEC_SPL_TX, I[I_SPL_NX], "SPL_TX") ||
       need(SEC_SPL_TY, I[I_SPL_NY], "SPL_TY") ||
-      need(SEC_SPL_C, I[I_N_TEC] * (I[I_N_TAU] - 1) * (I[I_SPL_NX] - 4) * (I[I_SPL_NY] - 4) * 2, "SPL_C") ||
+      need(SEC_GR_I, I[I_N_GROUPS] * GR_I_COUNT, "GR_I") ||
       need(SEC_MESH_X, I[I_MESH_NE_N] + I[I_MESH_TE_N], "MESH_X") ||
       need(SEC_MESH_LO, I[I_PROFILE_KIND] == 2 ? 2 * L : 0, "MESH_LO") || need(SEC_PIX_FRAC, t.count(SEC_PIX_IDX), "PIX_FRAC") ||
       need(SEC_ERR, t.count(SEC_Y), "ERR") || need(SEC_PIX_IDX, t.count(SEC_Y), "PIX_IDX"))
     return 1;
+  {
+    // ADAS line groups: members are unique-line ids, coefficient blocks lie inside SEC_SPL_C (32-byte entries, read with
+    // 256-bit loads: the section must start on a 32-byte boundary)
+    const int* gr_i = static_cast<const int*>(t.ptr(SEC_GR_I));
+    const int* gr_ul = static_cast<const int*>(t.ptr(SEC_GR_UL));
+    const int* ul_i = static_cast<const int*>(t.ptr(SEC_UL_I));
+    const int64_t cells = (I[I_SPL_NX] - 4) * (I[I_SPL_NY] - 4), pairs = I[I_N_TAU] - 1;
+    if (I[I_N_GROUPS] < 0 || (I[I_N_GROUPS] > 0 && (cells < 1 || pairs < 1 || (hdr[3 + 2 * SEC_SPL_C] & 31) != 0)))
+      return fail("descriptor ADAS line groups inconsistent with the spline tables");
+    for (int64_t g = 0; g < I[I_N_GROUPS]; ++g) {
+      const int* gr = gr_i + g * GR_I_COUNT;
+      if (gr[GR_SPECIES] < 0 || gr[GR_SPECIES] >= nsp || gr[GR_NK] < 1 || gr[GR_FIRST] < 0 ||
+          (int64_t)gr[GR_FIRST] + gr[GR_NK] > t.count(SEC_GR_UL) || gr[GR_COEF_OFF] < 0 ||
+          ((int64_t)gr[GR_COEF_OFF] + pairs * cells * gr[GR_NK]) * 4 > t.count(SEC_SPL_C))
+        return fail("descriptor ADAS line group " + std::to_string(g) + " out of range");
+      for (int k = 0; k < gr[GR_NK]; ++k) {
+        const int u = gr_ul[gr[GR_FIRST] + k];
+        if (u < 0 || u >= nul || ul_i[u * UL_I_COUNT + UL_KIND] != 1)
+          return fail("descriptor ADAS line group " + std::to_string(g) + " lists a line that is not an ADAS line");
+      }
+    }
+  }
   const int* ch_i = static_cast<const int*>(t.ptr(SEC_CH_I));
   const int* cl_i = static_cast<const int*>(t.ptr(SEC_CL_I));
   const int64_t n_comps = t.count(SEC_COMP_D) / 2;
@@ -462,6 +491,22 @@ int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, con
   d.mesh_x = static_cast<const double*>(dev.ptr(SEC_MESH_X));
   d.mesh_lo = static_cast<const int*>(dev.ptr(SEC_MESH_LO));
   d.pr_aux = static_cast<const int*>(dev.ptr(SEC_PR_AUX));
+  d.gr_i = static_cast<const int*>(dev.ptr(SEC_GR_I));
+  d.gr_ul = static_cast<const int*>(dev.ptr(SEC_GR_UL));
+  {
+    // reciprocal spacings, search buckets and the 2^(k/64) table of the LOS stage, derived from the axes in the blob
+    const los_tables::Host lt = los_tables::build(
+        m->I, static_cast<const double*>(host.ptr(SEC_A11_NE)), static_cast<const double*>(host.ptr(SEC_A11_TE)),
+        static_cast<const double*>(host.ptr(SEC_H_NE)), static_cast<const double*>(host.ptr(SEC_H_TE)),
+        static_cast<const double*>(host.ptr(SEC_SPL_TX)), static_cast<const double*>(host.ptr(SEC_SPL_TY)));
+    const size_t nd = lt.d.size() * sizeof(double), ni = lt.i.size() * sizeof(int);
+    cudaError_t el = cudaMalloc(&m->los_tables_dev, nd + ni);
+    if (el == cudaSuccess) el = cudaMemcpy(m->los_tables_dev, lt.d.data(), nd, cudaMemcpyHostToDevice);
+    if (el == cudaSuccess) el = cudaMemcpy(m->los_tables_dev + nd, lt.i.data(), ni, cudaMemcpyHostToDevice);
+    if (el != cudaSuccess) { baysar_model_destroy(m); return fail(std::string("LOS tables: ") + cudaGetErrorString(el)); }
+    d.lt = los_tables::view(lt, reinterpret_cast<const double*>(m->los_tables_dev),
+                            reinterpret_cast<const int*>(m->los_tables_dev + nd));
+  }
 
   // shared memory the chord kernel needs: the largest chord decides (one launch covers all chords)
   const int n_chords = (int)m->I[I_N_CHORDS];
@@ -571,7 +616,7 @@ int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, con
 void baysar_model_destroy(baysar_model_t* m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  cudaFree(m->blob_dev); cudaFree(m->lines); cudaFree(m->comps); cudaFree(m->hdr); cudaFree(m->status);
+  cudaFree(m->blob_dev); cudaFree(m->los_tables_dev); cudaFree(m->lines); cudaFree(m->comps); cudaFree(m->hdr); cudaFree(m->status);
   cudaFree(m->theta_stage); cudaFree(m->logp_stage); cudaFreeHost(m->out_pinned);
   if (m->host_stream) cudaStreamDestroy(m->host_stream);
   if (m->last_done) cudaEventDestroy(m->last_done);

@@ -15,6 +15,22 @@
 #define BAYSAR_HDR_STRIDE 4  // per-theta header written by the LOS stage: ne_max, reserved...
 #define BAYSAR_Z_CUT 8.85    // exp(-z*z/2) < 1e-17 beyond this
 
+// Tables derived from the interpolation axes at model creation (los_tables.h): reciprocal spacings, search buckets over
+// the leading bits of a double (hi32 >> BAYSAR_KEY_SHIFT: sign, exponent, three mantissa bits).
+#define BAYSAR_KEY_SHIFT 17
+enum LosAxis { AX_A11_NE, AX_A11_TE, AX_H_NE, AX_H_TE, AX_SPL_X, AX_SPL_Y, AX_COUNT };
+struct GridKey {  // bucket table of one sorted axis
+  int off;   // offset of the table in LosTablesDev::key_tbl
+  int key0;  // key of bucket 0
+  int nb;    // number of buckets
+  int pad;
+};
+struct LosTablesDev {
+  const double* recip[AX_COUNT];  // linear axes: [n - 1] 1 / (g[k + 1] - g[k]); spline axes: [3][n] 1 / (t[k + j] - t[k]), j = 1..3
+  const int* key_tbl;
+  GridKey key[AX_COUNT];
+};
+
 // Device-side view of one compiled model: pointers into the single HBM copy of the descriptor blob.
 struct ModelDev {
   const int64_t* I;
@@ -54,6 +70,9 @@ struct ModelDev {
   const double* mesh_x;
   const int* mesh_lo;
   const int* pr_aux;
+  const int* gr_i;
+  const int* gr_ul;
+  LosTablesDev lt;
 };
 
 // approximate reciprocal / square root (one MUFU op each, ~1 ulp): the float32 spectral sweeps do not need IEEE rounding
@@ -118,6 +137,93 @@ BAYSAR_DEV int lower_bound(const double* g, int n, double x) {
   return lo;
 }
 
+// ---- searches that start from a bucket table (LosTablesDev) instead of bisecting: one table read from the leading bits
+// of x, then a forward scan that almost always ends after zero or one step
+#ifndef BAYSAR_CPU_EMU
+BAYSAR_DEV int hi_word(double x) { return __double2hiint(x); }
+BAYSAR_DEV int lo_word(double x) { return __double2loint(x); }
+BAYSAR_DEV double from_words(int hi, int lo) { return __hiloint2double(hi, lo); }
+#else
+BAYSAR_DEV int hi_word(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
+BAYSAR_DEV int lo_word(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(b & 0xffffffffLL); }
+BAYSAR_DEV double from_words(int hi, int lo) {
+  const int64_t b = (int64_t)(((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo);
+  double x; std::memcpy(&x, &b, 8); return x;
+}
+#endif
+BAYSAR_DEV int bucket_start(const LosTablesDev& lt, int ax, double x) {
+  const GridKey k = lt.key[ax];
+  int b = (hi_word(x) >> BAYSAR_KEY_SHIFT) - k.key0;
+  b = b < 0 ? 0 : (b >= k.nb ? k.nb - 1 : b);
+  return lt.key_tbl[k.off + b];
+}
+// numpy.searchsorted(g, x, side="left"); `i` from bucket_start (a lower-bound table): never above the answer
+BAYSAR_DEV int lower_bound_from(const double* g, int n, double x, int i) {
+  if (x != x) return 0;  // what the bisection returns for NaN
+  while (i < n && g[i] < x) ++i;
+  return i;
+}
+// cell + unclamped weight as linear_cell below, the division replaced by the tabulated reciprocal spacing
+BAYSAR_DEV void linear_cell_fast(const double* g, int n, double x, const LosTablesDev& lt, int ax, int& i, double& a) {
+  int k = lower_bound_from(g, n, x, bucket_start(lt, ax, x)) - 1;
+  k = k < 0 ? 0 : (k > n - 2 ? n - 2 : k);
+  i = k;
+  a = (x - g[k]) * lt.recip[ax][k];
+}
+// bspline_basis3 below with the interval located from the bucket table (an upper-bound table) and the six divisions of
+// the Cox-de Boor recurrence replaced by tabulated reciprocals R_j[k] = 1 / (t[k + j] - t[k])
+BAYSAR_DEV void bspline_basis3_fast(const double* t, int n, double x, const LosTablesDev& lt, int ax, int& l, double* h) {
+  const double tb = t[3], te = t[n - 4];
+  if (x < tb) x = tb;
+  if (x > te) x = te;
+  int i = x != x ? 0 : bucket_start(lt, ax, x);
+  while (i < n && t[i] <= x) ++i;
+  l = i - 1 < 3 ? 3 : (i - 1 > n - 5 ? n - 5 : i - 1);
+  const double* R = lt.recip[ax];
+  double hh[3];
+  h[0] = 1.0;
+#pragma unroll
+  for (int j = 1; j <= 3; ++j) {
+#pragma unroll
+    for (int q = 0; q < j; ++q) hh[q] = h[q];
+    h[0] = 0.0;
+#pragma unroll
+    for (int q = 0; q < j; ++q) {
+      const int li = l + q + 1, lj = li - j;
+      const double f = hh[q] * R[(j - 1) * n + lj];
+      h[q] = h[q] + f * (t[li] - x);
+      h[q + 1] = f * (x - t[lj]);
+    }
+  }
+}
+
+// exp(x) = 2^n e^r, n = rint(x / ln 2), |r| <= ln 2 / 2, Taylor polynomial of degree 12 (truncation 2e-16; ~1 ulp overall;
+// the library routine outside |x| < 690 and for NaN).  No table: the LOS stage is bound by the L1 data pipe, and a
+// 2^(k/64) table costs a gather of ~4 wavefronts per call.
+BAYSAR_DEV double exp_fast(double x) {
+  if (!(fabs(x) < 690.0)) return exp(x);
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52: the integer lands in the low word
+  const double tt = fma(x, 1.4426950408889634, magic);
+  const int n = lo_word(tt);
+  const double tn = tt - magic;
+  double r = fma(tn, -0.6931471805599453, x);
+  r = fma(tn, -2.3190468138462996e-17, r);
+  double p = 1.0 / 479001600.0;
+  p = fma(r, p, 1.0 / 39916800.0);
+  p = fma(r, p, 1.0 / 3628800.0);
+  p = fma(r, p, 1.0 / 362880.0);
+  p = fma(r, p, 1.0 / 40320.0);
+  p = fma(r, p, 1.0 / 5040.0);
+  p = fma(r, p, 1.0 / 720.0);
+  p = fma(r, p, 1.0 / 120.0);
+  p = fma(r, p, 1.0 / 24.0);
+  p = fma(r, p, 1.0 / 6.0);
+  p = fma(r, p, 0.5);
+  p = fma(r, p, 1.0);
+  p = fma(r, p, 1.0);
+  return from_words(hi_word(p) + (n << 20), lo_word(p));
+}
+
 // cell + unclamped weight of scipy's linear RegularGridInterpolator (bounds_error=False, fill_value=None)
 BAYSAR_DEV void linear_cell(const double* g, int n, double x, int& i, double& a) {
   int k = lower_bound(g, n, x) - 1;
@@ -130,6 +236,16 @@ BAYSAR_DEV double bilinear(const double* t, int n1, int i, int j, double a, doub
   const double* r0 = t + (int64_t)i * n1 + j;
   const double* r1 = r0 + n1;
   return r0[0] * (1 - a) * (1 - b) + r0[1] * (1 - a) * b + r1[0] * a * (1 - b) + r1[1] * a * b;
+}
+
+// two tables at the same cell with the four corner weights formed once
+BAYSAR_DEV void bilinear2(const double* t0, const double* t1, int n1, int i, int j, double a, double b, double& v0, double& v1) {
+  const int64_t o = (int64_t)i * n1 + j;
+  const double w00 = (1 - a) * (1 - b), w01 = (1 - a) * b, w10 = a * (1 - b), w11 = a * b;
+  const double* p = t0 + o;
+  v0 = p[0] * w00 + p[1] * w01 + p[n1] * w10 + p[n1 + 1] * w11;
+  p = t1 + o;
+  v1 = p[0] * w00 + p[1] * w01 + p[n1] * w10 + p[n1 + 1] * w11;
 }
 
 // FITPACK fpbisp/fpbspl for one coordinate, degree 3: clamp to the knot span, locate the interval
@@ -165,17 +281,68 @@ BAYSAR_DEV void bspline_basis3(const double* t, int n, double x, int& l, double*
 // 2 x 20 fused multiply-adds from 16 sixteen-byte loads (FITPACK's fpbisp forms the same sums term by term).
 // hx / hy are strided (structure-of-arrays basis cache: element q of LOS point l at q * stride + l).
 struct alignas(16) Double2 { double x, y; };  // 16-byte aligned: one LDG.128 per pair (unaligned it was two LDG.64)
-BAYSAR_DEV void bspline_eval_pair(const double* c, int ncy, int lx, int ly, const double* hx, const double* hy, int stride,
+BAYSAR_DEV void bspline_eval_pair(const char* cell, size_t row_bytes, const double* hx, const double* hy, int stride,
                                   double& vi, double& vj) {
-  const Double2* base = reinterpret_cast<const Double2*>(c) + (int64_t)(lx - 3) * ncy + (ly - 3);
-  double si = 0.0, sj = 0.0;
+  // `cell`: address of coefficient pair (lx - 3, ly - 3); the four rows are row_bytes apart (explicit pointers: with
+  // an int row index the compiler re-derived a 64-bit address for every one of the 16 loads)
+  const Double2* r0 = reinterpret_cast<const Double2*>(cell);
+  const Double2* r1 = reinterpret_cast<const Double2*>(cell + row_bytes);
+  const Double2* r2 = reinterpret_cast<const Double2*>(cell + 2 * row_bytes);
+  const Double2* r3 = reinterpret_cast<const Double2*>(cell + 3 * row_bytes);
   const double y0 = hy[0], y1 = hy[stride], y2 = hy[2 * stride], y3 = hy[3 * stride];
+  double si, sj;
+  {
+    const Double2 c0 = r0[0], c1 = r0[1], c2 = r0[2], c3 = r0[3];
+    const double xw = hx[0];
+    si = fma(c3.x, y3, fma(c2.x, y2, fma(c1.x, y1, c0.x * y0))) * xw;
+    sj = fma(c3.y, y3, fma(c2.y, y2, fma(c1.y, y1, c0.y * y0))) * xw;
+  }
+  {
+    const Double2 c0 = r1[0], c1 = r1[1], c2 = r1[2], c3 = r1[3];
+    const double xw = hx[stride];
+    si = fma(fma(c3.x, y3, fma(c2.x, y2, fma(c1.x, y1, c0.x * y0))), xw, si);
+    sj = fma(fma(c3.y, y3, fma(c2.y, y2, fma(c1.y, y1, c0.y * y0))), xw, sj);
+  }
+  {
+    const Double2 c0 = r2[0], c1 = r2[1], c2 = r2[2], c3 = r2[3];
+    const double xw = hx[2 * stride];
+    si = fma(fma(c3.x, y3, fma(c2.x, y2, fma(c1.x, y1, c0.x * y0))), xw, si);
+    sj = fma(fma(c3.y, y3, fma(c2.y, y2, fma(c1.y, y1, c0.y * y0))), xw, sj);
+  }
+  {
+    const Double2 c0 = r3[0], c1 = r3[1], c2 = r3[2], c3 = r3[3];
+    const double xw = hx[3 * stride];
+    si = fma(fma(c3.x, y3, fma(c2.x, y2, fma(c1.x, y1, c0.x * y0))), xw, si);
+    sj = fma(fma(c3.y, y3, fma(c2.y, y2, fma(c1.y, y1, c0.y * y0))), xw, sj);
+  }
+  vi = si;
+  vj = sj;
+}
+
+// One line of an ADAS line group (layout.h SEC_SPL_C): every (ix, iy) entry holds, for each of the group's lines, 32 bytes
+// = (tau slice i, slice i + 1) of column iy and of column iy + 1, so a row of four columns is two 256-bit loads `2 entry`
+// bytes apart, and lanes that evaluate different lines at the same spline cell read neighbouring bytes of one cache line.
+struct alignas(32) Double4 { double a, b, c, d; };
+#ifndef BAYSAR_CPU_EMU
+BAYSAR_DEV Double4 ld256(const char* p) {
+  Double4 r;
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
+  return r;
+}
+#else
+BAYSAR_DEV Double4 ld256(const char* p) { Double4 r; std::memcpy(&r, p, 32); return r; }
+#endif
+BAYSAR_DEV void bspline_eval_group(const char* cell, size_t entry, size_t row_bytes, const double* hx, const double* hy,
+                                   int stride, double& vi, double& vj) {
+  const double y0 = hy[0], y1 = hy[stride], y2 = hy[2 * stride], y3 = hy[3 * stride];
+  double si = 0.0, sj = 0.0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const Double2 c0 = base[i * ncy], c1 = base[i * ncy + 1], c2 = base[i * ncy + 2], c3 = base[i * ncy + 3];
-    const double ri = fma(c3.x, y3, fma(c2.x, y2, fma(c1.x, y1, c0.x * y0)));
-    const double rj = fma(c3.y, y3, fma(c2.y, y2, fma(c1.y, y1, c0.y * y0)));
-    const double xw = hx[i * stride];
+  for (int r = 0; r < 4; ++r) {
+    const char* rp = cell + r * row_bytes;
+    const Double4 A = ld256(rp), B = ld256(rp + 2 * entry);
+    const double ri = fma(B.c, y3, fma(B.a, y2, fma(A.c, y1, A.a * y0)));
+    const double rj = fma(B.d, y3, fma(B.b, y2, fma(A.d, y1, A.b * y0)));
+    const double xw = hx[r * stride];
     si = fma(ri, xw, si);
     sj = fma(rj, xw, sj);
   }

@@ -9,7 +9,7 @@
 #define BAYSAR_LAYOUT_H
 
 #define BAYSAR_BLOB_MAGIC 0x4252415359534142LL /* "BAYSYSAB" */
-#define BAYSAR_BLOB_VERSION 9
+#define BAYSAR_BLOB_VERSION 10
 
 enum BaysarSection {
   SEC_I,              /* int64  [I_COUNT]           model-wide integer scalars                         */
@@ -29,8 +29,9 @@ enum BaysarSection {
   SEC_TAU_GRID,       /* double [n_tau]             log10 tau grid ("magical_tau")                     */
   SEC_SPL_TX,         /* double [spl_nx]            bicubic spline knots in ne                         */
   SEC_SPL_TY,         /* double [spl_ny]            bicubic spline knots in Te                         */
-  SEC_SPL_C,          /* double [n_tec][n_tau-1][(spl_nx-4)*(spl_ny-4)][2]  B-spline coefficients of log(ne*TEC),
-                         stored as (tau slice i, tau slice i+1) pairs: one 16-byte load serves both slices */
+  SEC_SPL_C,          /* double, per ADAS line group g (GR_COEF_OFF): [n_tau-1][spl_nx-4][spl_ny-4][n_k][4]  B-spline
+                         coefficients of log(ne*TEC) of the group's n_k lines side by side; the 4 doubles (32 bytes, one
+                         256-bit load) are (tau slice i, slice i+1) of column iy and of column iy+1 (clipped at the last) */
   SEC_UL_I,           /* int32  [n_ulines][UL_I_COUNT]  unique (line-of-sight) lines                    */
   SEC_UL_D,           /* double [n_ulines][UL_D_COUNT]                                                  */
   SEC_PR_I,           /* int32  [n_priors][PR_I_COUNT]                                                  */
@@ -50,6 +51,8 @@ enum BaysarSection {
   SEC_MESH_X,         /* double [mesh_ne_n + mesh_te_n]  MeshLine knot positions (density, then temperature)  */
   SEC_MESH_LO,        /* int32  [2][L]              MeshLine: lower knot of every LOS point (density, temperature) */
   SEC_PR_AUX,         /* int32  [..]                index lists of the optional priors (theta indices; PR_I0 = offset, PR_I1 = count) */
+  SEC_GR_I,           /* int32  [n_groups][GR_I_COUNT]  ADAS line groups: the unique lines of one species (one tau), evaluated together */
+  SEC_GR_UL,          /* int32  [sum n_k]           unique-line id of every group member                 */
   SEC_COUNT
 };
 
@@ -86,6 +89,7 @@ enum BaysarI {
   I_F_MAX,
   I_MESH_NE_N,          /* MeshLine: number of density / temperature knots */
   I_MESH_TE_N,
+  I_N_GROUPS,           /* ADAS line groups */
   I_COUNT
 };
 
@@ -107,6 +111,14 @@ enum BaysarProfD {
 
 enum BaysarSpI { SP_DENS_IDX, SP_TAU_IDX, SP_VEL_IDX, SP_TI_IDX, SP_IS_H, SP_IS_IMPURITY, SP_I_COUNT };
 enum BaysarSpD { SP_MASS, SP_D_COUNT };
+
+enum BaysarGrI {
+  GR_SPECIES,   /* index into the species table (density, tau) */
+  GR_NK,        /* lines in the group */
+  GR_FIRST,     /* offset of the group's members in SEC_GR_UL */
+  GR_COEF_OFF,  /* offset of the group's coefficients in SEC_SPL_C, in units of 4 doubles */
+  GR_I_COUNT
+};
 
 enum BaysarUlI {
   UL_KIND,     /* 0 Balmer, 1 ADAS406, 2 XLine */

@@ -24,16 +24,19 @@ struct LosArgs {
 
 // bytes of dynamic shared memory one warp needs for L line-of-sight points
 __host__ __device__ static inline size_t los_smem_per_warp(int L, int n_params, int n_species) {
-  return (size_t)L * (14 * sizeof(double) + 4 * sizeof(int)) +
-         (size_t)(2 * n_params + 3 * n_species + (L & 1)) * sizeof(double);
+  return (size_t)L * (14 * sizeof(double) + 2 * sizeof(int)) +
+         (size_t)(2 * n_params + 3 * n_species) * sizeof(double);
 }
+
+// exchange slots of a team of TW warps: four sums for each of a warp's 32 lanes (the ADAS line groups)
+__host__ __device__ static inline size_t los_team_xch_bytes(int tw) { return (size_t)tw * 32 * 4 * sizeof(double); }
 
 // TW warps cooperate on one theta.  TW = 1 is the warp-per-theta form (reductions are warp shuffles); TW = 4 runs one CTA
 // per theta with the line-of-sight points spread over 128 threads, for long lines of sight whose per-point cache
 // (128 bytes per point) would otherwise leave a single warp per SM (L = 1000: 128 KB per theta).
 template <int TW>
 struct LosTeam {
-  double* xch;  // [TW] exchange slots in shared memory (TW > 1)
+  double* xch;  // exchange slots in shared memory (TW > 1): los_team_xch_bytes(TW)
   BAYSAR_DEV void sync() const {
     if (TW == 1) __syncwarp();
     else __syncthreads();
@@ -48,6 +51,27 @@ struct LosTeam {
 #pragma unroll
     for (int i = 1; i < TW; ++i) r = comb(r, xch[i]);
     return r;
+  }
+  // NV sums with one exchange (TW > 1: a single pair of barriers instead of one pair per sum); xch holds at least 8 TW doubles
+  template <int NV>
+  BAYSAR_DEV void sum_n(double* v) const {
+    static_assert(NV <= 8, "exchange buffer holds eight sums");
+#pragma unroll
+    for (int q = 0; q < NV; ++q) v[q] = warp_sum(v[q]);
+    if (TW == 1) return;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int q = 0; q < NV; ++q) xch[q * TW + (threadIdx.x >> 5)] = v[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double r = xch[q * TW];
+#pragma unroll
+      for (int i = 1; i < TW; ++i) r += xch[q * TW + i];
+      v[q] = r;
+    }
   }
   BAYSAR_DEV double sum(double v) const { return reduce(warp_sum(v), [](double a, double b) { return a + b; }); }
   BAYSAR_DEV double max(double v) const { return reduce(warp_max(v), [](double a, double b) { return a > b ? a : b; }); }
@@ -115,10 +139,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
   double* __restrict__ hb_s = ha_s + L;
   double* __restrict__ bx_s = hb_s + L;   // [4][L] spline basis in ne (structure of arrays: conflict-free across lanes)
   double* __restrict__ by_s = bx_s + 4 * L;
-  int* __restrict__ hi_s = (int*)(by_s + 4 * L);
-  int* __restrict__ hj_s = hi_s + L;
-  int* __restrict__ lx_s = hj_s + L;
-  int* __restrict__ ly_s = lx_s + L;
+  int* __restrict__ ho_s = (int*)(by_s + 4 * L);  // adf15 cell: element offset of its (ne, Te) corner in a table
+  int* __restrict__ co_s = ho_s + L;              // spline cell: index of coefficient entry (lx - 3, ly - 3) in a group's table
+  const LosTablesDev& lt = m.lt;
   LosTeam<TW> team{reinterpret_cast<double*>(los_smem_raw + (size_t)(TW == 1 ? WARPS : 1) * los_smem_per_warp(L, n_params, n_species))};
 
   uint32_t st = 0;
@@ -148,17 +171,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     const double te_f = th[te_idx + 1], te_floor = th[te_idx + 2], te_c = m.prof_d[PROF_TE_CENTRE];
     const double ne_pk = p10[ne_idx], te_pk = p10[te_idx];
     for (int l = lane; l < L; l += TS) {
+      // sigma = 0.2 f + f / (1 + e), e = exp(-dx): dx / sigma = dx (1 + e) / (f (1.2 + 0.2 e)), one division instead of two
       double x = m.los_x[l];
       double dx = x - ne_c;
-      double sg = 0.2 * ne_f + ne_f / (1.0 + exp(-dx));
-      double r = dx / sg;
-      double v = clip_lo(ne_pk / (1.0 + r * r), ne_floor);
+      double e = exp_fast(-dx);
+      double r = (dx * (1.0 + e)) / (ne_f * fma(0.2, e, 1.2));
+      double v = clip_lo(ne_pk / fma(r, r, 1.0), ne_floor);
       ne_s[l] = v;
       nemax = v > nemax ? v : nemax;
       dx = x - te_c;
-      sg = 0.2 * te_f + te_f / (1.0 + exp(-dx));
-      r = dx / sg;
-      te_s[l] = clip_lo(te_pk / (1.0 + r * r), te_floor);
+      e = exp_fast(-dx);
+      r = (dx * (1.0 + e)) / (te_f * fma(0.2, e, 1.2));
+      te_s[l] = clip_lo(te_pk / fma(r, r, 1.0), te_floor);
     }
   } else if (profile_kind == 1) {
     // BowmanTeeNe / BowmanTeeTe (lineshapes.py:332-376): A (1 + |((x - x0) / sigma)|^q / nu)^(-(nu + 1) / 2) + b,
@@ -245,8 +269,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     for (int l = lane; l < L; l += TS) {
       double ne = ne_s[l], te = te_s[l];
       int ci, cj; double ca, cb;
-      linear_cell(m.a11_ne, nne, ne, ci, ca);
-      linear_cell(m.a11_te, nte, te, cj, cb);
+      linear_cell_fast(m.a11_ne, nne, ne, lt, AX_A11_NE, ci, ca);
+      linear_cell_fast(m.a11_te, nte, te, lt, AX_A11_TE, cj, cb);
       double scd = bilinear(m.a11_scd, nte, ci, cj, ca, cb);
       double n0 = dens_idx >= 0 ? n0_sampled : nm_s[l];
       n0 = n0 - n0 * ne * scd * tau_h;
@@ -258,9 +282,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     const int hne = (int)I[I_H_NNE], hte = (int)I[I_H_NTE];
     for (int l = lane; l < L; l += TS) {
       int ci, cj; double ca, cb;
-      linear_cell(m.h_ne, hne, ne_s[l], ci, ca);
-      linear_cell(m.h_te, hte, te_s[l], cj, cb);
-      hi_s[l] = ci; hj_s[l] = cj; ha_s[l] = ca; hb_s[l] = cb;
+      linear_cell_fast(m.h_ne, hne, ne_s[l], lt, AX_H_NE, ci, ca);
+      linear_cell_fast(m.h_te, hte, te_s[l], lt, AX_H_TE, cj, cb);
+      ho_s[l] = ci * hte + cj; ha_s[l] = ca; hb_s[l] = cb;
     }
   } else {
     for (int l = lane; l < L; l += TS) n0_s[l] = 0.0;
@@ -272,9 +296,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
   if (n_tec > 0) {
     for (int l = lane; l < L; l += TS) {
       int lx, ly; double hx[4], hy[4];
-      bspline_basis3(m.spl_tx, snx, ne_s[l], lx, hx);
-      bspline_basis3(m.spl_ty, sny, te_s[l], ly, hy);
-      lx_s[l] = lx; ly_s[l] = ly;
+      bspline_basis3_fast(m.spl_tx, snx, ne_s[l], lt, AX_SPL_X, lx, hx);
+      bspline_basis3_fast(m.spl_ty, sny, te_s[l], lt, AX_SPL_Y, ly, hy);
+      co_s[l] = (lx - 3) * (sny - 4) + (ly - 3);
 #pragma unroll
       for (int q = 0; q < 4; ++q) { bx_s[q * L + l] = hx[q]; by_s[q * L + l] = hy[q]; }
     }
@@ -308,16 +332,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
 #pragma unroll UNR
       for (int l = lane; l < L; l += TS) {
         double ne = ne_s[l], te = te_s[l], w = m.los_w[l];
-        double pe = exp(bilinear(texc, hte, hi_s[l], hj_s[l], ha_s[l], hb_s[l]));
-        double pr = exp(bilinear(trec, hte, hi_s[l], hj_s[l], ha_s[l], hb_s[l]));
+        double le, lr;
+        bilinear2(texc, trec, hte, 0, ho_s[l], ha_s[l], hb_s[l], le, lr);
+        double pe = exp_fast(le), pr = exp_fast(lr);
         if (pe != pe || pr != pr) st |= 1u << 4;
         double rp = clip_lo(nm_s[l], 1.0) * ne * pr;
         double ep = n0_s[l] * ne * pe;
         s[0] += rp; s[1] += ep; s[2] += w * rp; s[3] += w * ep;
         s[4] += rp * ne; s[5] += rp * te; s[6] += ep * ne; s[7] += ep * te;
       }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) s[q] = team.sum(s[q]);
+      team.template sum_n<8>(s);
       // The line's scalars (seven divisions, a square root) are uniform across the warp, so forming them here would run
       // them once per line, one line after the other; the raw sums wait in the record instead and one lane per line
       // forms all lines' scalars side by side after the loop.
@@ -325,38 +349,85 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
 #pragma unroll
         for (int q = 0; q < 8; ++q) rec[q] = s[q];
       }
-    } else if (kind == 1) {  // ADAS406 (linemodels.py:386-426, :445-494)
-      const int* sp = m.sp_i + ul[UL_SPECIES] * SP_I_COUNT;
-      const double dens = p10[sp[SP_DENS_IDX]];
-      const double* w3 = spw + 3 * ul[UL_SPECIES];
-      const int pair = (int)w3[0];
-      const double i_w = w3[1], j_w = w3[2];
-      const int ncx = snx - 4, ncy = sny - 4;
-      const double* cpair = m.spl_c + ((int64_t)ul[UL_TAB_A] * (n_tau - 1) + pair) * ncx * ncy * 2;
-      double s[5] = {0, 0, 0, 0, 0};
-      // n0 = dens * (ne / ne_max) and the concentration weight n0 / ne = dens / ne_max (linemodels.py:392-394, :411):
-      // the two float64 divisions per point and line become one reciprocal per theta (relative difference ~1e-16)
-      const double dens_over_max = dens * inv_nemax;
-#pragma unroll UNR
-      for (int l = lane; l < L; l += TS) {
-        double ne = ne_s[l], te = te_s[l];
-        double n0 = dens_over_max * ne;
-        double vi, vj;
-        bspline_eval_pair(cpair, ncy, lx_s[l], ly_s[l], bx_s + l, by_s + l, L, vi, vj);
-        double tec = nan_to_num(exp(vi) * i_w + exp(vj) * j_w);
-        double p = clip_lo(n0 * tec, 1.0);
-        s[0] += p; s[1] += m.los_w[l] * p; s[2] += p * ne; s[3] += p * dens_over_max; s[4] += p * te;
-      }
-#pragma unroll
-      for (int q = 0; q < 5; ++q) s[q] = team.sum(s[q]);
-      if (lane == 0) {  // raw sums; the scalars follow after the loop, one lane per line (as for the Balmer lines)
-#pragma unroll
-        for (int q = 0; q < 5; ++q) rec[q] = s[q];
-      }
+    } else if (kind == 1) {  // ADAS406: evaluated per group of lines below
     } else {  // XLine (linemodels.py:228-230)
       if (lane == 0) {
         rec[0] = p10[ul[UL_TAB_A]];
         for (int q = 1; q < BAYSAR_LINE_STRIDE; ++q) rec[q] = 0.0;
+      }
+    }
+  }
+  // ---- ADAS406 lines (linemodels.py:386-426, :445-494), one group at a time: the lines of one species share the tau
+  // slices, the density and, per line-of-sight point, the spline cell and basis.  The lanes of a warp are dealt
+  // (line k, point) pairs, K = min(32, lines) lines x P = 32 / K consecutive points per trip; the group's coefficients
+  // lie side by side (layout.h SEC_SPL_C), so the lanes of one cell read neighbouring bytes of the same cache lines
+  // and a gather costs one wavefront per distinct cell among P points, for all K lines at once -- the stage is bound
+  // by the L1 data pipe, and with one line at a time every line paid those wavefronts again.
+  {
+    const int n_groups = (int)I[I_N_GROUPS];
+    const int ncx = snx - 4, ncy = sny - 4;
+    const int wl = threadIdx.x & 31, wi = TW == 1 ? 0 : (int)(threadIdx.x >> 5);
+    for (int g = 0; g < n_groups; ++g) {
+      const int* gr = m.gr_i + g * GR_I_COUNT;
+      const int n_k = gr[GR_NK];
+      const int* sp = m.sp_i + gr[GR_SPECIES] * SP_I_COUNT;
+      // n0 = dens * (ne / ne_max) and the concentration weight n0 / ne = dens / ne_max (linemodels.py:392-394, :411):
+      // the two float64 divisions per point and line become one reciprocal per theta (relative difference ~1e-16)
+      const double dens_over_max = p10[sp[SP_DENS_IDX]] * inv_nemax;
+      const double* w3 = spw + 3 * gr[GR_SPECIES];
+      const int pair = (int)w3[0];
+      const double i_w = w3[1], j_w = w3[2];
+      const size_t entry = (size_t)n_k * 32, row_bytes = (size_t)ncy * entry;
+      const char* gbase = reinterpret_cast<const char*>(m.spl_c) +
+                          ((size_t)gr[GR_COEF_OFF] + (size_t)pair * ncx * ncy * n_k) * 32;
+      for (int k0 = 0; k0 < n_k; k0 += 32) {
+        const int K = n_k - k0 < 32 ? n_k - k0 : 32, P = 32 / K;
+        const int k = wl / P, pl = wl - k * P;
+        const bool active = k < K;
+        const char* lbase = gbase + (size_t)(k0 + (active ? k : 0)) * 32;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s4 = 0.0;
+        for (int p0 = wi * P; p0 < L; p0 += TW * P) {
+          const int l = p0 + pl;
+          if (active && l < L) {
+            const double ne = ne_s[l], te = te_s[l];
+            double vi, vj;
+            bspline_eval_group(lbase + (size_t)co_s[l] * entry, entry, row_bytes, bx_s + l, by_s + l, L, vi, vj);
+            double tec = exp_fast(vi) * i_w + exp_fast(vj) * j_w;
+            if (!(fabs(tec) <= 1.7976931348623157e308)) tec = nan_to_num(tec);
+            const double p = clip_lo((dens_over_max * ne) * tec, 1.0);
+            s0 += p; s1 += m.los_w[l] * p; s2 += p * ne; s4 += p * te;
+          }
+        }
+        // sums over the P lanes of every line: a shuffle tree that stays inside the segment
+        for (int o = 1; o < P; o <<= 1) {
+          const double t0 = __shfl_down_sync(0xffffffffu, s0, o), t1 = __shfl_down_sync(0xffffffffu, s1, o);
+          const double t2 = __shfl_down_sync(0xffffffffu, s2, o), t4 = __shfl_down_sync(0xffffffffu, s4, o);
+          if (pl + o < P) { s0 += t0; s1 += t1; s2 += t2; s4 += t4; }
+        }
+        // raw sums into the line records; the scalars follow below, one lane per line (as for the Balmer lines)
+        if (TW == 1) {
+          if (active && pl == 0) {
+            double* rec = lines_n + m.gr_ul[gr[GR_FIRST] + k0 + k] * BAYSAR_LINE_STRIDE;
+            rec[0] = s0; rec[1] = s1; rec[2] = s2; rec[3] = s0 * dens_over_max; rec[4] = s4;
+          }
+        } else {
+          __syncthreads();  // the exchange slots' previous use
+          if (active && pl == 0) {
+            double* x = team.xch + (wi * 32 + k) * 4;
+            x[0] = s0; x[1] = s1; x[2] = s2; x[3] = s4;
+          }
+          __syncthreads();
+          if ((int)threadIdx.x < K) {
+            double t[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int w = 0; w < TW; ++w) {
+              const double* x = team.xch + (w * 32 + (int)threadIdx.x) * 4;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) t[q] += x[q];
+            }
+            double* rec = lines_n + m.gr_ul[gr[GR_FIRST] + k0 + (int)threadIdx.x] * BAYSAR_LINE_STRIDE;
+            rec[0] = t[0]; rec[1] = t[1]; rec[2] = t[2]; rec[3] = t[0] * dens_over_max; rec[4] = t[3];
+          }
+        }
       }
     }
   }

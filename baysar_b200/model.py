@@ -5,6 +5,7 @@ The reference keeps this information in a web of mutable Python objects that eve
 (SURVEY.md §1); here it is resolved ONCE into index maps, constant tables and per-chord records so that a theta
 batch can be evaluated by three kernel launches with no host involvement.
 """
+import collections
 import re
 import struct
 
@@ -31,7 +32,7 @@ def _parse_layout():
 
 ENUMS, BLOB_MAGIC, BLOB_VERSION = _parse_layout()
 SEC = ENUMS["BaysarSection"]
-_DTYPES = {"SEC_PR_AUX": np.int32, "SEC_MESH_LO": np.int32, "SEC_I": np.int64, "SEC_SP_I": np.int32, "SEC_ELEM_DENS_IDX": np.int32, "SEC_UL_I": np.int32,
+_DTYPES = {"SEC_GR_I": np.int32, "SEC_GR_UL": np.int32, "SEC_PR_AUX": np.int32, "SEC_MESH_LO": np.int32, "SEC_I": np.int64, "SEC_SP_I": np.int32, "SEC_ELEM_DENS_IDX": np.int32, "SEC_UL_I": np.int32,
            "SEC_PR_I": np.int32, "SEC_CSO_OFF": np.int32, "SEC_CSO_UL": np.int32, "SEC_CH_I": np.int32,
            "SEC_CL_I": np.int32, "SEC_PIX_IDX": np.int32}
 
@@ -168,15 +169,14 @@ def compile_model(plasma, chords, priors):
         tecs.append(coeffs)
     if tecs:
         tx, ty = plasma.tec_knots
-        c = np.array(tecs)  # [n_tec][n_tau][cells]
-        pairs = np.stack([c[:, :-1, :], c[:, 1:, :]], axis=-1)  # [n_tec][n_tau - 1][cells][2]: slices (i, i + 1)
-        sec["SEC_SPL_TX"], sec["SEC_SPL_TY"], sec["SEC_SPL_C"] = tx, ty, np.ascontiguousarray(pairs)
+        sec["SEC_SPL_TX"], sec["SEC_SPL_TY"] = tx, ty
         iset("I_SPL_NX", len(tx)), iset("I_SPL_NY", len(ty))
         if np.array(tecs).shape[-1] != (len(tx) - 4) * (len(ty) - 4):
             raise ValueError("unexpected spline coefficient count")
     else:
-        sec["SEC_SPL_TX"], sec["SEC_SPL_TY"], sec["SEC_SPL_C"] = np.zeros(8), np.zeros(8), np.zeros(2)
+        sec["SEC_SPL_TX"], sec["SEC_SPL_TY"] = np.zeros(8), np.zeros(8)
         iset("I_SPL_NX", 8), iset("I_SPL_NY", 8)
+    # (SEC_SPL_C follows the unique-line table: the coefficients are laid out per group of lines that share a species)
 
     # ---- unique lines and per-chord line objects
     ul_rows, ul_index = [], {}
@@ -310,6 +310,31 @@ def compile_model(plasma, chords, priors):
     sec["SEC_CL_D"] = np.array(cl_d_rows) if cl_d_rows else np.zeros((1, E_CL_D["CL_D_COUNT"]))
     sec["SEC_COMP_D"] = np.array(comps, dtype=float) if comps else np.zeros((1, 2))
     sec["SEC_UL_I"] = np.array(ul_rows, dtype=np.int32) if ul_rows else np.zeros((1, 4), np.int32)
+
+    # ---- ADAS line groups: the unique ADAS406 lines of one species share the tau slices, the density and, per
+    # line-of-sight point, the spline cell; their coefficients are stored side by side so that one gather serves them all
+    groups = collections.OrderedDict()
+    for u, (kind, sp, tab_a, _) in enumerate(ul_rows):
+        if kind == 1:
+            groups.setdefault(sp, []).append((u, tab_a))
+    gr_rows, gr_ul, coef_blocks, coef_off = [], [], [], 0
+    if groups:
+        ncx, ncy = len(sec["SEC_SPL_TX"]) - 4, len(sec["SEC_SPL_TY"]) - 4
+        iy1 = np.minimum(np.arange(ncy) + 1, ncy - 1)
+    for sp, members in groups.items():
+        c = np.array([tecs[t] for _, t in members])  # [n_k][n_tau][cells]
+        c = c.reshape(len(members), c.shape[1], ncx, ncy)
+        lo, hi = c[:, :-1], c[:, 1:]  # tau slices (i, i + 1)
+        block = np.stack([lo, hi, lo[..., iy1], hi[..., iy1]], axis=-1)  # [n_k][n_tau - 1][ncx][ncy][4]
+        block = np.ascontiguousarray(np.moveaxis(block, 0, 3))  # [n_tau - 1][ncx][ncy][n_k][4]
+        gr_rows.append([sp, len(members), len(gr_ul), coef_off // 4])
+        gr_ul += [u for u, _ in members]
+        coef_blocks.append(block.ravel())
+        coef_off += block.size
+    sec["SEC_GR_I"] = np.array(gr_rows or [[0, 0, 0, 0]], dtype=np.int32)
+    sec["SEC_GR_UL"] = np.array(gr_ul or [0], dtype=np.int32)
+    sec["SEC_SPL_C"] = np.concatenate(coef_blocks) if coef_blocks else np.zeros(4)
+    iset("I_N_GROUPS", len(gr_rows))
     sec["SEC_UL_D"] = np.array(ul_d_rows, dtype=float) if ul_d_rows else np.zeros((1, e["BaysarUlD"]["UL_D_COUNT"]))
     cat = lambda arrs, dt: np.concatenate(arrs).astype(dt) if arrs else np.zeros(2, dtype=dt)  # noqa: E731
     sec["SEC_Y"], sec["SEC_ERR"], sec["SEC_IF"] = cat(ys, float), cat(errs, float), cat(ifs, float)
@@ -398,17 +423,17 @@ def compile_model(plasma, chords, priors):
     n_sec = SEC["SEC_COUNT"]
     names = [n for n, i in sorted(SEC.items(), key=lambda kv: kv[1]) if n != "SEC_COUNT"]
     header_bytes = 8 * (3 + 2 * n_sec)
-    offset = (header_bytes + 15) // 16 * 16
+    offset = (header_bytes + 31) // 32 * 32  # sections start on 32-byte boundaries (256-bit loads of SEC_SPL_C)
     table, payload = [], []
     for name in names:
         arr = np.ascontiguousarray(sec[name], dtype=_DTYPES.get(name, np.float64))
         raw = arr.tobytes()
         table += [offset, arr.size]
-        pad = (-len(raw)) % 16
+        pad = (-len(raw)) % 32
         payload.append(raw + b"\0" * pad)
         offset += len(raw) + pad
     head = struct.pack(f"<{3 + 2 * n_sec}q", BLOB_MAGIC, BLOB_VERSION, n_sec, *table)
-    head += b"\0" * ((-len(head)) % 16)
+    head += b"\0" * ((-len(head)) % 32)
     blob = head + b"".join(payload)
     info["n_ulines"], info["blob_bytes"] = len(ul_rows), len(blob)
     return blob, info

@@ -4,6 +4,7 @@
 #include "../../baysar_b200/csrc/chord_stage.cuh"
 #include "../../baysar_b200/csrc/finalize.cuh"
 #include "../../baysar_b200/csrc/los_stage.cuh"
+#include "../../baysar_b200/csrc/los_tables.h"
 
 static ModelDev view(const unsigned char* blob) {
   const int64_t* hdr = reinterpret_cast<const int64_t*>(blob);
@@ -22,6 +23,11 @@ static ModelDev view(const unsigned char* blob) {
   d.comp_d = (const double*)P(SEC_COMP_D); d.y = (const double*)P(SEC_Y); d.err = (const double*)P(SEC_ERR);
   d.ifn = (const double*)P(SEC_IF); d.pix_idx = (const int*)P(SEC_PIX_IDX); d.pix_frac = (const double*)P(SEC_PIX_FRAC);
   d.mesh_x = (const double*)P(SEC_MESH_X); d.mesh_lo = (const int*)P(SEC_MESH_LO); d.pr_aux = (const int*)P(SEC_PR_AUX);
+  d.gr_i = (const int*)P(SEC_GR_I); d.gr_ul = (const int*)P(SEC_GR_UL);
+  // derived LOS tables: one set per process is enough for the tests (kept alive for the duration of the call chain)
+  static thread_local los_tables::Host lt;
+  lt = los_tables::build(d.I, d.a11_ne, d.a11_te, d.h_ne, d.h_te, d.spl_tx, d.spl_ty);
+  d.lt = los_tables::view(lt, lt.d.data(), lt.i.data());
   return d;
 }
 
@@ -102,7 +108,7 @@ extern "C" int emu_eval(const unsigned char* blob, const double* theta, long n, 
   EmuDim3 g;
   if (getenv("BAYSAR_EMU_LOS_TEAM")) {  // the one-CTA-per-theta form the product uses for long lines of sight
     g.x = (unsigned)n;
-    emu_launch(los_stage_kernel<4, 1, 1, 4>, g, 128u, los_smem_per_warp(L, (int)I[I_N_PARAMS], (int)I[I_N_SPECIES]) + 128, m, la);
+    emu_launch(los_stage_kernel<4, 1, 1, 4>, g, 128u, los_smem_per_warp(L, (int)I[I_N_PARAMS], (int)I[I_N_SPECIES]) + los_team_xch_bytes(4), m, la);
   } else {
     g.x = (unsigned)((n + 3) / 4);
     emu_launch(los_stage_kernel<4>, g, 128u, 4 * los_smem_per_warp(L, (int)I[I_N_PARAMS], (int)I[I_N_SPECIES]), m, la);
