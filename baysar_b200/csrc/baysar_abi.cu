@@ -100,13 +100,15 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
   // the best choice for many waves.  A batch of a few thousand thetas, though, is one or two waves, and then fitting
   // every CTA into ONE wave beats the spills of a tighter budget (4096 thetas: 1024 CTAs = 1.7 waves of 592 at 0.080 ms,
   // one wave of 7 CTAs per SM at 72 registers at 0.068 ms).  options.los_min_blocks overrides.
-  int minb = 4;
+  // (many waves: 5 CTAs per SM at 96 registers when the per-point cache leaves room for them -- multi-species chord
+  // 1.88 ms at 4, 1.76 at 5, 1.82 at 6 with its spills)
+  int minb = (size_t)232448 / (4 * per_warp + 1024) >= 5 ? 5 : 4;
   if (m->opt.los_min_blocks > 0) {
     minb = m->opt.los_min_blocks;
   } else {
     const int64_t ctas = (n + 3) / 4;
-    if (ctas > (int64_t)4 * m->sm_count)
-      for (int b = 5; b <= 7; ++b)
+    if (ctas > (int64_t)minb * m->sm_count)
+      for (int b = minb + 1; b <= 7; ++b)
         if (ctas <= (int64_t)b * m->sm_count) { minb = b; break; }
   }
   // Long lines of sight: the per-point cache (128 B per point and theta) starves the warp-per-theta form of occupancy
@@ -164,7 +166,11 @@ int ensure_ifc_workspace(baysar_model* m, int64_t n) {
 // Launch the chord kernel with the register budget that matches how many CTAs the shared-memory footprint lets an SM hold
 template <int MODE>
 int launch_chord_kernel(baysar_model* m, const ChordArgs& a, dim3 grid, size_t smem, cudaStream_t stream, bool single_tap_only = false) {
-  if (m->opt.chord_threads == 128) {  // half the threads per theta: the per-thread fixed costs are paid half as often
+  // 128 threads per (theta, chord) on short fine grids: with a few thousand points 256 threads have a dozen points each
+  // and the per-thread set-up and the barriers dominate (multi-species chord, 3000 points: 2.84 -> 2.62 ms); long grids
+  // keep 256 (Balmer demo, 8000 points: 0.119 vs 0.128 ms).  options.chord_threads overrides.
+  const bool nt128 = m->opt.chord_threads == 128 || (m->opt.chord_threads == 0 && m->I[I_F_MAX] <= 4096);
+  if (nt128) {
     auto kern = single_tap_only ? chord_stage_kernel<128, MODE, 6, false> : chord_stage_kernel<128, MODE, 6>;
     kern<<<grid, 128, smem, stream>>>(m->dev, a);
     CUDA_OK(cudaGetLastError());

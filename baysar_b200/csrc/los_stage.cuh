@@ -24,7 +24,7 @@ struct LosArgs {
 
 // bytes of dynamic shared memory one warp needs for L line-of-sight points
 __host__ __device__ static inline size_t los_smem_per_warp(int L, int n_params, int n_species) {
-  return (size_t)L * (14 * sizeof(double) + 2 * sizeof(int)) +
+  return (size_t)L * 10 * sizeof(double) + (size_t)(L + (L & 1)) * sizeof(int) +
          (size_t)(2 * n_params + 3 * n_species) * sizeof(double);
 }
 
@@ -133,14 +133,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
   double* __restrict__ spw = l10 + n_params;       // per species: ADAS tau-slice pair index and its two weights
   double* __restrict__ ne_s = spw + 3 * n_species;
   double* __restrict__ te_s = ne_s + L;
-  double* __restrict__ nm_s = te_s + L;   // main ion density
+  // The rest of the per-point cache is a union (its size bounds the thetas resident on an SM, and with them the warps
+  // that hide the latency of this kernel): first the main-ion and neutral densities and the adf15 cell of every point
+  // (neutral profile, Balmer lines, the priors on the profiles), then -- those are dead -- the spline cell and basis
+  // (ADAS line groups).
+  double* __restrict__ un_s = te_s + L;
+  double* __restrict__ nm_s = un_s;       // main ion density
   double* __restrict__ n0_s = nm_s + L;   // neutral density profile
   double* __restrict__ ha_s = n0_s + L;   // adf15-grid cell weights
   double* __restrict__ hb_s = ha_s + L;
-  double* __restrict__ bx_s = hb_s + L;   // [4][L] spline basis in ne (structure of arrays: conflict-free across lanes)
+  double* __restrict__ bx_s = un_s;       // [4][L] spline basis in ne (structure of arrays: conflict-free across lanes)
   double* __restrict__ by_s = bx_s + 4 * L;
-  int* __restrict__ ho_s = (int*)(by_s + 4 * L);  // adf15 cell: element offset of its (ne, Te) corner in a table
-  int* __restrict__ co_s = ho_s + L;              // spline cell: index of coefficient entry (lx - 3, ly - 3) in a group's table
+  int* __restrict__ ho_s = (int*)(un_s + 8 * L);  // adf15 cell: element offset of its (ne, Te) corner in a table
+  int* __restrict__ co_s = ho_s;                  // spline cell: index of coefficient entry (lx - 3, ly - 3) in a group's table
   const LosTablesDev& lt = m.lt;
   LosTeam<TW> team{reinterpret_cast<double*>(los_smem_raw + (size_t)(TW == 1 ? WARPS : 1) * los_smem_per_warp(L, n_params, n_species))};
 
@@ -290,19 +295,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     for (int l = lane; l < L; l += TS) n0_s[l] = 0.0;
   }
 
-  // ---- bicubic B-spline basis per LOS point, shared by every impurity line and tau slice
-  const int n_tec = (int)I[I_N_TEC];
-  const int snx = (int)I[I_SPL_NX], sny = (int)I[I_SPL_NY];
-  if (n_tec > 0) {
-    for (int l = lane; l < L; l += TS) {
-      int lx, ly; double hx[4], hy[4];
-      bspline_basis3_fast(m.spl_tx, snx, ne_s[l], lt, AX_SPL_X, lx, hx);
-      bspline_basis3_fast(m.spl_ty, sny, te_s[l], lt, AX_SPL_Y, ly, hy);
-      co_s[l] = (lx - 3) * (sny - 4) + (ly - 3);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { bx_s[q * L + l] = hx[q]; by_s[q * L + l] = hy[q]; }
-    }
-  }
   team.sync();
 
   if (a.profiles) {
@@ -357,152 +349,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       }
     }
   }
-  // ---- ADAS406 lines (linemodels.py:386-426, :445-494), one group at a time: the lines of one species share the tau
-  // slices, the density and, per line-of-sight point, the spline cell and basis.  The lanes of a warp are dealt
-  // (line k, point) pairs, K = min(32, lines) lines x P = 32 / K consecutive points per trip; the group's coefficients
-  // lie side by side (layout.h SEC_SPL_C), so the lanes of one cell read neighbouring bytes of the same cache lines
-  // and a gather costs one wavefront per distinct cell among P points, for all K lines at once -- the stage is bound
-  // by the L1 data pipe, and with one line at a time every line paid those wavefronts again.
-  {
-    const int n_groups = (int)I[I_N_GROUPS];
-    const int ncx = snx - 4, ncy = sny - 4;
-    const int wl = threadIdx.x & 31, wi = TW == 1 ? 0 : (int)(threadIdx.x >> 5);
-    for (int g = 0; g < n_groups; ++g) {
-      const int* gr = m.gr_i + g * GR_I_COUNT;
-      const int n_k = gr[GR_NK];
-      const int* sp = m.sp_i + gr[GR_SPECIES] * SP_I_COUNT;
-      // n0 = dens * (ne / ne_max) and the concentration weight n0 / ne = dens / ne_max (linemodels.py:392-394, :411):
-      // the two float64 divisions per point and line become one reciprocal per theta (relative difference ~1e-16)
-      const double dens_over_max = p10[sp[SP_DENS_IDX]] * inv_nemax;
-      const double* w3 = spw + 3 * gr[GR_SPECIES];
-      const int pair = (int)w3[0];
-      const double i_w = w3[1], j_w = w3[2];
-      const size_t entry = (size_t)n_k * 32, row_bytes = (size_t)ncy * entry;
-      const char* gbase = reinterpret_cast<const char*>(m.spl_c) +
-                          ((size_t)gr[GR_COEF_OFF] + (size_t)pair * ncx * ncy * n_k) * 32;
-      for (int k0 = 0; k0 < n_k; k0 += 32) {
-        const int K = n_k - k0 < 32 ? n_k - k0 : 32, P = 32 / K;
-        const int k = wl / P, pl = wl - k * P;
-        const bool active = k < K;
-        const char* lbase = gbase + (size_t)(k0 + (active ? k : 0)) * 32;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s4 = 0.0;
-        for (int p0 = wi * P; p0 < L; p0 += TW * P) {
-          const int l = p0 + pl;
-          if (active && l < L) {
-            const double ne = ne_s[l], te = te_s[l];
-            double vi, vj;
-            bspline_eval_group(lbase + (size_t)co_s[l] * entry, entry, row_bytes, bx_s + l, by_s + l, L, vi, vj);
-            double tec = exp_fast(vi) * i_w + exp_fast(vj) * j_w;
-            if (!(fabs(tec) <= 1.7976931348623157e308)) tec = nan_to_num(tec);
-            const double p = clip_lo((dens_over_max * ne) * tec, 1.0);
-            s0 += p; s1 += m.los_w[l] * p; s2 += p * ne; s4 += p * te;
-          }
-        }
-        // sums over the P lanes of every line: a shuffle tree that stays inside the segment
-        for (int o = 1; o < P; o <<= 1) {
-          const double t0 = __shfl_down_sync(0xffffffffu, s0, o), t1 = __shfl_down_sync(0xffffffffu, s1, o);
-          const double t2 = __shfl_down_sync(0xffffffffu, s2, o), t4 = __shfl_down_sync(0xffffffffu, s4, o);
-          if (pl + o < P) { s0 += t0; s1 += t1; s2 += t2; s4 += t4; }
-        }
-        // raw sums into the line records; the scalars follow below, one lane per line (as for the Balmer lines)
-        if (TW == 1) {
-          if (active && pl == 0) {
-            double* rec = lines_n + m.gr_ul[gr[GR_FIRST] + k0 + k] * BAYSAR_LINE_STRIDE;
-            rec[0] = s0; rec[1] = s1; rec[2] = s2; rec[3] = s0 * dens_over_max; rec[4] = s4;
-          }
-        } else {
-          __syncthreads();  // the exchange slots' previous use
-          if (active && pl == 0) {
-            double* x = team.xch + (wi * 32 + k) * 4;
-            x[0] = s0; x[1] = s1; x[2] = s2; x[3] = s4;
-          }
-          __syncthreads();
-          if ((int)threadIdx.x < K) {
-            double t[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int w = 0; w < TW; ++w) {
-              const double* x = team.xch + (w * 32 + (int)threadIdx.x) * 4;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) t[q] += x[q];
-            }
-            double* rec = lines_n + m.gr_ul[gr[GR_FIRST] + k0 + (int)threadIdx.x] * BAYSAR_LINE_STRIDE;
-            rec[0] = t[0]; rec[1] = t[1]; rec[2] = t[2]; rec[3] = t[0] * dens_over_max; rec[4] = t[3];
-          }
-        }
-      }
-    }
-  }
-  team.sync();
-  // line scalars from the raw sums, one lane per line (Balmer: linemodels.py:796-836)
-  for (int u = lane; u < n_ul; u += TS) {
-    const int* ul = m.ul_i + u * UL_I_COUNT;
-    double* rec = lines_n + u * BAYSAR_LINE_STRIDE;
-    if (ul[UL_KIND] == 1) {  // ADAS406 (linemodels.py:405-426)
-      const int* sp = m.sp_i + ul[UL_SPECIES] * SP_I_COUNT;
-      double s[5];
-#pragma unroll
-      for (int q = 0; q < 5; ++q) s[q] = rec[q];
-      const double ems_te = s[4] / s[0];
-      double ti;
-      if (cold_ions) ti = 0.01;
-      else if (thermalised) ti = ems_te;
-      else ti = p10[sp[SP_TI_IDX]];
-      rec[0] = s[1] / four_pi; rec[1] = s[2] / s[0]; rec[2] = s[3] / s[0]; rec[3] = ems_te; rec[4] = ti;
-      for (int q = 5; q < BAYSAR_LINE_STRIDE; ++q) rec[q] = 0.0;
-      continue;
-    }
-    if (ul[UL_KIND] != 0) continue;
-    double s[12];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) s[q] = rec[q];
-    s[8] = s[0] + s[1]; s[9] = s[2] + s[3]; s[10] = s[4] + s[6]; s[11] = s[5] + s[7];
-    double rec_sum = s[2] / four_pi, exc_sum = s[3] / four_pi, ems = s[9] / four_pi;
-    double rec_ne = s[4] / s[0], rec_te = s[5] / s[0], exc_ne = s[6] / s[1], exc_te = s[7] / s[1];
-    double f_rec = rec_sum / ems;
-    double ti;
-    const int* sp = m.sp_i + ul[UL_SPECIES] * SP_I_COUNT;
-    if (cold_neutrals) ti = 0.01;
-    else if (thermalised) ti = (1 - f_rec) * exc_te + f_rec * rec_te;
-    else ti = p10[sp[SP_TI_IDX]];
-    // shape constants shared by every chord that sees this line: Doppler-shifted centre (linemodels.py:239-241) and
-    // Doppler sigma (:298, lineshapes.py:128); the pow-heavy Stark half-widths follow, one lane per (line,
-    // recombination / excitation)
-    const double* ud = m.ul_d + u * UL_D_COUNT;
-    rec[0] = rec_sum; rec[1] = exc_sum; rec[2] = rec_ne; rec[3] = rec_te; rec[4] = exc_ne; rec[5] = exc_te;
-    rec[6] = ti; rec[7] = f_rec; rec[8] = s[10] / s[8]; rec[9] = s[11] / s[8]; rec[10] = ems;
-    const int vi = sp[SP_VEL_IDX];
-    const double cwl = vi >= 0 ? ud[UL_CWL0] * ((1e3 * th[vi]) / 299792458.0 + 1.0) : ud[UL_CWL0];
-    rec[13] = cwl;
-    rec[14] = cwl * 7.715e-5 * sqrt(ti / ud[UL_MASS]) * 0.42466090014400953;
-    rec[15] = 0.0;
-  }
-  team.sync();
-  // Stark half-widths gamma^2.5 of every Balmer line (stehle_param, linemodels.py:554-566): lane 2q / 2q+1 take the
-  // recombination / excitation width of the q-th Balmer line, so that all the pow() calls run side by side
-  for (int idx = lane; idx < 2 * n_ul; idx += TS) {
-    const int u = idx >> 1, which = idx & 1;
-    if (m.ul_i[u * UL_I_COUNT + UL_KIND] != 0) continue;
-    const double* ud = m.ul_d + u * UL_D_COUNT;
-    double* rec = lines_n + u * BAYSAR_LINE_STRIDE;
-    const double la = ud[UL_LOMAN_A], lb = ud[UL_LOMAN_B], lc = ud[UL_LOMAN_C];
-    const double wne = rec[2 + 2 * which], wte = rec[3 + 2 * which];
-    // 10 c (1e6 ne)^a / Te^b / 2 with the two general powers as one exponential of logarithms, and g^2.5 = g^2 sqrt(g):
-    // ~1e-14 relative against three pow() calls, a third of their instructions (the widths end up in float32)
-    const double g = (10.0 * lc * exp(la * log(1e6 * wne) - lb * log(wte))) / 2.0;
-    rec[11 + which] = g * g * sqrt(g);
-  }
-  team.sync();
 
   // ---- priors, in posterior_components order (posterior.py:108-161)
+  // Two passes: the priors on the profiles run while the densities are still cached (before the spline basis takes their
+  // place), the two that read line scalars (StarkToPeak, ChargeStateOrder) after the lines are done.
   double* comp = a.components + n * (int64_t)(n_chords + n_pr) + n_chords;
+  auto priors_pass = [&](const bool line_priors) {
   for (int k = 0; k < n_pr; ++k) {
     const int* pi = m.pr_i + k * PR_I_COUNT;
     const double* pd = m.pr_d + k * PR_D_COUNT;
     const int kind = pi[PR_KIND];
+    if ((kind == PRIOR_STARK_TO_PEAK || kind == PRIOR_CHARGE_STATE_ORDER) != line_priors) continue;
     double val = 0.0;
     if (kind == PRIOR_CURVATURE) {  // priors.py:104-127: curvature of the raw density-knot parameters
       // grad = numpy.gradient (unit spacing): central differences inside, one-sided at the two ends
       const int nk = (int)I[I_MESH_NE_N];
-      double* g1 = bx_s;  // scratch (the spline bases are dead by now)
+      double* g1 = by_s;  // scratch (the second half of the union: free while the densities are cached)
       double vmax = -1.7976931348623157e308;
       for (int q = 0; q < nk; ++q) vmax = th[ne_idx + q] > vmax ? th[ne_idx + q] : vmax;
       team.sync();
@@ -655,6 +517,162 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     }
     if (lane == 0) comp[k] = val;
   }
+  };
+
+  priors_pass(false);
+  team.sync();  // the densities are dead: the spline cell and basis take their place
+
+  // ---- bicubic B-spline basis per LOS point, shared by every impurity line and tau slice
+  const int n_tec = (int)I[I_N_TEC];
+  const int snx = (int)I[I_SPL_NX], sny = (int)I[I_SPL_NY];
+  if (n_tec > 0) {
+    for (int l = lane; l < L; l += TS) {
+      int lx, ly; double hx[4], hy[4];
+      bspline_basis3_fast(m.spl_tx, snx, ne_s[l], lt, AX_SPL_X, lx, hx);
+      bspline_basis3_fast(m.spl_ty, sny, te_s[l], lt, AX_SPL_Y, ly, hy);
+      co_s[l] = (lx - 3) * (sny - 4) + (ly - 3);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { bx_s[q * L + l] = hx[q]; by_s[q * L + l] = hy[q]; }
+    }
+  }
+  team.sync();
+
+  // ---- ADAS406 lines (linemodels.py:386-426, :445-494), one group at a time: the lines of one species share the tau
+  // slices, the density and, per line-of-sight point, the spline cell and basis.  The lanes of a warp are dealt
+  // (line k, point) pairs, K = min(32, lines) lines x P = 32 / K consecutive points per trip; the group's coefficients
+  // lie side by side (layout.h SEC_SPL_C), so the lanes of one cell read neighbouring bytes of the same cache lines
+  // and a gather costs one wavefront per distinct cell among P points, for all K lines at once -- the stage is bound
+  // by the L1 data pipe, and with one line at a time every line paid those wavefronts again.
+  {
+    const int n_groups = (int)I[I_N_GROUPS];
+    const int ncx = snx - 4, ncy = sny - 4;
+    const int wl = threadIdx.x & 31, wi = TW == 1 ? 0 : (int)(threadIdx.x >> 5);
+    for (int g = 0; g < n_groups; ++g) {
+      const int* gr = m.gr_i + g * GR_I_COUNT;
+      const int n_k = gr[GR_NK];
+      const int* sp = m.sp_i + gr[GR_SPECIES] * SP_I_COUNT;
+      // n0 = dens * (ne / ne_max) and the concentration weight n0 / ne = dens / ne_max (linemodels.py:392-394, :411):
+      // the two float64 divisions per point and line become one reciprocal per theta (relative difference ~1e-16)
+      const double dens_over_max = p10[sp[SP_DENS_IDX]] * inv_nemax;
+      const double* w3 = spw + 3 * gr[GR_SPECIES];
+      const int pair = (int)w3[0];
+      const double i_w = w3[1], j_w = w3[2];
+      const size_t entry = (size_t)n_k * 32, row_bytes = (size_t)ncy * entry;
+      const char* gbase = reinterpret_cast<const char*>(m.spl_c) +
+                          ((size_t)gr[GR_COEF_OFF] + (size_t)pair * ncx * ncy * n_k) * 32;
+      for (int k0 = 0; k0 < n_k; k0 += 32) {
+        const int K = n_k - k0 < 32 ? n_k - k0 : 32, P = 32 / K;
+        const int k = wl / P, pl = wl - k * P;
+        const bool active = k < K;
+        const char* lbase = gbase + (size_t)(k0 + (active ? k : 0)) * 32;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s4 = 0.0;
+        for (int p0 = wi * P; p0 < L; p0 += TW * P) {
+          const int l = p0 + pl;
+          if (active && l < L) {
+            const double ne = ne_s[l], te = te_s[l];
+            double vi, vj;
+            bspline_eval_group(lbase + (size_t)co_s[l] * entry, entry, row_bytes, bx_s + l, by_s + l, L, vi, vj);
+            double tec = exp_fast(vi) * i_w + exp_fast(vj) * j_w;
+            if (!(fabs(tec) <= 1.7976931348623157e308)) tec = nan_to_num(tec);
+            const double p = clip_lo((dens_over_max * ne) * tec, 1.0);
+            s0 += p; s1 += m.los_w[l] * p; s2 += p * ne; s4 += p * te;
+          }
+        }
+        // sums over the P lanes of every line: a shuffle tree that stays inside the segment
+        for (int o = 1; o < P; o <<= 1) {
+          const double t0 = __shfl_down_sync(0xffffffffu, s0, o), t1 = __shfl_down_sync(0xffffffffu, s1, o);
+          const double t2 = __shfl_down_sync(0xffffffffu, s2, o), t4 = __shfl_down_sync(0xffffffffu, s4, o);
+          if (pl + o < P) { s0 += t0; s1 += t1; s2 += t2; s4 += t4; }
+        }
+        // raw sums into the line records; the scalars follow below, one lane per line (as for the Balmer lines)
+        if (TW == 1) {
+          if (active && pl == 0) {
+            double* rec = lines_n + m.gr_ul[gr[GR_FIRST] + k0 + k] * BAYSAR_LINE_STRIDE;
+            rec[0] = s0; rec[1] = s1; rec[2] = s2; rec[3] = s0 * dens_over_max; rec[4] = s4;
+          }
+        } else {
+          __syncthreads();  // the exchange slots' previous use
+          if (active && pl == 0) {
+            double* x = team.xch + (wi * 32 + k) * 4;
+            x[0] = s0; x[1] = s1; x[2] = s2; x[3] = s4;
+          }
+          __syncthreads();
+          if ((int)threadIdx.x < K) {
+            double t[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int w = 0; w < TW; ++w) {
+              const double* x = team.xch + (w * 32 + (int)threadIdx.x) * 4;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) t[q] += x[q];
+            }
+            double* rec = lines_n + m.gr_ul[gr[GR_FIRST] + k0 + (int)threadIdx.x] * BAYSAR_LINE_STRIDE;
+            rec[0] = t[0]; rec[1] = t[1]; rec[2] = t[2]; rec[3] = t[0] * dens_over_max; rec[4] = t[3];
+          }
+        }
+      }
+    }
+  }
+  team.sync();
+  // line scalars from the raw sums, one lane per line (Balmer: linemodels.py:796-836)
+  for (int u = lane; u < n_ul; u += TS) {
+    const int* ul = m.ul_i + u * UL_I_COUNT;
+    double* rec = lines_n + u * BAYSAR_LINE_STRIDE;
+    if (ul[UL_KIND] == 1) {  // ADAS406 (linemodels.py:405-426)
+      const int* sp = m.sp_i + ul[UL_SPECIES] * SP_I_COUNT;
+      double s[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) s[q] = rec[q];
+      const double ems_te = s[4] / s[0];
+      double ti;
+      if (cold_ions) ti = 0.01;
+      else if (thermalised) ti = ems_te;
+      else ti = p10[sp[SP_TI_IDX]];
+      rec[0] = s[1] / four_pi; rec[1] = s[2] / s[0]; rec[2] = s[3] / s[0]; rec[3] = ems_te; rec[4] = ti;
+      for (int q = 5; q < BAYSAR_LINE_STRIDE; ++q) rec[q] = 0.0;
+      continue;
+    }
+    if (ul[UL_KIND] != 0) continue;
+    double s[12];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[q] = rec[q];
+    s[8] = s[0] + s[1]; s[9] = s[2] + s[3]; s[10] = s[4] + s[6]; s[11] = s[5] + s[7];
+    double rec_sum = s[2] / four_pi, exc_sum = s[3] / four_pi, ems = s[9] / four_pi;
+    double rec_ne = s[4] / s[0], rec_te = s[5] / s[0], exc_ne = s[6] / s[1], exc_te = s[7] / s[1];
+    double f_rec = rec_sum / ems;
+    double ti;
+    const int* sp = m.sp_i + ul[UL_SPECIES] * SP_I_COUNT;
+    if (cold_neutrals) ti = 0.01;
+    else if (thermalised) ti = (1 - f_rec) * exc_te + f_rec * rec_te;
+    else ti = p10[sp[SP_TI_IDX]];
+    // shape constants shared by every chord that sees this line: Doppler-shifted centre (linemodels.py:239-241) and
+    // Doppler sigma (:298, lineshapes.py:128); the pow-heavy Stark half-widths follow, one lane per (line,
+    // recombination / excitation)
+    const double* ud = m.ul_d + u * UL_D_COUNT;
+    rec[0] = rec_sum; rec[1] = exc_sum; rec[2] = rec_ne; rec[3] = rec_te; rec[4] = exc_ne; rec[5] = exc_te;
+    rec[6] = ti; rec[7] = f_rec; rec[8] = s[10] / s[8]; rec[9] = s[11] / s[8]; rec[10] = ems;
+    const int vi = sp[SP_VEL_IDX];
+    const double cwl = vi >= 0 ? ud[UL_CWL0] * ((1e3 * th[vi]) / 299792458.0 + 1.0) : ud[UL_CWL0];
+    rec[13] = cwl;
+    rec[14] = cwl * 7.715e-5 * sqrt(ti / ud[UL_MASS]) * 0.42466090014400953;
+    rec[15] = 0.0;
+  }
+  team.sync();
+  // Stark half-widths gamma^2.5 of every Balmer line (stehle_param, linemodels.py:554-566): lane 2q / 2q+1 take the
+  // recombination / excitation width of the q-th Balmer line, so that all the pow() calls run side by side
+  for (int idx = lane; idx < 2 * n_ul; idx += TS) {
+    const int u = idx >> 1, which = idx & 1;
+    if (m.ul_i[u * UL_I_COUNT + UL_KIND] != 0) continue;
+    const double* ud = m.ul_d + u * UL_D_COUNT;
+    double* rec = lines_n + u * BAYSAR_LINE_STRIDE;
+    const double la = ud[UL_LOMAN_A], lb = ud[UL_LOMAN_B], lc = ud[UL_LOMAN_C];
+    const double wne = rec[2 + 2 * which], wte = rec[3 + 2 * which];
+    // 10 c (1e6 ne)^a / Te^b / 2 with the two general powers as one exponential of logarithms, and g^2.5 = g^2 sqrt(g):
+    // ~1e-14 relative against three pow() calls, a third of their instructions (the widths end up in float32)
+    const double g = (10.0 * lc * exp(la * log(1e6 * wne) - lb * log(wte))) / 2.0;
+    rec[11 + which] = g * g * sqrt(g);
+  }
+  team.sync();
+
+  priors_pass(true);
 
   st = team.or_bits(st);
   if (lane == 0) {
