@@ -21,7 +21,7 @@ X_TRIPLET = [[[4024.78, 4025.33, 4026.33]], [[0.541, 0.373, 0.086]]]
 
 class Workload:
     def __init__(self, name, input_kwargs, los, reference_theta, description, profile=None, curvature=None,
-                 extra_priors=()):
+                 extra_priors=(), plasma_attrs=None):
         self.name = name
         self.input_kwargs = input_kwargs
         self.los = los  # None -> profile default linspace(-10, 25, 50)
@@ -31,6 +31,9 @@ class Workload:
         self.curvature = curvature  # BaysarPosterior(curvature=...) (CurvatureCost needs the mesh family)
         # optional priors appended after the default components: [(class name in priors.py, keyword arguments)]
         self.extra_priors = list(extra_priors)
+        # attributes assigned to posterior.plasma after construction, the way the reference's switches are used
+        # (recombining, reverse_electroneutrality, ne_tau)
+        self.plasma_attrs = dict(plasma_attrs or {})
 
     def make_priors(self, ns, plasma=None, plasma_state=None):
         """Instances of the optional priors from the namespace ``ns`` (the reference's ``baysar.priors`` or
@@ -141,6 +144,14 @@ def multi_species(n_chords=1, data="selfconsistent", flags=None):
     name = "multi_species" if n_chords == 1 else f"multi_species_{n_chords}chords"
     return Workload(name, kw, np.linspace(-10.0, 25.0, 100), ref,
                     f"D Balmer + N II/N III + C III + X triplet, {n_chords} chord(s)")
+
+
+def multi_species_switched(**plasma_attrs):
+    """The multi-species chord with post-construction plasma switches (`plasma.recombining = True`, ...)."""
+    wl = multi_species(1)
+    tag = "_".join(k for k, v in sorted(plasma_attrs.items()) if v)
+    return Workload(f"multi_{tag}", wl.input_kwargs, wl.los, wl.reference_theta, wl.description + f", plasma.{tag} = True",
+                    plasma_attrs=plasma_attrs)
 
 
 def multi_species_bowman(background=False):

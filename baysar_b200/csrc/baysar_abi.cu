@@ -365,7 +365,8 @@ int validate_blob(const void* desc_blob, size_t nbytes) {
       need(SEC_CH_I, nc * CH_I_COUNT, "CH_I") || need(SEC_CH_D, nc * CH_D_COUNT, "CH_D") ||
       need(SEC_CL_I, ncl * CL_I_COUNT, "CL_I") || need(SEC_CL_D, ncl * CL_D_COUNT, "CL_D") ||
       need(SEC_A11_NE, I[I_A11_NNE], "A11_NE") || need(SEC_A11_TE, I[I_A11_NTE], "A11_TE") ||
-      need(SEC_A11_SCD, I[I_A11_NNE] * I[I_A11_NTE], "A11_SCD") || need(SEC_H_NE, I[I_H_NNE], "H_NE") ||
+      need(SEC_A11_SCD, I[I_A11_NNE] * I[I_A11_NTE], "A11_SCD") ||
+      need(SEC_A11_ACD, I[I_RECOMBINING] ? I[I_A11_NNE] * I[I_A11_NTE] : 0, "A11_ACD") || need(SEC_H_NE, I[I_H_NNE], "H_NE") ||
       need(SEC_H_TE, I[I_H_NTE], "H_TE") || need(SEC_H_TAB, I[I_N_HTAB] * I[I_H_NNE] * I[I_H_NTE], "H_TAB") ||
       need(SEC_TAU_GRID, I[I_N_TAU], "TAU_GRID") || need(SEC_SPL_TX, I[I_SPL_NX], "SPL_TX") ||
       need(SEC_SPL_TY, I[I_SPL_NY], "SPL_TY") ||
@@ -471,6 +472,7 @@ int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, con
   d.a11_ne = static_cast<const double*>(dev.ptr(SEC_A11_NE));
   d.a11_te = static_cast<const double*>(dev.ptr(SEC_A11_TE));
   d.a11_scd = static_cast<const double*>(dev.ptr(SEC_A11_SCD));
+  d.a11_acd = static_cast<const double*>(dev.ptr(SEC_A11_ACD));
   d.h_ne = static_cast<const double*>(dev.ptr(SEC_H_NE));
   d.h_te = static_cast<const double*>(dev.ptr(SEC_H_TE));
   d.h_tab = static_cast<const double*>(dev.ptr(SEC_H_TAB));

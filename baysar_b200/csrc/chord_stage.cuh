@@ -260,6 +260,7 @@ BAYSAR_DEV void pixel_likelihood(const ModelDev& m, const int* ch, const double*
   const double cwl_map = cw_idx >= 0 ? th[cw_idx] : chd[CH_CALWAVE_CWL];
   const double disp_map = cw_idx >= 0 ? th[cw_idx + 1] : chd[CH_CALWAVE_DISP];
   double acc = 0.0;
+  const bool gauss = m.I[I_GAUSS_LIKELIHOOD] != 0;
   for (int p = tid; p < P; p += NT) {
     int i; double w;
     if (cw_idx >= 0) {
@@ -286,7 +287,12 @@ BAYSAR_DEV void pixel_likelihood(const ModelDev& m, const int* ch, const double*
     const double d = m.y[poff + p] - fm, er = m.err[poff + p];
     const float rf = (float)d / (float)er;
     const float ar = fabsf(rf);
-    if (ar < 1e15f) {
+    if (gauss) {  // likelihood(cauchy=False), spectrometers.py:187-188: -0.5 sum r^2 (float64: it is not the default path)
+      const double r = d / er, r2 = r * r;
+      if (r2 == 0.0) st |= 1u << 11;
+      if (!(r2 - r2 == 0.0)) st |= 1u << 12;
+      acc += 0.5 * r2;
+    } else if (ar < 1e15f) {
       if (d == 0.0 || ar == 0.f) st |= 1u << 11;
       acc += (double)log1pf(ar * ar);
     } else {
@@ -1229,6 +1235,7 @@ __global__ void __launch_bounds__(NT, BAYSAR_PIXFOLD_MINB) pixel_fold_kernel(Mod
     __syncthreads();
     const int P = ch[CH_P], poff = ch[CH_PIX_OFF];
     double acc = 0.0;
+    const bool gauss = m.I[I_GAUSS_LIKELIHOOD] != 0;
 #pragma unroll 4
     for (int p = tid; p < P; p += NT) {
       const int col = a.pix_col[p];
@@ -1243,7 +1250,12 @@ __global__ void __launch_bounds__(NT, BAYSAR_PIXFOLD_MINB) pixel_fold_kernel(Mod
       if (!(d - d == 0.0)) st |= 1u << 10;
       const float rf = (float)d * a.inv_err[p];
       const float ar = fabsf(rf);
-      if (ar < 1e15f) {
+      if (gauss) {  // likelihood(cauchy=False), spectrometers.py:187-188
+        const double r = d / m.err[poff + p], r2 = r * r;
+        if (r2 == 0.0) st |= 1u << 11;
+        if (!(r2 - r2 == 0.0)) st |= 1u << 12;
+        acc += 0.5 * r2;
+      } else if (ar < 1e15f) {
         if (d == 0.0 || ar == 0.f) st |= 1u << 11;
         acc += (double)log1pf(ar * ar);
       } else {

@@ -44,6 +44,7 @@ struct ModelDev {
   const double* a11_ne;
   const double* a11_te;
   const double* a11_scd;
+  const double* a11_acd;
   const double* h_ne;
   const double* h_te;
   const double* h_tab;

@@ -9,7 +9,7 @@
 #define BAYSAR_LAYOUT_H
 
 #define BAYSAR_BLOB_MAGIC 0x4252415359534142LL /* "BAYSYSAB" */
-#define BAYSAR_BLOB_VERSION 10
+#define BAYSAR_BLOB_VERSION 11
 
 enum BaysarSection {
   SEC_I,              /* int64  [I_COUNT]           model-wide integer scalars                         */
@@ -23,6 +23,7 @@ enum BaysarSection {
   SEC_A11_NE,         /* double [a11_nne]           adf11 (scd) density grid                           */
   SEC_A11_TE,         /* double [a11_nte]                                                              */
   SEC_A11_SCD,        /* double [a11_nne][a11_nte]  ionisation rate, raw values                        */
+  SEC_A11_ACD,        /* double [a11_nne][a11_nte]  recombination rate on the same grid (used when I_RECOMBINING) */
   SEC_H_NE,           /* double [h_nne]             adf15 density grid                                 */
   SEC_H_TE,           /* double [h_nte]                                                                */
   SEC_H_TAB,          /* double [n_htab][h_nne][h_nte]  log(PEC)                                       */
@@ -90,6 +91,9 @@ enum BaysarI {
   I_MESH_NE_N,          /* MeshLine: number of density / temperature knots */
   I_MESH_TE_N,
   I_N_GROUPS,           /* ADAS line groups */
+  I_RECOMBINING,        /* plasma.recombining: the neutral profile gains n1 ne acd tau before the ionisation loss (plasmas.py:735-737) */
+  I_REVERSE_EN,         /* plasma.reverse_electroneutrality: the sampled profile is the main-ion density (plasmas.py:667-671) */
+  I_GAUSS_LIKELIHOOD,   /* chord likelihood -0.5 sum r^2 instead of the Cauchy form (spectrometers.py:185-188) */
   I_COUNT
 };
 

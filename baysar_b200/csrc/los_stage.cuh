@@ -230,9 +230,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     }
   }
   nemax = team.max(nemax);
-  const double inv_nemax = 1.0 / nemax;
+  double inv_nemax = 1.0 / nemax;
 
   // ---- impurity electrons, main ion density (plasmas.py:876-889, :673)
+  const int reverse_en = (int)I[I_REVERSE_EN];
   for (int l = lane; l < L; l += TS) {
     double ne = ne_s[l], tot = 0.0;
     for (int e = 0; e < n_elem; ++e) {
@@ -240,7 +241,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       double conc = (dens * inv_nemax) * ne;
       tot += (conc * inv_nemax) * ne;
     }
-    nm_s[l] = ne - nan_to_num(tot);
+    nm_s[l] = reverse_en ? nan_to_num(tot) : ne - nan_to_num(tot);
+  }
+  if (reverse_en) {
+    // plasma.reverse_electroneutrality (plasmas.py:667-671): the sampled profile is the main-ion density and the impurity
+    // electrons (formed above from it, :666) are added to the electron density every later stage sees
+    double mx = -1.7976931348623157e308;
+    for (int l = lane; l < L; l += TS) {
+      const double n1 = ne_s[l], ne = n1 + nm_s[l];  // (the loop above parked the impurity electrons there)
+      nm_s[l] = n1;
+      ne_s[l] = ne;
+      mx = ne > mx ? ne : mx;
+    }
+    nemax = team.max(mx);
+    inv_nemax = 1.0 / nemax;
   }
 
   // ---- impurity tau must index the ADAS tau grid (plasmas.py:1410-1429 raise; linemodels.py:454-467)
@@ -271,6 +285,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     const double tau_h = p10[sp[SP_TAU_IDX]];
     const double n0_sampled = dens_idx >= 0 ? p10[dens_idx] : 0.0;
     const int nne = (int)I[I_A11_NNE], nte = (int)I[I_A11_NTE];
+    const int recombining = (int)I[I_RECOMBINING];
     for (int l = lane; l < L; l += TS) {
       double ne = ne_s[l], te = te_s[l];
       int ci, cj; double ca, cb;
@@ -278,6 +293,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       linear_cell_fast(m.a11_te, nte, te, lt, AX_A11_TE, cj, cb);
       double scd = bilinear(m.a11_scd, nte, ci, cj, ca, cb);
       double n0 = dens_idx >= 0 ? n0_sampled : nm_s[l];
+      if (recombining) n0 += nm_s[l] * ne * bilinear(m.a11_acd, nte, ci, cj, ca, cb) * tau_h;  // plasmas.py:735-737
       n0 = n0 - n0 * ne * scd * tau_h;
       n0 = clip_lo(n0, 1.0);
       if (n0 != n0) st |= 1u << 3;

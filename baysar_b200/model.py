@@ -76,8 +76,9 @@ def _single_tap_guaranteed(plasma, chord):
     return True
 
 
-def compile_model(plasma, chords, priors):
-    """-> (blob bytes, info dict).  ``priors``: the prior descriptors in posterior_components order."""
+def compile_model(plasma, chords, priors, gaussian_likelihood=False):
+    """-> (blob bytes, info dict).  ``priors``: the prior descriptors in posterior_components order.
+    ``gaussian_likelihood``: the chords return ``likelihood(cauchy=False)`` (reference spectrometers.py:187-188)."""
     e = ENUMS
     I = np.zeros(e["BaysarI"]["I_COUNT"], dtype=np.int64)
     iset = lambda name, v: I.__setitem__(e["BaysarI"][name], int(v))  # noqa: E731
@@ -150,6 +151,13 @@ def compile_model(plasma, chords, priors):
     if plasma.contains_hydrogen:
         scd = plasma.neutral_adf11s["scd"]
         sec["SEC_A11_NE"], sec["SEC_A11_TE"], sec["SEC_A11_SCD"] = scd.ne, scd.te, scd.select(1)
+        sec["SEC_A11_ACD"] = np.zeros(2)
+        if getattr(plasma, "recombining", False) is True:  # plasmas.py:735-737 tests `is True`
+            acd = plasma.neutral_adf11s["acd"]
+            if not (np.array_equal(acd.ne, scd.ne) and np.array_equal(acd.te, scd.te)):
+                raise NotImplementedError("recombining: the hydrogen acd and scd tables must share one (ne, Te) grid")
+            sec["SEC_A11_ACD"] = acd.select(1)
+            iset("I_RECOMBINING", 1)
         sec["SEC_H_NE"], sec["SEC_H_TE"] = plasma.hydrogen_pec_grid
         for key, tab in plasma.hydrogen_pecs.items():
             htab_index[key] = len(htabs)
@@ -157,7 +165,7 @@ def compile_model(plasma, chords, priors):
         iset("I_A11_NNE", len(scd.ne)), iset("I_A11_NTE", len(scd.te))
         iset("I_H_NNE", len(sec["SEC_H_NE"])), iset("I_H_NTE", len(sec["SEC_H_TE"]))
     else:
-        for k in ("SEC_A11_NE", "SEC_A11_TE", "SEC_A11_SCD", "SEC_H_NE", "SEC_H_TE"):
+        for k in ("SEC_A11_NE", "SEC_A11_TE", "SEC_A11_SCD", "SEC_A11_ACD", "SEC_H_NE", "SEC_H_TE"):
             sec[k] = np.zeros(2)
     sec["SEC_H_TAB"] = np.array(htabs) if htabs else np.zeros(2)
 
@@ -412,6 +420,8 @@ def compile_model(plasma, chords, priors):
     iset("I_COLD_NEUTRALS", plasma.cold_neutrals), iset("I_COLD_IONS", plasma.cold_ions)
     iset("I_THERMALISED", plasma.thermalised), iset("I_CAL_WAVE", plasma.calibrate_wavelength)
     iset("I_CAL_INT", plasma.calibrate_intensity), iset("I_CAL_IF", plasma.calibrate_instrument_function)
+    iset("I_REVERSE_EN", bool(getattr(plasma, "reverse_electroneutrality", False)))
+    iset("I_GAUSS_LIKELIHOOD", bool(gaussian_likelihood))
     iset("I_N_HTAB", len(htabs)), iset("I_N_TAU", len(sec["SEC_TAU_GRID"])), iset("I_N_TEC", len(tecs))
     iset("I_P_MAX", max([len(c.x_data) for c in chords] or [0]))
     iset("I_F_MAX", max([len(c.x_data_fm) for c in chords] or [0]))

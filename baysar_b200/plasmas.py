@@ -94,6 +94,17 @@ class GaussianInstrumentFunctionCalibratior(_Functional):
 
 
 class PlasmaLine:
+    # post-construction switches the reference reads with hasattr() on every evaluation (plasmas.py:663, :735-737,
+    # linemodels.py:398): here they are compiled into the device model, so assigning one makes the posterior recompile
+    _RECOMPILE_ATTRS = ("recombining", "ne_tau", "reverse_electroneutrality")
+
+    def __setattr__(self, name, value):
+        object.__setattr__(self, name, value)
+        if name in self._RECOMPILE_ATTRS:
+            callback = self.__dict__.get("_on_option_change")
+            if callback is not None:
+                callback()
+
     def __init__(self, input_dict, profile_function=None, atomic_data=None):
         self.input_dict = d = input_dict
         self.atomic_data = atomic_data if atomic_data is not None else SyntheticADAS()
@@ -313,15 +324,17 @@ class PlasmaLine:
     def __call__(self, theta):
         self.update_plasma_state(theta)
 
-    def update_plasma_state(self, theta):
-        """Evaluate the line-of-sight stage on the GPU for one theta and publish the result in ``plasma_state``."""
+    def update_plasma_state(self, theta, out=None):
+        """Evaluate the line-of-sight stage on the GPU for one theta (or take its result ``out`` from a batched
+        evaluation) and publish it in ``plasma_state``."""
         theta = np.asarray(theta, dtype=float).ravel()
         if len(theta) != self.n_params:
             raise ValueError("len(theta)!=self.n_params")
         if self._evaluator is None:
             raise RuntimeError("PlasmaLine is not attached to a BaysarPosterior (no CUDA model to evaluate with)")
         self.plasma_theta = collections.OrderedDict((p, theta[s]) for p, s in self.slices.items())
-        out = self._evaluator(theta)
+        if out is None:
+            out = self._evaluator(theta)
         for p, s in self.slices.items():
             v = np.array(theta[s], dtype=float).flatten()
             if p in ("electron_density", "electron_temperature"):

@@ -66,10 +66,12 @@ def build_components(plasma, input_dict, curvature=None, passed_priors=()):
         priors.append(MainIonFractionCost())
         priors.append(ChargeStateOrderPrior(chords, plasma))
     for p in passed_priors:
-        if not isinstance(p, _DevicePrior):
-            raise NotImplementedError(f"user prior {type(p).__name__} has no device implementation; only the default "
-                                      "components of posterior.py:108-161 run on the CUDA path")
-        # posterior.py:163-165: `got_p(p)` compares types with the INSTANCE p, so a passed prior is always appended
+        # posterior.py:163-165: `got_p(p)` compares types with the INSTANCE p, so a passed prior is always appended.
+        # Priors of this package's classes are rows of the device prior table; any other zero-argument callable is a
+        # HOST prior, called like the reference calls it (posterior.py:228) after the plasma state and the line
+        # attributes of the theta at hand have been published (see BaysarPosterior._host_prior_sum).
+        if not isinstance(p, _DevicePrior) and not callable(p):
+            raise TypeError("priors must be callables: `sum(p() for p in posterior_components)` (posterior.py:228)")
         priors.append(p)
     return chords, priors
 
@@ -121,21 +123,50 @@ class BaysarPosterior:
 
         self.chords, self.priors = build_components(self.plasma, input_dict, curvature, priors)
         self.posterior_components = list(self.chords) + list(self.priors)
+        self.device_priors = [p for p in self.priors if isinstance(p, _DevicePrior)]
+        self.host_priors = [p for p in self.priors if not isinstance(p, _DevicePrior)]
         set_sensible_bounds(self.plasma, self.chords)
 
-        self.blob, self.model_info = compile_model(self.plasma, self.chords, self.priors)
         if device is None:
             import torch
 
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
         self.device = int(device)
-        self.model = runtime.DeviceModel(self.blob, self.device, options)  # raises without a GPU / library: no CPU fallback
+        self._options = options
+        self._models = {}  # gaussian_likelihood flag -> (blob, info, DeviceModel)
+        self._compile(False)  # raises without a GPU / library: no CPU fallback
         for c in self.chords:
             c._posterior = self
-        for k, p in enumerate(self.priors):
+        for k, p in enumerate(self.device_priors):
             p._posterior, p._column = self, len(self.chords) + k
         self.plasma._evaluator = self._evaluate_los
+        self.plasma._on_option_change = self._models.clear  # recombining / reverse_electroneutrality / ne_tau: recompile
         self.init_test(skip_test)
+
+    # ------------------------------------------------------------------------------------------ compiled device models
+    def _compile(self, gaussian):
+        """Compile (once per state of the plasma's switches) the descriptor blob and create its device model."""
+        if gaussian not in self._models:
+            if getattr(self.plasma, "ne_tau", False) and len(self.plasma.impurity_species) > 0 and len(self.plasma.los) > 1:
+                # linemodels.py:398-399 turns tau into an array over the line of sight and get_tec (:454) then takes the
+                # truth value of an array: the reference raises this on every evaluation of an impurity line
+                raise ValueError("The truth value of an array with more than one element is ambiguous. "
+                                 "Use a.any() or a.all()")
+            blob, info = compile_model(self.plasma, self.chords, self.device_priors, gaussian_likelihood=gaussian)
+            self._models[gaussian] = (blob, info, runtime.DeviceModel(blob, self.device, self._options))
+        return self._models[gaussian]
+
+    @property
+    def model(self):
+        return self._compile(False)[2]
+
+    @property
+    def blob(self):
+        return self._compile(False)[0]
+
+    @property
+    def model_info(self):
+        return self._compile(False)[1]
 
     # ------------------------------------------------------------------------------------------ reference protocol
     def check_init_inputs(self, priors, check_bounds, temper, curvature, print_errors):
@@ -173,13 +204,19 @@ class BaysarPosterior:
     def __call__(self, theta, skip_error=False):
         import torch
 
+        self._sync_components()
         if isinstance(theta, torch.Tensor):
-            if theta.dim() == 2:
+            if theta.dim() == 2 and not self.host_priors:
                 return self.logp_batch(theta)
+            device = theta.device
             theta = theta.detach().cpu().numpy()
+            if theta.ndim == 2:  # user prior callables run on the host (see _add_host_priors)
+                return torch.as_tensor(self(theta), device=device)
         arr = np.asarray(theta, dtype=float)
         if arr.ndim == 2:
             logp, status = self.model.eval_logp_host(arr)
+            if self.host_priors:
+                logp, status = self._add_host_priors(arr, logp, status)
             self.last_status = status
             return logp
         theta = list(arr)
@@ -187,13 +224,61 @@ class BaysarPosterior:
         if not skip_error:
             self.check_call_input(theta, skip_error)
         logp, status = self.model.eval_logp_host(arr[None, :])
-        self.last_status = status
         prob = float(logp[0])
         self._publish_line_attributes(arr)
+        if self.host_priors:
+            prob, status = self._finish_host(prob + self._host_prior_sum(), status)
+        self.last_status = status
         if not skip_error:
             self._raise_from_status(int(status[0]), theta=theta)
         self.last_proposal_logp = prob
         return prob
+
+    # ------------------------------------------------------------------------------------------ user prior callables
+    def _sync_components(self):
+        """``posterior_components`` is the live list the reference sums on every call (posterior.py:228), and user scripts
+        append priors to it after construction.  Re-derive the device prior table (recompiling when it changed) and
+        the host callables from it."""
+        tail = self.posterior_components[len(self.chords):]
+        dev = [p for p in tail if isinstance(p, _DevicePrior)]
+        if len(dev) != len(self.device_priors) or any(a is not b for a, b in zip(dev, self.device_priors)):
+            self.device_priors = dev
+            for k, p in enumerate(dev):
+                p._posterior, p._column = self, len(self.chords) + k
+            self._models.clear()
+        self.host_priors = [p for p in tail if not isinstance(p, _DevicePrior)]
+        self.priors = list(tail)
+
+    def _host_prior_sum(self):
+        """Sum of the user-supplied prior callables for the state just published (reference posterior.py:228)."""
+        return sum(p() for p in self.host_priors)
+
+    @staticmethod
+    def _finish_host(prob, status):
+        """The output checks of posterior.py:249-258 on a total that includes host priors (bits 13-15 of the status)."""
+        status = np.array(status, dtype=np.uint32, copy=True)
+        status[0] &= ~np.uint32(0xE000)
+        if np.isnan(prob):
+            status[0] |= 1 << 13
+        elif np.isinf(prob):
+            status[0] |= 1 << 14
+        elif prob >= 0:
+            status[0] |= 1 << 15
+        return prob, status
+
+    def _add_host_priors(self, thetas, logp, status):
+        """Batched call with user prior callables.  The device evaluates chords and device priors for the whole batch in
+        one launch; the callables are Python and read ``plasma.plasma_state`` / line attributes, so they are called
+        once per theta on the host after that theta's state (one batched LOS launch for all of them) is published.
+        A batch with host priors is therefore host-bound: use the package's prior classes where throughput matters."""
+        logp = np.array(logp, dtype=float, copy=True)
+        status = np.array(status, dtype=np.uint32, copy=True)
+        lines, _, prof = self.lines_batch(thetas, want_profiles=True)
+        for n, theta in enumerate(thetas):
+            out = dict(ne=prof[n, 0], te=prof[n, 1], main_ion_density=prof[n, 2], n0=prof[n, 3], lines=lines[n])
+            self._publish_line_attributes(theta, out)
+            logp[n], status[n:n + 1] = self._finish_host(logp[n] + self._host_prior_sum(), status[n:n + 1])
+        return logp, status
 
     def check_call_input(self, theta, skip_error):
         if any(np.isnan(theta)):
@@ -288,9 +373,11 @@ class BaysarPosterior:
         """``-gradient``: what `baysar/optimisation.py:84-92` passes to L-BFGS-B as ``fprime`` when it exists."""
         return -self.gradient(theta, step)
 
-    def components_batch(self, theta):
-        """-> (components [N, n_chords + n_priors], status) as numpy arrays, reference posterior_components order."""
-        _, status, comps = self.model.eval_logp(self._as_device(theta), want_components=True)
+    def components_batch(self, theta, gaussian=False):
+        """-> (components [N, n_chords + n_device_priors], status) as numpy arrays: the chords, then the device priors in
+        posterior_components order (host prior callables have no column).  ``gaussian``: the chord columns hold
+        ``likelihood(cauchy=False)`` (a second device model, compiled on first use)."""
+        _, status, comps = self._compile(bool(gaussian))[2].eval_logp(self._as_device(theta), want_components=True)
         return comps.cpu().numpy(), status.cpu().numpy().astype(np.uint32)
 
     def spectra_batch(self, theta, chord=0, want_fine=False):
@@ -308,9 +395,9 @@ class BaysarPosterior:
         lines, _, prof = self.lines_batch(np.asarray(theta, dtype=float)[None], want_profiles=True)
         return dict(ne=prof[0, 0], te=prof[0, 1], main_ion_density=prof[0, 2], n0=prof[0, 3], lines=lines[0])
 
-    def _publish_line_attributes(self, theta):
+    def _publish_line_attributes(self, theta, out=None):
         """After a scalar call, expose the reference's line attributes and plasma_state (priors/demos read them)."""
-        out = self.plasma.update_plasma_state(theta)
+        out = self.plasma.update_plasma_state(theta, out)
         for c, chord in enumerate(self.chords):
             for k, line in enumerate(chord.lines):
                 line._publish(out["lines"][self.model_info["chord_line_uline"][c][k]])

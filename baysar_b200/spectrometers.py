@@ -200,10 +200,10 @@ class SpectrometerChord:
         return spectra[0]
 
     def likelihood(self, cauchy=True):
-        if not cauchy:
-            raise NotImplementedError("only the Cauchy likelihood is on the CUDA path (the reference's default)")
+        """logP of the spectral fit for the posterior's last theta (spectrometers.py:154-195): Cauchy by default,
+        ``cauchy=False`` the Gaussian form -0.5 sum r^2 (a second device model, compiled on first use)."""
         post = self._require()
-        comps, status = post.components_batch(np.asarray(post.last_proposal, dtype=float)[None])
+        comps, status = post.components_batch(np.asarray(post.last_proposal, dtype=float)[None], gaussian=not cauchy)
         post._raise_from_status(int(status[0]), mask=0x1FFF)
         return float(comps[0, self.chord_number])
 

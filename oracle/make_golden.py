@@ -100,12 +100,15 @@ def main():
         ("multi_bowman_priors", configs.multi_species_bowman_priors(), 8, 0, {}),
         ("balmer_hot", configs.balmer_series(flags=dict(cold_neutrals=False)), 10, 1, {}),
         ("multi_species_32chords", configs.multi_species(32), 3, 0, {}),
+        ("multi_recombining", configs.multi_species_switched(recombining=True), 10, 0, {}),
+        ("multi_reverse_electroneutrality", configs.multi_species_switched(reverse_electroneutrality=True), 10, 0, {}),
+        ("multi_ne_tau", configs.multi_species_switched(ne_tau=True), 3, 0, {}),
     ]
     only = sys.argv[1:]
     for name, wl, n, nfine, attrs in jobs:
         if only and name not in only:
             continue
-        post = ref_harness.build_reference_posterior(wl, plasma_attrs=attrs)
+        post = ref_harness.build_reference_posterior(wl, plasma_attrs={**wl.plasma_attrs, **attrs})
         thetas = ref_harness.draw_thetas(post, n, wl, seed=20261019)
         rec = ref_harness.evaluate(post, thetas, full_fine_grid=nfine)
         save(name, post, rec)

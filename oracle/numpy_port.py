@@ -247,7 +247,11 @@ def curvature(profile):
 class OraclePosterior:
     """Stateless restatement of ``BaysarPosterior`` for the default component set."""
 
-    def __init__(self, input_dict, provider, profile_function=None, curvature=None, extra_priors=()):
+    def __init__(self, input_dict, provider, profile_function=None, curvature=None, extra_priors=(), plasma_attrs=None):
+        # post-construction switches of the reference's PlasmaLine (read with hasattr on every evaluation):
+        # recombining (plasmas.py:735-737), reverse_electroneutrality (:663-671), ne_tau (linemodels.py:398-399)
+        for k in ("recombining", "reverse_electroneutrality", "ne_tau"):
+            setattr(self, k, (plasma_attrs or {}).get(k, False))
         self.input_dict = input_dict
         self.curvature = curvature
         self.extra_priors = list(extra_priors)  # [(class name, kwargs)] appended after the default components
@@ -632,7 +636,11 @@ class OraclePosterior:
             conc = (st[sp + "_dens"] / ne.max()) * ne
             total = total + (conc / ne.max()) * ne
         st["total_impurity_electrons"] = np.nan_to_num(total)
-        st["main_ion_density"] = ne - st["total_impurity_electrons"]
+        if self.reverse_electroneutrality:  # plasmas.py:667-671
+            st["main_ion_density"] = ne.copy()
+            ne = st["electron_density"] = ne + st["total_impurity_electrons"]
+        else:
+            st["main_ion_density"] = ne - st["total_impurity_electrons"]
         for sp in self.impurity_species:  # get_impurity_electrons / impurity_power index the tau grid (Q16)
             lt = np.log10(st[sp + "_tau"][0])
             if not (lt > self.magical_tau[0] and lt <= self.magical_tau[-1]):
@@ -644,6 +652,8 @@ class OraclePosterior:
             n0 = st[sp + "_dens"][0] if (sp + "_dens") in self.slices else n1.copy()
             rates = {k: bilinear_extrap(g_ne, g_te, tab, ne, te) for k, (g_ne, g_te, tab) in self.neutral_adf11.items()}
             tau = st[sp + "_tau"][0]
+            if self.recombining is True:  # plasmas.py:735-737
+                n0 = n0 + n1 * ne * rates["acd"] * tau
             n0 = n0 - n0 * ne * rates["scd"] * tau
             st[sp + "_dens"] = n0.clip(1)
             st["adf11"] = rates
@@ -708,6 +718,10 @@ class OraclePosterior:
         ne, te = st["electron_density"], st["electron_temperature"]
         n0 = st[sp + "_dens"][0] * (ne / ne.max())
         tau = st[sp + "_tau"][0]
+        if self.ne_tau:  # linemodels.py:398-399: tau becomes an array over the line of sight ...
+            tau = 1e3 * tau / (ne * 1e-13)
+            if np.size(tau) > 1:  # ... and get_tec (:454) takes the truth value of an array comparison
+                raise OracleError("ValueError", "The truth value of an array with more than one element is ambiguous")
         cwls = line["lines"]
         if sp + "_velocity" in st:
             cwls = line["cwls"] * (st[sp + "_velocity"][0] / speed_of_light + 1)
@@ -789,14 +803,14 @@ class OraclePosterior:
             raise OracleError("TypeError", "spectra contains NaNs/infs")
         return out, scalars
 
-    def likelihood(self, ch, fm):
-        """spectrometers.py:154-195 (Cauchy)."""
+    def likelihood(self, ch, fm, cauchy=True):
+        """spectrometers.py:154-195 (Cauchy by default, :187-188 the Gaussian form)."""
         r2 = ((ch.y_data - fm) / ch.error) ** 2
         if (r2 == 0).any():
             raise OracleError("ValueError", "Some points of square_normalised_residuals are zero")
         if np.isinf(r2).any() or np.isnan(r2).any():
             raise OracleError("ValueError", "Some points of square_normalised_residuals are inf/nan")
-        return -np.log(1 + r2).sum()
+        return -np.log(1 + r2).sum() if cauchy else -0.5 * r2.sum()
 
     def prior(self, name, args, st, line_scalars):
         """priors.py — the default components (`posterior.py:108-161`)."""
@@ -924,6 +938,8 @@ class OraclePosterior:
             scalars.append(sc)
             extra.append(want)
             comps.append(self.likelihood(ch, fm))
+            if details:
+                want["gauss_likelihood"] = self.likelihood(ch, fm, cauchy=False)
         for name, args in self.priors:
             comps.append(self.prior(name, args, st, scalars))
         prob = sum(comps)

@@ -93,6 +93,7 @@ def evaluate(post, thetas, full_fine_grid=0):
         rec[f"c{c}_spectra"] = np.full((n, len(ch.x_data)), np.nan)
         rec[f"c{c}_preconv_integral"] = np.full(n, np.nan)
         rec[f"c{c}_postconv_integral"] = np.full(n, np.nan)
+        rec[f"c{c}_gauss_likelihood"] = np.full(n, np.nan)  # SpectrometerChord.likelihood(cauchy=False)
         rec[f"c{c}_line_scalars"] = np.full((n, len(ch.lines), len(_BALMER_FIELDS)), np.nan)
         if full_fine_grid:
             rec[f"c{c}_fine_lines_sum"] = np.full((min(n, full_fine_grid), len(ch.x_data_fm)), np.nan)
@@ -117,6 +118,7 @@ def evaluate(post, thetas, full_fine_grid=0):
                     rec[f"c{j}_spectra"][i] = ch.forward_model()
                     rec[f"c{j}_preconv_integral"][i] = ch.preconv_integral
                     rec[f"c{j}_postconv_integral"][i] = ch.postconv_integral
+                    rec[f"c{j}_gauss_likelihood"][i] = ch.likelihood(cauchy=False)
                     for k, l in enumerate(ch.lines):
                         tname = type(l).__name__
                         if tname == "BalmerHydrogenLine":

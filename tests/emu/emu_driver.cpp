@@ -14,7 +14,7 @@ static ModelDev view(const unsigned char* blob) {
   d.los_w = (const double*)P(SEC_LOS_W); d.prof_d = (const double*)P(SEC_PROF_D); d.sp_i = (const int*)P(SEC_SP_I);
   d.sp_d = (const double*)P(SEC_SP_D); d.elem_dens_idx = (const int*)P(SEC_ELEM_DENS_IDX);
   d.a11_ne = (const double*)P(SEC_A11_NE); d.a11_te = (const double*)P(SEC_A11_TE);
-  d.a11_scd = (const double*)P(SEC_A11_SCD); d.h_ne = (const double*)P(SEC_H_NE); d.h_te = (const double*)P(SEC_H_TE);
+  d.a11_scd = (const double*)P(SEC_A11_SCD); d.a11_acd = (const double*)P(SEC_A11_ACD); d.h_ne = (const double*)P(SEC_H_NE); d.h_te = (const double*)P(SEC_H_TE);
   d.h_tab = (const double*)P(SEC_H_TAB); d.tau_grid = (const double*)P(SEC_TAU_GRID);
   d.spl_tx = (const double*)P(SEC_SPL_TX); d.spl_ty = (const double*)P(SEC_SPL_TY); d.spl_c = (const double*)P(SEC_SPL_C);
   d.ul_i = (const int*)P(SEC_UL_I); d.ul_d = (const double*)P(SEC_UL_D); d.pr_i = (const int*)P(SEC_PR_I); d.pr_d = (const double*)P(SEC_PR_D);

@@ -26,7 +26,7 @@ def emu_library():
     return _lib
 
 
-def host_model(workload, atomic_data=None):
+def host_model(workload, atomic_data=None, gaussian_likelihood=False):
     """Host objects + blob without touching a GPU (BaysarPosterior itself needs one)."""
     from baysar_b200.atomic_data import SyntheticADAS
     from baysar_b200.input_functions import make_input_dict
@@ -37,12 +37,14 @@ def host_model(workload, atomic_data=None):
 
     d = make_input_dict(**workload.input_kwargs)
     plasma = PlasmaLine(d, profile_function=workload.make_profile(host_ns), atomic_data=atomic_data or SyntheticADAS())
+    for k, v in workload.plasma_attrs.items():
+        setattr(plasma, k, v)
     import baysar_b200.priors as host_priors
 
     chords, priors = build_components(plasma, d, curvature=workload.curvature,
                                       passed_priors=workload.make_priors(host_priors))
     set_sensible_bounds(plasma, chords)
-    blob, info = compile_model(plasma, chords, priors)
+    blob, info = compile_model(plasma, chords, priors, gaussian_likelihood=gaussian_likelihood)
     return plasma, chords, priors, blob, info
 
 

@@ -21,7 +21,7 @@ RTOL = 1e-12
 def build(name):
     wl = WORKLOADS[name]()
     return OraclePosterior(make_input_dict(**wl.input_kwargs), SyntheticADAS(), wl.make_profile(oracle_ns),
-                           curvature=wl.curvature, extra_priors=wl.extra_priors)
+                           curvature=wl.curvature, extra_priors=wl.extra_priors, plasma_attrs=wl.plasma_attrs)
 
 
 @pytest.mark.parametrize("name", sorted(WORKLOADS))
@@ -63,6 +63,8 @@ def test_evaluation_matches_reference(name):
         for c, ch in enumerate(post.chords):
             np.testing.assert_allclose(r["spectra"][c], z[f"c{c}_spectra"][i], rtol=RTOL)
             np.testing.assert_allclose(r["extra"][c]["preconv_integral"], z[f"c{c}_preconv_integral"][i], rtol=RTOL)
+            if f"c{c}_gauss_likelihood" in z.files:  # SpectrometerChord.likelihood(cauchy=False)
+                np.testing.assert_allclose(r["extra"][c]["gauss_likelihood"], z[f"c{c}_gauss_likelihood"][i], rtol=RTOL)
             for k, l in enumerate(ch.lines):
                 f = fields_b if l["kind"] == "balmer" else fields_a if l["kind"] == "adas" else ["emission_fitted"]
                 got = [float(r["line_scalars"][c][k][n]) for n in f]
@@ -81,3 +83,18 @@ def test_random_start_matches_reference_stream():
     post.random_start()  # the harness burns one draw for the base of the reference theta
     for i in range(1, 5):
         np.testing.assert_allclose(post.random_start(), z["theta"][i], rtol=1e-15)
+
+
+def test_ne_tau_raises_like_the_reference():
+    """plasma.ne_tau = True makes tau an array over the line of sight (linemodels.py:398-399) and get_tec then takes the
+    truth value of an array (:454): the reference raises ValueError on every evaluation (fixture multi_ne_tau)."""
+    from baysar_b200 import configs
+
+    z = np.load(GOLDEN / "multi_ne_tau.npz")
+    assert all(str(e).startswith("ValueError: The truth value of an array") for e in z["error"])
+    wl = configs.multi_species_switched(ne_tau=True)
+    post = OraclePosterior(make_input_dict(**wl.input_kwargs), SyntheticADAS(), wl.make_profile(oracle_ns),
+                           plasma_attrs=wl.plasma_attrs)
+    with pytest.raises(oracle_ns.OracleError) as err:
+        post.evaluate(z["theta"][0])
+    assert err.value.kind == "ValueError"

@@ -19,4 +19,6 @@ WORKLOADS = {
     "multi_bowman_priors": lambda: configs.multi_species_bowman_priors(),
     "balmer_hot": lambda: configs.balmer_series(flags=dict(cold_neutrals=False)),
     "multi_species_32chords": lambda: configs.multi_species(32),
+    "multi_recombining": lambda: configs.multi_species_switched(recombining=True),
+    "multi_reverse_electroneutrality": lambda: configs.multi_species_switched(reverse_electroneutrality=True),
 }
