@@ -6,8 +6,9 @@ text files (`/root/reference/OpenADAS/read_adf15.py:26-110`, `/root/reference/Op
 parsers below restate those two readers (same tolerance to the files' layout, same array orientation, same ``10**`` on
 ADF11), :func:`format_adf11` / :func:`format_adf15` write tables back in the same layout (used to produce the synthetic
 fixtures, since no ADAS file may be redistributed or downloaded here), and :class:`FileADAS` is an
-:class:`~baysar_b200.atomic_data.AtomicDataProvider` over files for the hydrogen primitives; the impurity primitives
-(the proprietary ``run_adas406`` / old-signature readers, `plasmas.py:983-1022,1215-1216`) are delegated.
+:class:`~baysar_b200.atomic_data.AtomicDataProvider` over files: the hydrogen tables as the reference loads them, and the
+impurity primitives the reference takes from the proprietary ADAS library (``run_adas406`` / old-signature readers,
+`plasmas.py:983-1022,1215-1216`) rebuilt from the element's ADF11 / ADF15 files.
 
 Parity: `tests/test_adas_files.py` compares the parsers with the reference's own functions on committed synthetic
 files (`oracle/make_adf_golden.py`, arrays in `tests/golden/adf_parsed.npz`).
@@ -137,17 +138,43 @@ def format_adf15(table, wavelengths=None, types=None, label="H 0", comment="synt
     return "\n".join(out) + "\n"
 
 
+def _loglog_interp(table, ne_grid, te_grid, dens, te):
+    """``table[ne, Te]`` (positive) at ``dens x te``: bilinear in ``(log10 ne, log10 Te)`` of ``log10(table)``, linear
+    extrapolation from the edge cells outside the grid (the rule `scipy.interpolate.interpn(..., fill_value=None)` and the
+    reference's ``DataArray.interp`` use for the hydrogen tables, `plasmas.py:723-733`) -> ``[len(dens), len(te)]``."""
+    from scipy.interpolate import interpn
+
+    pts = np.stack(np.meshgrid(np.log10(np.asarray(dens, dtype=float)), np.log10(np.asarray(te, dtype=float)),
+                               indexing="ij"), axis=-1)
+    out = interpn((np.log10(ne_grid), np.log10(te_grid)), np.log10(table), pts, method="linear", bounds_error=False,
+                  fill_value=None)
+    return np.power(10.0, out)
+
+
 class FileADAS(AtomicDataProvider):
-    """Hydrogen tables from ADAS text files; impurity primitives from ``impurities`` (another provider).
+    """Atomic data from ADAS text files.
 
     ``adf15``: path or text of the hydrogen PEC file (`plasmas.py:1290-1291` loads ``get_adf15("h", 0, year=12)``);
-    ``adf11``: mapping ``{"scd": path, "acd": path, "plt": path, "prb": path}`` (`plasmas.py:706-721`).
+    ``adf11``: mapping ``{"scd": path, "acd": path, "plt": path, "prb": path}`` for hydrogen (`plasmas.py:706-721`).
+
+    Impurities (`plasmas.py:939-1081, 1207-1243`): ``impurity_adf11 = {"N": {"scd": ..., "acd": ..., "plt": ..., "prb":
+    ...}, ...}`` and ``impurity_adf15 = {pec key: path or text}``, the key being the ``pec`` entry of the line catalogue
+    (the full string or its basename).  With them this provider supplies the three primitives the reference takes from
+    the proprietary ADAS Python library -- ``run_adas406`` (time-dependent ionisation balance: the matrix exponential
+    of the SCD / ACD rate matrix, `baysar_b200.ionisation_balance.time_dependent_abundance`), ``read_adf11`` and
+    ``read_adf15`` (tables interpolated onto the requested ``(Te, ne)`` grid in log-log space) -- so a posterior with
+    impurity lines is built from files alone.  ``impurities`` (another provider) is only consulted for what no file
+    was given for.
     """
 
-    def __init__(self, adf15, adf11, impurities=None):
+    def __init__(self, adf15, adf11, impurities=None, impurity_adf11=None, impurity_adf15=None):
         self._adf15 = parse_adf15(adf15)
         self._adf11 = {key: parse_adf11(src) for key, src in adf11.items()}
         self._impurities = impurities
+        self._imp11 = {elem: {k: parse_adf11(src) for k, src in files.items()} for elem, files in (impurity_adf11 or {}).items()}
+        self._imp15_src = dict(impurity_adf15 or {})
+        self._imp15 = {}
+        self._balance_cache = {}
 
     def hydrogen_adf15(self, element="h", charge=0):
         return self._adf15
@@ -158,16 +185,42 @@ class FileADAS(AtomicDataProvider):
         t = self._adf11[adf11type]
         return GridTable(t.block[:1], t.ne, t.te, t.data[:1])  # the reference selects block 1 (`plasmas.py:723`)
 
-    def _delegate(self):
+    def _delegate(self, what):
         if self._impurities is None:
-            raise NotImplementedError("impurity atomic data needs the ADAS ionisation-balance code: pass impurities=<provider>")
+            raise NotImplementedError(f"no file given for {what} and no fallback provider (impurities=...)")
         return self._impurities
 
+    def _on_grid(self, elem, kind, te, dens):
+        """All blocks of an element's adf11 table interpolated to ``[block, len(dens), len(te)]``."""
+        t = self._imp11[elem][kind]
+        data = np.array([_loglog_interp(t.data[b], t.ne, t.te, dens, te) for b in range(len(t.block))])
+        return GridTable(t.block, np.asarray(dens, dtype=float), np.asarray(te, dtype=float), data)
+
     def ionisation_balance(self, elem, te, dens, tint, meta):
-        return self._delegate().ionisation_balance(elem, te, dens, tint, meta)
+        if elem not in self._imp11 or not {"scd", "acd"} <= set(self._imp11[elem]):
+            return self._delegate(f"the scd/acd tables of {elem}").ionisation_balance(elem, te, dens, tint, meta)
+        from .ionisation_balance import time_dependent_abundance
+
+        key = (elem, np.asarray(te, dtype=float).tobytes(), np.asarray(dens, dtype=float).tobytes())
+        if key not in self._balance_cache:  # the constructor asks for 30 times on one grid
+            self._balance_cache = {key: (self._on_grid(elem, "scd", te, dens), self._on_grid(elem, "acd", te, dens))}
+        scd, acd = self._balance_cache[key]
+        return time_dependent_abundance(scd, acd, tint, meta)
 
     def adf11_rates(self, elem, adf11type, is1, te, dens):
-        return self._delegate().adf11_rates(elem, adf11type, is1, te, dens)
+        if elem not in self._imp11 or adf11type not in self._imp11[elem]:
+            return self._delegate(f"the {adf11type} table of {elem}").adf11_rates(elem, adf11type, is1, te, dens)
+        t = self._imp11[elem][adf11type]
+        return _loglog_interp(t.select(is1), t.ne, t.te, dens, te).T  # [len(te), len(dens)] like the old read_adf11
+
+    def _pec_table(self, file):
+        if file not in self._imp15:
+            src = self._imp15_src.get(file, self._imp15_src.get(pathlib.PurePosixPath(str(file)).name))
+            self._imp15[file] = parse_adf15(src) if src is not None else None
+        return self._imp15[file]
 
     def adf15_pecs(self, file, block, te, dens):
-        return self._delegate().adf15_pecs(file, block, te, dens)
+        t = self._pec_table(file)
+        if t is None:
+            return self._delegate(f"the adf15 file {file!r}").adf15_pecs(file, block, te, dens)
+        return _loglog_interp(t.select(block), t.ne, t.te, dens, te).T  # [len(te), len(dens)]

@@ -21,7 +21,7 @@ X_TRIPLET = [[[4024.78, 4025.33, 4026.33]], [[0.541, 0.373, 0.086]]]
 
 class Workload:
     def __init__(self, name, input_kwargs, los, reference_theta, description, profile=None, curvature=None,
-                 extra_priors=(), plasma_attrs=None):
+                 extra_priors=(), plasma_attrs=None, provider_factory=None):
         self.name = name
         self.input_kwargs = input_kwargs
         self.los = los  # None -> profile default linspace(-10, 25, 50)
@@ -34,6 +34,12 @@ class Workload:
         # attributes assigned to posterior.plasma after construction, the way the reference's switches are used
         # (recombining, reverse_electroneutrality, ne_tau)
         self.plasma_attrs = dict(plasma_attrs or {})
+        self.provider_factory = provider_factory  # None -> SyntheticADAS(); else a callable returning the atomic-data provider
+
+    def make_provider(self):
+        from .atomic_data import SyntheticADAS
+
+        return self.provider_factory() if self.provider_factory is not None else SyntheticADAS()
 
     def make_priors(self, ns, plasma=None, plasma_state=None):
         """Instances of the optional priors from the namespace ``ns`` (the reference's ``baysar.priors`` or
@@ -152,6 +158,25 @@ def multi_species_switched(**plasma_attrs):
     tag = "_".join(k for k, v in sorted(plasma_attrs.items()) if v)
     return Workload(f"multi_{tag}", wl.input_kwargs, wl.los, wl.reference_theta, wl.description + f", plasma.{tag} = True",
                     plasma_attrs=plasma_attrs)
+
+
+def file_adas_provider(adf_dir):
+    """`FileADAS` over the synthetic ADF11 / ADF15 text files of ``adf_dir`` (written by oracle/make_adf_golden.py):
+    hydrogen tables, the N and C rate coefficients and the PEC files the multi-species lines name -- no other provider."""
+    from .adas_files import FileADAS
+
+    adf_dir = pathlib.Path(adf_dir)
+    kinds = ("scd", "acd", "plt", "prb")
+    return FileADAS(adf15=adf_dir / "pec12_h0_synthetic.dat", adf11={k: adf_dir / f"{k}12_h_synthetic.dat" for k in kinds},
+                    impurity_adf11={e: {k: adf_dir / f"{k}96_{e.lower()}_synthetic.dat" for k in kinds} for e in ("N", "C")},
+                    impurity_adf15={p.name[:-len(".synthetic")]: p for p in adf_dir.glob("*.pass.synthetic")})
+
+
+def multi_species_file_adas(adf_dir):
+    """The multi-species chord with every atomic table read from ADAS-format text files."""
+    wl = multi_species(1, data="flat")
+    return Workload("file_adas_multi", wl.input_kwargs, wl.los, wl.reference_theta, wl.description + ", tables from ADF files",
+                    provider_factory=lambda: file_adas_provider(adf_dir))
 
 
 def multi_species_bowman(background=False):

@@ -12,7 +12,11 @@ ionisation rate.  Mirrors `/root/reference/gcr/ionisation_balance.py`:
   birth-death chain, so the null vector has the closed form ``f[k+1] / f[k] = SCD[k -> k+1] / ACD[k+1 -> k]`` (row ``k``
   of ``R f = 0`` given rows ``0..k-1``), evaluated here for the whole grid at once, in log space so that abundances
   far below 1e-300 of the dominant stage neither overflow nor lose their ratio;
-* :func:`fractional_abundance_transport` — `:214-232`: the stack over ``tau = logspace(4, -6, 11)``.
+* :func:`fractional_abundance_transport` — `:214-232`: the stack over ``tau = logspace(4, -6, 11)``;
+* :func:`time_dependent_abundance` — what the reference obtains from the proprietary ``run_adas406``
+  (`plasmas.py:983-996`, ADAS406: the time-dependent ionisation balance): the solution of ``d f / dt = ne R f`` after
+  ``tint`` seconds from the start vector ``meta``, ``f = expm(ne R tint) meta``, with the same rate matrix.  Its long-time
+  limit is :func:`fractional_abundance`, which pins it on the reference's own balance.
 
 Tables come from :func:`baysar_b200.adas_files.parse_adf11` (``GridTable(block, ne, Te)``).  Host code (numpy): it runs
 once per element when tables are built, not per posterior evaluation.  Parity: `tests/test_ionisation_balance.py`
@@ -72,3 +76,19 @@ def fractional_abundance_transport(scd, acd, taus=TRANSPORT_TAUS):
 def mean_charge(f_ion):
     """Mean charge ``sum_k k f[k]`` over the last axis (what `plasmas.py:891-905` interpolates per element)."""
     return (f_ion * np.arange(f_ion.shape[-1])).sum(axis=-1)
+
+
+def time_dependent_abundance(scd, acd, tint, meta):
+    """``[n_ne, n_Te, Z+1]`` fractional abundances ``tint`` seconds after the state ``meta`` (length Z+1, normalised
+    here): ``expm(ne R tint) meta`` at every grid point, ``R`` from :func:`build_rates_matrix` (cm3/s) and ``ne`` the
+    tables' density axis (cm-3).  Tiny negative values of the matrix exponential are clipped and the result is
+    renormalised (the exact solution is a probability vector)."""
+    from scipy.linalg import expm
+
+    rate = build_rates_matrix(scd, acd)                       # [ne, Te, Z+1, Z+1]
+    meta = np.asarray(meta, dtype=float)
+    if meta.shape != (rate.shape[-1],) or not meta.sum() > 0:
+        raise ValueError("meta must be a non-zero vector with one entry per charge state")
+    gen = rate * (np.asarray(scd.ne, dtype=float)[:, None, None, None] * float(tint))
+    f = np.clip(expm(gen) @ (meta / meta.sum()), 0.0, None)   # expm works on the stack of matrices
+    return f / f.sum(axis=-1, keepdims=True)

@@ -103,12 +103,13 @@ def main():
         ("multi_recombining", configs.multi_species_switched(recombining=True), 10, 0, {}),
         ("multi_reverse_electroneutrality", configs.multi_species_switched(reverse_electroneutrality=True), 10, 0, {}),
         ("multi_ne_tau", configs.multi_species_switched(ne_tau=True), 3, 0, {}),
+        ("file_adas_multi", configs.multi_species_file_adas(GOLDEN / "adf"), 8, 0, {}),
     ]
     only = sys.argv[1:]
     for name, wl, n, nfine, attrs in jobs:
         if only and name not in only:
             continue
-        post = ref_harness.build_reference_posterior(wl, plasma_attrs={**wl.plasma_attrs, **attrs})
+        post = ref_harness.build_reference_posterior(wl, provider=wl.make_provider(), plasma_attrs={**wl.plasma_attrs, **attrs})
         thetas = ref_harness.draw_thetas(post, n, wl, seed=20261019)
         rec = ref_harness.evaluate(post, thetas, full_fine_grid=nfine)
         save(name, post, rec)

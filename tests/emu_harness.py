@@ -36,7 +36,7 @@ def host_model(workload, atomic_data=None, gaussian_likelihood=False):
     from baysar_b200.posterior import build_components, set_sensible_bounds
 
     d = make_input_dict(**workload.input_kwargs)
-    plasma = PlasmaLine(d, profile_function=workload.make_profile(host_ns), atomic_data=atomic_data or SyntheticADAS())
+    plasma = PlasmaLine(d, profile_function=workload.make_profile(host_ns), atomic_data=atomic_data or workload.make_provider())
     for k, v in workload.plasma_attrs.items():
         setattr(plasma, k, v)
     import baysar_b200.priors as host_priors

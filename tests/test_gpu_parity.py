@@ -25,7 +25,7 @@ def gpu_posterior(name):
     import baysar_b200.priors as host_priors
 
     post = BaysarPosterior(make_input_dict(**wl.input_kwargs), profile_function=wl.make_profile(host_ns),
-                           atomic_data=SyntheticADAS(), skip_test=True, curvature=wl.curvature,
+                           atomic_data=wl.make_provider(), skip_test=True, curvature=wl.curvature,
                            priors=wl.make_priors(host_priors))
     for k, v in wl.plasma_attrs.items():  # the reference's post-construction switches: assigned the way a user does
         setattr(post.plasma, k, v)

@@ -78,3 +78,57 @@ def test_input_validation():
     neg = GridTable(scd.block, scd.ne, scd.te, -scd.data)
     with pytest.raises(ValueError):
         ib.fractional_abundance(neg, acd)
+
+
+def test_time_dependent_balance_limits_on_the_reference_balance():
+    """`time_dependent_abundance` (the run_adas406 primitive, expm of the reference's rate matrix): its long-time limit is
+    the steady state the REFERENCE computes (`gcr_balance.npz`, written by gcr/ionisation_balance.py), t -> 0 returns the
+    start vector, and the solution is a probability vector that relaxes monotonically in mean charge."""
+    z = np.load(GOLDEN / "gcr_balance.npz")
+    scd, acd = _tables(z, "z3")
+    meta = np.array([1.0, 0.0, 0.0, 0.0])
+    late = ib.time_dependent_abundance(scd, acd, 1e9, meta)
+    np.testing.assert_allclose(late, z["z3_none_f"], rtol=1e-8, atol=1e-12)
+    bare = np.array([0.0, 0.0, 0.0, 1.0])
+    np.testing.assert_allclose(ib.time_dependent_abundance(scd, acd, 1e9, bare), z["z3_none_f"], rtol=1e-8, atol=1e-12)
+    early = ib.time_dependent_abundance(scd, acd, 1e-30, meta)
+    np.testing.assert_allclose(early, np.broadcast_to(meta, early.shape), atol=1e-12)
+    zbar = [ib.mean_charge(ib.time_dependent_abundance(scd, acd, t, meta)) for t in np.logspace(-9, 3, 13)]
+    assert np.all(np.diff(np.array(zbar), axis=0) >= -1e-12)
+    for t in (1e-7, 1e-4, 1e-1):
+        f = ib.time_dependent_abundance(scd, acd, t, meta)
+        assert np.all(f >= 0.0)
+        np.testing.assert_allclose(f.sum(axis=-1), 1.0, rtol=1e-13)
+        # it solves the rate equation: (f(t + dt) - f(t - dt)) / (2 dt) = ne R f(t)
+        dt = 1e-4 * t
+        lhs = (ib.time_dependent_abundance(scd, acd, t + dt, meta) - ib.time_dependent_abundance(scd, acd, t - dt, meta)) / (2 * dt)
+        rhs = np.einsum("...ij,...j->...i", z["z3_none_rate"], f) * scd.ne[:, None, None]
+        # measured against the gross rates (at a point already in steady state the net rate is pure cancellation)
+        gross = np.einsum("...ij,...j->...i", np.abs(z["z3_none_rate"]), f) * scd.ne[:, None, None]
+        assert np.abs((lhs - rhs) / (gross.max(axis=-1, keepdims=True) + 1e-300)).max() < 1e-5
+
+
+def test_file_adas_needs_no_other_provider():
+    """FileADAS over the synthetic ADF11 / ADF15 files: the three impurity primitives come from the files alone; values at
+    file grid points are the file's, and a posterior's tables build (the GPU parity of that posterior against the
+    reference run on the same files is `test_golden_fixtures[file_adas_multi]`)."""
+    from baysar_b200 import configs
+    from baysar_b200.input_functions import make_input_dict
+    from baysar_b200.plasmas import PlasmaLine
+
+    adf = GOLDEN / "adf"
+    prov = configs.file_adas_provider(adf)
+    t = adas_files.parse_adf11(adf / "plt96_n_synthetic.dat")
+    got = prov.adf11_rates("N", "plt", 3, t.te[[2, 7]], t.ne[[1, 5]])
+    np.testing.assert_allclose(got, t.select(3)[np.ix_([1, 5], [2, 7])].T, rtol=1e-12)
+    p = adas_files.parse_adf15(adf / "c_iii_vsu.pass.synthetic")
+    got = prov.adf15_pecs("/home/dgahle/adas/idl_spectra/use_adas208/c_iii_vsu.pass", 7, p.te[[0, 3]], p.ne[[2]])
+    np.testing.assert_allclose(got, p.select(7)[np.ix_([2], [0, 3])].T, rtol=1e-12)
+    f = prov.ionisation_balance("C", np.array([1.0, 10.0]), np.array([1e13, 1e14]), 1e-3, np.eye(7)[0])
+    assert f.shape == (2, 2, 7) and np.all(f >= 0)
+    np.testing.assert_allclose(f.sum(-1), 1.0, rtol=1e-13)
+    with pytest.raises(NotImplementedError):
+        prov.ionisation_balance("O", np.array([1.0]), np.array([1e13]), 1e-3, np.eye(9)[0])
+    wl = configs.multi_species_file_adas(adf)
+    plasma = PlasmaLine(make_input_dict(**wl.input_kwargs), atomic_data=wl.make_provider())
+    assert set(plasma.impurity_ion_bal) == {"N", "C"} and len(plasma.impurity_tecs) > 0

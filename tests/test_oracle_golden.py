@@ -20,7 +20,7 @@ RTOL = 1e-12
 
 def build(name):
     wl = WORKLOADS[name]()
-    return OraclePosterior(make_input_dict(**wl.input_kwargs), SyntheticADAS(), wl.make_profile(oracle_ns),
+    return OraclePosterior(make_input_dict(**wl.input_kwargs), wl.make_provider(), wl.make_profile(oracle_ns),
                            curvature=wl.curvature, extra_priors=wl.extra_priors, plasma_attrs=wl.plasma_attrs)
 
 

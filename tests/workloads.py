@@ -1,5 +1,9 @@
 """Fixture name -> workload builder, shared by the oracle and the GPU parity tests."""
+import pathlib
+
 from baysar_b200 import configs
+
+ADF_DIR = pathlib.Path(__file__).resolve().parent / "golden" / "adf"
 
 WORKLOADS = {
     "balmer_series": lambda: configs.balmer_series(),
@@ -19,6 +23,7 @@ WORKLOADS = {
     "multi_bowman_priors": lambda: configs.multi_species_bowman_priors(),
     "balmer_hot": lambda: configs.balmer_series(flags=dict(cold_neutrals=False)),
     "multi_species_32chords": lambda: configs.multi_species(32),
+    "file_adas_multi": lambda: configs.multi_species_file_adas(ADF_DIR),
     "multi_recombining": lambda: configs.multi_species_switched(recombining=True),
     "multi_reverse_electroneutrality": lambda: configs.multi_species_switched(reverse_electroneutrality=True),
 }
