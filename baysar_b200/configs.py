@@ -52,7 +52,11 @@ class Workload:
         spec = dict(self.profile or {"family": "esymmetric"})
         family = spec.pop("family")
         if family == "esymmetric":
+            if spec:  # e.g. ptype="gaussian"
+                return ns.EsymmtricCauchyPlasma(x=np.array(self.los, dtype=float), **spec)
             return ns.EsymmtricCauchyPlasma(x=np.array(self.los, dtype=float)) if self.los is not None else None
+        if family in ("SimplePlasma", "LessSimplePlasma", "SimpleGaussianPlasma", "SlabPlasma", "DoubleSlabPlasma"):
+            return getattr(ns, family)(x=np.array(self.los, dtype=float), **spec)
         if family == "bowman_tee":
             return ns.BowmanTeePlasma(x=np.array(self.los, dtype=float), **spec)
         if family == "mesh":
@@ -158,6 +162,33 @@ def multi_species_switched(**plasma_attrs):
     tag = "_".join(k for k, v in sorted(plasma_attrs.items()) if v)
     return Workload(f"multi_{tag}", wl.input_kwargs, wl.los, wl.reference_theta, wl.description + f", plasma.{tag} = True",
                     plasma_attrs=plasma_attrs)
+
+
+CLOSED_FORM_FAMILIES = {
+    # family: (line of sight, reference theta of the density, of the temperature)
+    "SimplePlasma": (np.linspace(0.0, 30.0, 100), [14.3, -1.0], [1.0, -1.3]),
+    "LessSimplePlasma": (np.linspace(0.0, 30.0, 100), [14.3, -1.0, 10.0, -1.0, 0.5], [1.0, -1.3]),
+    "SimpleGaussianPlasma": (np.linspace(0.0, 30.0, 100), [14.3, 0.9, 12.0], [1.0, 1.1]),
+    "SlabPlasma": (np.linspace(0.0, 20.0, 100), [14.3, 1.0], [0.8]),
+    "DoubleSlabPlasma": (np.linspace(0.0, 20.0, 100), [14.3, 13.8, 5.0], [0.3, 1.2]),
+}
+
+
+def multi_species_family(family, **spec):
+    """The multi-species chord on one of the reference's other profile families (lineshapes.py:456-606, :855-948), or on
+    the default family with ``ptype="gaussian"``."""
+    wl = multi_species(1)
+    ref = dict(wl.reference_theta)
+    if family == "esymmetric":
+        los, name = wl.los, "multi_esym_" + "_".join(str(v) for v in spec.values())
+    else:
+        los, ref["electron_density"], ref["electron_temperature"] = CLOSED_FORM_FAMILIES[family]
+        name = "multi_" + family
+    out = Workload(name, wl.input_kwargs, los, ref, wl.description + f", profile family {family}",
+                   profile=dict(family=family, **spec))
+    if family == "LessSimplePlasma":  # uniform draws from its bounds overflow (base^(x0 - x)): fixtures stay near the reference theta
+        out.theta_jitter = 0.03
+    return out
 
 
 def file_adas_provider(adf_dir):

@@ -9,7 +9,7 @@
 #define BAYSAR_LAYOUT_H
 
 #define BAYSAR_BLOB_MAGIC 0x4252415359534142LL /* "BAYSYSAB" */
-#define BAYSAR_BLOB_VERSION 11
+#define BAYSAR_BLOB_VERSION 12
 
 enum BaysarSection {
   SEC_I,              /* int64  [I_COUNT]           model-wide integer scalars                         */
@@ -66,7 +66,7 @@ enum BaysarI {
   I_N_ULINES,
   I_N_PRIORS,
   I_N_CLINES,
-  I_PROFILE_KIND,       /* 0 = EsymmtricCauchyPlasma, 1 = BowmanTeePlasma, 2 = MeshPlasma */
+  I_PROFILE_KIND,       /* 0 = EsymmtricCauchyPlasma, 1 = BowmanTeePlasma, 2 = MeshPlasma, 3 = closed-form pair (I_NE_FN, I_TE_FN) */
   I_NE_IDX,             /* first theta index of the electron_density slice */
   I_TE_IDX,
   I_HAS_HYDROGEN,
@@ -93,6 +93,8 @@ enum BaysarI {
   I_N_GROUPS,           /* ADAS line groups */
   I_RECOMBINING,        /* plasma.recombining: the neutral profile gains n1 ne acd tau before the ionisation loss (plasmas.py:735-737) */
   I_REVERSE_EN,         /* plasma.reverse_electroneutrality: the sampled profile is the main-ion density (plasmas.py:667-671) */
+  I_NE_FN,              /* I_PROFILE_KIND 3: BaysarProfileFn of the density / temperature profile */
+  I_TE_FN,
   I_GAUSS_LIKELIHOOD,   /* chord likelihood -0.5 sum r^2 instead of the Cauchy form (spectrometers.py:185-188) */
   I_COUNT
 };
@@ -110,7 +112,24 @@ enum BaysarProfD {
   PROF_BACKGROUND,      /* BowmanTee: 1.0 if the last parameter of each profile is log10 of a background level */
   PROF_MESH_NE_LOG,     /* MeshLine: 1.0 if the knot parameters are log10 values */
   PROF_MESH_TE_LOG,
+  PROF_ESYM_GAUSSIAN,   /* EsymmtricCauchyPlasma(ptype="gaussian"): exp(-0.5 z^2) instead of 1 / (1 + z^2) */
+  PROF_NE_AUX,          /* closed-form families: a constant of the density function (fixed Gaussian centre, top-hat grid step) */
+  PROF_NE_AUX_SET,      /* 1.0 if PROF_NE_AUX is in use (GaussianPlasma with a fixed centre) */
+  PROF_TE_AUX,
+  PROF_TE_AUX_SET,
   PROF_D_COUNT
+};
+
+/* closed-form profile functions of one coordinate (reference lineshapes.py:483-591, :855-929) */
+enum BaysarProfileFn {
+  PF_EXP_DECAY,           /* theta = [log10 a, log10 b]:        max(a (1 + b)^-x, 0.01)                                   */
+  PF_DOUBLE_EXP_DECAY,    /* [log10 a, log10 b, x0, log10 f, k]: max(a ((1 + b) exp(f tanh(k (x - x0))))^(x0 - x), 0.01)    */
+  PF_GAUSSIAN,            /* [log10 I, log10 fwhm (, centre)]:   max(I exp(-0.5 ((x - c) / sigma)^2), 0.01); fixed centre = aux */
+  PF_FLAT,                /* [log10 v]:                          v                                                          */
+  PF_LEFT_TOP_HAT,        /* [log10 v, edge]:                    v where x < edge + aux (the grid step), 1e10 elsewhere     */
+  PF_LEFT_RIGHT_TOP_HAT,  /* [log10 l, log10 r (, centre)]:      l left of the centre, r right of it, 0 on it; the temperature
+                             of a DoubleSlabPlasma takes the centre from the density's third parameter                      */
+  PF_COUNT
 };
 
 enum BaysarSpI { SP_DENS_IDX, SP_TAU_IDX, SP_VEL_IDX, SP_TI_IDX, SP_IS_H, SP_IS_IMPURITY, SP_I_COUNT };

@@ -31,6 +31,33 @@ __host__ __device__ static inline size_t los_smem_per_warp(int L, int n_params, 
 // exchange slots of a team of TW warps: four sums for each of a warp's 32 lanes (the ADAS line groups)
 __host__ __device__ static inline size_t los_team_xch_bytes(int tw) { return (size_t)tw * 32 * 4 * sizeof(double); }
 
+// Closed-form profile functions (layout.h BaysarProfileFn; reference lineshapes.py:483-591, :855-929).  th / p10: the
+// function's slice of theta and of 10^theta; aux / aux_set: PROF_*_AUX(_SET); linked: the centre a DoubleSlabPlasma's
+// density hands to its temperature.
+BAYSAR_DEV double profile_fn(int fn, double x, const double* th, const double* p10, double aux, double aux_set, double linked) {
+  switch (fn) {
+    case PF_EXP_DECAY:
+      return clip_lo(p10[0] * pow(1.0 + p10[1], -x), 0.01);
+    case PF_DOUBLE_EXP_DECAY: {
+      const double base = (1.0 + p10[1]) * exp(p10[3] * tanh(th[4] * (x - th[2])));
+      return clip_lo(p10[0] * pow(base, th[2] - x), 0.01);
+    }
+    case PF_GAUSSIAN: {
+      const double c = aux_set != 0.0 ? aux : th[2];
+      const double z = (x - c) / (p10[1] * 0.42466090014400953);
+      return clip_lo(p10[0] * exp(-0.5 * (z * z)), 0.01);
+    }
+    case PF_FLAT:
+      return p10[0] + 0.0;
+    case PF_LEFT_TOP_HAT:
+      return x < th[1] + aux ? p10[0] : 1e10;
+    default: {  // PF_LEFT_RIGHT_TOP_HAT
+      const double c = aux_set == 1.0 ? th[2] : (aux_set == 2.0 ? aux : linked);
+      return x < c ? p10[0] : (c < x ? p10[1] : 0.0);
+    }
+  }
+}
+
 // TW warps cooperate on one theta.  TW = 1 is the warp-per-theta form (reductions are warp shuffles); TW = 4 runs one CTA
 // per theta with the line-of-sight points spread over 128 threads, for long lines of sight whose per-point cache
 // (128 bytes per point) would otherwise leave a single warp per SM (L = 1000: 128 KB per theta).
@@ -175,19 +202,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
     (void)ne_A;
     const double te_f = th[te_idx + 1], te_floor = th[te_idx + 2], te_c = m.prof_d[PROF_TE_CENTRE];
     const double ne_pk = p10[ne_idx], te_pk = p10[te_idx];
+    const bool esym_gauss = m.prof_d[PROF_ESYM_GAUSSIAN] != 0.0;  // ptype="gaussian" (lineshapes.py:769-776)
     for (int l = lane; l < L; l += TS) {
       // sigma = 0.2 f + f / (1 + e), e = exp(-dx): dx / sigma = dx (1 + e) / (f (1.2 + 0.2 e)), one division instead of two
       double x = m.los_x[l];
       double dx = x - ne_c;
       double e = exp_fast(-dx);
       double r = (dx * (1.0 + e)) / (ne_f * fma(0.2, e, 1.2));
-      double v = clip_lo(ne_pk / fma(r, r, 1.0), ne_floor);
+      double v = clip_lo(esym_gauss ? ne_pk * exp(-0.5 * (r * r)) : ne_pk / fma(r, r, 1.0), ne_floor);
       ne_s[l] = v;
       nemax = v > nemax ? v : nemax;
       dx = x - te_c;
       e = exp_fast(-dx);
       r = (dx * (1.0 + e)) / (te_f * fma(0.2, e, 1.2));
-      te_s[l] = clip_lo(te_pk / fma(r, r, 1.0), te_floor);
+      te_s[l] = clip_lo(esym_gauss ? te_pk * exp(-0.5 * (r * r)) : te_pk / fma(r, r, 1.0), te_floor);
     }
   } else if (profile_kind == 1) {
     // BowmanTeeNe / BowmanTeeTe (lineshapes.py:332-376): A (1 + |((x - x0) / sigma)|^q / nu)^(-(nu + 1) / 2) + b,
@@ -207,6 +235,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       sg = ts0 * exp(tf * tanh(tk * (x - 0.0)));
       z = pow(fabs((x - 0.0) / sg), tq);
       te_s[l] = tA * pow(1.0 + z / tnu, -(tnu + 1.0) * 0.5) + tb;
+    }
+  } else if (profile_kind == 3) {
+    // closed-form pair (SimplePlasma, LessSimplePlasma, SimpleGaussianPlasma, SlabPlasma, DoubleSlabPlasma)
+    const int ne_fn = (int)I[I_NE_FN], te_fn = (int)I[I_TE_FN];
+    const double linked = th[ne_idx + 2 < n_params ? ne_idx + 2 : ne_idx];  // DoubleSlabPlasma: the density's centre
+    for (int l = lane; l < L; l += TS) {
+      const double x = m.los_x[l];
+      const double v = profile_fn(ne_fn, x, th + ne_idx, p10 + ne_idx, m.prof_d[PROF_NE_AUX], m.prof_d[PROF_NE_AUX_SET], 0.0);
+      ne_s[l] = v;
+      nemax = v > nemax ? v : nemax;
+      te_s[l] = profile_fn(te_fn, x, th + te_idx, p10 + te_idx, m.prof_d[PROF_TE_AUX], m.prof_d[PROF_TE_AUX_SET], linked);
     }
   } else {
     // MeshLine (lineshapes.py:282-301): values at the knots (10^theta if log), scipy interp1d "linear" with

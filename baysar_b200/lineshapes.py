@@ -80,7 +80,10 @@ class EsymmtricProfile:
 
     kind = "esymmetric_cauchy"
 
-    def __init__(self, x, log_peak_bounds, centre=None):
+    def __init__(self, x, log_peak_bounds, centre=None, ptype="cauchy"):
+        if ptype not in ("cauchy", "gaussian"):
+            raise ValueError("ptype not in ('cauchy', 'gaussian')")
+        self.ptype = ptype  # "gaussian": exp(-0.5 ((x-c)/s)^2) instead of the Cauchy form (lineshapes.py:769-776)
         self.x = np.asarray(x, dtype=float)
         self.centre = centre
         self.bounds = [list(log_peak_bounds)]
@@ -100,17 +103,19 @@ class EsymmtricProfile:
             centre = self.centre
         dx = self.x - centre
         width = 0.2 * factor + factor / (1 + np.exp(-dx))
+        if self.ptype == "gaussian":
+            return (np.power(10, amp) * np.exp(-0.5 * np.square(dx / width))).clip(floor)
         return (np.power(10, amp) / (1 + np.square(dx / width))).clip(floor)
 
 
 class EsymmtricCauchyPlasma:
     """Default profile pair (reference lineshapes.py:829-852): LOS ``linspace(-10, 25, 50)`` unless given."""
 
-    def __init__(self, x=None, dr_bounds=(-5, 2), bounds_ne=(13, 15), bounds_te=(0.0, 1.7), dr=None, **_):
+    def __init__(self, x=None, dr_bounds=(-5, 2), bounds_ne=(13, 15), bounds_te=(0.0, 1.7), dr=None, ptype="cauchy", **_):
         self.x = np.linspace(-10, 25, 50) if x is None else np.asarray(x, dtype=float)
         self.dr = dr
-        self.electron_density = EsymmtricProfile(self.x, bounds_ne, centre=dr)
-        self.electron_temperature = EsymmtricProfile(self.x, bounds_te, centre=0)
+        self.electron_density = EsymmtricProfile(self.x, bounds_ne, centre=dr, ptype=ptype)
+        self.electron_temperature = EsymmtricProfile(self.x, bounds_te, centre=0, ptype=ptype)
 
 
 class MeshLine:
@@ -211,3 +216,163 @@ class BowmanTeePlasma:
         self.electron_density.bounds, self.electron_temperature.bounds = self.bounds_ne, self.bounds_te
         self.electron_density.number_of_variables = len(self.bounds_ne)
         self.electron_temperature.number_of_variables = len(self.bounds_te)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Closed-form profile families (reference lineshapes.py:456-606, :855-948).  Every class carries ``kind = "closed_form"``
+# and ``fn``, the name of the device function K1 evaluates per line-of-sight point (csrc/los_stage.cuh, layout.h
+# BaysarProfileFn); ``__call__`` is the host statement of the same formula.
+class _ClosedForm:
+    kind = "closed_form"
+
+    def __init__(self, x, bounds):
+        self.x = np.asarray(x, dtype=float)
+        self.x_len = len(self.x)
+        self.bounds = [list(b) for b in bounds]
+        self.number_of_variables = len(self.bounds)
+
+
+class ExpDecay(_ClosedForm):
+    """``10^a (1 + 10^b)^(-x)``, floored at 0.01 (lineshapes.py:483-495)."""
+
+    fn = "PF_EXP_DECAY"
+
+    def __init__(self, x):
+        super().__init__(x, [[-1, 2], [-2, 1]])
+
+    def __call__(self, theta):
+        a, b = (np.power(10.0, t) for t in theta)
+        return (a * np.power(1.0 + b, -self.x)).clip(0.01)
+
+
+class ADoubleExpDecay(_ClosedForm):
+    """Two-sided decay about ``x0`` with a tanh-switched base (lineshapes.py:498-518); theta = [a, b, x0, f, k]."""
+
+    fn = "PF_DOUBLE_EXP_DECAY"
+
+    def __init__(self, x):
+        super().__init__(x, [[12, 16], [-2, 1], [0, 50], [-3, 1], [-5, 5]])
+
+    def __call__(self, theta):
+        a, b, x0, f, k = theta
+        base = (1.0 + np.power(10.0, b)) * np.exp(np.power(10.0, f) * np.tanh(k * (self.x - x0)))
+        return (np.power(10.0, a) * np.power(base, x0 - self.x)).clip(0.01)
+
+
+class GaussianPlasma(_ClosedForm):
+    """Height-normalised Gaussian ``10^I exp(-0.5 ((x - cwl) / sigma)^2)``, ``sigma`` from ``fwhm = 10^w``, floored at
+    0.01; the centre is sampled unless ``cwl`` is given (lineshapes.py:556-591)."""
+
+    fn = "PF_GAUSSIAN"
+
+    def __init__(self, x=None, cwl=None):
+        x = np.asarray(x, dtype=float)
+        self.cwl = cwl
+        bounds = [[12, 16], [-1, np.log10(x.max() / 2)]]
+        if cwl is None:
+            bounds.append([x.min(), x.max()])
+        super().__init__(x, bounds)
+
+    def __call__(self, theta):
+        if self.cwl is None:
+            intensity, fwhm, cwl = theta
+        else:
+            (intensity, fwhm), cwl = theta, self.cwl
+        return gaussian(self.x, cwl, np.power(10, fwhm), np.power(10, intensity)).clip(0.01)
+
+
+class FlatProfile(_ClosedForm):
+    """Constant ``10^theta`` (lineshapes.py:855-866)."""
+
+    fn = "PF_FLAT"
+
+    def __init__(self, x, bounds_te):
+        super().__init__(x, [bounds_te])
+
+    def __call__(self, theta):
+        return np.power(10, theta[0]) + np.zeros(self.x.shape)
+
+
+class LeftTopHatProfile(_ClosedForm):
+    """``10^ne`` left of ``l`` plus one grid step, ``1e10`` elsewhere (lineshapes.py:869-883)."""
+
+    fn = "PF_LEFT_TOP_HAT"
+
+    def __init__(self, x, bounds_ne, dr_bounds):
+        super().__init__(x, [bounds_ne, dr_bounds])
+
+    def __call__(self, theta):
+        ne, edge = theta
+        profile = np.zeros(self.x.shape) + 1e10
+        profile[np.where(self.x < edge + (self.x[1] - self.x[0]))] = np.power(10, ne)
+        return profile
+
+
+class LeftRightTopHatProfile(_ClosedForm):
+    """``10^left`` left of the centre, ``10^right`` right of it, 0 on it (lineshapes.py:906-929).  With ``alt`` (the
+    density of a DoubleSlabPlasma) the centre is a third parameter and is handed to ``alt`` -- the temperature, which is
+    evaluated after the density (the order of ``plasma.slices``)."""
+
+    fn = "PF_LEFT_RIGHT_TOP_HAT"
+
+    def __init__(self, x, centre, bounds_left, bounds_right, alt=None):
+        self.centre, self.alt = centre, alt
+        super().__init__(x, [bounds_left, bounds_right] + ([[2, 8]] if alt is not None else []))
+
+    def __call__(self, theta):
+        if self.alt is not None:
+            left, right, centre = theta
+            self.centre = self.alt.centre = centre
+        else:
+            left, right = theta
+        profile = np.zeros(self.x.shape)
+        profile[np.where(self.x < self.centre)] = np.power(10, left)
+        profile[np.where(self.centre < self.x)] = np.power(10, right)
+        return profile
+
+
+class SimplePlasma:
+    """lineshapes.py:469-480 (the second definition, which shadows the Poisson one at :456-466)."""
+
+    def __init__(self, x=None):
+        self.x = np.linspace(0, 60, 100) if x is None else np.asarray(x, dtype=float)
+        self.electron_density = ExpDecay(self.x)
+        self.electron_density.bounds[0] = [12, 16]
+        self.electron_temperature = ExpDecay(self.x)
+
+
+class LessSimplePlasma:
+    """lineshapes.py:521-532."""
+
+    def __init__(self, x=None):
+        self.x = np.linspace(0, 60, 100) if x is None else np.asarray(x, dtype=float)
+        self.electron_density = ADoubleExpDecay(self.x)
+        self.electron_temperature = ExpDecay(self.x)
+
+
+class SimpleGaussianPlasma:
+    """lineshapes.py:594-606."""
+
+    def __init__(self, x=None):
+        self.x = np.linspace(0, 60, 100) if x is None else np.asarray(x, dtype=float)
+        self.electron_density = GaussianPlasma(x=self.x)
+        self.electron_temperature = GaussianPlasma(x=self.x, cwl=0)
+
+
+class SlabPlasma:
+    """lineshapes.py:886-901."""
+
+    def __init__(self, x=None, dr_bounds=(-5, 2), bounds_ne=(13, 15), bounds_te=(0.0, 2.0), **_):
+        self.x = np.linspace(0, 20, 200) if x is None else np.asarray(x, dtype=float)
+        self.electron_density = LeftTopHatProfile(self.x, list(bounds_ne), list(dr_bounds))
+        self.electron_temperature = FlatProfile(self.x, list(bounds_te))
+
+
+class DoubleSlabPlasma:
+    """lineshapes.py:932-948."""
+
+    def __init__(self, x=None, centre=4, **_):
+        self.x = np.linspace(0, 20, 200) if x is None else np.asarray(x, dtype=float)
+        self.electron_temperature = LeftRightTopHatProfile(self.x, centre, bounds_left=[-1, 0.7], bounds_right=[0, 2.0])
+        self.electron_density = LeftRightTopHatProfile(self.x, centre, bounds_left=[13, 15], bounds_right=[13, 14.7],
+                                                       alt=self.electron_temperature)

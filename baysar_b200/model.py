@@ -101,6 +101,9 @@ def compile_model(plasma, chords, priors, gaussian_likelihood=False):
         if te_fn.centre is None:
             raise NotImplementedError("the temperature profile needs a fixed centre (reference default: 0)")
         profile_kind = 0
+        if ne_fn.ptype != te_fn.ptype:
+            raise NotImplementedError("density and temperature profiles must share one ptype")
+        prof[e["BaysarProfD"]["PROF_ESYM_GAUSSIAN"]] = 1.0 if ne_fn.ptype == "gaussian" else 0.0
         prof[e["BaysarProfD"]["PROF_NE_CENTRE_FIXED"]] = 0.0 if ne_fn.centre is None else 1.0
         prof[e["BaysarProfD"]["PROF_NE_CENTRE"]] = 0.0 if ne_fn.centre is None else ne_fn.centre
         prof[e["BaysarProfD"]["PROF_TE_CENTRE"]] = te_fn.centre
@@ -119,9 +122,23 @@ def compile_model(plasma, chords, priors, gaussian_likelihood=False):
         sec["SEC_MESH_X"] = np.concatenate([ne_fn.x_points, te_fn.x_points])
         sec["SEC_MESH_LO"] = np.concatenate(lows).astype(np.int32)
         iset("I_MESH_NE_N", len(ne_fn.x_points)), iset("I_MESH_TE_N", len(te_fn.x_points))
+    elif kinds == ("closed_form", "closed_form"):
+        profile_kind = 3
+        pf, pd = e["BaysarProfileFn"], e["BaysarProfD"]
+        iset("I_NE_FN", pf[ne_fn.fn]), iset("I_TE_FN", pf[te_fn.fn])
+        for fn, aux, aux_set in ((ne_fn, "PROF_NE_AUX", "PROF_NE_AUX_SET"), (te_fn, "PROF_TE_AUX", "PROF_TE_AUX_SET")):
+            if fn.fn == "PF_GAUSSIAN" and fn.cwl is not None:
+                prof[pd[aux]], prof[pd[aux_set]] = fn.cwl, 1.0
+            elif fn.fn == "PF_LEFT_TOP_HAT":
+                prof[pd[aux]] = los[1] - los[0]
+            elif fn.fn == "PF_LEFT_RIGHT_TOP_HAT":
+                # the density of a DoubleSlabPlasma carries the centre as its third parameter and hands it to the temperature
+                prof[pd[aux_set]] = 1.0 if fn.alt is not None else 0.0
+                if fn.alt is None and not (ne_fn.fn == "PF_LEFT_RIGHT_TOP_HAT" and ne_fn.alt is fn):
+                    prof[pd[aux]], prof[pd[aux_set]] = fn.centre, 2.0  # a stand-alone top hat: fixed centre
     else:
-        raise NotImplementedError(f"profile family {kinds} is not compiled for the GPU "
-                                  "(EsymmtricCauchyPlasma, BowmanTeePlasma and MeshPlasma are)")
+        raise NotImplementedError(f"profile family {kinds} is not compiled for the GPU (EsymmtricCauchyPlasma, "
+                                  "BowmanTeePlasma, MeshPlasma and the closed-form families of lineshapes.py are)")
     sec["SEC_PROF_D"] = prof
 
     # ---- species

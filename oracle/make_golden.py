@@ -103,6 +103,8 @@ def main():
         ("multi_recombining", configs.multi_species_switched(recombining=True), 10, 0, {}),
         ("multi_reverse_electroneutrality", configs.multi_species_switched(reverse_electroneutrality=True), 10, 0, {}),
         ("multi_ne_tau", configs.multi_species_switched(ne_tau=True), 3, 0, {}),
+        *[("multi_" + f, configs.multi_species_family(f), 8, 0, {}) for f in configs.CLOSED_FORM_FAMILIES],
+        ("multi_esym_gaussian", configs.multi_species_family("esymmetric", ptype="gaussian"), 8, 0, {}),
         ("file_adas_multi", configs.multi_species_file_adas(GOLDEN / "adf"), 8, 0, {}),
     ]
     only = sys.argv[1:]

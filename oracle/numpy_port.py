@@ -113,10 +113,11 @@ def low_pass(tmp, threshold, error):  # priors.py:9-11
 
 
 class EsymmtricProfile:
-    """lineshapes.py:779-826 (``ptype="cauchy"``)."""
+    """lineshapes.py:779-826 (``ptype``: :769-784)."""
 
-    def __init__(self, x, log_peak_bounds, centre=None):
+    def __init__(self, x, log_peak_bounds, centre=None, ptype="cauchy"):
         self.x = x
+        self.ptype = ptype
         self.centre = centre
         self.bounds = [log_peak_bounds]
         if centre is None:
@@ -135,16 +136,89 @@ class EsymmtricProfile:
             c = self.centre
         dx = self.x - c
         sigma = 0.2 * f + f / (1 + np.exp(-dx))
-        return (np.power(10, A) / (1 + np.square(dx / sigma))).clip(floor)
+        ms = np.square(dx / sigma)
+        peak = np.power(10, A) * np.exp(-0.5 * ms) if self.ptype == "gaussian" else np.power(10, A) / (1 + ms)
+        return peak.clip(floor)
 
 
 class EsymmtricCauchyPlasma:
     """lineshapes.py:829-852."""
 
-    def __init__(self, x=None, bounds_ne=(13, 15), bounds_te=(0.0, 1.7)):
+    def __init__(self, x=None, bounds_ne=(13, 15), bounds_te=(0.0, 1.7), ptype="cauchy"):
         self.x = np.linspace(-10, 25, 50) if x is None else np.asarray(x, dtype=float)
-        self.electron_density = EsymmtricProfile(self.x, list(bounds_ne), centre=None)
-        self.electron_temperature = EsymmtricProfile(self.x, list(bounds_te), centre=0)
+        self.electron_density = EsymmtricProfile(self.x, list(bounds_ne), centre=None, ptype=ptype)
+        self.electron_temperature = EsymmtricProfile(self.x, list(bounds_te), centre=0, ptype=ptype)
+
+
+def _pf(x, bounds, fn):
+    """A closed-form profile object: bounds, number_of_variables and the callable theta -> profile."""
+    obj = type("Profile", (), {})()
+    obj.x, obj.bounds, obj.number_of_variables, obj.fn = x, [list(b) for b in bounds], len(bounds), fn
+    type(obj).__call__ = lambda self, theta: self.fn(np.asarray(theta, dtype=float))
+    return obj
+
+
+def _exp_decay(x, peak_bounds=(-1, 2)):  # lineshapes.py:483-495
+    return _pf(x, [peak_bounds, [-2, 1]], lambda t: (np.power(10.0, t[0]) * np.power(np.ones(len(x)) + np.power(10.0, t[1]), -x)).clip(0.01))
+
+
+def _double_exp_decay(x):  # lineshapes.py:498-518
+    def fn(t):
+        base = (np.ones(len(x)) + np.power(10.0, t[1])) * np.exp(np.power(10.0, t[3]) * np.tanh(t[4] * (x - t[2])))
+        return (np.power(10.0, t[0]) * np.power(base, t[2] - x)).clip(0.01)
+    return _pf(x, [[12, 16], [-2, 1], [0, 50], [-3, 1], [-5, 5]], fn)
+
+
+def _gaussian_plasma(x, cwl=None):  # lineshapes.py:556-591 (height-normalised gaussian :109-120)
+    def fn(t):
+        c = t[2] if cwl is None else cwl
+        sigma = np.power(10.0, t[1]) / np.sqrt(8 * np.log(2))
+        return (np.power(10.0, t[0]) * np.exp(-0.5 * ((x - c) / sigma) ** 2)).clip(0.01)
+    bounds = [[12, 16], [-1, np.log10(x.max() / 2)]] + ([[x.min(), x.max()]] if cwl is None else [])
+    return _pf(x, bounds, fn)
+
+
+class SimplePlasma:  # lineshapes.py:469-480
+    def __init__(self, x=None):
+        self.x = np.linspace(0, 60, 100) if x is None else np.asarray(x, dtype=float)
+        self.electron_density, self.electron_temperature = _exp_decay(self.x, (12, 16)), _exp_decay(self.x)
+
+
+class LessSimplePlasma:  # lineshapes.py:521-532
+    def __init__(self, x=None):
+        self.x = np.linspace(0, 60, 100) if x is None else np.asarray(x, dtype=float)
+        self.electron_density, self.electron_temperature = _double_exp_decay(self.x), _exp_decay(self.x)
+
+
+class SimpleGaussianPlasma:  # lineshapes.py:594-606
+    def __init__(self, x=None):
+        self.x = np.linspace(0, 60, 100) if x is None else np.asarray(x, dtype=float)
+        self.electron_density, self.electron_temperature = _gaussian_plasma(self.x), _gaussian_plasma(self.x, cwl=0)
+
+
+class SlabPlasma:  # lineshapes.py:855-901
+    def __init__(self, x=None, dr_bounds=(-5, 2), bounds_ne=(13, 15), bounds_te=(0.0, 2.0)):
+        x = self.x = np.linspace(0, 20, 200) if x is None else np.asarray(x, dtype=float)
+        self.electron_density = _pf(x, [bounds_ne, dr_bounds],
+                                    lambda t: np.where(x < t[1] + (x[1] - x[0]), np.power(10.0, t[0]), np.zeros(x.shape) + 1e10))
+        self.electron_temperature = _pf(x, [bounds_te], lambda t: np.power(10.0, t[0]) + np.zeros(x.shape))
+
+
+class DoubleSlabPlasma:  # lineshapes.py:906-948: the density carries the centre and hands it to the temperature
+    def __init__(self, x=None, centre=4):
+        x = self.x = np.linspace(0, 20, 200) if x is None else np.asarray(x, dtype=float)
+        state = {"centre": centre}
+
+        def hat(t):
+            c = state["centre"]
+            return np.where(x < c, np.power(10.0, t[0]), np.where(c < x, np.power(10.0, t[1]), 0.0))
+
+        def density(t):
+            state["centre"] = t[2]
+            return hat(t)
+
+        self.electron_density = _pf(x, [[13, 15], [13, 14.7], [2, 8]], density)
+        self.electron_temperature = _pf(x, [[-1, 0.7], [0, 2.0]], hat)
 
 
 class MeshLine:

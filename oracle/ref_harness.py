@@ -15,12 +15,21 @@ def build_reference_posterior(workload, provider=None, seed=0, plasma_attrs=None
     mods = ref_shim.install(provider)
     kw = dict(workload.input_kwargs)
     kw.setdefault("line_data", ref_shim.pristine_line_data())
-    np.random.seed(seed)  # PlasmaLine.__init__ and init_test draw from the global RNG
-    with ref_shim.quiet():
-        input_dict = mods["input_functions"].make_input_dict(**kw)
-        profile = workload.make_profile(mods["lineshapes"])
-        post = mods["posterior"].BaysarPosterior(input_dict=input_dict, profile_function=profile, skip_test=True,
-                                                 curvature=getattr(workload, "curvature", None))
+    # PlasmaLine.__init__ and init_test draw from the global RNG; the reference's constructor evaluates the posterior at a
+    # random start and lets a numerical failure there propagate (posterior.py:197-217), so a family whose random starts
+    # can overflow (ADoubleExpDecay) is constructed with the first seed that survives
+    for attempt in range(50):
+        np.random.seed(seed + attempt)
+        try:
+            with ref_shim.quiet():
+                input_dict = mods["input_functions"].make_input_dict(**dict(kw))
+                profile = workload.make_profile(mods["lineshapes"])
+                post = mods["posterior"].BaysarPosterior(input_dict=input_dict, profile_function=profile, skip_test=True,
+                                                         curvature=getattr(workload, "curvature", None))
+            break
+        except (ValueError, TypeError):
+            if attempt == 49:
+                raise
     for k, v in (plasma_attrs or {}).items():
         setattr(post.plasma, k, v)
     # optional priors: the reference appends passed priors after the defaults (posterior.py:163-165); they need the
@@ -145,6 +154,12 @@ def draw_thetas(post, n, workload, seed):
     out = []
     base = post.random_start()
     out.append(workload.theta_from_tags(post.plasma.slices, base))
+    jitter = getattr(workload, "theta_jitter", None)
+    rng = np.random.default_rng(seed)
     while len(out) < n:
-        out.append(post.random_start())
+        if jitter:  # families whose uniform draws overflow: stay within `jitter` of the bound range around the reference theta
+            tb = np.asarray(post.plasma.theta_bounds, dtype=float)
+            out.append(np.clip(out[0] + jitter * (tb[:, 1] - tb[:, 0]) * rng.uniform(-1, 1, len(tb)), tb[:, 0], tb[:, 1]))
+        else:
+            out.append(post.random_start())
     return np.array(out)

@@ -23,6 +23,8 @@ WORKLOADS = {
     "multi_bowman_priors": lambda: configs.multi_species_bowman_priors(),
     "balmer_hot": lambda: configs.balmer_series(flags=dict(cold_neutrals=False)),
     "multi_species_32chords": lambda: configs.multi_species(32),
+    **{"multi_" + f: (lambda f=f: configs.multi_species_family(f)) for f in configs.CLOSED_FORM_FAMILIES},
+    "multi_esym_gaussian": lambda: configs.multi_species_family("esymmetric", ptype="gaussian"),
     "file_adas_multi": lambda: configs.multi_species_file_adas(ADF_DIR),
     "multi_recombining": lambda: configs.multi_species_switched(recombining=True),
     "multi_reverse_electroneutrality": lambda: configs.multi_species_switched(reverse_electroneutrality=True),
