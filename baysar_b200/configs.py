@@ -41,10 +41,23 @@ class Workload:
 
         return self.provider_factory() if self.provider_factory is not None else SyntheticADAS()
 
-    def make_priors(self, ns, plasma=None, plasma_state=None):
+    def make_priors(self, ns, plasma=None, plasma_state=None, posterior=None, late=None):
         """Instances of the optional priors from the namespace ``ns`` (the reference's ``baysar.priors`` or
-        ``baysar_b200.priors``: same class names and signatures; TeMinPrior takes the plasma_state, the others the plasma)."""
-        return [getattr(ns, name)(plasma_state if name == "TeMinPrior" else plasma, **kw) for name, kw in self.extra_priors]
+        ``baysar_b200.priors``: same class names and signatures).  Entries whose keyword arguments hold the markers
+        ``"@plasma"`` / ``"@plasma_state"`` / ``"@posterior"`` are built from keywords alone, with the markers replaced by
+        the live objects -- they can only be made once the posterior exists (``late=True`` selects them, ``late=False``
+        the others); the older entries take the plasma (TeMinPrior: the plasma_state) as their first argument."""
+        live = {"@plasma": plasma, "@plasma_state": plasma_state, "@posterior": posterior}
+        out = []
+        for name, kw in self.extra_priors:
+            marked = any(isinstance(v, str) and v in live for v in kw.values())
+            if late is not None and marked != late:
+                continue
+            if marked:
+                out.append(getattr(ns, name)(**{k: live[v] if isinstance(v, str) and v in live else v for k, v in kw.items()}))
+            else:
+                out.append(getattr(ns, name)(plasma_state if name == "TeMinPrior" else plasma, **kw))
+        return out
 
     def make_profile(self, ns):
         """Profile-function object from the namespace ``ns`` — the reference's ``baysar.lineshapes`` module,
@@ -240,6 +253,28 @@ def multi_species_bowman_priors():
     return Workload("multi_bowman_priors", wl.input_kwargs, wl.los, wl.reference_theta, wl.description + ", optional priors",
                     profile=wl.profile, extra_priors=[("BowmanTeePrior", dict(sigma_err=0.3)), ("PeakTePrior", {}),
                                                       ("TeMinPrior", {})])
+
+
+HOST_PRIORS = [  # evaluated on the host (baysar_b200/host_priors.py); built once the posterior exists
+    ("FlatnessPriorBasic", dict(scale=-15.5, tag="electron_density", plasma="@plasma")),
+    ("FlatnessPriorBasic", dict(scale=-1.5, tag="electron_temperature", plasma="@plasma")),
+    ("NIIITauPrior", dict(plasma_state="@plasma_state", mean=1, sigma=0.3)),
+    ("CiiiPrior", dict(plasma="@plasma", mean=0, sigma=0.5)),
+    ("EmsTeOrderPrior", dict(posterior="@posterior", mean=2.0, sigma=0.5, species=["N_1", "N_2"])),
+]
+MESH_HOST_PRIORS = [  # the two that refresh the knot vectors first: PlasmaGradientPrior reads what they leave there
+    ("GaussianProcessPrior", dict(mu=13.0, plasma="@plasma", A=2.0, L=0.5, profile="electron_density")),
+    ("FlatnessPrior", dict(scale=-1.0, tag="electron_temperature", plasma="@plasma")),
+    ("PlasmaGradientPrior", dict(plasma="@plasma", te_scale=0.05, ne_scale=0.05)),
+    ("SeparatrixTePrior", dict(scale=0.2, plasma="@plasma", index=2, ne_scale=0.1)),
+]
+
+
+def multi_species_host_priors(mesh=False):
+    wl = multi_species_mesh() if mesh else multi_species(1)
+    name = "multi_mesh_host_priors" if mesh else "multi_host_priors"
+    return Workload(name, wl.input_kwargs, wl.los, wl.reference_theta, wl.description + ", host-evaluated optional priors",
+                    profile=wl.profile, extra_priors=MESH_HOST_PRIORS if mesh else HOST_PRIORS)
 
 
 def multi_species_mesh(curvature=None):

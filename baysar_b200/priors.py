@@ -209,3 +209,9 @@ class BowmanTeePrior(_DevicePrior):
     def __init__(self, plasma=None, sigma_err=0.2, nu_err=0.2):
         super().__init__()
         self.sigma_err, self.nu_err = sigma_err, nu_err
+
+
+# the reference's remaining optional priors, evaluated on the host (baysar_b200/host_priors.py): same namespace as above
+from .host_priors import (BolometryPrior, CiiiPrior, EmsTeOrderPrior, FastStarkPrior, FlatnessPrior,  # noqa: E402,F401
+                          FlatnessPriorBasic, GaussianProcessPrior, NeutralPowerPrior, NIIITauPrior, NIVTauPrior,
+                          PlasmaGradientPrior, SeparatrixTePrior, flatness_prior)

@@ -105,6 +105,8 @@ def main():
         ("multi_ne_tau", configs.multi_species_switched(ne_tau=True), 3, 0, {}),
         *[("multi_" + f, configs.multi_species_family(f), 8, 0, {}) for f in configs.CLOSED_FORM_FAMILIES],
         ("multi_esym_gaussian", configs.multi_species_family("esymmetric", ptype="gaussian"), 8, 0, {}),
+        ("multi_host_priors", configs.multi_species_host_priors(), 8, 0, {}),
+        ("multi_mesh_host_priors", configs.multi_species_host_priors(mesh=True), 8, 0, {}),
         ("file_adas_multi", configs.multi_species_file_adas(GOLDEN / "adf"), 8, 0, {}),
     ]
     only = sys.argv[1:]

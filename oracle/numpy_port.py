@@ -994,6 +994,56 @@ class OraclePosterior:
         if name == "BowmanTeePrior":  # priors.py:484-506
             sigma_diff = raw["electron_temperature"][1] - raw["electron_density"][2]
             return 0.0 + low_pass(sigma_diff, 0.0, args.get("sigma_err", 0.2))
+        # ---- the optional priors the product evaluates on the host (baysar_b200/host_priors.py)
+        fns = {"electron_density": self.profile_function.electron_density,
+               "electron_temperature": self.profile_function.electron_temperature}
+
+        def knot_vector(tag):  # priors.py:187-208: the mesh parameter vector with the sampled knots filled in
+            fn = fns[tag]
+            v = fn.empty_theta.copy()
+            v[fn.slice] = raw[tag]
+            return v
+
+        if name == "FlatnessPriorBasic":  # priors.py:133-152
+            return -np.power(10, args["scale"]) * abs(np.gradient(st[args["tag"]])).sum()
+        if name == "FlatnessPrior":  # priors.py:180-208
+            return -np.power(10, args["scale"]) * abs(np.gradient(knot_vector(args["tag"]))).sum()
+        if name == "PlasmaGradientPrior":  # priors.py:155-177 (knot vectors as the preceding priors left them: current theta)
+            cost = 0
+            for tag, scale in (("electron_density", args["ne_scale"]), ("electron_temperature", args["te_scale"])):
+                cost += -scale * abs(np.gradient(knot_vector(tag), fns[tag].x_points)).sum()
+            return cost
+        if name == "SeparatrixTePrior":  # priors.py:211-238
+            parts = []
+            for tag, scale in (("electron_temperature", args["scale"]), ("electron_density", args.get("ne_scale", 0))):
+                v = np.array(raw[tag])
+                parts.append(scale * abs(fns[tag].x[np.where(v == v.max())]).max() * (v - v.max())[args["index"]])
+            return parts[0] + parts[1]
+        if name == "NIIITauPrior":  # priors.py:325-344
+            return high_pass(st["N_1_tau"][0] / st["N_2_tau"][0], args.get("mean", 1), args.get("sigma", 0.3))
+        if name == "NIVTauPrior":  # priors.py:304-322
+            r, mean, sigma, ratio = st["N_3_tau"][0] / st["N_2_tau"][0], args.get("mean", 1), args.get("sigma", 0.2), args.get("ratio", 5)
+            return high_pass(r, mean, sigma) + low_pass(r, ratio * mean, ratio * sigma)
+        if name == "CiiiPrior":  # priors.py:559-573
+            if "C_2_tau" not in st:
+                return 0
+            r_tau = np.log10(st["C_2_tau"].mean() / st["N_2_tau"].mean())
+            return -0.5 * np.square((r_tau - args.get("mean", 0)) / args.get("sigma", 0.2))
+        if name == "EmsTeOrderPrior":  # priors.py:347-391: first line of each wanted species, highest charge first
+            found = {}
+            for c, ch in enumerate(self.chords):
+                for k, l in enumerate(ch.lines):
+                    sp = l.get("species")
+                    if sp in self.impurity_species and sp in args["species"] and sp not in found:
+                        found[sp] = (sp, c, k)
+            order = sorted(found.values(), key=lambda rec: -int(rec[0].split("_")[1]))
+            ems_te = [line_scalars[c][k]["ems_te"] for _, c, k in order]
+            return high_pass(ems_te[0] - ems_te[1], args.get("mean", 2.0), args.get("sigma", 0.2))
+        if name == "GaussianProcessPrior":  # priors.py:1129-1176
+            x = fns["electron_density"].x_points
+            cov = (args["A"] ** 2) * np.exp(-0.5 * np.subtract.outer(x, x) ** 2 / args["L"] ** 2)
+            field = knot_vector(args["profile"]) - args["mu"]
+            return -0.5 * field.T.dot(np.linalg.solve(cov, np.eye(len(cov))).dot(field))
         raise KeyError(name)
 
     def evaluate(self, theta, details=False):

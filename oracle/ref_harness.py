@@ -37,7 +37,7 @@ def build_reference_posterior(workload, provider=None, seed=0, plasma_attrs=None
     if getattr(workload, "extra_priors", None):
         post(list(workload.theta_from_tags(post.plasma.slices, post.random_start())), True)  # fills plasma_state
         post.posterior_components.extend(workload.make_priors(mods["priors"], plasma=post.plasma,
-                                                              plasma_state=post.plasma.plasma_state))
+                                                              plasma_state=post.plasma.plasma_state, posterior=post))
     return post
 
 

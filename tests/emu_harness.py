@@ -42,7 +42,7 @@ def host_model(workload, atomic_data=None, gaussian_likelihood=False):
     import baysar_b200.priors as host_priors
 
     chords, priors = build_components(plasma, d, curvature=workload.curvature,
-                                      passed_priors=workload.make_priors(host_priors))
+                                      passed_priors=workload.make_priors(host_priors, late=False))
     set_sensible_bounds(plasma, chords)
     blob, info = compile_model(plasma, chords, priors, gaussian_likelihood=gaussian_likelihood)
     return plasma, chords, priors, blob, info

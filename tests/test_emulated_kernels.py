@@ -25,7 +25,8 @@ def test_host_setup_matches_reference(name):
     assert plasma.n_params == int(z["setup_n_params"])
     np.testing.assert_allclose(plasma.theta_bounds, z["setup_theta_bounds"], rtol=1e-14)
     names = ["SpectrometerChord"] * len(chords) + [type(p).__name__ for p in priors]
-    assert names == [str(s) for s in z["setup_components"]]
+    late = [n for n, kw in WORKLOADS[name]().extra_priors if any(isinstance(v, str) and v.startswith("@") for v in kw.values())]
+    assert names + late == [str(s) for s in z["setup_components"]]  # (host-evaluated priors are appended after construction)
     for c, ch in enumerate(chords):
         np.testing.assert_array_equal(ch.x_data_fm, z[f"setup_c{c}_x_data_fm"])
         np.testing.assert_allclose(ch.error, z[f"setup_c{c}_error"], rtol=1e-14)
@@ -43,12 +44,16 @@ def test_emulated_kernels_match_reference(name):
         o = emu_eval(blob, th, chord=c, n_chords=len(chords), n_priors=len(priors), n_ul=info["n_ulines"],
                      L=len(plasma.los), P=len(chords[c].x_data), F=len(chords[c].x_data_fm))
         assert (o["status"] == 0).all()
-        np.testing.assert_allclose(o["logp"], z["logp"][:N_THETA], rtol=1e-6)  # north_star: 1e-6 relative
+        # host-evaluated optional priors (baysar_b200/host_priors.py) are the trailing columns of the reference's
+        # components and are not part of the device model: the kernels' logP is the total without them
+        ncol = len(chords) + len(priors)
+        ref_logp = z["logp"][:N_THETA] - z["components"][:N_THETA, ncol:].sum(axis=1)
+        np.testing.assert_allclose(o["logp"], ref_logp, rtol=1e-6)  # north_star: 1e-6 relative
         np.testing.assert_allclose(o["spectra"], z[f"c{c}_spectra"][:N_THETA], rtol=1e-5)  # 1e-5 per pixel
         # components: the same 1e-6, measured against the posterior they add up to (a well-fitted chord's likelihood
         # can be a small part of it, and float32 pixel rounding does not shrink with it)
         for i in range(N_THETA):
-            np.testing.assert_allclose(o["comps"][i], z["components"][i], rtol=1e-6, atol=1e-6 * abs(z["logp"][i]))
+            np.testing.assert_allclose(o["comps"][i], z["components"][i, :ncol], rtol=1e-6, atol=1e-6 * abs(z["logp"][i]))
         np.testing.assert_allclose(o["profiles"][:, 0], z["ne"][:N_THETA], rtol=1e-12)
         np.testing.assert_allclose(o["profiles"][:, 2], z["main_ion_density"][:N_THETA], rtol=1e-12)
         ref = z[f"c{c}_line_scalars"][:N_THETA]

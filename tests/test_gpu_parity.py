@@ -26,7 +26,10 @@ def gpu_posterior(name):
 
     post = BaysarPosterior(make_input_dict(**wl.input_kwargs), profile_function=wl.make_profile(host_ns),
                            atomic_data=wl.make_provider(), skip_test=True, curvature=wl.curvature,
-                           priors=wl.make_priors(host_priors))
+                           priors=wl.make_priors(host_priors, late=False))
+    # host-evaluated priors need the live plasma / posterior: appended afterwards, as scripts for the reference do
+    post.posterior_components.extend(wl.make_priors(host_priors, plasma=post.plasma, plasma_state=post.plasma.plasma_state,
+                                                    posterior=post, late=True))
     for k, v in wl.plasma_attrs.items():  # the reference's post-construction switches: assigned the way a user does
         setattr(post.plasma, k, v)
     return post, wl
@@ -59,8 +62,14 @@ def test_golden_fixtures(name, posteriors):
     assert (post.last_status == 0).all(), post.last_status
     np.testing.assert_allclose(logp, z["logp"], rtol=LOGP_RTOL)
     comps, status = post.components_batch(theta)
+    ncol = comps.shape[1]  # chords + device priors; host-evaluated priors follow in the reference's component list
     for i in range(len(theta)):  # 1e-6 of the posterior the components add up to (see tests/test_emulated_kernels.py)
-        np.testing.assert_allclose(comps[i], z["components"][i], rtol=LOGP_RTOL, atol=LOGP_RTOL * abs(z["logp"][i]))
+        np.testing.assert_allclose(comps[i], z["components"][i, :ncol], rtol=LOGP_RTOL, atol=LOGP_RTOL * abs(z["logp"][i]))
+    if z["components"].shape[1] > ncol:  # host priors, through the scalar protocol: values from the published state
+        assert len(post.host_priors) == z["components"].shape[1] - ncol
+        for i in range(min(4, len(theta))):
+            np.testing.assert_allclose(post(theta[i]), z["logp"][i], rtol=LOGP_RTOL)
+            np.testing.assert_allclose([p() for p in post.host_priors], z["components"][i, ncol:], rtol=1e-8, atol=1e-12)
     lines, _, prof = post.lines_batch(theta, want_profiles=True)
     # CUDA's pow(10, x) and numpy's differ by an ulp now and then; the mesh family interpolates between knot values,
     # whose difference amplifies that ulp (2e-12 seen) — every other family holds 1e-12
