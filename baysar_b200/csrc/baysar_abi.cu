@@ -775,26 +775,26 @@ int baysar_model_get_profile(baysar_model_t* m, double* stage_ms, int64_t* calls
 }
 
 int baysar_stretch_propose(const double* walkers, const double* complement, int n_params, int64_t n_walkers,
-                           int64_t n_complement, double a, uint64_t seed, uint64_t step, double* proposal,
-                           double* log_factor, void* stream_) {
+                           int64_t n_complement, double a, uint64_t seed, uint64_t step, int64_t walker_offset,
+                           double* proposal, double* log_factor, void* stream_) {
   if (!walkers || !complement || !proposal || !log_factor) return fail("null argument");
   if (n_params < 1 || n_complement < 1 || !(a > 1.0)) return fail("bad stretch-move arguments");
   if (n_walkers <= 0) return 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ens::stretch_propose_kernel<<<(unsigned)((n_walkers + 127) / 128), 128, 0, stream>>>(
-      walkers, complement, n_params, n_walkers, n_complement, a, seed, step, proposal, log_factor);
+      walkers, complement, n_params, n_walkers, n_complement, a, seed, step, walker_offset, proposal, log_factor);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int baysar_stretch_accept(double* walkers, double* logp, const double* proposal, const double* logp_new,
                           const double* log_factor, const uint32_t* status_new, int n_params, int64_t n_walkers,
-                          uint64_t seed, uint64_t step, unsigned long long* n_accepted, void* stream_) {
+                          uint64_t seed, uint64_t step, int64_t walker_offset, unsigned long long* n_accepted, void* stream_) {
   if (!walkers || !logp || !proposal || !logp_new || !log_factor) return fail("null argument");
   if (n_walkers <= 0) return 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ens::stretch_accept_kernel<<<(unsigned)((n_walkers + 127) / 128), 128, 0, stream>>>(
-      walkers, logp, proposal, logp_new, log_factor, status_new, n_params, n_walkers, seed, step, n_accepted);
+      walkers, logp, proposal, logp_new, log_factor, status_new, n_params, n_walkers, seed, step, walker_offset, n_accepted);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -2,7 +2,9 @@
 // the batched posterior for the 1M-walker workload (reference caller: emcee's EnsembleSampler driven from
 // tulasa/fitting.py:1275-1304; emcee's StretchMove: z = ((a - 1) u + 1)^2 / a, proposal = c + z (x - c),
 // accept with probability min(1, z^(n-1) p(proposal) / p(x))).  Walkers, proposals and log-posteriors never leave HBM.
-// Random numbers: Philox4x32-10, counter = (walker, step, draw, 0), key = seed — reproducible for any grid shape.
+// Random numbers: Philox4x32-10, counter = (global walker index: 64 bits, step: low 32 bits, draw + 2 * high 32 bits of
+// step), key = seed — reproducible for any grid shape; `walker_offset` is the global index of this launch's first walker,
+// so ranks that share a seed still draw distinct streams.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,11 +32,13 @@ __host__ __device__ inline double u01(uint32_t hi, uint32_t lo) {
 
 // proposal[s] = c + z (x_s - c), c a uniformly drawn walker of the complementary ensemble; log_factor = (n - 1) ln z
 __global__ void stretch_propose_kernel(const double* __restrict__ walkers, const double* __restrict__ complement, int n_params,
-                                       int64_t S, int64_t C, double a, uint64_t seed, uint64_t step,
+                                       int64_t S, int64_t C, double a, uint64_t seed, uint64_t step, int64_t walker_offset,
                                        double* __restrict__ proposal, double* __restrict__ log_factor) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
-  const Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)step, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint64_t g = (uint64_t)(s + walker_offset);
+  const Philox4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, 2u * (uint32_t)(step >> 32),
+                                  (uint32_t)seed, (uint32_t)(seed >> 32));
   const double u = u01(r.x, r.y);
   const double t = (a - 1.0) * u + 1.0;
   const double z = t * t / a;
@@ -50,10 +54,12 @@ __global__ void stretch_propose_kernel(const double* __restrict__ walkers, const
 __global__ void stretch_accept_kernel(double* __restrict__ walkers, double* __restrict__ logp, const double* __restrict__ proposal,
                                       const double* __restrict__ logp_new, const double* __restrict__ log_factor,
                                       const uint32_t* __restrict__ status_new, int n_params, int64_t S, uint64_t seed,
-                                      uint64_t step, unsigned long long* __restrict__ n_accepted) {
+                                      uint64_t step, int64_t walker_offset, unsigned long long* __restrict__ n_accepted) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
-  const Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)step, 1u, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint64_t g = (uint64_t)(s + walker_offset);
+  const Philox4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, 1u + 2u * (uint32_t)(step >> 32),
+                                  (uint32_t)seed, (uint32_t)(seed >> 32));
   const double lnu = log(u01(r.x, r.y));
   const double lp = logp_new[s];
   const bool ok = (status_new == nullptr || status_new[s] == 0u) && lp == lp && lp < 1.7976931348623157e308;

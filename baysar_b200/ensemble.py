@@ -3,9 +3,13 @@
 The reference drives emcee's ``EnsembleSampler`` from the host (`tulasa/fitting.py:1275-1304`): every half-step costs
 a host round trip per walker.  Here walkers, proposals and log-posteriors stay in HBM: per half-step one proposal
 kernel, the batched posterior (LOS -> chord -> ... -> finalize) and one accept kernel, all on the current stream
-(`csrc/ensemble.cuh`; Philox4x32-10, so a run is reproducible from ``seed`` alone).  With `torch.distributed` every
-rank advances its own walkers (independent ensembles need no data-path collective); `gather_logp` all-gathers the
-per-walker log-posteriors, which is all a convergence monitor needs.
+(`csrc/ensemble.cuh`; Philox4x32-10 keyed by ``seed`` and counted by GLOBAL walker index, so a run is reproducible from
+``seed`` alone and ranks never share a stream).  With `torch.distributed` the walkers are sharded over the ranks and
+form ONE ensemble (``global_ensemble=True``, the default under a process group): before each half-step the
+complementary half of every rank is all-gathered over NCCL (N/2 x n_params x 8 bytes in total) and the stretch move
+draws its partner from all of it, which is what "one ensemble of 2^20 walkers on 8 GPUs" (BASELINE configs[3]) means;
+``global_ensemble=False`` keeps one independent ensemble per rank (no data-path collective).  `gather_logp`
+all-gathers the per-walker log-posteriors, which is all a convergence monitor needs.
 """
 import ctypes
 
@@ -33,25 +37,44 @@ def uniform01(hi, lo):
     return (bits.astype(np.float64) + 0.5) / 4503599627370496.0
 
 
-def reference_draws(n_walkers, seed, step, n_complement, a=2.0):
-    """(z, partner index, ln u_accept) the kernels draw for walkers 0..n_walkers-1 of one half-step."""
-    s = np.arange(n_walkers, dtype=np.uint64)
+def reference_draws(n_walkers, seed, step, n_complement, a=2.0, walker_offset=0):
+    """(z, partner index, ln u_accept) the kernels draw for the walkers with global indices walker_offset ..
+    walker_offset + n_walkers - 1 in one half-step."""
+    s = np.arange(n_walkers, dtype=np.uint64) + np.uint64(walker_offset)
     key = (seed & 0xFFFFFFFF, seed >> 32)
     zero = np.zeros(n_walkers, dtype=np.uint64)
-    r = philox4x32_10((s & 0xFFFFFFFF, s >> np.uint64(32), zero + (step & 0xFFFFFFFF), zero), key)
+    hi = 2 * ((step >> 32) & 0xFFFFFFFF)
+    r = philox4x32_10((s & 0xFFFFFFFF, s >> np.uint64(32), zero + (step & 0xFFFFFFFF), zero + hi), key)
     t = (a - 1.0) * uniform01(r[0], r[1]) + 1.0
     pick = np.minimum((uniform01(r[2], r[3]) * n_complement).astype(np.int64), n_complement - 1)
-    q = philox4x32_10((s & 0xFFFFFFFF, s >> np.uint64(32), zero + (step & 0xFFFFFFFF), zero + 1), key)
+    q = philox4x32_10((s & 0xFFFFFFFF, s >> np.uint64(32), zero + (step & 0xFFFFFFFF), zero + hi + 1), key)
     return t * t / a, pick, np.log(uniform01(q[0], q[1]))
+
+
+def gather_complement(local, world=None):
+    """The complementary half-ensemble a half-step draws partners from: this rank's rows followed by nothing else without
+    a process group, else the rows of every rank in rank order (one all-gather; works on NCCL and gloo tensors)."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    out = local.new_empty((dist.get_world_size() * local.shape[0],) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, local.contiguous())
+    return out
 
 
 class StretchEnsemble:
     """``StretchEnsemble(posterior, walkers)``: walkers (N, n_params) array or CUDA tensor, N even."""
 
-    def __init__(self, posterior, walkers, seed=0, a=2.0):
+    def __init__(self, posterior, walkers, seed=0, a=2.0, global_ensemble=None):
         import torch
+        import torch.distributed as dist
 
         self.torch, self.post, self.a, self.seed = torch, posterior, float(a), int(seed)
+        grouped = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.rank, self.world = (dist.get_rank(), dist.get_world_size()) if grouped else (0, 1)
+        # one ensemble over all ranks (complement all-gathered) unless asked for rank-local ensembles
+        self.global_ensemble = grouped if global_ensemble is None else bool(global_ensemble) and grouped
         self.lib = runtime.library()
         self.walkers = posterior._as_device(walkers).clone().contiguous()
         n, self.n_params = self.walkers.shape
@@ -72,16 +95,20 @@ class StretchEnsemble:
             raise RuntimeError("baysar_b200: " + self.lib.baysar_last_error().decode())
 
     def _half_step(self, lo, hi, clo, chi, counter):
-        stream = ctypes.c_void_p(self.torch.cuda.current_stream(self.walkers.device).cuda_stream)
         w, c = self.walkers[lo:hi], self.walkers[clo:chi]
-        self._check(self.lib.baysar_stretch_propose(w.data_ptr(), c.data_ptr(), self.n_params, hi - lo, chi - clo, self.a,
-                                                    self.seed, counter, self.proposal.data_ptr(),
+        if self.global_ensemble:
+            c = gather_complement(c)  # every rank's complementary half: partners come from the whole ensemble
+        # global index of this launch's first walker: rank-major within each half (distinct streams on every rank)
+        offset = self.rank * self.half + (0 if lo == 0 else self.world * self.half)
+        stream = ctypes.c_void_p(self.torch.cuda.current_stream(self.walkers.device).cuda_stream)
+        self._check(self.lib.baysar_stretch_propose(w.data_ptr(), c.data_ptr(), self.n_params, hi - lo, c.shape[0], self.a,
+                                                    self.seed, counter, offset, self.proposal.data_ptr(),
                                                     self.log_factor.data_ptr(), stream))
         logp_new, status = self.post.logp_batch(self.proposal, return_status=True)
         self._check(self.lib.baysar_stretch_accept(w.data_ptr(), self.logp[lo:hi].data_ptr(), self.proposal.data_ptr(),
                                                    logp_new.data_ptr(), self.log_factor.data_ptr(), status.data_ptr(),
-                                                   self.n_params, hi - lo, self.seed, counter, self.accepted.data_ptr(),
-                                                   stream))
+                                                   self.n_params, hi - lo, self.seed, counter, offset,
+                                                   self.accepted.data_ptr(), stream))
 
     def step(self):
         """One ensemble step = red half against blue, then blue half against the updated red."""

@@ -95,9 +95,9 @@ def library():
     lib.baysar_model_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     lib.baysar_model_get_profile.restype = i32
     u64 = ctypes.c_uint64
-    lib.baysar_stretch_propose.argtypes = [vp, vp, i32, i64, i64, ctypes.c_double, u64, u64, vp, vp, vp]
+    lib.baysar_stretch_propose.argtypes = [vp, vp, i32, i64, i64, ctypes.c_double, u64, u64, i64, vp, vp, vp]
     lib.baysar_stretch_propose.restype = i32
-    lib.baysar_stretch_accept.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, u64, u64, vp, vp]
+    lib.baysar_stretch_accept.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, u64, u64, i64, vp, vp]
     lib.baysar_stretch_accept.restype = i32
     lib.baysar_last_error.restype = ctypes.c_char_p
     lib.baysar_version.restype = ctypes.c_char_p

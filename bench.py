@@ -447,6 +447,70 @@ def run_workload(env, name, batch, steps, warmup, sync_gather=False, scaling="we
     return line
 
 
+def run_ensemble(env, walkers_per_gpu, steps, warmup, chords=32):
+    """BASELINE configs[3]: the 32-chord divertor set under the on-device affine-invariant ensemble (stretch move), the
+    walkers sharded over the ranks as ONE ensemble: every half-step all-gathers the complementary half's positions over
+    NCCL, proposes, evaluates the batched posterior on this rank's half and accepts.  One step = two half-steps = one
+    posterior evaluation per walker; value = posterior evals/s over all ranks (device time, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    import baysar_b200.lineshapes as host_ns
+    from baysar_b200 import configs
+    from baysar_b200.atomic_data import SyntheticADAS
+    from baysar_b200.ensemble import StretchEnsemble
+    from baysar_b200.input_functions import make_input_dict
+    from baysar_b200.posterior import BaysarPosterior
+
+    rank, world = env.rank, env.world
+    wl = configs.multi_species(chords)
+    np.random.seed(0)
+    post = BaysarPosterior(make_input_dict(**wl.input_kwargs), profile_function=wl.make_profile(host_ns),
+                           atomic_data=SyntheticADAS(), device=env.local_rank, skip_test=True)
+    centre = wl.theta_from_tags(post.plasma.slices, post.random_start())
+    tb = np.asarray(post.plasma.theta_bounds, dtype=float)
+    rng = np.random.default_rng(20261019 + 4 + rank)
+    start = centre + 1e-3 * (tb[:, 1] - tb[:, 0]) * rng.standard_normal((walkers_per_gpu, len(centre)))
+    ens = StretchEnsemble(post, start, seed=1234)  # one seed: the draws are counted by global walker index
+    for _ in range(warmup):
+        ens.step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(steps):
+        ens.step()
+    allp = ens.gather_logp()
+    e1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # the stored log-posteriors are those of the stored walkers (same kernels: bit-identical), a cheap in-run consistency check
+    again = post.logp_batch(ens.walkers[:4096])
+    consistent = bool(torch.equal(again, ens.logp[:4096]))
+    if rank != 0:
+        return None
+    total_ms = float(ms.item())
+    n_params = int(post.plasma.n_params)
+    return {"metric": METRIC, "value": world * walkers_per_gpu * steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 element-wise / f64 line-of-sight, reductions and likelihood", "data": "synthetic",
+            "config": {"workload": "ensemble_32chords", "chords": chords, "walkers_per_gpu": walkers_per_gpu,
+                       "walkers": world * walkers_per_gpu, "n_params": n_params,
+                       "l2_between_steps": f"inputs larger than L2 ({walkers_per_gpu // 2 * chords * 12 // 1024} MB of spectra per half-step)"},
+            "implementation": {"ensemble": "one global ensemble: complementary half all-gathered over NCCL every half-step"
+                               if world > 1 else "one ensemble on one GPU",
+                               "complement_all_gather_bytes_per_half_step": world * (walkers_per_gpu // 2) * n_params * 8},
+            "clocks": env.sampler.window(t_wall0, t_wall1) if env.sampler else None,
+            "gpu_launches": steps * 2 * (2 + post.model.launches_last_eval),
+            "acceptance_fraction": ens.acceptance_fraction, "stored_logp_bit_identical": consistent,
+            "mean_logp": float(allp.mean().item())}
+
+
 # ----------------------------------------------------------------------------------------------- main
 def reference_arm(args, batch):
     """`--impl reference`: the reference is pure Python and cannot travel to the GPU box; its CPU implementation of the
@@ -487,13 +551,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="only the main workload's line")
+    ap.add_argument("--ensemble-walkers", type=int, default=131072, help="walkers per GPU of the ensemble_32chords line")
     ap.add_argument("--sync-gather", action="store_true", help="N > 1: logP all-gather on the compute stream")
     ap.add_argument("--options", default="", help="baysar_options_t fields of the main workload's model, key=value,... "
                                                   "(kernel-selection experiments; default: the library's choices)")
     args = ap.parse_args()
 
     env = Env()
-    batch = args.batch or BATCH_PER_GPU[args.workload]
+    batch = args.batch or BATCH_PER_GPU.get(args.workload, args.ensemble_walkers)
     if args.scaling == "strong":
         batch = max(batch // env.world, 1)
 
@@ -516,6 +581,15 @@ def main():
     env.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
     env.peaks = runtime.microbench(env.local_rank) if env.rank == 0 else None
     parity = None if args.no_parity else (256, 16)
+
+    if args.workload == "ensemble_32chords":
+        line = run_ensemble(env, args.ensemble_walkers, args.steps, max(args.warmup, 1))
+        if env.rank == 0:
+            env.sampler.stop()
+            print(json.dumps(line))
+        if env.world > 1:
+            dist.destroy_process_group()
+        return
 
     options = {k: int(v) for k, v in (kv.split("=") for kv in args.options.split(",") if kv)} or None
     line = run_workload(env, args.workload, batch, args.steps, args.warmup, sync_gather=args.sync_gather,
@@ -541,6 +615,10 @@ def main():
             if res is not None:
                 res.pop("_thetas_pool", None)
                 extras.append(res)
+        # BASELINE configs[3]: 32 chords, 2^20 walkers over 8 GPUs = 131072 per GPU (weak), one global ensemble
+        res = run_ensemble(env, args.ensemble_walkers, 3, 1)
+        if res is not None:
+            extras.append(res)
 
     if env.rank != 0:
         if env.world > 1:

@@ -133,11 +133,11 @@ const char* baysar_version(void);
  * All pointers are device pointers.
  */
 int baysar_stretch_propose(const double* walkers, const double* complement, int n_params, int64_t n_walkers,
-                           int64_t n_complement, double a, uint64_t seed, uint64_t step, double* proposal,
-                           double* log_factor, void* stream);
+                           int64_t n_complement, double a, uint64_t seed, uint64_t step, int64_t walker_offset,
+                           double* proposal, double* log_factor, void* stream);
 int baysar_stretch_accept(double* walkers, double* logp, const double* proposal, const double* logp_new,
                           const double* log_factor, const uint32_t* status_new, int n_params, int64_t n_walkers,
-                          uint64_t seed, uint64_t step, unsigned long long* n_accepted, void* stream);
+                          uint64_t seed, uint64_t step, int64_t walker_offset, unsigned long long* n_accepted, void* stream);
 
 #ifdef __cplusplus
 }

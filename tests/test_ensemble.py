@@ -47,9 +47,11 @@ def test_propose_and_accept_kernels_match_numpy_twin():
     w, c = torch.as_tensor(walkers, device="cuda"), torch.as_tensor(comp, device="cuda")
     prop = torch.empty_like(w)
     fac = torch.empty(S, dtype=torch.float64, device="cuda")
-    assert lib.baysar_stretch_propose(w.data_ptr(), c.data_ptr(), n, S, C, a, seed, step, prop.data_ptr(), fac.data_ptr(),
-                                      None) == 0
-    z, pick, lnu = reference_draws(S, seed, step, C, a)
+    off = (1 << 33) + 12345  # global index of the first walker: the counter's 64-bit walker word
+    step = (5 << 32) + 13     # and a step past 2^32: its high word goes into the counter too
+    assert lib.baysar_stretch_propose(w.data_ptr(), c.data_ptr(), n, S, C, a, seed, step, off, prop.data_ptr(),
+                                      fac.data_ptr(), None) == 0
+    z, pick, lnu = reference_draws(S, seed, step, C, a, walker_offset=off)
     expect = comp[pick] + z[:, None] * (walkers - comp[pick])
     np.testing.assert_allclose(prop.cpu().numpy(), expect, rtol=1e-14, atol=1e-14)
     np.testing.assert_allclose(fac.cpu().numpy(), (n - 1) * np.log(z), rtol=1e-13, atol=1e-13)
@@ -62,7 +64,7 @@ def test_propose_and_accept_kernels_match_numpy_twin():
     st = torch.as_tensor(status.astype(np.int32), device="cuda")
     count = torch.zeros(1, dtype=torch.int64, device="cuda")
     assert lib.baysar_stretch_accept(w.data_ptr(), lo.data_ptr(), prop.data_ptr(), ln.data_ptr(), fac.data_ptr(),
-                                     st.data_ptr(), n, S, seed, step, count.data_ptr(), None) == 0
+                                     st.data_ptr(), n, S, seed, step, off, count.data_ptr(), None) == 0
     take = (status == 0) & np.isfinite(logp_new) & (lnu < (n - 1) * np.log(z) + logp_new - logp_old)
     assert int(count.item()) == int(take.sum())
     np.testing.assert_array_equal(w.cpu().numpy(), np.where(take[:, None], prop.cpu().numpy(), walkers))
@@ -94,3 +96,55 @@ def test_ensemble_on_a_real_posterior():
     ens2 = StretchEnsemble(post, start, seed=42)
     ens2.run(12)
     assert torch.equal(ens2.walkers, ens.walkers)
+
+
+def _two_rank_half_step(rank, world, port, out):
+    """One red half-step of a 2-rank GLOBAL ensemble: the partner of every walker is drawn from both ranks' blue halves."""
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from baysar_b200 import runtime
+    from baysar_b200.ensemble import gather_complement
+
+    lib = runtime.library()
+    rng = np.random.default_rng(100)
+    half, n = 64, 5
+    all_walkers = rng.normal(size=(world, 2 * half, n))  # [rank][red then blue][param]
+    mine = torch.as_tensor(all_walkers[rank], device="cuda")
+    comp = gather_complement(mine[half:])
+    prop = torch.empty((half, n), dtype=torch.float64, device="cuda")
+    fac = torch.empty(half, dtype=torch.float64, device="cuda")
+    assert lib.baysar_stretch_propose(mine[:half].data_ptr(), comp.data_ptr(), n, half, comp.shape[0], 2.0, 77, 3,
+                                      rank * half, prop.data_ptr(), fac.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    out[rank] = (comp.cpu().numpy(), prop.cpu().numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_global_complement_half_step_on_two_gpus():
+    """BASELINE configs[3] semantics: ONE ensemble sharded over the ranks.  Each rank's proposals use partners from the
+    all-gathered complementary half (both ranks' rows, rank order) and the counter-based draws of its global walker
+    indices -- compared with the numpy twin."""
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    world, half, n = 2, 64, 5
+    out = mp.Manager().dict()
+    mp.spawn(_two_rank_half_step, args=(world, 29731, out), nprocs=world, join=True)
+    rng = np.random.default_rng(100)
+    all_walkers = rng.normal(size=(world, 2 * half, n))
+    blue = np.concatenate([all_walkers[r, half:] for r in range(world)])
+    for r in range(world):
+        comp, prop = out[r]
+        np.testing.assert_array_equal(comp, blue)
+        z, pick, _ = reference_draws(half, 77, 3, world * half, 2.0, walker_offset=r * half)
+        assert pick.max() >= half  # partners do come from the other rank's rows
+        np.testing.assert_allclose(prop, blue[pick] + z[:, None] * (all_walkers[r, :half] - blue[pick]), rtol=1e-14, atol=1e-14)

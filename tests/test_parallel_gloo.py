@@ -79,3 +79,38 @@ def test_stretch_move_is_affine_combination():
     partner = (prop[keep] - z[keep, None] * w[keep]) / (1 - z[keep, None])
     d = (partner[:, None, :] - c[None, :, :]).norm(dim=2).min(dim=1).values
     assert keep.sum() > 32 and np.all(d.numpy() < 1e-9)
+
+
+def _complement_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from baysar_b200.ensemble import gather_complement, reference_draws
+
+        half, n = 6, 3
+        blue = torch.arange(half * n, dtype=torch.float64).reshape(half, n) + 1000.0 * rank  # this rank's complementary half
+        comp = gather_complement(blue)
+        # the global ensemble's half-step on the host: partner rows from every rank, draws counted by global walker index
+        z, pick, _ = reference_draws(half, seed=5, step=2, n_complement=world * half, walker_offset=rank * half)
+        out[rank] = (comp.numpy().copy(), pick.copy(), z.copy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_global_ensemble_complement_two_ranks():
+    """The N > 1 ensemble is ONE ensemble: the complementary half is every rank's rows in rank order, identical on all
+    ranks, and two ranks that share the seed still draw different partners (global walker index in the counter)."""
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        out = mgr.dict()
+        port = 31500 + os.getpid() % 2000
+        procs = [ctx.Process(target=_complement_worker, args=(r, 2, port, out)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+        (c0, p0, z0), (c1, p1, z1) = out[0], out[1]
+        np.testing.assert_array_equal(c0, c1)
+        assert c0.shape == (12, 3) and c0[6, 0] == 1000.0 and c0[0, 0] == 0.0
+        assert not np.array_equal(z0, z1) and p0.max() < 12 and p1.max() < 12

@@ -10,7 +10,10 @@ def show(l, indent=""):
     roof = l.get("roofline") or {}
     print(f"{indent}{l['config']['workload'][:40]:40s} n={l['n_gpus']} {l['scaling']:6s} {l['value'] / 1e6:8.3f} M evals/s  "
           f"{l['ms_per_step']:.4f} ms/step  e2e {e2e.get('value', 0) / 1e6:.3f} M  launches/step {l['gpu_launches'] // l['steps']}  "
-          f"ok {l['status_ok_fraction']:.3f}")
+          f"ok {l.get('status_ok_fraction', float('nan')):.3f}")
+    if "stage_ms" not in l:  # the ensemble line
+        print(f"{indent}   {l['implementation']['ensemble']}; acceptance {l['acceptance_fraction']:.3f}, walkers {l['config']['walkers']}")
+        return
     print(f"{indent}   stages " + " ".join(f"{k}={v:.4f}" for k, v in l["stage_ms"].items() if v > 0) +
           f" | all-gather: {l['implementation']['logp_all_gather']}")
     if par:
