@@ -345,7 +345,12 @@ int launch_pxc(PxcPlan& pl, const float* spec, int n_rb, float* out, double* tsu
   p.bbar = tsum ? pl.d_bbar : nullptr; p.tile_boff = pl.d_tile_boff; p.tsum = tsum;
   p.n_col_tiles = pl.n_col_tiles;
   // A loader: cp.async by two loader warps.  The TMA variant (one cp.async.bulk.tensor box per k-block) is compiled only
-  // with -DBAYSAR_PXC_TMA: one build of it delivered stale A rows in cold first launches (DESIGN.md section 4, K2b').
+  // with -DBAYSAR_PXC_TMA.  Its data hazard is root-caused (round 2): the converters read a ring stage through the generic
+  // proxy and the TMA refill writes it through the async proxy; the mbarrier hand-over alone does not order the two, so
+  // a lagging lane could read the next cycle's data (single elements, a few launches in a thousand:
+  // profiles/r2_pxc_tma_loader_unfenced_determinism.log).  With fence.proxy.async before the hand-over it is bit-
+  // reproducible (profiles/r2_pxc_tma_loader_fenced_determinism.log) but the fence costs more than the TMA saves
+  // (contraction 0.1076 ms against 0.1038 ms with cp.async), so cp.async stays the loader.
   p.use_tma = 0;
   p.sleep_epi = 0; p.sleep_build = 0;
   CUtensorMap tmap;

@@ -269,6 +269,10 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p, cons
           split_fast(raw[c].z, hi[4 * c + 2], lo[4 * c + 2]);
           split_fast(raw[c].w, hi[4 * c + 3], lo[4 * c + 3]);
         }
+        // TMA loader: the stage is refilled through the async proxy, and nothing orders this warp's generic-proxy
+        // reads before that write except a cross-proxy fence (without it single elements of a row came back with the
+        // NEXT ring cycle's data in a few of a thousand launches: write-after-read across proxies)
+        if (p.use_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive32(consumed + 8 * r);
         if (d_pending >= 0) {  // the group's previous k-block is in tensor memory: hand it over
