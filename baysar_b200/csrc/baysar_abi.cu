@@ -111,21 +111,40 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
       for (int b = minb + 1; b <= 7; ++b)
         if (ctas <= (int64_t)b * m->sm_count) { minb = b; break; }
   }
-  // Long lines of sight: the per-point cache (128 B per point and theta) starves the warp-per-theta form of occupancy
-  // (L = 1000: one warp per SM).  From options.los_team_points points on (default: as soon as four thetas no longer fit
-  // one CTA's 200 KB) one CTA of four warps works on ONE theta, the points spread over its 128 threads.
-  const int team_l = m->opt.los_team_points;
-  const bool team = (team_l > 0 && L >= team_l) || 4 * per_warp > 200 * 1024;
-  if (m->opt.los_team_warps == 2 && per_warp + los_team_xch_bytes(2) <= 200 * 1024) {
-    // two warps per theta: the per-point cache (the occupancy limit of the warp-per-theta form) is shared by twice the threads
-    const size_t smem = per_warp + los_team_xch_bytes(2);
-    if (m->opt.los_min_blocks >= 16) los_stage_kernel<2, 16, 1, 2><<<(unsigned)n, 64, smem, stream>>>(m->dev, a);
-    else los_stage_kernel<2, 12, 1, 2><<<(unsigned)n, 64, smem, stream>>>(m->dev, a);
-  } else if (team && per_warp + los_team_xch_bytes(8) <= 200 * 1024) {
-    if (2 * (per_warp + los_team_xch_bytes(4)) > 200 * 1024)  // one CTA per SM anyway: eight warps per theta
-      los_stage_kernel<8, 1, 1, 8><<<(unsigned)n, 256, per_warp + los_team_xch_bytes(8), stream>>>(m->dev, a);
-    else
-      los_stage_kernel<4, 1, 1, 4><<<(unsigned)n, 128, per_warp + los_team_xch_bytes(4), stream>>>(m->dev, a);
+  // Long lines of sight: the per-point cache (84 B per point and theta) starves the warp-per-theta form of occupancy, so
+  // from a few hundred points on TW warps share ONE theta (one CTA per theta, the points spread over its threads).
+  // Measured LOS time per 32768 thetas (20 lines, tools/los_team_probe.py): L = 100: 1.92 ms warp-per-theta, 2.66 team
+  // of four at 128 registers, 2.13 at 96; 160: 2.91 / 2.87; 200: 4.35 / 3.32; 300: 8.88 / 4.66; 500: 18.0 / 7.87;
+  // 700: 10.8 with eight warps, two CTAs per SM (12.4 with four); 1000: 15.2 (23.0).  Default: warp-per-theta up to
+  // 160 points, then the team size (four or eight warps) and register budget that keep the most warps on an SM.
+  // options.los_team_points (teams from that length on), los_team_warps (2, 4, 8) and los_min_blocks override.
+  const size_t smem_sm = 227 * 1024;
+  int tw = m->opt.los_team_warps;
+  if (tw != 2 && tw != 4 && tw != 8) {
+    tw = 0;
+    const int team_l = m->opt.los_team_points;
+    if ((team_l > 0 && L >= team_l) || 4 * per_warp > 200 * 1024 || L > 160) {
+      const int n4 = (int)std::min<size_t>(smem_sm / (per_warp + los_team_xch_bytes(4) + 1024), 5);
+      const int n8 = (int)std::min<size_t>(smem_sm / (per_warp + los_team_xch_bytes(8) + 1024), 2);
+      tw = 8 * n8 > 4 * n4 ? 8 : 4;
+    }
+  }
+  if (tw && per_warp + los_team_xch_bytes(tw) > 200 * 1024) tw = 0;
+  if (tw) {
+    const size_t smem = per_warp + los_team_xch_bytes(tw);
+    const int fit = (int)(smem_sm / (smem + 1024));
+    const int want = m->opt.los_min_blocks > 0 ? m->opt.los_min_blocks : fit;
+    if (tw == 2) {
+      if (want >= 16) los_stage_kernel<2, 16, 1, 2><<<(unsigned)n, 64, smem, stream>>>(m->dev, a);
+      else los_stage_kernel<2, 12, 1, 2><<<(unsigned)n, 64, smem, stream>>>(m->dev, a);
+    } else if (tw == 4) {
+      if (want >= 5) los_stage_kernel<4, 5, 1, 4><<<(unsigned)n, 128, smem, stream>>>(m->dev, a);
+      else if (want == 4) los_stage_kernel<4, 4, 1, 4><<<(unsigned)n, 128, smem, stream>>>(m->dev, a);
+      else los_stage_kernel<4, 1, 1, 4><<<(unsigned)n, 128, smem, stream>>>(m->dev, a);
+    } else {
+      if (want >= 2) los_stage_kernel<8, 2, 1, 8><<<(unsigned)n, 256, smem, stream>>>(m->dev, a);
+      else los_stage_kernel<8, 1, 1, 8><<<(unsigned)n, 256, smem, stream>>>(m->dev, a);
+    }
   } else if (4 * per_warp <= 200 * 1024) {
     const size_t smem = 4 * per_warp;
     auto kern = minb >= 6 ? los_stage_kernel<4, 6> : (minb == 5 ? los_stage_kernel<4, 5> : los_stage_kernel<4, 4>);
@@ -158,6 +177,9 @@ int ensure_ifc_workspace(baysar_model* m, int64_t n) {
   CUDA_OK(cudaMalloc(&m->aux, sizeof(double) * rows * BAYSAR_AUX_STRIDE));
   // rows past the end of a batch are multiplied too (M = 128 granularity): keep them finite
   CUDA_OK(cudaMemset(m->spec, 0, sizeof(float) * rows * m->split_pitch_max));
+  // the memset runs on the legacy stream, the evaluation on a non-blocking one: without this (allocation-time only)
+  // synchronisation nothing orders the zero fill before the first spectral-stage launch that writes the same rows
+  CUDA_OK(cudaDeviceSynchronize());
   m->ifc_rows = rows;
   m->spec_pitch_last = -1; m->spec_rows_last = 0;
   return 0;
@@ -208,6 +230,8 @@ int mark(baysar_model* m, int slot, cudaStream_t stream) {
 // Opt-in shared-memory limits of every kernel variant the launchers can pick: once per model creation
 int set_kernel_attributes() {
   if (allow_max_smem(los_stage_kernel<2, 12, 1, 2>) || allow_max_smem(los_stage_kernel<2, 16, 1, 2>) ||
+      allow_max_smem(los_stage_kernel<4, 4, 1, 4>) || allow_max_smem(los_stage_kernel<4, 5, 1, 4>) ||
+      allow_max_smem(los_stage_kernel<8, 2, 1, 8>) ||
       allow_max_smem(los_stage_kernel<8, 1, 1, 8>) || allow_max_smem(los_stage_kernel<4, 1, 1, 4>) ||
       allow_max_smem(los_stage_kernel<4, 4>) || allow_max_smem(los_stage_kernel<4, 5>) ||
       allow_max_smem(los_stage_kernel<4, 6>) || allow_max_smem(los_stage_kernel<4, 7>) ||

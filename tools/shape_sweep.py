@@ -7,8 +7,8 @@ Synthetic chords (`baysar_b200.configs.synthetic_sweep`): L line-of-sight points
 lines (+ 2 Balmer lines) x P pixels at 0.15 A per pixel, refine 0.05 (F ~ 3 P).  By default one axis is varied at a
 time around (L, n_G, P) = (100, 20, 1024); `--full` walks the whole 5 x 5 x 4 grid.  For every shape: log-posterior
 evals/s on one GPU (thetas resident in HBM, CUDA events, theta batches sized so that a step takes >= 50 ms), the time
-per stage and the executed-work fractions of the spectral kernel against the FP32 / MUFU peaks measured in the same
-run.  One JSON line per shape.
+per stage (the pipe fractions of the stage kernels come from ncu opcode counters, tools/ncu_counters.py, for the two
+bench workloads).  One JSON line per shape.
 """
 import argparse
 import json
@@ -30,7 +30,7 @@ def run_shape(L, G, P, balmer, peaks, target_ms=50.0):
     from baysar_b200.atomic_data import SyntheticADAS
     from baysar_b200.input_functions import make_input_dict
     from baysar_b200.posterior import BaysarPosterior
-    from bench import draw_thetas, flop_model
+    from bench import draw_thetas
 
     wl = configs.synthetic_sweep(L, G, P, balmer=balmer)
     np.random.seed(0)
@@ -66,14 +66,10 @@ def run_shape(L, G, P, balmer, peaks, target_ms=50.0):
     post.model.set_profiling(False)
     ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     status = post.last_status_device.cpu().numpy()
-    flops = flop_model(post)
-    chord_ms = stage_ms["chord"] / max(calls, 1)
     out = {"L": L, "n_G": G, "P": P, "F": len(post.chords[0].x_data_fm), "n_B": 2 if balmer else 0, "n_params": n_params,
            "thetas_per_step": n, "ms_per_step": ms, "evals_per_s": n / (ms * 1e-3),
            "stage_ms": {k: v / max(calls, 1) for k, v in stage_ms.items()},
            "tensor_core_contraction": post.model.uses_tensor_cores,
-           "chord_fp32_frac": flops["chord"] * n / (chord_ms * 1e-3) / peaks["fp32_fma_flops"] if chord_ms > 0 else None,
-           "chord_mufu_frac": flops["chord_mufu"] * n / (chord_ms * 1e-3) / peaks["mufu_ops"] if chord_ms > 0 else None,
            "status_ok_fraction": float((status == 0).mean()), "model_build_s": build_s}
     post.model.close()
     return out
