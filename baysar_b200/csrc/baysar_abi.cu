@@ -93,6 +93,7 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
   LosArgs a;
   a.theta = theta; a.n = n; a.lines = lines; a.components = comps; a.hdr = m->hdr; a.profiles = profiles;
   a.status = status;
+  const bool pdl = !m->opt.serial_launches;
   const int L = (int)m->I[I_L];
   const size_t per_warp = los_smem_per_warp(L, (int)m->I[I_N_PARAMS], (int)m->I[I_N_SPECIES]);
   if (per_warp > 200 * 1024) return fail("line-of-sight grid too long for the shared-memory LOS stage");
@@ -135,24 +136,24 @@ int launch_los(baysar_model* m, const double* theta, int64_t n, double* lines, d
     const int fit = (int)(smem_sm / (smem + 1024));
     const int want = m->opt.los_min_blocks > 0 ? m->opt.los_min_blocks : fit;
     if (tw == 2) {
-      if (want >= 16) los_stage_kernel<2, 16, 1, 2><<<(unsigned)n, 64, smem, stream>>>(m->dev, a);
-      else los_stage_kernel<2, 12, 1, 2><<<(unsigned)n, 64, smem, stream>>>(m->dev, a);
+      if (want >= 16) CUDA_OK(launch_k(pdl, los_stage_kernel<2, 16, 1, 2>, dim3((unsigned)n), dim3(64), smem, stream, m->dev, a));
+      else CUDA_OK(launch_k(pdl, los_stage_kernel<2, 12, 1, 2>, dim3((unsigned)n), dim3(64), smem, stream, m->dev, a));
     } else if (tw == 4) {
-      if (want >= 5) los_stage_kernel<4, 5, 1, 4><<<(unsigned)n, 128, smem, stream>>>(m->dev, a);
-      else if (want == 4) los_stage_kernel<4, 4, 1, 4><<<(unsigned)n, 128, smem, stream>>>(m->dev, a);
-      else los_stage_kernel<4, 1, 1, 4><<<(unsigned)n, 128, smem, stream>>>(m->dev, a);
+      if (want >= 5) CUDA_OK(launch_k(pdl, los_stage_kernel<4, 5, 1, 4>, dim3((unsigned)n), dim3(128), smem, stream, m->dev, a));
+      else if (want == 4) CUDA_OK(launch_k(pdl, los_stage_kernel<4, 4, 1, 4>, dim3((unsigned)n), dim3(128), smem, stream, m->dev, a));
+      else CUDA_OK(launch_k(pdl, los_stage_kernel<4, 1, 1, 4>, dim3((unsigned)n), dim3(128), smem, stream, m->dev, a));
     } else {
-      if (want >= 2) los_stage_kernel<8, 2, 1, 8><<<(unsigned)n, 256, smem, stream>>>(m->dev, a);
-      else los_stage_kernel<8, 1, 1, 8><<<(unsigned)n, 256, smem, stream>>>(m->dev, a);
+      if (want >= 2) CUDA_OK(launch_k(pdl, los_stage_kernel<8, 2, 1, 8>, dim3((unsigned)n), dim3(256), smem, stream, m->dev, a));
+      else CUDA_OK(launch_k(pdl, los_stage_kernel<8, 1, 1, 8>, dim3((unsigned)n), dim3(256), smem, stream, m->dev, a));
     }
   } else if (4 * per_warp <= 200 * 1024) {
     const size_t smem = 4 * per_warp;
     auto kern = minb >= 6 ? los_stage_kernel<4, 6> : (minb == 5 ? los_stage_kernel<4, 5> : los_stage_kernel<4, 4>);
     if (minb == 7) kern = los_stage_kernel<4, 7>;
     if (minb >= 8) kern = los_stage_kernel<4, 8>;
-    kern<<<(unsigned)((n + 3) / 4), 128, smem, stream>>>(m->dev, a);
+    CUDA_OK(launch_k(pdl, kern, dim3((unsigned)((n + 3) / 4)), dim3(128), smem, stream, m->dev, a));
   } else {
-    los_stage_kernel<1><<<(unsigned)n, 32, per_warp, stream>>>(m->dev, a);
+    CUDA_OK(launch_k(pdl, los_stage_kernel<1>, dim3((unsigned)n), dim3(32), per_warp, stream, m->dev, a));
   }
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -194,7 +195,7 @@ int launch_chord_kernel(baysar_model* m, const ChordArgs& a, dim3 grid, size_t s
   const bool nt128 = m->opt.chord_threads == 128 || (m->opt.chord_threads == 0 && m->I[I_F_MAX] <= 4096);
   if (nt128) {
     auto kern = single_tap_only ? chord_stage_kernel<128, MODE, 6, false> : chord_stage_kernel<128, MODE, 6>;
-    kern<<<grid, 128, smem, stream>>>(m->dev, a);
+    CUDA_OK(launch_k(!m->opt.serial_launches, kern, grid, dim3(128), smem, stream, m->dev, a));
     CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -206,7 +207,7 @@ int launch_chord_kernel(baysar_model* m, const ChordArgs& a, dim3 grid, size_t s
   if (single_tap_only)  // every Balmer line of the chord is a guaranteed single Doppler tap: leaner build
     kern = minb >= 5 ? chord_stage_kernel<NT, MODE, 5, false>
                      : (minb == 4 ? chord_stage_kernel<NT, MODE, 4, false> : chord_stage_kernel<NT, MODE, 3, false>);
-  kern<<<grid, NT, smem, stream>>>(m->dev, a);
+  CUDA_OK(launch_k(!m->opt.serial_launches, kern, grid, dim3(NT), smem, stream, m->dev, a));
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -295,7 +296,7 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
       if (mark(m, ST_CHORD, stream)) return 1;
       if (folded) {
         // K2b': instrument function and wavelength map as one tcgen05 contraction; K2c': area identity + likelihood
-        if (launch_pxc(fx, m->spec, (int)(rows128 / ifc::TILE_M), m->conv, m->trapz_part, m->sm_count, stream)) return 1;
+        if (launch_pxc(fx, m->spec, (int)(rows128 / ifc::TILE_M), m->conv, m->trapz_part, m->sm_count, stream, nullptr, !m->opt.serial_launches)) return 1;
         if (mark(m, ST_CONTRACT, stream)) return 1;
         PixelFoldArgs pf{};
         pf.theta = theta + r0 * n_params; pf.n = rows; pf.chord = c; pf.cp = m->conv; pf.cp_pitch = fx.out_pitch;
@@ -311,7 +312,7 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
           if (fuse && finalized) *finalized = true;
           const size_t row_bytes = sizeof(float) * (size_t)fx.out_pitch;
           if (row_bytes > 160 * 1024) return fail("contraction row too long for the pixel stage's shared-memory copy");
-          pixel_fold_kernel<128><<<(unsigned)rows, 128, row_bytes, stream>>>(m->dev, pf);
+          CUDA_OK(launch_k(!m->opt.serial_launches, pixel_fold_kernel<128>, dim3((unsigned)rows), dim3(128), row_bytes, stream, m->dev, pf));
         }
         CUDA_OK(cudaGetLastError());
         if (mark(m, ST_PIXEL, stream)) return 1;
@@ -708,7 +709,7 @@ int baysar_eval_logp(baysar_model_t* m, const double* theta, int64_t n, double* 
     return 1;
   if (!finalized) {
     const int ncols = (int)(m->I[I_N_CHORDS] + m->I[I_N_PRIORS]);
-    finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(comps, ncols, n, logp, st);
+    CUDA_OK(launch_k(!m->opt.serial_launches, finalize_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, comps, ncols, n, logp, st));
     CUDA_OK(cudaGetLastError());
     m->last_launches += 1;
   }

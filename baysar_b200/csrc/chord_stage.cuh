@@ -341,6 +341,8 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
 #else
   extern __shared__ __align__(16) unsigned char chord_smem_raw[];
 #endif
+  pdl_trigger();
+  pdl_wait();  // the line records come from the LOS stage
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n = blockIdx.x;
   const int c = a.chord;
@@ -1156,6 +1158,8 @@ struct PixelFoldArgs {
 #endif
 template <int NT>
 __global__ void __launch_bounds__(NT, BAYSAR_PIXFOLD_MINB) pixel_fold_kernel(ModelDev m, PixelFoldArgs a) {
+  pdl_trigger();
+  pdl_wait();  // the contraction's columns and tile sums
 #ifdef BAYSAR_CPU_EMU
   double* scratch = reinterpret_cast<double*>(emu_dynamic_smem());
   float* row = reinterpret_cast<float*>(scratch + 160);

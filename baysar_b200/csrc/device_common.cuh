@@ -104,6 +104,17 @@ BAYSAR_DEV f32x2 mul2(f32x2 a, f32x2 b) { return f32x2{a.lo * b.lo, a.hi * b.hi}
 BAYSAR_DEV f32x2 add2(f32x2 a, f32x2 b) { return f32x2{a.lo + b.lo, a.hi + b.hi}; }
 #endif
 
+// Programmatic dependent launch (host_plans.h launch_k): pdl_trigger lets the next kernel of the stream be scheduled once
+// every CTA of this grid has started; pdl_wait blocks until the previous grid has completed and flushed its writes.
+// Every kernel of an evaluation calls both before its first global-memory access, so stream order is preserved.
+#ifndef BAYSAR_CPU_EMU
+BAYSAR_DEV void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+BAYSAR_DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#else
+BAYSAR_DEV void pdl_trigger() {}
+BAYSAR_DEV void pdl_wait() {}
+#endif
+
 // np.clip(v, lo, None): NaN propagates (fmax would swallow it)
 BAYSAR_DEV double clip_lo(double v, double lo) { return v < lo ? lo : v; }
 

@@ -4,6 +4,8 @@
 #include "device_common.cuh"
 
 __global__ void finalize_kernel(const double* comps, int ncols, int64_t n, double* logp, uint32_t* status) {
+  pdl_trigger();
+  pdl_wait();  // the components of the chord / pixel kernels
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double* c = comps + i * ncols;

@@ -11,6 +11,7 @@
 #include <map>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "if_contract.cuh"
@@ -27,6 +28,23 @@ static int fail(const std::string& msg) {
     cudaError_t e_ = (expr);                                                                   \
     if (e_ != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));    \
   } while (0)
+
+// Kernel launch with programmatic dependent launch (PDL): the grid may be scheduled while the previous kernel of the
+// stream is still draining its last wave, so launch latency and the prologue of this kernel overlap with that tail.
+// Every kernel of the evaluation executes griddepcontrol.wait (pdl_wait) before its first access to global memory, which
+// blocks until the previous grid has completed and its writes are visible: stream order is unchanged, only the gaps
+// between the kernels close.  `pdl = false` launches plainly (options.serial_launches, for A/B timing).
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 namespace {
 // Host-side packing of one chord's instrument function for the tensor-core contraction (if_contract.cuh).
@@ -303,8 +321,8 @@ int contraction_kernel_attributes() {
 }
 
 template <int TN, bool TRACE>
-int launch_pxc_t(const pxc::Params& p, const CUtensorMap& tmap, int ctas, size_t smem, cudaStream_t stream) {
-  pxc::pix_contract_kernel<TN, TRACE><<<ctas, pxc::THREADS, smem, stream>>>(p, tmap);
+int launch_pxc_t(const pxc::Params& p, const CUtensorMap& tmap, int ctas, size_t smem, cudaStream_t stream, bool pdl) {
+  CUDA_OK(launch_k(pdl, pxc::pix_contract_kernel<TN, TRACE>, dim3(ctas), dim3(pxc::THREADS), smem, stream, p, tmap));
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -334,7 +352,7 @@ int make_spec_tmap(const float* spec, int64_t pitch, int64_t rows, CUtensorMap* 
 }
 
 int launch_pxc(PxcPlan& pl, const float* spec, int n_rb, float* out, double* tsum, int sms, cudaStream_t stream,
-               long long* dbg_cycles = nullptr) {
+               long long* dbg_cycles = nullptr, bool pdl = false) {
   if (n_rb > 65535) return fail("too many theta blocks for one folded contraction launch");
   const PxcSchedule* sc = nullptr;
   if (pxc_schedule(pl, n_rb, sms, &sc)) return 1;
@@ -361,12 +379,12 @@ int launch_pxc(PxcPlan& pl, const float* spec, int n_rb, float* out, double* tsu
 #endif
   if (pl.tn == 64) {
     const size_t smem = pxc::smem_bytes<64>(pl.ring, pl.wlen);
-    return dbg_cycles ? launch_pxc_t<64, true>(p, tmap, sc->ctas, smem, stream)
-                      : launch_pxc_t<64, false>(p, tmap, sc->ctas, smem, stream);
+    return dbg_cycles ? launch_pxc_t<64, true>(p, tmap, sc->ctas, smem, stream, pdl)
+                      : launch_pxc_t<64, false>(p, tmap, sc->ctas, smem, stream, pdl);
   }
   const size_t smem = pxc::smem_bytes<128>(pl.ring, pl.wlen);
-  return dbg_cycles ? launch_pxc_t<128, true>(p, tmap, sc->ctas, smem, stream)
-                    : launch_pxc_t<128, false>(p, tmap, sc->ctas, smem, stream);
+  return dbg_cycles ? launch_pxc_t<128, true>(p, tmap, sc->ctas, smem, stream, pdl)
+                    : launch_pxc_t<128, false>(p, tmap, sc->ctas, smem, stream, pdl);
 }
 
 }  // namespace

@@ -137,6 +137,8 @@ struct LosTeam {
 template <int WARPS, int MINB = 1, int UNR = 1, int TW = 1>
 __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m, LosArgs a) {
   static_assert(TW == 1 || TW == WARPS, "team mode: the whole CTA works on one theta");
+  pdl_trigger();
+  pdl_wait();  // theta comes from the caller's previous kernel; the workspaces are read by the previous evaluation
 #ifdef BAYSAR_CPU_EMU
   unsigned char* los_smem_raw = emu_dynamic_smem();
 #else

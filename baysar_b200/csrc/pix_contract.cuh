@@ -207,6 +207,9 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p, cons
   const uint32_t tmem_slot = acc_free + 8;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // programmatic dependent launch: this prologue (tap table, barriers, tensor-memory allocation; model constants only)
+  // overlaps with the tail of the spectral stage; the spectra are touched only after griddepcontrol.wait below
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int my_tiles = p.sched_cnt[blockIdx.x];
   const int* my_sched = p.sched + (int64_t)blockIdx.x * p.sched_slots;
 
@@ -229,6 +232,7 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p, cons
   asm volatile("tcgen05.fence::after_thread_sync;");
   uint32_t tmem_d;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_d) : "r"(tmem_slot));
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous kernel (the spectral stage) has completed
 
   if (warp < CONVERTER_WARPS) {
     // ===================== A converters: ring (shared memory) -> TF32 split -> tensor memory =====================

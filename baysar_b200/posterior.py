@@ -386,6 +386,24 @@ class BaysarPosterior:
             return spectra.cpu().numpy(), status.cpu().numpy().astype(np.uint32), pre.cpu().numpy(), post.cpu().numpy()
         return spectra.cpu().numpy(), status.cpu().numpy().astype(np.uint32)
 
+    def synthetic_measurement(self, theta, calibration_constant=1e9, rng=None):
+        """Synthetic measured spectra for one theta (or a batch): the forward model of every chord plus the noise model of
+        the reference's synthetic spectrometer (`solps_spectrometer.py:464-471`): sigma^2 = (1e2 c)^2 + c * spectrum,
+        normal noise, floored at the calibration constant c.  -> (list of [N, P_chord] spectra, list of their sigmas).
+        (The reference builds its synthetic spectra from SOLPS grids, which are outside this path; this applies the same
+        measurement model to the posterior's own forward model, e.g. to make self-consistent test data on the GPU.)"""
+        rng = np.random.default_rng() if rng is None else rng
+        thetas = np.atleast_2d(np.asarray(theta, dtype=float))
+        spectra, sigmas = [], []
+        for c in range(len(self.chords)):
+            fm, status = self.spectra_batch(thetas, c)
+            if (status & 0x7FF).any():
+                raise ValueError("the forward model failed for at least one theta (status flags set)")
+            sigma = np.sqrt(np.square(1e2 * calibration_constant) + calibration_constant * fm)
+            spectra.append((fm + rng.normal(0.0, sigma)).clip(calibration_constant))
+            sigmas.append(sigma)
+        return spectra, sigmas
+
     def lines_batch(self, theta, want_profiles=False):
         lines, status, prof = self.model.eval_lines(self._as_device(theta), want_profiles)
         out = lines.cpu().numpy(), status.cpu().numpy().astype(np.uint32)

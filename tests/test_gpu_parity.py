@@ -539,3 +539,18 @@ def test_user_prior_callables():
     with pytest.raises(TypeError):
         BaysarPosterior(make_input_dict(**wl.input_kwargs), profile_function=wl.make_profile(host_ns),
                         atomic_data=SyntheticADAS(), skip_test=True, priors=[3.0])
+
+
+def test_synthetic_measurement_noise_model(posteriors):
+    """Forward model + the reference's synthetic-spectrometer noise model (solps_spectrometer.py:464-471)."""
+    post, _ = posteriors("multi_species")
+    z = np.load(GOLDEN / "multi_species.npz")
+    c = 1e9
+    spectra, sigmas = post.synthetic_measurement(np.repeat(z["theta"][:1], 400, axis=0), c, np.random.default_rng(1))
+    fm = z["c0_spectra"][0]
+    np.testing.assert_allclose(sigmas[0][0], np.sqrt((1e2 * c) ** 2 + c * fm), rtol=2e-5)
+    assert spectra[0].shape == (400, len(fm)) and (spectra[0] >= c).all()
+    resid = (spectra[0] - fm) / sigmas[0]
+    assert abs(resid.mean()) < 0.01 and abs(resid.std() - 1.0) < 0.01  # 400 x 1024 standard-normal draws
+    again, _ = post.synthetic_measurement(np.repeat(z["theta"][:1], 400, axis=0), c, np.random.default_rng(1))
+    np.testing.assert_array_equal(again[0], spectra[0])
