@@ -446,7 +446,9 @@ def run_workload(env, name, batch, steps, warmup, sync_gather=False, scaling="we
                                                    "NCCL on the compute stream"),
                                "options": post.model.options},
             "clocks": env.sampler.window(t_wall0, t_wall1) if env.sampler else None, "e2e": e2e,
-            "gpu_launches": launches * steps, "stage_ms": per_call, "status_ok_fraction": float((status == 0).mean())}
+            "gpu_launches": launches * steps, "stage_ms": per_call, "status_ok_fraction": float((status == 0).mean()),
+            "step_ms": {"median": float(np.median(step_ms)), "min": float(step_ms.min()), "max": float(step_ms.max()),
+                        "gather_tail_ms": float(tail0.elapsed_time(tail1))}}
     if parity and parity[0] > 0:
         line["parity"] = parity_check(name, post, thetas_host[warmup], logp_dev, status_dev, parity[0], parity[1], usable_cores())
     if with_roofline:
