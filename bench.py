@@ -253,13 +253,14 @@ def build_roofline(name, post, batch, per_call, step_ms_mean, peaks, measured):
             k["counters"] = c
             rates = {"fp32": (c.get("fp32_flop_per_eval", 0.0) * batch / sec, fp32_peak),
                      "mufu": (c.get("mufu_per_eval", 0.0) * batch / sec, mufu_peak),
+                     "xu": (c.get("xu_ops_per_eval", 0.0) * batch / sec, mufu_peak),  # all XU-pipe instructions
                      "fp64": (c.get("fp64_flop_per_eval", 0.0) * batch / sec, fp64_peak),
                      "tensor": (c.get("tensor_flop_per_eval", 0.0) * batch / sec, tf32_peak)}
             k["pipes"] = {p: {"achieved": a, "peak": pk, "frac": a / pk} for p, (a, pk) in rates.items() if a > 0}
             if k["pipes"]:
                 bound = max(k["pipes"], key=lambda p: k["pipes"][p]["frac"])
                 k.update(bound=bound, achieved=k["pipes"][bound]["achieved"], peak=k["pipes"][bound]["peak"],
-                         frac=k["pipes"][bound]["frac"], unit="op/s" if bound == "mufu" else "flop/s")
+                         frac=k["pipes"][bound]["frac"], unit="op/s" if bound in ("mufu", "xu") else "flop/s")
             if c.get("dram_bytes_per_launch") is not None:
                 k["traffic"] = c["dram_bytes_per_launch"] * batch / max(c.get("thetas_per_launch", batch), 1)
         kernels[stage] = k
@@ -273,7 +274,7 @@ def build_roofline(name, post, batch, per_call, step_ms_mean, peaks, measured):
         hbm_bytes += batch * sum(len(c.x_data_fm) * 8.0 + (len(c.x_data) if post.model.folded_contraction[i][0] else
                                                            len(c.x_data_fm)) * 8.0 for i, c in enumerate(post.chords))
     roof = {"kernel": KERNEL_OF_STAGE.get(dom, dom), "stage": dom,
-            "bound": {"fp32": "fp32", "mufu": "mufu", "fp64": "fp64", "tensor": "tensor"}.get(d.get("bound"), None),
+            "bound": {"fp32": "fp32", "mufu": "mufu", "xu": "xu", "fp64": "fp64", "tensor": "tensor"}.get(d.get("bound"), None),
             "achieved": d.get("achieved"), "peak": d.get("peak"), "unit": d.get("unit"), "frac": d.get("frac"),
             "traffic": d.get("traffic"), "traffic_unit": "DRAM bytes read + written per launch (ncu --set full capture)",
             "counters_source": src,

@@ -7,6 +7,8 @@ For each captured kernel the SASS source page gives the predicated-on THREAD ins
 script sums them by class (no hand-written flop model):
     fp32 flop  = 2 FFMA + FMUL + FADD + 2 (2 FFMA2 + FMUL2 + FADD2)      (packed .f32x2 forms carry two lanes)
     mufu ops   = MUFU                                                     (ex2, lg2, rcp, rsq, sqrt, sin, cos)
+    xu ops     = sm__inst_executed_pipe_xu (busy fraction x cycles x 16 lanes/clk x SMs): MUFU plus the conversions
+                 that execute on the same pipe
     fp64 flop  = 2 DFMA + DMUL + DADD
     tensor flop = UTCHMMA x 2 x 128 x N x 8                               (kind::tf32, M = 128, K = 8 per instruction)
 and the raw page gives dram bytes, duration and the pipe utilisations.  bench.py divides by the thetas of the captured
@@ -28,7 +30,9 @@ RAW = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"
        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size",
-       "launch__block_size", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+       "launch__block_size", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg",
+       "sm__inst_executed_pipe_xu.sum.pct_of_peak_sustained_elapsed"]
+XU_LANES_PER_CLK_SM = 16  # one warp instruction per two cycles and SM: the rate the in-run MUFU micro-benchmark measures
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
 
@@ -50,6 +54,7 @@ def main():
     ap.add_argument("--batch", type=int, required=True, help="thetas of the captured launches")
     ap.add_argument("--out", required=True)
     ap.add_argument("--command", default="")
+    ap.add_argument("--sms", type=int, default=148, help="SMs of the GPU the capture ran on")
     args = ap.parse_args()
 
     raw = list(csv.reader(io.StringIO(ncu("-i", args.report, "--page", "raw", "--csv"))))
@@ -105,6 +110,11 @@ def main():
                                                   "DADD", "UTCHMMA") if ops[op]}
         k["fp32_flop_per_eval"] = (2 * ops["FFMA"] + ops["FMUL"] + ops["FADD"] + 2 * (2 * ops["FFMA2"] + ops["FMUL2"] + ops["FADD2"])) / n
         k["mufu_per_eval"] = ops["MUFU"] / n
+        # every instruction of the XU pipe (MUFU and the int <-> float conversions that share it): the pipe's busy
+        # fraction over the launch x its peak rate x the SMs of the capture (sm__inst_executed_pipe_xu)
+        if "sm__inst_executed_pipe_xu.sum.pct_of_peak_sustained_elapsed" in k and "sm__cycles_elapsed.avg" in k:
+            k["xu_ops_per_eval"] = (k["sm__inst_executed_pipe_xu.sum.pct_of_peak_sustained_elapsed"] / 100.0 *
+                                    k["sm__cycles_elapsed.avg"] * XU_LANES_PER_CLK_SM * args.sms) / n
         k["fp64_flop_per_eval"] = (2 * ops["DFMA"] + ops["DMUL"] + ops["DADD"]) / n
         k["tensor_flop_per_eval"] = warp_ops["UTCHMMA"] * 2.0 * 128 * tn * 8 / n
         k["warp_inst_per_eval"] = sum(warp_ops.values()) / n
