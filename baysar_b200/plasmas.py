@@ -137,7 +137,17 @@ class PlasmaLine:
         if self.zeeman:
             raise NotImplementedError("zeeman=True is outside the B200 hot path (north_star: Zeeman-free profiles)")
         if len(self.hydrogen_species) > 1:
-            raise NotImplementedError("one hydrogen-isotope species per posterior is supported")
+            # The reference cannot evaluate a second hydrogen isotope either, and its constructor already runs one evaluation
+            # (posterior.py:197-217): with no_sample_neutrals the isotope has no `<species>_dens` entry and total_power
+            # raises KeyError (plasmas.py:1184-1185); with sampled neutrals only the first isotope gets a neutral profile
+            # (plasmas.py:678-686), the second stays a one-element array and BalmerHydrogenLine raises ValueError in
+            # dot(weights, n0_profile) (linemodels.py:817).  Same exception types here, at construction.
+            second = self.hydrogen_species[1]
+            if self.no_sample_neutrals:
+                raise KeyError(second + "_dens")
+            n_los = len(profile_function.electron_density.x) if profile_function is not None else 50
+            raise ValueError(f"shapes ({n_los},) and (1,) not aligned: only the first hydrogen isotope has a neutral "
+                             "density profile")
         self.concstar = True  # plasmas.py:948-950; the non-concstar TEC path raises in the reference too
 
         self.impurities = []
