@@ -277,6 +277,13 @@ def multi_species_host_priors(mesh=False):
                     profile=wl.profile, extra_priors=MESH_HOST_PRIORS if mesh else HOST_PRIORS)
 
 
+def multi_species_bolometry():
+    """The multi-species chord with BolometryPrior (priors.py:595-643), which reads the radiated-power side outputs."""
+    wl = multi_species(1)
+    return Workload("multi_bolometry", wl.input_kwargs, wl.los, wl.reference_theta, wl.description + ", BolometryPrior",
+                    extra_priors=[("BolometryPrior", dict(plasma="@plasma", mean=1500.0, sigma=400.0))])
+
+
 def multi_species_mesh(curvature=None):
     """The multi-species chord on the MeshPlasma profile family (reference lineshapes.py:235-329): 10^theta at 7
     knots, linear interpolation onto arange(-10, 25, 0.1) (L = 350); optional CurvatureCost (priors.py:104-127)."""

@@ -7,9 +7,10 @@ theta's state has been published (`BaysarPosterior._add_host_priors`).  The prio
 line-of-sight point are rows of the device prior table instead (`baysar_b200/priors.py`).
 
 Same class names, constructor signatures and values as the reference (fixtures `multi_host_priors`,
-`multi_mesh_host_priors` are written by the reference itself).  Not built: ``NeutralPowerPrior`` / ``BolometryPrior``
-(they read the radiated-power side outputs the device path skips) and ``FastStarkPrior`` (its constructor
-runs an MCMC fit with inference-tools).
+`multi_mesh_host_priors`, `multi_bolometry` are written by the reference itself).  ``BolometryPrior`` reads the
+radiated-power side outputs, which `baysar_b200/side_outputs.py` evaluates on the host from the published
+state; ``NeutralPowerPrior`` raises KeyError on every call, as in the reference.  Not built: ``FastStarkPrior`` (its
+constructor runs an MCMC fit with inference-tools).
 """
 import numpy as np
 
@@ -159,6 +160,51 @@ class GaussianProcessPrior:
         return -0.5 * field.T.dot(self.iK.dot(field))
 
 
+class BolometryPrior:
+    """priors.py:595-643: the line-integrated radiated power (hydrogen excitation and recombination, and for every
+    impurity element the charge-state-extrapolated power of its reference species) is normal about `mean`.  Reads the
+    radiated-power side outputs, evaluated on the host from the published state (`baysar_b200/side_outputs.py`)."""
+
+    def __init__(self, plasma, mean=10, sigma=0.5):
+        self.plasma, self.mean, self.sigma = plasma, mean, sigma
+        self.reference_species = []
+        for elem in plasma.impurities:  # the <elem>_2 species if sampled, else the element's last species
+            own = [s for s in plasma.impurity_species if s.startswith(f"{elem}_")]
+            self.reference_species.append(elem + "_2" if elem + "_2" in plasma.impurity_species else own[-1])
+
+    def syntetic_bolometer(self):
+        trapz = getattr(np, "trapezoid", None) or np.trapz
+        pl, estimate = self.plasma, []
+        if pl.contains_hydrogen:
+            power = pl.radiated_power.neutral_power()
+            for species in pl.hydrogen_species:
+                for reaction in ("exc", "rec"):
+                    estimate.append(trapz(power[species + f"_{reaction}"], pl.los).sum())
+        self.power_profiles = {}
+        for species in self.reference_species:
+            profile = pl.extrapolate_impurity_power(species)
+            self.power_profiles[species.split("_")[0]] = profile.copy()
+            estimate.append(trapz(profile, pl.los).sum())
+        return np.array(estimate)
+
+    def __call__(self):
+        self.synthetic_measurement = self.syntetic_bolometer().sum()
+        return -0.5 * np.square((self.synthetic_measurement - self.mean) / self.sigma)
+
+
+class NeutralPowerPrior:
+    """priors.py:576-588.  The reference reads plasma_state["power"]["D_ADAS_0_exc"], a key nothing writes (total_power
+    stores "<species>_exc", plasmas.py:1187): every call raises KeyError, and so does this one."""
+
+    def __init__(self, plasma, mean=1.0, sigma=0.5):
+        self.plasma, self.mean, self.sigma = plasma, mean, sigma
+
+    def __call__(self):
+        power = self.plasma.radiated_power.neutral_power()
+        self.exc_power = (getattr(np, "trapezoid", None) or np.trapz)(power["D_ADAS_0_exc"], self.plasma.los)
+        return gaussian_low_pass_cost(self.exc_power, self.mean, self.sigma)
+
+
 def _needs_side_outputs(name, why):
     def ctor(*args, **kwargs):
         raise NotImplementedError(f"{name}: {why}")
@@ -166,8 +212,4 @@ def _needs_side_outputs(name, why):
     return ctor
 
 
-NeutralPowerPrior = _needs_side_outputs("NeutralPowerPrior", "reads the radiated-power side outputs (plasma_state['power']) "
-                                        "that the device path skips (SURVEY 8a P12)")
-BolometryPrior = _needs_side_outputs("BolometryPrior", "reads the radiated-power side outputs (plasma_state['power'], "
-                                     "extrapolate_impurity_power) that the device path skips (SURVEY 8a P12)")
 FastStarkPrior = _needs_side_outputs("FastStarkPrior", "its constructor runs an MCMC fit (inference-tools), outside the posterior path")

@@ -334,6 +334,20 @@ class PlasmaLine:
     def __call__(self, theta):
         self.update_plasma_state(theta)
 
+    # ------------------------------------------------------------------------------------------ side outputs (P12)
+    @property
+    def radiated_power(self):
+        """Host-side radiated-power side outputs (`baysar_b200/side_outputs.py`), built on first use."""
+        if self.__dict__.get("_radiated_power") is None:
+            from .side_outputs import RadiatedPower
+
+            self._radiated_power = RadiatedPower(self)
+        return self._radiated_power
+
+    def extrapolate_impurity_power(self, species="N_2", proton_number=None):
+        """Per-charge-state radiated power of an element along the line of sight (reference plasmas.py:1137-1172)."""
+        return self.radiated_power.extrapolate_impurity_power(species, proton_number)
+
     def update_plasma_state(self, theta, out=None):
         """Evaluate the line-of-sight stage on the GPU for one theta (or take its result ``out`` from a batched
         evaluation) and publish it in ``plasma_state``."""

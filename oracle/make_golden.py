@@ -106,6 +106,7 @@ def main():
         *[("multi_" + f, configs.multi_species_family(f), 8, 0, {}) for f in configs.CLOSED_FORM_FAMILIES],
         ("multi_esym_gaussian", configs.multi_species_family("esymmetric", ptype="gaussian"), 8, 0, {}),
         ("multi_host_priors", configs.multi_species_host_priors(), 8, 0, {}),
+        ("multi_bolometry", configs.multi_species_bolometry(), 6, 0, {}),
         ("multi_mesh_host_priors", configs.multi_species_host_priors(mesh=True), 8, 0, {}),
         ("file_adas_multi", configs.multi_species_file_adas(GOLDEN / "adf"), 8, 0, {}),
     ]

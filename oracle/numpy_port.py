@@ -394,6 +394,27 @@ class OraclePosterior:
                     bal[half * len(self.tau_exc) + t_counter] = ion
             self.impurity_ion_bal[elem] = bal
 
+    def _radiated_power_splines(self):
+        """plasmas.py:997-1020, :1052-1075, :1083-1096: log radiated-power coefficient splines per (ion, tau).  The
+        reference's second (tau_rec) loop re-writes power[t_counter] of the first half, so the rec slices stay zero."""
+        if getattr(self, "_rad_splines", None) is None:
+            big_ne = np.array([self.adas_ne for _ in self.adas_te]).T
+            out = {}
+            for elem in self.impurities:
+                bal = self.impurity_ion_bal[elem]
+                n_pow = ATOMIC_NUMBER[elem]
+                power = np.zeros((len(self.magical_tau), len(self.adas_ne), len(self.adas_te), n_pow))
+                for t in range(len(self.tau_exc)):
+                    for ion in range(n_pow):
+                        plt = self.provider.adf11_rates(elem, "plt", ion + 1, self.adas_te, self.adas_ne)
+                        prb = self.provider.adf11_rates(elem, "prb", ion + 1, self.adas_te, self.adas_ne)
+                        power[t, :, :, ion] = (bal[t, :, :, ion] * plt.T + bal[t, :, :, ion + 1] * prb.T) * big_ne
+                for ion in range(n_pow):
+                    out[f"{elem}_{ion}"] = {tau: RectBivariateSpline(self.adas_ne, self.adas_te, np.log(power[t, :, :, ion].clip(1e-30)))
+                                            for t, tau in enumerate(self.magical_tau)}
+            self._rad_splines = out
+        return self._rad_splines
+
     def _build_tecs(self):
         """plasmas.py:1207-1266 — 30 bicubic splines of log(ne*TEC) per transition."""
         self.impurity_tecs = {}
@@ -1039,6 +1060,31 @@ class OraclePosterior:
             order = sorted(found.values(), key=lambda rec: -int(rec[0].split("_")[1]))
             ems_te = [line_scalars[c][k]["ems_te"] for _, c, k in order]
             return high_pass(ems_te[0] - ems_te[1], args.get("mean", 2.0), args.get("sigma", 0.2))
+        if name == "BolometryPrior":  # priors.py:595-643 on the side outputs of plasmas.py:997-1020, :1083-1096, :1137-1192
+            trapz_ = trapz
+            total = []
+            if self.contains_hydrogen:
+                n1 = st["main_ion_density"]
+                for sp in self.hydrogen_species:  # (exc, rec) per species; only the first species has a "_rec" entry
+                    total.append(trapz_(ne * st[sp + "_dens"] * st["adf11"]["plt"], self.los).sum())
+                    total.append(trapz_(ne * n1 * st["adf11"]["prb"], self.los).sum())
+            splines = self._radiated_power_splines()
+            for elem in self.impurities:
+                own = [s_ for s_ in self.impurity_species if s_.startswith(f"{elem}_")]
+                ref = elem + "_2" if elem + "_2" in self.impurity_species else own[-1]
+                tau = np.log10(st[ref + "_tau"])
+                upper = self.magical_tau.searchsorted(tau)
+                upper_tau, lower_tau = self.magical_tau[upper][0], self.magical_tau[upper - 1][0]
+                upper_weight = (tau - lower_tau) / (upper_tau - lower_tau)
+                lower_weight = 1 - upper_weight
+                power = []
+                for charge in range(ATOMIC_NUMBER[elem]):
+                    sp_ = splines[f"{elem}_{charge}"]
+                    rates = upper_weight * np.exp(sp_[upper_tau].ev(ne, te)) + lower_weight * np.exp(sp_[lower_tau].ev(ne, te))
+                    power.append(st[ref + "_dens"] * rates)
+                total.append(trapz_(np.array(power), self.los).sum())
+            res = (np.array(total).sum() - args.get("mean", 10)) / args.get("sigma", 0.5)
+            return -0.5 * np.square(res)
         if name == "GaussianProcessPrior":  # priors.py:1129-1176
             x = fns["electron_density"].x_points
             cov = (args["A"] ** 2) * np.exp(-0.5 * np.subtract.outer(x, x) ** 2 / args["L"] ** 2)

@@ -554,3 +554,15 @@ def test_synthetic_measurement_noise_model(posteriors):
     assert abs(resid.mean()) < 0.01 and abs(resid.std() - 1.0) < 0.01  # 400 x 1024 standard-normal draws
     again, _ = post.synthetic_measurement(np.repeat(z["theta"][:1], 400, axis=0), c, np.random.default_rng(1))
     np.testing.assert_array_equal(again[0], spectra[0])
+
+
+def test_neutral_power_prior_raises_key_error_like_the_reference(posteriors):
+    """priors.py:576-588 reads plasma_state["power"]["D_ADAS_0_exc"], a key total_power never writes (plasmas.py:1187
+    stores "<species>_exc"): the reference raises KeyError on every call, and so does the mirror."""
+    from baysar_b200.priors import NeutralPowerPrior
+
+    post, _ = posteriors("multi_species")
+    z = np.load(GOLDEN / "multi_species.npz")
+    post(z["theta"][0])
+    with pytest.raises(KeyError):
+        NeutralPowerPrior(post.plasma)()

@@ -26,6 +26,7 @@ WORKLOADS = {
     **{"multi_" + f: (lambda f=f: configs.multi_species_family(f)) for f in configs.CLOSED_FORM_FAMILIES},
     "multi_esym_gaussian": lambda: configs.multi_species_family("esymmetric", ptype="gaussian"),
     "multi_host_priors": lambda: configs.multi_species_host_priors(),
+    "multi_bolometry": lambda: configs.multi_species_bolometry(),
     "multi_mesh_host_priors": lambda: configs.multi_species_host_priors(mesh=True),
     "file_adas_multi": lambda: configs.multi_species_file_adas(ADF_DIR),
     "multi_recombining": lambda: configs.multi_species_switched(recombining=True),
