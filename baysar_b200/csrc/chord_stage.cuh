@@ -96,6 +96,7 @@ struct alignas(16) GaussComp {
 #define BAYSAR_WIN_MIN 48        // line centre point by point; the two tails beyond are integrated in closed form
 #define BAYSAR_TAIL_TERMS 4      // terms of the tail series in g / |x|^2.5 (<= 1e-2.5 beyond 10 gamma: truncation < 1e-10)
 #define BAYSAR_FAR_RATIO 500.f  // sweep 2: series in g / |d|^2.5 beyond this ratio (third-order term < 1e-8)
+#define BAYSAR_FAR_SIGMAS 40.0  // multi-tap lines: the convolution is a moment series beyond this many Doppler widths
 #ifndef BAYSAR_FUSED_GPT
 #define BAYSAR_FUSED_GPT 4      // sweep 2: groups of four consecutive points a thread keeps in registers per chunk
 #endif
@@ -770,6 +771,10 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
         if (++nf == BAYSAR_MAX_FUSED_LINES) flush_fused(false);
         continue;
       }
+      if constexpr (!FUSED3) {  // this build serves chords whose Balmer lines are guaranteed single taps (CH_B_OPTIONAL):
+        st |= 1u << 16;         // the multi-tap path is compiled out of it
+        continue;
+      } else {
       const double* cld = m.cl_d + (ch[CH_LINE_OFF] + k) * CL_D_COUNT;
       const double* rec = lines_n + cl[CL_ULINE] * BAYSAR_LINE_STRIDE;
       const double cwl0 = cld[CL_CWL0];
@@ -819,6 +824,30 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
         double run = incl - s;
         for (int q = b; q < e; ++q) { tappre[q] = run; run += tapd[q]; }
         if (lane == 31) tappre[T] = incl;
+        // moments of the taps about the output point, mu_n = sum_u g_u (u delta)^n / sum_u g_u (u = kk - o), and from
+        // them the coefficients of the far-field polynomials P_p(y) = sum_n mu_n (p)_n / n! y^n (see the far pass below)
+        double mo[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int q = lane; q < T; q += 32) {
+          const double xu = (double)(k_lo + q - o) * delta;
+          double w = tapd[q];
+#pragma unroll
+          for (int n_ = 0; n_ < 6; ++n_) { w *= xu; mo[n_] += w; }
+        }
+#pragma unroll
+        for (int n_ = 0; n_ < 6; ++n_) mo[n_] = warp_sum(mo[n_]);
+        const double ig = 1.0 / __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) {
+          float* fco = reinterpret_cast<float*>(scratch + 136);
+          const double r25[6] = {2.5, 4.375, 6.5625, 9.0234375, 11.73046875, 14.6630859375};  // (2.5)_n / n!
+          const double r50[4] = {5.0, 15.0, 35.0, 70.0};                                       // (5)_n / n!
+          const double r75[2] = {7.5, 31.875};                                                 // (7.5)_n / n!
+#pragma unroll
+          for (int n_ = 0; n_ < 6; ++n_) fco[n_] = (float)(mo[n_] * ig * r25[n_]);
+#pragma unroll
+          for (int n_ = 0; n_ < 4; ++n_) fco[6 + n_] = (float)(mo[n_] * ig * r50[n_]);
+#pragma unroll
+          for (int n_ = 0; n_ < 2; ++n_) fco[10 + n_] = (float)(mo[n_] * ig * r75[n_]);
+        }
       }
       __syncthreads();
       const double g_full = tappre[T];
@@ -862,30 +891,119 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
       const double s_rec = rec[0] / (dl * red[0]) / cal, s_exc = rec[1] / (dl * red[1]) / cal;
       if (!(s_rec - s_rec == 0.0) || !(s_exc - s_exc == 0.0)) st |= 1u << 6;
       const float fr = (float)s_rec, fe = (float)s_exc;
-      // pass 2: m = s_rec u_rec + s_exc u_exc = (s_rec den_exc + s_exc den_rec) * inv  (in place over the stash)
-      for (int j = tid; j < F; j += NT) {
-        float a25 = B_AT(j);
-        float dr = a25 + g25_rec, de = a25 + g25_exc;
-        B_AT(j) = fmaf(fr, de, fe * dr) * rcp_approx(dr * de);
+      // Where the convolution is taken explicitly.  Far from the line centre the Stark pair is smooth on the scale of
+      // the Doppler taps, and sum_u g_u m(x - u delta) = sum_n (-1)^n G_n m^(n)(x) / n! with the raw tap moments G_n;
+      // for the far-field series m = c0 |d|^-2.5 - c1 |d|^-5 + c2 |d|^-7.5 every derivative is again a power of |d|, so
+      //   (m (*) g)(x) = G_0 ia (c0 P_2.5(y) - ia (c1 P_5(y) - ia c2 P_7.5(y))),  ia = |d|^-2.5,  y = 1 / d,
+      //   P_p(y) = sum_n mu_n (p)_n / n! y^n  (n <= 6, 4, 2),
+      // one rsqrt and ~20 FMAs per point instead of two passes and T taps (relative error < 1e-8 beyond
+      // BAYSAR_FAR_SIGMAS Doppler widths and the far ratio of the series; tests/test_kernel_model.py).  Explicit stay a
+      // window around the centre and the two end zones where the taps leave the grid (the reference's "same"
+      // convolution pads with zeros); when they would cover most of the grid anyway the whole grid is explicit.
+      const int u_min = k_lo - o, u_max = k_hi - 1 - o;  // tap offsets: out[j] = sum_u g_u m[j - u]
+      const int ext = (u_max > -u_min ? u_max : -u_min) + 8;
+      int sa[3], sb[3];  // explicit segments [sa, sb] (empty: sb < sa), ascending, block-uniform
+      bool far_on = false;
+      {
+        const float gmx = g25_rec > g25_exc ? g25_rec : g25_exc;
+        const float wsig = (float)BAYSAR_FAR_SIGMAS * (float)sigma, wrat = __powf(BAYSAR_FAR_RATIO * gmx, 0.4f) * 1.001f;
+        float wf = ceilf((wsig > wrat ? wsig : wrat) / (float)delta) + 2.f;
+        wf = wf < (float)F ? wf : (float)F;  // NaN -> F: everything explicit
+        const int Wp = wf == wf ? (int)wf : F;
+        int a0 = 0, b0 = u_max - 1;                                         // left end zone
+        int a1 = jc - Wp < 0 ? 0 : jc - Wp, b1 = jc + Wp > F - 1 ? F - 1 : jc + Wp;  // window (empty if off the grid)
+        int a2 = F + u_min, b2 = F - 1;                                     // right end zone
+        if (b0 > F - 1) b0 = F - 1;
+        if (a2 < 0) a2 = 0;
+        // whole blocks of eight outputs: the convolution's blocks tile a segment exactly and no 128-bit group of the far
+        // pass straddles a boundary, so the two passes touch disjoint elements of the spectrum and need no barrier
+        b0 |= 7; a1 &= ~7; b1 |= 7; a2 &= ~7; b2 |= 7;
+        // merge neighbours whose pass-2 ranges (segment +- ext) would overlap; an empty segment has sb < sa
+        // (scalars and fully unrolled loops only: a dynamically indexed array would live in local memory)
+        if (b1 >= a1 && b0 >= a0 && a1 <= b0 + 2 * ext + 1) { b0 = b1 > b0 ? b1 : b0; b1 = a1 - 1; }
+        if (b2 >= a2) {
+          if (b1 >= a1) { if (a2 <= b1 + 2 * ext + 1) { b1 = b2 > b1 ? b2 : b1; b2 = a2 - 1; } }
+          else if (b0 >= a0 && a2 <= b0 + 2 * ext + 1) { b0 = b2 > b0 ? b2 : b0; b2 = a2 - 1; }
+        }
+        sa[0] = a0; sb[0] = b0; sa[1] = a1; sb[1] = b1; sa[2] = a2; sb[2] = b2;
+        int covered = 0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) covered += sb[q] >= sa[q] ? sb[q] - sa[q] + 1 + 2 * ext : 0;
+        far_on = T >= 12 && covered < (F * 3) / 5;
+        if (!far_on) { sa[0] = 0; sb[0] = F - 1; sb[1] = sa[1] - 1; sb[2] = sa[2] - 1; }
+      }
+      // pass 2: m = s_rec u_rec + s_exc u_exc = (s_rec den_exc + s_exc den_rec) * inv  (in place over the stash), on the
+      // explicit segments and the tap reach around them
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        if (sb[q] < sa[q]) continue;
+        const int lo = sa[q] - ext < 0 ? 0 : sa[q] - ext, hi = sb[q] + ext > F - 1 ? F - 1 : sb[q] + ext;
+        for (int j = lo + tid; j <= hi; j += NT) {
+          float a25 = B_AT(j);
+          float dr = a25 + g25_rec, de = a25 + g25_exc;
+          B_AT(j) = fmaf(fr, de, fe * dr) * rcp_approx(dr * de);
+        }
       }
       __syncthreads();
-      // A += m (*) g
-      for (int j0 = 8 * tid; j0 < F; j0 += 8 * NT) {
-        float acc[8];
-        conv8(bufB, HALO + j0 + q_start, tapq, nq, acc);
-        float4* dst = reinterpret_cast<float4*>(bufA + pad_index(HALO + j0));
-        float4 v = dst[0];
-        v.x += acc[0]; v.y += acc[1]; v.z += acc[2]; v.w += acc[3];
-        dst[0] = v;
-        dst = reinterpret_cast<float4*>(bufA + pad_index(HALO + j0 + 4));
-        v = dst[0];
-        v.x += acc[4]; v.y += acc[5]; v.z += acc[6]; v.w += acc[7];
-        dst[0] = v;
+      // A += m (*) g on the explicit segments
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        if (sb[q] < sa[q]) continue;
+        const int ja = sa[q], jb = sb[q] < F - 1 ? sb[q] : F - 1;
+        for (int j0 = ja + 8 * tid; j0 <= jb; j0 += 8 * NT) {
+          float acc[8];
+          conv8(bufB, HALO + j0 + q_start, tapq, nq, acc);
+          float4* dst = reinterpret_cast<float4*>(bufA + pad_index(HALO + j0));
+          float4 v = dst[0];
+          v.x += acc[0]; v.y += acc[1]; v.z += acc[2]; v.w += acc[3];
+          dst[0] = v;
+          dst = reinterpret_cast<float4*>(bufA + pad_index(HALO + j0 + 4));
+          v = dst[0];
+          v.x += acc[4]; v.y += acc[5]; v.z += acc[6]; v.w += acc[7];
+          dst[0] = v;
+        }
       }
-      __syncthreads();
+      if (far_on) {  // (no barrier: disjoint elements, see above)
+        const float* fco = reinterpret_cast<const float*>(scratch + 136);
+        // coefficients in registers (the loop writes shared memory: the compiler would re-read them every point); the
+        // amplitudes and G_0 folded in: value = ia (q1(y) - ia (q2(y) - ia q3(y)))
+        const float gf = (float)g_full;
+        const float c0f = gf * (fr + fe), c1f = gf * fmaf(fr, g25_rec, fe * g25_exc),
+                    c2f = gf * fmaf(fr * g25_rec, g25_rec, fe * g25_exc * g25_exc);
+        const float a0 = c0f, a1 = c0f * fco[0], a2 = c0f * fco[1], a3 = c0f * fco[2], a4 = c0f * fco[3], a5 = c0f * fco[4],
+                    a6 = c0f * fco[5];
+        const float e0 = c1f, e1 = c1f * fco[6], e2 = c1f * fco[7], e3 = c1f * fco[8], e4 = c1f * fco[9];
+        const float h0 = c2f, h1 = c2f * fco[10], h2 = c2f * fco[11];
+        // four consecutive points per thread and trip (128-bit read-modify-write of the spectrum); a group that touches an
+        // explicit segment is handled point by point
+        for (int j0 = 4 * tid; j0 < F; j0 += 4 * NT) {
+          if ((j0 >= sa[0] && j0 <= sb[0]) || (j0 >= sa[1] && j0 <= sb[1]) || (j0 >= sa[2] && j0 <= sb[2])) continue;
+          const bool clear = j0 + 3 < F;
+          float4* ap = reinterpret_cast<float4*>(bufA + pad_index(HALO + j0));
+          float4 v4 = *ap;
+          float v[4] = {v4.x, v4.y, v4.z, v4.w};
+          const float kf0 = (float)(j0 - jc);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int j = j0 + r;
+            if (!clear && j >= F) continue;
+            const float kf2 = kf0 + (float)r;
+            const float dd = fmaf(kf2, d_hi, fmaf(kf2, d_lo, r_f));
+            const float rs = rsqrt_approx(fabsf(dd)), iq = rs * rs;
+            const float y = dd < 0.f ? -iq : iq, ia = iq * iq * rs;
+            const float q1 = fmaf(y, fmaf(y, fmaf(y, fmaf(y, fmaf(y, fmaf(y, a6, a5), a4), a3), a2), a1), a0);
+            const float q2 = fmaf(y, fmaf(y, fmaf(y, fmaf(y, e4, e3), e2), e1), e0);
+            const float q3 = fmaf(y, fmaf(y, h2, h1), h0);
+            v[r] = fmaf(ia, fmaf(-ia, fmaf(-ia, q3, q2), q1), v[r]);
+          }
+          *ap = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+      __syncthreads();  // the convolution's last block may have added to the alignment tail
       for (int j = F + tid; j < f8; j += NT) A_AT(j) = 0.f;  // keep the alignment tail clean
       a_dirty = true;
       __syncthreads();
+      }  // FUSED3 build
     }
   }
   if (nf > 0) flush_fused(true);

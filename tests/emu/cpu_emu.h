@@ -83,6 +83,7 @@ inline T emu_shfl(T v, int src_lane) {
   return out;
 }
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_shfl(v, (int)((threadIdx.x & 31) ^ m)); }
+template <typename T> inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl(v, src & 31); }
 template <typename T> inline T __shfl_down_sync(unsigned, T v, int d) {
   const int lane = (int)(threadIdx.x & 31);
   return emu_shfl(v, lane + d < 32 ? lane + d : lane);
