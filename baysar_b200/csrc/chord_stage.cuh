@@ -308,6 +308,31 @@ BAYSAR_DEV void pixel_likelihood(const ModelDev& m, const int* ch, const double*
   if (tid == 0) components[n * (int64_t)ncomp_cols + c] = -red4[0];
 }
 
+// trapz (unit spacing in the grid index, half weights at the two ends) of 1 / (|x_j|^2.5 + g), x_j = (j - jc) delta + r,
+// over the grid indices [ja, jb] of a tail: both ends on one side of the line centre and beyond ~10 Stark half-widths, where
+// g / |x|^2.5 <= 10^-2.5.  Integral of the four-term series in that ratio plus the first two Euler-Maclaurin end
+// corrections (tests/kernel_model.py: < 2.1e-11 of the whole integral in float64; float32 here, the tails are a few per
+// cent of it).  f_ends (may be null): the integrand at ja and jb.
+BAYSAR_DEV float stark_tail_trapz(int ja, int jb, float jc_f, float r, float g, float d_hi, float d_lo, float df, float* f_ends) {
+  float A[2], f1[2], f3[2];
+  float sgn = 1.f;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const float kf = (float)(e == 0 ? ja : jb) - jc_f;
+    const float xs = fmaf(kf, d_hi, fmaf(kf, d_lo, r));
+    if (e == 0) sgn = xs > 0.f ? 1.f : -1.f;
+    const float x = fabsf(xs), sq = sqrt_approx(x), x25 = x * x * sq;
+    const float ix15 = rcp_approx(x * sq), u = -g * rcp_approx(x25);  // x^-1.5, -g x^-2.5
+    A[e] = -ix15 * (1.f / 1.5f + u * (1.f / 4.f + u * (1.f / 6.5f + u * (1.f / 9.f))));
+    const float D1 = 2.5f * x * sq, D2 = 3.75f * sq, D3 = 1.875f * rcp_approx(sq);
+    const float iD = rcp_approx(x25 + g), iD2 = iD * iD;
+    f1[e] = -D1 * iD2;
+    f3[e] = -D3 * iD2 + 6.f * D1 * D2 * iD2 * iD - 6.f * D1 * D1 * D1 * iD2 * iD2;
+    if (f_ends) f_ends[e] = iD;
+  }
+  return sgn * ((A[1] - A[0]) * (1.f / df) + df * (f1[1] - f1[0]) * (1.f / 12.f) - df * df * df * (f3[1] - f3[0]) * (1.f / 720.f));
+}
+
 // Sweep 2 of the fused narrow-Doppler passes.  Far field, two fine-grid points (packed FP32 pipe, fma.rn.f32x2):
 // v2 += s_r / (a + g_r) + s_e / (a + g_e) as the three-term series ia (c0 - ia (c1 - ia c2)), ia = 1 / a = rsqrt(|d|)^5,
 // a = |d|^2.5 at the grid offsets kf2 from the line centre (one MUFU op per point instead of two).
@@ -518,30 +543,11 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
           for (int w = 0; w < wpl; ++w) integ += scratch[tid * NW + w];
           // the two tails are at most a few per cent of the integral: float32 with approximate reciprocals is ample
           const float g = q == 0 ? L.g_r : L.g_e;
-          const float df = (float)delta, idf = 1.f / df;
           float tails = 0.f;
 #pragma unroll
           for (int side = 0; side < 2; ++side) {
             const int ja = side == 0 ? 0 : L.jR, jb = side == 0 ? L.jL : F - 1;
-            if (jb > ja) {
-              float A[2], f1[2], f3[2];
-              float sgn = 1.f;
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const float kf = (float)(e == 0 ? ja : jb) - L.jc_f;
-                const float xs = fmaf(kf, d_hi, fmaf(kf, d_lo, L.r));
-                if (e == 0) sgn = xs > 0.f ? 1.f : -1.f;
-                const float x = fabsf(xs), sq = sqrt_approx(x), x25 = x * x * sq;
-                const float ix15 = rcp_approx(x * sq), u = -g * rcp_approx(x25);  // x^-1.5, -g x^-2.5
-                A[e] = -ix15 * (1.f / 1.5f + u * (1.f / 4.f + u * (1.f / 6.5f + u * (1.f / 9.f))));
-                const float D1 = 2.5f * x * sq, D2 = 3.75f * sq, D3 = 1.875f * rcp_approx(sq);
-                const float iD = rcp_approx(x25 + g), iD2 = iD * iD;
-                f1[e] = -D1 * iD2;
-                f3[e] = -D3 * iD2 + 6.f * D1 * D2 * iD2 * iD - 6.f * D1 * D1 * D1 * iD2 * iD2;
-              }
-              tails += sgn * ((A[1] - A[0]) * idf + df * (f1[1] - f1[0]) * (1.f / 12.f) -
-                              df * df * df * (f3[1] - f3[0]) * (1.f / 720.f));
-            }
+            if (jb > ja) tails += stark_tail_trapz(ja, jb, L.jc_f, L.r, g, d_hi, d_lo, (float)delta, nullptr);
           }
           integ += (double)tails;
           const double amp = (q == 0 ? L.sum_r : L.sum_e) / (dl * integ) / cal;
@@ -861,36 +867,6 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
       const double c0 = x0 - cwl;
       const int jc = (int)rint(-c0 / delta);
       const float r_f = (float)fma((double)jc, delta, c0);
-      // pass 1: a25 = |d|^2.5 stashed in B;  A_e = sum_i u_e[i] G[i] with u_rec = den_exc * inv, u_exc = den_rec * inv,
-      // inv = 1 / (den_rec * den_exc): one reciprocal serves both profiles
-      float sr = 0.f, se = 0.f;
-      double er = 0.0, ee = 0.0;
-      float kf = (float)(tid - jc);
-      for (int j = tid; j < F; j += NT, kf += NTf) {
-        float d = fabsf(fmaf(kf, d_hi, fmaf(kf, d_lo, r_f)));
-        float a25 = d * d * sqrt_approx(d);
-        B_AT(j) = a25;
-        float dr = a25 + g25_rec, de = a25 + g25_exc;
-        float inv = rcp_approx(dr * de);
-        float ur = de * inv, ue = dr * inv;
-        if (j >= i_lo && j <= i_hi) { sr += ur; se += ue; }
-        else {
-          int kmin = o - j, kmax = F - 1 + o - j;  // taps that reach outputs 0 and F-1
-          int lo = kmin > k_lo ? kmin : k_lo, hi = kmax + 1 < k_hi ? kmax + 1 : k_hi;
-          double G = 0.0;
-          if (hi > lo) {
-            G = tappre[hi - k_lo] - tappre[lo - k_lo];
-            if (kmin >= lo && kmin < hi) G -= 0.5 * tapd[kmin - k_lo];
-            if (kmax >= lo && kmax < hi) G -= 0.5 * tapd[kmax - k_lo];
-          }
-          er += (double)ur * G; ee += (double)ue * G;
-        }
-      }
-      double red[2] = {(double)sr * g_full + er, (double)se * g_full + ee};
-      block_sum<NT, 2>(red, scratch);
-      const double s_rec = rec[0] / (dl * red[0]) / cal, s_exc = rec[1] / (dl * red[1]) / cal;
-      if (!(s_rec - s_rec == 0.0) || !(s_exc - s_exc == 0.0)) st |= 1u << 6;
-      const float fr = (float)s_rec, fe = (float)s_exc;
       // Where the convolution is taken explicitly.  Far from the line centre the Stark pair is smooth on the scale of
       // the Doppler taps, and sum_u g_u m(x - u delta) = sum_n (-1)^n G_n m^(n)(x) / n! with the raw tap moments G_n;
       // for the far-field series m = c0 |d|^-2.5 - c1 |d|^-5 + c2 |d|^-7.5 every derivative is again a power of |d|, so
@@ -910,9 +886,11 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
         float wf = ceilf((wsig > wrat ? wsig : wrat) / (float)delta) + 2.f;
         wf = wf < (float)F ? wf : (float)F;  // NaN -> F: everything explicit
         const int Wp = wf == wf ? (int)wf : F;
-        int a0 = 0, b0 = u_max - 1;                                         // left end zone
+        // end zones: outputs whose taps reach beyond the grid, and inputs whose taps do (the weighted zone of pass 1)
+        const int ez = (u_max > -u_min ? u_max : -u_min) + 1;
+        int a0 = 0, b0 = ez;                                                 // left end zone
         int a1 = jc - Wp < 0 ? 0 : jc - Wp, b1 = jc + Wp > F - 1 ? F - 1 : jc + Wp;  // window (empty if off the grid)
-        int a2 = F + u_min, b2 = F - 1;                                     // right end zone
+        int a2 = F - 1 - ez, b2 = F - 1;                                     // right end zone
         if (b0 > F - 1) b0 = F - 1;
         if (a2 < 0) a2 = 0;
         // whole blocks of eight outputs: the convolution's blocks tile a segment exactly and no 128-bit group of the far
@@ -932,6 +910,71 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
         far_on = T >= 12 && covered < (F * 3) / 5;
         if (!far_on) { sa[0] = 0; sb[0] = F - 1; sb[1] = sa[1] - 1; sb[2] = sa[2] - 1; }
       }
+      // pass 1: a25 = |d|^2.5 stashed in B;  A_e = sum_i u_e[i] G[i] with u_rec = den_exc * inv, u_exc = den_rec * inv,
+      // inv = 1 / (den_rec * den_exc): one reciprocal serves both profiles.  Point by point on the explicit segments (the
+      // stash also on the tap reach around them); the far parts in between are interior (weight G_0) and their sums
+      // are closed forms: sum_{j=A}^{B} f = trapz + (f_A + f_B) / 2 with the tail integral of sweep 1.
+      float sr = 0.f, se = 0.f;
+      double er = 0.0, ee = 0.0;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        if (sb[q] < sa[q]) continue;
+        const int lo_ = sa[q] - ext < 0 ? 0 : sa[q] - ext, hi_ = sb[q] + ext > F - 1 ? F - 1 : sb[q] + ext;
+        for (int j = lo_ + tid; j <= hi_; j += NT) {
+          const float kf = (float)(j - jc);
+          float d = fabsf(fmaf(kf, d_hi, fmaf(kf, d_lo, r_f)));
+          float a25 = d * d * sqrt_approx(d);
+          B_AT(j) = a25;
+          if (j < sa[q] || j > sb[q]) continue;  // tap reach only: its sum belongs to a far part
+          float dr = a25 + g25_rec, de = a25 + g25_exc;
+          float inv = rcp_approx(dr * de);
+          float ur = de * inv, ue = dr * inv;
+          if (j >= i_lo && j <= i_hi) { sr += ur; se += ue; }
+          else {
+            int kmin = o - j, kmax = F - 1 + o - j;  // taps that reach outputs 0 and F-1
+            int lo = kmin > k_lo ? kmin : k_lo, hi = kmax + 1 < k_hi ? kmax + 1 : k_hi;
+            double G = 0.0;
+            if (hi > lo) {
+              G = tappre[hi - k_lo] - tappre[lo - k_lo];
+              if (kmin >= lo && kmin < hi) G -= 0.5 * tapd[kmin - k_lo];
+              if (kmax >= lo && kmax < hi) G -= 0.5 * tapd[kmax - k_lo];
+            }
+            er += (double)ur * G; ee += (double)ue * G;
+          }
+        }
+      }
+      if (far_on && tid < 8) {  // far part tid >> 1 (the gaps before, between and after the segments), profile tid & 1
+        int pa = 0, pb = -1, prev = -1, np_ = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool seg = q < 3 && sb[q < 3 ? q : 0] >= sa[q < 3 ? q : 0];
+          if (q < 3 && !seg) continue;
+          const int ga = prev + 1, gb = q < 3 ? sa[q] - 1 : F - 1;
+          if (gb >= ga) { if (np_ == (tid >> 1)) { pa = ga; pb = gb; } ++np_; }
+          if (q < 3) prev = sb[q];
+        }
+        double far_sum = 0.0;
+        if (pb >= pa) {
+          const float g = (tid & 1) ? g25_exc : g25_rec;
+          float fe2[2];
+          const float tz = pb > pa ? stark_tail_trapz(pa, pb, (float)jc, r_f, g, d_hi, d_lo, (float)delta, fe2) : 0.f;
+          if (pb == pa) {
+            const float kf = (float)(pa - jc), d = fabsf(fmaf(kf, d_hi, fmaf(kf, d_lo, r_f)));
+            fe2[0] = fe2[1] = rcp_approx(d * d * sqrt_approx(d) + g);  // a single point: the sum is its value
+          }
+          far_sum = (double)tz + 0.5 * ((double)fe2[0] + (double)fe2[1]);
+        }
+        scratch[150 + tid] = far_sum;
+      }
+      double red[2] = {(double)sr * g_full + er, (double)se * g_full + ee};
+      block_sum<NT, 2>(red, scratch);
+      if (far_on) {
+        red[0] += g_full * (scratch[150] + scratch[152] + scratch[154] + scratch[156]);
+        red[1] += g_full * (scratch[151] + scratch[153] + scratch[155] + scratch[157]);
+      }
+      const double s_rec = rec[0] / (dl * red[0]) / cal, s_exc = rec[1] / (dl * red[1]) / cal;
+      if (!(s_rec - s_rec == 0.0) || !(s_exc - s_exc == 0.0)) st |= 1u << 6;
+      const float fr = (float)s_rec, fe = (float)s_exc;
       // pass 2: m = s_rec u_rec + s_exc u_exc = (s_rec den_exc + s_exc den_rec) * inv  (in place over the stash), on the
       // explicit segments and the tap reach around them
 #pragma unroll
