@@ -187,29 +187,35 @@ int ensure_ifc_workspace(baysar_model* m, int64_t n) {
 }
 
 // Launch the chord kernel with the register budget that matches how many CTAs the shared-memory footprint lets an SM hold
-template <int MODE>
-int launch_chord_kernel(baysar_model* m, const ChordArgs& a, dim3 grid, size_t smem, cudaStream_t stream, bool single_tap_only = false) {
+template <int MODE, int TAPS>
+int launch_chord_kernel_t(baysar_model* m, const ChordArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
   // 128 threads per (theta, chord) on short fine grids: with a few thousand points 256 threads have a dozen points each
   // and the per-thread set-up and the barriers dominate (multi-species chord, 3000 points: 2.84 -> 2.62 ms); long grids
   // keep 256 (Balmer demo, 8000 points: 0.119 vs 0.128 ms).  options.chord_threads overrides.
+  const bool pdl = !m->opt.serial_launches;
   const bool nt128 = m->opt.chord_threads == 128 || (m->opt.chord_threads == 0 && m->I[I_F_MAX] <= 4096);
   if (nt128) {
-    auto kern = single_tap_only ? chord_stage_kernel<128, MODE, 6, false> : chord_stage_kernel<128, MODE, 6>;
-    CUDA_OK(launch_k(!m->opt.serial_launches, kern, grid, dim3(128), smem, stream, m->dev, a));
-    CUDA_OK(cudaGetLastError());
+    CUDA_OK(launch_k(pdl, chord_stage_kernel<128, MODE, 6, TAPS>, grid, dim3(128), smem, stream, m->dev, a));
     return 0;
   }
   constexpr int NT = 256;
   const int cap = m->opt.chord_min_blocks > 0 ? m->opt.chord_min_blocks : 5;
   const int by_smem = (int)((size_t)232448 / (smem + 1024));
   const int minb = by_smem < cap ? by_smem : cap;
-  auto kern = minb >= 5 ? chord_stage_kernel<NT, MODE, 5> : (minb == 4 ? chord_stage_kernel<NT, MODE, 4> : chord_stage_kernel<NT, MODE, 3>);
-  if (single_tap_only)  // every Balmer line of the chord is a guaranteed single Doppler tap: leaner build
-    kern = minb >= 5 ? chord_stage_kernel<NT, MODE, 5, false>
-                     : (minb == 4 ? chord_stage_kernel<NT, MODE, 4, false> : chord_stage_kernel<NT, MODE, 3, false>);
-  CUDA_OK(launch_k(!m->opt.serial_launches, kern, grid, dim3(NT), smem, stream, m->dev, a));
-  CUDA_OK(cudaGetLastError());
+  auto kern = minb >= 5 ? chord_stage_kernel<NT, MODE, 5, TAPS>
+                        : (minb == 4 ? chord_stage_kernel<NT, MODE, 4, TAPS> : chord_stage_kernel<NT, MODE, 3, TAPS>);
+  CUDA_OK(launch_k(pdl, kern, grid, dim3(NT), smem, stream, m->dev, a));
   return 0;
+}
+
+// Launch the chord kernel with the register budget that matches how many CTAs the shared-memory footprint lets an SM
+// hold, in the build that matches what the host guarantees about the chord's Doppler kernels (chord_stage.cuh TAPS)
+template <int MODE>
+int launch_chord_kernel(baysar_model* m, const ChordArgs& a, dim3 grid, size_t smem, cudaStream_t stream, int chord) {
+  const int* ch = m->ch_i + chord * CH_I_COUNT;
+  if (ch[CH_B_OPTIONAL]) return launch_chord_kernel_t<MODE, 0>(m, a, grid, smem, stream);
+  if (ch[CH_NARROW]) return launch_chord_kernel_t<MODE, 1>(m, a, grid, smem, stream);
+  return launch_chord_kernel_t<MODE, 2>(m, a, grid, smem, stream);
 }
 
 // stage tags for the optional event log
@@ -238,14 +244,18 @@ int set_kernel_attributes() {
       allow_max_smem(los_stage_kernel<4, 6>) || allow_max_smem(los_stage_kernel<4, 7>) ||
       allow_max_smem(los_stage_kernel<4, 8>) || allow_max_smem(los_stage_kernel<1>))
     return 1;
-  if (allow_max_smem(chord_stage_kernel<256, 0, 3>) || allow_max_smem(chord_stage_kernel<256, 0, 4>) ||
-      allow_max_smem(chord_stage_kernel<256, 0, 5>) || allow_max_smem(chord_stage_kernel<256, 1, 3>) ||
-      allow_max_smem(chord_stage_kernel<256, 1, 4>) || allow_max_smem(chord_stage_kernel<256, 1, 5>) ||
-      allow_max_smem(chord_stage_kernel<256, 0, 3, false>) || allow_max_smem(chord_stage_kernel<256, 0, 4, false>) ||
-      allow_max_smem(chord_stage_kernel<256, 0, 5, false>) || allow_max_smem(chord_stage_kernel<256, 1, 3, false>) ||
-      allow_max_smem(chord_stage_kernel<256, 1, 4, false>) || allow_max_smem(chord_stage_kernel<256, 1, 5, false>) ||
-      allow_max_smem(chord_stage_kernel<128, 0, 6>) || allow_max_smem(chord_stage_kernel<128, 1, 6>) ||
-      allow_max_smem(chord_stage_kernel<128, 0, 6, false>) || allow_max_smem(chord_stage_kernel<128, 1, 6, false>))
+  if (allow_max_smem(chord_stage_kernel<256, 0, 3, 2>) || allow_max_smem(chord_stage_kernel<256, 0, 4, 2>) ||
+      allow_max_smem(chord_stage_kernel<256, 0, 5, 2>) || allow_max_smem(chord_stage_kernel<256, 1, 3, 2>) ||
+      allow_max_smem(chord_stage_kernel<256, 1, 4, 2>) || allow_max_smem(chord_stage_kernel<256, 1, 5, 2>) ||
+      allow_max_smem(chord_stage_kernel<256, 0, 3, 1>) || allow_max_smem(chord_stage_kernel<256, 0, 4, 1>) ||
+      allow_max_smem(chord_stage_kernel<256, 0, 5, 1>) || allow_max_smem(chord_stage_kernel<256, 1, 3, 1>) ||
+      allow_max_smem(chord_stage_kernel<256, 1, 4, 1>) || allow_max_smem(chord_stage_kernel<256, 1, 5, 1>) ||
+      allow_max_smem(chord_stage_kernel<256, 0, 3, 0>) || allow_max_smem(chord_stage_kernel<256, 0, 4, 0>) ||
+      allow_max_smem(chord_stage_kernel<256, 0, 5, 0>) || allow_max_smem(chord_stage_kernel<256, 1, 3, 0>) ||
+      allow_max_smem(chord_stage_kernel<256, 1, 4, 0>) || allow_max_smem(chord_stage_kernel<256, 1, 5, 0>) ||
+      allow_max_smem(chord_stage_kernel<128, 0, 6, 2>) || allow_max_smem(chord_stage_kernel<128, 1, 6, 2>) ||
+      allow_max_smem(chord_stage_kernel<128, 0, 6, 1>) || allow_max_smem(chord_stage_kernel<128, 1, 6, 1>) ||
+      allow_max_smem(chord_stage_kernel<128, 0, 6, 0>) || allow_max_smem(chord_stage_kernel<128, 1, 6, 0>))
     return 1;
   return allow_max_smem(pixel_fold_kernel<128>) || contraction_kernel_attributes();
 }
@@ -266,7 +276,7 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
       chord_args_set_chord(a, m->I, m->ch_i, m->ch_d, m->cl_i, c);
       a.theta = theta; a.n = n; a.lines = lines; a.components = comps;
       a.spectra = spectra; a.fine_pre = fine_pre; a.fine_post = fine_post; a.status = status;
-      if (launch_chord_kernel<0>(m, a, dim3((unsigned)n, 1), m->chord_smem[c], stream)) return 1;
+      if (launch_chord_kernel<0>(m, a, dim3((unsigned)n, 1), m->chord_smem[c], stream, c)) return 1;
       m->last_launches += 1;
       if (mark(m, ST_CHORD, stream)) return 1;
       continue;
@@ -290,9 +300,7 @@ int launch_chords(baysar_model* m, const double* theta, int64_t n, int chord_beg
       a.keep_padding = (m->spec_pitch_last == a.split_pitch && m->spec_pad_last == a.split_pad && m->spec_f_last == F &&
                         m->spec_rows_last >= rows) ? 1 : 0;
       if (!a.keep_padding) { m->spec_pitch_last = a.split_pitch; m->spec_pad_last = a.split_pad; m->spec_f_last = F; m->spec_rows_last = rows; }
-      if (launch_chord_kernel<1>(m, a, dim3((unsigned)rows, 1), m->chord_smem[c], stream,
-                                 m->ch_i[c * CH_I_COUNT + CH_B_OPTIONAL] != 0))
-        return 1;
+      if (launch_chord_kernel<1>(m, a, dim3((unsigned)rows, 1), m->chord_smem[c], stream, c)) return 1;
       if (mark(m, ST_CHORD, stream)) return 1;
       if (folded) {
         // K2b': instrument function and wavelength map as one tcgen05 contraction; K2c': area identity + likelihood

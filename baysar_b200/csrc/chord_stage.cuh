@@ -358,10 +358,13 @@ BAYSAR_DEV float stark_exact(float kf, float d_hi, float d_lo, float r, float g_
 // MODE 0: fused (spectrum -> instrument convolution on the FP32 pipe -> likelihood, everything in shared memory).
 // MODE 1: spectral stage only: writes the pre-convolution spectrum and the per-theta scalars for the tensor-core
 //         contraction (if_contract.cuh) and the pixel stage (pixel_stage_kernel below).
-// FUSED3 = false compiles the three-tap variant of the fused Balmer passes out (chords whose Balmer lines are all
-// guaranteed single taps, CH_B_OPTIONAL: the extra code costs the 48-register MINB = 5 build spills).
-template <int NT, int MODE, int MINB = 3, bool FUSED3 = true>
+// TAPS: what the host guarantees about the Doppler kernels of the chord's Balmer lines for every theta inside the bounds
+// (model.py): 0 = single taps only (CH_B_OPTIONAL) -- the three-tap variant of the fused passes and the multi-tap path
+// are compiled out; 1 = at most three taps (CH_NARROW, cold neutrals on a fine grid) -- the multi-tap path is compiled
+// out; 2 = anything.  The leaner builds keep the register budgets of the fused sweeps free of spills.
+template <int NT, int MODE, int MINB = 3, int TAPS = 2>
 __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, ChordArgs a) {
+  constexpr bool FUSED3 = TAPS >= 1;
 #ifdef BAYSAR_CPU_EMU
   unsigned char* chord_smem_raw = emu_dynamic_smem();
 #else
@@ -777,8 +780,8 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
         if (++nf == BAYSAR_MAX_FUSED_LINES) flush_fused(false);
         continue;
       }
-      if constexpr (!FUSED3) {  // this build serves chords whose Balmer lines are guaranteed single taps (CH_B_OPTIONAL):
-        st |= 1u << 16;         // the multi-tap path is compiled out of it
+      if constexpr (TAPS < 2) {  // this build serves chords whose Balmer lines are guaranteed narrow (see TAPS above):
+        st |= 1u << 16;           // the multi-tap path is compiled out of it
         continue;
       } else {
       const double* cld = m.cl_d + (ch[CH_LINE_OFF] + k) * CL_D_COUNT;
@@ -1046,7 +1049,7 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
       for (int j = F + tid; j < f8; j += NT) A_AT(j) = 0.f;  // keep the alignment tail clean
       a_dirty = true;
       __syncthreads();
-      }  // FUSED3 build
+      }  // TAPS == 2 build
     }
   }
   if (nf > 0) flush_fused(true);

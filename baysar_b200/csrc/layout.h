@@ -9,7 +9,7 @@
 #define BAYSAR_LAYOUT_H
 
 #define BAYSAR_BLOB_MAGIC 0x4252415359534142LL /* "BAYSYSAB" */
-#define BAYSAR_BLOB_VERSION 12
+#define BAYSAR_BLOB_VERSION 13
 
 enum BaysarSection {
   SEC_I,              /* int64  [I_COUNT]           model-wide integer scalars                         */
@@ -203,6 +203,8 @@ enum BaysarChI {
   CH_TAPS_MAX,   /* capacity of the shared-memory tap buffer */
   CH_B_OPTIONAL, /* 1: no Gaussian components and every Balmer line is a guaranteed single Doppler tap, so the
                     spectral stage of the tensor-core path needs no second fine-grid buffer */
+  CH_NARROW,     /* 1: every Balmer line of the chord has at most three Doppler taps for every theta inside the bounds
+                    (cold neutrals): the chord kernel's multi-tap path is not needed */
   CH_I_COUNT
 };
 enum BaysarChD {

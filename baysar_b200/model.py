@@ -76,6 +76,33 @@ def _single_tap_guaranteed(plasma, chord):
     return True
 
 
+def _narrow_taps_guaranteed(plasma, chord):
+    """True if every Balmer line of the chord has a Doppler kernel of one or three taps for EVERY theta inside the bounds
+    (cold neutrals; the kernel's block-uniform tests of csrc/chord_stage.cuh with a 1e-3 margin on sigma): the chord
+    kernel's multi-tap path can then be compiled out (CH_NARROW)."""
+    if not plasma.cold_neutrals:
+        return False
+    for line in chord.lines:
+        if not isinstance(line, BalmerHydrogenLine):
+            continue
+        taps = np.asarray(line.wavelengths_doppler, dtype=float)
+        KD = len(taps)
+        if KD < 5:
+            return False
+        o = (KD - 1) // 2
+        zc = np.abs(taps[o - 2:o + 3] - line.cwl)
+        tag = line.species + "_velocity"
+        vmax = 1e3 * np.abs(plasma.theta_bounds[plasma.slices[tag].start]).max() if tag in plasma.slices else 0.0
+        cw = line.cwl * np.array([1 - vmax / 299792458.0, 1 + vmax / 299792458.0])
+        sigma = cw * 7.715e-5 * np.sqrt(0.01 / line.atomic_mass) * FWHM_TO_SIGMA
+        lo, hi = 6.9 * sigma.min() * (1 - 1e-3), 6.9 * sigma.max() * (1 + 1e-3)
+        one = zc[2] <= lo and zc[1] > hi and zc[3] > hi
+        three = zc[1] <= lo and zc[2] <= lo and zc[3] <= lo and zc[0] > hi and zc[4] > hi
+        if not (one or three):
+            return False
+    return True
+
+
 def compile_model(plasma, chords, priors, gaussian_likelihood=False):
     """-> (blob bytes, info dict).  ``priors``: the prior descriptors in posterior_components order.
     ``gaussian_likelihood``: the chords return ``likelihood(cauchy=False)`` (reference spectrometers.py:187-188)."""
@@ -327,6 +354,7 @@ def compile_model(plasma, chords, priors, gaussian_likelihood=False):
             line_ulines.append(u)
         info["chord_line_uline"].append(line_ulines)
         row[E_CH_I["CH_B_OPTIONAL"]] = int(_single_tap_guaranteed(plasma, chord))
+        row[E_CH_I["CH_NARROW"]] = int(_narrow_taps_guaranteed(plasma, chord))
         row[E_CH_I["CH_HALO"]] = (half + 4 + 3) // 4 * 4
         row[E_CH_I["CH_TAPS_MAX"]] = taps_needed + 8
 
