@@ -16,9 +16,6 @@ for w in $WHAT; do
     sanitize)
       bash tools/sanitize.sh gpurun_out ;;
     ncu)
-      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_raw.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity --no-extra > gpurun_out/ncu_launch.log 2>&1
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:'los_stage|chord_stage|pix_contract|pixel_fold' --launch-skip 12 -c 4 -o gpurun_out/balmer_full -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity --no-extra > gpurun_out/ncu_full.log 2>&1
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:'los_stage|chord_stage' --launch-skip 6 -c 2 -o gpurun_out/multi_full -f python bench.py --workload multi_species --steps 2 --warmup 3 --no-cpu-baseline --no-parity --no-extra > gpurun_out/ncu_full_multi.log 2>&1
-      ls -la gpurun_out/*.ncu-rep ;;
+      echo 'ncu captures: tools/gpu_evidence.sh (one capture per gpurun call, 64 MiB limit)' ;;
   esac
 done
