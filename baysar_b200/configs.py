@@ -68,7 +68,14 @@ class Workload:
             if spec:  # e.g. ptype="gaussian"
                 return ns.EsymmtricCauchyPlasma(x=np.array(self.los, dtype=float), **spec)
             return ns.EsymmtricCauchyPlasma(x=np.array(self.los, dtype=float)) if self.los is not None else None
-        if family in ("SimplePlasma", "LessSimplePlasma", "SimpleGaussianPlasma", "SlabPlasma", "DoubleSlabPlasma"):
+        if family == "PoissonPlasma" and not hasattr(ns, family):
+            # the reference's Poisson-density SimplePlasma (lineshapes.py:443-453) is shadowed by the second definition:
+            # compose it the way a reference user has to
+            import types
+
+            x = np.array(self.los, dtype=float)
+            return types.SimpleNamespace(x=x, electron_density=ns.Poisson(x), electron_temperature=ns.ExpDecay(x))
+        if family in CLOSED_FORM_FAMILIES:
             return getattr(ns, family)(x=np.array(self.los, dtype=float), **spec)
         if family == "bowman_tee":
             return ns.BowmanTeePlasma(x=np.array(self.los, dtype=float), **spec)
@@ -184,6 +191,7 @@ CLOSED_FORM_FAMILIES = {
     "SimpleGaussianPlasma": (np.linspace(0.0, 30.0, 100), [14.3, 0.9, 12.0], [1.0, 1.1]),
     "SlabPlasma": (np.linspace(0.0, 20.0, 100), [14.3, 1.0], [0.8]),
     "DoubleSlabPlasma": (np.linspace(0.0, 20.0, 100), [14.3, 13.8, 5.0], [0.3, 1.2]),
+    "PoissonPlasma": (np.linspace(0.0, 30.0, 100), [14.3, 1.0], [1.0, -1.3]),
 }
 
 

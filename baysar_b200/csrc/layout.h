@@ -121,6 +121,7 @@ enum BaysarProfD {
 };
 
 /* closed-form profile functions of one coordinate (reference lineshapes.py:483-591, :855-929) */
+/* appended values keep the blob layout: BAYSAR_BLOB_VERSION is unchanged by PF_POISSON */
 enum BaysarProfileFn {
   PF_EXP_DECAY,           /* theta = [log10 a, log10 b]:        max(a (1 + b)^-x, 0.01)                                   */
   PF_DOUBLE_EXP_DECAY,    /* [log10 a, log10 b, x0, log10 f, k]: max(a ((1 + b) exp(f tanh(k (x - x0))))^(x0 - x), 0.01)    */
@@ -129,6 +130,8 @@ enum BaysarProfileFn {
   PF_LEFT_TOP_HAT,        /* [log10 v, edge]:                    v where x < edge + aux (the grid step), 1e10 elsewhere     */
   PF_LEFT_RIGHT_TOP_HAT,  /* [log10 l, log10 r (, centre)]:      l left of the centre, r right of it, 0 on it; the temperature
                              of a DoubleSlabPlasma takes the centre from the density's third parameter                      */
+  PF_POISSON,             /* [log10 a, log10 nu]:                a p / max_LOS(p), p = nu^x e^-nu / Gamma(x + 1) (lineshapes.py:537-550;
+                             the kernel returns p, the profile stage scales it by a / max)                                  */
   PF_COUNT
 };
 

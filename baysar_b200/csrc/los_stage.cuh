@@ -51,6 +51,8 @@ BAYSAR_DEV double profile_fn(int fn, double x, const double* th, const double* p
       return p10[0] + 0.0;
     case PF_LEFT_TOP_HAT:
       return x < th[1] + aux ? p10[0] : 1e10;
+    case PF_POISSON:  // unscaled: nu^x e^-nu / x! (scipy's factorial of a float is Gamma(x + 1), 0 for x < 0)
+      return pow(p10[1], x) * (x < 0.0 ? 0.0 : exp(-p10[1]) / tgamma(x + 1.0));
     default: {  // PF_LEFT_RIGHT_TOP_HAT
       const double c = aux_set == 1.0 ? th[2] : (aux_set == 2.0 ? aux : linked);
       return x < c ? p10[0] : (c < x ? p10[1] : 0.0);
@@ -248,6 +250,24 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) los_stage_kernel(ModelDev m,
       ne_s[l] = v;
       nemax = v > nemax ? v : nemax;
       te_s[l] = profile_fn(te_fn, x, th + te_idx, p10 + te_idx, m.prof_d[PROF_TE_AUX], m.prof_d[PROF_TE_AUX_SET], linked);
+    }
+    if (ne_fn == PF_POISSON || te_fn == PF_POISSON) {
+      // Poisson (lineshapes.py:544-550): peak *= a / peak.max() -- one more pass once the maximum over the line of sight
+      // is known
+      for (int pass = 0; pass < 2; ++pass) {
+        if ((pass == 0 ? ne_fn : te_fn) != PF_POISSON) continue;  // block-uniform
+        double* prof = pass == 0 ? ne_s : te_s;
+        double pmax = -1.7976931348623157e308;
+        for (int l = lane; l < L; l += TS) pmax = prof[l] > pmax ? prof[l] : pmax;
+        pmax = team.max(pmax);
+        const double scale = p10[pass == 0 ? ne_idx : te_idx] / pmax;
+        if (pass == 0) nemax = -1.7976931348623157e308;
+        for (int l = lane; l < L; l += TS) {
+          const double v = prof[l] * scale;
+          prof[l] = v;
+          if (pass == 0) nemax = v > nemax ? v : nemax;
+        }
+      }
     }
   } else {
     // MeshLine (lineshapes.py:282-301): values at the knots (10^theta if log), scipy interp1d "linear" with

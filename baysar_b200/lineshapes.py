@@ -259,6 +259,23 @@ class ADoubleExpDecay(_ClosedForm):
         return (np.power(10.0, a) * np.power(base, x0 - self.x)).clip(0.01)
 
 
+class Poisson(_ClosedForm):
+    """``a p / max(p)``, ``p = nu^x e^-nu / x!`` with ``a, nu = 10^theta`` (lineshapes.py:537-550)."""
+
+    fn = "PF_POISSON"
+
+    def __init__(self, x):
+        super().__init__(x, [[12, 16], [-3, 2]])
+
+    def __call__(self, theta):
+        from scipy.special import factorial
+
+        a, nu = (np.power(10.0, t) for t in theta)
+        peak = np.power(np.zeros(self.x_len) + nu, self.x)
+        peak *= np.exp(-nu) / factorial(self.x)
+        return peak * (a / peak.max())
+
+
 class GaussianPlasma(_ClosedForm):
     """Height-normalised Gaussian ``10^I exp(-0.5 ((x - cwl) / sigma)^2)``, ``sigma`` from ``fwhm = 10^w``, floored at
     0.01; the centre is sampled unless ``cwl`` is given (lineshapes.py:556-591)."""
@@ -341,6 +358,17 @@ class SimplePlasma:
         self.electron_temperature = ExpDecay(self.x)
 
 
+class PoissonPlasma:
+    """The reference's FIRST ``SimplePlasma`` (lineshapes.py:443-453: Poisson density, ExpDecay temperature).  The second
+    definition at :456 shadows it there, so a reference user reaches it only by composing ``Poisson`` and ``ExpDecay`` by
+    hand; here it has its own name."""
+
+    def __init__(self, x=None):
+        self.x = np.linspace(0, 60, 100) if x is None else np.asarray(x, dtype=float)
+        self.electron_density = Poisson(self.x)
+        self.electron_temperature = ExpDecay(self.x)
+
+
 class LessSimplePlasma:
     """lineshapes.py:521-532."""
 
@@ -376,3 +404,44 @@ class DoubleSlabPlasma:
         self.electron_temperature = LeftRightTopHatProfile(self.x, centre, bounds_left=[-1, 0.7], bounds_right=[0, 2.0])
         self.electron_density = LeftRightTopHatProfile(self.x, centre, bounds_left=[13, 15], bounds_right=[13, 14.7],
                                                        alt=self.electron_temperature)
+
+
+class LinearSeparatrix:
+    """``log10(clip(10^Te - grad x, 0.1))`` (lineshapes.py:723-734).  The separatrix profiles return log10 values and carry
+    the parameters of the reference's 2-D wrapper (`PlasmaSimple2D`, plasmas.py:1468), which never hands them to a
+    `PlasmaLine`; they are host callables here as they are there."""
+
+    def __init__(self, x, peak_bounds=(0, 1.7)):
+        self.x = np.asarray(x, dtype=float)
+        self.bounds = [list(peak_bounds), [0.5, 1.5]]
+        self.number_of_variables = len(self.bounds)
+
+    def __call__(self, theta):
+        te, grad = theta
+        return np.log10((np.power(10, te) - grad * self.x).clip(0.1))
+
+
+class CauchySeparatrix:
+    """``log10(10^ne_min + 10^ne / (1 + ((centre - x) / sigma)^2))`` (lineshapes.py:737-757; the reference's
+    ``profile.clip(1e11)`` discards its result, so there is no floor)."""
+
+    def __init__(self, x, peak_bounds=(12.7, 16), centre=None):
+        self.x = np.asarray(x, dtype=float)
+        self.centre = centre
+        self.bounds = [list(peak_bounds), [12.7, 14]] + ([[-5, 5]] if centre is None else []) + [[0.5, 1.5]]
+
+    def __call__(self, theta):
+        if self.centre is None:
+            ne, ne_min, centre, sigma = theta
+        else:
+            (ne, ne_min, sigma), centre = theta, self.centre
+        return np.log10(np.power(10, ne_min) + np.power(10, ne) / (1 + np.square((centre - self.x) / sigma)))
+
+
+class SimpleSeparatrix:
+    """lineshapes.py:760-767."""
+
+    def __init__(self, chords, bounds_ne=(11, 16), bounds_te=(-1, 2)):
+        self.x = np.array(chords)
+        self.electron_density = CauchySeparatrix(self.x, list(bounds_ne))
+        self.electron_temperature = LinearSeparatrix(self.x, list(bounds_te))

@@ -178,6 +178,24 @@ def _gaussian_plasma(x, cwl=None):  # lineshapes.py:556-591 (height-normalised g
     return _pf(x, bounds, fn)
 
 
+def _poisson(x):  # lineshapes.py:537-550
+    from scipy.special import factorial
+
+    def fn(t):
+        a, nu = np.power(10.0, t[0]), np.power(10.0, t[1])
+        peak = np.power(np.zeros(len(x)) + nu, x)
+        peak *= np.exp(-nu) / factorial(x)
+        peak *= a / peak.max()
+        return peak
+    return _pf(x, [[12, 16], [-3, 2]], fn)
+
+
+class PoissonPlasma:  # lineshapes.py:443-453 (the SimplePlasma definition the second one shadows)
+    def __init__(self, x=None):
+        self.x = np.linspace(0, 60, 100) if x is None else np.asarray(x, dtype=float)
+        self.electron_density, self.electron_temperature = _poisson(self.x), _exp_decay(self.x)
+
+
 class SimplePlasma:  # lineshapes.py:469-480
     def __init__(self, x=None):
         self.x = np.linspace(0, 60, 100) if x is None else np.asarray(x, dtype=float)

@@ -48,3 +48,26 @@ def test_closed_form_profile_families_host_statements():
     assert ls.SimpleGaussianPlasma(x=x).electron_temperature.number_of_variables == 2
     assert {c.fn for c in (ls.ExpDecay(x), ls.ADoubleExpDecay(x), ls.FlatProfile(x, [0, 2]))} == \
         {"PF_EXP_DECAY", "PF_DOUBLE_EXP_DECAY", "PF_FLAT"}
+
+
+def test_stand_alone_profile_callables_match_the_reference():
+    """Poisson (lineshapes.py:537-550) and the separatrix profiles (:723-767) against values the unmodified reference
+    classes returned (`oracle/make_profile_golden.py`)."""
+    from baysar_b200 import lineshapes as ls
+
+    from .conftest import GOLDEN
+
+    z = np.load(GOLDEN / "profile_callables.npz")
+    x, chords = z["x"], z["chords"]
+    cases = {
+        "poisson": ls.Poisson(x),
+        "linear_separatrix": ls.LinearSeparatrix(chords),
+        "cauchy_separatrix": ls.CauchySeparatrix(chords),
+        "cauchy_separatrix_centred": ls.CauchySeparatrix(chords, centre=2.5),
+        "simple_separatrix_ne": ls.SimpleSeparatrix(chords).electron_density,
+        "simple_separatrix_te": ls.SimpleSeparatrix(chords).electron_temperature,
+    }
+    for name, fn in cases.items():
+        np.testing.assert_array_equal(np.array(fn.bounds, dtype=float), z[name + "_bounds"])
+        for theta, want in zip(z[name + "_theta"], z[name + "_value"]):
+            np.testing.assert_allclose(fn(list(theta)), want, rtol=1e-14, atol=0, err_msg=name)
