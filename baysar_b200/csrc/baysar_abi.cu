@@ -195,7 +195,14 @@ int launch_chord_kernel_t(baysar_model* m, const ChordArgs& a, dim3 grid, size_t
   const bool pdl = !m->opt.serial_launches;
   const bool nt128 = m->opt.chord_threads == 128 || (m->opt.chord_threads == 0 && m->I[I_F_MAX] <= 4096);
   if (nt128) {
-    CUDA_OK(launch_k(pdl, chord_stage_kernel<128, MODE, 6, TAPS>, grid, dim3(128), smem, stream, m->dev, a));
+    // register budget by how many CTAs the shared-memory footprint lets an SM hold (6 by default, options.chord_min_blocks
+    // raises it to 7 or 8 where the footprint allows)
+    const int by_smem128 = (int)((size_t)232448 / (smem + 1024));
+    const int want128 = m->opt.chord_min_blocks > 6 ? m->opt.chord_min_blocks : 6;
+    const int minb128 = by_smem128 < want128 ? by_smem128 : want128;
+    auto kern128 = minb128 >= 8 ? chord_stage_kernel<128, MODE, 8, TAPS>
+                                : (minb128 == 7 ? chord_stage_kernel<128, MODE, 7, TAPS> : chord_stage_kernel<128, MODE, 6, TAPS>);
+    CUDA_OK(launch_k(pdl, kern128, grid, dim3(128), smem, stream, m->dev, a));
     return 0;
   }
   constexpr int NT = 256;
@@ -213,8 +220,12 @@ int launch_chord_kernel_t(baysar_model* m, const ChordArgs& a, dim3 grid, size_t
 template <int MODE>
 int launch_chord_kernel(baysar_model* m, const ChordArgs& a, dim3 grid, size_t smem, cudaStream_t stream, int chord) {
   const int* ch = m->ch_i + chord * CH_I_COUNT;
-  if (ch[CH_B_OPTIONAL]) return launch_chord_kernel_t<MODE, 0>(m, a, grid, smem, stream);
-  if (ch[CH_NARROW]) return launch_chord_kernel_t<MODE, 1>(m, a, grid, smem, stream);
+  if (ch[CH_B_OPTIONAL] || ch[CH_NARROW]) {
+    ChordArgs b = a;
+    b.kd_max = 0;  // no Doppler tap table in these builds (the shared-memory size was computed without it)
+    return ch[CH_B_OPTIONAL] ? launch_chord_kernel_t<MODE, 0>(m, b, grid, smem, stream)
+                             : launch_chord_kernel_t<MODE, 1>(m, b, grid, smem, stream);
+  }
   return launch_chord_kernel_t<MODE, 2>(m, a, grid, smem, stream);
 }
 
@@ -255,7 +266,13 @@ int set_kernel_attributes() {
       allow_max_smem(chord_stage_kernel<256, 1, 4, 0>) || allow_max_smem(chord_stage_kernel<256, 1, 5, 0>) ||
       allow_max_smem(chord_stage_kernel<128, 0, 6, 2>) || allow_max_smem(chord_stage_kernel<128, 1, 6, 2>) ||
       allow_max_smem(chord_stage_kernel<128, 0, 6, 1>) || allow_max_smem(chord_stage_kernel<128, 1, 6, 1>) ||
-      allow_max_smem(chord_stage_kernel<128, 0, 6, 0>) || allow_max_smem(chord_stage_kernel<128, 1, 6, 0>))
+      allow_max_smem(chord_stage_kernel<128, 0, 6, 0>) || allow_max_smem(chord_stage_kernel<128, 1, 6, 0>) ||
+      allow_max_smem(chord_stage_kernel<128, 0, 7, 2>) || allow_max_smem(chord_stage_kernel<128, 1, 7, 2>) ||
+      allow_max_smem(chord_stage_kernel<128, 0, 7, 1>) || allow_max_smem(chord_stage_kernel<128, 1, 7, 1>) ||
+      allow_max_smem(chord_stage_kernel<128, 0, 7, 0>) || allow_max_smem(chord_stage_kernel<128, 1, 7, 0>) ||
+      allow_max_smem(chord_stage_kernel<128, 0, 8, 2>) || allow_max_smem(chord_stage_kernel<128, 1, 8, 2>) ||
+      allow_max_smem(chord_stage_kernel<128, 0, 8, 1>) || allow_max_smem(chord_stage_kernel<128, 1, 8, 1>) ||
+      allow_max_smem(chord_stage_kernel<128, 0, 8, 0>) || allow_max_smem(chord_stage_kernel<128, 1, 8, 0>))
     return 1;
   return allow_max_smem(pixel_fold_kernel<128>) || contraction_kernel_attributes();
 }
@@ -561,6 +578,8 @@ int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, con
     }
     if (ch[CH_F] < 8) { baysar_model_destroy(m); return fail("fine grid shorter than 8 points"); }
     if (ch[CH_HALO] % 4 != 0) { baysar_model_destroy(m); return fail("CH_HALO must be a multiple of 4"); }
+    // the single- and three-tap builds (chord_stage.cuh TAPS < 2) never tabulate a Doppler kernel: no tap table for them
+    if (ch[CH_B_OPTIONAL] || ch[CH_NARROW]) kd_max = 0;
     ChordSmem s = chord_smem_layout(ch[CH_F], ch[CH_HALO], ch[CH_TAPS_MAX], kd_max, 1, ch[CH_N_LINES]);
     smem_max = s.total > smem_max ? s.total : smem_max;
     m->chord_smem.push_back(s.total);
@@ -598,12 +617,7 @@ int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, con
     if (e2 != cudaSuccess) { baysar_model_destroy(m); return fail(std::string("ifc taps upload: ") + cudaGetErrorString(e2)); }
     m->any_ifc = true;
     if (ch[CH_B_OPTIONAL]) {  // MODE 1 never touches buffer B on this chord
-      int kd_max = 0;
-      for (int k = 0; k < ch[CH_N_LINES]; ++k) {
-        int kd = m->cl_i[(ch[CH_LINE_OFF] + k) * CL_I_COUNT + CL_KD];
-        kd_max = kd > kd_max ? kd : kd_max;
-      }
-      m->chord_smem[c] = chord_smem_layout(ch[CH_F], ch[CH_HALO], ch[CH_TAPS_MAX], kd_max, 0, ch[CH_N_LINES]).total;
+      m->chord_smem[c] = chord_smem_layout(ch[CH_F], ch[CH_HALO], ch[CH_TAPS_MAX], 0, 0, ch[CH_N_LINES]).total;
     }
     if (ch[CH_CALWAVE_IDX] < 0) {  // static wavelength map: the pixel stage reads columns i_p and i_p + 1 only
       IfcPlan& plw = m->ifc[c];
