@@ -60,6 +60,8 @@ struct baysar_model {
   // host-buffer entry point: its own non-blocking stream (the legacy default stream would serialise with every other
   // stream of the process)
   cudaStream_t host_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;       // baysar_eval_logp_host: theta chunks are copied here while earlier chunks are evaluated
+  std::vector<cudaEvent_t> copy_done;       // one event per chunk in flight
   // one workspace per model: every evaluation waits for the previous one (whatever stream it ran on) before it starts
   cudaEvent_t last_done = nullptr;
 };
@@ -504,6 +506,7 @@ int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, con
   {
     cudaError_t es = cudaStreamCreateWithFlags(&m->host_stream, cudaStreamNonBlocking);
     if (es == cudaSuccess) es = cudaEventCreateWithFlags(&m->last_done, cudaEventDisableTiming);
+    if (es == cudaSuccess) es = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
     if (es != cudaSuccess) { baysar_model_destroy(m); return fail(std::string("cudaStreamCreate: ") + cudaGetErrorString(es)); }
   }
   m->I = static_cast<const int64_t*>(host.ptr(SEC_I));
@@ -674,6 +677,8 @@ void baysar_model_destroy(baysar_model_t* m) {
   cudaFree(m->blob_dev); cudaFree(m->los_tables_dev); cudaFree(m->lines); cudaFree(m->comps); cudaFree(m->hdr); cudaFree(m->status);
   cudaFree(m->theta_stage); cudaFree(m->logp_stage); cudaFreeHost(m->out_pinned);
   if (m->host_stream) cudaStreamDestroy(m->host_stream);
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  for (cudaEvent_t e : m->copy_done) cudaEventDestroy(e);
   if (m->last_done) cudaEventDestroy(m->last_done);
   cudaFree(m->spec); cudaFree(m->conv); cudaFree(m->conv_c); cudaFree(m->trapz_part); cudaFree(m->aux);
   for (float* t : m->ifc_taps_dev) cudaFree(t);
@@ -788,8 +793,36 @@ int baysar_eval_logp_host(baysar_model_t* m, const double* theta_host, int64_t n
     m->stage_cap = cap;
   }
   uint32_t* status_dev = reinterpret_cast<uint32_t*>(m->logp_stage + n);
-  CUDA_OK(cudaMemcpyAsync(m->theta_stage, theta_host, sizeof(double) * n * np, cudaMemcpyHostToDevice, m->host_stream));
-  if (baysar_eval_logp(m, m->theta_stage, n, m->logp_stage, status_dev, nullptr, m->host_stream)) return 1;
+  // Large batches: the copy of theta (multi-species, 65 536 thetas: 8.9 MB, a few hundred microseconds over PCIe) is
+  // pipelined with the evaluation in chunks -- chunk c + 1 crosses the bus on a second stream while chunk c is evaluated.
+  // Small batches (the 4096-theta Balmer step is one wave of the line-of-sight kernel) stay one copy and one evaluation.
+  constexpr int64_t HOST_CHUNK = 16384;
+  if (n >= 2 * HOST_CHUNK) {
+    const int64_t n_chunks = (n + HOST_CHUNK - 1) / HOST_CHUNK;
+    while ((int64_t)m->copy_done.size() < n_chunks) {
+      cudaEvent_t ev;
+      CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      m->copy_done.push_back(ev);
+    }
+    // (the previous call ended with a synchronisation of host_stream: nothing still reads the staging buffer)
+    for (int64_t c = 0; c < n_chunks; ++c) {
+      const int64_t off = c * HOST_CHUNK, nc = n - off < HOST_CHUNK ? n - off : HOST_CHUNK;
+      CUDA_OK(cudaMemcpyAsync(m->theta_stage + off * np, theta_host + off * np, sizeof(double) * nc * np, cudaMemcpyHostToDevice,
+                              m->copy_stream));
+      CUDA_OK(cudaEventRecord(m->copy_done[c], m->copy_stream));
+    }
+    int launches = 0;
+    for (int64_t c = 0; c < n_chunks; ++c) {
+      const int64_t off = c * HOST_CHUNK, nc = n - off < HOST_CHUNK ? n - off : HOST_CHUNK;
+      CUDA_OK(cudaStreamWaitEvent(m->host_stream, m->copy_done[c], 0));
+      if (baysar_eval_logp(m, m->theta_stage + off * np, nc, m->logp_stage + off, status_dev + off, nullptr, m->host_stream)) return 1;
+      launches += m->last_launches;
+    }
+    m->last_launches = launches;
+  } else {
+    CUDA_OK(cudaMemcpyAsync(m->theta_stage, theta_host, sizeof(double) * n * np, cudaMemcpyHostToDevice, m->host_stream));
+    if (baysar_eval_logp(m, m->theta_stage, n, m->logp_stage, status_dev, nullptr, m->host_stream)) return 1;
+  }
   const size_t out_bytes = (sizeof(double) + (status_host ? sizeof(uint32_t) : 0)) * (size_t)n;
   CUDA_OK(cudaMemcpyAsync(m->out_pinned, m->logp_stage, out_bytes, cudaMemcpyDeviceToHost, m->host_stream));
   CUDA_OK(cudaStreamSynchronize(m->host_stream));
