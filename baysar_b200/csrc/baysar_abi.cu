@@ -211,8 +211,9 @@ int launch_chord_kernel_t(baysar_model* m, const ChordArgs& a, dim3 grid, size_t
   const int cap = m->opt.chord_min_blocks > 0 ? m->opt.chord_min_blocks : 5;
   const int by_smem = (int)((size_t)232448 / (smem + 1024));
   const int minb = by_smem < cap ? by_smem : cap;
-  auto kern = minb >= 5 ? chord_stage_kernel<NT, MODE, 5, TAPS>
-                        : (minb == 4 ? chord_stage_kernel<NT, MODE, 4, TAPS> : chord_stage_kernel<NT, MODE, 3, TAPS>);
+  auto kern = minb >= 6 ? chord_stage_kernel<NT, MODE, 6, TAPS>
+                        : (minb == 5 ? chord_stage_kernel<NT, MODE, 5, TAPS>
+                                     : (minb == 4 ? chord_stage_kernel<NT, MODE, 4, TAPS> : chord_stage_kernel<NT, MODE, 3, TAPS>));
   CUDA_OK(launch_k(pdl, kern, grid, dim3(NT), smem, stream, m->dev, a));
   return 0;
 }
@@ -225,6 +226,13 @@ int launch_chord_kernel(baysar_model* m, const ChordArgs& a, dim3 grid, size_t s
   if (ch[CH_B_OPTIONAL] || ch[CH_NARROW]) {
     ChordArgs b = a;
     b.kd_max = 0;  // no Doppler tap table in these builds (the shared-memory size was computed without it)
+    if (MODE == 1 && a.skip_edge64 && ch[CH_B_OPTIONAL]) {
+      // Spectral stage of the folded contraction with single-tap lines only: nothing is convolved in this kernel, so the
+      // spectrum buffer needs neither haloes nor the instrument-tap table (Balmer demo: 38.2 -> 34.6 KB, a sixth CTA fits)
+      b.ch_i[CH_HALO] = 0;
+      b.ch_i[CH_TAPS_MAX] = 0;
+      smem = chord_smem_layout(ch[CH_F], 0, 0, 0, 0, ch[CH_N_LINES]).total;
+    }
     return ch[CH_B_OPTIONAL] ? launch_chord_kernel_t<MODE, 0>(m, b, grid, smem, stream)
                              : launch_chord_kernel_t<MODE, 1>(m, b, grid, smem, stream);
   }
@@ -266,6 +274,9 @@ int set_kernel_attributes() {
       allow_max_smem(chord_stage_kernel<256, 0, 3, 0>) || allow_max_smem(chord_stage_kernel<256, 0, 4, 0>) ||
       allow_max_smem(chord_stage_kernel<256, 0, 5, 0>) || allow_max_smem(chord_stage_kernel<256, 1, 3, 0>) ||
       allow_max_smem(chord_stage_kernel<256, 1, 4, 0>) || allow_max_smem(chord_stage_kernel<256, 1, 5, 0>) ||
+      allow_max_smem(chord_stage_kernel<256, 0, 6, 2>) || allow_max_smem(chord_stage_kernel<256, 1, 6, 2>) ||
+      allow_max_smem(chord_stage_kernel<256, 0, 6, 1>) || allow_max_smem(chord_stage_kernel<256, 1, 6, 1>) ||
+      allow_max_smem(chord_stage_kernel<256, 0, 6, 0>) || allow_max_smem(chord_stage_kernel<256, 1, 6, 0>) ||
       allow_max_smem(chord_stage_kernel<128, 0, 6, 2>) || allow_max_smem(chord_stage_kernel<128, 1, 6, 2>) ||
       allow_max_smem(chord_stage_kernel<128, 0, 6, 1>) || allow_max_smem(chord_stage_kernel<128, 1, 6, 1>) ||
       allow_max_smem(chord_stage_kernel<128, 0, 6, 0>) || allow_max_smem(chord_stage_kernel<128, 1, 6, 0>) ||

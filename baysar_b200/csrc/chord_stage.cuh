@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
     // 128-bit shared-memory store (and one 128-bit global store in MODE 1) per group, and the far / near decision is one
     // test per group on the integer distance to the line centre.  Far-field points go two at a time through the packed
     // FP32 pipe (fma.rn.f32x2).
-    constexpr int GPT = NT == 128 ? 2 * BAYSAR_FUSED_GPT : BAYSAR_FUSED_GPT;
+    constexpr int GPT = NT == 128 ? 2 * BAYSAR_FUSED_GPT : (MINB >= 6 ? BAYSAR_FUSED_GPT / 2 : BAYSAR_FUSED_GPT);
     float* sp = (MODE == 1) ? a.spec + n * a.split_pitch + a.split_pad : nullptr;
     const f32x2 dhi2 = pack2(d_hi, d_hi), dlo2 = pack2(d_lo, d_lo);
     const int n_groups = (F + 3) >> 2;
