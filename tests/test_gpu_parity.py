@@ -398,6 +398,12 @@ def test_config2_full_batch_sample_against_oracle(posteriors):
     assert torch.equal(a, parts)
     a, st = a.cpu().numpy(), st.cpu().numpy()
     assert (st == 0).mean() > 0.9
+    # the reference-facing call with a HOST array: batches from 32 768 thetas cross the bus in chunks of 16 384 while the
+    # earlier chunks are evaluated (baysar_eval_logp_host) -- same bits as the device-resident call, also with a ragged
+    # last chunk
+    np.testing.assert_array_equal(post(theta), a)
+    np.testing.assert_array_equal(post.last_status, st)
+    np.testing.assert_array_equal(post(theta[:40001]), a[:40001])
     from oracle.numpy_port import OracleError
 
     checked = 0
