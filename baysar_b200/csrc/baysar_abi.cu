@@ -667,7 +667,9 @@ int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, con
         if (fx.x_l < 2 || fx.x_r < 2) fx.no_extrapolation = false;
         fx.inv_err.resize(ch[CH_P]);
         for (int px = 0; px < ch[CH_P]; ++px) fx.inv_err[px] = (float)(1.0 / err_host[px]);
-        if (upload_pxc_plan(fx)) { free_pxc_plan(fx); baysar_model_destroy(m); return 1; }
+        if (upload_pxc_plan(fx) || (m->opt.contraction_b_image >= 0 && build_pxc_b_image(fx))) {
+          free_pxc_plan(fx); baysar_model_destroy(m); return 1;
+        }
         m->pxc[c] = fx;
         m->split_pitch_max = fx.pitch > m->split_pitch_max ? fx.pitch : m->split_pitch_max;
         m->conv_pitch_max = fx.out_pitch > m->conv_pitch_max ? fx.out_pitch : m->conv_pitch_max;

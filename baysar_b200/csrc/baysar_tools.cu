@@ -187,7 +187,7 @@ int baysar_debug_pix_contract(const float* spectra_dev, int64_t n_rows, int F, c
   if (pix_col_host) memcpy(pix_col_host, pl.pix_col.data(), sizeof(int) * P);
   if (!out_dev) return 0;  // layout query only
   if (out_capacity < n_rows * pl.out_pitch) return fail("output buffer too small");
-  if (upload_pxc_plan(pl)) { free_pxc_plan(pl); return 1; }
+  if (upload_pxc_plan(pl) || (!getenv("BAYSAR_PXC_BUILDERS") && build_pxc_b_image(pl))) { free_pxc_plan(pl); return 1; }
   if (contraction_kernel_attributes()) { free_pxc_plan(pl); return 1; }
   float* spec = nullptr;
   if (tsum_dev && tsum_capacity < n_rows * pl.n_col_tiles * 2) return fail("tsum buffer too small");

@@ -81,6 +81,10 @@ struct PxcPlan {
   float *d_col_frac = nullptr, *d_wtab = nullptr, *d_bbar = nullptr;
   double* d_dtab = nullptr;
   std::map<int, PxcSchedule> schedules;  // by number of theta blocks
+  // B operand as a precomputed image (pix_contract.cuh b_image_kernel): one stage-sized tile per k-block of every column tile
+  std::vector<int> tile_bimg;
+  int* d_tile_bimg = nullptr;
+  unsigned char* d_bimg = nullptr;
 };
 
 static float tf32_round(float v) {  // round to nearest, ties away from zero, 10-bit mantissa (cvt.rna.tf32.f32)
@@ -267,8 +271,36 @@ int upload_pxc_plan(PxcPlan& pl) {
 void free_pxc_plan(PxcPlan& pl) {
   cudaFree(pl.d_tile_kcol0); cudaFree(pl.d_tile_nkb); cudaFree(pl.d_tile_boff); cudaFree(pl.d_col_idx); cudaFree(pl.d_pix_col);
   cudaFree(pl.d_col_frac); cudaFree(pl.d_wtab); cudaFree(pl.d_dtab); cudaFree(pl.d_bbar); cudaFree(pl.d_inv_err);
+  cudaFree(pl.d_tile_bimg); cudaFree(pl.d_bimg);
+  pl.d_tile_bimg = nullptr; pl.d_bimg = nullptr;
   for (auto& kv : pl.schedules) { cudaFree(kv.second.d_sched); cudaFree(kv.second.d_cnt); }
   pl.schedules.clear();
+}
+
+// The theta-independent B operand of the folded contraction, written once per plan: 16 KB (TN = 128) per k-block of every
+// column tile, in the bytes a ring stage holds (Balmer demo: 790 tiles, 12.9 MB -- it stays in L2 while the 32 theta blocks
+// of a 4096-theta step read it).  Plans whose image would exceed `max_bytes` keep the builder warps.
+int build_pxc_b_image(PxcPlan& pl, size_t max_bytes = (size_t)512 << 20) {
+  int64_t total = 0;
+  int max_kb = 0;
+  pl.tile_bimg.resize(pl.n_col_tiles);
+  for (int t = 0; t < pl.n_col_tiles; ++t) {
+    pl.tile_bimg[t] = (int)total;
+    total += pl.tile_nkb[t];
+    max_kb = std::max(max_kb, pl.tile_nkb[t]);
+  }
+  const size_t stage = (size_t)pl.tn * 128;
+  if (total == 0 || (size_t)total * stage > max_bytes || max_kb > 65535) return 0;
+  if (upload(&pl.d_tile_bimg, pl.tile_bimg)) return 1;
+  CUDA_OK(cudaMalloc(&pl.d_bimg, (size_t)total * stage));
+  const dim3 grid((unsigned)pl.n_col_tiles, (unsigned)max_kb);
+  if (pl.tn == 64)
+    pxc::b_image_kernel<64><<<grid, 64>>>(pl.d_tile_nkb, pl.d_tile_bimg, pl.d_col_idx, pl.d_col_frac, pl.d_wtab, pl.wlen, pl.d_bimg);
+  else
+    pxc::b_image_kernel<128><<<grid, 64>>>(pl.d_tile_nkb, pl.d_tile_bimg, pl.d_col_idx, pl.d_col_frac, pl.d_wtab, pl.wlen, pl.d_bimg);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaDeviceSynchronize());
+  return 0;
 }
 
 // Longest-first deal of the (column tile, theta block) pairs to `sms` persistent CTAs (cost = k-blocks + a constant
@@ -362,6 +394,7 @@ int launch_pxc(PxcPlan& pl, const float* spec, int n_rb, float* out, double* tsu
   p.sched_slots = sc->slots; p.out = out; p.out_pitch = pl.out_pitch; p.ring = pl.ring; p.dbg_cycles = dbg_cycles;
   p.bbar = tsum ? pl.d_bbar : nullptr; p.tile_boff = pl.d_tile_boff; p.tsum = tsum;
   p.n_col_tiles = pl.n_col_tiles;
+  p.bimg = pl.d_bimg; p.tile_bimg = pl.d_tile_bimg;
   // A loader: cp.async by two loader warps.  The TMA variant (one cp.async.bulk.tensor box per k-block) is compiled only
   // with -DBAYSAR_PXC_TMA.  Its data hazard is root-caused (round 2): the converters read a ring stage through the generic
   // proxy and the TMA refill writes it through the async proxy; the mbarrier hand-over alone does not order the two, so

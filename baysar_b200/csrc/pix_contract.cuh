@@ -88,6 +88,10 @@ struct Params {
   double* tsum;            // [rows][n_col_tiles][2]
   int n_col_tiles;
   long long* dbg_cycles;   // TRACE instantiation: [ctas][16] cycles spent waiting per role
+  // B from a precomputed image (b_image_kernel, model creation): stage-sized, already swizzled and TF32-split tiles, one
+  // per (column tile, position i in the tile's k-block sequence); nullptr: the builder warps generate B
+  const unsigned char* bimg;
+  const int* tile_bimg;    // [n_col_tiles] index of the tile's first stage image
 };
 
 template <int TN>
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p, cons
   if (tid == 0) {
     auto init = [](uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); };
     for (int s = 0; s < C::A_STAGES; ++s) { init(full + 8 * s, CONVERTER_WARPS / 2); init(empty + 8 * s, 1); }
-    for (int s = 0; s < C::B_STAGES; ++s) { init(bfull + 8 * s, BUILDER_WARPS / BUILDER_TEAMS); init(bempty + 8 * s, 1); }
+    for (int s = 0; s < C::B_STAGES; ++s) { init(bfull + 8 * s, p.bimg ? 1 : BUILDER_WARPS / BUILDER_TEAMS); init(bempty + 8 * s, 1); }
     init(acc_full, 1);
     init(acc_free, EPILOGUE_WARPS);
     for (int r = 0; r < RING_MAX; ++r) { init(landed + 8 * r, p.use_tma ? 1 : 32 * LOADER_WARPS); init(consumed + 8 * r, CONVERTER_WARPS / 2); }
@@ -357,6 +361,34 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p, cons
     }
     if (!p.use_tma) asm volatile("cp.async.wait_all;" ::: "memory");
     if (TRACE && lane == 0 && warp == WARP_LOADER) p.dbg_cycles[(int64_t)blockIdx.x * 16 + 3] = w0;
+  } else if (warp >= WARP_BUILDER0 && p.bimg) {
+    // ===================== B loader: one bulk copy (16 KB at TN = 128) of a precomputed stage image per k-block ========
+    // B does not depend on theta: b_image_kernel writes every (column tile, k-block) tile once per model, in exactly the
+    // bytes the builder warps would store, and the image stays in L2.  The copy is written through the async proxy and
+    // read by the tensor core through the async proxy: no cross-proxy fence; the builders' tap reads and tile stores
+    // (368 of the ~690 shared-memory wavefronts per k-block) are gone.
+    if (warp == WARP_BUILDER0 && lane == 0) {
+      int64_t g = 0;
+      long long w0 = 0;
+      const long long t_begin = TRACE ? clock64() : 0;
+      for (int q = 0; q < my_tiles; ++q) {
+        const int ct = my_sched[q] >> 16;
+        const int n_kb = p.tile_nkb[ct];
+        const unsigned char* src = p.bimg + (size_t)p.tile_bimg[ct] * C::B_STAGE_BYTES;
+        for (int i = 0; i < n_kb; ++i, ++g) {
+          const int sb = (int)(g % C::B_STAGES);
+          if (g >= C::B_STAGES) mbar_wait32_timed<TRACE>(bempty + 8 * sb, (uint32_t)(((g / C::B_STAGES) - 1) & 1), w0);
+          const uint32_t bar = bfull + 8 * sb, dst = bring + (uint32_t)sb * C::B_STAGE_BYTES;
+          asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(C::B_STAGE_BYTES) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                       "l"(src + (size_t)i * C::B_STAGE_BYTES), "r"(C::B_STAGE_BYTES), "r"(bar) : "memory");
+        }
+      }
+      if (TRACE) {
+        long long* o = p.dbg_cycles + (int64_t)blockIdx.x * 16;
+        o[4] = w0; o[5] = clock64() - t_begin;
+      }
+    }
   } else if (warp >= WARP_BUILDER0) {
     // ===================== B builders: tap table -> interpolated, TF32-split k-block tiles =====================
     // Builder team tm (two warps, each half of the columns) owns the k-blocks g = tm (mod 4) of this CTA's sequence:
@@ -528,6 +560,41 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p, cons
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   if (warp == WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(512));
+}
+
+// One stage image per (column tile, sequence position): the builder warps' arithmetic and store pattern (see above) with
+// the tap table read from global memory and the stores going to the image instead of a ring stage.  64 threads = the two
+// warps of a builder team; grid (n_col_tiles, max k-blocks of a tile).
+template <int TN>
+__global__ void __launch_bounds__(64) b_image_kernel(const int* __restrict__ tile_nkb, const int* __restrict__ tile_bimg,
+                                                     const int* __restrict__ col_idx, const float* __restrict__ col_frac,
+                                                     const float* __restrict__ wtab, int wlen, unsigned char* __restrict__ bimg) {
+  using C = Cfg<TN>;
+  constexpr int ITS = TN / 16;
+  const int ct = blockIdx.x, i = blockIdx.y;
+  const int n_kb = tile_nkb[ct];
+  if (i >= n_kb) return;
+  const int wb = threadIdx.x >> 5, lane = threadIdx.x & 31, it_base = wb * ITS, j = lane >> 2, qc = lane & 3;
+  const uint32_t soff0 = (uint32_t)(j * 128 + ((qc ^ j) << 4));
+  const int kb = ifc::kb_order(i, n_kb);
+  unsigned char* img = bimg + (size_t)(tile_bimg[ct] + i) * C::B_STAGE_BYTES;
+  for (int it = 0; it < ITS; ++it) {
+    const int n = (it_base + it) * 8 + j;
+    const int x0 = col_idx[ct * TN + n] - 4 * qc - 3 - TILE_K * kb;  // tap at x - 3 + m is wtab[x0 + m]
+    const float cf = col_frac[ct * TN + n];
+    float L[5];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      const int e = x0 + m;
+      L[m] = (e >= 0 && e < wlen) ? wtab[e] : 0.f;
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) split_fast(fmaf(cf, L[4 - t] - L[3 - t], L[3 - t]), hi[t], lo[t]);
+    const uint32_t off = soff0 + (uint32_t)((it_base + it) * 1024);
+    *reinterpret_cast<uint4*>(img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(img + (off ^ 64u)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
 }
 
 }  // namespace pxc

@@ -78,7 +78,9 @@ typedef struct baysar_options {
   int chord_threads;     /* threads per CTA (= per theta and chord) of the chord kernel: 0 auto, 128 or 256 */
   int los_team_warps;    /* warps that share one theta in the LOS kernel: 0 auto by line-of-sight length, or 2, 4, 8 */
   int serial_launches;   /* 1: plain kernel launches instead of programmatic dependent launch (A/B timing) */
-  int reserved[6];
+  int contraction_b_image; /* folded contraction's B operand: 0 auto (a precomputed image in HBM / L2, copied with
+                            cp.async.bulk), -1 generated by builder warps from the tap table in shared memory */
+  int reserved[5];
 } baysar_options_t;
 int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, const baysar_options_t* options,
                            baysar_model_t** out);

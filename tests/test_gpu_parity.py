@@ -241,6 +241,10 @@ def test_contraction_variants_agree():
     lo, hi = folded.plasma.theta_bounds[:, 0], folded.plasma.theta_bounds[:, 1]
     theta = lo + rng.random((512, folded.plasma.n_params)) * (hi - lo)
     a, b, c = folded(theta), folded64(theta), toeplitz(theta)
+    # the B operand from the precomputed image (default) and from the builder warps: the same bytes reach the tensor core
+    for opts, want in (({"contraction_b_image": -1}, a), ({"contraction_b_image": -1, "folded_tile": 64}, b)):
+        built = _fresh_posterior(wl, opts)
+        np.testing.assert_array_equal(built(theta), want)
     ok = (folded.last_status == 0) & (folded64.last_status == 0) & (toeplitz.last_status == 0)
     assert ok.mean() > 0.9
     np.testing.assert_allclose(a[ok], c[ok], rtol=LOGP_RTOL)
