@@ -673,7 +673,7 @@ int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, con
         m->pxc[c] = fx;
         m->split_pitch_max = fx.pitch > m->split_pitch_max ? fx.pitch : m->split_pitch_max;
         m->conv_pitch_max = fx.out_pitch > m->conv_pitch_max ? fx.out_pitch : m->conv_pitch_max;
-        m->tiles_max = 2 * fx.n_col_tiles > m->tiles_max ? 2 * fx.n_col_tiles : m->tiles_max;  // tsum lives in trapz_part
+        m->tiles_max = pxc::TSUM_SLOTS * fx.n_col_tiles > m->tiles_max ? pxc::TSUM_SLOTS * fx.n_col_tiles : m->tiles_max;  // tsum lives in trapz_part
       }
     }
     m->split_pitch_max = pl.pitch > m->split_pitch_max ? pl.pitch : m->split_pitch_max;

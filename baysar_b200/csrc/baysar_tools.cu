@@ -190,7 +190,7 @@ int baysar_debug_pix_contract(const float* spectra_dev, int64_t n_rows, int F, c
   if (upload_pxc_plan(pl) || (!getenv("BAYSAR_PXC_BUILDERS") && build_pxc_b_image(pl))) { free_pxc_plan(pl); return 1; }
   if (contraction_kernel_attributes()) { free_pxc_plan(pl); return 1; }
   float* spec = nullptr;
-  if (tsum_dev && tsum_capacity < n_rows * pl.n_col_tiles * 2) return fail("tsum buffer too small");
+  if (tsum_dev && tsum_capacity < n_rows * pl.n_col_tiles * pxc::TSUM_SLOTS) return fail("tsum buffer too small");
   cudaError_t e = cudaMalloc(&spec, sizeof(float) * n_rows * pl.pitch);
   if (e == cudaSuccess) e = cudaMemset(spec, 0, sizeof(float) * n_rows * pl.pitch);
   if (e != cudaSuccess) { free_pxc_plan(pl); return fail(std::string("debug spectra: ") + cudaGetErrorString(e)); }

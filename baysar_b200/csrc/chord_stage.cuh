@@ -1304,7 +1304,7 @@ struct PixelFoldArgs {
   int n_dl, n_dr;
   double wsum;              // W
   const float* inv_err;     // [P] float32 1 / err of the chord's pixels (log-posterior-only fast loop), may be nullptr
-  const double* tsum;       // [rows][n_col_tiles][2] exact column sums per tile (converter groups), may be nullptr
+  const double* tsum;       // [rows][n_col_tiles][pxc::TSUM_SLOTS] exact column sums per tile (converter groups), may be nullptr
   int n_col_tiles, n_fold_tiles, tile_n;
   double* logp;             // log-posterior path of single-chord models: also do K3's job (sum of components, flags)
   const double* aux;        // [N][BAYSAR_AUX_STRIDE]
@@ -1381,8 +1381,8 @@ __global__ void __launch_bounds__(NT, BAYSAR_PIXFOLD_MINB) pixel_fold_kernel(Mod
       double cs = 0.0;
       for (int e = tid & 31; e < a.tile_n; e += 32) cs += (double)row[t * a.tile_n + e];
       cs = warp_sum(cs);
-      const double* ts = a.tsum + (n * a.n_col_tiles + t) * 2;
-      const double k = (ts[0] + ts[1]) / cs;
+      const double* ts = a.tsum + (n * a.n_col_tiles + t) * 3;  // pxc::TSUM_SLOTS
+      const double k = ((ts[0] + ts[1]) + ts[2]) / cs;
       if (fabs(k - 1.0) < 1e-4) kap = (float)k;  // a correction, not a repair: anything larger is not truncation bias
     }
     if ((tid & 31) == 0) kappa_s[t] = kap;

@@ -249,7 +249,7 @@ PxcPlan make_pxc_plan(const double* w, int KI, int k_lo, int k_hi, int F, int P,
   pl.ring = tn == 64 ? pxc::ring_stages<64>(pl.wlen) : pxc::ring_stages<128>(pl.wlen);
   // the pixel stage keeps one correction / scale per folded tile in 64-entry shared-memory tables: wider chords (P > 8192
   // at 128-column tiles) stay on the every-column Toeplitz contraction
-  pl.on = pl.ring >= 2 && pl.n_col_tiles < 32768 && pl.n_fold_tiles <= pxc::MAX_FOLD_TILES;
+  pl.on = pl.ring >= 3 && pl.n_col_tiles < 32768 && pl.n_fold_tiles <= pxc::MAX_FOLD_TILES;
   return pl;
 }
 

@@ -43,6 +43,7 @@ using ifc::TILE_K;
 using ifc::TILE_M;
 
 constexpr int CONVERTER_WARPS = 8, EPILOGUE_WARPS = 4, BUILDER_WARPS = 8, BUILDER_TEAMS = 4;
+constexpr int TSUM_SLOTS = 3;    // partial column sums per (row, tile): one per converter group
 constexpr int LOADER_WARPS = 2;  // cp.async mode: each loader warp copies half of the rows of a k-block
 constexpr int WARP_MMA = CONVERTER_WARPS + EPILOGUE_WARPS, WARP_LOADER = WARP_MMA + 1, WARP_BUILDER0 = WARP_LOADER + LOADER_WARPS;
 constexpr int THREADS = (WARP_BUILDER0 + BUILDER_WARPS) * 32;
@@ -55,7 +56,10 @@ struct Cfg {
   static constexpr int N_ACC_HI = TN == 64 ? 4 : BAYSAR_PXC_NACC128;
   static constexpr int ACC_COLS = (N_ACC_HI + 1) * TN;        // 320 / 384 TMEM columns of accumulators
   static constexpr int A_STAGES = (512 - ACC_COLS) / 32;      // 6 / 4 tensor-memory stages of the split A operand
-  static constexpr int B_STAGES = TN == 64 ? 8 : 6;           // shared-memory stages of generated B tiles
+#ifndef BAYSAR_PXC_BSTAGES128
+#define BAYSAR_PXC_BSTAGES128 6
+#endif
+  static constexpr int B_STAGES = TN == 64 ? 8 : BAYSAR_PXC_BSTAGES128;  // shared-memory stages of B tiles
   static constexpr int B_STAGE_BYTES = TN * 128;              // TN rows x (16 hi + 16 lo) floats
   static constexpr int STAGING_BYTES = TILE_M * TN * 4;
   static_assert(A_STAGES % 2 == 0, "the two converter groups take alternate stages");
@@ -85,7 +89,7 @@ struct Params {
   // sum_s S[row, s] * bbar[tile_boff[ct] + (s - k0)], bbar = sum over the tile's folded columns of B[s, c]
   const float* bbar;       // may be nullptr (no sums)
   const int* tile_boff;    // [n_col_tiles] offset of the tile's 16 n_kb floats in bbar, -1: none (explicit edge columns)
-  double* tsum;            // [rows][n_col_tiles][2]
+  double* tsum;            // [rows][n_col_tiles][TSUM_SLOTS]
   int n_col_tiles;
   long long* dbg_cycles;   // TRACE instantiation: [ctas][16] cycles spent waiting per role
   // B from a precomputed image (b_image_kernel, model creation): stage-sized, already swizzled and TF32-split tiles, one
@@ -238,10 +242,15 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p, cons
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_d) : "r"(tmem_slot));
   asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous kernel (the spectral stage) has completed
 
-  if (warp < CONVERTER_WARPS) {
+  // With the B image the builder warps are free: four of them (16..19, tensor-memory lane quadrants 0..3 like every group
+  // of four consecutive warps) form a third converter group -- the converters are latency-bound (wait for the ring, split,
+  // wait for the tensor-memory stage, store) and set the pace of the kernel
+  const bool third_group = p.bimg != nullptr && warp >= WARP_BUILDER0 + 1 && warp < WARP_BUILDER0 + 5;
+  if (warp < CONVERTER_WARPS || third_group) {
     // ===================== A converters: ring (shared memory) -> TF32 split -> tensor memory =====================
-    // (if_contract.cuh: group `grp` takes the k-block iterations grp, grp + 2, ... of this CTA's tiles, back to back)
-    const int quad = warp & 3, grp = warp >> 2;
+    // (if_contract.cuh: group `grp` takes the k-block iterations grp, grp + n_grp, ... of this CTA's tiles, back to back)
+    const int n_grp = p.bimg ? 3 : 2;
+    const int quad = warp & 3, grp = third_group ? 2 : warp >> 2;
     const int row_in_tile = quad * 32 + lane;
     const uint32_t lane_base = tmem_d + ((uint32_t)(quad * 32) << 16) + C::ACC_COLS;
     int r = grp % p.ring;
@@ -255,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p, cons
       const int n_kb = p.tile_nkb[ct];
       const int boff = p.bbar ? p.tile_boff[ct] : -1;
       double tacc = 0.0;
-      for (int i = (int)((grp - g0) & 1); i < n_kb; i += 2) {
+      for (int i = (int)(((grp - g0) % n_grp + n_grp) % n_grp); i < n_kb; i += n_grp) {
         const int64_t g = g0 + i;
         const int d = (int)(g % C::A_STAGES);
         float4 bb[4];
@@ -296,7 +305,7 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p, cons
         ifc::tmem_st16(lane_base + 32 * d, hi);
         ifc::tmem_st16(lane_base + 32 * d + TILE_K, lo);
         d_pending = d;
-        r += 2;
+        r += n_grp;
         if (r >= p.ring) { r -= p.ring; r_phase ^= 1u; }
         if (boff >= 0) {  // sixteen float32 products per k-block, float64 across k-blocks
           float part = 0.f;
@@ -310,7 +319,11 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p, cons
           tacc += (double)part;
         }
       }
-      if (boff >= 0) p.tsum[((int64_t)(rb * TILE_M + row_in_tile) * p.n_col_tiles + ct) * 2 + grp] = tacc;
+      if (boff >= 0) {
+        double* ts = p.tsum + ((int64_t)(rb * TILE_M + row_in_tile) * p.n_col_tiles + ct) * TSUM_SLOTS;
+        ts[grp] = tacc;
+        if (n_grp == 2 && grp == 0) ts[2] = 0.0;
+      }
       g0 += n_kb;
     }
     if (d_pending >= 0) {
@@ -361,7 +374,7 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p, cons
     }
     if (!p.use_tma) asm volatile("cp.async.wait_all;" ::: "memory");
     if (TRACE && lane == 0 && warp == WARP_LOADER) p.dbg_cycles[(int64_t)blockIdx.x * 16 + 3] = w0;
-  } else if (warp >= WARP_BUILDER0 && p.bimg) {
+  } else if (warp >= WARP_BUILDER0 && p.bimg) {  // (warps 16..19 took the converter branch above)
     // ===================== B loader: one bulk copy (16 KB at TN = 128) of a precomputed stage image per k-block ========
     // B does not depend on theta: b_image_kernel writes every (column tile, k-block) tile once per model, in exactly the
     // bytes the builder warps would store, and the image stays in L2.  The copy is written through the async proxy and

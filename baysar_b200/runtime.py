@@ -201,7 +201,7 @@ def debug_pix_contract(spectra, taps, pix_idx, pix_frac, tile_n=128):
                                        ctypes.byref(ms))
     _tools_check(rc)
     out = torch.empty((n, info[0]), dtype=torch.float32, device=spectra.device)
-    tsum = torch.zeros((n, info[5], 2), dtype=torch.float64, device=spectra.device)
+    tsum = torch.zeros((n, info[5], 3), dtype=torch.float64, device=spectra.device)  # pxc::TSUM_SLOTS
     rc = lib.baysar_debug_pix_contract(*args, out.data_ptr(), out.numel(), tsum.data_ptr(), tsum.numel(),
                                        ctypes.cast(info, ctypes.c_void_p), pix_col.ctypes.data, ctypes.byref(ms))
     _tools_check(rc)
