@@ -219,11 +219,11 @@ int baysar_debug_pix_contract(const float* spectra_dev, int64_t n_rows, int F, c
   if (dbg && rc == 0) {
     std::vector<long long> h(16 * 256);
     cudaMemcpy(h.data(), dbg, sizeof(long long) * 16 * 256, cudaMemcpyDeviceToHost);
-    const char* names[13] = {"conv.wait_landed", "conv.wait_empty", "conv.total", "load.wait_consumed", "build.wait_bempty",
+    const char* names[15] = {"conv.wait_landed", "conv.wait_empty", "conv.total", "load.wait_consumed", "build.wait_bempty",
                              "build.total", "epi.wait_acc_full", "epi.drain", "mma.wait_full", "mma.wait_bfull",
-                             "mma.wait_acc_free", "mma.total", "mma.k_blocks"};
+                             "mma.wait_acc_free", "mma.total", "mma.k_blocks", "cta.prologue", "cta.total"};
     const int ctas = (int)std::min<int64_t>(sms, (n_rows / ifc::TILE_M) * pl.n_col_tiles);
-    for (int k = 0; k < 13; ++k) {
+    for (int k = 0; k < 15; ++k) {
       double mean = 0, mx = 0;
       for (int b = 0; b < ctas; ++b) { mean += (double)h[b * 16 + k]; mx = std::max(mx, (double)h[b * 16 + k]); }
       fprintf(stderr, "[pxc trace] %-20s mean %.0f max %.0f (CTA0 %lld)\n", names[k], mean / ctas, mx, h[k]);

@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p, cons
   const uint32_t tmem_slot = acc_free + 8;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long t_entry = TRACE ? clock64() : 0;
   // programmatic dependent launch: this prologue (tap table, barriers, tensor-memory allocation; model constants only)
   // overlaps with the tail of the spectral stage; the spectra are touched only after griddepcontrol.wait below
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -241,6 +242,7 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p, cons
   uint32_t tmem_d;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_d) : "r"(tmem_slot));
   asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous kernel (the spectral stage) has completed
+  if (TRACE && tid == 0) p.dbg_cycles[(int64_t)blockIdx.x * 16 + 13] = clock64() - t_entry;
 
   // With the B image the builder warps are free: four of them (16..19, tensor-memory lane quadrants 0..3 like every group
   // of four consecutive warps) form a third converter group -- the converters are latency-bound (wait for the ring, split,
@@ -572,6 +574,7 @@ __global__ void __launch_bounds__(THREADS, 1) pix_contract_kernel(Params p, cons
 
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
+  if (TRACE && tid == 0) p.dbg_cycles[(int64_t)blockIdx.x * 16 + 14] = clock64() - t_entry;
   if (warp == WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(512));
 }
 
