@@ -80,3 +80,20 @@ def test_product_never_imports_the_oracle():
     for py in (ROOT / "baysar_b200").glob("*.py"):
         src = py.read_text()
         assert "import oracle" not in src and "from oracle" not in src, py
+
+
+def test_options_struct_mirrors_the_header():
+    """`runtime.Options` (ctypes) has the fields of `baysar_options_t` in declaration order and the same size."""
+    import ctypes
+    import re
+
+    from baysar_b200 import runtime
+
+    text = (runtime.INCLUDE / "baysar_b200.h").read_text()
+    body = text[text.index("typedef struct baysar_options {"):text.index("} baysar_options_t;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    decls = re.findall(r"\bint\s+(\w+)(?:\[(\d+)\])?\s*;", body)
+    names = [n for n, dim in decls if not dim]
+    reserved = [int(dim) for n, dim in decls if dim]
+    assert tuple(names) == runtime.OPTION_FIELDS
+    assert ctypes.sizeof(runtime.Options) == 4 * (len(names) + sum(reserved)) == 64
