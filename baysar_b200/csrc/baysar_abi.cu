@@ -809,8 +809,8 @@ int baysar_eval_logp_host(baysar_model_t* m, const double* theta_host, int64_t n
   // Large batches: the copy of theta (multi-species, 65 536 thetas: 8.9 MB, a few hundred microseconds over PCIe) is
   // pipelined with the evaluation in chunks -- chunk c + 1 crosses the bus on a second stream while chunk c is evaluated.
   // Small batches (the 4096-theta Balmer step is one wave of the line-of-sight kernel) stay one copy and one evaluation.
-  constexpr int64_t HOST_CHUNK = 16384;
-  if (n >= 2 * HOST_CHUNK) {
+  const int64_t HOST_CHUNK = m->opt.host_chunk_thetas > 0 ? m->opt.host_chunk_thetas : 32768;
+  if (m->opt.host_chunk_thetas >= 0 && n >= 2 * HOST_CHUNK) {
     const int64_t n_chunks = (n + HOST_CHUNK - 1) / HOST_CHUNK;
     while ((int64_t)m->copy_done.size() < n_chunks) {
       cudaEvent_t ev;

@@ -20,12 +20,12 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "--compiler-options", "-fPIC", "-shared"]
 OPTION_FIELDS = ("tensor_cores", "ifc_min_taps", "ifc_budget_mb", "folded_tile", "los_min_blocks", "los_team_points",
                  "chord_min_blocks", "chord_threads", "los_team_warps", "serial_launches",
-                 "contraction_b_image")  # baysar_options_t, in declaration order
+                 "contraction_b_image", "host_chunk_thetas")  # baysar_options_t, in declaration order
 
 
 class Options(ctypes.Structure):
     """baysar_options_t (include/baysar_b200.h): 0 = library default for every field."""
-    _fields_ = [(name, ctypes.c_int) for name in OPTION_FIELDS] + [("reserved", ctypes.c_int * 5)]
+    _fields_ = [(name, ctypes.c_int) for name in OPTION_FIELDS] + [("reserved", ctypes.c_int * 4)]
 
 
 def _sources():

@@ -80,7 +80,9 @@ typedef struct baysar_options {
   int serial_launches;   /* 1: plain kernel launches instead of programmatic dependent launch (A/B timing) */
   int contraction_b_image; /* folded contraction's B operand: 0 auto (a precomputed image in HBM / L2, copied with
                             cp.async.bulk), -1 generated by builder warps from the tap table in shared memory */
-  int reserved[5];
+  int host_chunk_thetas; /* baysar_eval_logp_host: thetas per chunk of the pipelined host-to-device copy (0 auto = 32768;
+                            batches below two chunks are copied in one piece; -1: never chunk) */
+  int reserved[4];
 } baysar_options_t;
 int baysar_model_create_ex(const void* desc_blob, size_t nbytes, int device, const baysar_options_t* options,
                            baysar_model_t** out);

@@ -402,12 +402,17 @@ def test_config2_full_batch_sample_against_oracle(posteriors):
     assert torch.equal(a, parts)
     a, st = a.cpu().numpy(), st.cpu().numpy()
     assert (st == 0).mean() > 0.9
-    # the reference-facing call with a HOST array: batches from 32 768 thetas cross the bus in chunks of 16 384 while the
-    # earlier chunks are evaluated (baysar_eval_logp_host) -- same bits as the device-resident call, also with a ragged
-    # last chunk
+    # the reference-facing call with a HOST array: batches from 65 536 thetas cross the bus in chunks of 32 768 while the
+    # earlier chunks are evaluated (baysar_eval_logp_host) -- same bits as the device-resident call; with a smaller chunk
+    # (options.host_chunk_thetas) also with a ragged last chunk
     np.testing.assert_array_equal(post(theta), a)
     np.testing.assert_array_equal(post.last_status, st)
-    np.testing.assert_array_equal(post(theta[:40001]), a[:40001])
+    from baysar_b200 import configs
+
+    small_chunks = _fresh_posterior(configs.multi_species(), {"host_chunk_thetas": 12000})
+    lo2, hi2 = small_chunks.plasma.theta_bounds[:, 0], small_chunks.plasma.theta_bounds[:, 1]
+    theta2 = lo2 + rng.random((40001, small_chunks.plasma.n_params)) * (hi2 - lo2)
+    np.testing.assert_array_equal(small_chunks(theta2), small_chunks.logp_batch(torch.as_tensor(theta2, device="cuda")).cpu().numpy())
     from oracle.numpy_port import OracleError
 
     checked = 0
