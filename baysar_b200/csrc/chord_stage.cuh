@@ -671,7 +671,9 @@ __global__ void __launch_bounds__(NT, MINB) chord_stage_kernel(ModelDev m, Chord
           for (int k = 0; k < 4; ++k)
             if (j + k >= F) v[k] = 0.f;
         }
-        *ap = make_float4(v[0], v[1], v[2], v[3]);
+        // the spectrum stays in shared memory only if something reads it there: an earlier or later pass, the in-kernel
+        // convolution, the fine-grid diagnostic; the folded path's single fused pass hands it over from registers
+        if (!(MODE == 1 && final_pass && !a_dirty && a.skip_edge64 && a.fine_pre == nullptr)) *ap = make_float4(v[0], v[1], v[2], v[3]);
         if (final_pass) {  // pre-convolution area / minimum (spectrometers.py:256, :271) and MODE 1 hand-over
           const float s4 = (v[0] + v[1]) + (v[2] + v[3]);
           pre_f += s4;
