@@ -28,6 +28,7 @@ Under torchrun (N > 1) every rank evaluates its own shard and the per-walker log
 NCCL inside the timed region, as an ensemble-sampler step needs.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -366,12 +367,17 @@ def run_workload(env, name, batch, steps, warmup, sync_gather=False, scaling="we
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     torch.cuda.synchronize()
+    # no interpreter garbage collection inside the timed loop: a pause of one rank's host thread stalls that rank's
+    # launches and, through the all-gather, every rank's next step (seen as single 10-15 ms steps among 4 ms ones)
+    gc.collect()
+    gc.disable()
     t_wall0 = time.time()
     for k in range(steps):
         env.flush.fill_(float(k))  # evict L2 between timed steps (untimed)
         starts[k].record()
         step(warmup + k)
         ends[k].record()
+    gc.enable()
     tail0, tail1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tail0.record()
     sharded.wait()      # outstanding overlapped all-gathers
@@ -399,6 +405,10 @@ def run_workload(env, name, batch, steps, warmup, sync_gather=False, scaling="we
         dist.barrier()
     launches = post.model.launches_last_eval
     step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
+    if os.environ.get("BAYSAR_BENCH_RANK_STATS"):  # diagnostics: every rank's slowest steps
+        worst = np.argsort(step_ms)[-3:]
+        print(f"[rank {rank}] {name} steps {steps}: median {np.median(step_ms):.4f} ms, slowest "
+              + ", ".join(f"#{i} {step_ms[i]:.3f}" for i in worst), file=sys.stderr, flush=True)
     total_ms = torch.tensor([float(step_ms.sum()) + float(tail0.elapsed_time(tail1))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -417,6 +427,8 @@ def run_workload(env, name, batch, steps, warmup, sync_gather=False, scaling="we
         if world > 1:
             dist.barrier()
         t_e2e = 0.0
+        gc.collect()
+        gc.disable()
         for k in range(e2e_steps):
             pinned.copy_(torch.from_numpy(thetas_host[(warmup + k) % total_steps]))
             env.flush.fill_(float(k))
@@ -424,6 +436,7 @@ def run_workload(env, name, batch, steps, warmup, sync_gather=False, scaling="we
             t0 = time.perf_counter()
             post(pinned.numpy())  # numpy in, numpy out: copies happen inside baysar_eval_logp_host
             t_e2e += time.perf_counter() - t0
+        gc.enable()
         t_e2e_t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t_e2e_t, op=dist.ReduceOp.MAX)
