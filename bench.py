@@ -362,15 +362,16 @@ def run_workload(env, name, batch, steps, warmup, sync_gather=False, scaling="we
     for i in range(warmup):
         step(i)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-    torch.cuda.synchronize()
     # no interpreter garbage collection inside the timed loop: a pause of one rank's host thread stalls that rank's
-    # launches and, through the all-gather, every rank's next step (seen as single 10-15 ms steps among 4 ms ones)
+    # launches and, through the all-gather, every rank's next step.  Collected BEFORE the barrier: rank 0 holds the larger
+    # heap (oracle, parity arrays), and a rank that enters the timed loop late makes every other rank's gathers wait for it
     gc.collect()
     gc.disable()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t_wall0 = time.time()
     for k in range(steps):
         env.flush.fill_(float(k))  # evict L2 between timed steps (untimed)
